@@ -1,0 +1,274 @@
+/*
+ * mgpu.h -- C ABI of the B200-native full-text query hot path.
+ *
+ * Drop-in boundary for Manticore Search 3.6.0's local-index search
+ * (CSphIndex_VLN::MultiQuery, src/sphinx.cpp:15362; the seam is ParsedMultiQuery,
+ * src/sphinx.cpp:15664-15943: sphCreateRanker + MatchExtended fill the caller's sorters).
+ *
+ * Every entry point below names the reference interface it replaces.  Plain C types only:
+ * no C++ classes, no torch types, no exceptions cross this boundary.  There is NO CPU
+ * fallback behind these calls: an operator or option the CUDA path does not implement
+ * returns MGPU_E_UNSUPPORTED; a missing GPU returns MGPU_E_NO_DEVICE.
+ */
+#ifndef MGPU_H_
+#define MGPU_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGPU_ABI_VERSION 1
+
+/* ---- status codes (reference: bool return + tMeta.m_sError, src/sphinx.cpp:15690) ---- */
+enum {
+	MGPU_OK = 0,
+	MGPU_E_IO = -1,           /* index files missing / unreadable */
+	MGPU_E_FORMAT = -2,       /* not an index-format v54..v62 plain index, or hitless/unsupported settings */
+	MGPU_E_UNSUPPORTED = -3,  /* query uses an operator/ranker/sort the CUDA path does not implement */
+	MGPU_E_BAD_QUERY = -4,    /* malformed tree (reference: sphCreateRanker returns nullptr, sphinxsearch.cpp:4377) */
+	MGPU_E_NO_DEVICE = -5,    /* no CUDA device; the product never falls back to the CPU */
+	MGPU_E_CUDA = -6,         /* CUDA runtime error, see mgpu_last_error() */
+	MGPU_E_NOMEM = -7
+};
+
+/* ---- XQOperator_e (src/sphinxquery.h:43-62); only the listed values are accepted ---- */
+enum {
+	MGPU_OP_AND = 0,        /* SPH_QUERY_AND */
+	MGPU_OP_OR = 1,         /* SPH_QUERY_OR */
+	MGPU_OP_MAYBE = 2,      /* SPH_QUERY_MAYBE */
+	MGPU_OP_NOT = 3,        /* SPH_QUERY_NOT (must have been fixed up to ANDNOT by the parser) */
+	MGPU_OP_ANDNOT = 4,     /* SPH_QUERY_ANDNOT */
+	MGPU_OP_BEFORE = 5,
+	MGPU_OP_PHRASE = 6,     /* SPH_QUERY_PHRASE */
+	MGPU_OP_PROXIMITY = 7,  /* SPH_QUERY_PROXIMITY, oparg = N of "..."~N */
+	MGPU_OP_QUORUM = 8,
+	MGPU_OP_NEAR = 9
+};
+
+/* ---- ESphRankMode (src/sphinx.h:2388-2404) ---- */
+enum {
+	MGPU_RANK_PROXIMITY_BM25 = 0,
+	MGPU_RANK_BM25 = 1,
+	MGPU_RANK_NONE = 2,
+	MGPU_RANK_WORDCOUNT = 3
+};
+
+/* ---- sort key parts: ESphSortKeyPart (src/sortsetup.h:19-57) ---- */
+enum {
+	MGPU_KEYPART_ROWID = 0,
+	MGPU_KEYPART_WEIGHT = 1,
+	MGPU_KEYPART_INT = 2      /* fixed-width integer row attribute (<=32 bits on the GPU path) */
+};
+
+/* ---- filters: the integer subset of ISphFilter::Eval (src/sphinxfilter.h:51) ---- */
+enum {
+	MGPU_FILTER_RANGE = 0,    /* min <= attr <= max  (SPH_FILTER_RANGE, closed bounds) */
+	MGPU_FILTER_VALUES = 1    /* attr IN (values)    (SPH_FILTER_VALUES) */
+};
+
+/* XQKeyword_t (src/sphinxquery.h:21-39) */
+typedef struct mgpu_xqkeyword {
+	const char *	word;        /* m_sWord, dictionary form (tokenised, lower-cased by the caller's tokenizer) */
+	int32_t			atom_pos;    /* m_iAtomPos, 1-based in-query position */
+	float			boost;       /* m_fBoost (1.0f default) */
+	uint8_t			field_start; /* m_bFieldStart  -> MGPU_E_UNSUPPORTED for now */
+	uint8_t			field_end;   /* m_bFieldEnd    -> MGPU_E_UNSUPPORTED for now */
+	uint8_t			excluded;    /* m_bExcluded */
+	uint8_t			expanded;    /* m_bExpanded */
+} mgpu_xqkeyword;
+
+/* XQNode_t (src/sphinxquery.h:134-280), flattened: children and words are index ranges */
+typedef struct mgpu_xqnode {
+	int32_t			op;            /* MGPU_OP_* */
+	int32_t			oparg;         /* m_iOpArg */
+	int32_t			first_child;   /* index into mgpu_query.children[] */
+	int32_t			n_children;
+	int32_t			first_word;    /* index into mgpu_query.words[] */
+	int32_t			n_words;
+	uint32_t		field_mask;    /* XQLimitSpec_t::m_dFieldMask, fields 0..31; 0xFFFFFFFF = all */
+	int32_t			field_max_pos; /* XQLimitSpec_t::m_iFieldMaxPos; nonzero -> MGPU_E_UNSUPPORTED */
+	uint8_t			not_weighted;  /* m_bNotWeighted */
+	uint8_t			pad[3];
+} mgpu_xqnode;
+
+/* one key of CSphMatchComparatorState (src/sortsetup.h:19-57) */
+typedef struct mgpu_sortkey {
+	int32_t			kind;          /* MGPU_KEYPART_* */
+	int32_t			attr;          /* attribute index in the index schema (MGPU_KEYPART_INT) */
+	int32_t			desc;          /* bit of m_uAttrDesc */
+} mgpu_sortkey;
+
+/* CSphFilterSettings subset (src/sphinx.h:2249-2320) */
+typedef struct mgpu_filter {
+	int32_t			kind;          /* MGPU_FILTER_* */
+	int32_t			attr;          /* attribute index in the index schema */
+	int64_t			min_value;     /* RANGE */
+	int64_t			max_value;     /* RANGE */
+	const int64_t *	values;        /* VALUES */
+	int32_t			n_values;
+	int32_t			exclude;       /* m_bExclude */
+} mgpu_filter;
+
+/* CSphQuery subset (src/sphinx.h:2586-2691) + CSphMultiQueryArgs (src/sphinx.h:2909-2925) */
+typedef struct mgpu_query {
+	const mgpu_xqnode *		nodes;
+	int32_t					n_nodes;
+	int32_t					root;           /* XQQuery_t::m_pRoot */
+	const int32_t *			children;       /* flattened child index lists */
+	int32_t					n_children;
+	const mgpu_xqkeyword *	words;
+	int32_t					n_words;
+
+	int32_t					ranker;         /* m_eRanker, MGPU_RANK_* */
+	const int32_t *			field_weights;  /* CSphQueryContext::m_dWeights after BindWeights (sphinx.cpp:13903); NULL = all 1 */
+	int32_t					n_field_weights;
+
+	const mgpu_sortkey *	sort_keys;      /* NULL/0 = SPH_SORT_RELEVANCE (weight desc, rowid asc) */
+	int32_t					n_sort_keys;    /* <= 5; ties always broken by rowid asc (sphinxsort.cpp:4541-4790) */
+	const mgpu_filter *		filters;
+	int32_t					n_filters;
+
+	int32_t					max_matches;    /* m_iMaxMatches (default 1000) -- the sorter size, not LIMIT */
+	int32_t					index_weight;   /* iIndexWeight of MatchExtended (sphinx.cpp:12222); 0 -> 1 */
+	uint8_t					plain_idf;      /* m_bPlainIDF */
+	uint8_t					unnormalized_tfidf; /* !m_bNormalizedTFIDF */
+	uint8_t					pad[2];
+
+	/* CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs (global IDF inputs for sharded indexes) */
+	int64_t					total_docs;     /* 0 = use the index's own document count */
+	const int64_t *			word_docs;      /* per words[] entry; NULL or <0 entries = use local dictionary docs */
+} mgpu_query;
+
+/* per-keyword statistics: CSphQueryResultMeta::AddStat (src/sphinxsearch.cpp:4365-4371) */
+typedef struct mgpu_wordstat {
+	int64_t			docs;
+	int64_t			hits;
+} mgpu_wordstat;
+
+/* what ISphMatchSorter::Flatten would return (src/sphinxsort.cpp:627-641), caller-allocated */
+typedef struct mgpu_result {
+	int32_t			status;         /* MGPU_OK or error for this query (reference: m_iMultiplier=-1) */
+	int32_t			n_matches;      /* <= max_matches */
+	int64_t			total_found;    /* ISphMatchSorter::GetTotalCount() */
+	uint32_t *		rowid;          /* [max_matches] best first */
+	int32_t *		weight;         /* [max_matches] */
+	int64_t *		docid;          /* [max_matches] the `id` attribute of the row; may be NULL */
+	int64_t *		sort_attr;      /* [max_matches] value of the first INT sort key; may be NULL */
+	mgpu_wordstat *	word_stats;     /* [n_words], per words[] entry; may be NULL */
+} mgpu_result;
+
+typedef struct mgpu_index mgpu_index;
+
+/* ------------------------------------------------------------------------------------- */
+/* index lifetime: replaces CSphIndex_VLN::Prealloc/Preread (src/sphinx.cpp:13782) for the files the
+ * query path needs (.sph .spi .spd .spp .spe .spa .spm).  `device` = CUDA ordinal.
+ * `rowid_base` = global rowid of local row 0 (contiguous rowid-range shards); only
+ * used when packing multi-GPU merge keys. */
+int				mgpu_index_open ( const char * path_prefix, int device, uint32_t rowid_base, mgpu_index ** out );
+void			mgpu_index_close ( mgpu_index * idx );
+const char *	mgpu_last_error ( const mgpu_index * idx );   /* idx may be NULL: last open error */
+
+/* index facts (CSphIndex::GetStats, schema), for callers building queries */
+int64_t			mgpu_index_total_docs ( const mgpu_index * idx );
+int32_t			mgpu_index_num_fields ( const mgpu_index * idx );
+int32_t			mgpu_index_field_index ( const mgpu_index * idx, const char * name );   /* CSphSchema::GetFieldIndex */
+int32_t			mgpu_index_attr_index ( const mgpu_index * idx, const char * name );    /* CSphSchema::GetAttrIndex */
+/* dictionary lookup: DiskIndexQwordSetup_c::Setup (src/sphinx.cpp:12950-13078). returns 1 if found */
+int				mgpu_index_word_stats ( const mgpu_index * idx, const char * word, int64_t * docs, int64_t * hits );
+/* algorithmic bytes of a word on this index: .spd extent incl. terminator + .spe extent */
+int				mgpu_index_word_bytes ( const mgpu_index * idx, const char * word, int64_t * doclist_bytes, int64_t * skiplist_bytes );
+
+/* ------------------------------------------------------------------------------------- */
+/* the hot path: replaces sphCreateRanker + MatchExtended + ISphMatchSorter::Push/Flatten
+ * (src/sphinxsearch.cpp:4167, src/sphinx.cpp:12190, src/sphinxsort.cpp:582-812) for a batch of
+ * parsed queries against one local index.  Host buffers in, host buffers out; thread-safe on a
+ * shared handle (calls are serialised per index).  Returns MGPU_OK if the batch ran; per-query
+ * status in results[i].status. */
+int				mgpu_search_batch ( mgpu_index * idx, const mgpu_query * queries, int n_queries, mgpu_result * results );
+
+/* Same, but the timed region can exclude host<->device copies: prepare uploads the batch plan,
+ * run launches the kernels on the resident plan (may be called repeatedly), fetch copies results
+ * back.  mgpu_search_batch == prepare + run + fetch + free. */
+typedef struct mgpu_batch mgpu_batch;
+int				mgpu_batch_prepare ( mgpu_index * idx, const mgpu_query * queries, int n_queries, mgpu_batch ** out );
+int				mgpu_batch_run ( mgpu_batch * b );            /* asynchronous on the index stream */
+int				mgpu_batch_sync ( mgpu_batch * b );
+int				mgpu_batch_fetch ( mgpu_batch * b, mgpu_result * results );
+void			mgpu_batch_free ( mgpu_batch * b );
+/* counters of the last run: kernels launched, work items, algorithmic bytes, postings */
+typedef struct mgpu_batch_stats {
+	int64_t			kernel_launches;
+	int64_t			work_items;
+	int64_t			algorithmic_bytes;   /* sum over queries of B(q) */
+	int64_t			postings;            /* sum over queries of sum_t df(t) */
+	int64_t			h2d_bytes;
+	int64_t			d2h_bytes;
+	float			eval_kernel_ms;      /* CUDA-event time of the fused eval kernel in the last run */
+	float			merge_kernel_ms;
+} mgpu_batch_stats;
+int				mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out );
+
+/* ------------------------------------------------------------------------------------- */
+/* distributed-local merge: replaces MergeAllMatches/KillPlainDupes for disjoint rowid-range shards
+ * (src/searchd.cpp:3910-3952, 4653-4738).  Each shard exports, per query, its K best packed
+ * 128-bit keys {hi = sort key, lo = ~global_rowid:32 | weight:32} to DEVICE memory (for an NCCL
+ * all-gather by the caller); the merge kernel selects the global K best. */
+int				mgpu_batch_export_keys ( mgpu_batch * b, void * dev_keys /* [nq][K][2] u64 */, void * dev_counts /* [nq] i32 */, void * dev_total_found /* [nq] i64 */, int K );
+int				mgpu_merge_shard_keys ( int device, const void * dev_keys /* [n_shards][nq][K][2] u64 */, const void * dev_counts /* [n_shards][nq] i32 */,
+					int n_shards, int nq, int K, void * dev_out_keys /* [nq][K][2] u64 */, void * dev_out_counts /* [nq] i32 */, void * stream );
+/* unpack merged keys on the host side: rowid (global), weight */
+void			mgpu_unpack_key ( const uint64_t key[2], uint32_t * global_rowid, int32_t * weight, uint64_t * sortkey_hi );
+
+/* ------------------------------------------------------------------------------------- */
+/* standalone doclist decode (kernel K1): decodes every posting of `word` into caller DEVICE or HOST
+ * arrays; used by the parity tests of the VByte block decoder against the oracle's
+ * DiskIndexQword_c::ReadNext restatement (src/sphinx.cpp:511-549). host arrays sized docs. */
+int				mgpu_decode_doclist ( mgpu_index * idx, const char * word, uint32_t * rowid, uint32_t * hits, uint32_t * fields, uint64_t * hitlist_pos, int64_t capacity, int64_t * n_out );
+
+/* ------------------------------------------------------------------------------------- */
+/* index writer (format v62): the byte layout of CSphHitBuilder::cidxHit/cidxDone + IndexWriteHeader +
+ * CSphDictKeywords (src/sphinx.cpp:8297-8936, 19374-19700).  Host-only; SURVEY 8(f) rank 1. */
+typedef struct mgpu_build_doc_input {
+	int32_t			n_docs;
+	int32_t			n_fields;
+	const char * const * field_names;
+	int32_t			n_attrs;          /* uint32 attributes besides `id` */
+	const char * const * attr_names;
+	const int64_t *	docids;           /* [n_docs] ascending */
+	const uint32_t *attrs;            /* [n_docs][n_attrs] */
+	int32_t			n_keywords;
+	const char * const * keywords;    /* dictionary forms */
+	const int64_t *	field_tok_offsets;/* [n_docs*n_fields+1] into tok_* */
+	const int32_t *	tok_keyword;      /* keyword index */
+	const int32_t *	tok_pos;          /* 1-based position inside the field (gaps allowed) */
+	int32_t			skiplist_block;   /* 0 -> 32 */
+	int32_t			hit_format_inline;/* 1 = inline (default), 0 = plain */
+} mgpu_build_doc_input;
+int				mgpu_build_index ( const char * path_prefix, const mgpu_build_doc_input * in, char * err, int errlen );
+
+/* synthetic Zipfian corpus: docs [first_doc, first_doc+n_docs) of the seeded corpus are
+ * written as a self-contained index with local rowids from 0 (a contiguous rowid-range shard). */
+typedef struct mgpu_synth_params {
+	uint64_t		seed;
+	int64_t			first_doc;
+	int64_t			n_docs;
+	int32_t			vocab;            /* number of distinct terms, Zipf(s=1) */
+	int32_t			title_min, title_max;
+	int32_t			body_min, body_max;
+	float			body_mu, body_sigma; /* lognormal */
+	int32_t			threads;          /* 0 = all */
+} mgpu_synth_params;
+int				mgpu_build_synthetic ( const char * path_prefix, const mgpu_synth_params * p, char * err, int errlen );
+/* token at (doc, field, pos0) of the synthetic corpus, and field length; lets query generators sample phrases */
+int32_t			mgpu_synth_field_len ( const mgpu_synth_params * p, int64_t doc, int field );
+int32_t			mgpu_synth_token ( const mgpu_synth_params * p, int64_t doc, int field, int pos0 );
+
+int				mgpu_abi_version ( void );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGPU_H_ */

@@ -1,0 +1,79 @@
+"""Builds libmgpu.so (hand-written sm_100a kernels + C++ host + C ABI) in-tree with nvcc.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmgpu.so")
+
+CUDA_SOURCES = ["cuda/kernels.cu"]
+HOST_SOURCES = ["host/index_format.cpp", "host/index_writer.cpp", "host/engine.cpp", "host/api.cpp"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",            # TF*IDF arithmetic must match the reference's scalar fp32
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-ffp-contract=off",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES]
+
+
+def _deps():
+    deps = list(_sources())
+    for root, _, files in os.walk(CSRC):
+        deps += [os.path.join(root, f) for f in files if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(HERE, "..", "include", "mgpu.h"))
+    return deps
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu" if src.endswith(".cu") else "c++", "-c", src, "-o", obj]
+        if not src.endswith(".cu"):
+            # host files only need cuda_runtime.h; compile them as plain C++ through nvcc's host compiler
+            cmd = [nvcc] + NVCC_FLAGS + ["-x", "c++", "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s" % src)
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

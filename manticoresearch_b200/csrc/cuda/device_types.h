@@ -1,0 +1,194 @@
+// Plain structs shared between the host planner (engine.cpp) and the sm_100a kernels (kernels.cu).
+// HBM layout of an index (see DESIGN.md "Data layout in HBM"):
+//   spd / spp / spa : the reference's own .spd/.spp/.spa bytes, uploaded verbatim (16 B zero padding after each)
+//   block table     : every term's skiplist decoded once at open (+ the implicit entry 0 and the trailing
+//                     partial block the reference's reader drops, src/sphinx.cpp:13056-13073), 20 B per 32 docs
+#pragma once
+
+#include <stdint.h>
+
+namespace mgpu
+{
+
+static const int TILE_W = 2048;			///< rowids per dense tile
+static const int EVAL_THREADS = 256;
+static const int EVAL_WARPS = EVAL_THREADS/32;
+static const int MAX_STACK = 4;			///< doc-vector stack depth of the tile program
+static const int MAX_LEAVES = 16;		///< term leaves per query on the GPU path
+static const int MAX_OPS = 48;
+static const int MAX_FILTERS = 4;
+static const int MAX_FILTER_VALUES = 16;
+static const int MAX_FIELDS = 32;
+static const int STAGE_BYTES = 896;		///< per-warp staging: 15 B alignment head + 32 docs * (5+5+5+10) B, rounded up to a multiple of 128
+static const int MAX_PHRASE_WORDS = 16;	///< FSM state bound on the GPU path
+static const int MAX_NWAY = 4;			///< phrase/proximity nodes per query
+
+struct DevIndex_t
+{
+	const uint8_t *		m_pSpd;
+	const uint8_t *		m_pSpp;
+	const uint32_t *	m_pSpa;
+	const uint32_t *	m_pDead;		///< dead-row bitmap (.spm) or null
+	const uint32_t *	m_pBlkRowid;	///< SkiplistEntry_t::m_tBaseRowIDPlus1 per block
+	const uint64_t *	m_pBlkOff;		///< SkiplistEntry_t::m_iOffset
+	const uint64_t *	m_pBlkHitpos;	///< SkiplistEntry_t::m_iBaseHitlistPos
+	int64_t				m_iSpdLen;
+	int64_t				m_iSppLen;
+	uint32_t			m_uRows;
+	int32_t				m_iStride;		///< .spa row stride in DWORDs
+	int32_t				m_bInlineHits;
+	uint32_t			m_uRowidBase;	///< global rowid of local row 0 (shards)
+};
+
+/// one query keyword occurrence = ExtTerm_T / ExtMultiAnd_T::NodeInfo_t
+struct DevLeaf_t
+{
+	uint64_t	m_uDoclistEnd;		///< offset of the doclist's terminating zero byte
+	uint32_t	m_uFirstBlk;		///< index into the block table
+	uint32_t	m_nBlocks;
+	uint32_t	m_nDocs;
+	uint32_t	m_uQueriedFields;	///< XQLimitSpec_t field mask (fields 0..31)
+	float		m_fIDF;
+	uint16_t	m_uAtomPos;
+	uint16_t	m_uNodePos;
+};
+
+enum DevOpCode_e : uint8_t
+{
+	OP_TERM_SET = 0,	///< v[dst] = leaf
+	OP_TERM_AND,		///< v[dst] &= leaf      (ExtAnd_c / ExtMultiAnd_T step: tfidf += , fields |=)
+	OP_TERM_OR,			///< v[dst] |= leaf      (ExtOr_c)
+	OP_TERM_ANDNOT,		///< v[dst] -= leaf      (ExtAndNot_c)
+	OP_TERM_MAYBE,		///< v[dst] ?= leaf      (ExtMaybe_c)
+	OP_VEC_AND,			///< v[dst] &= v[src]
+	OP_VEC_OR,
+	OP_VEC_ANDNOT,
+	OP_VEC_MAYBE,
+	OP_NWAY				///< v[dst] = FSM filter (phrase/proximity) over the hits of v[dst]'s leaves; arg = nway index
+};
+
+struct DevOp_t
+{
+	uint8_t		m_eCode;
+	uint8_t		m_uDst;
+	uint8_t		m_uSrc;
+	uint8_t		m_uAliveDst;	///< value of cnt[] meaning "alive" in v[dst] BEFORE the op
+	uint8_t		m_uAliveSrc;	///< same for v[src]
+	uint8_t		m_uLeaf;
+	uint8_t		m_uArg;
+	uint8_t		m_uAliveOut;	///< alive value of v[dst] AFTER the op
+};
+
+struct DevFilter_t
+{
+	int64_t		m_iMin, m_iMax;
+	int64_t		m_dValues[MAX_FILTER_VALUES];
+	int32_t		m_nValues;
+	int32_t		m_eKind;
+	int32_t		m_iDwordOff;	///< attribute locator: DWORD offset in the row
+	int32_t		m_iBitCount;	///< 32 or 64
+	int32_t		m_bExclude;
+	int32_t		m_iPad;
+};
+
+struct DevSortKey_t
+{
+	int32_t		m_eKind;
+	int32_t		m_iDwordOff;
+	int32_t		m_iBitCount;
+	int32_t		m_bDesc;
+	int32_t		m_iShift;		///< position of the key's low bit inside the 64-bit packed sort key
+};
+
+/// phrase / proximity node: ExtNWay_T<FSMphrase_c|FSMproximity_c>
+struct DevNWay_t
+{
+	int32_t		m_bProximity;
+	int32_t		m_iOpArg;					///< "..."~N
+	int32_t		m_nWords;
+	int32_t		m_dLeaf[MAX_PHRASE_WORDS];	///< leaves in query (atom pos) order
+	int32_t		m_dAtomPos[MAX_PHRASE_WORDS];
+};
+
+struct DevQuery_t
+{
+	DevLeaf_t	m_dLeaves[MAX_LEAVES];
+	DevOp_t		m_dOps[MAX_OPS];
+	DevFilter_t	m_dFilters[MAX_FILTERS];
+	DevSortKey_t m_dSortKeys[5];
+	DevNWay_t	m_dNWay[MAX_NWAY];
+	int32_t		m_dWeights[MAX_FIELDS];	///< bound field weights
+	int32_t		m_nLeaves;
+	int32_t		m_nOps;
+	int32_t		m_nFilters;
+	int32_t		m_nSortKeys;			///< 0 = relevance
+	int32_t		m_nNWay;
+	int32_t		m_nWeights;				///< CSphQueryContext::m_iWeights = min(fields, 32) here
+	int32_t		m_eRanker;
+	int32_t		m_iIndexWeight;
+	int32_t		m_iMaxMatches;
+	int32_t		m_uAliveRoot;			///< alive value of v[0] after the last op
+	int32_t		m_bNeedHits;			///< ranker consumes hits (PROXIMITY_BM25 multi-word, WORDCOUNT) or tree has phrase/proximity
+	int32_t		m_bDupes;				///< HasQwordDupes: RankerState_Proximity_fn<*,true>
+	int32_t		m_iFirstItem;			///< first work item of this query
+	int32_t		m_nItems;
+	int32_t		m_iPad[2];
+};
+
+/// 128-bit match key: hi = packed sort keys (bigger = better), lo = ~rowid:32 | weight:32
+struct Key128_t
+{
+	uint64_t	m_uHi;
+	uint64_t	m_uLo;
+};
+
+struct DevWorkItem_t
+{
+	uint32_t	m_uQuery;
+	uint32_t	m_uRowLo;		///< rowid range [lo, hi) this item evaluates
+	uint32_t	m_uRowHi;
+	uint32_t	m_uPad;
+};
+
+struct DevItemOut_t
+{
+	int64_t		m_iTotalFound;
+	int32_t		m_nKeys;
+	int32_t		m_iPad;
+};
+
+struct EvalParams_t
+{
+	DevIndex_t				m_tIndex;
+	const DevQuery_t *		m_pQueries;
+	const DevWorkItem_t *	m_pItems;
+	int32_t					m_nItems;
+	int32_t					m_iPoolCap;		///< keys per pool buffer (per CTA, two buffers)
+	Key128_t *				m_pPool;		///< [gridDim.x][2][m_iPoolCap]
+	Key128_t *				m_pItemKeys;	///< [m_nItems][m_iKMax]
+	DevItemOut_t *			m_pItemOut;		///< [m_nItems]
+	int32_t *				m_pCounter;		///< work-queue head
+	int32_t					m_iKMax;		///< stride of m_pItemKeys
+	int32_t					m_iPad;
+};
+
+struct MergeParams_t
+{
+	DevIndex_t				m_tIndex;
+	const DevQuery_t *		m_pQueries;
+	int32_t					m_nQueries;
+	int32_t					m_iKMax;
+	const Key128_t *		m_pItemKeys;
+	const DevItemOut_t *	m_pItemOut;
+	Key128_t *				m_pScratch;		///< [nQueries][m_iScratchStride]
+	int32_t					m_iScratchStride;
+	int32_t					m_iPad;
+	const int32_t *			m_pOutSlot;		///< device query -> output slot (the caller's query index)
+	// outputs, [nSlots][m_iKMax]
+	Key128_t *				m_pOutKeys;
+	int64_t *				m_pOutDocid;
+	int32_t *				m_pOutCount;	///< [nSlots]
+	int64_t *				m_pOutTotal;	///< [nSlots]
+};
+
+} // namespace mgpu

@@ -1,0 +1,949 @@
+// sm_100a kernels of the full-text query hot path.
+//
+//   K1  decode_block()       warp-per-skiplist-block VByte doclist decoder
+//                            (DiskIndexQword_c::ReadNext, src/sphinx.cpp:511-549; sphUnzipInt src/fileio.cpp:31-45)
+//   K2/K3/K6/K7/K8  eval_kernel()  one persistent CTA per work item = (query, rowid range):
+//                            decode -> dense-tile boolean evaluation (ExtMultiAnd/ExtAnd/ExtOr/ExtAndNot/ExtMaybe,
+//                            src/searchnode.cpp:2570-3711) -> BM25 weight (src/sphinxsearch.cpp:1070, 1096-1141)
+//                            -> filters (src/sphinx.cpp:11903) -> threshold-pruned candidate pool + CTA radix select
+//                            (CSphMatchQueue semantics, src/sphinxsort.cpp:722-761)
+//   K8b merge_kernel()       per query: select + bitonic sort of the work items' candidates, best first
+//   K9  shard_merge_kernel() disjoint-rowid-range shard merge (MergeAllMatches, src/searchd.cpp:4653-4738)
+//
+// All of this is HBM-bound integer/byte work; no tensor cores by design.  Float math uses the
+// round-to-nearest intrinsics explicitly (and the file is built with -fmad=false) so that TF*IDF sums
+// are bit-identical to the reference's scalar fp32 code.
+#include "device_types.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgpu
+{
+
+#define FULL_MASK 0xffffffffu
+
+//////////////////////////////////////////////////////////////////////////
+// small helpers
+//////////////////////////////////////////////////////////////////////////
+
+__device__ __forceinline__ uint4 LdNc16 ( const uint8_t * p )
+{
+	return __ldg ( reinterpret_cast<const uint4 *>( p ) );
+}
+
+__device__ __forceinline__ int WarpInclusiveScan ( int v, int iLane )
+{
+	#pragma unroll
+	for ( int d=1; d<32; d<<=1 )
+	{
+		int n = __shfl_up_sync ( FULL_MASK, v, d );
+		if ( iLane>=d )
+			v += n;
+	}
+	return v;
+}
+
+__device__ __forceinline__ uint32_t WarpInclusiveScanU32 ( uint32_t v, int iLane )
+{
+	#pragma unroll
+	for ( int d=1; d<32; d<<=1 )
+	{
+		uint32_t n = __shfl_up_sync ( FULL_MASK, v, d );
+		if ( iLane>=d )
+			v += n;
+	}
+	return v;
+}
+
+__device__ __forceinline__ uint64_t WarpInclusiveScanU64 ( uint64_t v, int iLane )
+{
+	#pragma unroll
+	for ( int d=1; d<32; d<<=1 )
+	{
+		uint64_t n = __shfl_up_sync ( FULL_MASK, v, d );
+		if ( iLane>=d )
+			v += n;
+	}
+	return v;
+}
+
+__device__ __forceinline__ bool KeyLess ( const Key128_t & a, const Key128_t & b )
+{
+	return a.m_uHi<b.m_uHi || ( a.m_uHi==b.m_uHi && a.m_uLo<b.m_uLo );
+}
+
+/// first index in [uFrom,n) with a[idx]>=x (n if none). Warp-cooperative: a few forward 32-wide probes
+/// (consecutive tiles move forward by a handful of blocks), then a uniform binary search.
+__device__ uint32_t WarpLowerBound ( const uint32_t * __restrict__ a, uint32_t uFrom, uint32_t n, uint32_t x, int iLane )
+{
+	uint32_t uPos = uFrom;
+	#pragma unroll 1
+	for ( int it=0; it<3; ++it )
+	{
+		uint32_t i = uPos+iLane;
+		bool bGe = ( i>=n ) || ( __ldg ( a+i )>=x );
+		unsigned m = __ballot_sync ( FULL_MASK, bGe );
+		if ( m )
+		{
+			uint32_t r = uPos + __ffs ( m ) - 1;
+			return r<n ? r : n;
+		}
+		uPos += 32;
+	}
+	uint32_t lo = uPos, hi = n;
+	while ( lo<hi )
+	{
+		uint32_t mid = lo + ( ( hi-lo )>>1 );
+		if ( __ldg ( a+mid )>=x ) hi = mid; else lo = mid+1;
+	}
+	return lo;
+}
+
+//////////////////////////////////////////////////////////////////////////
+// K1: warp-cooperative doclist block decoder
+//////////////////////////////////////////////////////////////////////////
+
+struct DecodedDoc_t
+{
+	uint32_t	m_uRowid;
+	uint32_t	m_uHits;
+	uint32_t	m_uFields;
+	uint64_t	m_uHitlistPos;
+	bool		m_bValid;
+};
+
+/// Decodes block uBlk (<=32 docs) of a leaf's doclist. One doc per lane.
+/// pStage: STAGE_BYTES of warp-private shared memory (16 B aligned); pRecStart: 34 x u16.
+/// A doclist record is exactly 4 varints (src/sphinx.cpp:8425-8497), so record d starts right after the
+/// (4d)-th varint terminator byte of the block: terminators are found with a ballot-free word scan
+/// (popc + warp prefix sum), record starts are scattered to shared memory, then each lane decodes its
+/// own 4 varints and two warp scans rebuild rowids and hitlist offsets from their deltas.
+template<bool NEED_HITPOS>
+__device__ __forceinline__ void DecodeBlock ( const DevIndex_t & tIdx, const DevLeaf_t & tLeaf, uint32_t uBlk,
+	uint8_t * pStage, uint16_t * pRecStart, int iLane, DecodedDoc_t & tOut )
+{
+	const uint32_t uGlobalBlk = tLeaf.m_uFirstBlk + uBlk;
+	const bool bLast = ( uBlk+1>=tLeaf.m_nBlocks );
+	const uint64_t uOff0 = __ldg ( tIdx.m_pBlkOff+uGlobalBlk );
+	const uint64_t uOff1 = bLast ? tLeaf.m_uDoclistEnd : __ldg ( tIdx.m_pBlkOff+uGlobalBlk+1 );
+	const int nDocs = bLast ? (int)( tLeaf.m_nDocs - 32u*uBlk ) : 32;
+	const uint32_t uBaseRowid = __ldg ( tIdx.m_pBlkRowid+uGlobalBlk );
+
+	// stage the block's bytes: 128-bit coalesced loads from a 16 B aligned start
+	const uint64_t uAligned = uOff0 & ~15ull;
+	const int iHead = (int)( uOff0-uAligned );
+	int iTotal = iHead + (int)( uOff1-uOff0 );
+	if ( iTotal>STAGE_BYTES )
+		iTotal = STAGE_BYTES;	// cannot happen for well-formed 32-doc blocks (<=800 B); guards corrupt input
+	for ( int c=iLane; c*16<iTotal; c+=32 )
+		*reinterpret_cast<uint4 *>( pStage+16*c ) = LdNc16 ( tIdx.m_pSpd+uAligned+16*c );
+	if ( iLane==0 )
+		pRecStart[0] = (uint16_t)iHead;
+	__syncwarp();
+
+	// find record starts
+	int iCarry = 0;
+	for ( int iBase=0; iBase<iTotal; iBase+=128 )
+	{
+		const int iPos = iBase + iLane*4;
+		uint32_t w = *reinterpret_cast<const uint32_t *>( pStage+iPos );
+		uint32_t t = ( ~w>>7 ) & 0x01010101u;
+		// keep only bytes inside [iHead, iTotal)
+		int iLo = iHead-iPos, iHi = iTotal-iPos;
+		uint32_t m = 0x01010101u;
+		if ( iLo>0 )
+			m = iLo>=4 ? 0u : ( m & ~( ( 1u<<( 8*iLo ) )-1u ) );
+		if ( iHi<4 )
+			m = iHi<=0 ? 0u : ( m & ( ( 1u<<( 8*iHi ) )-1u ) );
+		t &= m;
+		const int c = __popc ( t );
+		const int iIncl = WarpInclusiveScan ( c, iLane );
+		int iRun = iIncl-c+iCarry;
+		#pragma unroll
+		for ( int j=0; j<4; ++j )
+			if ( ( t>>( 8*j ) ) & 1u )
+			{
+				if ( ( iRun & 3 )==3 && ( iRun>>2 )<32 )
+					pRecStart[( iRun>>2 )+1] = (uint16_t)( iPos+j+1 );
+				++iRun;
+			}
+		iCarry += __shfl_sync ( FULL_MASK, iIncl, 31 );
+	}
+	__syncwarp();
+
+	// each lane decodes its record
+	const bool bValid = iLane<nDocs;
+	uint32_t v0 = 0, v1 = 0, v2 = 0;
+	uint64_t v3 = 0;
+	if ( bValid )
+	{
+		const uint8_t * p = pStage + pRecStart[iLane];
+		uint32_t b;
+		do { b = *p++; v0 = ( v0<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+		if ( tIdx.m_bInlineHits )
+		{
+			do { b = *p++; v1 = ( v1<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+			do { b = *p++; v2 = ( v2<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+			do { b = *p++; v3 = ( v3<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+		} else
+		{
+			// plain format: rowid delta, hitlist offset delta, field mask, hits (src/sphinx.cpp:539-545)
+			do { b = *p++; v3 = ( v3<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+			do { b = *p++; v2 = ( v2<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+			do { b = *p++; v1 = ( v1<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+		}
+	}
+	__syncwarp();	// staging buffer may be reused by the caller's next block
+
+	// rowid = (base-1) + prefix sum of deltas, mod 2^32 (reader starts at INVALID_ROWID for block 0)
+	tOut.m_uRowid = uBaseRowid - 1u + WarpInclusiveScanU32 ( v0, iLane );
+	tOut.m_uHits = v1;
+	tOut.m_bValid = bValid;
+
+	const bool bInlined = tIdx.m_bInlineHits && v1==1;
+	if ( bInlined )
+	{
+		// the only hit lives in the doclist: v2 = pos (23 bits), v3 = field<<1 | end (src/sphinx.cpp:523-530)
+		uint32_t uField = ( (uint32_t)v3>>1 ) & 255u;
+		tOut.m_uFields = uField<32 ? ( 1u<<uField ) : 0u;
+	} else
+		tOut.m_uFields = v2;
+
+	if ( NEED_HITPOS )
+	{
+		const uint64_t uBaseHitpos = __ldg ( tIdx.m_pBlkHitpos+uGlobalBlk );
+		uint64_t uDelta = ( bValid && !bInlined ) ? v3 : 0ull;
+		uint64_t uPos = uBaseHitpos + WarpInclusiveScanU64 ( uDelta, iLane );
+		tOut.m_uHitlistPos = bInlined ? ( (uint64_t)v2 | ( v3<<23 ) | ( 1ull<<63 ) ) : uPos;
+	} else
+		tOut.m_uHitlistPos = 0;
+}
+
+
+/// standalone decode of one doclist (parity tests of K1, and the decode-only roofline probe)
+__global__ void __launch_bounds__ ( EVAL_THREADS ) decode_doclist_kernel ( DevIndex_t tIdx, DevLeaf_t tLeaf,
+	uint32_t * pRowid, uint32_t * pHits, uint32_t * pFields, uint64_t * pHitlistPos, unsigned long long * pChecksum )
+{
+	__shared__ __align__(16) uint8_t dStage[EVAL_WARPS][STAGE_BYTES];
+	__shared__ uint16_t dRecStart[EVAL_WARPS][34];
+	const int iWarp = threadIdx.x>>5, iLane = threadIdx.x & 31;
+	unsigned long long uSum = 0;
+	for ( uint32_t b = blockIdx.x*EVAL_WARPS+iWarp; b<tLeaf.m_nBlocks; b += gridDim.x*EVAL_WARPS )
+	{
+		DecodedDoc_t d;
+		DecodeBlock<true> ( tIdx, tLeaf, b, dStage[iWarp], dRecStart[iWarp], iLane, d );
+		if ( d.m_bValid )
+		{
+			if ( pRowid )
+			{
+				size_t i = (size_t)b*32+iLane;
+				pRowid[i] = d.m_uRowid;
+				pHits[i] = d.m_uHits;
+				pFields[i] = d.m_uFields;
+				pHitlistPos[i] = d.m_uHitlistPos;
+			}
+			uSum += d.m_uRowid + d.m_uHits + d.m_uFields + d.m_uHitlistPos;
+		}
+	}
+	if ( pChecksum )
+	{
+		#pragma unroll
+		for ( int d=16; d; d>>=1 )
+			uSum += __shfl_xor_sync ( FULL_MASK, uSum, d );
+		if ( iLane==0 && uSum )
+			atomicAdd ( pChecksum, uSum );
+	}
+}
+
+//////////////////////////////////////////////////////////////////////////
+// CTA-wide exact top-K selection on 128-bit keys (MSB-first radix select)
+//////////////////////////////////////////////////////////////////////////
+
+struct SelectSmem_t
+{
+	uint32_t	m_dHist[256];
+	uint64_t	m_uPrefixHi, m_uPrefixLo;
+	int			m_iK;
+	int			m_iOut;
+};
+
+__device__ __forceinline__ bool MatchesPrefix ( const Key128_t & k, uint64_t uPHi, uint64_t uPLo, int iByte )
+{
+	// true if all bytes above iByte (15 = most significant of hi) equal the prefix
+	if ( iByte>=8 )
+	{
+		int s = 8*( iByte-8 )+8;
+		return s>=64 ? true : ( ( k.m_uHi>>s )==( uPHi>>s ) );
+	}
+	if ( k.m_uHi!=uPHi )
+		return false;
+	int s = 8*iByte+8;
+	return s>=64 ? true : ( ( k.m_uLo>>s )==( uPLo>>s ) );
+}
+
+__device__ __forceinline__ uint32_t KeyByte ( const Key128_t & k, int iByte )
+{
+	return iByte>=8 ? (uint32_t)( ( k.m_uHi>>( 8*( iByte-8 ) ) ) & 255u ) : (uint32_t)( ( k.m_uLo>>( 8*iByte ) ) & 255u );
+}
+
+/// Keeps the iK largest of pIn[0..n) (n>iK, keys distinct) in pOut[0..iK); returns the iK-th largest key.
+/// Must be called by all threads of the CTA.
+__device__ Key128_t CtaSelectTopK ( const Key128_t * pIn, int n, int iK, Key128_t * pOut, SelectSmem_t & s )
+{
+	const int tid = threadIdx.x, nThreads = blockDim.x;
+	if ( tid==0 )
+	{
+		s.m_uPrefixHi = 0; s.m_uPrefixLo = 0; s.m_iK = iK; s.m_iOut = 0;
+	}
+	__syncthreads();
+	for ( int iByte=15; iByte>=0; --iByte )
+	{
+		for ( int i=tid; i<256; i+=nThreads )
+			s.m_dHist[i] = 0;
+		__syncthreads();
+		const uint64_t uPHi = s.m_uPrefixHi, uPLo = s.m_uPrefixLo;
+		for ( int i=tid; i<n; i+=nThreads )
+		{
+			Key128_t k = pIn[i];
+			if ( MatchesPrefix ( k, uPHi, uPLo, iByte ) )
+				atomicAdd ( &s.m_dHist[KeyByte ( k, iByte )], 1u );
+		}
+		__syncthreads();
+		if ( tid<32 )
+		{
+			// warp 0 finds the digit holding the k-th largest: scan bins from 255 down, 8 bins per lane
+			int k = s.m_iK;
+			uint32_t uMine = 0;
+			#pragma unroll
+			for ( int j=0; j<8; ++j )
+				uMine += s.m_dHist[255-( tid*8+j )];
+			uint32_t uIncl = WarpInclusiveScanU32 ( uMine, tid );
+			unsigned m = __ballot_sync ( FULL_MASK, (int)uIncl>=k );
+			int iSel = __ffs ( m )-1;		// always found: the prefix bucket holds >= k keys
+			if ( tid==iSel )
+			{
+				int iCum = (int)( uIncl-uMine );
+				int d = 255-tid*8;
+				for ( int j=0; j<8; ++j, --d )
+				{
+					int c = (int)s.m_dHist[d];
+					if ( iCum+c>=k )
+						break;
+					iCum += c;
+				}
+				s.m_iK = k-iCum;
+				if ( iByte>=8 )
+					s.m_uPrefixHi |= (uint64_t)d<<( 8*( iByte-8 ) );
+				else
+					s.m_uPrefixLo |= (uint64_t)d<<( 8*iByte );
+			}
+		}
+		__syncthreads();
+	}
+	Key128_t tThr { s.m_uPrefixHi, s.m_uPrefixLo };
+	for ( int i=tid; i<n; i+=nThreads )
+	{
+		Key128_t k = pIn[i];
+		if ( !KeyLess ( k, tThr ) )
+		{
+			int o = atomicAdd ( &s.m_iOut, 1 );
+			if ( o<iK )
+				pOut[o] = k;
+		}
+	}
+	__syncthreads();
+	return tThr;
+}
+
+//////////////////////////////////////////////////////////////////////////
+// the fused evaluation kernel
+//////////////////////////////////////////////////////////////////////////
+
+struct EvalShared_t
+{
+	DevQuery_t		m_tQ;
+	SelectSmem_t	m_tSel;
+	uint32_t		m_dLeafB0[MAX_LEAVES];
+	uint32_t		m_dLeafB1[MAX_LEAVES];
+	uint32_t		m_dLeafCursor[MAX_LEAVES];
+	Key128_t		m_tThr;
+	unsigned long long m_uTotal;
+	int				m_iItem;
+	int				m_iPoolCnt;
+	int				m_iPoolBuf;
+	uint16_t		m_dRecStart[EVAL_WARPS][34];
+	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
+};
+
+/// dense doc vectors live in dynamic shared memory: [nStack] x { float tfidf[W]; u32 fields[W]; u8 cnt[W] }
+struct Vectors_t
+{
+	float *		m_pTfidf;
+	uint32_t *	m_pFields;
+	uint8_t *	m_pCnt;
+	__device__ __forceinline__ float &		Tfidf ( int v, int s )	{ return m_pTfidf[v*TILE_W+s]; }
+	__device__ __forceinline__ uint32_t &	Fields ( int v, int s )	{ return m_pFields[v*TILE_W+s]; }
+	__device__ __forceinline__ uint8_t &	Cnt ( int v, int s )	{ return m_pCnt[v*TILE_W+s]; }
+};
+
+__device__ __forceinline__ int64_t LoadAttr ( const DevIndex_t & tIdx, uint32_t uRowid, int iDwordOff, int iBitCount )
+{
+	const uint32_t * p = tIdx.m_pSpa + (size_t)uRowid*tIdx.m_iStride + iDwordOff;
+	uint32_t lo = __ldg ( p );
+	if ( iBitCount==64 )
+		return (int64_t)( (uint64_t)lo | ( (uint64_t)__ldg ( p+1 )<<32 ) );
+	return (int64_t)lo;
+}
+
+__device__ __forceinline__ bool PassFilters ( const DevIndex_t & tIdx, const DevQuery_t & q, uint32_t uRowid )
+{
+	for ( int f=0; f<q.m_nFilters; ++f )
+	{
+		const DevFilter_t & t = q.m_dFilters[f];
+		int64_t v = LoadAttr ( tIdx, uRowid, t.m_iDwordOff, t.m_iBitCount );
+		bool bOk;
+		if ( t.m_eKind==0 )
+			bOk = ( v>=t.m_iMin && v<=t.m_iMax );
+		else
+		{
+			bOk = false;
+			for ( int k=0; k<t.m_nValues; ++k )
+				bOk |= ( t.m_dValues[k]==v );
+		}
+		if ( t.m_bExclude )
+			bOk = !bOk;
+		if ( !bOk )
+			return false;
+	}
+	return true;
+}
+
+/// packs the sort keys of one match: bigger key = better match (CSphMatchComparatorState semantics)
+__device__ __forceinline__ Key128_t MakeKey ( const DevIndex_t & tIdx, const DevQuery_t & q, uint32_t uRowid, int iWeight )
+{
+	Key128_t k;
+	const uint32_t uW = (uint32_t)iWeight ^ 0x80000000u;
+	if ( q.m_nSortKeys==0 )
+		k.m_uHi = (uint64_t)uW<<32;	// MatchRelevanceLt_fn
+	else
+	{
+		uint64_t uHi = 0;
+		for ( int i=0; i<q.m_nSortKeys; ++i )
+		{
+			const DevSortKey_t & t = q.m_dSortKeys[i];
+			uint64_t v;
+			int iBits = 32;
+			if ( t.m_eKind==1 )			v = uW;
+			else if ( t.m_eKind==0 )	v = uRowid + tIdx.m_uRowidBase;
+			else
+			{
+				int64_t a = LoadAttr ( tIdx, uRowid, t.m_iDwordOff, t.m_iBitCount );
+				if ( t.m_iBitCount==64 ) { v = (uint64_t)a ^ 0x8000000000000000ull; iBits = 64; }
+				else v = (uint64_t)a;
+			}
+			if ( !t.m_bDesc )
+				v = iBits==64 ? ~v : ( ~v & 0xffffffffull );
+			uHi |= v<<t.m_iShift;
+		}
+		k.m_uHi = uHi;
+	}
+	k.m_uLo = ( (uint64_t)( ~( uRowid+tIdx.m_uRowidBase ) )<<32 ) | (uint32_t)iWeight;
+	return k;
+}
+
+__global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P, int nStack )
+{
+	extern __shared__ __align__(16) uint8_t dDyn[];
+	__shared__ EvalShared_t S;
+
+	Vectors_t V;
+	V.m_pTfidf = reinterpret_cast<float *>( dDyn );
+	V.m_pFields = reinterpret_cast<uint32_t *>( dDyn + (size_t)nStack*TILE_W*4 );
+	V.m_pCnt = dDyn + (size_t)nStack*TILE_W*8;
+
+	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
+	const DevIndex_t & tIdx = P.m_tIndex;
+	Key128_t * pPool0 = P.m_pPool + (size_t)blockIdx.x*2*P.m_iPoolCap;
+
+	while ( true )
+	{
+		__syncthreads();
+		if ( tid==0 )
+			S.m_iItem = atomicAdd ( P.m_pCounter, 1 );
+		__syncthreads();
+		const int iItem = S.m_iItem;
+		if ( iItem>=P.m_nItems )
+			break;
+		const DevWorkItem_t tItem = P.m_pItems[iItem];
+
+		// stage the query descriptor
+		{
+			const uint32_t * pSrc = reinterpret_cast<const uint32_t *>( P.m_pQueries+tItem.m_uQuery );
+			uint32_t * pDst = reinterpret_cast<uint32_t *>( &S.m_tQ );
+			for ( int i=tid; i<(int)( sizeof(DevQuery_t)/4 ); i+=EVAL_THREADS )
+				pDst[i] = pSrc[i];
+		}
+		if ( tid==0 )
+		{
+			S.m_iPoolCnt = 0;
+			S.m_iPoolBuf = 0;
+			S.m_tThr.m_uHi = 0; S.m_tThr.m_uLo = 0;
+			S.m_uTotal = 0;
+		}
+		if ( tid<MAX_LEAVES )
+			S.m_dLeafCursor[tid] = 0;
+		__syncthreads();
+		const DevQuery_t & q = S.m_tQ;
+		const int iK = q.m_iMaxMatches;
+		int iMyTotal = 0;
+
+		for ( uint32_t uTileLo=tItem.m_uRowLo; uTileLo<tItem.m_uRowHi; uTileLo+=TILE_W )
+		{
+			const uint32_t uTileHi = min ( uTileLo+(uint32_t)TILE_W, tItem.m_uRowHi );
+
+			// compact the candidate pool if this tile could overflow it
+			if ( S.m_iPoolCnt+TILE_W>P.m_iPoolCap )
+			{
+				Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+				Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
+				Key128_t tThr = CtaSelectTopK ( pIn, S.m_iPoolCnt, iK, pOut, S.m_tSel );
+				if ( tid==0 )
+				{
+					S.m_tThr = tThr;
+					S.m_iPoolCnt = iK;
+					S.m_iPoolBuf ^= 1;
+				}
+				__syncthreads();
+			}
+
+			// block range of every leaf inside this tile
+			for ( int l=iWarp; l<q.m_nLeaves; l+=EVAL_WARPS )
+			{
+				const DevLeaf_t & tLeaf = q.m_dLeaves[l];
+				uint32_t b0 = 0, b1 = 0;
+				if ( tLeaf.m_nBlocks )
+				{
+					const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
+					// b0 = last block whose base <= tile lo; b1 = first block whose base >= tile hi
+					uint32_t u = WarpLowerBound ( pBase, S.m_dLeafCursor[l], tLeaf.m_nBlocks, uTileLo+1, iLane );
+					b0 = u ? u-1 : 0;
+					b1 = WarpLowerBound ( pBase, u, tLeaf.m_nBlocks, uTileHi, iLane );
+				}
+				if ( iLane==0 )
+				{
+					S.m_dLeafB0[l] = b0;
+					S.m_dLeafB1[l] = b1;
+					S.m_dLeafCursor[l] = b1 ? b1-1 : 0;
+				}
+			}
+			__syncthreads();
+
+			// run the tile program
+			for ( int iOp=0; iOp<q.m_nOps; ++iOp )
+			{
+				const DevOp_t tOp = q.m_dOps[iOp];
+				const int d = tOp.m_uDst;
+				if ( tOp.m_eCode==OP_TERM_SET )
+				{
+					uint32_t * pCnt32 = reinterpret_cast<uint32_t *>( &V.Cnt ( d, 0 ) );
+					for ( int i=tid; i<TILE_W/4; i+=EVAL_THREADS )
+						pCnt32[i] = 0;
+					__syncthreads();
+				}
+				if ( tOp.m_eCode<=OP_TERM_MAYBE )
+				{
+					const DevLeaf_t & tLeaf = q.m_dLeaves[tOp.m_uLeaf];
+					const uint32_t b1 = S.m_dLeafB1[tOp.m_uLeaf];
+					const uint8_t uAlive = tOp.m_uAliveDst;
+					for ( uint32_t b=S.m_dLeafB0[tOp.m_uLeaf]+iWarp; b<b1; b+=EVAL_WARPS )
+					{
+						DecodedDoc_t tDoc;
+						DecodeBlock<false> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
+						const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
+						if ( !tDoc.m_bValid || tDoc.m_uRowid<uTileLo || tDoc.m_uRowid>=uTileHi || !uFields )
+							continue;
+						const int s = (int)( tDoc.m_uRowid-uTileLo );
+						// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946
+						const float fHits = __uint2float_rn ( tDoc.m_uHits );
+						const float fTf = __fmul_rn ( __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
+						switch ( tOp.m_eCode )
+						{
+						case OP_TERM_SET:
+							V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = 1;
+							break;
+						case OP_TERM_AND:
+							if ( V.Cnt ( d, s )==uAlive )
+							{
+								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
+								V.Fields ( d, s ) |= uFields;
+								V.Cnt ( d, s ) = tOp.m_uAliveOut;
+							}
+							break;
+						case OP_TERM_OR:
+							if ( V.Cnt ( d, s )==uAlive )
+							{
+								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
+								V.Fields ( d, s ) |= uFields;
+							} else
+							{
+								V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = uAlive;
+							}
+							break;
+						case OP_TERM_ANDNOT:
+							if ( V.Cnt ( d, s )==uAlive )
+								V.Cnt ( d, s ) = 0;
+							break;
+						default: // OP_TERM_MAYBE
+							if ( V.Cnt ( d, s )==uAlive )
+							{
+								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
+								V.Fields ( d, s ) |= uFields;
+							}
+							break;
+						}
+					}
+				} else
+				{
+					const int r = tOp.m_uSrc;
+					const uint8_t uAd = tOp.m_uAliveDst, uAs = tOp.m_uAliveSrc;
+					for ( int s=tid; s<TILE_W; s+=EVAL_THREADS )
+					{
+						const bool bD = V.Cnt ( d, s )==uAd, bS = V.Cnt ( r, s )==uAs;
+						switch ( tOp.m_eCode )
+						{
+						case OP_VEC_AND:
+							if ( bD && bS )
+							{
+								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), V.Tfidf ( r, s ) );
+								V.Fields ( d, s ) |= V.Fields ( r, s );
+							} else if ( bD )
+								V.Cnt ( d, s ) = 0;
+							break;
+						case OP_VEC_OR:
+							if ( bD && bS )
+							{
+								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), V.Tfidf ( r, s ) );
+								V.Fields ( d, s ) |= V.Fields ( r, s );
+							} else if ( bS )
+							{
+								V.Tfidf ( d, s ) = V.Tfidf ( r, s ); V.Fields ( d, s ) = V.Fields ( r, s ); V.Cnt ( d, s ) = uAd;
+							}
+							break;
+						case OP_VEC_ANDNOT:
+							if ( bD && bS )
+								V.Cnt ( d, s ) = 0;
+							break;
+						case OP_VEC_MAYBE:
+							if ( bD && bS )
+							{
+								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), V.Tfidf ( r, s ) );
+								V.Fields ( d, s ) |= V.Fields ( r, s );
+							}
+							break;
+						default:
+							break;
+						}
+					}
+				}
+				__syncthreads();
+			}
+
+			// rank + filter + push survivors of this tile
+			{
+				const uint8_t uAlive = (uint8_t)q.m_uAliveRoot;
+				const Key128_t tThr = S.m_tThr;
+				Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+				const int nSlots = (int)( uTileHi-uTileLo );
+				for ( int sBase=0; sBase<nSlots; sBase+=EVAL_THREADS )
+				{
+					const int s = sBase+tid;
+					bool bPush = false;
+					Key128_t tKey;
+					if ( s<nSlots && V.Cnt ( 0, s )==uAlive )
+					{
+						const uint32_t uRowid = uTileLo+s;
+						bool bOk = PassFilters ( tIdx, q, uRowid );
+						if ( bOk && tIdx.m_pDead )
+							bOk = !( ( __ldg ( tIdx.m_pDead+( uRowid>>5 ) )>>( uRowid & 31 ) ) & 1u );
+						if ( bOk )
+						{
+							int iWeight;
+							if ( q.m_eRanker==2 )
+								iWeight = 1;	// ExtRanker_None_c, src/sphinxsearch.cpp:1160
+							else
+							{
+								// seed weight src/sphinxsearch.cpp:1070, ExtRanker_WeightSum_c :1112-1129
+								int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( V.Tfidf ( 0, s ), 0.5f ), 1000.0f ) );
+								uint32_t uMask = V.Fields ( 0, s );
+								uint32_t uRank = 0;
+								if ( !uMask )
+									uRank = 1;
+								else
+									for ( int i=0; i<q.m_nWeights; ++i )
+										if ( uMask & ( 1u<<i ) )
+											uRank += (uint32_t)q.m_dWeights[i];
+								iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+							}
+							iWeight *= q.m_iIndexWeight;
+							++iMyTotal;
+							tKey = MakeKey ( tIdx, q, uRowid, iWeight );
+							bPush = !KeyLess ( tKey, tThr );
+						}
+					}
+					const unsigned m = __ballot_sync ( FULL_MASK, bPush );
+					if ( m )
+					{
+						int iBase = 0;
+						if ( iLane==0 )
+							iBase = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
+						iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
+						if ( bPush )
+							pPool[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+					}
+				}
+			}
+			__syncthreads();
+		}
+
+		// item epilogue: final selection, publish keys + counters
+		if ( S.m_iPoolCnt>iK )
+		{
+			Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+			Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
+			CtaSelectTopK ( pIn, S.m_iPoolCnt, iK, pOut, S.m_tSel );
+			if ( tid==0 )
+			{
+				S.m_iPoolCnt = iK;
+				S.m_iPoolBuf ^= 1;
+			}
+			__syncthreads();
+		}
+		{
+			#pragma unroll
+			for ( int d=16; d; d>>=1 )
+				iMyTotal += __shfl_xor_sync ( FULL_MASK, iMyTotal, d );
+			if ( iLane==0 && iMyTotal )
+				atomicAdd ( &S.m_uTotal, (unsigned long long)iMyTotal );
+			__syncthreads();
+			const Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+			Key128_t * pDst = P.m_pItemKeys + (size_t)iItem*P.m_iKMax;
+			const int n = S.m_iPoolCnt;
+			for ( int i=tid; i<n; i+=EVAL_THREADS )
+				pDst[i] = pPool[i];
+			if ( tid==0 )
+			{
+				P.m_pItemOut[iItem].m_iTotalFound = (int64_t)S.m_uTotal;
+				P.m_pItemOut[iItem].m_nKeys = n;
+			}
+		}
+	}
+}
+
+//////////////////////////////////////////////////////////////////////////
+// per-query merge of the work items' candidates: select K, sort best first
+//////////////////////////////////////////////////////////////////////////
+
+__device__ void CtaBitonicSortDesc ( Key128_t * p, int n /* power of two */ )
+{
+	const int tid = threadIdx.x, nThreads = blockDim.x;
+	for ( int k=2; k<=n; k<<=1 )
+		for ( int j=k>>1; j>0; j>>=1 )
+		{
+			for ( int i=tid; i<n; i+=nThreads )
+			{
+				int l = i ^ j;
+				if ( l>i )
+				{
+					Key128_t a = p[i], b = p[l];
+					bool bDesc = ( i & k )==0;
+					if ( bDesc ? KeyLess ( a, b ) : KeyLess ( b, a ) )
+					{
+						p[i] = b; p[l] = a;
+					}
+				}
+			}
+			__syncthreads();
+		}
+}
+
+__global__ void __launch_bounds__ ( 256 ) merge_kernel ( MergeParams_t P )
+{
+	__shared__ SelectSmem_t tSel;
+	__shared__ int iTotalKeys;
+	__shared__ unsigned long long uTotalFound;
+	const int tid = threadIdx.x;
+
+	for ( int iQuery=blockIdx.x; iQuery<P.m_nQueries; iQuery+=gridDim.x )
+	{
+		const DevQuery_t & q = P.m_pQueries[iQuery];
+		const int iK = q.m_iMaxMatches;
+		Key128_t * pA = P.m_pScratch + (size_t)iQuery*P.m_iScratchStride;	// [0, stride/2) gather, [stride/2, stride) select output
+		const int iHalf = P.m_iScratchStride/2;
+		Key128_t * pB = pA+iHalf;
+
+		if ( tid==0 )
+		{
+			iTotalKeys = 0;
+			uTotalFound = 0;
+		}
+		__syncthreads();
+		// gather
+		for ( int it=0; it<q.m_nItems; ++it )
+		{
+			const int iItem = q.m_iFirstItem+it;
+			const int n = P.m_pItemOut[iItem].m_nKeys;
+			const int iBase = iTotalKeys;
+			const Key128_t * pSrc = P.m_pItemKeys + (size_t)iItem*P.m_iKMax;
+			for ( int i=tid; i<n; i+=blockDim.x )
+				pA[iBase+i] = pSrc[i];
+			__syncthreads();
+			if ( tid==0 )
+			{
+				iTotalKeys = iBase+n;
+				uTotalFound += (unsigned long long)P.m_pItemOut[iItem].m_iTotalFound;
+			}
+			__syncthreads();
+		}
+		int n = iTotalKeys;
+		Key128_t * pCur = pA;
+		if ( n>iK )
+		{
+			CtaSelectTopK ( pA, n, iK, pB, tSel );
+			n = iK;
+			pCur = pB;
+		}
+		int nPad = 1;
+		while ( nPad<n )
+			nPad <<= 1;
+		for ( int i=n+tid; i<nPad; i+=blockDim.x )
+		{
+			pCur[i].m_uHi = 0; pCur[i].m_uLo = 0;
+		}
+		__syncthreads();
+		CtaBitonicSortDesc ( pCur, nPad );
+
+		const int iSlot = P.m_pOutSlot[iQuery];
+		Key128_t * pOut = P.m_pOutKeys + (size_t)iSlot*P.m_iKMax;
+		int64_t * pDocid = P.m_pOutDocid + (size_t)iSlot*P.m_iKMax;
+		for ( int i=tid; i<n; i+=blockDim.x )
+		{
+			Key128_t k = pCur[i];
+			pOut[i] = k;
+			uint32_t uRowid = ~(uint32_t)( k.m_uLo>>32 ) - P.m_tIndex.m_uRowidBase;
+			const uint32_t * pRow = P.m_tIndex.m_pSpa + (size_t)uRowid*P.m_tIndex.m_iStride;
+			pDocid[i] = (int64_t)( (uint64_t)pRow[0] | ( (uint64_t)pRow[1]<<32 ) );	// `id` is always attribute 0, bigint
+		}
+		if ( tid==0 )
+		{
+			P.m_pOutCount[iSlot] = n;
+			P.m_pOutTotal[iSlot] = (int64_t)uTotalFound;
+		}
+		__syncthreads();
+	}
+}
+
+//////////////////////////////////////////////////////////////////////////
+// K9: merge of per-shard top-K key lists (disjoint rowid ranges => no dedupe, src/searchd.cpp:3910-3952)
+//////////////////////////////////////////////////////////////////////////
+
+__global__ void __launch_bounds__ ( 256 ) shard_merge_kernel ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
+	Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts )
+{
+	__shared__ SelectSmem_t tSel;
+	__shared__ int iTotalKeys;
+	const int tid = threadIdx.x;
+	for ( int iQuery=blockIdx.x; iQuery<nQueries; iQuery+=gridDim.x )
+	{
+		Key128_t * pA = pScratch + (size_t)iQuery*iScratchStride;
+		Key128_t * pB = pA + iScratchStride/2;
+		if ( tid==0 )
+			iTotalKeys = 0;
+		__syncthreads();
+		for ( int s=0; s<nShards; ++s )
+		{
+			const int n = min ( pCounts[(size_t)s*nQueries+iQuery], iK );
+			const int iBase = iTotalKeys;
+			const Key128_t * pSrc = pKeys + ( (size_t)s*nQueries+iQuery )*iK;
+			for ( int i=tid; i<n; i+=blockDim.x )
+				pA[iBase+i] = pSrc[i];
+			__syncthreads();
+			if ( tid==0 )
+				iTotalKeys = iBase+n;
+			__syncthreads();
+		}
+		int n = iTotalKeys;
+		Key128_t * pCur = pA;
+		if ( n>iK )
+		{
+			CtaSelectTopK ( pA, n, iK, pB, tSel );
+			n = iK;
+			pCur = pB;
+		}
+		int nPad = 1;
+		while ( nPad<n )
+			nPad <<= 1;
+		for ( int i=n+tid; i<nPad; i+=blockDim.x )
+		{
+			pCur[i].m_uHi = 0; pCur[i].m_uLo = 0;
+		}
+		__syncthreads();
+		CtaBitonicSortDesc ( pCur, nPad );
+		for ( int i=tid; i<n; i+=blockDim.x )
+			pOutKeys[(size_t)iQuery*iK+i] = pCur[i];
+		if ( tid==0 )
+			pOutCounts[iQuery] = n;
+		__syncthreads();
+	}
+}
+
+//////////////////////////////////////////////////////////////////////////
+// host-callable launchers (engine.cpp is plain C++ and never sees <<< >>>)
+//////////////////////////////////////////////////////////////////////////
+
+size_t EvalDynSmemBytes ( int nStack )
+{
+	return (size_t)nStack*TILE_W*9;
+}
+
+cudaError_t LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream )
+{
+	size_t iDyn = EvalDynSmemBytes ( nStack );
+	cudaError_t e = cudaFuncSetAttribute ( eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	if ( e!=cudaSuccess )
+		return e;
+	eval_kernel<<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
+	return cudaGetLastError();
+}
+
+int EvalOccupancy ( int nStack )
+{
+	int n = 0;
+	size_t iDyn = EvalDynSmemBytes ( nStack );
+	cudaFuncSetAttribute ( eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel, EVAL_THREADS, iDyn )!=cudaSuccess )
+		return 1;
+	return n>0 ? n : 1;
+}
+
+cudaError_t LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream )
+{
+	merge_kernel<<<nCtas, 256, 0, tStream>>> ( P );
+	return cudaGetLastError();
+}
+
+cudaError_t LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
+	Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream )
+{
+	shard_merge_kernel<<<nCtas, 256, 0, tStream>>> ( pKeys, pCounts, nShards, nQueries, iK, pScratch, iScratchStride, pOutKeys, pOutCounts );
+	return cudaGetLastError();
+}
+
+cudaError_t LaunchDecodeDoclist ( const DevIndex_t & tIdx, const DevLeaf_t & tLeaf, uint32_t * pRowid, uint32_t * pHits, uint32_t * pFields,
+	uint64_t * pHitlistPos, unsigned long long * pChecksum, int nCtas, cudaStream_t tStream )
+{
+	decode_doclist_kernel<<<nCtas, EVAL_THREADS, 0, tStream>>> ( tIdx, tLeaf, pRowid, pHits, pFields, pHitlistPos, pChecksum );
+	return cudaGetLastError();
+}
+
+} // namespace mgpu

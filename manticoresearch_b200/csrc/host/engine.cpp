@@ -1,0 +1,960 @@
+// Index loader, query planner and batch executor of the GPU query engine. See engine.h.
+#include "engine.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace mgpu
+{
+
+#define CUDA_TRY(_expr,_err) \
+	do { cudaError_t _e = (_expr); if ( _e!=cudaSuccess ) { _err = std::string ( #_expr ": " ) + cudaGetErrorString ( _e ); return MGPU_E_CUDA; } } while (0)
+
+//////////////////////////////////////////////////////////////////////////
+// loader
+//////////////////////////////////////////////////////////////////////////
+
+namespace
+{
+
+struct MappedFile_t
+{
+	const BYTE * m_p = nullptr;
+	size_t m_iLen = 0;
+	bool Map ( const std::string & sPath )
+	{
+		int fd = open ( sPath.c_str(), O_RDONLY );
+		if ( fd<0 )
+			return false;
+		struct stat st;
+		if ( fstat ( fd, &st )<0 ) { close ( fd ); return false; }
+		m_iLen = (size_t)st.st_size;
+		if ( m_iLen )
+		{
+			void * p = mmap ( nullptr, m_iLen, PROT_READ, MAP_PRIVATE, fd, 0 );
+			if ( p==MAP_FAILED ) { close ( fd ); return false; }
+			m_p = (const BYTE *)p;
+		}
+		close ( fd );
+		return true;
+	}
+	~MappedFile_t() { if ( m_p ) munmap ( (void*)m_p, m_iLen ); }
+};
+
+template<typename T>
+int Upload ( DevBuf_T<T> & tDst, const void * pSrc, size_t nBytes, size_t nPadBytes, std::string & sError )
+{
+	size_t nElems = ( nBytes+nPadBytes+sizeof(T)-1 )/sizeof(T);
+	CUDA_TRY ( tDst.Alloc ( nElems ), sError );
+	CUDA_TRY ( cudaMemset ( tDst.m_p, 0, nElems*sizeof(T) ), sError );
+	if ( nBytes )
+		CUDA_TRY ( cudaMemcpy ( tDst.m_p, pSrc, nBytes, cudaMemcpyHostToDevice ), sError );
+	return MGPU_OK;
+}
+
+} // namespace
+
+
+Index_c::~Index_c()
+{
+	if ( m_tStream )
+	{
+		cudaSetDevice ( m_iDevice );
+		cudaStreamDestroy ( m_tStream );
+	}
+}
+
+int Index_c::AttrIndex ( const char * szName ) const
+{
+	for ( size_t i=0; i<m_tHdr.m_dAttrs.size(); ++i )
+		if ( m_tHdr.m_dAttrs[i].m_sName==szName )
+			return (int)i;
+	return -1;
+}
+
+int Index_c::FieldIndex ( const char * szName ) const
+{
+	for ( size_t i=0; i<m_tHdr.m_dFields.size(); ++i )
+		if ( m_tHdr.m_dFields[i].m_sName==szName )
+			return (int)i;
+	return -1;
+}
+
+int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
+{
+	const std::string sPrefix ( szPrefix );
+	m_iDevice = iDevice;
+	m_uRowidBase = uRowidBase;
+
+	// the product has no CPU path: fail loudly without a device
+	int nDevices = 0;
+	if ( cudaGetDeviceCount ( &nDevices )!=cudaSuccess || nDevices<=0 )
+	{
+		m_sError = "no CUDA device available (the GPU query path has no CPU fallback)";
+		return MGPU_E_NO_DEVICE;
+	}
+	if ( iDevice<0 || iDevice>=nDevices )
+	{
+		m_sError = "CUDA device ordinal out of range";
+		return MGPU_E_NO_DEVICE;
+	}
+	CUDA_TRY ( cudaSetDevice ( iDevice ), m_sError );
+	cudaDeviceProp tProp;
+	CUDA_TRY ( cudaGetDeviceProperties ( &tProp, iDevice ), m_sError );
+	m_nSMs = tProp.multiProcessorCount;
+
+	MappedFile_t tSph, tSpi, tSpd, tSpp, tSpe, tSpa, tSpm;
+	if ( !tSph.Map ( sPrefix+".sph" ) || !tSpi.Map ( sPrefix+".spi" ) || !tSpd.Map ( sPrefix+".spd" )
+		|| !tSpp.Map ( sPrefix+".spp" ) || !tSpe.Map ( sPrefix+".spe" ) || !tSpa.Map ( sPrefix+".spa" ) )
+	{
+		m_sError = "failed to open index files at " + sPrefix + ".{sph,spi,spd,spp,spe,spa}";
+		return MGPU_E_IO;
+	}
+	tSpm.Map ( sPrefix+".spm" );
+
+	if ( !ReadHeader ( tSph.m_p, tSph.m_iLen, m_tHdr, m_sError ) )
+		return MGPU_E_FORMAT;
+	if ( m_tHdr.m_eHitless!=SPH_HITLESS_NONE )
+	{
+		m_sError = "hitless indexes are not supported";
+		return MGPU_E_FORMAT;
+	}
+	if ( m_tHdr.m_iSkiplistBlockSize!=32 )
+	{
+		m_sError = "skiplist_block_size must be 32 (one warp per skiplist block)";
+		return MGPU_E_FORMAT;
+	}
+	if ( m_tHdr.m_dFields.size()>MAX_FIELDS )
+	{
+		m_sError = "more than 32 full-text fields are not supported";
+		return MGPU_E_FORMAT;
+	}
+	if ( m_tHdr.m_iDocinfo>=(int64_t)0xFFFF0000u )
+	{
+		m_sError = "too many rows";
+		return MGPU_E_FORMAT;
+	}
+	const int iStride = m_tHdr.RowStride();
+	if ( (int64_t)tSpa.m_iLen<m_tHdr.m_iDocinfo*iStride*4 )
+	{
+		m_sError = ".spa is shorter than the header says";
+		return MGPU_E_FORMAT;
+	}
+
+	std::vector<DictEntry_t> dDict;
+	if ( !ReadDictionary ( tSpi.m_p, tSpi.m_iLen, m_tHdr, dDict, m_sError ) )
+		return MGPU_E_FORMAT;
+
+	// doclist extents: doclists are laid back to back in .spd, so the length is the distance to the next one
+	{
+		std::vector<size_t> dOrder ( dDict.size() );
+		for ( size_t i=0; i<dOrder.size(); ++i )
+			dOrder[i] = i;
+		std::sort ( dOrder.begin(), dOrder.end(), [&] ( size_t a, size_t b ) { return dDict[a].m_iDoclistOffset<dDict[b].m_iDoclistOffset; } );
+		for ( size_t k=0; k<dOrder.size(); ++k )
+		{
+			DictEntry_t & e = dDict[dOrder[k]];
+			int64_t iNext = k+1<dOrder.size() ? dDict[dOrder[k+1]].m_iDoclistOffset : (int64_t)tSpd.m_iLen;
+			e.m_iDoclistLength = iNext-e.m_iDoclistOffset;
+			if ( e.m_iDoclistOffset<=0 || e.m_iDoclistLength<=0 || iNext>(int64_t)tSpd.m_iLen )
+			{
+				m_sError = "dictionary entry points outside .spd";
+				return MGPU_E_FORMAT;
+			}
+		}
+	}
+
+	// decode every skiplist once into the flat block table (DiskIndexQwordSetup_c::Setup, src/sphinx.cpp:13056-13073,
+	// except that we keep the trailing partial block's entry, which the writer emits (:8447-8453) and the reader skips)
+	std::vector<uint32_t> dBlkRowid;
+	std::vector<uint64_t> dBlkOff, dBlkHitpos;
+	size_t nTotalBlocks = 0;
+	for ( const auto & e : dDict )
+		nTotalBlocks += ( (size_t)e.m_iDocs+31 )/32;
+	dBlkRowid.reserve ( nTotalBlocks );
+	dBlkOff.reserve ( nTotalBlocks );
+	dBlkHitpos.reserve ( nTotalBlocks );
+	m_hTerms.reserve ( dDict.size()*2 );
+	for ( const auto & e : dDict )
+	{
+		TermInfo_t t;
+		t.m_uFirstBlk = (uint32_t)dBlkRowid.size();
+		t.m_nBlocks = (uint32_t)( ( e.m_iDocs+31 )/32 );
+		t.m_iDocs = e.m_iDocs;
+		t.m_iHits = e.m_iHits;
+		t.m_iDoclistOffset = e.m_iDoclistOffset;
+		t.m_iDoclistLength = e.m_iDoclistLength;
+
+		uint32_t uRow = 0;
+		uint64_t uOff = (uint64_t)e.m_iDoclistOffset, uHit = 0;
+		dBlkRowid.push_back ( uRow ); dBlkOff.push_back ( uOff ); dBlkHitpos.push_back ( uHit );
+		if ( e.m_iDocs>32 )
+		{
+			if ( e.m_iSkiplistOffset<=0 || e.m_iSkiplistOffset>=(int64_t)tSpe.m_iLen )
+			{
+				m_sError = "skiplist offset outside .spe";
+				return MGPU_E_FORMAT;
+			}
+			ByteReader_t r ( tSpe.m_p+e.m_iSkiplistOffset, tSpe.m_iLen-e.m_iSkiplistOffset );
+			for ( uint32_t b=1; b<t.m_nBlocks; ++b )
+			{
+				uRow += 32 + (uint32_t)r.Unzip();
+				uOff += 4*32 + r.Unzip();
+				uHit += r.Unzip();
+				dBlkRowid.push_back ( uRow ); dBlkOff.push_back ( uOff ); dBlkHitpos.push_back ( uHit );
+			}
+			if ( r.m_bError || uOff>=(uint64_t)( e.m_iDoclistOffset+e.m_iDoclistLength ) )
+			{
+				m_sError = "corrupt skiplist for keyword " + e.m_sKeyword;
+				return MGPU_E_FORMAT;
+			}
+			t.m_iSkiplistBytes = (int64_t)( r.m_p-( tSpe.m_p+e.m_iSkiplistOffset ) );
+		}
+		m_hTerms.emplace ( e.m_sKeyword, t );
+	}
+
+	// upload
+	int iRes;
+	if ( ( iRes = Upload ( m_dSpd, tSpd.m_p, tSpd.m_iLen, 64, m_sError ) )!=MGPU_OK ) return iRes;
+	if ( ( iRes = Upload ( m_dSpp, tSpp.m_p, tSpp.m_iLen, 64, m_sError ) )!=MGPU_OK ) return iRes;
+	if ( ( iRes = Upload ( m_dSpa, tSpa.m_p, (size_t)m_tHdr.m_iDocinfo*iStride*4, 64, m_sError ) )!=MGPU_OK ) return iRes;
+	if ( ( iRes = Upload ( m_dBlkRowid, dBlkRowid.data(), dBlkRowid.size()*4, 256, m_sError ) )!=MGPU_OK ) return iRes;
+	if ( ( iRes = Upload ( m_dBlkOff, dBlkOff.data(), dBlkOff.size()*8, 64, m_sError ) )!=MGPU_OK ) return iRes;
+	if ( ( iRes = Upload ( m_dBlkHitpos, dBlkHitpos.data(), dBlkHitpos.size()*8, 64, m_sError ) )!=MGPU_OK ) return iRes;
+	bool bAnyDead = false;
+	for ( size_t i=0; i<tSpm.m_iLen && !bAnyDead; ++i )
+		bAnyDead = tSpm.m_p[i]!=0;
+	if ( bAnyDead )
+	{
+		std::vector<uint32_t> dDead ( (size_t)( m_tHdr.m_iDocinfo+31 )/32, 0 );
+		memcpy ( dDead.data(), tSpm.m_p, std::min ( tSpm.m_iLen, dDead.size()*4 ) );
+		if ( ( iRes = Upload ( m_dDead, dDead.data(), dDead.size()*4, 64, m_sError ) )!=MGPU_OK ) return iRes;
+	}
+
+	m_tDev.m_pSpd = m_dSpd.m_p;
+	m_tDev.m_pSpp = m_dSpp.m_p;
+	m_tDev.m_pSpa = m_dSpa.m_p;
+	m_tDev.m_pDead = m_dDead.m_p;
+	m_tDev.m_pBlkRowid = m_dBlkRowid.m_p;
+	m_tDev.m_pBlkOff = m_dBlkOff.m_p;
+	m_tDev.m_pBlkHitpos = m_dBlkHitpos.m_p;
+	m_tDev.m_iSpdLen = (int64_t)tSpd.m_iLen;
+	m_tDev.m_iSppLen = (int64_t)tSpp.m_iLen;
+	m_tDev.m_uRows = (uint32_t)m_tHdr.m_iDocinfo;
+	m_tDev.m_iStride = iStride;
+	m_tDev.m_bInlineHits = ( m_tHdr.m_eHitFormat==SPH_HIT_FORMAT_INLINE ) ? 1 : 0;
+	m_tDev.m_uRowidBase = uRowidBase;
+
+	CUDA_TRY ( cudaStreamCreateWithFlags ( &m_tStream, cudaStreamNonBlocking ), m_sError );
+	return MGPU_OK;
+}
+
+//////////////////////////////////////////////////////////////////////////
+// planner
+//////////////////////////////////////////////////////////////////////////
+
+namespace
+{
+
+// sphSort for <=33 elements is this (unstable) insertion sort, src/sphinxstd.h:853-866
+template<typename T, typename LESS>
+void RefSort ( std::vector<T> & d, LESS fnLess )
+{
+	for ( size_t i=1; i<d.size(); ++i )
+		for ( size_t j=i; j>0; --j )
+		{
+			if ( fnLess ( d[j-1], d[j] ) )
+				break;
+			std::swap ( d[j], d[j-1] );
+		}
+}
+
+enum { PN_TERM, PN_MULTIAND, PN_AND, PN_OR, PN_MAYBE, PN_ANDNOT, PN_NWAY };
+
+struct PLeaf_t
+{
+	int					m_iWord = 0;
+	const TermInfo_t *	m_pTerm = nullptr;
+	uint32_t			m_uFields = 0xFFFFFFFFu;
+	int					m_iAtomPos = 0;
+	int					m_iNodePos = 0;
+	bool				m_bNotWeighted = false;
+	bool				m_bOwnsIDF = false;		///< first occurrence of the word in eval-tree order
+	int					Docs() const { return m_pTerm ? m_pTerm->m_iDocs : 0; }
+};
+
+struct PNode_t
+{
+	int					m_eKind = PN_TERM;
+	int					m_iLeaf = -1;
+	std::vector<int>	m_dLeaves;		///< multi-AND: sorted order; n-way: chain order
+	int					m_iLeft = -1, m_iRight = -1;
+	int					m_iNWay = -1;
+};
+
+struct Planner_c
+{
+	const Index_c &		m_tIndex;
+	const mgpu_query &	m_q;
+	PlannedQuery_t &	m_tOut;
+	std::vector<PLeaf_t> m_dLeaves;
+	std::vector<PNode_t> m_dNodes;
+	int					m_iError = MGPU_OK;
+	int					m_iMaxSp = 0;
+
+	struct Qword_t { int m_iDocs; float m_fBoost; int m_iFirstWord; float m_fIDF; };
+	std::unordered_map<std::string,Qword_t> m_hQwords;
+
+	Planner_c ( const Index_c & tIndex, const mgpu_query & q, PlannedQuery_t & tOut ) : m_tIndex ( tIndex ), m_q ( q ), m_tOut ( tOut ) {}
+
+	int Fail ( int iErr )	{ if ( m_iError==MGPU_OK ) m_iError = iErr; return -1; }
+
+	int AddLeaf ( const mgpu_xqnode & tNode, int iWord, int iNodePos )
+	{
+		if ( iWord<0 || iWord>=m_q.n_words || !m_q.words[iWord].word )
+			return Fail ( MGPU_E_BAD_QUERY );
+		const mgpu_xqkeyword & tWord = m_q.words[iWord];
+		if ( tWord.field_start || tWord.field_end || tNode.field_max_pos )
+			return Fail ( MGPU_E_UNSUPPORTED );	// ExtTermPos_T filters are not on the GPU path yet
+		if ( (int)m_dLeaves.size()>=MAX_LEAVES )
+			return Fail ( MGPU_E_UNSUPPORTED );
+		PLeaf_t t;
+		t.m_iWord = iWord;
+		t.m_pTerm = m_tIndex.FindTerm ( tWord.word );
+		t.m_uFields = tNode.field_mask;
+		t.m_iAtomPos = tWord.atom_pos;
+		t.m_iNodePos = iNodePos;
+		t.m_bNotWeighted = tNode.not_weighted!=0;
+		m_dLeaves.push_back ( t );
+		return (int)m_dLeaves.size()-1;
+	}
+
+	int NewNode ( const PNode_t & t )	{ m_dNodes.push_back ( t ); return (int)m_dNodes.size()-1; }
+
+	/// ExtNode_i::Create, src/searchnode.cpp:1599-1811
+	int Create ( int iNode )
+	{
+		if ( iNode<0 || iNode>=m_q.n_nodes )
+			return Fail ( MGPU_E_BAD_QUERY );
+		const mgpu_xqnode & tNode = m_q.nodes[iNode];
+		if ( tNode.n_words )
+		{
+			if ( tNode.n_words==1 )
+			{
+				PNode_t t;
+				t.m_eKind = PN_TERM;
+				t.m_iLeaf = AddLeaf ( tNode, tNode.first_word, 0 );
+				return t.m_iLeaf<0 ? -1 : NewNode ( t );
+			}
+			if ( tNode.op!=MGPU_OP_PHRASE && tNode.op!=MGPU_OP_PROXIMITY )
+				return Fail ( MGPU_E_UNSUPPORTED );
+			return Fail ( MGPU_E_UNSUPPORTED );	// phrase/proximity: hit-stage kernel (K4/K5) not wired yet
+		}
+		const int nChildren = tNode.n_children;
+		if ( nChildren<1 )
+			return -1;
+		if ( tNode.first_child<0 || tNode.first_child+nChildren>m_q.n_children )
+			return Fail ( MGPU_E_BAD_QUERY );
+		const int32_t * pChildren = m_q.children + tNode.first_child;
+		for ( int i=0; i<nChildren; ++i )
+			if ( pChildren[i]<0 || pChildren[i]>=m_q.n_nodes )
+				return Fail ( MGPU_E_BAD_QUERY );
+
+		bool bAndTerms = ( tNode.op==MGPU_OP_AND );
+		for ( int i=0; i<nChildren && bAndTerms; ++i )
+			bAndTerms = ( m_q.nodes[pChildren[i]].n_words==1 );
+		if ( bAndTerms && nChildren>1 )
+		{
+			// ExtMultiAnd_T: children sorted by doc count (src/searchnode.cpp:2791)
+			PNode_t t;
+			t.m_eKind = PN_MULTIAND;
+			for ( int i=0; i<nChildren; ++i )
+			{
+				const mgpu_xqnode & tChild = m_q.nodes[pChildren[i]];
+				int iLeaf = AddLeaf ( tChild, tChild.first_word, i );
+				if ( iLeaf<0 )
+					return -1;
+				t.m_dLeaves.push_back ( iLeaf );
+			}
+			RefSort ( t.m_dLeaves, [this] ( int a, int b ) { return m_dLeaves[a].Docs()<m_dLeaves[b].Docs(); } );
+			return NewNode ( t );
+		}
+		if ( bAndTerms )
+			return Create ( pChildren[0] );
+
+		int iKind;
+		switch ( tNode.op )
+		{
+		case MGPU_OP_OR:		iKind = PN_OR; break;
+		case MGPU_OP_MAYBE:		iKind = PN_MAYBE; break;
+		case MGPU_OP_AND:		iKind = PN_AND; break;
+		case MGPU_OP_ANDNOT:	iKind = PN_ANDNOT; break;
+		default:				return Fail ( MGPU_E_UNSUPPORTED );
+		}
+		int iCur = -1;
+		for ( int i=0; i<nChildren; ++i )
+		{
+			int iNext = Create ( pChildren[i] );
+			if ( m_iError!=MGPU_OK )
+				return -1;
+			if ( iNext<0 ) continue;
+			if ( iCur<0 ) { iCur = iNext; continue; }
+			PNode_t t;
+			t.m_eKind = iKind;
+			t.m_iLeft = iCur;
+			t.m_iRight = iNext;
+			iCur = NewNode ( t );
+		}
+		return iCur;
+	}
+
+	/// ExtNode_i::GetQwords in eval-tree order (src/searchnode.cpp:2030-2057, 3244-3253, ExtTwofer_c)
+	void GetQwords ( int iNode )
+	{
+		const PNode_t & t = m_dNodes[iNode];
+		switch ( t.m_eKind )
+		{
+		case PN_TERM:		Register ( t.m_iLeaf ); break;
+		case PN_MULTIAND:
+		case PN_NWAY:		for ( int l : t.m_dLeaves ) Register ( l ); break;
+		default:			GetQwords ( t.m_iLeft ); GetQwords ( t.m_iRight ); break;
+		}
+	}
+
+	void Register ( int iLeaf )
+	{
+		PLeaf_t & l = m_dLeaves[iLeaf];
+		const mgpu_xqkeyword & w = m_q.words[l.m_iWord];
+		auto it = m_hQwords.find ( w.word );
+		if ( l.m_bNotWeighted || it!=m_hQwords.end() )
+			return;
+		l.m_bOwnsIDF = true;
+		m_hQwords.emplace ( w.word, Qword_t { l.Docs(), w.boost, l.m_iWord, 0.0f } );
+	}
+
+	/// emits the tile program; returns the alive value of v[iSp]
+	int Emit ( int iNode, int iSp )
+	{
+		if ( iSp>=MAX_STACK )
+		{
+			Fail ( MGPU_E_UNSUPPORTED );
+			return 1;
+		}
+		m_iMaxSp = std::max ( m_iMaxSp, iSp );
+		const PNode_t & t = m_dNodes[iNode];
+		switch ( t.m_eKind )
+		{
+		case PN_TERM:
+			AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_iLeaf, 1 );
+			return 1;
+		case PN_MULTIAND:
+			{
+				AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_dLeaves[0], 1 );
+				int iAlive = 1;
+				for ( size_t i=1; i<t.m_dLeaves.size(); ++i, ++iAlive )
+					AddOp ( OP_TERM_AND, iSp, 0, iAlive, 0, t.m_dLeaves[i], iAlive+1 );
+				return iAlive;
+			}
+		default:
+			{
+				int iAliveL = Emit ( t.m_iLeft, iSp );
+				const PNode_t & r = m_dNodes[t.m_iRight];
+				if ( r.m_eKind==PN_TERM )
+				{
+					switch ( t.m_eKind )
+					{
+					case PN_AND:	AddOp ( OP_TERM_AND, iSp, 0, iAliveL, 0, r.m_iLeaf, iAliveL+1 ); return iAliveL+1;
+					case PN_OR:		AddOp ( OP_TERM_OR, iSp, 0, iAliveL, 0, r.m_iLeaf, iAliveL ); return iAliveL;
+					case PN_MAYBE:	AddOp ( OP_TERM_MAYBE, iSp, 0, iAliveL, 0, r.m_iLeaf, iAliveL ); return iAliveL;
+					default:		AddOp ( OP_TERM_ANDNOT, iSp, 0, iAliveL, 0, r.m_iLeaf, iAliveL ); return iAliveL;
+					}
+				}
+				int iAliveR = Emit ( t.m_iRight, iSp+1 );
+				int eCode = t.m_eKind==PN_AND ? OP_VEC_AND : t.m_eKind==PN_OR ? OP_VEC_OR : t.m_eKind==PN_MAYBE ? OP_VEC_MAYBE : OP_VEC_ANDNOT;
+				AddOp ( eCode, iSp, iSp+1, iAliveL, iAliveR, 0, iAliveL );
+				return iAliveL;
+			}
+		}
+	}
+
+	void AddOp ( int eCode, int iDst, int iSrc, int iAliveDst, int iAliveSrc, int iLeaf, int iAliveOut )
+	{
+		if ( m_tOut.m_tDev.m_nOps>=MAX_OPS || iAliveOut>250 )
+		{
+			Fail ( MGPU_E_UNSUPPORTED );
+			return;
+		}
+		DevOp_t & o = m_tOut.m_tDev.m_dOps[m_tOut.m_tDev.m_nOps++];
+		o.m_eCode = (uint8_t)eCode;
+		o.m_uDst = (uint8_t)iDst;
+		o.m_uSrc = (uint8_t)iSrc;
+		o.m_uAliveDst = (uint8_t)iAliveDst;
+		o.m_uAliveSrc = (uint8_t)iAliveSrc;
+		o.m_uLeaf = (uint8_t)iLeaf;
+		o.m_uArg = 0;
+		o.m_uAliveOut = (uint8_t)iAliveOut;
+	}
+
+	int Run()
+	{
+		DevQuery_t & d = m_tOut.m_tDev;
+		memset ( &d, 0, sizeof(d) );
+		m_tOut.m_dWordStats.assign ( std::max ( m_q.n_words, 0 ), mgpu_wordstat { 0, 0 } );
+		for ( int i=0; i<m_q.n_words; ++i )
+			if ( m_q.words[i].word )
+				if ( const TermInfo_t * p = m_tIndex.FindTerm ( m_q.words[i].word ) )
+				{
+					m_tOut.m_dWordStats[i].docs = p->m_iDocs;
+					m_tOut.m_dWordStats[i].hits = p->m_iHits;
+				}
+
+		if ( m_q.ranker!=MGPU_RANK_BM25 && m_q.ranker!=MGPU_RANK_NONE && m_q.ranker!=MGPU_RANK_PROXIMITY_BM25 && m_q.ranker!=MGPU_RANK_WORDCOUNT )
+			return MGPU_E_UNSUPPORTED;
+
+		int iRoot = -1;
+		if ( m_q.n_nodes>0 && m_q.root>=0 )
+			iRoot = Create ( m_q.root );
+		if ( m_iError!=MGPU_OK )
+			return m_iError;
+
+		// ranker selection, sphCreateRanker src/sphinxsearch.cpp:4192-4226
+		bool bSingleWord = false;
+		if ( m_q.n_nodes>0 && m_q.root>=0 && m_q.root<m_q.n_nodes )
+			bSingleWord = ( m_q.nodes[m_q.root].n_words==1 && m_q.nodes[m_q.root].n_children==0 );
+		int eRanker = m_q.ranker;
+		if ( eRanker==MGPU_RANK_PROXIMITY_BM25 && bSingleWord )
+			eRanker = MGPU_RANK_BM25;	// ExtRanker_WeightSum_c<WITH_BM25>
+		if ( eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_WORDCOUNT )
+			return MGPU_E_UNSUPPORTED;	// hit-consuming rankers: stage 2 kernel
+		d.m_eRanker = eRanker;
+		const bool bUseBM25 = ( eRanker==MGPU_RANK_BM25 );
+
+		if ( iRoot>=0 )
+		{
+			GetQwords ( iRoot );
+			// IDF, src/sphinxsearch.cpp:4293-4361
+			const int iQwords = (int)m_hQwords.size();
+			const int64_t iTotalDocuments = m_q.total_docs>0 ? m_q.total_docs : (int64_t)m_tIndex.m_tHdr.m_iTotalDocuments;
+			for ( auto & kv : m_hQwords )
+			{
+				Qword_t & w = kv.second;
+				int64_t iTermDocs = w.m_iDocs;
+				if ( m_q.word_docs && m_q.word_docs[w.m_iFirstWord]>=0 )
+					iTermDocs = m_q.word_docs[w.m_iFirstWord];
+				float fIDF = 0.0f;
+				if ( iTermDocs )
+				{
+					const int64_t iTotalClamped = std::max ( iTotalDocuments, iTermDocs );
+					float fLogTotal = logf ( float ( 1+iTotalClamped ) );
+					if ( !m_q.plain_idf )
+						fIDF = logf ( float ( iTotalClamped-iTermDocs+1 ) / float ( iTermDocs ) ) / ( 2*fLogTotal );
+					else
+						fIDF = logf ( float ( iTotalClamped ) / float ( iTermDocs ) ) / ( 2*fLogTotal );
+				}
+				if ( !m_q.unnormalized_tfidf )
+					fIDF /= iQwords;
+				w.m_fIDF = fIDF * w.m_fBoost;
+			}
+
+			int iAlive = Emit ( iRoot, 0 );
+			if ( m_iError!=MGPU_OK )
+				return m_iError;
+			d.m_uAliveRoot = iAlive;
+		}
+
+		d.m_nLeaves = (int)m_dLeaves.size();
+		for ( size_t i=0; i<m_dLeaves.size(); ++i )
+		{
+			const PLeaf_t & l = m_dLeaves[i];
+			DevLeaf_t & t = d.m_dLeaves[i];
+			if ( l.m_pTerm )
+			{
+				t.m_uFirstBlk = l.m_pTerm->m_uFirstBlk;
+				t.m_nBlocks = l.m_pTerm->m_nBlocks;
+				t.m_nDocs = (uint32_t)l.m_pTerm->m_iDocs;
+				t.m_uDoclistEnd = (uint64_t)( l.m_pTerm->m_iDoclistOffset+l.m_pTerm->m_iDoclistLength-1 );
+				m_tOut.m_iCost += l.m_pTerm->m_iDocs;
+				m_tOut.m_iAlgBytes += l.m_pTerm->m_iDoclistLength + l.m_pTerm->m_iSkiplistBytes;
+			}
+			t.m_uQueriedFields = l.m_uFields;
+			t.m_fIDF = 0.0f;
+			if ( bUseBM25 && l.m_bOwnsIDF )
+				t.m_fIDF = m_hQwords.at ( m_q.words[l.m_iWord].word ).m_fIDF;
+			t.m_uAtomPos = (uint16_t)l.m_iAtomPos;
+			t.m_uNodePos = (uint16_t)l.m_iNodePos;
+		}
+		m_tOut.m_nStack = m_iMaxSp+1;
+
+		// field weights (already bound by the caller: BindWeights, src/sphinx.cpp:13903-13943)
+		const int nFields = (int)m_tIndex.m_tHdr.m_dFields.size();
+		d.m_nWeights = std::min ( nFields, 32 );
+		for ( int i=0; i<MAX_FIELDS; ++i )
+			d.m_dWeights[i] = ( m_q.field_weights && i<m_q.n_field_weights ) ? m_q.field_weights[i] : 1;
+
+		// filters
+		if ( m_q.n_filters>MAX_FILTERS )
+			return MGPU_E_UNSUPPORTED;
+		d.m_nFilters = std::max ( m_q.n_filters, 0 );
+		for ( int i=0; i<d.m_nFilters; ++i )
+		{
+			const mgpu_filter & f = m_q.filters[i];
+			if ( f.attr<0 || f.attr>=(int)m_tIndex.m_tHdr.m_dAttrs.size() )
+				return MGPU_E_BAD_QUERY;
+			const SchemaAttr_t & a = m_tIndex.m_tHdr.m_dAttrs[f.attr];
+			if ( ( a.m_iBitCount!=32 && a.m_iBitCount!=64 ) || ( a.m_iBitOffset & 31 ) )
+				return MGPU_E_UNSUPPORTED;
+			DevFilter_t & t = d.m_dFilters[i];
+			t.m_eKind = f.kind;
+			t.m_iMin = f.min_value;
+			t.m_iMax = f.max_value;
+			t.m_bExclude = f.exclude;
+			t.m_iDwordOff = (int)( a.m_iBitOffset/32 );
+			t.m_iBitCount = (int)a.m_iBitCount;
+			if ( f.kind==MGPU_FILTER_VALUES )
+			{
+				if ( f.n_values>MAX_FILTER_VALUES )
+					return MGPU_E_UNSUPPORTED;
+				t.m_nValues = f.n_values;
+				for ( int k=0; k<f.n_values; ++k )
+					t.m_dValues[k] = f.values[k];
+			} else if ( f.kind!=MGPU_FILTER_RANGE )
+				return MGPU_E_UNSUPPORTED;
+		}
+
+		// sort keys -> 64-bit packed key, most significant first
+		if ( m_q.n_sort_keys>5 )
+			return MGPU_E_BAD_QUERY;
+		d.m_nSortKeys = std::max ( m_q.n_sort_keys, 0 );
+		int iCur = 64;
+		for ( int i=0; i<d.m_nSortKeys; ++i )
+		{
+			const mgpu_sortkey & k = m_q.sort_keys[i];
+			DevSortKey_t & t = d.m_dSortKeys[i];
+			t.m_eKind = k.kind;
+			t.m_bDesc = k.desc;
+			int iBits = 32;
+			if ( k.kind==MGPU_KEYPART_INT )
+			{
+				if ( k.attr<0 || k.attr>=(int)m_tIndex.m_tHdr.m_dAttrs.size() )
+					return MGPU_E_BAD_QUERY;
+				const SchemaAttr_t & a = m_tIndex.m_tHdr.m_dAttrs[k.attr];
+				if ( ( a.m_iBitCount!=32 && a.m_iBitCount!=64 ) || ( a.m_iBitOffset & 31 ) )
+					return MGPU_E_UNSUPPORTED;
+				t.m_iDwordOff = (int)( a.m_iBitOffset/32 );
+				t.m_iBitCount = (int)a.m_iBitCount;
+				iBits = t.m_iBitCount;
+			} else if ( k.kind!=MGPU_KEYPART_WEIGHT && k.kind!=MGPU_KEYPART_ROWID )
+				return MGPU_E_UNSUPPORTED;
+			iCur -= iBits;
+			if ( iCur<0 )
+				return MGPU_E_UNSUPPORTED;	// more than 64 bits of sort keys
+			t.m_iShift = iCur;
+			if ( k.kind==MGPU_KEYPART_INT && m_tOut.m_iFirstIntKeyShift<0 )
+			{
+				m_tOut.m_iFirstIntKeyShift = iCur;
+				m_tOut.m_iFirstIntKeyBits = iBits;
+				m_tOut.m_bFirstIntKeyDesc = k.desc!=0;
+			}
+		}
+
+		d.m_iIndexWeight = m_q.index_weight ? m_q.index_weight : 1;
+		d.m_iMaxMatches = m_q.max_matches>0 ? m_q.max_matches : 1000;
+		if ( d.m_iMaxMatches>65536 )
+			return MGPU_E_UNSUPPORTED;
+		return MGPU_OK;
+	}
+};
+
+} // namespace
+
+
+int PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut )
+{
+	Planner_c tPlanner ( tIndex, tQuery, tOut );
+	tOut.m_iStatus = tPlanner.Run();
+	return tOut.m_iStatus;
+}
+
+//////////////////////////////////////////////////////////////////////////
+// batch executor
+//////////////////////////////////////////////////////////////////////////
+
+Batch_c::~Batch_c()
+{
+	if ( m_pIndex )
+		cudaSetDevice ( m_pIndex->m_iDevice );
+	if ( m_tEv0 ) cudaEventDestroy ( m_tEv0 );
+	if ( m_tEv1 ) cudaEventDestroy ( m_tEv1 );
+	if ( m_tEv2 ) cudaEventDestroy ( m_tEv2 );
+}
+
+static int Pow2Ceil ( int n )
+{
+	int p = 1;
+	while ( p<n )
+		p <<= 1;
+	return p;
+}
+
+int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries )
+{
+	m_pIndex = pIndex;
+	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
+	m_dPlans.resize ( nQueries );
+	for ( int i=0; i<nQueries; ++i )
+		PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
+
+	// runnable queries, biggest first (items are handed out in array order: longest-processing-time-first)
+	std::vector<int> dOrder;
+	int64_t iTotalCost = 0;
+	for ( int i=0; i<nQueries; ++i )
+		if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
+		{
+			dOrder.push_back ( i );
+			iTotalCost += m_dPlans[i].m_iCost;
+			m_nStack = std::max ( m_nStack, m_dPlans[i].m_nStack );
+			m_iKMax = std::max ( m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
+			m_tStats.algorithmic_bytes += m_dPlans[i].m_iAlgBytes;
+			m_tStats.postings += m_dPlans[i].m_iCost;
+		}
+	if ( dOrder.empty() )
+		return MGPU_OK;
+
+	const int iOcc = EvalOccupancy ( m_nStack );
+	const int nMaxCtas = pIndex->m_nSMs*iOcc;
+	const uint32_t uRows = pIndex->m_tDev.m_uRows;
+	const int nTiles = (int)( ( (uint64_t)uRows+TILE_W-1 )/TILE_W );
+	const int64_t iTarget = std::max<int64_t> ( 262144, iTotalCost/( (int64_t)nMaxCtas*4 ) );
+
+	struct Part_t { int m_iQuery; int m_nParts; int64_t m_iCostPerPart; };
+	std::vector<Part_t> dParts;
+	for ( int i : dOrder )
+	{
+		const PlannedQuery_t & p = m_dPlans[i];
+		int64_t nParts = ( p.m_iCost+iTarget-1 )/iTarget;
+		int iCap = std::max ( 1, 131072/std::max ( 1, p.m_tDev.m_iMaxMatches ) );
+		nParts = std::max<int64_t> ( 1, std::min<int64_t> ( nParts, std::min ( { nTiles, 64, iCap } ) ) );
+		dParts.push_back ( { i, (int)nParts, p.m_iCost/nParts } );
+	}
+	std::stable_sort ( dParts.begin(), dParts.end(), [] ( const Part_t & a, const Part_t & b ) { return a.m_iCostPerPart>b.m_iCostPerPart; } );
+
+	int iMaxKeysPerQuery = 1;
+	for ( const Part_t & t : dParts )
+	{
+		DevQuery_t q = m_dPlans[t.m_iQuery].m_tDev;
+		q.m_iFirstItem = (int)m_dItems.size();
+		q.m_nItems = t.m_nParts;
+		const int iDevQuery = (int)m_dDevQueries.size();
+		for ( int p=0; p<t.m_nParts; ++p )
+		{
+			uint64_t uT0 = (uint64_t)nTiles*p/t.m_nParts, uT1 = (uint64_t)nTiles*( p+1 )/t.m_nParts;
+			DevWorkItem_t tItem;
+			tItem.m_uQuery = (uint32_t)iDevQuery;
+			tItem.m_uRowLo = (uint32_t)( uT0*TILE_W );
+			tItem.m_uRowHi = (uint32_t)std::min<uint64_t> ( uT1*TILE_W, uRows );
+			tItem.m_uPad = 0;
+			m_dItems.push_back ( tItem );
+		}
+		iMaxKeysPerQuery = std::max ( iMaxKeysPerQuery, t.m_nParts*q.m_iMaxMatches );
+		m_dDevQueries.push_back ( q );
+		m_dDevToQuery.push_back ( t.m_iQuery );
+	}
+
+	const int nDevQ = (int)m_dDevQueries.size();
+	const int nItems = (int)m_dItems.size();
+	m_nCtas = std::min ( nMaxCtas, nItems );
+	m_iPoolCap = m_iKMax + 2*TILE_W;
+	m_iScratchStride = 2*Pow2Ceil ( iMaxKeysPerQuery );
+
+	CUDA_TRY ( m_dQ.Alloc ( nDevQ ), m_sError );
+	CUDA_TRY ( m_dI.Alloc ( nItems ), m_sError );
+	CUDA_TRY ( m_dCounter.Alloc ( 1 ), m_sError );
+	CUDA_TRY ( m_dPool.Alloc ( (size_t)m_nCtas*2*m_iPoolCap ), m_sError );
+	CUDA_TRY ( m_dItemKeys.Alloc ( (size_t)nItems*m_iKMax ), m_sError );
+	CUDA_TRY ( m_dItemOut.Alloc ( nItems ), m_sError );
+	CUDA_TRY ( m_dScratch.Alloc ( (size_t)nDevQ*m_iScratchStride ), m_sError );
+	CUDA_TRY ( m_dOutKeys.Alloc ( (size_t)nQueries*m_iKMax ), m_sError );
+	CUDA_TRY ( m_dOutDocid.Alloc ( (size_t)nQueries*m_iKMax ), m_sError );
+	CUDA_TRY ( m_dOutCount.Alloc ( nQueries ), m_sError );
+	CUDA_TRY ( m_dOutTotal.Alloc ( nQueries ), m_sError );
+	CUDA_TRY ( m_dOutSlot.Alloc ( nDevQ ), m_sError );
+	CUDA_TRY ( cudaMemset ( m_dOutCount.m_p, 0, (size_t)nQueries*4 ), m_sError );
+	CUDA_TRY ( cudaMemset ( m_dOutTotal.m_p, 0, (size_t)nQueries*8 ), m_sError );
+
+	cudaStream_t s = pIndex->m_tStream;
+	CUDA_TRY ( cudaMemcpyAsync ( m_dQ.m_p, m_dDevQueries.data(), (size_t)nDevQ*sizeof(DevQuery_t), cudaMemcpyHostToDevice, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( m_dI.m_p, m_dItems.data(), (size_t)nItems*sizeof(DevWorkItem_t), cudaMemcpyHostToDevice, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( m_dOutSlot.m_p, m_dDevToQuery.data(), (size_t)nDevQ*4, cudaMemcpyHostToDevice, s ), m_sError );
+	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
+	m_tStats.h2d_bytes = (int64_t)nDevQ*sizeof(DevQuery_t) + (int64_t)nItems*sizeof(DevWorkItem_t);
+	m_tStats.work_items = nItems;
+
+	CUDA_TRY ( cudaEventCreate ( &m_tEv0 ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEv1 ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEv2 ), m_sError );
+	return MGPU_OK;
+}
+
+int Batch_c::Run()
+{
+	if ( m_dDevQueries.empty() )
+		return MGPU_OK;
+	Index_c * pIndex = m_pIndex;
+	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
+	cudaStream_t s = pIndex->m_tStream;
+
+	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, sizeof(int32_t), s ), m_sError );
+
+	EvalParams_t P {};
+	P.m_tIndex = pIndex->m_tDev;
+	P.m_pQueries = m_dQ.m_p;
+	P.m_pItems = m_dI.m_p;
+	P.m_nItems = (int)m_dItems.size();
+	P.m_iPoolCap = m_iPoolCap;
+	P.m_pPool = m_dPool.m_p;
+	P.m_pItemKeys = m_dItemKeys.m_p;
+	P.m_pItemOut = m_dItemOut.m_p;
+	P.m_pCounter = m_dCounter.m_p;
+	P.m_iKMax = m_iKMax;
+
+	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
+	CUDA_TRY ( LaunchEval ( P, m_nStack, m_nCtas, s ), m_sError );
+	CUDA_TRY ( cudaEventRecord ( m_tEv1, s ), m_sError );
+
+	MergeParams_t M {};
+	M.m_tIndex = pIndex->m_tDev;
+	M.m_pQueries = m_dQ.m_p;
+	M.m_nQueries = (int)m_dDevQueries.size();
+	M.m_iKMax = m_iKMax;
+	M.m_pItemKeys = m_dItemKeys.m_p;
+	M.m_pItemOut = m_dItemOut.m_p;
+	M.m_pScratch = m_dScratch.m_p;
+	M.m_iScratchStride = m_iScratchStride;
+	M.m_pOutSlot = m_dOutSlot.m_p;
+	M.m_pOutKeys = m_dOutKeys.m_p;
+	M.m_pOutDocid = m_dOutDocid.m_p;
+	M.m_pOutCount = m_dOutCount.m_p;
+	M.m_pOutTotal = m_dOutTotal.m_p;
+	CUDA_TRY ( LaunchMerge ( M, std::min ( M.m_nQueries, pIndex->m_nSMs*8 ), s ), m_sError );
+	CUDA_TRY ( cudaEventRecord ( m_tEv2, s ), m_sError );
+	m_tStats.kernel_launches = 2;
+	m_bRan = true;
+	return MGPU_OK;
+}
+
+int Batch_c::Sync()
+{
+	if ( !m_pIndex )
+		return MGPU_OK;
+	CUDA_TRY ( cudaSetDevice ( m_pIndex->m_iDevice ), m_sError );
+	CUDA_TRY ( cudaStreamSynchronize ( m_pIndex->m_tStream ), m_sError );
+	if ( m_bRan && !m_dDevQueries.empty() )
+	{
+		cudaEventElapsedTime ( &m_tStats.eval_kernel_ms, m_tEv0, m_tEv1 );
+		cudaEventElapsedTime ( &m_tStats.merge_kernel_ms, m_tEv1, m_tEv2 );
+	}
+	return MGPU_OK;
+}
+
+int Batch_c::Fetch ( mgpu_result * pResults )
+{
+	const int nQueries = (int)m_dPlans.size();
+	for ( int i=0; i<nQueries; ++i )
+	{
+		mgpu_result & r = pResults[i];
+		r.status = m_dPlans[i].m_iStatus;
+		r.n_matches = 0;
+		r.total_found = 0;
+		if ( r.word_stats )
+			for ( size_t w=0; w<m_dPlans[i].m_dWordStats.size(); ++w )
+				r.word_stats[w] = m_dPlans[i].m_dWordStats[w];
+	}
+	if ( m_dDevQueries.empty() )
+		return MGPU_OK;
+	int iRes = Sync();
+	if ( iRes!=MGPU_OK )
+		return iRes;
+
+	std::vector<int32_t> dCount ( nQueries );
+	std::vector<int64_t> dTotal ( nQueries );
+	cudaStream_t s = m_pIndex->m_tStream;
+	CUDA_TRY ( cudaMemcpyAsync ( dCount.data(), m_dOutCount.m_p, (size_t)nQueries*4, cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( dTotal.data(), m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToHost, s ), m_sError );
+	std::vector<Key128_t> dKeys ( (size_t)nQueries*m_iKMax );
+	std::vector<int64_t> dDocid ( (size_t)nQueries*m_iKMax );
+	CUDA_TRY ( cudaMemcpyAsync ( dKeys.data(), m_dOutKeys.m_p, dKeys.size()*sizeof(Key128_t), cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( dDocid.data(), m_dOutDocid.m_p, dDocid.size()*8, cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
+	m_tStats.d2h_bytes = (int64_t)nQueries*12 + (int64_t)dKeys.size()*24;
+
+	for ( int iQuery=0; iQuery<nQueries; ++iQuery )
+	{
+		const PlannedQuery_t & p = m_dPlans[iQuery];
+		mgpu_result & r = pResults[iQuery];
+		if ( p.m_iStatus!=MGPU_OK )
+			continue;
+		r.n_matches = dCount[iQuery];
+		r.total_found = dTotal[iQuery];
+		for ( int i=0; i<r.n_matches; ++i )
+		{
+			const Key128_t & k = dKeys[(size_t)iQuery*m_iKMax+i];
+			uint32_t uGlobalRow = ~(uint32_t)( k.m_uLo>>32 );
+			if ( r.rowid ) r.rowid[i] = uGlobalRow - m_pIndex->m_uRowidBase;
+			if ( r.weight ) r.weight[i] = (int32_t)(uint32_t)k.m_uLo;
+			if ( r.docid ) r.docid[i] = dDocid[(size_t)iQuery*m_iKMax+i];
+			if ( r.sort_attr )
+			{
+				int64_t v = 0;
+				if ( p.m_iFirstIntKeyShift>=0 )
+				{
+					uint64_t u = k.m_uHi>>p.m_iFirstIntKeyShift;
+					if ( p.m_iFirstIntKeyBits==32 )
+					{
+						u &= 0xffffffffull;
+						if ( !p.m_bFirstIntKeyDesc ) u = ~u & 0xffffffffull;
+						v = (int64_t)u;
+					} else
+					{
+						if ( !p.m_bFirstIntKeyDesc ) u = ~u;
+						v = (int64_t)( u ^ 0x8000000000000000ull );
+					}
+				}
+				r.sort_attr[i] = v;
+			}
+		}
+	}
+	return MGPU_OK;
+}
+
+int Batch_c::ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, int iK )
+{
+	// device-to-device repack of the per-query keys [nq][KMax] -> [nq][iK]; outputs are already in the caller's query order
+	const int nQueries = (int)m_dPlans.size();
+	CUDA_TRY ( cudaSetDevice ( m_pIndex->m_iDevice ), m_sError );
+	cudaStream_t s = m_pIndex->m_tStream;
+	if ( m_dDevQueries.empty() )
+	{
+		CUDA_TRY ( cudaMemsetAsync ( pDevCounts, 0, (size_t)nQueries*4, s ), m_sError );
+		CUDA_TRY ( cudaMemsetAsync ( pDevTotal, 0, (size_t)nQueries*8, s ), m_sError );
+	} else
+	{
+		const int iW = std::min ( iK, m_iKMax );
+		CUDA_TRY ( cudaMemcpy2DAsync ( pDevKeys, (size_t)iK*sizeof(Key128_t), m_dOutKeys.m_p, (size_t)m_iKMax*sizeof(Key128_t),
+			(size_t)iW*sizeof(Key128_t), nQueries, cudaMemcpyDeviceToDevice, s ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( pDevCounts, m_dOutCount.m_p, (size_t)nQueries*4, cudaMemcpyDeviceToDevice, s ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( pDevTotal, m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToDevice, s ), m_sError );
+	}
+	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
+	return MGPU_OK;
+}
+
+} // namespace mgpu

@@ -1,0 +1,149 @@
+// Host side of the GPU query engine: index loader (CSphIndex_VLN::Prealloc equivalent), query planner
+// (ExtNode_i::Create + sphCreateRanker equivalent) and batch executor.  C++ in the reference's idiom;
+// the only way in from outside is the C ABI in include/mgpu.h (api.cpp).
+#pragma once
+
+#include "index_format.h"
+#include "../cuda/device_types.h"
+#include "../../../include/mgpu.h"
+
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace mgpu
+{
+
+/// dictionary entry + where the term's blocks live in the device block table
+struct TermInfo_t
+{
+	uint32_t	m_uFirstBlk = 0;
+	uint32_t	m_nBlocks = 0;
+	int			m_iDocs = 0;
+	int			m_iHits = 0;
+	int64_t		m_iDoclistOffset = 0;
+	int64_t		m_iDoclistLength = 0;	///< .spd extent incl. the terminating zero
+	int64_t		m_iSkiplistBytes = 0;	///< .spe extent
+};
+
+template<typename T>
+struct DevBuf_T
+{
+	T *		m_p = nullptr;
+	size_t	m_n = 0;
+	cudaError_t Alloc ( size_t n )
+	{
+		Free();
+		m_n = n;
+		if ( !n )
+			return cudaSuccess;
+		return cudaMalloc ( (void**)&m_p, n*sizeof(T) );
+	}
+	void Free()
+	{
+		if ( m_p )
+			cudaFree ( m_p );
+		m_p = nullptr;
+		m_n = 0;
+	}
+	~DevBuf_T() { Free(); }
+	DevBuf_T() = default;
+	DevBuf_T ( const DevBuf_T & ) = delete;
+	DevBuf_T & operator= ( const DevBuf_T & ) = delete;
+};
+
+class Index_c
+{
+public:
+	std::string		m_sError;
+	IndexHeader_t	m_tHdr;
+	int				m_iDevice = 0;
+	uint32_t		m_uRowidBase = 0;
+	cudaStream_t	m_tStream = nullptr;
+	int				m_nSMs = 148;
+	std::mutex		m_tLock;		///< serialises batches on this handle
+
+	std::unordered_map<std::string,TermInfo_t> m_hTerms;
+
+	DevBuf_T<uint8_t>	m_dSpd, m_dSpp;
+	DevBuf_T<uint32_t>	m_dSpa, m_dDead;
+	DevBuf_T<uint32_t>	m_dBlkRowid;
+	DevBuf_T<uint64_t>	m_dBlkOff, m_dBlkHitpos;
+	DevIndex_t			m_tDev {};
+
+	int		Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase );
+	~Index_c();
+
+	const TermInfo_t * FindTerm ( const char * szWord ) const
+	{
+		auto it = m_hTerms.find ( szWord );
+		return it==m_hTerms.end() ? nullptr : &it->second;
+	}
+	int		AttrIndex ( const char * szName ) const;
+	int		FieldIndex ( const char * szName ) const;
+};
+
+/// one planned query: device descriptor + host bookkeeping
+struct PlannedQuery_t
+{
+	int				m_iStatus = MGPU_OK;
+	DevQuery_t		m_tDev {};
+	int				m_nStack = 1;
+	int64_t			m_iCost = 0;			///< sum of df over leaves (postings)
+	int64_t			m_iAlgBytes = 0;		///< SURVEY 8(d) algorithmic bytes (doclists + skiplists)
+	std::vector<mgpu_wordstat> m_dWordStats;
+	int				m_iFirstIntKeyShift = -1;
+	int				m_iFirstIntKeyBits = 0;
+	bool			m_bFirstIntKeyDesc = false;
+};
+
+int		PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut );
+
+class Batch_c
+{
+public:
+	Index_c *		m_pIndex = nullptr;
+	std::string		m_sError;
+	std::vector<PlannedQuery_t> m_dPlans;
+	std::vector<DevQuery_t>		m_dDevQueries;	///< only the runnable ones, in order
+	std::vector<int>			m_dDevToQuery;	///< device query -> batch query index
+	std::vector<DevWorkItem_t>	m_dItems;
+	int		m_nStack = 1;
+	int		m_iKMax = 1;
+	int		m_iPoolCap = 0;
+	int		m_nCtas = 0;
+	int		m_iScratchStride = 0;
+
+	DevBuf_T<DevQuery_t>	m_dQ;
+	DevBuf_T<DevWorkItem_t>	m_dI;
+	DevBuf_T<int32_t>		m_dCounter;
+	DevBuf_T<Key128_t>		m_dPool, m_dItemKeys, m_dScratch, m_dOutKeys;
+	DevBuf_T<DevItemOut_t>	m_dItemOut;
+	DevBuf_T<int64_t>		m_dOutDocid, m_dOutTotal;
+	DevBuf_T<int32_t>		m_dOutCount, m_dOutSlot;
+
+	cudaEvent_t		m_tEv0 = nullptr, m_tEv1 = nullptr, m_tEv2 = nullptr;
+	mgpu_batch_stats m_tStats {};
+	bool			m_bRan = false;
+
+	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries );
+	int		Run();
+	int		Sync();
+	int		Fetch ( mgpu_result * pResults );
+	int		ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, int iK );
+	~Batch_c();
+};
+
+// kernels.cu launchers
+size_t		EvalDynSmemBytes ( int nStack );
+int			EvalOccupancy ( int nStack );
+cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );
+cudaError_t	LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream );
+cudaError_t	LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
+				Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream );
+cudaError_t	LaunchDecodeDoclist ( const DevIndex_t & tIdx, const DevLeaf_t & tLeaf, uint32_t * pRowid, uint32_t * pHits, uint32_t * pFields,
+				uint64_t * pHitlistPos, unsigned long long * pChecksum, int nCtas, cudaStream_t tStream );
+
+} // namespace mgpu

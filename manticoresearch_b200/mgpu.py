@@ -1,0 +1,554 @@
+"""ctypes mirror of include/mgpu.h.
+
+Query trees are built from the same pieces the reference's parser produces (XQNode_t / XQKeyword_t,
+src/sphinxquery.h:21-39, 134-280): keyword nodes carry one word; AND/OR/ANDNOT/MAYBE nodes carry
+children; PHRASE/PROXIMITY nodes carry a word list.  `Query.pack()` flattens a tree into the C structs.
+The same packed structs are accepted by the CPU oracle (oracle/oracle.cpp), which is how the parity
+tests feed both sides identical inputs.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+MGPU_OK = 0
+MGPU_E_IO, MGPU_E_FORMAT, MGPU_E_UNSUPPORTED, MGPU_E_BAD_QUERY, MGPU_E_NO_DEVICE, MGPU_E_CUDA, MGPU_E_NOMEM = -1, -2, -3, -4, -5, -6, -7
+
+OP_AND, OP_OR, OP_MAYBE, OP_NOT, OP_ANDNOT, OP_BEFORE, OP_PHRASE, OP_PROXIMITY, OP_QUORUM, OP_NEAR = range(10)
+RANK_PROXIMITY_BM25, RANK_BM25, RANK_NONE, RANK_WORDCOUNT = range(4)
+KEYPART_ROWID, KEYPART_WEIGHT, KEYPART_INT = range(3)
+FILTER_RANGE, FILTER_VALUES = range(2)
+
+
+class MgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class c_xqkeyword(C.Structure):
+    _fields_ = [("word", C.c_char_p), ("atom_pos", C.c_int32), ("boost", C.c_float),
+                ("field_start", C.c_uint8), ("field_end", C.c_uint8), ("excluded", C.c_uint8), ("expanded", C.c_uint8)]
+
+
+class c_xqnode(C.Structure):
+    _fields_ = [("op", C.c_int32), ("oparg", C.c_int32), ("first_child", C.c_int32), ("n_children", C.c_int32),
+                ("first_word", C.c_int32), ("n_words", C.c_int32), ("field_mask", C.c_uint32), ("field_max_pos", C.c_int32),
+                ("not_weighted", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class c_sortkey(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("attr", C.c_int32), ("desc", C.c_int32)]
+
+
+class c_filter(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("attr", C.c_int32), ("min_value", C.c_int64), ("max_value", C.c_int64),
+                ("values", C.POINTER(C.c_int64)), ("n_values", C.c_int32), ("exclude", C.c_int32)]
+
+
+class c_query(C.Structure):
+    _fields_ = [("nodes", C.POINTER(c_xqnode)), ("n_nodes", C.c_int32), ("root", C.c_int32),
+                ("children", C.POINTER(C.c_int32)), ("n_children", C.c_int32),
+                ("words", C.POINTER(c_xqkeyword)), ("n_words", C.c_int32),
+                ("ranker", C.c_int32), ("field_weights", C.POINTER(C.c_int32)), ("n_field_weights", C.c_int32),
+                ("sort_keys", C.POINTER(c_sortkey)), ("n_sort_keys", C.c_int32),
+                ("filters", C.POINTER(c_filter)), ("n_filters", C.c_int32),
+                ("max_matches", C.c_int32), ("index_weight", C.c_int32),
+                ("plain_idf", C.c_uint8), ("unnormalized_tfidf", C.c_uint8), ("pad", C.c_uint8 * 2),
+                ("total_docs", C.c_int64), ("word_docs", C.POINTER(C.c_int64))]
+
+
+class c_wordstat(C.Structure):
+    _fields_ = [("docs", C.c_int64), ("hits", C.c_int64)]
+
+
+class c_result(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_matches", C.c_int32), ("total_found", C.c_int64),
+                ("rowid", C.POINTER(C.c_uint32)), ("weight", C.POINTER(C.c_int32)), ("docid", C.POINTER(C.c_int64)),
+                ("sort_attr", C.POINTER(C.c_int64)), ("word_stats", C.POINTER(c_wordstat))]
+
+
+class c_batch_stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("work_items", C.c_int64), ("algorithmic_bytes", C.c_int64),
+                ("postings", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float)]
+
+
+class c_build_doc_input(C.Structure):
+    _fields_ = [("n_docs", C.c_int32), ("n_fields", C.c_int32), ("field_names", C.POINTER(C.c_char_p)),
+                ("n_attrs", C.c_int32), ("attr_names", C.POINTER(C.c_char_p)),
+                ("docids", C.POINTER(C.c_int64)), ("attrs", C.POINTER(C.c_uint32)),
+                ("n_keywords", C.c_int32), ("keywords", C.POINTER(C.c_char_p)),
+                ("field_tok_offsets", C.POINTER(C.c_int64)), ("tok_keyword", C.POINTER(C.c_int32)), ("tok_pos", C.POINTER(C.c_int32)),
+                ("skiplist_block", C.c_int32), ("hit_format_inline", C.c_int32)]
+
+
+class SynthParams(C.Structure):
+    """mgpu_synth_params; defaults = the corpus of SURVEY.md 8(d)."""
+    _fields_ = [("seed", C.c_uint64), ("first_doc", C.c_int64), ("n_docs", C.c_int64), ("vocab", C.c_int32),
+                ("title_min", C.c_int32), ("title_max", C.c_int32), ("body_min", C.c_int32), ("body_max", C.c_int32),
+                ("body_mu", C.c_float), ("body_sigma", C.c_float), ("threads", C.c_int32)]
+
+    def __init__(self, n_docs, first_doc=0, seed=0x5EED0001, vocab=1 << 20, threads=0,
+                 title_min=4, title_max=12, body_min=16, body_max=1024, body_mu=4.6, body_sigma=0.6):
+        super().__init__(seed, first_doc, n_docs, vocab, title_min, title_max, body_min, body_max, body_mu, body_sigma, threads)
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Loads libmgpu.so (building it first if the sources are newer). Raises if that is impossible."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    if path is None:
+        from . import build as _build
+        path = _build.LIB
+        if _build.needs_build():
+            _build.build()
+    if not os.path.exists(path):
+        raise MgpuError(MGPU_E_IO, "libmgpu.so is not built (run python -m manticoresearch_b200.build)")
+    lib_ = C.CDLL(path)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    sig = {
+        "mgpu_abi_version": (C.c_int, []),
+        "mgpu_index_open": (C.c_int, [C.c_char_p, C.c_int, u32, C.POINTER(vp)]),
+        "mgpu_index_close": (None, [vp]),
+        "mgpu_last_error": (C.c_char_p, [vp]),
+        "mgpu_index_total_docs": (i64, [vp]),
+        "mgpu_index_num_fields": (i32, [vp]),
+        "mgpu_index_field_index": (i32, [vp, C.c_char_p]),
+        "mgpu_index_attr_index": (i32, [vp, C.c_char_p]),
+        "mgpu_index_word_stats": (C.c_int, [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
+        "mgpu_index_word_bytes": (C.c_int, [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
+        "mgpu_search_batch": (C.c_int, [vp, C.POINTER(c_query), C.c_int, C.POINTER(c_result)]),
+        "mgpu_batch_prepare": (C.c_int, [vp, C.POINTER(c_query), C.c_int, C.POINTER(vp)]),
+        "mgpu_batch_run": (C.c_int, [vp]),
+        "mgpu_batch_sync": (C.c_int, [vp]),
+        "mgpu_batch_fetch": (C.c_int, [vp, C.POINTER(c_result)]),
+        "mgpu_batch_free": (None, [vp]),
+        "mgpu_batch_get_stats": (C.c_int, [vp, C.POINTER(c_batch_stats)]),
+        "mgpu_batch_export_keys": (C.c_int, [vp, vp, vp, vp, C.c_int]),
+        "mgpu_merge_shard_keys": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+        "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
+        "mgpu_decode_doclist": (C.c_int, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), i64, C.POINTER(i64)]),
+        "mgpu_build_index": (C.c_int, [C.c_char_p, C.POINTER(c_build_doc_input), C.c_char_p, C.c_int]),
+        "mgpu_build_synthetic": (C.c_int, [C.c_char_p, C.POINTER(SynthParams), C.c_char_p, C.c_int]),
+        "mgpu_synth_field_len": (i32, [C.POINTER(SynthParams), i64, C.c_int]),
+        "mgpu_synth_token": (i32, [C.POINTER(SynthParams), i64, C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib_, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib_
+    return lib_
+
+
+def lib():
+    return load_library()
+
+
+EXPORTED_SYMBOLS = [
+    "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_last_error", "mgpu_index_total_docs",
+    "mgpu_index_num_fields", "mgpu_index_field_index", "mgpu_index_attr_index", "mgpu_index_word_stats",
+    "mgpu_index_word_bytes", "mgpu_search_batch", "mgpu_batch_prepare", "mgpu_batch_run", "mgpu_batch_sync",
+    "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_batch_export_keys",
+    "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist", "mgpu_build_index",
+    "mgpu_build_synthetic", "mgpu_synth_field_len", "mgpu_synth_token",
+]
+
+# ---------------------------------------------------------------------------------------------
+# query trees
+# ---------------------------------------------------------------------------------------------
+
+ALL_FIELDS = 0xFFFFFFFF
+
+
+class Keyword:
+    """XQKeyword_t"""
+    def __init__(self, word, atom_pos, boost=1.0, field_start=False, field_end=False, excluded=False, expanded=False):
+        self.word, self.atom_pos, self.boost = word, atom_pos, boost
+        self.field_start, self.field_end, self.excluded, self.expanded = field_start, field_end, excluded, expanded
+
+
+class Node:
+    """XQNode_t: either words (keyword / phrase / proximity) or children (AND/OR/...)."""
+    def __init__(self, op, children=None, words=None, oparg=0, field_mask=ALL_FIELDS, field_max_pos=0, not_weighted=False):
+        self.op, self.children, self.words = op, list(children or []), list(words or [])
+        self.oparg, self.field_mask, self.field_max_pos, self.not_weighted = oparg, field_mask, field_max_pos, not_weighted
+
+    def fields(self, mask):
+        """apply a field limit (@title ...) to this node and everything below it"""
+        self.field_mask = mask
+        for c in self.children:
+            c.fields(mask)
+        return self
+
+    def all_keywords(self):
+        out = list(self.words)
+        for c in self.children:
+            out += c.all_keywords()
+        return out
+
+
+def kw(word, atom_pos, **kwargs):
+    return Node(OP_AND, words=[Keyword(word, atom_pos, **kwargs)])
+
+
+def AND(*children):
+    return Node(OP_AND, children=children)
+
+
+def OR(*children):
+    return Node(OP_OR, children=children)
+
+
+def ANDNOT(*children):
+    return Node(OP_ANDNOT, children=children)
+
+
+def MAYBE(*children):
+    return Node(OP_MAYBE, children=children)
+
+
+def PHRASE(words_with_pos, **kwargs):
+    return Node(OP_PHRASE, words=[Keyword(w, p) for w, p in words_with_pos], **kwargs)
+
+
+def PROXIMITY(words_with_pos, distance, **kwargs):
+    return Node(OP_PROXIMITY, words=[Keyword(w, p) for w, p in words_with_pos], oparg=distance, **kwargs)
+
+
+class SortKey:
+    def __init__(self, kind, attr=0, desc=True):
+        self.kind, self.attr, self.desc = kind, attr, desc
+
+
+class Filter:
+    def __init__(self, attr, min_value=None, max_value=None, values=None, exclude=False):
+        self.attr, self.min_value, self.max_value, self.values, self.exclude = attr, min_value, max_value, values, exclude
+
+
+class Query:
+    """CSphQuery subset + the parsed tree."""
+    def __init__(self, root, ranker=RANK_PROXIMITY_BM25, field_weights=None, sort_keys=None, filters=None,
+                 max_matches=1000, index_weight=1, plain_idf=False, unnormalized_tfidf=False, total_docs=0, word_docs=None):
+        self.root, self.ranker, self.field_weights = root, ranker, field_weights
+        self.sort_keys, self.filters = sort_keys or [], filters or []
+        self.max_matches, self.index_weight = max_matches, index_weight
+        self.plain_idf, self.unnormalized_tfidf = plain_idf, unnormalized_tfidf
+        self.total_docs, self.word_docs = total_docs, word_docs
+        self._keep = []
+
+    def keywords(self):
+        return self.root.all_keywords() if self.root is not None else []
+
+    def pack(self, out=None):
+        """fills (and returns) a c_query; keeps the backing arrays alive on self"""
+        nodes, children, words = [], [], []
+
+        def walk(n):
+            idx = len(nodes)
+            nodes.append(None)
+            cn = c_xqnode()
+            cn.op, cn.oparg = n.op, n.oparg
+            cn.field_mask, cn.field_max_pos, cn.not_weighted = n.field_mask & 0xFFFFFFFF, n.field_max_pos, int(n.not_weighted)
+            cn.first_word, cn.n_words = len(words), len(n.words)
+            for k in n.words:
+                ck = c_xqkeyword(k.word.encode("utf-8"), k.atom_pos, k.boost, int(k.field_start), int(k.field_end), int(k.excluded), int(k.expanded))
+                words.append(ck)
+            kids = [walk(c) for c in n.children]
+            cn.first_child, cn.n_children = len(children), len(kids)
+            children.extend(kids)
+            nodes[idx] = cn
+            return idx
+
+        q = out if out is not None else c_query()
+        root = walk(self.root) if self.root is not None else -1
+        a_nodes = (c_xqnode * max(1, len(nodes)))(*nodes)
+        a_children = (C.c_int32 * max(1, len(children)))(*children)
+        a_words = (c_xqkeyword * max(1, len(words)))(*words)
+        self._keep = [a_nodes, a_children, a_words]
+        q.nodes, q.n_nodes, q.root = a_nodes, len(nodes), root
+        q.children, q.n_children = a_children, len(children)
+        q.words, q.n_words = a_words, len(words)
+        q.ranker = self.ranker
+        if self.field_weights is not None:
+            a_w = (C.c_int32 * len(self.field_weights))(*self.field_weights)
+            self._keep.append(a_w)
+            q.field_weights, q.n_field_weights = a_w, len(self.field_weights)
+        else:
+            q.field_weights, q.n_field_weights = None, 0
+        if self.sort_keys:
+            a_s = (c_sortkey * len(self.sort_keys))(*[c_sortkey(s.kind, s.attr, int(s.desc)) for s in self.sort_keys])
+            self._keep.append(a_s)
+            q.sort_keys, q.n_sort_keys = a_s, len(self.sort_keys)
+        else:
+            q.sort_keys, q.n_sort_keys = None, 0
+        if self.filters:
+            fl = []
+            for f in self.filters:
+                cf = c_filter()
+                cf.attr, cf.exclude = f.attr, int(f.exclude)
+                if f.values is not None:
+                    a_v = (C.c_int64 * len(f.values))(*f.values)
+                    self._keep.append(a_v)
+                    cf.kind, cf.values, cf.n_values = FILTER_VALUES, a_v, len(f.values)
+                else:
+                    cf.kind, cf.min_value, cf.max_value = FILTER_RANGE, f.min_value, f.max_value
+                fl.append(cf)
+            a_f = (c_filter * len(fl))(*fl)
+            self._keep.append(a_f)
+            q.filters, q.n_filters = a_f, len(fl)
+        else:
+            q.filters, q.n_filters = None, 0
+        q.max_matches, q.index_weight = self.max_matches, self.index_weight
+        q.plain_idf, q.unnormalized_tfidf = int(self.plain_idf), int(self.unnormalized_tfidf)
+        q.total_docs = self.total_docs
+        if self.word_docs is not None:
+            a_d = (C.c_int64 * len(self.word_docs))(*self.word_docs)
+            self._keep.append(a_d)
+            q.word_docs = a_d
+        else:
+            q.word_docs = None
+        return q
+
+
+class ResultSet:
+    """host buffers for a batch of mgpu_result + numpy-free accessors"""
+    def __init__(self, queries):
+        n = len(queries)
+        self.results = (c_result * max(1, n))()
+        self._keep = []
+        for i, q in enumerate(queries):
+            k = q.max_matches if q.max_matches > 0 else 1000
+            nw = max(1, len(q.keywords()))
+            bufs = ((C.c_uint32 * k)(), (C.c_int32 * k)(), (C.c_int64 * k)(), (C.c_int64 * k)(), (c_wordstat * nw)())
+            self._keep.append(bufs)
+            r = self.results[i]
+            r.rowid, r.weight, r.docid, r.sort_attr, r.word_stats = bufs
+        self.n = n
+
+    def get(self, i):
+        r = self.results[i]
+        n = r.n_matches
+        return {
+            "status": r.status, "total_found": r.total_found,
+            "rowid": list(r.rowid[:n]), "weight": list(r.weight[:n]), "docid": list(r.docid[:n]), "sort_attr": list(r.sort_attr[:n]),
+        }
+
+    def word_stats(self, i, nwords):
+        r = self.results[i]
+        return [(r.word_stats[w].docs, r.word_stats[w].hits) for w in range(nwords)]
+
+
+def pack_queries(queries):
+    arr = (c_query * max(1, len(queries)))()
+    for i, q in enumerate(queries):
+        q.pack(arr[i])
+    return arr
+
+
+class Index:
+    """Handle of an index resident in one GPU's HBM (mgpu_index)."""
+    def __init__(self, path_prefix, device=0, rowid_base=0):
+        self._lib = lib()
+        h = C.c_void_p()
+        rc = self._lib.mgpu_index_open(path_prefix.encode(), device, rowid_base, C.byref(h))
+        if rc != MGPU_OK:
+            raise MgpuError(rc, (self._lib.mgpu_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._lib.mgpu_index_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc):
+        raise MgpuError(rc, (self._lib.mgpu_last_error(self._h) or b"").decode())
+
+    @property
+    def total_docs(self):
+        return self._lib.mgpu_index_total_docs(self._h)
+
+    @property
+    def num_fields(self):
+        return self._lib.mgpu_index_num_fields(self._h)
+
+    def field_index(self, name):
+        return self._lib.mgpu_index_field_index(self._h, name.encode())
+
+    def attr_index(self, name):
+        return self._lib.mgpu_index_attr_index(self._h, name.encode())
+
+    def word_stats(self, word):
+        d, h = C.c_int64(), C.c_int64()
+        if not self._lib.mgpu_index_word_stats(self._h, word.encode(), C.byref(d), C.byref(h)):
+            return None
+        return d.value, h.value
+
+    def word_bytes(self, word):
+        d, s = C.c_int64(), C.c_int64()
+        if not self._lib.mgpu_index_word_bytes(self._h, word.encode(), C.byref(d), C.byref(s)):
+            return None
+        return d.value, s.value
+
+    def search(self, queries):
+        """mgpu_search_batch: host buffers in, host buffers out. Returns a ResultSet."""
+        arr = pack_queries(queries)
+        rs = ResultSet(queries)
+        rc = self._lib.mgpu_search_batch(self._h, arr, len(queries), rs.results)
+        if rc != MGPU_OK:
+            self._err(rc)
+        return rs
+
+    def prepare(self, queries):
+        return Batch(self, queries)
+
+    def decode_doclist(self, word):
+        import numpy as np
+        st = self.word_stats(word)
+        if st is None:
+            return None
+        n = st[0]
+        rowid = np.zeros(n, dtype=np.uint32)
+        hits = np.zeros(n, dtype=np.uint32)
+        fields = np.zeros(n, dtype=np.uint32)
+        pos = np.zeros(n, dtype=np.uint64)
+        nout = C.c_int64()
+        rc = self._lib.mgpu_decode_doclist(self._h, word.encode(),
+                                           rowid.ctypes.data_as(C.POINTER(C.c_uint32)), hits.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           fields.ctypes.data_as(C.POINTER(C.c_uint32)), pos.ctypes.data_as(C.POINTER(C.c_uint64)), n, C.byref(nout))
+        if rc != MGPU_OK:
+            self._err(rc)
+        return rowid, hits, fields, pos
+
+    def decode_doclist_timed(self, word):
+        """decode only, nothing copied back (roofline probe of kernel K1)"""
+        nout = C.c_int64()
+        rc = self._lib.mgpu_decode_doclist(self._h, word.encode(), None, None, None, None, 0, C.byref(nout))
+        if rc != MGPU_OK:
+            self._err(rc)
+        return nout.value
+
+
+class Batch:
+    """mgpu_batch: plan uploaded once; run() may be repeated (the device-resident timed region)."""
+    def __init__(self, index, queries):
+        self.index, self.queries = index, queries
+        self._lib = index._lib
+        self._arr = pack_queries(queries)
+        h = C.c_void_p()
+        rc = self._lib.mgpu_batch_prepare(index._h, self._arr, len(queries), C.byref(h))
+        if rc != MGPU_OK:
+            index._err(rc)
+        self._h = h
+
+    def run(self):
+        rc = self._lib.mgpu_batch_run(self._h)
+        if rc != MGPU_OK:
+            self.index._err(rc)
+
+    def sync(self):
+        rc = self._lib.mgpu_batch_sync(self._h)
+        if rc != MGPU_OK:
+            self.index._err(rc)
+
+    def fetch(self):
+        rs = ResultSet(self.queries)
+        rc = self._lib.mgpu_batch_fetch(self._h, rs.results)
+        if rc != MGPU_OK:
+            self.index._err(rc)
+        return rs
+
+    def stats(self):
+        st = c_batch_stats()
+        self._lib.mgpu_batch_get_stats(self._h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in c_batch_stats._fields_}
+
+    def export_keys(self, dev_keys_ptr, dev_counts_ptr, dev_total_ptr, k):
+        rc = self._lib.mgpu_batch_export_keys(self._h, dev_keys_ptr, dev_counts_ptr, dev_total_ptr, k)
+        if rc != MGPU_OK:
+            self.index._err(rc)
+
+    def free(self):
+        if self._h:
+            self._lib.mgpu_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# index building (host only)
+# ---------------------------------------------------------------------------------------------
+
+def build_index(path_prefix, field_names, docs, attr_names=(), skiplist_block=32, hit_format_inline=True):
+    """docs: list of dicts {"id": int, "fields": [[(keyword, pos), ...] per field], "attrs": [uint32...]}.
+
+    Row order = list order (the reference assigns rowids in source order)."""
+    kw_index, keywords = {}, []
+    offsets, tok_kw, tok_pos = [0], [], []
+    for d in docs:
+        for f in range(len(field_names)):
+            for (w, p) in d["fields"][f]:
+                if w not in kw_index:
+                    kw_index[w] = len(keywords)
+                    keywords.append(w)
+                tok_kw.append(kw_index[w])
+                tok_pos.append(p)
+            offsets.append(len(tok_kw))
+    inp = c_build_doc_input()
+    n = len(docs)
+    a_fields = (C.c_char_p * len(field_names))(*[f.encode() for f in field_names])
+    a_attrs = (C.c_char_p * max(1, len(attr_names)))(*[a.encode() for a in attr_names])
+    a_ids = (C.c_int64 * max(1, n))(*[d["id"] for d in docs])
+    flat_attrs = [v for d in docs for v in d.get("attrs", [])]
+    a_attrv = (C.c_uint32 * max(1, len(flat_attrs)))(*flat_attrs)
+    a_kw = (C.c_char_p * max(1, len(keywords)))(*[k.encode("utf-8") for k in keywords])
+    a_off = (C.c_int64 * len(offsets))(*offsets)
+    a_tk = (C.c_int32 * max(1, len(tok_kw)))(*tok_kw)
+    a_tp = (C.c_int32 * max(1, len(tok_pos)))(*tok_pos)
+    inp.n_docs, inp.n_fields, inp.field_names = n, len(field_names), a_fields
+    inp.n_attrs, inp.attr_names = len(attr_names), a_attrs
+    inp.docids, inp.attrs = a_ids, a_attrv
+    inp.n_keywords, inp.keywords = len(keywords), a_kw
+    inp.field_tok_offsets, inp.tok_keyword, inp.tok_pos = a_off, a_tk, a_tp
+    inp.skiplist_block, inp.hit_format_inline = skiplist_block, int(hit_format_inline)
+    err = C.create_string_buffer(512)
+    rc = lib().mgpu_build_index(path_prefix.encode(), C.byref(inp), err, 512)
+    if rc != MGPU_OK:
+        raise MgpuError(rc, err.value.decode())
+
+
+def build_synthetic(path_prefix, params):
+    err = C.create_string_buffer(512)
+    rc = lib().mgpu_build_synthetic(path_prefix.encode(), C.byref(params), err, 512)
+    if rc != MGPU_OK:
+        raise MgpuError(rc, err.value.decode())
+
+
+def synth_field_len(params, doc, field):
+    return lib().mgpu_synth_field_len(C.byref(params), doc, field)
+
+
+def synth_token(params, doc, field, pos0):
+    return lib().mgpu_synth_token(C.byref(params), doc, field, pos0)
+
+
+def synth_keyword(term):
+    """keyword string of 0-based term id (0 = most frequent)"""
+    return "t%07d" % (term + 1)

@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/golden_vectors.json from the reference's own functional tests.
+
+Reads /root/reference/test/test_NNN/{test.xml,model.bin} (this container only; the GPU box has no
+/root/reference, which is why the resulting JSON is committed).  The documents are transcribed from
+each test.xml's <db_insert>/<custom_insert>; the expected results come straight out of model.bin
+(PHP serialize(), see php_unserialize.py).  Query TREES are written by hand below, in the shape the
+reference's parser produces (XQParser_t::AddOp n-ary nodes, one keyword per leaf, phrase/proximity
+nodes with word lists, atom positions 1,2,3.. in query order, src/sphinxquery.cpp:1267, 1634-1678),
+because the parser itself needs bison and is out of scope.
+
+Tree notation: ["kw", word, atompos, fieldmask?], ["and"|"or"|"andnot"|"maybe", child...],
+["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]].
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from php_unserialize import php_unserialize  # noqa: E402
+
+REF = "/root/reference/test"
+
+
+def model(test):
+    m = php_unserialize(open(os.path.join(REF, test, "model.bin"), "rb").read())
+    return m[0]
+
+
+def api_expect(r, want_query=None):
+    if want_query is not None:
+        assert r["query"] == want_query, (r["query"], want_query)
+    matches = [[int(k), int(v["weight"])] for k, v in (r.get("matches") or {}).items()]
+    words = {str(k): [int(v["docs"]), int(v["hits"])] for k, v in (r.get("words") or {}).items()}
+    return {"matches": matches, "total_found": int(r["total_found"]), "words": words}
+
+
+def ql_expect(r):
+    rows = [[int(row["id"]), int(row["w"])] for row in r["rows"].values()]
+    return {"matches": rows, "total_found": int(r["total_rows"]), "words": {}}
+
+
+ALL = 0xFFFFFFFF
+TITLE, BODY = 1, 2
+
+out = {"source": "ravelry/manticoresearch test/test_019,037,114,116,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+
+# ---------------------------------------------------------------------------------------------
+# test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
+# ---------------------------------------------------------------------------------------------
+docs_019 = [
+    (111, "", "basic query"),
+    (222, "", "phrase query on steroids"),
+    (333, "sample program", 'this is a test program that prints out "hello world" to the console'),
+    (444, "", "china 吐我"),
+    (555, "sample program two", "something written in basic | canon ef 16-35 lens"),
+    (666, "sample program three", "something written in perl"),
+    (777, "", "77 lies multiplied by 77"),
+    (888, "", "agent 0077"),
+    (999, "", "1234567812345678"),
+    (901, "aaa", "aaa"),
+    (902, "aaa", ""),
+    (903, "", "aaa"),
+    (910, "", "wordbefore\0\0wordafter"),
+]
+m19 = model("test_019")
+q019 = [
+    (0, "basic query", ["and", ["kw", "basic", 1], ["kw", "query", 2]]),
+    (1, '"phrase query"', ["phrase", [["phrase", 1], ["query", 2]]]),
+    (3, "@title sample @body world", ["and", ["kw", "sample", 1, TITLE], ["kw", "world", 2, BODY]]),
+    (6, '"hello program"~3', ["prox", 3, [["hello", 1], ["program", 2]]]),
+    (7, '"hello program"~4', ["prox", 4, [["hello", 1], ["program", 2]]]),
+    (8, "吐", ["kw", "吐", 1]),
+    (9, "我", ["kw", "我", 1]),
+    (10, "basic | china", ["or", ["kw", "basic", 1], ["kw", "china", 2]]),
+    (11, '"test program" | basic', ["or", ["phrase", [["test", 1], ["program", 2]]], ["kw", "basic", 3]]),
+    (12, '"test that"~3 | basic', ["or", ["prox", 3, [["test", 1], ["that", 2]]], ["kw", "basic", 3]]),
+    (14, "@title sample @body -basic", ["andnot", ["kw", "sample", 1, TITLE], ["kw", "basic", 2, BODY]]),
+    (15, "-basic|perl sample", ["andnot", ["kw", "sample", 3], ["or", ["kw", "basic", 1], ["kw", "perl", 2]]]),
+    (17, "77", ["kw", "77", 1]),
+    (18, "0077", ["kw", "0077", 1]),
+    (19, "@title test", ["kw", "test", 1, TITLE]),
+    (20, "@!title aaa", ["kw", "aaa", 1, ALL & ~TITLE]),
+    (21, "@!(title,body) aaa", ["kw", "aaa", 1, ALL & ~(TITLE | BODY)]),
+    (30, "1234567812345678", ["kw", "1234567812345678", 1]),
+    (33, "canon 16 35", ["and", ["kw", "canon", 1], ["kw", "16", 2], ["kw", "35", 3]]),
+]
+case = {"name": "test_019", "fields": ["title", "body"], "min_word_len": 2,
+        "docs": [{"id": d[0], "fields": [d[1], d[2]]} for d in docs_019], "queries": []}
+for qi, text, tree in q019:
+    case["queries"].append({"text": text, "tree": tree, "ranker": "proximity_bm25", "expect": api_expect(m19[qi], text)})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_037 "rankers", index `test` (stem_ru/stem_en: both doc and query words are stemmed alike, so
+# treating the Russian words as opaque tokens gives the same postings; word stats are NOT compared)
+# ---------------------------------------------------------------------------------------------
+docs_037 = [(1, "зимние шины диски чего то тут зимние шины", ""),
+            (2, "test doc two", "second stupid test document with random content")] + [(i, "filler", "filler") for i in range(3, 11)]
+m37 = model("test_037")
+ph = ["phrase", [["зимние", 1], ["шины", 2]]]
+case = {"name": "test_037", "fields": ["title", "body"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1], d[2]]} for d in docs_037], "queries": [], "skip_word_stats": True}
+for qi, tree, ranker in [(0, ph, "proximity_bm25"), (1, ph, "bm25"), (2, ph, "none"), (3, ph, "wordcount"), (4, ["kw", "test", 1, TITLE], "bm25")]:
+    case["queries"].append({"text": m37[qi]["query"], "tree": tree, "ranker": ranker, "expect": api_expect(m37[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_322 "field weights" (fields title, body, spam; default ranker = proximity_bm25; negative weights)
+# ---------------------------------------------------------------------------------------------
+docs_322 = [(1, "|sample program", "|program flow direct", "|sample program flow"),
+            (2, "|one sample program", "|program rev flow", "|one rev flow"),
+            (3, "|sample two program", "|sub program flow", "|two sub program"),
+            (100, "unsigned", "", "")]
+m322 = model("test_322")
+pf = ["and", ["kw", "program", 1], ["kw", "flow", 2]]
+case = {"name": "test_322", "fields": ["title", "body", "spam"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": list(d[1:])} for d in docs_322], "queries": []}
+for qi, fw, ranker in [(1, [1, 2, 1], "proximity_bm25"), (2, [1, 2, 10], "proximity_bm25"), (3, [1, 2, 10], "wordcount"),
+                       (4, [1, 2, 0], "proximity_bm25"), (5, [1, 2, 0], "wordcount"), (6, [1, 2, -2], "proximity_bm25"),
+                       (7, [1, 2, -10], "proximity_bm25"), (8, [1, 2, -10], "wordcount")]:
+    case["queries"].append({"text": m322[qi]["sphinxql"], "tree": pf, "ranker": ranker, "field_weights": fw, "expect": ql_expect(m322[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_116 "bound cases of the proximity node" (>32 docs per chunk, 532 matches in one doc)
+# ---------------------------------------------------------------------------------------------
+docs_116 = []
+line = ""
+for i in range(10):
+    docs_116.append("a %s b" % line)
+    line += "x "
+docs_116 += ["e x f"] * 510
+docs_116.append("e x f x x x e x f x x e x f x x")
+docs_116.append(" y y i x j" * 532)
+m116 = model("test_116")
+case = {"name": "test_116", "fields": ["title"], "min_word_len": 1,
+        "docs": [{"id": i + 1, "fields": [t]} for i, t in enumerate(docs_116)], "queries": []}
+for qi, tree in [(0, ["prox", 3, [["a", 1], ["b", 2]]]), (1, ["prox", 2, [["e", 1], ["f", 2]]]), (2, ["prox", 2, [["i", 1], ["j", 2]]])]:
+    case["queries"].append({"text": m116[qi]["query"], "tree": tree, "ranker": "wordcount", "limit": 20, "expect": api_expect(m116[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_114 "phrase matching vs hit buffer boundary" (520 phrase hits in one document)
+# ---------------------------------------------------------------------------------------------
+docs_114 = ["aaaa bbbb cccc dddd"] * 510 + ["aaaa bbbb x aaaa bbbb " + " x cccc dddd" * 520]
+m114 = model("test_114")
+case = {"name": "test_114", "fields": ["title"], "min_word_len": 1,
+        "docs": [{"id": i + 1, "fields": [t]} for i, t in enumerate(docs_114)], "queries": []}
+for qi, tree in [(0, ["phrase", [["aaaa", 1], ["bbbb", 2]]]), (1, ["phrase", [["cccc", 1], ["dddd", 2]]])]:
+    case["queries"].append({"text": m114[qi]["query"], "tree": tree, "ranker": "wordcount", "limit": 20, "expect": api_expect(m114[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# RTN.WeightBoundary, src/gtests/gtests_rtstuff.cpp:244-335: 1 doc, `@title cat` -> rowid 0, weight 1500
+# ---------------------------------------------------------------------------------------------
+out["cases"].append({
+    "name": "gtest_RTN_WeightBoundary", "fields": ["title", "content"], "min_word_len": 1,
+    "docs": [{"id": 1, "fields": ["If I were a cat...", "We are the greatest cat"]}],
+    "queries": [{"text": "@title cat", "tree": ["kw", "cat", 1, TITLE], "ranker": "proximity_bm25",
+                 "expect": {"matches": [[1, 1500]], "total_found": 1, "words": {}}}],
+})
+
+with open(os.path.join(HERE, "golden_vectors.json"), "w", encoding="utf-8") as f:
+    json.dump(out, f, ensure_ascii=False, indent=1)
+print("wrote", sum(len(c["queries"]) for c in out["cases"]), "golden queries in", len(out["cases"]), "cases")

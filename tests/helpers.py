@@ -1,0 +1,190 @@
+"""Shared test helpers: oracle FFI, golden-corpus tokenizer, tree builders, result comparison.
+
+The oracle (oracle/liboracle.so) is the CHECKER: it is loaded only here, in the tests.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import manticoresearch_b200.mgpu as M  # noqa: E402
+
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_vectors.json")
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+    return ORACLE_LIB
+
+
+_olib = None
+
+
+def oracle_lib():
+    global _olib
+    if _olib is None:
+        build_oracle()
+        lib = C.CDLL(ORACLE_LIB)
+        lib.oracle_open.restype = C.c_void_p
+        lib.oracle_open.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        lib.oracle_close.argtypes = [C.c_void_p]
+        lib.oracle_total_docs.restype = C.c_int64
+        lib.oracle_total_docs.argtypes = [C.c_void_p]
+        lib.oracle_search_batch.restype = C.c_int
+        lib.oracle_search_batch.argtypes = [C.c_void_p, C.POINTER(M.c_query), C.c_int, C.POINTER(M.c_result)]
+        lib.oracle_decode_doclist.restype = C.c_int
+        lib.oracle_decode_doclist.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                              C.POINTER(C.c_uint64), C.c_int64, C.POINTER(C.c_int64)]
+        lib.oracle_decode_hitlist.restype = C.c_int
+        lib.oracle_decode_hitlist.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_int]
+        lib.oracle_word_stats.restype = C.c_int
+        lib.oracle_word_stats.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        _olib = lib
+    return _olib
+
+
+class OracleIndex:
+    def __init__(self, prefix):
+        self.lib = oracle_lib()
+        err = C.create_string_buffer(512)
+        self.h = self.lib.oracle_open(prefix.encode(), err, 512)
+        if not self.h:
+            raise RuntimeError("oracle_open failed: " + err.value.decode())
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_close(self.h)
+            self.h = None
+
+    @property
+    def total_docs(self):
+        return self.lib.oracle_total_docs(self.h)
+
+    def search(self, queries):
+        arr = M.pack_queries(queries)
+        rs = M.ResultSet(queries)
+        self.lib.oracle_search_batch(self.h, arr, len(queries), rs.results)
+        return rs
+
+    def word_stats(self, word):
+        d, h = C.c_int64(), C.c_int64()
+        if not self.lib.oracle_word_stats(self.h, word.encode("utf-8"), C.byref(d), C.byref(h)):
+            return None
+        return d.value, h.value
+
+    def decode_doclist(self, word):
+        import numpy as np
+        st = self.word_stats(word)
+        if st is None:
+            return None
+        n = st[0]
+        rowid = np.zeros(n, dtype=np.uint32)
+        hits = np.zeros(n, dtype=np.uint32)
+        fields = np.zeros(n, dtype=np.uint32)
+        pos = np.zeros(n, dtype=np.uint64)
+        nout = C.c_int64()
+        self.lib.oracle_decode_doclist(self.h, word.encode("utf-8"), rowid.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       hits.ctypes.data_as(C.POINTER(C.c_uint32)), fields.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       pos.ctypes.data_as(C.POINTER(C.c_uint64)), n, C.byref(nout))
+        assert nout.value == n, (nout.value, n)
+        return rowid, hits, fields, pos
+
+    def decode_hitlist(self, word, hitlist_pos, cap=100000):
+        buf = (C.c_uint32 * cap)()
+        n = self.lib.oracle_decode_hitlist(self.h, word.encode("utf-8"), C.c_uint64(int(hitlist_pos)), buf, cap)
+        return list(buf[:n])
+
+
+# ---------------------------------------------------------------------------------------------
+# golden corpora: whitespace/punctuation tokenizer equivalent to the reference's default charset_table
+# for the ASCII / Cyrillic / CJK-ngram texts the golden tests use
+# ---------------------------------------------------------------------------------------------
+
+def _is_cjk(ch):
+    o = ord(ch)
+    return 0x2E80 <= o <= 0x9FFF or 0xAC00 <= o <= 0xD7AF or 0xF900 <= o <= 0xFAFF
+
+
+def _is_word_char(ch):
+    o = ord(ch)
+    return ch.isascii() and (ch.isalnum() or ch == "_") or 0x410 <= o <= 0x44F
+
+
+def tokenize(text, min_word_len=1):
+    """-> [(keyword, pos)], pos 1-based; overshort tokens consume a position (overshort_step=1)"""
+    out, pos, cur = [], 0, ""
+
+    def flush():
+        nonlocal cur, pos
+        if cur:
+            pos += 1
+            if len(cur) >= min_word_len:
+                out.append((cur, pos))
+            cur = ""
+
+    for ch in text:
+        if _is_cjk(ch):
+            flush()
+            pos += 1
+            out.append((ch, pos))
+        elif _is_word_char(ch):
+            cur += ch.lower()
+        else:
+            flush()
+    flush()
+    return out
+
+
+def tree_to_node(t):
+    kind = t[0]
+    if kind == "kw":
+        n = M.kw(t[1], t[2])
+        if len(t) > 3:
+            n.field_mask = t[3]
+        return n
+    if kind in ("and", "or", "andnot", "maybe"):
+        op = {"and": M.OP_AND, "or": M.OP_OR, "andnot": M.OP_ANDNOT, "maybe": M.OP_MAYBE}[kind]
+        return M.Node(op, children=[tree_to_node(c) for c in t[1:]])
+    if kind == "phrase":
+        n = M.PHRASE([(w, p) for w, p in t[1]])
+        if len(t) > 2:
+            n.field_mask = t[2]
+        return n
+    if kind == "prox":
+        return M.PROXIMITY([(w, p) for w, p in t[2]], t[1])
+    raise ValueError(kind)
+
+
+RANKERS = {"proximity_bm25": M.RANK_PROXIMITY_BM25, "bm25": M.RANK_BM25, "none": M.RANK_NONE, "wordcount": M.RANK_WORDCOUNT}
+
+
+def load_golden():
+    with open(GOLDEN, encoding="utf-8") as f:
+        return json.load(f)["cases"]
+
+
+def build_golden_index(case, prefix):
+    docs = []
+    for d in case["docs"]:
+        docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1)) for t in d["fields"]], "attrs": []})
+    M.build_index(prefix, case["fields"], docs)
+
+
+def golden_query(case, q):
+    return M.Query(tree_to_node(q["tree"]), ranker=RANKERS[q["ranker"]], field_weights=q.get("field_weights"), max_matches=1000)
+
+
+def assert_same_results(a, b, ctx=""):
+    """bit-exact comparison of two ResultSet.get() dicts: ids, integer weights, order, total_found"""
+    assert a["status"] == b["status"], (ctx, a["status"], b["status"])
+    assert a["total_found"] == b["total_found"], (ctx, "total_found", a["total_found"], b["total_found"])
+    assert a["rowid"] == b["rowid"], (ctx, "rowid/order", a["rowid"][:10], b["rowid"][:10])
+    assert a["weight"] == b["weight"], (ctx, "weight", a["weight"][:10], b["weight"][:10])
+    assert a["docid"] == b["docid"], (ctx, "docid")
