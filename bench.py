@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""Benchmark of the full-text query hot path (BASELINE.json metric: queries/sec & compressed-postings GB/s).
+
+A "step" = one pass of the hot path over one batch of synthetic queries:
+  workload = BASELINE.json configs[1]: 10M-doc synthetic Zipfian index, 10k-query batch of 2-8 term AND/OR
+  mixes, SPH_RANK_BM25 with field weights (title=10, body=1), top-100.
+  --gpus N: the SAME index is split into N contiguous rowid-range shards, one per GPU (strong scaling);
+  every rank evaluates the whole batch on its shard, K best keys per query are all-gathered over NCCL
+  and merged on the GPU (global IDF inputs come from the all-reduced per-shard dictionaries).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            # our arm
+  python bench.py --impl reference --gpus 1 ...            # CPU arm: the oracle (the reference cannot be built here)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = ("configs[1]: 10M-doc synthetic Zipfian plain index (seed 0x5EED0001, V=2^20, hit_format=inline, skiplist 32), "
+            "10k-query batch of 2-8 term AND/OR/(a b)|(c d) mixes, SPH_RANK_BM25 field_weights=(title=10,body=1), top-100")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=int(os.environ.get("MGPU_BENCH_DOCS", 10_000_000)))
+    ap.add_argument("--queries", type=int, default=int(os.environ.get("MGPU_BENCH_QUERIES", 10_000)))
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def bench_dir():
+    d = os.environ.get("MGPU_BENCH_DIR")
+    if not d:
+        d = "/tmp/mgpu_bench"
+        try:
+            st = shutil.disk_usage("/dev/shm")
+            if st.free > 24 << 30:
+                d = "/dev/shm/mgpu_bench"
+        except Exception:
+            pass
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def ensure_index(M, total_docs, shard, n_shards):
+    """builds (or reuses) shard `shard` of `n_shards` of the seeded corpus; returns (prefix, first_doc, n_docs, build_seconds)"""
+    first = total_docs * shard // n_shards
+    n = total_docs * (shard + 1) // n_shards - first
+    prefix = os.path.join(bench_dir(), "zipf_%d_%dof%d" % (total_docs, shard, n_shards))
+    t0 = time.time()
+    if not os.path.exists(prefix + ".ok"):
+        M.build_synthetic(prefix, M.SynthParams(n, first_doc=first))
+        open(prefix + ".ok", "w").write("ok")
+    return prefix, first, n, time.time() - t0
+
+
+class ClockSampler:
+    """samples SM clocks / throttle reasons with nvidia-smi during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.samples, self.stop, self.th = gpu_index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per eval_kernel launch from the committed ncu capture of this command, if any"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "eval_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_oracle_qps(prefix, queries, seconds, threads):
+    """oracle (CPU restatement of the reference path) on a bounded sample: one query per thread, striped"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    idx = helpers.OracleIndex(prefix)
+    done = [0] * threads
+    t_end = time.time() + seconds
+    t0 = time.time()
+
+    def work(t):
+        i = t
+        while i < len(queries) and time.time() < t_end:
+            idx.search([queries[i]])
+            done[t] += 1
+            i += threads
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.time() - t0
+    idx.close()
+    n = sum(done)
+    return n / dt if dt > 0 else 0.0, n, dt
+
+
+def run_reference(args):
+    import manticoresearch_b200.mgpu as M
+    from manticoresearch_b200 import workload
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prefix, _, _, _ = ensure_index(M, args.docs, 0, 1)
+    queries = workload.cfg2_queries(n=args.queries, max_matches=100)
+    threads = os.cpu_count() or 1
+    qps_runs = []
+    budget = max(5.0, min(args.cpu_seconds, 60.0))
+    n_done = 0
+    for _ in range(args.warmup and 1):
+        cpu_oracle_qps(prefix, queries[:threads * 2], 5.0, threads)
+    t_all = time.time()
+    for s in range(max(1, args.steps)):
+        qps, n, dt = cpu_oracle_qps(prefix, queries[s * 997 % max(1, len(queries) - threads * 8):], budget / max(1, args.steps), threads)
+        qps_runs.append(qps)
+        n_done += n
+    dt_all = time.time() - t_all
+    value = statistics.mean(qps_runs)
+    line = {
+        "impl": "reference", "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * dt_all / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "docs": args.docs, "queries_per_batch": args.queries, "l2": "inputs >> L2"},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": "%d queries of the same seeded batch, one query per thread, %d threads, %.0f s" % (n_done, threads, dt_all)},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference searchd cannot be built in this image (no bison/flex/boost); this is oracle/oracle.cpp, the CPU restatement of its path",
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import manticoresearch_b200.mgpu as M
+    from manticoresearch_b200 import workload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- index shard of this rank
+    prefix, first_doc, n_docs, build_s = ensure_index(M, args.docs, rank, world)
+    t0 = time.time()
+    index = M.Index(prefix, device=local_rank, rowid_base=first_doc)
+    load_s = time.time() - t0
+    stream = torch.cuda.current_stream()
+    index.set_stream(stream.cuda_stream)
+
+    # ---- queries; global IDF inputs when sharded (CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs)
+    queries = workload.cfg2_queries(n=args.queries, max_matches=100)
+    K = 100
+    if world > 1:
+        words = sorted({k.word for q in queries for k in q.keywords()})
+        df = torch.tensor([(index.word_stats(w) or (0, 0))[0] for w in words], dtype=torch.int64, device=dev)
+        dist.all_reduce(df)
+        gdf = dict(zip(words, df.tolist()))
+        for q in queries:
+            q.total_docs = args.docs
+            q.word_docs = [gdf[k.word] for k in q.keywords()]
+
+    nq = len(queries)
+    keys = torch.zeros((nq, K, 2), dtype=torch.int64, device=dev)
+    counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
+    totals = torch.zeros((nq,), dtype=torch.int64, device=dev)
+    if world > 1:
+        all_keys = torch.zeros((world, nq, K, 2), dtype=torch.int64, device=dev)
+        all_counts = torch.zeros((world, nq), dtype=torch.int32, device=dev)
+        out_keys = torch.zeros((nq, K, 2), dtype=torch.int64, device=dev)
+        out_counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
+    lib = M.lib()
+
+    def merge_step(batch):
+        """local top-K keys -> NCCL all-gather -> GPU merge; total_found via all-reduce"""
+        batch.export_keys(keys.data_ptr(), counts.data_ptr(), totals.data_ptr(), K)
+        dist.all_gather_into_tensor(all_keys, keys)
+        dist.all_gather_into_tensor(all_counts, counts)
+        dist.all_reduce(totals)
+        rc = lib.mgpu_merge_shard_keys(local_rank, all_keys.data_ptr(), all_counts.data_ptr(), world, nq, K,
+                                       out_keys.data_ptr(), out_counts.data_ptr(), stream.cuda_stream)
+        assert rc == 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: plan uploaded once, K steps of (eval + merge [+ shard merge])
+    batch = index.prepare(queries)
+    for _ in range(args.warmup):
+        batch.run()
+        if world > 1:
+            merge_step(batch)
+    barrier()
+    eval_ms, merge_ms = [], []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            batch.run()
+            if world > 1:
+                merge_step(batch)
+            else:
+                batch.sync()
+            st = batch.stats()
+            eval_ms.append(st["eval_kernel_ms"])
+            merge_ms.append(st["merge_kernel_ms"])
+        ev1.record(stream)
+        barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    st = batch.stats()
+    n_unsupported = 0
+    if rank == 0:
+        fetched = batch.fetch()
+        n_unsupported = sum(1 for i in range(nq) if fetched.results[i].status != 0)
+
+    # algorithmic bytes / postings of the whole job (all shards)
+    agg = torch.tensor([st["algorithmic_bytes"], st["postings"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg)
+    job_bytes, job_postings = float(agg[0].item()), float(agg[1].item())
+
+    # ---- end to end through the C ABI with host buffers: plan + H2D + kernels + D2H every step
+    barrier()
+    e2e_t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        if world == 1:
+            rs = index.search(queries)          # mgpu_search_batch
+            assert rs.results[0].status == 0
+            b2 = None
+        else:
+            b2 = index.prepare(queries)
+            b2.run()
+            merge_step(b2)
+            host_keys = out_keys.cpu()
+            host_counts = out_counts.cpu()
+            host_totals = totals.cpu()
+            d2h = host_keys.numel() * 8 + host_counts.numel() * 4 + host_totals.numel() * 8
+            h2d = b2.stats()["h2d_bytes"]
+            b2.free()
+    barrier()
+    e2e_s = time.perf_counter() - e2e_t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    if world == 1:
+        b3 = index.prepare(queries)
+        b3.run()
+        b3.fetch()
+        s3 = b3.stats()
+        h2d, d2h = s3["h2d_bytes"], s3["d2h_bytes"]
+        b3.free()
+
+    if rank == 0:
+        qps = nq / (ms_per_step / 1000.0)
+        peak, peak_src = measured_peak()
+        eval_avg_ms = statistics.mean(eval_ms)
+        achieved = st["algorithmic_bytes"] / (eval_avg_ms / 1000.0) / 1e9      # this rank's eval kernel, this rank's bytes
+        line = {
+            "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "docs": args.docs, "queries_per_batch": nq, "parallelism": "rowid-range shards x%d" % world,
+                       "l2": "inputs >> L2 (%.1f GB algorithmic bytes per step)" % (job_bytes / 1e9),
+                       "index_build_s": round(build_s, 1), "index_load_s": round(load_s, 1), "unsupported_queries": n_unsupported},
+            "postings_per_sec": job_postings / (ms_per_step / 1000.0),
+            "compressed_GBps": job_bytes / (ms_per_step / 1000.0) / 1e9,
+            "e2e": {"value": nq / (e2e_s / args.steps), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(args.steps * (st["kernel_launches"] + (1 if world > 1 else 0))),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": st["algorithmic_bytes"], "kernel_ms": eval_avg_ms,
+                         "merge_kernel_ms": statistics.mean(merge_ms), "frac_of_nominal_8TBs": achieved / 8000.0},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cqps, cn, cdt = cpu_oracle_qps(prefix, queries, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": cqps, "unit": "queries/s", "cores": threads, "kind": "port",
+                                    "sample": "%d queries of the same seeded batch, one query per thread, %d threads, %.1f s" % (cn, threads, cdt)}
+        print(json.dumps(line))
+    batch.free()
+    index.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    from __graft_entry__ import build
+    build()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,9 @@ typedef struct mgpu_index mgpu_index;
  * used when packing multi-GPU merge keys. */
 int				mgpu_index_open ( const char * path_prefix, int device, uint32_t rowid_base, mgpu_index ** out );
 void			mgpu_index_close ( mgpu_index * idx );
+/* run this handle's kernels and copies on the caller's CUDA stream (cudaStream_t) instead of the handle's own one,
+ * so that callers can bracket batches with their own events; NULL restores the private stream */
+int				mgpu_index_set_stream ( mgpu_index * idx, void * cuda_stream );
 const char *	mgpu_last_error ( const mgpu_index * idx );   /* idx may be NULL: last open error */
 
 /* index facts (CSphIndex::GetStats, schema), for callers building queries */

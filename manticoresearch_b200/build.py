@@ -41,19 +41,42 @@ def _deps():
     return deps
 
 
+STAMP = LIB + ".stamp"
+
+
+def _digest():
+    import hashlib
+    h = hashlib.sha1()
+    for d in sorted(_deps()):
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """content based (mtimes do not survive the snapshot copy to the GPU box)"""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    return open(STAMP).read().strip() != _digest()
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
+    with open(os.path.join(HERE, "_obj", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)       # several ranks may get here at once
+        if force or needs_build():
+            _build_locked(verbose)
+    return LIB
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     objs = []
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "_obj")
     os.makedirs(objdir, exist_ok=True)
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
@@ -67,11 +90,13 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lpthread"]
+    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB + ".tmp"] + objs + ["-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    os.replace(LIB + ".tmp", LIB)
+    open(STAMP, "w").write(_digest())
     return LIB
 
 

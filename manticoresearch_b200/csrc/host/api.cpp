@@ -50,6 +50,17 @@ void mgpu_index_close ( mgpu_index * idx )
 	delete idx;
 }
 
+int mgpu_index_set_stream ( mgpu_index * idx, void * cuda_stream )
+{
+	if ( !idx )
+		return MGPU_E_BAD_QUERY;
+	std::lock_guard<std::mutex> tGuard ( idx->m_t.m_tLock );
+	cudaSetDevice ( idx->m_t.m_iDevice );
+	cudaStreamSynchronize ( idx->m_t.m_tStream );
+	idx->m_t.m_tStream = cuda_stream ? (cudaStream_t)cuda_stream : idx->m_t.m_tOwnStream;
+	return MGPU_OK;
+}
+
 const char * mgpu_last_error ( const mgpu_index * idx )
 {
 	return idx ? idx->m_t.m_sError.c_str() : g_sLastOpenError.c_str();

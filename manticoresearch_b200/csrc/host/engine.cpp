@@ -66,10 +66,10 @@ int Upload ( DevBuf_T<T> & tDst, const void * pSrc, size_t nBytes, size_t nPadBy
 
 Index_c::~Index_c()
 {
-	if ( m_tStream )
+	if ( m_tOwnStream )
 	{
 		cudaSetDevice ( m_iDevice );
-		cudaStreamDestroy ( m_tStream );
+		cudaStreamDestroy ( m_tOwnStream );
 	}
 }
 
@@ -254,7 +254,8 @@ int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
 	m_tDev.m_bInlineHits = ( m_tHdr.m_eHitFormat==SPH_HIT_FORMAT_INLINE ) ? 1 : 0;
 	m_tDev.m_uRowidBase = uRowidBase;
 
-	CUDA_TRY ( cudaStreamCreateWithFlags ( &m_tStream, cudaStreamNonBlocking ), m_sError );
+	CUDA_TRY ( cudaStreamCreateWithFlags ( &m_tOwnStream, cudaStreamNonBlocking ), m_sError );
+	m_tStream = m_tOwnStream;
 	return MGPU_OK;
 }
 

@@ -61,7 +61,8 @@ public:
 	IndexHeader_t	m_tHdr;
 	int				m_iDevice = 0;
 	uint32_t		m_uRowidBase = 0;
-	cudaStream_t	m_tStream = nullptr;
+	cudaStream_t	m_tStream = nullptr;		///< stream in use (own or caller's)
+	cudaStream_t	m_tOwnStream = nullptr;
 	int				m_nSMs = 148;
 	std::mutex		m_tLock;		///< serialises batches on this handle
 

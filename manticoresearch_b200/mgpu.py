@@ -115,6 +115,7 @@ def load_library(path=None):
         "mgpu_abi_version": (C.c_int, []),
         "mgpu_index_open": (C.c_int, [C.c_char_p, C.c_int, u32, C.POINTER(vp)]),
         "mgpu_index_close": (None, [vp]),
+        "mgpu_index_set_stream": (C.c_int, [vp, vp]),
         "mgpu_last_error": (C.c_char_p, [vp]),
         "mgpu_index_total_docs": (i64, [vp]),
         "mgpu_index_num_fields": (i32, [vp]),
@@ -151,7 +152,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_last_error", "mgpu_index_total_docs",
+    "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_index_set_stream", "mgpu_last_error", "mgpu_index_total_docs",
     "mgpu_index_num_fields", "mgpu_index_field_index", "mgpu_index_attr_index", "mgpu_index_word_stats",
     "mgpu_index_word_bytes", "mgpu_search_batch", "mgpu_batch_prepare", "mgpu_batch_run", "mgpu_batch_sync",
     "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_batch_export_keys",
@@ -375,6 +376,10 @@ class Index:
 
     def _err(self, rc):
         raise MgpuError(rc, (self._lib.mgpu_last_error(self._h) or b"").decode())
+
+    def set_stream(self, cuda_stream_handle):
+        """run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = private stream"""
+        self._lib.mgpu_index_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0))
 
     @property
     def total_docs(self):

@@ -1,0 +1,155 @@
+"""Seeded synthetic query sets over the synthetic Zipfian corpus.
+
+Pure host-side input generation for the tests and bench.py: builds XQNode-shaped trees (mgpu.Node).
+"""
+import bisect
+import math
+import random
+
+from . import mgpu as M
+
+
+class ZipfRanks:
+    """ranks Zipf(s=1)-sampled from [lo, hi] (1-based term ranks)"""
+    def __init__(self, lo, hi):
+        self.lo = lo
+        self.cum = []
+        acc = 0.0
+        for r in range(lo, hi + 1):
+            acc += 1.0 / r
+            self.cum.append(acc)
+
+    def sample(self, rng):
+        x = rng.random() * self.cum[-1]
+        return self.lo + bisect.bisect_left(self.cum, x)
+
+
+def _kw(rank, pos):
+    return M.kw(M.synth_keyword(rank - 1), pos)
+
+
+def distinct_ranks(rng, sampler, n):
+    seen = []
+    while len(seen) < n:
+        r = sampler.sample(rng)
+        if r not in seen:
+            seen.append(r)
+    return seen
+
+
+def cfg1_queries(n=1000, seed=0x5EED0002, max_matches=1000, ranker=M.RANK_PROXIMITY_BM25):
+    """two-term AND, terms from rank bands [10,100] x [100,10000]"""
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        a = rng.randint(10, 100)
+        b = int(math.exp(rng.uniform(math.log(100), math.log(10000))))
+        out.append(M.Query(M.AND(_kw(a, 1), _kw(b, 2)), ranker=ranker, max_matches=max_matches))
+    return out
+
+
+def cfg2_queries(n=10000, seed=0x5EED0002, max_rank=100000, max_matches=100, with_andnot=0.0):
+    """2-8 terms; 50% pure AND, 30% pure OR, 20% (a b)|(c d) mixes; SPH_RANK_BM25, field_weights=(title=10, body=1)"""
+    rng = random.Random(seed)
+    sampler = ZipfRanks(1, max_rank)
+    out = []
+    for _ in range(n):
+        x = rng.random()
+        nterms = rng.randint(2, 8)
+        ranks = distinct_ranks(rng, sampler, nterms)
+        leaves = [_kw(r, i + 1) for i, r in enumerate(ranks)]
+        if with_andnot and x < with_andnot and nterms >= 3:
+            root = M.ANDNOT(M.AND(*leaves[:-1]) if nterms > 2 else leaves[0], leaves[-1])
+        elif x < 0.5 + with_andnot * 0.5:
+            root = M.AND(*leaves)
+        elif x < 0.8:
+            root = M.OR(*leaves)
+        else:
+            if nterms < 4:
+                ranks = distinct_ranks(rng, sampler, 4)
+                leaves = [_kw(r, i + 1) for i, r in enumerate(ranks)]
+            h = len(leaves) // 2
+            root = M.OR(M.AND(*leaves[:h]), M.AND(*leaves[h:]))
+        out.append(M.Query(root, ranker=M.RANK_BM25, field_weights=[10, 1], max_matches=max_matches))
+    return out
+
+
+def cfg3_queries(params, n=2000, seed=0x5EED0002, max_matches=1000):
+    """50% 2-3 word phrases sampled from adjacent tokens of random docs, 50% "a b c"~5 with words co-occurring within 8 positions"""
+    rng = random.Random(seed)
+    out = []
+    ndocs = params.n_docs
+    while len(out) < n:
+        doc = params.first_doc + rng.randrange(ndocs)
+        blen = M.synth_field_len(params, doc, 1)
+        if blen < 12:
+            continue
+        if len(out) % 2 == 0:
+            k = rng.randint(2, 3)
+            p0 = rng.randrange(blen - k)
+            terms = [M.synth_token(params, doc, 1, p0 + i) for i in range(k)]
+            if len(set(terms)) != k:
+                continue
+            node = M.PHRASE([(M.synth_keyword(t), i + 1) for i, t in enumerate(terms)])
+        else:
+            p0 = rng.randrange(blen - 8)
+            offs = sorted(rng.sample(range(8), 3))
+            terms = [M.synth_token(params, doc, 1, p0 + o) for o in offs]
+            if len(set(terms)) != 3:
+                continue
+            node = M.PROXIMITY([(M.synth_keyword(t), i + 1) for i, t in enumerate(terms)], 5)
+        out.append(M.Query(node, ranker=M.RANK_PROXIMITY_BM25, max_matches=max_matches))
+    return out
+
+
+def cfg5_queries(index, n=500, seed=0x5EED0002, max_matches=10000):
+    """3-6 term OR from ranks [1,50] + gid BETWEEN 100 AND 299 + ORDER BY ts DESC"""
+    rng = random.Random(seed)
+    gid, ts = index.attr_index("gid"), index.attr_index("ts")
+    out = []
+    for _ in range(n):
+        ranks = rng.sample(range(1, 51), rng.randint(3, 6))
+        root = M.OR(*[_kw(r, i + 1) for i, r in enumerate(ranks)])
+        out.append(M.Query(root, ranker=M.RANK_BM25, max_matches=max_matches,
+                           sort_keys=[M.SortKey(M.KEYPART_INT, ts, True)], filters=[M.Filter(gid, 100, 299)]))
+    return out
+
+
+def random_boolean_queries(n, seed, max_rank=20000, nfields=2, rankers=(M.RANK_BM25, M.RANK_NONE), max_matches=50):
+    """parity fuzz set: random trees over AND/OR/ANDNOT/MAYBE with field limits, weights, boosts, missing words"""
+    rng = random.Random(seed)
+    sampler = ZipfRanks(1, max_rank)
+    out = []
+    for qi in range(n):
+        pos = [0]
+
+        def leaf():
+            pos[0] += 1
+            r = sampler.sample(rng)
+            word = M.synth_keyword(r - 1) if rng.random() > 0.03 else "zzmissing%d" % r
+            node = M.kw(word, pos[0], boost=rng.choice([1.0, 1.0, 1.0, 2.0, 0.5]))
+            u = rng.random()
+            if u < 0.15:
+                node.field_mask = 1
+            elif u < 0.3:
+                node.field_mask = 2
+            return node
+
+        def tree(depth):
+            u = rng.random()
+            if depth >= 2 or u < 0.25:
+                return leaf()
+            k = rng.randint(2, 4)
+            if u < 0.55:
+                return M.AND(*[tree(depth + 1) if rng.random() < 0.3 else leaf() for _ in range(k)])
+            if u < 0.85:
+                return M.OR(*[tree(depth + 1) if rng.random() < 0.3 else leaf() for _ in range(k)])
+            if u < 0.95:
+                return M.ANDNOT(tree(depth + 1), leaf() if rng.random() < 0.7 else tree(depth + 1))
+            return M.MAYBE(tree(depth + 1), leaf())
+
+        root = tree(0)
+        fw = [rng.choice([1, 1, 2, 10, 0, -3]) for _ in range(nfields)] if rng.random() < 0.5 else None
+        out.append(M.Query(root, ranker=rng.choice(rankers), field_weights=fw, max_matches=rng.choice([1, 7, max_matches, 1000]),
+                           index_weight=rng.choice([1, 1, 1, 3])))
+    return out

@@ -1,0 +1,172 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar: bit-exact matched rowids, integer weights, order (ties by rowid) and total_found.
+Run on the B200 box with:  python -m pytest tests -m gpu
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import manticoresearch_b200.mgpu as M
+from manticoresearch_b200 import workload
+
+pytestmark = pytest.mark.gpu
+
+N_DOCS = 200_000
+
+
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory):
+    base = tmp_path_factory.mktemp("synth")
+    prefix = str(base / "s200k")
+    params = M.SynthParams(N_DOCS)
+    M.build_synthetic(prefix, params)
+    gpu = M.Index(prefix, device=0)
+    cpu = helpers.OracleIndex(prefix)
+    yield {"prefix": prefix, "params": params, "gpu": gpu, "cpu": cpu}
+    gpu.close()
+    cpu.close()
+
+
+def _compare_batch(synth, queries, allow_unsupported=0.0):
+    g = synth["gpu"].search(queries)
+    c = synth["cpu"].search(queries)
+    unsupported = 0
+    for i in range(len(queries)):
+        a, b = g.get(i), c.get(i)
+        if a["status"] == M.MGPU_E_UNSUPPORTED:
+            unsupported += 1
+            continue
+        helpers.assert_same_results(a, b, ctx="query %d" % i)
+    assert unsupported <= allow_unsupported * len(queries), "too many unsupported queries: %d" % unsupported
+    return unsupported
+
+
+def test_library_is_native_cuda():
+    lib = M.lib()
+    assert lib.mgpu_abi_version() == 1
+
+
+@pytest.mark.parametrize("word", ["t0000001", "t0000002", "t0000010", "t0000100", "t0001000", "t0010000", "t0100000", "t0500000"])
+def test_decode_doclist_matches_oracle(synth, word):
+    """K1: warp-per-block VByte decode == DiskIndexQword_c::ReadNext for every posting (rowid, hits, fields, hitlist pos)"""
+    exp = synth["cpu"].decode_doclist(word)
+    got = synth["gpu"].decode_doclist(word)
+    if exp is None:
+        assert got is None
+        return
+    for name, e, g in zip(("rowid", "hits", "fields", "hitlist_pos"), exp, got):
+        assert np.array_equal(e, g), (word, name, int(np.argmax(e != g)) if len(e) else -1)
+
+
+def test_decode_doclist_block_boundaries(synth):
+    """terms whose df straddles the 32-doc block size (short lists have no skiplist at all)"""
+    cpu, gpu = synth["cpu"], synth["gpu"]
+    seen = set()
+    for t in range(1000, 400000, 37):
+        w = M.synth_keyword(t)
+        st = cpu.word_stats(w)
+        if st is None:
+            continue
+        df = st[0]
+        bucket = df if df <= 70 else None
+        if bucket is None or bucket in seen:
+            continue
+        seen.add(bucket)
+        exp, got = cpu.decode_doclist(w), gpu.decode_doclist(w)
+        for e, g in zip(exp, got):
+            assert np.array_equal(e, g), (w, df)
+    assert {1, 31, 32, 33, 64}.issubset(seen) or len(seen) > 40
+
+
+def test_cfg2_mix_bm25(synth):
+    """config 2 query mix (2-8 term AND / OR / (a b)|(c d)), SPH_RANK_BM25 with field weights, top-100"""
+    queries = workload.cfg2_queries(n=300, max_rank=50000, max_matches=100)
+    _compare_batch(synth, queries)
+
+
+def test_cfg4_mix_with_andnot(synth):
+    queries = workload.cfg2_queries(n=200, seed=77, max_rank=50000, max_matches=1000, with_andnot=0.2)
+    _compare_batch(synth, queries)
+
+
+def test_random_boolean_trees(synth):
+    """fuzz: random AND/OR/ANDNOT/MAYBE trees, field limits, boosts, negative/zero weights, missing words, index weights"""
+    queries = workload.random_boolean_queries(400, seed=1234)
+    _compare_batch(synth, queries, allow_unsupported=0.1)
+
+
+def test_rank_none_and_single_word(synth):
+    qs = [M.Query(M.kw("t0000005", 1), ranker=M.RANK_NONE, max_matches=10),
+          M.Query(M.kw("t0000005", 1), ranker=M.RANK_BM25, max_matches=10),
+          M.Query(M.kw("t0000005", 1), ranker=M.RANK_PROXIMITY_BM25, max_matches=10),   # single word -> WeightSum ranker
+          M.Query(M.kw("nosuchword", 1), ranker=M.RANK_BM25, max_matches=10),
+          M.Query(M.AND(M.kw("nosuchword", 1), M.kw("t0000005", 2)), ranker=M.RANK_BM25, max_matches=10)]
+    _compare_batch(synth, qs)
+
+
+def test_stopword_or_filter_sort_topk(synth):
+    """config 5 shape: stop-word ORs + gid range filter + ORDER BY ts DESC, sorter-bound top-10k"""
+    queries = workload.cfg5_queries(synth["gpu"], n=12, max_matches=10000)
+    g = synth["gpu"].search(queries)
+    c = synth["cpu"].search(queries)
+    for i in range(len(queries)):
+        a, b = g.get(i), c.get(i)
+        helpers.assert_same_results(a, b, ctx="cfg5 %d" % i)
+        assert a["sort_attr"] == b["sort_attr"]
+        assert a["sort_attr"] == sorted(a["sort_attr"], reverse=True)
+
+
+def test_values_filter_and_asc_sort(synth):
+    gpu = synth["gpu"]
+    gid, ts = gpu.attr_index("gid"), gpu.attr_index("ts")
+    root = M.OR(M.kw("t0000003", 1), M.kw("t0000050", 2))
+    qs = [M.Query(root, ranker=M.RANK_BM25, max_matches=200, filters=[M.Filter(gid, values=[5, 17, 900])],
+                  sort_keys=[M.SortKey(M.KEYPART_INT, ts, False), M.SortKey(M.KEYPART_WEIGHT, 0, True)]),
+          M.Query(root, ranker=M.RANK_BM25, max_matches=200, filters=[M.Filter(gid, 0, 499, exclude=True)],
+                  sort_keys=[M.SortKey(M.KEYPART_WEIGHT, 0, False), M.SortKey(M.KEYPART_INT, gid, True)]),
+          M.Query(root, ranker=M.RANK_BM25, max_matches=50, sort_keys=[M.SortKey(M.KEYPART_ROWID, 0, True)])]
+    _compare_batch(synth, qs)
+
+
+def test_golden_vectors_on_gpu(golden_cases, golden_indexes):
+    """the reference's own golden results, for every golden query the CUDA path supports"""
+    ran = 0
+    for case in golden_cases:
+        gpu = M.Index(golden_indexes[case["name"]], device=0)
+        try:
+            for q in case["queries"]:
+                query = helpers.golden_query(case, q)
+                r = gpu.search([query]).get(0)
+                if r["status"] == M.MGPU_E_UNSUPPORTED:
+                    continue
+                ran += 1
+                got = list(zip(r["docid"], r["weight"]))
+                if q.get("limit"):
+                    got = got[:q["limit"]]
+                assert got == [tuple(m) for m in q["expect"]["matches"]], (case["name"], q["text"])
+                assert r["total_found"] == q["expect"]["total_found"]
+        finally:
+            gpu.close()
+    assert ran >= 8
+
+
+def test_full_size_properties(synth):
+    """size-independent properties: AND subset of OR, total_found additivity over disjoint filters, idempotence"""
+    gpu = synth["gpu"]
+    a, b = M.kw("t0000004", 1), M.kw("t0000009", 2)
+    gid = gpu.attr_index("gid")
+    q_and = M.Query(M.AND(a, b), ranker=M.RANK_BM25, max_matches=1000)
+    q_or = M.Query(M.OR(M.kw("t0000004", 1), M.kw("t0000009", 2)), ranker=M.RANK_BM25, max_matches=1000)
+    q_lo = M.Query(M.OR(M.kw("t0000004", 1), M.kw("t0000009", 2)), ranker=M.RANK_BM25, max_matches=10, filters=[M.Filter(gid, 0, 499)])
+    q_hi = M.Query(M.OR(M.kw("t0000004", 1), M.kw("t0000009", 2)), ranker=M.RANK_BM25, max_matches=10, filters=[M.Filter(gid, 500, 999)])
+    rs = gpu.search([q_and, q_or, q_lo, q_hi, q_or])
+    r_and, r_or, r_lo, r_hi, r_or2 = (rs.get(i) for i in range(5))
+    da, db = gpu.word_stats("t0000004")[0], gpu.word_stats("t0000009")[0]
+    assert r_and["total_found"] + r_or["total_found"] == da + db     # |A and B| + |A or B| = |A| + |B|
+    assert r_lo["total_found"] + r_hi["total_found"] == r_or["total_found"]
+    assert r_or == r_or2
+    w = r_or["weight"]
+    assert all(w[i] > w[i + 1] or (w[i] == w[i + 1] and r_or["rowid"][i] < r_or["rowid"][i + 1]) for i in range(len(w) - 1))

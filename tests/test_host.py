@@ -1,0 +1,113 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/mgpu.h declares, fails loudly
+without a GPU, and the index writer's bytes round-trip through the (independent) oracle reader."""
+import ctypes as C
+import os
+import re
+import struct
+
+import pytest
+
+import helpers
+import manticoresearch_b200.mgpu as M
+from conftest import has_gpu
+
+ROOT = helpers.ROOT
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "mgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgpu_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = M.lib()
+    declared = _declared_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libmgpu.so does not export %s" % name
+    assert sorted(M.EXPORTED_SYMBOLS) == declared
+    assert lib.mgpu_abi_version() == 1
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_open_fails_loudly_without_gpu(golden_indexes):
+    with pytest.raises(M.MgpuError) as e:
+        M.Index(golden_indexes["test_019"])
+    assert e.value.code == M.MGPU_E_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_header_is_format_v62(golden_indexes):
+    raw = open(golden_indexes["test_019"] + ".sph", "rb").read()
+    magic, version, nfields = struct.unpack_from("<III", raw, 0)
+    assert magic == 0x58485053 and version == 62 and nfields == 2
+    for ext in ("spd", "spp", "spe", "spi"):
+        assert open(golden_indexes["test_019"] + "." + ext, "rb").read(1) == b"\x01"   # dummy first byte, src/sphinx.cpp:8404-8409
+
+
+def test_synthetic_index_roundtrip(tmp_path):
+    """every posting the oracle decodes from the written files equals the corpus definition"""
+    prefix = str(tmp_path / "rt")
+    p = M.SynthParams(3000, vocab=5000, threads=3)
+    M.build_synthetic(prefix, p)
+    # ground truth straight from the corpus definition
+    postings = {}
+    for d in range(3000):
+        for f in range(2):
+            n = M.synth_field_len(p, d, f)
+            for k in range(n):
+                t = M.synth_token(p, d, f, k)
+                postings.setdefault(t, {}).setdefault(d, []).append((f << 24) | (k + 1) | ((1 << 23) if k == n - 1 else 0))
+    idx = helpers.OracleIndex(prefix)
+    try:
+        assert idx.total_docs == 3000
+        for t in list(range(0, 60)) + list(range(100, 5000, 97)):
+            w = M.synth_keyword(t)
+            exp = postings.get(t)
+            got = idx.decode_doclist(w)
+            if exp is None:
+                assert got is None
+                continue
+            rowid, hits, fields, pos = got
+            assert list(rowid) == sorted(exp.keys())
+            for i, d in enumerate(sorted(exp.keys())):
+                hl = sorted(exp[d])
+                assert hits[i] == len(hl)
+                fm = 0
+                for h in hl:
+                    fm |= 1 << (h >> 24)
+                assert fields[i] == fm
+                assert idx.decode_hitlist(w, pos[i]) == hl
+    finally:
+        idx.close()
+
+
+def test_same_corpus_any_thread_count(tmp_path):
+    """the parallel builder is deterministic: 1 thread and 5 threads write identical bytes"""
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    M.build_synthetic(a, M.SynthParams(2000, vocab=3000, threads=1))
+    M.build_synthetic(b, M.SynthParams(2000, vocab=3000, threads=5))
+    for ext in ("spd", "spp", "spe", "spi", "spa", "sph"):
+        assert open(a + "." + ext, "rb").read() == open(b + "." + ext, "rb").read(), ext
+
+
+def test_shard_builder_is_a_rowid_range_of_the_corpus(tmp_path):
+    """docs [first_doc, first_doc+n) written as a shard carry the same postings as that range of the full index"""
+    full, shard = str(tmp_path / "full"), str(tmp_path / "shard")
+    M.build_synthetic(full, M.SynthParams(1200, vocab=2000, threads=2))
+    M.build_synthetic(shard, M.SynthParams(500, first_doc=700, vocab=2000, threads=2))
+    fi, si = helpers.OracleIndex(full), helpers.OracleIndex(shard)
+    try:
+        for t in (0, 1, 5, 50, 300, 999):
+            w = M.synth_keyword(t)
+            f, s = fi.decode_doclist(w), si.decode_doclist(w)
+            if f is None:
+                assert s is None
+                continue
+            rows = [(int(r), int(h), int(m)) for r, h, m in zip(f[0], f[1], f[2]) if 700 <= r < 1200]
+            got = [] if s is None else [(int(r) + 700, int(h), int(m)) for r, h, m in zip(s[0], s[1], s[2])]
+            assert rows == got
+    finally:
+        fi.close()
+        si.close()
