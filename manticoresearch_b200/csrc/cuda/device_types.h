@@ -20,8 +20,9 @@ static const int MAX_FILTERS = 4;
 static const int MAX_FILTER_VALUES = 16;
 static const int MAX_FIELDS = 32;
 static const int STAGE_BYTES = 896;		///< per-warp staging: 15 B alignment head + 32 docs * (5+5+5+10) B, rounded up to a multiple of 128
-static const int MAX_PHRASE_WORDS = 16;	///< FSM state bound on the GPU path
+static const int MAX_PHRASE_WORDS = 16;	///< keywords per phrase/proximity node on the GPU path
 static const int MAX_NWAY = 4;			///< phrase/proximity nodes per query
+static const int NWAY_MAX_SPAN = 31;	///< max (last atom pos - first atom pos) of a phrase/proximity node: bounds the FSM state
 
 struct DevIndex_t
 {
@@ -106,8 +107,10 @@ struct DevNWay_t
 	int32_t		m_bProximity;
 	int32_t		m_iOpArg;					///< "..."~N
 	int32_t		m_nWords;
+	int32_t		m_iQLen;					///< last atom pos - first atom pos
 	int32_t		m_dLeaf[MAX_PHRASE_WORDS];	///< leaves in query (atom pos) order
-	int32_t		m_dAtomPos[MAX_PHRASE_WORDS];
+	int32_t		m_dAtomPos[MAX_PHRASE_WORDS+1];
+	int32_t		m_dQposDelta[NWAY_MAX_SPAN+1];	///< FSMphrase_c::m_dQposDelta (src/searchnode.cpp:3884-3899)
 };
 
 struct DevQuery_t
@@ -132,7 +135,8 @@ struct DevQuery_t
 	int32_t		m_bDupes;				///< HasQwordDupes: RankerState_Proximity_fn<*,true>
 	int32_t		m_iFirstItem;			///< first work item of this query
 	int32_t		m_nItems;
-	int32_t		m_iPad[2];
+	int32_t		m_bStateRanker;			///< ExtRanker_State_T: PROXIMITY_BM25 over >1 keyword, WORDCOUNT
+	int32_t		m_iPad;
 };
 
 /// 128-bit match key: hi = packed sort keys (bigger = better), lo = ~rowid:32 | weight:32
@@ -170,6 +174,7 @@ struct EvalParams_t
 	int32_t *				m_pCounter;		///< work-queue head
 	int32_t					m_iKMax;		///< stride of m_pItemKeys
 	int32_t					m_iPad;
+	uint64_t *				m_pHitpos;		///< hit stage only: [gridDim.x][MAX_LEAVES][TILE_W] hitlist position of (leaf, tile slot)
 };
 
 struct MergeParams_t

@@ -1,0 +1,454 @@
+// Hit stage of the fused evaluation kernel (K4/K5/K6): per candidate document, one thread
+//   - streams each emitting keyword's hitlist straight out of .spp (DiskIndexQword_c::GetNextHit,
+//     src/sphinx.cpp:374-388, 479-501; the single inlined hit of the doclist record, :523-530),
+//   - merges the streams in the order the reference's CollectHits() chain produces
+//     (ExtAnd_c/ExtOr_c: IsHitLess, src/searchnode.cpp:2611-2615; ExtMultiAnd_T: MergeHits2/3/N :3098-3181;
+//     inside a phrase/proximity node: CmpAndHitReverse_fn :2618-2624),
+//   - runs the phrase / proximity acceptors (FSMphrase_c::HitFSM :3901-3947, FSMproximity_c::HitFSM :3973-4065),
+//   - feeds the ranker state (RankerState_Proximity_fn::Update/Finalize, src/sphinxsearch.cpp:1351-1437;
+//     RankerState_Wordcount_fn :1620-1643).
+// Everything is a streaming generator: no per-document hit buffer exists, so documents with thousands
+// of hits (test_114, test_116) need no special case.  State lives in per-thread local memory.
+#pragma once
+
+#include "device_types.h"
+#include <stdint.h>
+
+namespace mgpu
+{
+
+static const uint32_t EMIT_NWAY_SHIFT = 16;		///< emitter mask: bits 0..15 plain leaves, 16..19 n-way nodes
+
+/// DiskIndexQword_c hit decoder state
+struct HitCursor_t
+{
+	const uint8_t *	m_p;
+	uint32_t		m_uCur;		///< running hitpos (state 0) or the inlined hit (state 1)
+	int				m_iState;	///< 0 = stream from .spp, 1 = inlined hit pending, 2 = done
+};
+
+__device__ __forceinline__ void SeekHitlist ( HitCursor_t & c, const uint8_t * pSpp, uint64_t uHitlistPos )
+{
+	if ( uHitlistPos>>63 )
+	{
+		c.m_iState = 1;
+		c.m_uCur = (uint32_t)uHitlistPos;
+		c.m_p = nullptr;
+	} else
+	{
+		c.m_iState = 0;
+		c.m_uCur = 0;
+		c.m_p = pSpp + uHitlistPos;
+	}
+}
+
+/// next hit that lies in a queried field (ExtTerm_T::CollectHits, src/searchnode.cpp:1971-2010); 0 = EMPTY_HIT
+__device__ __forceinline__ uint32_t NextHit ( HitCursor_t & c, uint32_t uQueriedFields )
+{
+	while ( true )
+	{
+		uint32_t h;
+		if ( c.m_iState==0 )
+		{
+			uint32_t d = 0, b;
+			do { b = __ldg ( c.m_p++ ); d = ( d<<7 ) + ( b & 0x7f ); } while ( b & 0x80 );
+			if ( !d )
+			{
+				c.m_iState = 2;
+				return 0;
+			}
+			c.m_uCur += d;
+			h = c.m_uCur;
+		} else if ( c.m_iState==1 )
+		{
+			c.m_iState = 2;
+			h = c.m_uCur;
+		} else
+			return 0;
+		const uint32_t f = h>>24;
+		if ( f<32 && ( ( uQueriedFields>>f ) & 1u ) )
+			return h;
+	}
+}
+
+/// one hit as the ranker sees it (ExtHit_t, src/sphinxint.h:725-736)
+struct RankHit_t
+{
+	uint32_t	m_uHitpos;
+	uint32_t	m_uQpos;
+	uint32_t	m_uSpanlen;
+	uint32_t	m_uWeight;
+};
+
+/// acceptor + generator state of one phrase/proximity node
+struct NWayState_t
+{
+	// FSMphrase_c: m_dStates; FSMproximity_c: m_dProx
+	uint32_t	m_dVal[NWAY_MAX_SPAN+2];	///< phrase: expected hitpos-with-field per state; proximity: last position per query word
+	uint8_t		m_dTag[NWAY_MAX_SPAN+2];	///< phrase: m_iTagQword per state
+	int			m_nStates;
+	uint32_t	m_uExpPos, m_uWords;		///< proximity
+	int			m_iMinQindex;
+	RankHit_t	m_tHead;					///< next folded hit (m_uHitpos==0: exhausted)
+	uint32_t	m_uFirstRawHit;				///< raw hit that completed the first match (doc field mask, src/searchnode.cpp:3827-3833)
+	bool		m_bAny;
+};
+
+__device__ __forceinline__ void ResetFSM ( const DevNWay_t & n, NWayState_t & s )
+{
+	s.m_nStates = 0;
+	if ( n.m_bProximity )
+	{
+		s.m_uExpPos = 0;
+		s.m_uWords = 0;
+		s.m_iMinQindex = -1;
+		for ( int i=0; i<=n.m_iQLen; ++i )
+			s.m_dVal[i] = 0xFFFFFFFFu;
+	}
+}
+
+/// FSMphrase_c::HitFSM, src/searchnode.cpp:3901-3947
+__device__ __forceinline__ bool PhraseFSM ( const DevNWay_t & n, NWayState_t & s, uint32_t uHit, int iQpos, RankHit_t & tOut )
+{
+	const uint32_t uHPF = uHit & ~( 1u<<23 );
+	const int iAtom0 = n.m_dAtomPos[0];
+	if ( iQpos==iAtom0 && s.m_nStates<NWAY_MAX_SPAN+2 )
+	{
+		s.m_dTag[s.m_nStates] = 0;
+		s.m_dVal[s.m_nStates] = uHPF + (uint32_t)n.m_dQposDelta[0];
+		++s.m_nStates;
+	}
+	for ( int i=s.m_nStates-1; i>=0; --i )
+	{
+		if ( s.m_dVal[i]<uHPF )
+		{
+			--s.m_nStates;					// RemoveFast
+			s.m_dVal[i] = s.m_dVal[s.m_nStates];
+			s.m_dTag[i] = s.m_dTag[s.m_nStates];
+			continue;
+		}
+		int iTag = s.m_dTag[i];
+		if ( s.m_dVal[i]==uHPF && n.m_dAtomPos[iTag+1]==iQpos )
+		{
+			++iTag;
+			s.m_dTag[i] = (uint8_t)iTag;
+			s.m_dVal[i] = uHPF + (uint32_t)n.m_dQposDelta[iQpos-iAtom0];
+		}
+		if ( iTag==n.m_nWords-1 )
+		{
+			const uint32_t uSpan = (uint32_t)n.m_iQLen;
+			tOut.m_uHitpos = uHPF-uSpan;
+			tOut.m_uQpos = (uint32_t)iAtom0;
+			tOut.m_uSpanlen = uSpan+1;
+			tOut.m_uWeight = (uint32_t)n.m_nWords;
+			s.m_nStates = 0;				// ResetFSM
+			return true;
+		}
+	}
+	return false;
+}
+
+/// FSMproximity_c::HitFSM, src/searchnode.cpp:3973-4065
+__device__ __forceinline__ bool ProximityFSM ( const DevNWay_t & n, NWayState_t & s, uint32_t uHit, int iQpos, RankHit_t & tOut )
+{
+	const int iQindex = iQpos-n.m_dAtomPos[0];
+	const int nProx = n.m_iQLen+1;
+	const uint32_t uQLen = (uint32_t)n.m_iQLen;
+	uint32_t uHPF = uHit & ~( 1u<<23 );
+	if ( s.m_dVal[iQindex]==0xFFFFFFFFu )
+		s.m_uWords++;
+	s.m_dVal[iQindex] = uHPF;
+	if ( uHPF>=s.m_uExpPos || iQindex==s.m_iMinQindex )
+	{
+		s.m_iMinQindex = iQindex;
+		const int iMinPos = (int)( uHPF-uQLen-(uint32_t)n.m_iOpArg );
+		for ( int i=0; i<nProx; ++i )
+			if ( s.m_dVal[i]!=0xFFFFFFFFu )
+			{
+				if ( (int)s.m_dVal[i]<=iMinPos )
+				{
+					s.m_dVal[i] = 0xFFFFFFFFu;
+					s.m_uWords--;
+					continue;
+				}
+				if ( s.m_dVal[i]<uHPF )
+				{
+					s.m_iMinQindex = i;
+					uHPF = s.m_dVal[i];
+				}
+			}
+		s.m_uExpPos = s.m_dVal[s.m_iMinQindex] + uQLen + (uint32_t)n.m_iOpArg;
+	}
+	if ( s.m_uWords!=(uint32_t)n.m_nWords )
+		return false;
+
+	// weight = sum over runs of equal (pos - qindex) of (1 + run length - 1), min 1: sort the deltas (insertion sort, <=32 entries)
+	int dDeltas[NWAY_MAX_SPAN+1];
+	int nDeltas = 0;
+	uint32_t uMax = 0;
+	for ( int i=0; i<nProx; ++i )
+		if ( s.m_dVal[i]!=0xFFFFFFFFu )
+		{
+			int v = (int)( s.m_dVal[i]-(uint32_t)i );
+			int j = nDeltas++;
+			while ( j>0 && dDeltas[j-1]>v )
+			{
+				dDeltas[j] = dDeltas[j-1];
+				--j;
+			}
+			dDeltas[j] = v;
+			uMax = max ( uMax, s.m_dVal[i] );
+		}
+	uint32_t uCurWeight = 0, uWeight = 0;
+	int iLast = -2147483647;
+	for ( int i=0; i<nDeltas; ++i )
+	{
+		if ( dDeltas[i]==iLast )
+			uCurWeight++;
+		else
+		{
+			uWeight += uCurWeight ? ( 1+uCurWeight ) : 0;
+			uCurWeight = 0;
+		}
+		iLast = dDeltas[i];
+	}
+	uWeight += uCurWeight ? ( 1+uCurWeight ) : 0;
+	if ( !uWeight )
+		uWeight = 1;
+
+	const uint32_t uMinPos = s.m_dVal[s.m_iMinQindex];
+	tOut.m_uHitpos = uMinPos;
+	tOut.m_uQpos = (uint32_t)n.m_dAtomPos[0];
+	tOut.m_uSpanlen = uMax-uMinPos+1;
+	tOut.m_uWeight = uWeight;
+
+	s.m_dVal[s.m_iMinQindex] = 0xFFFFFFFFu;
+	s.m_iMinQindex = -1;
+	s.m_uWords--;
+	s.m_uExpPos = 0;
+	return true;
+}
+
+/// per-document hit machinery: cursors of every keyword + the n-way generators
+struct DocHits_t
+{
+	HitCursor_t	m_dCur[MAX_LEAVES];
+	uint32_t	m_dHead[MAX_LEAVES];	///< current filtered hit of each open cursor (0 = exhausted)
+	NWayState_t	m_dNWay[MAX_NWAY];
+};
+
+/// advances n-way node j to its next folded hit (ExtNWay_T::GetDocsChunk inner loop, src/searchnode.cpp:3805-3848):
+/// raw hits of its keywords arrive ordered by (hitpos asc, qpos desc)
+__device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
+{
+	const DevNWay_t & n = q.m_dNWay[j];
+	NWayState_t & s = H.m_dNWay[j];
+	while ( true )
+	{
+		int iBest = -1;
+		uint32_t uBestHit = 0, uBestQpos = 0;
+		for ( int w=0; w<n.m_nWords; ++w )
+		{
+			const int l = n.m_dLeaf[w];
+			const uint32_t h = H.m_dHead[l];
+			if ( !h )
+				continue;
+			const uint32_t uQpos = q.m_dLeaves[l].m_uAtomPos;
+			if ( iBest<0 || h<uBestHit || ( h==uBestHit && uQpos>uBestQpos ) )
+			{
+				iBest = l; uBestHit = h; uBestQpos = uQpos;
+			}
+		}
+		if ( iBest<0 )
+		{
+			s.m_tHead.m_uHitpos = 0;
+			return;
+		}
+		H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields );
+		const bool bEmit = n.m_bProximity
+			? ProximityFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead )
+			: PhraseFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead );
+		if ( bEmit )
+		{
+			if ( !s.m_bAny )
+			{
+				s.m_bAny = true;
+				s.m_uFirstRawHit = uBestHit;
+			}
+			return;
+		}
+	}
+}
+
+/// opens the cursors of n-way node j on the document in tile slot `s` and produces its first folded hit
+__device__ void NWayOpen ( const DevIndex_t & tIdx, const DevQuery_t & q, int j, const uint64_t * pHitpos, int s, DocHits_t & H )
+{
+	const DevNWay_t & n = q.m_dNWay[j];
+	for ( int w=0; w<n.m_nWords; ++w )
+	{
+		const int l = n.m_dLeaf[w];
+		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*TILE_W+s] );
+		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields );
+	}
+	H.m_dNWay[j].m_bAny = false;
+	H.m_dNWay[j].m_uFirstRawHit = 0;
+	ResetFSM ( n, H.m_dNWay[j] );
+	NWayAdvance ( q, j, H );
+}
+
+/// RankerState_Proximity_fn<true,HANDLE_DUPES> + RankerState_Wordcount_fn
+struct RankState_t
+{
+	uint8_t		m_uLCS[MAX_FIELDS];
+	uint8_t		m_uCurLCS;
+	int			m_iExpDelta;
+	int			m_iLastHitPosWithField;
+	uint32_t	m_uLcsTailPos, m_uLcsTailQposMask, m_uCurQposMask, m_uCurPos;
+	uint32_t	m_uWordcount;
+};
+
+__device__ __forceinline__ void RankInit ( RankState_t & r )
+{
+	#pragma unroll
+	for ( int i=0; i<MAX_FIELDS; ++i )
+		r.m_uLCS[i] = 0;
+	r.m_uCurLCS = 0;
+	r.m_iExpDelta = -1;
+	r.m_iLastHitPosWithField = -1;
+	r.m_uLcsTailPos = 0; r.m_uLcsTailQposMask = 0; r.m_uCurQposMask = 0; r.m_uCurPos = 0;
+	r.m_uWordcount = 0;
+}
+
+__device__ __forceinline__ void RankUpdate ( const DevQuery_t & q, RankState_t & r, const RankHit_t & h )
+{
+	const uint32_t uField = h.m_uHitpos>>24;	// <32: hits of other fields never get here
+	if ( q.m_eRanker==3 )
+	{
+		r.m_uWordcount += (uint32_t)q.m_dWeights[uField];	// src/sphinxsearch.cpp:1620-1643
+		return;
+	}
+	if ( !q.m_bDupes )
+	{
+		// src/sphinxsearch.cpp:1357-1367
+		const int iPosWithField = (int)( h.m_uHitpos & ~( 1u<<23 ) );
+		const int iDelta = iPosWithField - (int)h.m_uQpos;
+		if ( iPosWithField>r.m_iLastHitPosWithField )
+			r.m_uCurLCS = (uint8_t)( ( ( iDelta==r.m_iExpDelta ) ? r.m_uCurLCS : 0 ) + (uint8_t)h.m_uWeight );
+		if ( r.m_uCurLCS>r.m_uLCS[uField] )
+			r.m_uLCS[uField] = r.m_uCurLCS;
+		r.m_iLastHitPosWithField = iPosWithField;
+		r.m_iExpDelta = iDelta + (int)h.m_uSpanlen - 1;
+	} else
+	{
+		// src/sphinxsearch.cpp:1370-1411
+		const uint32_t uPos = h.m_uHitpos & ~( 1u<<23 );
+		if ( ( r.m_uCurPos>>24 )!=uField )
+			r.m_uCurQposMask = 0;
+		if ( uPos!=r.m_uCurPos )
+		{
+			if ( r.m_uCurLCS<2 )
+			{
+				r.m_uLcsTailPos = r.m_uCurPos;
+				r.m_uLcsTailQposMask = r.m_uCurQposMask;
+				r.m_uCurLCS = 1;
+			}
+			r.m_uCurQposMask = 0;
+			r.m_uCurPos = uPos;
+			if ( r.m_uLCS[uField]<h.m_uWeight )
+				r.m_uLCS[uField] = (uint8_t)h.m_uWeight;
+		}
+		const uint32_t uQposBit = h.m_uQpos<32 ? ( 1u<<h.m_uQpos ) : 0u;	// (DWORD)(1UL<<qpos)
+		r.m_uCurQposMask |= uQposBit;
+		const int iDelta = (int)( r.m_uCurPos-r.m_uLcsTailPos );
+		if ( iDelta>0 && iDelta<32 && ( ( r.m_uCurQposMask>>iDelta ) & r.m_uLcsTailQposMask ) )
+		{
+			r.m_uLcsTailQposMask = uQposBit;
+			r.m_uLcsTailPos = r.m_uCurPos;
+			r.m_uCurLCS = (uint8_t)( r.m_uCurLCS+h.m_uWeight );
+			r.m_uCurQposMask = 0;
+			if ( r.m_uCurLCS>r.m_uLCS[uField] )
+				r.m_uLCS[uField] = r.m_uCurLCS;
+		}
+	}
+}
+
+/// Streams the document's hits (root CollectHits order) through the ranker state.
+/// uEmit = emitters sitting on this document (plain leaves + n-way nodes). Returns false if the document yields no
+/// hits (ExtRanker_State_T skips it, src/sphinxsearch.cpp:1299-1304); else iWeight = final weight before index weight.
+__device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, uint32_t uEmit, const uint64_t * pHitpos, int s,
+	int iSeedWeight, DocHits_t & H, int & iWeight )
+{
+	uint32_t uLeaves = uEmit & 0xFFFFu;
+	uint32_t uNWays = uEmit>>EMIT_NWAY_SHIFT;
+	for ( uint32_t m=uLeaves; m; m&=m-1 )
+	{
+		const int l = __ffs ( m )-1;
+		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*TILE_W+s] );
+		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields );
+	}
+	for ( uint32_t m=uNWays; m; m&=m-1 )
+		NWayOpen ( tIdx, q, __ffs ( m )-1, pHitpos, s, H );
+
+	RankState_t R;
+	RankInit ( R );
+	bool bAny = false;
+	while ( true )
+	{
+		// k-way merge by (hitpos, qpos); full ties go to the emitter met first in tree order
+		int iBest = -1;
+		uint32_t uBestHit = 0, uBestQpos = 0;
+		for ( uint32_t m=uLeaves; m; m&=m-1 )
+		{
+			const int l = __ffs ( m )-1;
+			const uint32_t h = H.m_dHead[l];
+			if ( !h )
+				continue;
+			const uint32_t uQpos = q.m_dLeaves[l].m_uAtomPos;
+			if ( iBest<0 || h<uBestHit || ( h==uBestHit && uQpos<uBestQpos ) )
+			{
+				iBest = l; uBestHit = h; uBestQpos = uQpos;
+			}
+		}
+		for ( uint32_t m=uNWays; m; m&=m-1 )
+		{
+			const int j = __ffs ( m )-1;
+			const RankHit_t & t = H.m_dNWay[j].m_tHead;
+			if ( !t.m_uHitpos )
+				continue;
+			if ( iBest<0 || t.m_uHitpos<uBestHit || ( t.m_uHitpos==uBestHit && t.m_uQpos<uBestQpos ) )
+			{
+				iBest = MAX_LEAVES+j; uBestHit = t.m_uHitpos; uBestQpos = t.m_uQpos;
+			}
+		}
+		if ( iBest<0 )
+			break;
+		bAny = true;
+		RankHit_t t;
+		if ( iBest<MAX_LEAVES )
+		{
+			t.m_uHitpos = uBestHit; t.m_uQpos = uBestQpos; t.m_uSpanlen = 1; t.m_uWeight = 1;
+			H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields );
+		} else
+		{
+			t = H.m_dNWay[iBest-MAX_LEAVES].m_tHead;
+			NWayAdvance ( q, iBest-MAX_LEAVES, H );
+		}
+		RankUpdate ( q, R, t );
+	}
+	if ( !bAny )
+		return false;
+
+	if ( q.m_eRanker==3 )
+		iWeight = (int)R.m_uWordcount;
+	else
+	{
+		// Finalize, src/sphinxsearch.cpp:1415-1437
+		uint32_t uRank = 0;
+		for ( int i=0; i<q.m_nWeights; ++i )
+			uRank += (uint32_t)R.m_uLCS[i]*(uint32_t)q.m_dWeights[i];
+		iWeight = (int)( (uint32_t)iSeedWeight + uRank*1000u );
+	}
+	return true;
+}
+
+} // namespace mgpu

@@ -14,6 +14,7 @@
 // round-to-nearest intrinsics explicitly (and the file is built with -fmad=false) so that TF*IDF sums
 // are bit-identical to the reference's scalar fp32 code.
 #include "device_types.h"
+#include "hit_stage.cuh"
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -372,20 +373,52 @@ struct EvalShared_t
 	int				m_iItem;
 	int				m_iPoolCnt;
 	int				m_iPoolBuf;
+	int				m_iListCnt;
 	uint16_t		m_dRecStart[EVAL_WARPS][34];
 	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
 };
 
 /// dense doc vectors live in dynamic shared memory: [nStack] x { float tfidf[W]; u32 fields[W]; u8 cnt[W] }
+/// hit stage adds { u32 emit[W] } per level (which keywords / n-way nodes sit on the doc: the CollectHits() recursion,
+/// src/searchnode.cpp:2627-2705, 3516-3545) and one u16 list of compacted candidate slots
 struct Vectors_t
 {
 	float *		m_pTfidf;
 	uint32_t *	m_pFields;
 	uint8_t *	m_pCnt;
+	uint32_t *	m_pEmit;
+	uint16_t *	m_pList;
 	__device__ __forceinline__ float &		Tfidf ( int v, int s )	{ return m_pTfidf[v*TILE_W+s]; }
 	__device__ __forceinline__ uint32_t &	Fields ( int v, int s )	{ return m_pFields[v*TILE_W+s]; }
 	__device__ __forceinline__ uint8_t &	Cnt ( int v, int s )	{ return m_pCnt[v*TILE_W+s]; }
+	__device__ __forceinline__ uint32_t &	Emit ( int v, int s )	{ return m_pEmit[v*TILE_W+s]; }
 };
+
+/// CTA-wide compaction of the slots of v[iVec] whose cnt equals uAlive into V.m_pList; returns the count
+__device__ int CompactAlive ( Vectors_t & V, int iVec, uint8_t uAlive, int nSlots, int * pCount )
+{
+	const int tid = threadIdx.x, iLane = tid & 31;
+	if ( tid==0 )
+		*pCount = 0;
+	__syncthreads();
+	for ( int sBase=0; sBase<nSlots; sBase+=EVAL_THREADS )
+	{
+		const int s = sBase+tid;
+		const bool b = s<nSlots && V.Cnt ( iVec, s )==uAlive;
+		const unsigned m = __ballot_sync ( FULL_MASK, b );
+		if ( m )
+		{
+			int iBase = 0;
+			if ( iLane==0 )
+				iBase = atomicAdd ( pCount, __popc ( m ) );
+			iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
+			if ( b )
+				V.m_pList[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = (uint16_t)s;
+		}
+	}
+	__syncthreads();
+	return *pCount;
+}
 
 __device__ __forceinline__ int64_t LoadAttr ( const DevIndex_t & tIdx, uint32_t uRowid, int iDwordOff, int iBitCount )
 {
@@ -452,6 +485,7 @@ __device__ __forceinline__ Key128_t MakeKey ( const DevIndex_t & tIdx, const Dev
 	return k;
 }
 
+template<bool HITS>
 __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P, int nStack )
 {
 	extern __shared__ __align__(16) uint8_t dDyn[];
@@ -460,7 +494,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 	Vectors_t V;
 	V.m_pTfidf = reinterpret_cast<float *>( dDyn );
 	V.m_pFields = reinterpret_cast<uint32_t *>( dDyn + (size_t)nStack*TILE_W*4 );
-	V.m_pCnt = dDyn + (size_t)nStack*TILE_W*8;
+	V.m_pEmit = reinterpret_cast<uint32_t *>( dDyn + (size_t)nStack*TILE_W*8 );
+	V.m_pList = reinterpret_cast<uint16_t *>( dDyn + (size_t)nStack*TILE_W*( HITS ? 12 : 8 ) );
+	V.m_pCnt = dDyn + (size_t)nStack*TILE_W*( HITS ? 12 : 8 ) + ( HITS ? TILE_W*2 : 0 );
+	uint64_t * pHitpos = HITS ? P.m_pHitpos + (size_t)blockIdx.x*MAX_LEAVES*TILE_W : nullptr;
 
 	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
 	const DevIndex_t & tIdx = P.m_tIndex;
@@ -556,10 +593,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 					const DevLeaf_t & tLeaf = q.m_dLeaves[tOp.m_uLeaf];
 					const uint32_t b1 = S.m_dLeafB1[tOp.m_uLeaf];
 					const uint8_t uAlive = tOp.m_uAliveDst;
+					const uint32_t uEmitBit = 1u<<tOp.m_uLeaf;
 					for ( uint32_t b=S.m_dLeafB0[tOp.m_uLeaf]+iWarp; b<b1; b+=EVAL_WARPS )
 					{
 						DecodedDoc_t tDoc;
-						DecodeBlock<false> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
+						DecodeBlock<HITS> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
 						const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
 						if ( !tDoc.m_bValid || tDoc.m_uRowid<uTileLo || tDoc.m_uRowid>=uTileHi || !uFields )
 							continue;
@@ -567,10 +605,12 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 						// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946
 						const float fHits = __uint2float_rn ( tDoc.m_uHits );
 						const float fTf = __fmul_rn ( __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
+						bool bOn = false;	// the keyword sits on this doc as far as CollectHits() is concerned
 						switch ( tOp.m_eCode )
 						{
 						case OP_TERM_SET:
 							V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = 1;
+							if ( HITS ) { V.Emit ( d, s ) = uEmitBit; bOn = true; }
 							break;
 						case OP_TERM_AND:
 							if ( V.Cnt ( d, s )==uAlive )
@@ -578,6 +618,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
 								V.Fields ( d, s ) |= uFields;
 								V.Cnt ( d, s ) = tOp.m_uAliveOut;
+								if ( HITS ) { V.Emit ( d, s ) |= uEmitBit; bOn = true; }
 							}
 							break;
 						case OP_TERM_OR:
@@ -585,10 +626,13 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							{
 								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
 								V.Fields ( d, s ) |= uFields;
+								if ( HITS ) V.Emit ( d, s ) |= uEmitBit;
 							} else
 							{
 								V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = uAlive;
+								if ( HITS ) V.Emit ( d, s ) = uEmitBit;
 							}
+							bOn = true;
 							break;
 						case OP_TERM_ANDNOT:
 							if ( V.Cnt ( d, s )==uAlive )
@@ -599,8 +643,35 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							{
 								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
 								V.Fields ( d, s ) |= uFields;
+								if ( HITS ) { V.Emit ( d, s ) |= uEmitBit; bOn = true; }
 							}
 							break;
+						}
+						if ( HITS && bOn )
+							pHitpos[(size_t)tOp.m_uLeaf*TILE_W+s] = tDoc.m_uHitlistPos;
+					}
+				} else if ( tOp.m_eCode==OP_NWAY )
+				{
+					// ExtNWay_T::GetDocsChunk, src/searchnode.cpp:3805-3848: candidates = AND of the node's keywords (already in v[dst]);
+					// a candidate survives iff the acceptor emits at least one folded hit
+					if ( HITS )
+					{
+						const int j = tOp.m_uArg;
+						const int n = CompactAlive ( V, d, tOp.m_uAliveDst, TILE_W, &S.m_iListCnt );
+						if ( n )
+							__threadfence_block();	// hitpos scratch written by other warps of this CTA
+						for ( int i=tid; i<n; i+=EVAL_THREADS )
+						{
+							const int s = V.m_pList[i];
+							DocHits_t H;
+							NWayOpen ( tIdx, q, j, pHitpos, s, H );
+							if ( H.m_dNWay[j].m_tHead.m_uHitpos )
+							{
+								V.Fields ( d, s ) = 1u<<( ( H.m_dNWay[j].m_uFirstRawHit>>24 ) & 31u );
+								V.Emit ( d, s ) = 1u<<( EMIT_NWAY_SHIFT+j );
+								V.Cnt ( d, s ) = tOp.m_uAliveOut;
+							} else
+								V.Cnt ( d, s ) = 0;
 						}
 					}
 				} else
@@ -617,6 +688,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							{
 								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), V.Tfidf ( r, s ) );
 								V.Fields ( d, s ) |= V.Fields ( r, s );
+								if ( HITS ) V.Emit ( d, s ) |= V.Emit ( r, s );
 							} else if ( bD )
 								V.Cnt ( d, s ) = 0;
 							break;
@@ -625,9 +697,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							{
 								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), V.Tfidf ( r, s ) );
 								V.Fields ( d, s ) |= V.Fields ( r, s );
+								if ( HITS ) V.Emit ( d, s ) |= V.Emit ( r, s );
 							} else if ( bS )
 							{
 								V.Tfidf ( d, s ) = V.Tfidf ( r, s ); V.Fields ( d, s ) = V.Fields ( r, s ); V.Cnt ( d, s ) = uAd;
+								if ( HITS ) V.Emit ( d, s ) = V.Emit ( r, s );
 							}
 							break;
 						case OP_VEC_ANDNOT:
@@ -639,6 +713,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							{
 								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), V.Tfidf ( r, s ) );
 								V.Fields ( d, s ) |= V.Fields ( r, s );
+								if ( HITS ) V.Emit ( d, s ) |= V.Emit ( r, s );
 							}
 							break;
 						default:
@@ -655,26 +730,43 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 				const Key128_t tThr = S.m_tThr;
 				Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 				const int nSlots = (int)( uTileHi-uTileLo );
-				for ( int sBase=0; sBase<nSlots; sBase+=EVAL_THREADS )
+				// hit-consuming rankers walk a compacted candidate list (one document per thread); the others scan the slots
+				const bool bStateRanker = HITS && q.m_bStateRanker;
+				int nWork = nSlots;
+				if ( bStateRanker )
+					nWork = CompactAlive ( V, 0, uAlive, nSlots, &S.m_iListCnt );
+				for ( int sBase=0; sBase<nWork; sBase+=EVAL_THREADS )
 				{
-					const int s = sBase+tid;
+					int s = sBase+tid;
 					bool bPush = false;
 					Key128_t tKey;
-					if ( s<nSlots && V.Cnt ( 0, s )==uAlive )
+					bool bCand = s<nWork;
+					if ( bCand )
+					{
+						if ( bStateRanker )
+							s = V.m_pList[s];
+						else
+							bCand = V.Cnt ( 0, s )==uAlive;
+					}
+					if ( bCand )
 					{
 						const uint32_t uRowid = uTileLo+s;
 						bool bOk = PassFilters ( tIdx, q, uRowid );
-						if ( bOk && tIdx.m_pDead )
-							bOk = !( ( __ldg ( tIdx.m_pDead+( uRowid>>5 ) )>>( uRowid & 31 ) ) & 1u );
-						if ( bOk )
+						int iWeight = 1;	// ExtRanker_None_c, src/sphinxsearch.cpp:1160
+						if ( bOk && q.m_eRanker!=2 )
 						{
-							int iWeight;
-							if ( q.m_eRanker==2 )
-								iWeight = 1;	// ExtRanker_None_c, src/sphinxsearch.cpp:1160
-							else
+							// seed weight src/sphinxsearch.cpp:1070
+							const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( V.Tfidf ( 0, s ), 0.5f ), 1000.0f ) );
+							if ( bStateRanker )
 							{
-								// seed weight src/sphinxsearch.cpp:1070, ExtRanker_WeightSum_c :1112-1129
-								int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( V.Tfidf ( 0, s ), 0.5f ), 1000.0f ) );
+								if constexpr ( HITS )
+								{
+									DocHits_t H;
+									bOk = RankDocByHits ( tIdx, q, V.Emit ( 0, s ), pHitpos, s, iSeed, H, iWeight );
+								}
+							} else
+							{
+								// ExtRanker_WeightSum_c :1112-1129
 								uint32_t uMask = V.Fields ( 0, s );
 								uint32_t uRank = 0;
 								if ( !uMask )
@@ -685,7 +777,12 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 											uRank += (uint32_t)q.m_dWeights[i];
 								iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
 							}
-							iWeight *= q.m_iIndexWeight;
+						}
+						if ( bOk && tIdx.m_pDead )
+							bOk = !( ( __ldg ( tIdx.m_pDead+( uRowid>>5 ) )>>( uRowid & 31 ) ) & 1u );
+						if ( bOk )
+						{
+							iWeight = (int)( (uint32_t)iWeight*(uint32_t)q.m_iIndexWeight );
 							++iMyTotal;
 							tKey = MakeKey ( tIdx, q, uRowid, iWeight );
 							bPush = !KeyLess ( tKey, tThr );
@@ -901,27 +998,41 @@ __global__ void __launch_bounds__ ( 256 ) shard_merge_kernel ( const Key128_t * 
 // host-callable launchers (engine.cpp is plain C++ and never sees <<< >>>)
 //////////////////////////////////////////////////////////////////////////
 
-size_t EvalDynSmemBytes ( int nStack )
+size_t EvalDynSmemBytes ( int nStack, bool bHits )
 {
-	return (size_t)nStack*TILE_W*9;
+	return bHits ? (size_t)nStack*TILE_W*13 + (size_t)TILE_W*2 : (size_t)nStack*TILE_W*9;
 }
 
-cudaError_t LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream )
+cudaError_t LaunchEval ( const EvalParams_t & P, int nStack, bool bHits, int nCtas, cudaStream_t tStream )
 {
-	size_t iDyn = EvalDynSmemBytes ( nStack );
-	cudaError_t e = cudaFuncSetAttribute ( eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	size_t iDyn = EvalDynSmemBytes ( nStack, bHits );
+	cudaError_t e = bHits
+		? cudaFuncSetAttribute ( eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn )
+		: cudaFuncSetAttribute ( eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
 	if ( e!=cudaSuccess )
 		return e;
-	eval_kernel<<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
+	if ( bHits )
+		eval_kernel<true><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
+	else
+		eval_kernel<false><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
 	return cudaGetLastError();
 }
 
-int EvalOccupancy ( int nStack )
+int EvalOccupancy ( int nStack, bool bHits )
 {
 	int n = 0;
-	size_t iDyn = EvalDynSmemBytes ( nStack );
-	cudaFuncSetAttribute ( eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-	if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel, EVAL_THREADS, iDyn )!=cudaSuccess )
+	size_t iDyn = EvalDynSmemBytes ( nStack, bHits );
+	cudaError_t e;
+	if ( bHits )
+	{
+		cudaFuncSetAttribute ( eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel<true>, EVAL_THREADS, iDyn );
+	} else
+	{
+		cudaFuncSetAttribute ( eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel<false>, EVAL_THREADS, iDyn );
+	}
+	if ( e!=cudaSuccess )
 		return 1;
 	return n>0 ? n : 1;
 }

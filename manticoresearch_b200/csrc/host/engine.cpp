@@ -358,7 +358,7 @@ struct Planner_c
 			}
 			if ( tNode.op!=MGPU_OP_PHRASE && tNode.op!=MGPU_OP_PROXIMITY )
 				return Fail ( MGPU_E_UNSUPPORTED );
-			return Fail ( MGPU_E_UNSUPPORTED );	// phrase/proximity: hit-stage kernel (K4/K5) not wired yet
+			return CreateMultiNode ( tNode );
 		}
 		const int nChildren = tNode.n_children;
 		if ( nChildren<1 )
@@ -418,6 +418,47 @@ struct Planner_c
 		return iCur;
 	}
 
+	/// CreateMultiNode<ExtPhrase_c|ExtProximity_c> (plain keywords branch, src/searchnode.cpp:986-1042) + ExtNWay_T::ConstructNode (:3767-3802):
+	/// an AND chain over the keywords sorted by doc count, then the acceptor over their merged hits
+	int CreateMultiNode ( const mgpu_xqnode & tNode )
+	{
+		DevQuery_t & d = m_tOut.m_tDev;
+		if ( d.m_nNWay>=MAX_NWAY || tNode.n_words>MAX_PHRASE_WORDS )
+			return Fail ( MGPU_E_UNSUPPORTED );
+		if ( tNode.first_word<0 || tNode.first_word+tNode.n_words>m_q.n_words )
+			return Fail ( MGPU_E_BAD_QUERY );
+		PNode_t t;
+		t.m_eKind = PN_NWAY;
+		t.m_iNWay = d.m_nNWay;
+		DevNWay_t & n = d.m_dNWay[d.m_nNWay++];
+		n.m_bProximity = ( tNode.op==MGPU_OP_PROXIMITY );
+		n.m_iOpArg = tNode.oparg;
+		n.m_nWords = tNode.n_words;
+		for ( int i=0; i<tNode.n_words; ++i )
+		{
+			int iLeaf = AddLeaf ( tNode, tNode.first_word+i, i );
+			if ( iLeaf<0 )
+				return -1;
+			t.m_dLeaves.push_back ( iLeaf );
+			n.m_dLeaf[i] = iLeaf;
+			n.m_dAtomPos[i] = m_dLeaves[iLeaf].m_iAtomPos;
+			if ( i && n.m_dAtomPos[i]<=n.m_dAtomPos[i-1] )
+				return Fail ( MGPU_E_BAD_QUERY );
+		}
+		n.m_dAtomPos[tNode.n_words] = -1;
+		n.m_iQLen = n.m_dAtomPos[tNode.n_words-1]-n.m_dAtomPos[0];
+		if ( n.m_iQLen>NWAY_MAX_SPAN || n.m_dAtomPos[0]<0 || n.m_dAtomPos[tNode.n_words-1]>0xFFFF )
+			return Fail ( MGPU_E_UNSUPPORTED );
+		// FSMphrase_c ctor, src/searchnode.cpp:3884-3899
+		for ( int i=0; i<=NWAY_MAX_SPAN; ++i )
+			n.m_dQposDelta[i] = -INT_MAX;
+		for ( int i=1; i<tNode.n_words; ++i )
+			n.m_dQposDelta [ n.m_dAtomPos[i-1]-n.m_dAtomPos[0] ] = n.m_dAtomPos[i]-n.m_dAtomPos[i-1];
+		// chain order: by doc count (sphSort over positions, :3800)
+		RefSort ( t.m_dLeaves, [this] ( int a, int b ) { return m_dLeaves[a].Docs()<m_dLeaves[b].Docs(); } );
+		return NewNode ( t );
+	}
+
 	/// ExtNode_i::GetQwords in eval-tree order (src/searchnode.cpp:2030-2057, 3244-3253, ExtTwofer_c)
 	void GetQwords ( int iNode )
 	{
@@ -458,11 +499,14 @@ struct Planner_c
 			AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_iLeaf, 1 );
 			return 1;
 		case PN_MULTIAND:
+		case PN_NWAY:
 			{
 				AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_dLeaves[0], 1 );
 				int iAlive = 1;
 				for ( size_t i=1; i<t.m_dLeaves.size(); ++i, ++iAlive )
 					AddOp ( OP_TERM_AND, iSp, 0, iAlive, 0, t.m_dLeaves[i], iAlive+1 );
+				if ( t.m_eKind==PN_NWAY )
+					AddOp ( OP_NWAY, iSp, 0, iAlive, 0, 0, iAlive, t.m_iNWay );
 				return iAlive;
 			}
 		default:
@@ -487,7 +531,7 @@ struct Planner_c
 		}
 	}
 
-	void AddOp ( int eCode, int iDst, int iSrc, int iAliveDst, int iAliveSrc, int iLeaf, int iAliveOut )
+	void AddOp ( int eCode, int iDst, int iSrc, int iAliveDst, int iAliveSrc, int iLeaf, int iAliveOut, int iArg=0 )
 	{
 		if ( m_tOut.m_tDev.m_nOps>=MAX_OPS || iAliveOut>250 )
 		{
@@ -501,7 +545,7 @@ struct Planner_c
 		o.m_uAliveDst = (uint8_t)iAliveDst;
 		o.m_uAliveSrc = (uint8_t)iAliveSrc;
 		o.m_uLeaf = (uint8_t)iLeaf;
-		o.m_uArg = 0;
+		o.m_uArg = (uint8_t)iArg;
 		o.m_uAliveOut = (uint8_t)iAliveOut;
 	}
 
@@ -534,10 +578,17 @@ struct Planner_c
 		int eRanker = m_q.ranker;
 		if ( eRanker==MGPU_RANK_PROXIMITY_BM25 && bSingleWord )
 			eRanker = MGPU_RANK_BM25;	// ExtRanker_WeightSum_c<WITH_BM25>
-		if ( eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_WORDCOUNT )
-			return MGPU_E_UNSUPPORTED;	// hit-consuming rankers: stage 2 kernel
 		d.m_eRanker = eRanker;
-		const bool bUseBM25 = ( eRanker==MGPU_RANK_BM25 );
+		d.m_bStateRanker = ( eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_WORDCOUNT ) ? 1 : 0;	// ExtRanker_State_T
+		d.m_bNeedHits = ( d.m_bStateRanker || d.m_nNWay>0 ) ? 1 : 0;
+		const bool bUseBM25 = ( eRanker==MGPU_RANK_BM25 || eRanker==MGPU_RANK_PROXIMITY_BM25 );
+		{
+			// HasQwordDupes, src/sphinxsearch.cpp:4148-4164
+			std::unordered_map<std::string,int> hSeen;
+			for ( int i=0; i<m_q.n_words; ++i )
+				if ( m_q.words[i].word && !hSeen.emplace ( m_q.words[i].word, 1 ).second )
+					d.m_bDupes = 1;
+		}
 
 		if ( iRoot>=0 )
 		{
@@ -714,72 +765,81 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	for ( int i=0; i<nQueries; ++i )
 		PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
 
-	// runnable queries, biggest first (items are handed out in array order: longest-processing-time-first)
-	std::vector<int> dOrder;
-	int64_t iTotalCost = 0;
+	// runnable queries, biggest first (items are handed out in array order: longest-processing-time-first).
+	// Two classes, one launch each: doc-only queries (eval_kernel<false>) and hit-consuming ones (eval_kernel<true>).
+	std::vector<int> dOrder[2];
+	int64_t dTotalCost[2] = { 0, 0 };
 	for ( int i=0; i<nQueries; ++i )
 		if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
 		{
-			dOrder.push_back ( i );
-			iTotalCost += m_dPlans[i].m_iCost;
-			m_nStack = std::max ( m_nStack, m_dPlans[i].m_nStack );
+			const int c = m_dPlans[i].m_tDev.m_bNeedHits ? 1 : 0;
+			dOrder[c].push_back ( i );
+			dTotalCost[c] += m_dPlans[i].m_iCost;
+			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
 			m_iKMax = std::max ( m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
 			m_tStats.algorithmic_bytes += m_dPlans[i].m_iAlgBytes;
 			m_tStats.postings += m_dPlans[i].m_iCost;
 		}
-	if ( dOrder.empty() )
+	if ( dOrder[0].empty() && dOrder[1].empty() )
 		return MGPU_OK;
 
-	const int iOcc = EvalOccupancy ( m_nStack );
-	const int nMaxCtas = pIndex->m_nSMs*iOcc;
 	const uint32_t uRows = pIndex->m_tDev.m_uRows;
 	const int nTiles = (int)( ( (uint64_t)uRows+TILE_W-1 )/TILE_W );
-	const int64_t iTarget = std::max<int64_t> ( 262144, iTotalCost/( (int64_t)nMaxCtas*4 ) );
-
-	struct Part_t { int m_iQuery; int m_nParts; int64_t m_iCostPerPart; };
-	std::vector<Part_t> dParts;
-	for ( int i : dOrder )
-	{
-		const PlannedQuery_t & p = m_dPlans[i];
-		int64_t nParts = ( p.m_iCost+iTarget-1 )/iTarget;
-		int iCap = std::max ( 1, 131072/std::max ( 1, p.m_tDev.m_iMaxMatches ) );
-		nParts = std::max<int64_t> ( 1, std::min<int64_t> ( nParts, std::min ( { nTiles, 64, iCap } ) ) );
-		dParts.push_back ( { i, (int)nParts, p.m_iCost/nParts } );
-	}
-	std::stable_sort ( dParts.begin(), dParts.end(), [] ( const Part_t & a, const Part_t & b ) { return a.m_iCostPerPart>b.m_iCostPerPart; } );
-
 	int iMaxKeysPerQuery = 1;
-	for ( const Part_t & t : dParts )
+	for ( int c=0; c<2; ++c )
 	{
-		DevQuery_t q = m_dPlans[t.m_iQuery].m_tDev;
-		q.m_iFirstItem = (int)m_dItems.size();
-		q.m_nItems = t.m_nParts;
-		const int iDevQuery = (int)m_dDevQueries.size();
-		for ( int p=0; p<t.m_nParts; ++p )
+		m_dFirstItem[c] = (int)m_dItems.size();
+		if ( dOrder[c].empty() )
+			continue;
+		const int iOcc = EvalOccupancy ( m_dStack[c], c==1 );
+		const int nMaxCtas = pIndex->m_nSMs*iOcc;
+		const int64_t iTarget = std::max<int64_t> ( c ? 32768 : 262144, dTotalCost[c]/( (int64_t)nMaxCtas*4 ) );
+
+		struct Part_t { int m_iQuery; int m_nParts; int64_t m_iCostPerPart; };
+		std::vector<Part_t> dParts;
+		for ( int i : dOrder[c] )
 		{
-			uint64_t uT0 = (uint64_t)nTiles*p/t.m_nParts, uT1 = (uint64_t)nTiles*( p+1 )/t.m_nParts;
-			DevWorkItem_t tItem;
-			tItem.m_uQuery = (uint32_t)iDevQuery;
-			tItem.m_uRowLo = (uint32_t)( uT0*TILE_W );
-			tItem.m_uRowHi = (uint32_t)std::min<uint64_t> ( uT1*TILE_W, uRows );
-			tItem.m_uPad = 0;
-			m_dItems.push_back ( tItem );
+			const PlannedQuery_t & p = m_dPlans[i];
+			int64_t nParts = ( p.m_iCost+iTarget-1 )/iTarget;
+			int iCap = std::max ( 1, 131072/std::max ( 1, p.m_tDev.m_iMaxMatches ) );
+			nParts = std::max<int64_t> ( 1, std::min<int64_t> ( nParts, std::min ( { nTiles, 64, iCap } ) ) );
+			dParts.push_back ( { i, (int)nParts, p.m_iCost/nParts } );
 		}
-		iMaxKeysPerQuery = std::max ( iMaxKeysPerQuery, t.m_nParts*q.m_iMaxMatches );
-		m_dDevQueries.push_back ( q );
-		m_dDevToQuery.push_back ( t.m_iQuery );
+		std::stable_sort ( dParts.begin(), dParts.end(), [] ( const Part_t & a, const Part_t & b ) { return a.m_iCostPerPart>b.m_iCostPerPart; } );
+
+		for ( const Part_t & t : dParts )
+		{
+			DevQuery_t q = m_dPlans[t.m_iQuery].m_tDev;
+			q.m_iFirstItem = (int)m_dItems.size();
+			q.m_nItems = t.m_nParts;
+			const int iDevQuery = (int)m_dDevQueries.size();
+			for ( int p=0; p<t.m_nParts; ++p )
+			{
+				uint64_t uT0 = (uint64_t)nTiles*p/t.m_nParts, uT1 = (uint64_t)nTiles*( p+1 )/t.m_nParts;
+				DevWorkItem_t tItem;
+				tItem.m_uQuery = (uint32_t)iDevQuery;
+				tItem.m_uRowLo = (uint32_t)( uT0*TILE_W );
+				tItem.m_uRowHi = (uint32_t)std::min<uint64_t> ( uT1*TILE_W, uRows );
+				tItem.m_uPad = 0;
+				m_dItems.push_back ( tItem );
+			}
+			iMaxKeysPerQuery = std::max ( iMaxKeysPerQuery, t.m_nParts*q.m_iMaxMatches );
+			m_dDevQueries.push_back ( q );
+			m_dDevToQuery.push_back ( t.m_iQuery );
+		}
+		m_dCtas[c] = std::min ( nMaxCtas, (int)m_dItems.size()-m_dFirstItem[c] );
 	}
 
 	const int nDevQ = (int)m_dDevQueries.size();
 	const int nItems = (int)m_dItems.size();
-	m_nCtas = std::min ( nMaxCtas, nItems );
 	m_iPoolCap = m_iKMax + 2*TILE_W;
 	m_iScratchStride = 2*Pow2Ceil ( iMaxKeysPerQuery );
 
 	CUDA_TRY ( m_dQ.Alloc ( nDevQ ), m_sError );
 	CUDA_TRY ( m_dI.Alloc ( nItems ), m_sError );
-	CUDA_TRY ( m_dCounter.Alloc ( 1 ), m_sError );
-	CUDA_TRY ( m_dPool.Alloc ( (size_t)m_nCtas*2*m_iPoolCap ), m_sError );
+	CUDA_TRY ( m_dCounter.Alloc ( 2 ), m_sError );
+	CUDA_TRY ( m_dPool.Alloc ( (size_t)std::max ( m_dCtas[0], m_dCtas[1] )*2*m_iPoolCap ), m_sError );
+	CUDA_TRY ( m_dHitpos.Alloc ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W ), m_sError );
 	CUDA_TRY ( m_dItemKeys.Alloc ( (size_t)nItems*m_iKMax ), m_sError );
 	CUDA_TRY ( m_dItemOut.Alloc ( nItems ), m_sError );
 	CUDA_TRY ( m_dScratch.Alloc ( (size_t)nDevQ*m_iScratchStride ), m_sError );
@@ -813,22 +873,31 @@ int Batch_c::Run()
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	cudaStream_t s = pIndex->m_tStream;
 
-	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, sizeof(int32_t), s ), m_sError );
-
-	EvalParams_t P {};
-	P.m_tIndex = pIndex->m_tDev;
-	P.m_pQueries = m_dQ.m_p;
-	P.m_pItems = m_dI.m_p;
-	P.m_nItems = (int)m_dItems.size();
-	P.m_iPoolCap = m_iPoolCap;
-	P.m_pPool = m_dPool.m_p;
-	P.m_pItemKeys = m_dItemKeys.m_p;
-	P.m_pItemOut = m_dItemOut.m_p;
-	P.m_pCounter = m_dCounter.m_p;
-	P.m_iKMax = m_iKMax;
+	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, 2*sizeof(int32_t), s ), m_sError );
 
 	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
-	CUDA_TRY ( LaunchEval ( P, m_nStack, m_nCtas, s ), m_sError );
+	int nLaunches = 1;
+	for ( int c=0; c<2; ++c )
+	{
+		const int iFirst = m_dFirstItem[c];
+		const int nClassItems = ( c==0 ? m_dFirstItem[1] : (int)m_dItems.size() ) - iFirst;
+		if ( nClassItems<=0 )
+			continue;
+		EvalParams_t P {};
+		P.m_tIndex = pIndex->m_tDev;
+		P.m_pQueries = m_dQ.m_p;
+		P.m_pItems = m_dI.m_p + iFirst;
+		P.m_nItems = nClassItems;
+		P.m_iPoolCap = m_iPoolCap;
+		P.m_pPool = m_dPool.m_p;
+		P.m_pItemKeys = m_dItemKeys.m_p + (size_t)iFirst*m_iKMax;
+		P.m_pItemOut = m_dItemOut.m_p + iFirst;
+		P.m_pCounter = m_dCounter.m_p + c;
+		P.m_iKMax = m_iKMax;
+		P.m_pHitpos = m_dHitpos.m_p;
+		CUDA_TRY ( LaunchEval ( P, m_dStack[c], c==1, m_dCtas[c], s ), m_sError );
+		++nLaunches;
+	}
 	CUDA_TRY ( cudaEventRecord ( m_tEv1, s ), m_sError );
 
 	MergeParams_t M {};
@@ -847,7 +916,7 @@ int Batch_c::Run()
 	M.m_pOutTotal = m_dOutTotal.m_p;
 	CUDA_TRY ( LaunchMerge ( M, std::min ( M.m_nQueries, pIndex->m_nSMs*8 ), s ), m_sError );
 	CUDA_TRY ( cudaEventRecord ( m_tEv2, s ), m_sError );
-	m_tStats.kernel_launches = 2;
+	m_tStats.kernel_launches = nLaunches;
 	m_bRan = true;
 	return MGPU_OK;
 }

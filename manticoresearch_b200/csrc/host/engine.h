@@ -111,10 +111,11 @@ public:
 	std::vector<DevQuery_t>		m_dDevQueries;	///< only the runnable ones, in order
 	std::vector<int>			m_dDevToQuery;	///< device query -> batch query index
 	std::vector<DevWorkItem_t>	m_dItems;
-	int		m_nStack = 1;
+	int		m_dStack[2] = { 1, 1 };		///< per launch class: [0] doc-only queries, [1] hit-consuming queries
+	int		m_dCtas[2] = { 0, 0 };
+	int		m_dFirstItem[2] = { 0, 0 };
 	int		m_iKMax = 1;
 	int		m_iPoolCap = 0;
-	int		m_nCtas = 0;
 	int		m_iScratchStride = 0;
 
 	DevBuf_T<DevQuery_t>	m_dQ;
@@ -124,6 +125,7 @@ public:
 	DevBuf_T<DevItemOut_t>	m_dItemOut;
 	DevBuf_T<int64_t>		m_dOutDocid, m_dOutTotal;
 	DevBuf_T<int32_t>		m_dOutCount, m_dOutSlot;
+	DevBuf_T<uint64_t>		m_dHitpos;		///< hit stage scratch: hitlist position per (CTA, leaf, tile slot)
 
 	cudaEvent_t		m_tEv0 = nullptr, m_tEv1 = nullptr, m_tEv2 = nullptr;
 	mgpu_batch_stats m_tStats {};
@@ -138,9 +140,9 @@ public:
 };
 
 // kernels.cu launchers
-size_t		EvalDynSmemBytes ( int nStack );
-int			EvalOccupancy ( int nStack );
-cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );
+size_t		EvalDynSmemBytes ( int nStack, bool bHits );
+int			EvalOccupancy ( int nStack, bool bHits );
+cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, bool bHits, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
 				Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream );

@@ -153,3 +153,87 @@ def random_boolean_queries(n, seed, max_rank=20000, nfields=2, rankers=(M.RANK_B
         out.append(M.Query(root, ranker=rng.choice(rankers), field_weights=fw, max_matches=rng.choice([1, 7, max_matches, 1000]),
                            index_weight=rng.choice([1, 1, 1, 3])))
     return out
+
+
+def random_hit_queries(params, n, seed, max_matches=200):
+    """parity fuzz set of the hit stage: phrases / proximities sampled from real docs (some of stop words), combined with
+    AND / OR / ANDNOT / MAYBE and plain keywords, ranked by every ranker; some queries repeat a keyword (dupes path)"""
+    rng = random.Random(seed)
+    sampler = ZipfRanks(1, 20000)
+    out = []
+    while len(out) < n:
+        pos = [0]
+
+        def leaf(word=None):
+            pos[0] += 1
+            node = M.kw(word or M.synth_keyword(sampler.sample(rng) - 1), pos[0])
+            u = rng.random()
+            if u < 0.1:
+                node.field_mask = 1
+            elif u < 0.2:
+                node.field_mask = 2
+            return node
+
+        def nway():
+            while True:
+                doc = params.first_doc + rng.randrange(params.n_docs)
+                field = 1 if rng.random() < 0.8 else 0
+                flen = M.synth_field_len(params, doc, field)
+                if flen >= 10:
+                    break
+            if rng.random() < 0.5:
+                k = rng.randint(2, 4)
+                p0 = rng.randrange(flen - k)
+                terms = [M.synth_token(params, doc, field, p0 + i) for i in range(k)]
+                words = []
+                for t in terms:
+                    pos[0] += 1
+                    words.append((M.synth_keyword(t), pos[0]))
+                if rng.random() < 0.15:
+                    pos[0] += 1                     # a gap in atom positions (a stop word dropped from the phrase)
+                    words[-1] = (words[-1][0], pos[0])
+                node = M.PHRASE(words)
+            else:
+                k = rng.randint(2, 4)
+                span = min(flen - 1, 9)
+                p0 = rng.randrange(flen - span)
+                offs = sorted(rng.sample(range(span), k))
+                terms = [M.synth_token(params, doc, field, p0 + o) for o in offs]
+                if rng.random() < 0.3:
+                    rng.shuffle(terms)
+                words = []
+                for t in terms:
+                    pos[0] += 1
+                    words.append((M.synth_keyword(t), pos[0]))
+                node = M.PROXIMITY(words, rng.choice([1, 2, 5, 8]))
+            if rng.random() < 0.15:
+                node.field_mask = 1 << field
+            return node
+
+        u = rng.random()
+        if u < 0.25:
+            root = nway()
+        elif u < 0.4:
+            root = M.OR(nway(), leaf())
+        elif u < 0.5:
+            root = M.AND(nway(), leaf())
+        elif u < 0.58:
+            root = M.OR(nway(), nway())
+        elif u < 0.64:
+            root = M.ANDNOT(nway(), leaf())
+        elif u < 0.70:
+            root = M.MAYBE(leaf(), nway())
+        elif u < 0.80:
+            root = M.AND(*[leaf() for _ in range(rng.randint(2, 4))])
+        elif u < 0.88:
+            root = M.OR(M.AND(leaf(), leaf()), leaf())
+        elif u < 0.94:
+            w = M.synth_keyword(sampler.sample(rng) - 1)    # the same keyword twice: HasQwordDupes
+            root = M.AND(leaf(w), leaf(), leaf(w)) if rng.random() < 0.5 else M.OR(leaf(w), M.AND(leaf(w), leaf()))
+        else:
+            root = M.OR(M.ANDNOT(leaf(), leaf()), M.MAYBE(leaf(), leaf()))
+        ranker = rng.choice([M.RANK_PROXIMITY_BM25] * 5 + [M.RANK_WORDCOUNT] * 2 + [M.RANK_BM25, M.RANK_NONE])
+        fw = [rng.choice([1, 2, 10, 0, -3]) for _ in range(2)] if rng.random() < 0.5 else None
+        out.append(M.Query(root, ranker=ranker, field_weights=fw, max_matches=rng.choice([5, max_matches, 1000]),
+                           index_weight=rng.choice([1, 1, 2])))
+    return out
