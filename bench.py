@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=int(os.environ.get("MGPU_BENCH_QUERIES", 10_000)))
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="", choices=["", "and", "or", "mix"], help="analysis only: keep one query shape of the batch")
     return ap.parse_args()
 
 
@@ -210,6 +211,13 @@ def run_ours(args):
 
     # ---- queries; global IDF inputs when sharded (CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs)
     queries = workload.cfg2_queries(n=args.queries, max_matches=100)
+    if args.only:
+        def shape(q):
+            r = q.root
+            if r.op == M.OP_AND:
+                return "and"
+            return "mix" if any(c.children for c in r.children) else "or"
+        queries = [q for q in queries if shape(q) == args.only]
     K = 100
     if world > 1:
         words = sorted({k.word for q in queries for k in q.keywords()})
@@ -253,7 +261,7 @@ def run_ours(args):
         if world > 1:
             merge_step(batch)
     barrier()
-    eval_ms, merge_ms = [], []
+    eval_ms, merge_ms, hot_ms = [], [], []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
@@ -266,6 +274,7 @@ def run_ours(args):
             st = batch.stats()
             eval_ms.append(st["eval_kernel_ms"])
             merge_ms.append(st["merge_kernel_ms"])
+            hot_ms.append(st["hot_decode_ms"])
         ev1.record(stream)
         barrier()
     total_ms = ev0.elapsed_time(ev1)
@@ -328,7 +337,7 @@ def run_ours(args):
             "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "docs": args.docs, "queries_per_batch": nq, "parallelism": "rowid-range shards x%d" % world,
+            "config": {"workload": WORKLOAD + (" [ANALYSIS SUBSET: only %s queries]" % args.only if args.only else ""), "docs": args.docs, "queries_per_batch": nq, "parallelism": "rowid-range shards x%d" % world,
                        "l2": "inputs >> L2 (%.1f GB algorithmic bytes per step)" % (job_bytes / 1e9),
                        "index_build_s": round(build_s, 1), "index_load_s": round(load_s, 1), "unsupported_queries": n_unsupported},
             "postings_per_sec": job_postings / (ms_per_step / 1000.0),
@@ -339,7 +348,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st["algorithmic_bytes"], "kernel_ms": eval_avg_ms,
-                         "merge_kernel_ms": statistics.mean(merge_ms), "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "merge_kernel_ms": statistics.mean(merge_ms), "hot_decode_ms": statistics.mean(hot_ms), "hot_terms": st["hot_terms"],
+                         "class_ms": {"dense": st["dense_kernel_ms"], "hits": st["hits_kernel_ms"], "and": st["and_kernel_ms"]},
+                         "class_queries": {"dense": st["queries_dense"], "hits": st["queries_hits"], "and": st["queries_and"]},
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -211,6 +211,11 @@ typedef struct mgpu_batch_stats {
 	int64_t			d2h_bytes;
 	float			eval_kernel_ms;      /* CUDA-event time of the fused eval kernel in the last run */
 	float			merge_kernel_ms;
+	float			hot_decode_ms;       /* K0: the batch's shared hot keywords decoded once into the dense store */
+	int32_t			hot_terms;
+	/* per launch class: dense-tile kernel (doc-only queries), hit-stage kernel, intersection kernel (pure AND queries) */
+	float			dense_kernel_ms, hits_kernel_ms, and_kernel_ms;
+	int32_t			queries_dense, queries_hits, queries_and;
 } mgpu_batch_stats;
 int				mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out );
 

@@ -22,6 +22,7 @@ static const int MAX_FIELDS = 32;
 static const int STAGE_BYTES = 896;		///< per-warp staging: 15 B alignment head + 32 docs * (5+5+5+10) B, rounded up to a multiple of 128
 static const int MAX_PHRASE_WORDS = 16;	///< keywords per phrase/proximity node on the GPU path
 static const int MAX_NWAY = 4;			///< phrase/proximity nodes per query
+static const int PRE_BLOCKS = MAX_LEAVES*( TILE_W/32+2 );	///< predecode scratch per CTA: a keyword has at most TILE_W/32+2 blocks overlapping a tile
 static const int NWAY_MAX_SPAN = 31;	///< max (last atom pos - first atom pos) of a phrase/proximity node: bounds the FSM state
 
 struct DevIndex_t
@@ -52,6 +53,22 @@ struct DevLeaf_t
 	float		m_fIDF;
 	uint16_t	m_uAtomPos;
 	uint16_t	m_uNodePos;
+	int32_t		m_iHot;				///< slot in the batch's dense hot-term store, -1 = evaluate from the compressed doclist
+	int32_t		m_iPad;
+};
+
+/// Dense hot-term store, rebuilt by hot_decode_kernel at the start of every batch run: keywords that many queries of the
+/// batch share and that sit in >= 1/8 of the rows are decoded ONCE per batch into one byte of hit count + one byte of field
+/// mask per row (the GPU's take on the reference's multi-query common-subtree cache, src/searchnode.cpp:5487-5890).
+struct DevHotStore_t
+{
+	const uint16_t *	m_pData;		///< [nHot][m_iStride]: low byte 0 = keyword absent, 1..254 = hit count, 255 = see escape list;
+										///< high byte = field mask (indexes with <= 8 fields)
+	const uint32_t *	m_pEscape;		///< [m_nEscape][3]: hot slot, rowid, hit count (documents with >= 255 hits)
+	const int32_t *		m_pEscapeCount;
+	int64_t				m_iStride;		///< rows rounded up to TILE_W
+	int32_t				m_nHot;
+	int32_t				m_iPad;
 };
 
 enum DevOpCode_e : uint8_t
@@ -72,7 +89,8 @@ struct DevOp_t
 {
 	uint8_t		m_eCode;
 	uint8_t		m_uDst;
-	uint8_t		m_uSrc;
+	uint8_t		m_uSrc;			///< VEC ops: source level. TERM_AND: 1 + index of the first op after this AND chain (0 = none):
+							///< where to resume when no candidate is left in the tile
 	uint8_t		m_uAliveDst;	///< value of cnt[] meaning "alive" in v[dst] BEFORE the op
 	uint8_t		m_uAliveSrc;	///< same for v[src]
 	uint8_t		m_uLeaf;
@@ -136,7 +154,20 @@ struct DevQuery_t
 	int32_t		m_iFirstItem;			///< first work item of this query
 	int32_t		m_nItems;
 	int32_t		m_bStateRanker;			///< ExtRanker_State_T: PROXIMITY_BM25 over >1 keyword, WORDCOUNT
+	uint32_t	m_uPreMask;				///< leaves whose op scatters unconditionally (SET/OR/ANDNOT/MAYBE): decoded in the tile predecode phase
+	uint32_t	m_uOrigMask;			///< leaves whose op can bring a document into the result (SET / OR operands)
+	int32_t		m_bOrigHot;				///< one of those is a hot (dense) keyword: every mini-tile has to be visited
 	int32_t		m_iPad;
+	int32_t		m_iDriverLeaf;			///< pure AND program opened by this (sparse) keyword: tiles without its postings are skipped; -1 = none
+};
+
+/// one predecoded posting of the tile predecode phase
+struct PreEntry_t
+{
+	uint32_t	m_uRowid;		///< 0xFFFFFFFF = not a posting of this tile
+	float		m_fTf;			///< hits/(hits+1.2)*idf
+	uint32_t	m_uFields;		///< already masked by the queried fields
+	uint32_t	m_uPad;
 };
 
 /// 128-bit match key: hi = packed sort keys (bigger = better), lo = ~rowid:32 | weight:32
@@ -175,6 +206,21 @@ struct EvalParams_t
 	int32_t					m_iKMax;		///< stride of m_pItemKeys
 	int32_t					m_iPad;
 	uint64_t *				m_pHitpos;		///< hit stage only: [gridDim.x][MAX_LEAVES][TILE_W] hitlist position of (leaf, tile slot)
+	PreEntry_t *			m_pPre;			///< [gridDim.x][PRE_BLOCKS*32] tile predecode scratch
+	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]
+	DevHotStore_t			m_tHot;
+};
+
+struct HotDecodeParams_t
+{
+	DevIndex_t				m_tIndex;
+	const DevLeaf_t *		m_pTerms;		///< [nHot] doclist descriptors
+	int32_t					m_nHot;
+	int32_t					m_iEscapeCap;
+	uint16_t *				m_pData;
+	uint32_t *				m_pEscape;
+	int32_t *				m_pEscapeCount;
+	int64_t					m_iStride;
 };
 
 struct MergeParams_t

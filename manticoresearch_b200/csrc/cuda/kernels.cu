@@ -374,6 +374,11 @@ struct EvalShared_t
 	int				m_iPoolCnt;
 	int				m_iPoolBuf;
 	int				m_iListCnt;
+	uint32_t		m_uNextRow;
+	int				m_dPreOff[MAX_LEAVES+1];	///< first predecode block slot of each leaf in this tile
+	uint32_t		m_dRankTab[16];		///< ExtRanker_WeightSum_c: sum of the weights of the fields in a 4-bit mask (indexes with <= 4 fields)
+	uint32_t		m_dAliveBits[TILE_W/32];
+	float			m_dTf[256];			///< float(hits)/float(hits+1.2f), src/searchnode.cpp:1946
 	uint16_t		m_dRecStart[EVAL_WARPS][34];
 	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
 };
@@ -485,6 +490,122 @@ __device__ __forceinline__ Key128_t MakeKey ( const DevIndex_t & tIdx, const Dev
 	return k;
 }
 
+/// one posting of a keyword meets tile slot s of v[d]: the per-document step of ExtTerm_T (SET), ExtAnd_c / ExtMultiAnd_T (AND),
+/// ExtOr_c (OR), ExtAndNot_c (ANDNOT), ExtMaybe_c (MAYBE). Returns whether the keyword "sits on" the doc for CollectHits().
+template<bool HITS, typename VEC>
+__device__ __forceinline__ bool ApplyTermOp ( VEC & V, const DevOp_t & tOp, int d, int s, float fTf, uint32_t uFields, uint32_t uEmitBit )
+{
+	const uint8_t uAlive = tOp.m_uAliveDst;
+	switch ( tOp.m_eCode )
+	{
+	case OP_TERM_SET:
+		V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = 1;
+		if ( HITS ) V.Emit ( d, s ) = uEmitBit;
+		return true;
+	case OP_TERM_AND:
+		if ( V.Cnt ( d, s )==uAlive )
+		{
+			V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
+			V.Fields ( d, s ) |= uFields;
+			V.Cnt ( d, s ) = tOp.m_uAliveOut;
+			if ( HITS ) V.Emit ( d, s ) |= uEmitBit;
+			return true;
+		}
+		return false;
+	case OP_TERM_OR:
+		if ( V.Cnt ( d, s )==uAlive )
+		{
+			V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
+			V.Fields ( d, s ) |= uFields;
+			if ( HITS ) V.Emit ( d, s ) |= uEmitBit;
+		} else
+		{
+			V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = uAlive;
+			if ( HITS ) V.Emit ( d, s ) = uEmitBit;
+		}
+		return true;
+	case OP_TERM_ANDNOT:
+		if ( V.Cnt ( d, s )==uAlive )
+			V.Cnt ( d, s ) = 0;
+		return false;
+	default: // OP_TERM_MAYBE
+		if ( V.Cnt ( d, s )==uAlive )
+		{
+			V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
+			V.Fields ( d, s ) |= uFields;
+			if ( HITS ) V.Emit ( d, s ) |= uEmitBit;
+			return true;
+		}
+		return false;
+	}
+}
+
+/// warp-uniform: any alive bit in slots [uLo, uHi) of the 2048-bit map
+__device__ __forceinline__ bool AnyAliveInRange ( const uint32_t * pBits, uint32_t uLo, uint32_t uHi, int iLane )
+{
+	if ( uLo>=uHi )
+		return false;
+	bool bAny = false;
+	#pragma unroll
+	for ( int k=0; k<TILE_W/32/32; ++k )
+	{
+		const uint32_t w = (uint32_t)( k*32+iLane );
+		const uint32_t uBase = w*32;
+		uint32_t m = pBits[w];
+		if ( uBase+32<=uLo || uBase>=uHi )
+			m = 0;
+		else
+		{
+			if ( uLo>uBase )
+				m &= ~0u<<( uLo-uBase );
+			if ( uHi<uBase+32 )
+				m &= ( 1u<<( uHi-uBase ) )-1u;
+		}
+		bAny |= ( m!=0 );
+	}
+	return __any_sync ( FULL_MASK, bAny );
+}
+
+/// documents with >= 255 hits of a hot keyword are rare: their hit counts live in a short list
+__device__ uint32_t HotEscapeHits ( const DevHotStore_t & tHot, int iHot, uint32_t uRowid )
+{
+	const int n = __ldg ( tHot.m_pEscapeCount );
+	for ( int i=0; i<n; ++i )
+		if ( __ldg ( tHot.m_pEscape+3*i )==(uint32_t)iHot && __ldg ( tHot.m_pEscape+3*i+1 )==uRowid )
+			return __ldg ( tHot.m_pEscape+3*i+2 );
+	return 255u;
+}
+
+/// K0: decodes every hot keyword's doclist ONCE per batch into the dense store (warp per 32-doc block)
+__global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecodeParams_t P )
+{
+	__shared__ __align__(16) uint8_t dStage[EVAL_WARPS][STAGE_BYTES];
+	__shared__ uint16_t dRecStart[EVAL_WARPS][34];
+	const int iWarp = threadIdx.x>>5, iLane = threadIdx.x & 31;
+	const uint32_t uWarpGlobal = blockIdx.x*EVAL_WARPS+iWarp, nWarps = gridDim.x*EVAL_WARPS;
+	for ( int h=0; h<P.m_nHot; ++h )
+	{
+		const DevLeaf_t tLeaf = P.m_pTerms[h];
+		uint16_t * pD = P.m_pData + (size_t)h*P.m_iStride;
+		for ( uint32_t b=uWarpGlobal; b<tLeaf.m_nBlocks; b+=nWarps )
+		{
+			DecodedDoc_t d;
+			DecodeBlock<false> ( P.m_tIndex, tLeaf, b, dStage[iWarp], dRecStart[iWarp], iLane, d );
+			if ( !d.m_bValid )
+				continue;
+			pD[d.m_uRowid] = (uint16_t)( min ( d.m_uHits, 255u ) | ( ( d.m_uFields & 255u )<<8 ) );
+			if ( d.m_uHits>=255u )
+			{
+				const int i = atomicAdd ( P.m_pEscapeCount, 1 );
+				if ( i<P.m_iEscapeCap )
+				{
+					P.m_pEscape[3*i] = (uint32_t)h; P.m_pEscape[3*i+1] = d.m_uRowid; P.m_pEscape[3*i+2] = d.m_uHits;
+				}
+			}
+		}
+	}
+}
+
 template<bool HITS>
 __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P, int nStack )
 {
@@ -498,10 +619,16 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 	V.m_pList = reinterpret_cast<uint16_t *>( dDyn + (size_t)nStack*TILE_W*( HITS ? 12 : 8 ) );
 	V.m_pCnt = dDyn + (size_t)nStack*TILE_W*( HITS ? 12 : 8 ) + ( HITS ? TILE_W*2 : 0 );
 	uint64_t * pHitpos = HITS ? P.m_pHitpos + (size_t)blockIdx.x*MAX_LEAVES*TILE_W : nullptr;
+	PreEntry_t * pPre = P.m_pPre + (size_t)blockIdx.x*PRE_BLOCKS*32;
+	uint64_t * pPreHitpos = HITS ? P.m_pPreHitpos + (size_t)blockIdx.x*PRE_BLOCKS*32 : nullptr;
 
 	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
 	const DevIndex_t & tIdx = P.m_tIndex;
 	Key128_t * pPool0 = P.m_pPool + (size_t)blockIdx.x*2*P.m_iPoolCap;
+	{
+		const float fHits = __uint2float_rn ( (uint32_t)tid );
+		S.m_dTf[tid & 255] = __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
+	}
 
 	while ( true )
 	{
@@ -535,7 +662,18 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 		const int iK = q.m_iMaxMatches;
 		int iMyTotal = 0;
 
-		for ( uint32_t uTileLo=tItem.m_uRowLo; uTileLo<tItem.m_uRowHi; uTileLo+=TILE_W )
+		if ( tid<16 )
+		{
+			uint32_t uSum = 0;
+			for ( int i=0; i<4 && i<q.m_nWeights; ++i )
+				if ( tid & ( 1<<i ) )
+					uSum += (uint32_t)q.m_dWeights[i];
+			S.m_dRankTab[tid] = uSum;
+		}
+		const bool bJump = q.m_iDriverLeaf>=0;	// pure AND query opened by a sparse keyword: visit only the tiles that keyword touches
+
+		uint32_t uTileLo = tItem.m_uRowLo;
+		while ( uTileLo<tItem.m_uRowHi )
 		{
 			const uint32_t uTileHi = min ( uTileLo+(uint32_t)TILE_W, tItem.m_uRowHi );
 
@@ -554,12 +692,12 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 				__syncthreads();
 			}
 
-			// block range of every leaf inside this tile
+			// block range of every sparse leaf inside this tile
 			for ( int l=iWarp; l<q.m_nLeaves; l+=EVAL_WARPS )
 			{
 				const DevLeaf_t & tLeaf = q.m_dLeaves[l];
 				uint32_t b0 = 0, b1 = 0;
-				if ( tLeaf.m_nBlocks )
+				if ( tLeaf.m_nBlocks && ( HITS || tLeaf.m_iHot<0 ) )
 				{
 					const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
 					// b0 = last block whose base <= tile lo; b1 = first block whose base >= tile hi
@@ -574,92 +712,200 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 					S.m_dLeafCursor[l] = b1 ? b1-1 : 0;
 				}
 			}
+			if ( tid==0 )
+				S.m_uNextRow = 0xFFFFFFFFu;
 			__syncthreads();
 
-			// run the tile program
+			// Tile predecode: every block of every scattering (non-chain) sparse keyword that overlaps the tile is decoded in ONE
+			// cooperative phase -- all warps busy -- into this CTA's scratch list; the keyword's op then scatters its entries with
+			// the whole CTA. (AND-chain keywords stay lazy: they only decode blocks that still hold candidates.)
+			if ( tid==0 )
+			{
+				int iOff = 0;
+				for ( int l=0; l<q.m_nLeaves; ++l )
+				{
+					S.m_dPreOff[l] = iOff;
+					if ( ( ( q.m_uPreMask>>l ) & 1u ) && ( HITS || q.m_dLeaves[l].m_iHot<0 ) )
+						iOff += (int)( S.m_dLeafB1[l]-S.m_dLeafB0[l] );
+				}
+				S.m_dPreOff[q.m_nLeaves] = iOff;
+			}
+			__syncthreads();
+			{
+				const int nPre = S.m_dPreOff[q.m_nLeaves];
+				for ( int p=iWarp; p<nPre; p+=EVAL_WARPS )
+				{
+					int l = 0;
+					while ( S.m_dPreOff[l+1]<=p )
+						++l;
+					const DevLeaf_t & tLeaf = q.m_dLeaves[l];
+					const uint32_t b = S.m_dLeafB0[l] + (uint32_t)( p-S.m_dPreOff[l] );
+					DecodedDoc_t tDoc;
+					DecodeBlock<HITS> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
+					const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
+					const bool bOk = tDoc.m_bValid && uFields;
+					if ( bOk && tDoc.m_uRowid>=uTileHi && q.m_iDriverLeaf==l )
+						atomicMin ( &S.m_uNextRow, tDoc.m_uRowid );	// exact next candidate of a pure AND query: tiles in between are skipped
+					PreEntry_t tEntry;
+					tEntry.m_uRowid = ( bOk && tDoc.m_uRowid>=uTileLo && tDoc.m_uRowid<uTileHi ) ? tDoc.m_uRowid : 0xFFFFFFFFu;
+					// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946
+					const float fHits = __uint2float_rn ( tDoc.m_uHits );
+					tEntry.m_fTf = __fmul_rn ( __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
+					tEntry.m_uFields = uFields;
+					tEntry.m_uPad = 0;
+					pPre[(size_t)p*32+iLane] = tEntry;
+					if ( HITS )
+						pPreHitpos[(size_t)p*32+iLane] = tDoc.m_uHitlistPos;
+				}
+			}
+			__syncthreads();
+
+			// Run the tile program. Dense keyword ops and vector ops are slot-local: thread t only ever touches slots
+			// t, t+256, ... so they need no barrier between them; barriers surround the scattering (sparse) ops only.
+			bool bDirty = false;	// slot-local writes not yet published by a barrier
 			for ( int iOp=0; iOp<q.m_nOps; ++iOp )
 			{
 				const DevOp_t tOp = q.m_dOps[iOp];
 				const int d = tOp.m_uDst;
-				if ( tOp.m_eCode==OP_TERM_SET )
-				{
-					uint32_t * pCnt32 = reinterpret_cast<uint32_t *>( &V.Cnt ( d, 0 ) );
-					for ( int i=tid; i<TILE_W/4; i+=EVAL_THREADS )
-						pCnt32[i] = 0;
-					__syncthreads();
-				}
 				if ( tOp.m_eCode<=OP_TERM_MAYBE )
 				{
 					const DevLeaf_t & tLeaf = q.m_dLeaves[tOp.m_uLeaf];
-					const uint32_t b1 = S.m_dLeafB1[tOp.m_uLeaf];
-					const uint8_t uAlive = tOp.m_uAliveDst;
-					const uint32_t uEmitBit = 1u<<tOp.m_uLeaf;
-					for ( uint32_t b=S.m_dLeafB0[tOp.m_uLeaf]+iWarp; b<b1; b+=EVAL_WARPS )
+					const bool bDense = !HITS && tLeaf.m_iHot>=0;
+					const uint32_t b0 = S.m_dLeafB0[tOp.m_uLeaf], b1 = S.m_dLeafB1[tOp.m_uLeaf];
+
+					// AND chains: no candidate left in the tile (or an opening keyword without postings here) -> resume after the chain
+					const bool bChain = ( tOp.m_uSrc!=0 );
+					if ( bChain && tOp.m_eCode==OP_TERM_SET && !bDense && b0>=b1 )
 					{
-						DecodedDoc_t tDoc;
-						DecodeBlock<HITS> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
-						const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
-						if ( !tDoc.m_bValid || tDoc.m_uRowid<uTileLo || tDoc.m_uRowid>=uTileHi || !uFields )
-							continue;
-						const int s = (int)( tDoc.m_uRowid-uTileLo );
-						// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946
-						const float fHits = __uint2float_rn ( tDoc.m_uHits );
-						const float fTf = __fmul_rn ( __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
-						bool bOn = false;	// the keyword sits on this doc as far as CollectHits() is concerned
-						switch ( tOp.m_eCode )
+						#pragma unroll
+						for ( int k=0; k<TILE_W/EVAL_THREADS; ++k )
+							V.Cnt ( d, k*EVAL_THREADS+tid ) = 0;	// slot-local: no barrier needed
+						bDirty = true;
+						iOp = (int)tOp.m_uSrc-2;
+						continue;
+					}
+					if ( bChain && tOp.m_eCode==OP_TERM_AND )
+					{
+						bool bMine = false;
+						#pragma unroll
+						for ( int k=0; k<TILE_W/EVAL_THREADS; ++k )
 						{
-						case OP_TERM_SET:
-							V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = 1;
-							if ( HITS ) { V.Emit ( d, s ) = uEmitBit; bOn = true; }
-							break;
-						case OP_TERM_AND:
-							if ( V.Cnt ( d, s )==uAlive )
+							const int s = k*EVAL_THREADS+tid;
+							const bool bA = V.Cnt ( d, s )==tOp.m_uAliveDst;
+							if ( !bDense )
 							{
-								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
-								V.Fields ( d, s ) |= uFields;
-								V.Cnt ( d, s ) = tOp.m_uAliveOut;
-								if ( HITS ) { V.Emit ( d, s ) |= uEmitBit; bOn = true; }
+								const unsigned m = __ballot_sync ( FULL_MASK, bA );
+								if ( iLane==0 )
+									S.m_dAliveBits[s>>5] = m;
 							}
-							break;
-						case OP_TERM_OR:
-							if ( V.Cnt ( d, s )==uAlive )
-							{
-								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
-								V.Fields ( d, s ) |= uFields;
-								if ( HITS ) V.Emit ( d, s ) |= uEmitBit;
-							} else
-							{
-								V.Tfidf ( d, s ) = fTf; V.Fields ( d, s ) = uFields; V.Cnt ( d, s ) = uAlive;
-								if ( HITS ) V.Emit ( d, s ) = uEmitBit;
-							}
-							bOn = true;
-							break;
-						case OP_TERM_ANDNOT:
-							if ( V.Cnt ( d, s )==uAlive )
-								V.Cnt ( d, s ) = 0;
-							break;
-						default: // OP_TERM_MAYBE
-							if ( V.Cnt ( d, s )==uAlive )
-							{
-								V.Tfidf ( d, s ) = __fadd_rn ( V.Tfidf ( d, s ), fTf );
-								V.Fields ( d, s ) |= uFields;
-								if ( HITS ) { V.Emit ( d, s ) |= uEmitBit; bOn = true; }
-							}
-							break;
+							bMine |= bA;
 						}
-						if ( HITS && bOn )
-							pHitpos[(size_t)tOp.m_uLeaf*TILE_W+s] = tDoc.m_uHitlistPos;
+						const int iAny = __syncthreads_or ( bMine );
+						bDirty = false;
+						if ( !iAny )
+						{
+							iOp = (int)tOp.m_uSrc-2;
+							continue;
+						}
+					}
+
+					if ( bDense )
+					{
+						// the keyword comes from the batch's dense hot-term store: u16 per row = hits | fields<<8.
+						// All 8 loads of a thread are independent and issued up front (one round trip per op).
+						const uint16_t * pD = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride + uTileLo;
+						uint32_t dRaw[TILE_W/EVAL_THREADS];
+						#pragma unroll
+						for ( int k=0; k<TILE_W/EVAL_THREADS; ++k )
+							dRaw[k] = __ldg ( pD + k*EVAL_THREADS+tid );
+						#pragma unroll
+						for ( int k=0; k<TILE_W/EVAL_THREADS; ++k )
+						{
+							const int s = k*EVAL_THREADS+tid;
+							uint32_t uHits = dRaw[k] & 255u;
+							const uint32_t uFields = uHits ? ( ( dRaw[k]>>8 ) & tLeaf.m_uQueriedFields ) : 0u;
+							if ( !uFields )
+							{
+								if ( tOp.m_eCode==OP_TERM_SET )
+									V.Cnt ( d, s ) = 0;
+								continue;
+							}
+							float fBase;
+							if ( uHits<255 )
+								fBase = S.m_dTf[uHits];
+							else
+							{
+								uHits = HotEscapeHits ( P.m_tHot, tLeaf.m_iHot, uTileLo+s );
+								const float fHits = __uint2float_rn ( uHits );
+								fBase = __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
+							}
+							ApplyTermOp<false> ( V, tOp, d, s, __fmul_rn ( fBase, tLeaf.m_fIDF ), uFields, 0u );
+						}
+						bDirty = true;
+					} else
+					{
+						if ( tOp.m_eCode==OP_TERM_SET )
+						{
+							#pragma unroll
+							for ( int k=0; k<TILE_W/EVAL_THREADS; ++k )
+								V.Cnt ( d, k*EVAL_THREADS+tid ) = 0;	// slot-local
+							bDirty = true;
+						}
+						if ( bDirty )
+							__syncthreads();
+						const uint32_t uEmitBit = 1u<<tOp.m_uLeaf;
+						if ( ( q.m_uPreMask>>tOp.m_uLeaf ) & 1u )
+						{
+							// scatter the predecoded entries of this keyword, one entry per thread
+							const int iFrom = S.m_dPreOff[tOp.m_uLeaf]*32, iTo = iFrom + (int)( b1-b0 )*32;
+							for ( int i=iFrom+tid; i<iTo; i+=EVAL_THREADS )
+							{
+								const PreEntry_t tEntry = pPre[i];
+								if ( tEntry.m_uRowid==0xFFFFFFFFu )
+									continue;
+								const int s = (int)( tEntry.m_uRowid-uTileLo );
+								const bool bOn = ApplyTermOp<HITS> ( V, tOp, d, s, tEntry.m_fTf, tEntry.m_uFields, uEmitBit );
+								if ( HITS && bOn )
+									pHitpos[(size_t)tOp.m_uLeaf*TILE_W+s] = pPreHitpos[i];
+							}
+						} else
+						{
+							const bool bSkippable = bChain && tOp.m_eCode==OP_TERM_AND;
+							for ( uint32_t b=b0+iWarp; b<b1; b+=EVAL_WARPS )
+							{
+								if ( bSkippable )
+								{
+									// no candidate inside this block's rowid range [base_b, base_b+1): never decode it
+									const uint32_t uLo = max ( __ldg ( tIdx.m_pBlkRowid+tLeaf.m_uFirstBlk+b ), uTileLo ) - uTileLo;
+									const uint32_t uHi = ( b+1<tLeaf.m_nBlocks ? min ( __ldg ( tIdx.m_pBlkRowid+tLeaf.m_uFirstBlk+b+1 ), uTileHi ) : uTileHi ) - uTileLo;
+									if ( !AnyAliveInRange ( S.m_dAliveBits, uLo, uHi, iLane ) )
+										continue;
+								}
+								DecodedDoc_t tDoc;
+								DecodeBlock<HITS> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
+								const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
+								if ( !tDoc.m_bValid || tDoc.m_uRowid<uTileLo || tDoc.m_uRowid>=uTileHi || !uFields )
+									continue;
+								const int s = (int)( tDoc.m_uRowid-uTileLo );
+								// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946
+								const float fHits = __uint2float_rn ( tDoc.m_uHits );
+								const float fTf = __fmul_rn ( __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
+								const bool bOn = ApplyTermOp<HITS> ( V, tOp, d, s, fTf, uFields, uEmitBit );
+								if ( HITS && bOn )
+									pHitpos[(size_t)tOp.m_uLeaf*TILE_W+s] = tDoc.m_uHitlistPos;
+							}
+						}
+						__syncthreads();
+						bDirty = false;
 					}
 				} else if ( tOp.m_eCode==OP_NWAY )
 				{
 					// ExtNWay_T::GetDocsChunk, src/searchnode.cpp:3805-3848: candidates = AND of the node's keywords (already in v[dst]);
 					// a candidate survives iff the acceptor emits at least one folded hit
-					if ( HITS )
+					if constexpr ( HITS )
 					{
 						const int j = tOp.m_uArg;
 						const int n = CompactAlive ( V, d, tOp.m_uAliveDst, TILE_W, &S.m_iListCnt );
-						if ( n )
-							__threadfence_block();	// hitpos scratch written by other warps of this CTA
 						for ( int i=tid; i<n; i+=EVAL_THREADS )
 						{
 							const int s = V.m_pList[i];
@@ -673,11 +919,14 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							} else
 								V.Cnt ( d, s ) = 0;
 						}
+						__syncthreads();
+						bDirty = false;
 					}
 				} else
 				{
 					const int r = tOp.m_uSrc;
 					const uint8_t uAd = tOp.m_uAliveDst, uAs = tOp.m_uAliveSrc;
+					#pragma unroll 2
 					for ( int s=tid; s<TILE_W; s+=EVAL_THREADS )
 					{
 						const bool bD = V.Cnt ( d, s )==uAd, bS = V.Cnt ( r, s )==uAs;
@@ -720,8 +969,21 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 							break;
 						}
 					}
+					bDirty = true;
 				}
-				__syncthreads();
+			}
+
+			// where to go next (read the shared cursor state now: the barrier at the end of the tile separates these reads
+			// from the next tile's writes)
+			uint32_t uNextLo = uTileLo+TILE_W;
+			if ( bJump )
+			{
+				const DevLeaf_t & tDrv = q.m_dLeaves[q.m_iDriverLeaf];
+				const uint32_t b1 = S.m_dLeafB1[q.m_iDriverLeaf];
+				uint32_t uNext = S.m_uNextRow;
+				if ( b1<tDrv.m_nBlocks )
+					uNext = min ( uNext, __ldg ( tIdx.m_pBlkRowid+tDrv.m_uFirstBlk+b1 ) );
+				uNextLo = uNext==0xFFFFFFFFu ? 0xFFFFFFFFu : max ( uNextLo, uNext & ~(uint32_t)( TILE_W-1 ) );
 			}
 
 			// rank + filter + push survivors of this tile
@@ -771,6 +1033,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								uint32_t uRank = 0;
 								if ( !uMask )
 									uRank = 1;
+								else if ( q.m_nWeights<=4 )
+									uRank = S.m_dRankTab[uMask & 15u];
 								else
 									for ( int i=0; i<q.m_nWeights; ++i )
 										if ( uMask & ( 1u<<i ) )
@@ -801,7 +1065,279 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 				}
 			}
 			__syncthreads();
+
+			uTileLo = uNextLo;
 		}
+
+		// item epilogue: final selection, publish keys + counters
+		if ( S.m_iPoolCnt>iK )
+		{
+			Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+			Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
+			CtaSelectTopK ( pIn, S.m_iPoolCnt, iK, pOut, S.m_tSel );
+			if ( tid==0 )
+			{
+				S.m_iPoolCnt = iK;
+				S.m_iPoolBuf ^= 1;
+			}
+			__syncthreads();
+		}
+		{
+			#pragma unroll
+			for ( int d=16; d; d>>=1 )
+				iMyTotal += __shfl_xor_sync ( FULL_MASK, iMyTotal, d );
+			if ( iLane==0 && iMyTotal )
+				atomicAdd ( &S.m_uTotal, (unsigned long long)iMyTotal );
+			__syncthreads();
+			const Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+			Key128_t * pDst = P.m_pItemKeys + (size_t)iItem*P.m_iKMax;
+			const int n = S.m_iPoolCnt;
+			for ( int i=tid; i<n; i+=EVAL_THREADS )
+				pDst[i] = pPool[i];
+			if ( tid==0 )
+			{
+				P.m_pItemOut[iItem].m_iTotalFound = (int64_t)S.m_uTotal;
+				P.m_pItemOut[iItem].m_nKeys = n;
+			}
+		}
+	}
+}
+
+#include "stream_kernel.cuh"
+
+//////////////////////////////////////////////////////////////////////////
+// K2: driver-led intersection kernel for pure AND queries (ExtMultiAnd_T::AdvanceQwords, src/searchnode.cpp:2864-2889;
+// the skiplist jump of DiskIndexQword_c::HintRowID/AdvanceTo, src/sphinx.cpp:391-451)
+//////////////////////////////////////////////////////////////////////////
+
+static const int AND_CHUNK_BLOCKS = 128;	///< driver blocks per CTA round: 4096 candidates = what the candidate pool can take
+
+struct AndShared_t
+{
+	DevQuery_t		m_tQ;
+	SelectSmem_t	m_tSel;
+	Key128_t		m_tThr;
+	unsigned long long m_uTotal;
+	int				m_iItem;
+	int				m_iPoolCnt;
+	int				m_iPoolBuf;
+	uint32_t		m_dRankTab[16];
+	float			m_dTf[256];
+	uint32_t		m_dRows[EVAL_WARPS][32];	///< the other keyword's decoded block, for the candidates' lookups
+	uint32_t		m_dHits[EVAL_WARPS][32];
+	uint32_t		m_dFields[EVAL_WARPS][32];
+	uint16_t		m_dRecStart[EVAL_WARPS][34];
+	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
+};
+
+/// Work item = (query, range of the rarest keyword's 32-doc blocks). A warp decodes one driver block: 32 candidate rows, one
+/// per lane, kept in registers. For every other keyword, in the reference's rarest-first order: hot keywords are probed in the
+/// dense store; sparse ones by a binary search of the resident skiplist (block table) per candidate, then only the blocks that
+/// hold a candidate are decoded (each once per warp) and searched. TF*IDF accumulates in that same order.
+__global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
+{
+	__shared__ AndShared_t S;
+	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
+	const DevIndex_t & tIdx = P.m_tIndex;
+	Key128_t * pPool0 = P.m_pPool + (size_t)blockIdx.x*2*P.m_iPoolCap;
+	{
+		const float fHits = __uint2float_rn ( (uint32_t)tid );
+		S.m_dTf[tid & 255] = __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
+	}
+
+	while ( true )
+	{
+		__syncthreads();
+		if ( tid==0 )
+			S.m_iItem = atomicAdd ( P.m_pCounter, 1 );
+		__syncthreads();
+		const int iItem = S.m_iItem;
+		if ( iItem>=P.m_nItems )
+			break;
+		const DevWorkItem_t tItem = P.m_pItems[iItem];
+		{
+			const uint32_t * pSrc = reinterpret_cast<const uint32_t *>( P.m_pQueries+tItem.m_uQuery );
+			uint32_t * pDst = reinterpret_cast<uint32_t *>( &S.m_tQ );
+			for ( int i=tid; i<(int)( sizeof(DevQuery_t)/4 ); i+=EVAL_THREADS )
+				pDst[i] = pSrc[i];
+		}
+		if ( tid==0 )
+		{
+			S.m_iPoolCnt = 0;
+			S.m_iPoolBuf = 0;
+			S.m_tThr.m_uHi = 0; S.m_tThr.m_uLo = 0;
+			S.m_uTotal = 0;
+		}
+		__syncthreads();
+		const DevQuery_t & q = S.m_tQ;
+		const int iK = q.m_iMaxMatches;
+		if ( tid<16 )
+		{
+			uint32_t uSum = 0;
+			for ( int i=0; i<4 && i<q.m_nWeights; ++i )
+				if ( tid & ( 1<<i ) )
+					uSum += (uint32_t)q.m_dWeights[i];
+			S.m_dRankTab[tid] = uSum;
+		}
+		int iMyTotal = 0;
+		const DevLeaf_t & tDrv = q.m_dLeaves[q.m_dOps[0].m_uLeaf];
+
+		for ( uint32_t uChunk=tItem.m_uRowLo; uChunk<tItem.m_uRowHi; uChunk+=AND_CHUNK_BLOCKS )
+		{
+			// compact the candidate pool if this round could overflow it
+			__syncthreads();
+			const int iPoolNow = S.m_iPoolCnt;
+			__syncthreads();	// nobody pushes before everybody has read the level
+			if ( iPoolNow+AND_CHUNK_BLOCKS*32>P.m_iPoolCap )
+			{
+				Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+				Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
+				Key128_t tThr = CtaSelectTopK ( pIn, iPoolNow, iK, pOut, S.m_tSel );
+				if ( tid==0 )
+				{
+					S.m_tThr = tThr;
+					S.m_iPoolCnt = iK;
+					S.m_iPoolBuf ^= 1;
+				}
+				__syncthreads();
+			}
+			const Key128_t tThr = S.m_tThr;
+			Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+			const uint32_t uChunkEnd = min ( uChunk+(uint32_t)AND_CHUNK_BLOCKS, tItem.m_uRowHi );
+
+			for ( uint32_t b=uChunk+iWarp; b<uChunkEnd; b+=EVAL_WARPS )
+			{
+				// the driver block: 32 candidates
+				DecodedDoc_t tDoc;
+				DecodeBlock<false> ( tIdx, tDrv, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
+				const uint32_t uRowid = tDoc.m_uRowid;
+				uint32_t uFields = tDoc.m_uFields & tDrv.m_uQueriedFields;
+				bool bAlive = tDoc.m_bValid && uFields;
+				float fTfidf;
+				{
+					const float fHits = __uint2float_rn ( tDoc.m_uHits );
+					fTfidf = __fmul_rn ( tDoc.m_uHits<255 ? S.m_dTf[tDoc.m_uHits & 255u] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tDrv.m_fIDF );
+				}
+
+				for ( int iOp=1; iOp<q.m_nOps; ++iOp )
+				{
+					if ( !__any_sync ( FULL_MASK, bAlive ) )
+						break;
+					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+					uint32_t uHits = 0, uF = 0;
+					if ( tLeaf.m_iHot>=0 )
+					{
+						if ( bAlive )
+						{
+							const uint32_t v = __ldg ( P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride + uRowid );
+							uHits = v & 255u;
+							uF = uHits ? ( ( v>>8 ) & tLeaf.m_uQueriedFields ) : 0u;
+							if ( uF && uHits==255u )
+								uHits = HotEscapeHits ( P.m_tHot, tLeaf.m_iHot, uRowid );
+						}
+					} else if ( tLeaf.m_nBlocks )
+					{
+						// block that may hold the candidate: the last one whose base rowid <= candidate (FindSpan, src/sphinx.cpp:407-451)
+						const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
+						uint32_t uBlk = 0;
+						if ( bAlive )
+						{
+							uint32_t lo = 0, hi = tLeaf.m_nBlocks;	// first index with base > rowid
+							while ( lo<hi )
+							{
+								const uint32_t mid = lo + ( ( hi-lo )>>1 );
+								if ( __ldg ( pBase+mid )>uRowid ) hi = mid; else lo = mid+1;
+							}
+							uBlk = lo-1;	// base of block 0 is 0, so lo>=1
+						}
+						unsigned uTodo = __ballot_sync ( FULL_MASK, bAlive );
+						while ( uTodo )
+						{
+							const int iLeader = __ffs ( uTodo )-1;
+							const uint32_t uSel = __shfl_sync ( FULL_MASK, uBlk, iLeader );
+							DecodedDoc_t tOther;
+							DecodeBlock<false> ( tIdx, tLeaf, uSel, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tOther );
+							S.m_dRows[iWarp][iLane] = tOther.m_bValid ? tOther.m_uRowid : 0xFFFFFFFFu;
+							S.m_dHits[iWarp][iLane] = tOther.m_uHits;
+							S.m_dFields[iWarp][iLane] = tOther.m_uFields;
+							__syncwarp();
+							const bool bMine = bAlive && uBlk==uSel;
+							if ( bMine )
+							{
+								// rows ascend (invalid tail = 0xFFFFFFFF): lower bound over 32 entries
+								int l = 0;
+								#pragma unroll
+								for ( int iStep=16; iStep; iStep>>=1 )
+									if ( S.m_dRows[iWarp][l+iStep-1]<uRowid )
+										l += iStep;
+								if ( S.m_dRows[iWarp][l]==uRowid )
+								{
+									uHits = S.m_dHits[iWarp][l];
+									uF = S.m_dFields[iWarp][l] & tLeaf.m_uQueriedFields;
+								}
+							}
+							uTodo &= ~__ballot_sync ( FULL_MASK, bMine );
+							__syncwarp();
+						}
+					}
+					if ( bAlive )
+					{
+						if ( uF )
+						{
+							// ExtMultiAnd_T::GetDocsChunk, src/searchnode.cpp:2821-2832
+							const float fHits = __uint2float_rn ( uHits );
+							const float fBase = uHits<255 ? S.m_dTf[uHits & 255u] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
+							fTfidf = __fadd_rn ( fTfidf, __fmul_rn ( fBase, tLeaf.m_fIDF ) );
+							uFields |= uF;
+						} else
+							bAlive = false;
+					}
+				}
+
+				// rank + filter + push
+				bool bPush = false;
+				Key128_t tKey;
+				if ( bAlive )
+				{
+					bool bOk = PassFilters ( tIdx, q, uRowid );
+					int iWeight = 1;
+					if ( bOk && q.m_eRanker!=2 )
+					{
+						const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( fTfidf, 0.5f ), 1000.0f ) );
+						uint32_t uRank = 0;
+						if ( !uFields )
+							uRank = 1;
+						else if ( q.m_nWeights<=4 )
+							uRank = S.m_dRankTab[uFields & 15u];
+						else
+							for ( int i=0; i<q.m_nWeights; ++i )
+								if ( uFields & ( 1u<<i ) )
+									uRank += (uint32_t)q.m_dWeights[i];
+						iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+					}
+					if ( bOk && tIdx.m_pDead )
+						bOk = !( ( __ldg ( tIdx.m_pDead+( uRowid>>5 ) )>>( uRowid & 31 ) ) & 1u );
+					if ( bOk )
+					{
+						iWeight = (int)( (uint32_t)iWeight*(uint32_t)q.m_iIndexWeight );
+						++iMyTotal;
+						tKey = MakeKey ( tIdx, q, uRowid, iWeight );
+						bPush = !KeyLess ( tKey, tThr );
+					}
+				}
+				const unsigned m = __ballot_sync ( FULL_MASK, bPush );
+				if ( m )
+				{
+					int iBase = 0;
+					if ( iLane==0 )
+						iBase = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
+					iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
+					if ( bPush )
+						pPool[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+				}
+			}
+		}
+		__syncthreads();
 
 		// item epilogue: final selection, publish keys + counters
 		if ( S.m_iPoolCnt>iK )
@@ -1035,6 +1571,75 @@ int EvalOccupancy ( int nStack, bool bHits )
 	if ( e!=cudaSuccess )
 		return 1;
 	return n>0 ? n : 1;
+}
+
+/// single-level programs (pure OR / single keyword) take 512-row mini-tiles, deeper ones 256-row (shared memory per level)
+static int StreamMiniWidth ( int nStack )
+{
+	return nStack<=1 ? 512 : 256;
+}
+
+size_t StreamDynSmemBytes ( int nStack )
+{
+	return (size_t)nStack*EVAL_WARPS*StreamMiniWidth ( nStack )*9;
+}
+
+cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream )
+{
+	size_t iDyn = StreamDynSmemBytes ( nStack );
+	if ( StreamMiniWidth ( nStack )==512 )
+	{
+		cudaError_t e = cudaFuncSetAttribute ( stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		if ( e!=cudaSuccess )
+			return e;
+		stream_kernel<512><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
+	} else
+	{
+		cudaError_t e = cudaFuncSetAttribute ( stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		if ( e!=cudaSuccess )
+			return e;
+		stream_kernel<256><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
+	}
+	return cudaGetLastError();
+}
+
+int StreamOccupancy ( int nStack )
+{
+	int n = 0;
+	size_t iDyn = StreamDynSmemBytes ( nStack );
+	cudaError_t e;
+	if ( StreamMiniWidth ( nStack )==512 )
+	{
+		cudaFuncSetAttribute ( stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, stream_kernel<512>, EVAL_THREADS, iDyn );
+	} else
+	{
+		cudaFuncSetAttribute ( stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, stream_kernel<256>, EVAL_THREADS, iDyn );
+	}
+	if ( e!=cudaSuccess )
+		return 1;
+	return n>0 ? n : 1;
+}
+
+cudaError_t LaunchAnd ( const EvalParams_t & P, int nCtas, cudaStream_t tStream )
+{
+	and_kernel<<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
+	return cudaGetLastError();
+}
+
+int AndOccupancy()
+{
+	int n = 0;
+	if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, and_kernel, EVAL_THREADS, 0 )!=cudaSuccess )
+		return 1;
+	return n>0 ? n : 1;
+}
+
+cudaError_t LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream )
+{
+	hot_decode_kernel<<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
+	return cudaGetLastError();
 }
 
 cudaError_t LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream )

@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -15,6 +16,8 @@
 
 namespace mgpu
 {
+
+static const int AND_CHUNK = 128;	///< = AND_CHUNK_BLOCKS of kernels.cu: driver blocks per CTA round
 
 #define CUDA_TRY(_expr,_err) \
 	do { cudaError_t _e = (_expr); if ( _e!=cudaSuccess ) { _err = std::string ( #_expr ": " ) + cudaGetErrorString ( _e ); return MGPU_E_CUDA; } } while (0)
@@ -623,11 +626,41 @@ struct Planner_c
 			d.m_uAliveRoot = iAlive;
 		}
 
+		// AND chains: where to resume when a tile has no candidate left (consecutive TERM_ANDs into the same level, plus
+		// the acceptor of a phrase/proximity node; an empty vector stays empty through all of them)
+		for ( int i=0; i<d.m_nOps; ++i )
+			if ( d.m_dOps[i].m_eCode==OP_TERM_AND || d.m_dOps[i].m_eCode==OP_TERM_SET )
+			{
+				int j = i+1;
+				while ( j<d.m_nOps && d.m_dOps[j].m_eCode==OP_TERM_AND && d.m_dOps[j].m_uDst==d.m_dOps[i].m_uDst )
+					++j;
+				if ( j<d.m_nOps && d.m_dOps[j].m_eCode==OP_NWAY && d.m_dOps[j].m_uDst==d.m_dOps[i].m_uDst )
+					++j;
+				d.m_dOps[i].m_uSrc = (uint8_t)( 1+j );
+			}
+
+		if ( getenv ( "MGPU_NO_CHAIN" ) )
+			for ( int i=0; i<d.m_nOps; ++i )
+				if ( d.m_dOps[i].m_eCode<=OP_TERM_MAYBE )
+					d.m_dOps[i].m_uSrc = 0;
+		for ( int i=0; i<d.m_nOps; ++i )
+			if ( d.m_dOps[i].m_eCode<=OP_TERM_MAYBE && !( d.m_dOps[i].m_eCode==OP_TERM_AND && d.m_dOps[i].m_uSrc ) )
+				d.m_uPreMask |= 1u<<d.m_dOps[i].m_uLeaf;
+		for ( int i=0; i<d.m_nOps; ++i )
+			if ( d.m_dOps[i].m_eCode==OP_TERM_SET || d.m_dOps[i].m_eCode==OP_TERM_OR )
+				d.m_uOrigMask |= 1u<<d.m_dOps[i].m_uLeaf;
+		d.m_iDriverLeaf = -1;
+		if ( !getenv ( "MGPU_NO_JUMP" ) && d.m_nOps>0 && d.m_dOps[0].m_eCode==OP_TERM_SET && (int)d.m_dOps[0].m_uSrc==d.m_nOps+1 )
+			d.m_iDriverLeaf = d.m_dOps[0].m_uLeaf;
+
 		d.m_nLeaves = (int)m_dLeaves.size();
+		m_tOut.m_dLeafTerms.assign ( m_dLeaves.size(), nullptr );
 		for ( size_t i=0; i<m_dLeaves.size(); ++i )
 		{
 			const PLeaf_t & l = m_dLeaves[i];
 			DevLeaf_t & t = d.m_dLeaves[i];
+			t.m_iHot = -1;
+			m_tOut.m_dLeafTerms[i] = l.m_pTerm;
 			if ( l.m_pTerm )
 			{
 				t.m_uFirstBlk = l.m_pTerm->m_uFirstBlk;
@@ -747,6 +780,9 @@ Batch_c::~Batch_c()
 	if ( m_tEv0 ) cudaEventDestroy ( m_tEv0 );
 	if ( m_tEv1 ) cudaEventDestroy ( m_tEv1 );
 	if ( m_tEv2 ) cudaEventDestroy ( m_tEv2 );
+	if ( m_tEvHot ) cudaEventDestroy ( m_tEvHot );
+	for ( int c=0; c<NUM_CLASSES; ++c )
+		if ( m_dEvClass[c] ) cudaEventDestroy ( m_dEvClass[c] );
 }
 
 static int Pow2Ceil ( int n )
@@ -765,45 +801,130 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	for ( int i=0; i<nQueries; ++i )
 		PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
 
-	// runnable queries, biggest first (items are handed out in array order: longest-processing-time-first).
-	// Two classes, one launch each: doc-only queries (eval_kernel<false>) and hit-consuming ones (eval_kernel<true>).
-	std::vector<int> dOrder[2];
-	int64_t dTotalCost[2] = { 0, 0 };
+	// runnable queries; three launch classes (see engine.h)
+	std::vector<int> dDocOnly, dOrder[NUM_CLASSES];
 	for ( int i=0; i<nQueries; ++i )
 		if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
 		{
-			const int c = m_dPlans[i].m_tDev.m_bNeedHits ? 1 : 0;
-			dOrder[c].push_back ( i );
-			dTotalCost[c] += m_dPlans[i].m_iCost;
-			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
+			if ( m_dPlans[i].m_tDev.m_bNeedHits )
+				dOrder[1].push_back ( i );
+			else
+				dDocOnly.push_back ( i );
 			m_iKMax = std::max ( m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
 			m_tStats.algorithmic_bytes += m_dPlans[i].m_iAlgBytes;
 			m_tStats.postings += m_dPlans[i].m_iCost;
 		}
-	if ( dOrder[0].empty() && dOrder[1].empty() )
+	if ( dDocOnly.empty() && dOrder[1].empty() )
 		return MGPU_OK;
 
 	const uint32_t uRows = pIndex->m_tDev.m_uRows;
 	const int nTiles = (int)( ( (uint64_t)uRows+TILE_W-1 )/TILE_W );
 	int iMaxKeysPerQuery = 1;
-	for ( int c=0; c<2; ++c )
+
+	// hot keywords of the batch: shared by >= 2 doc-only queries and present in >= 1/8 of the rows -> dense store
+	if ( pIndex->m_tHdr.m_dFields.size()<=8 && !getenv ( "MGPU_NO_HOT" ) )
+	{
+		std::unordered_map<const TermInfo_t*,int> hUse;
+		for ( int i : dDocOnly )
+			for ( const TermInfo_t * p : m_dPlans[i].m_dLeafTerms )
+				if ( p && (int64_t)p->m_iDocs*8>=(int64_t)uRows )
+					++hUse[p];
+		std::vector<std::pair<int64_t,const TermInfo_t*>> dHot;
+		for ( const auto & kv : hUse )
+			if ( kv.second>=2 )
+				dHot.push_back ( { (int64_t)kv.second*kv.first->m_iDocs, kv.first } );
+		std::sort ( dHot.begin(), dHot.end(), [] ( const auto & a, const auto & b ) { return a.first>b.first || ( a.first==b.first && a.second->m_uFirstBlk<b.second->m_uFirstBlk ); } );
+		m_iHotStride = (int64_t)nTiles*TILE_W;
+		const size_t nMaxHot = std::min<size_t> ( 256, ( (size_t)4<<30 )/( 2*(size_t)m_iHotStride ) );	// <= 4 GB of store
+		if ( dHot.size()>nMaxHot )
+			dHot.resize ( nMaxHot );
+		std::unordered_map<const TermInfo_t*,int> hSlot;
+		int64_t iEscapeCap = 16;
+		for ( const auto & t : dHot )
+		{
+			const TermInfo_t * p = t.second;
+			hSlot[p] = (int)m_dHotTerms.size();
+			DevLeaf_t tLeaf {};
+			tLeaf.m_uFirstBlk = p->m_uFirstBlk;
+			tLeaf.m_nBlocks = p->m_nBlocks;
+			tLeaf.m_nDocs = (uint32_t)p->m_iDocs;
+			tLeaf.m_uDoclistEnd = (uint64_t)( p->m_iDoclistOffset+p->m_iDoclistLength-1 );
+			tLeaf.m_uQueriedFields = 0xFFFFFFFFu;
+			tLeaf.m_iHot = -1;
+			m_dHotTerms.push_back ( tLeaf );
+			iEscapeCap += std::min<int64_t> ( p->m_iDocs, p->m_iHits/255 );	// at most hits/255 documents can hold >= 255 hits
+		}
+		m_iHotEscapeCap = (int)std::min<int64_t> ( iEscapeCap, 1<<26 );
+		if ( !m_dHotTerms.empty() )
+			for ( int i : dDocOnly )
+			{
+				PlannedQuery_t & p = m_dPlans[i];
+				for ( size_t l=0; l<p.m_dLeafTerms.size(); ++l )
+				{
+					auto it = hSlot.find ( p.m_dLeafTerms[l] );
+					if ( it!=hSlot.end() )
+					{
+						p.m_tDev.m_dLeaves[l].m_iHot = it->second;
+						if ( ( p.m_tDev.m_uOrigMask>>l ) & 1u )
+							p.m_tDev.m_bOrigHot = 1;
+						if ( p.m_tDev.m_iDriverLeaf==(int)l )
+							p.m_tDev.m_iDriverLeaf = -1;
+					}
+				}
+			}
+	}
+
+	m_bStream = getenv ( "MGPU_OLD_DENSE" )==nullptr;
+	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
+	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
+	for ( int i : dDocOnly )
+		dOrder [ ( m_dPlans[i].m_tDev.m_iDriverLeaf>=0 && !bNoAndKernel ) ? 2 : ( m_dPlans[i].m_nStack>1 && m_bStream ) ? 3 : 0 ].push_back ( i );
+
+	// estimated work of a query in its class (decides how many items it is cut into)
+	auto fnWork = [&] ( const PlannedQuery_t & p, int c ) -> int64_t
+	{
+		int64_t iWork = 0;
+		if ( c==2 )
+		{
+			const TermInfo_t * pDrv = p.m_dLeafTerms[p.m_tDev.m_iDriverLeaf];
+			return pDrv ? (int64_t)pDrv->m_iDocs*p.m_tDev.m_nLeaves : 0;
+		}
+		for ( int l=0; l<p.m_tDev.m_nLeaves; ++l )
+			iWork += ( ( c==0 || c==3 ) && p.m_tDev.m_dLeaves[l].m_iHot>=0 ) ? (int64_t)uRows/4 : ( p.m_dLeafTerms[l] ? p.m_dLeafTerms[l]->m_iDocs : 0 );
+		return ( c==0 || c==3 ) ? iWork + uRows/16 : iWork;
+	};
+
+	for ( int c=0; c<NUM_CLASSES; ++c )
 	{
 		m_dFirstItem[c] = (int)m_dItems.size();
 		if ( dOrder[c].empty() )
 			continue;
-		const int iOcc = EvalOccupancy ( m_dStack[c], c==1 );
+		int64_t iTotalWork = 0;
+		for ( int i : dOrder[c] )
+		{
+			iTotalWork += fnWork ( m_dPlans[i], c );
+			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
+		}
+		const int iOcc = c==2 ? AndOccupancy() : ( ( c==0 || c==3 ) && m_bStream ) ? StreamOccupancy ( m_dStack[c] ) : EvalOccupancy ( m_dStack[c], c==1 );
 		const int nMaxCtas = pIndex->m_nSMs*iOcc;
-		const int64_t iTarget = std::max<int64_t> ( c ? 32768 : 262144, dTotalCost[c]/( (int64_t)nMaxCtas*4 ) );
+		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
 
 		struct Part_t { int m_iQuery; int m_nParts; int64_t m_iCostPerPart; };
 		std::vector<Part_t> dParts;
 		for ( int i : dOrder[c] )
 		{
 			const PlannedQuery_t & p = m_dPlans[i];
-			int64_t nParts = ( p.m_iCost+iTarget-1 )/iTarget;
+			const int64_t iWork = fnWork ( p, c );
+			int64_t nParts = ( iWork+iTarget-1 )/iTarget;
 			int iCap = std::max ( 1, 131072/std::max ( 1, p.m_tDev.m_iMaxMatches ) );
-			nParts = std::max<int64_t> ( 1, std::min<int64_t> ( nParts, std::min ( { nTiles, 64, iCap } ) ) );
-			dParts.push_back ( { i, (int)nParts, p.m_iCost/nParts } );
+			int64_t nUnits = nTiles;
+			if ( c==2 )
+			{
+				const TermInfo_t * pDrv = p.m_dLeafTerms[p.m_tDev.m_iDriverLeaf];
+				nUnits = pDrv ? ( pDrv->m_nBlocks+AND_CHUNK-1 )/AND_CHUNK : 1;
+			}
+			nParts = std::max<int64_t> ( 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, iCap } ) ) );
+			dParts.push_back ( { i, (int)nParts, iWork/nParts } );
 		}
 		std::stable_sort ( dParts.begin(), dParts.end(), [] ( const Part_t & a, const Part_t & b ) { return a.m_iCostPerPart>b.m_iCostPerPart; } );
 
@@ -813,13 +934,22 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			q.m_iFirstItem = (int)m_dItems.size();
 			q.m_nItems = t.m_nParts;
 			const int iDevQuery = (int)m_dDevQueries.size();
+			int64_t nUnits = nTiles, iUnit = TILE_W, iLimit = uRows;
+			if ( c==2 )
+			{
+				// units = chunks of the driver keyword's blocks
+				const TermInfo_t * pDrv = m_dPlans[t.m_iQuery].m_dLeafTerms[q.m_iDriverLeaf];
+				iLimit = pDrv ? pDrv->m_nBlocks : 0;
+				nUnits = ( iLimit+AND_CHUNK-1 )/AND_CHUNK;
+				iUnit = AND_CHUNK;
+			}
 			for ( int p=0; p<t.m_nParts; ++p )
 			{
-				uint64_t uT0 = (uint64_t)nTiles*p/t.m_nParts, uT1 = (uint64_t)nTiles*( p+1 )/t.m_nParts;
+				uint64_t uT0 = (uint64_t)nUnits*p/t.m_nParts, uT1 = (uint64_t)nUnits*( p+1 )/t.m_nParts;
 				DevWorkItem_t tItem;
 				tItem.m_uQuery = (uint32_t)iDevQuery;
-				tItem.m_uRowLo = (uint32_t)( uT0*TILE_W );
-				tItem.m_uRowHi = (uint32_t)std::min<uint64_t> ( uT1*TILE_W, uRows );
+				tItem.m_uRowLo = (uint32_t)( uT0*iUnit );
+				tItem.m_uRowHi = (uint32_t)std::min<uint64_t> ( uT1*iUnit, (uint64_t)iLimit );
 				tItem.m_uPad = 0;
 				m_dItems.push_back ( tItem );
 			}
@@ -829,17 +959,28 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 		m_dCtas[c] = std::min ( nMaxCtas, (int)m_dItems.size()-m_dFirstItem[c] );
 	}
+	m_dFirstItem[NUM_CLASSES] = (int)m_dItems.size();
 
 	const int nDevQ = (int)m_dDevQueries.size();
 	const int nItems = (int)m_dItems.size();
-	m_iPoolCap = m_iKMax + 2*TILE_W;
+	m_iPoolCap = m_iKMax + 32768;	// >= K + what one round of any kernel can push (stream: 8 mini-tiles x 8 warps x 512 rows)
 	m_iScratchStride = 2*Pow2Ceil ( iMaxKeysPerQuery );
 
 	CUDA_TRY ( m_dQ.Alloc ( nDevQ ), m_sError );
 	CUDA_TRY ( m_dI.Alloc ( nItems ), m_sError );
-	CUDA_TRY ( m_dCounter.Alloc ( 2 ), m_sError );
-	CUDA_TRY ( m_dPool.Alloc ( (size_t)std::max ( m_dCtas[0], m_dCtas[1] )*2*m_iPoolCap ), m_sError );
+	CUDA_TRY ( m_dCounter.Alloc ( NUM_CLASSES ), m_sError );
+	CUDA_TRY ( m_dPool.Alloc ( (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3] } )*2*m_iPoolCap ), m_sError );
 	CUDA_TRY ( m_dHitpos.Alloc ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W ), m_sError );
+	CUDA_TRY ( m_dPre.Alloc ( (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32 ), m_sError );
+	CUDA_TRY ( m_dPreHitpos.Alloc ( (size_t)m_dCtas[1]*PRE_BLOCKS*32 ), m_sError );
+	if ( !m_dHotTerms.empty() )
+	{
+		CUDA_TRY ( m_dHotDesc.Alloc ( m_dHotTerms.size() ), m_sError );
+		CUDA_TRY ( m_dHotData.Alloc ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
+		CUDA_TRY ( m_dHotEscape.Alloc ( (size_t)m_iHotEscapeCap*3 ), m_sError );
+		CUDA_TRY ( m_dHotEscapeCount.Alloc ( 1 ), m_sError );
+		CUDA_TRY ( cudaMemcpy ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice ), m_sError );
+	}
 	CUDA_TRY ( m_dItemKeys.Alloc ( (size_t)nItems*m_iKMax ), m_sError );
 	CUDA_TRY ( m_dItemOut.Alloc ( nItems ), m_sError );
 	CUDA_TRY ( m_dScratch.Alloc ( (size_t)nDevQ*m_iScratchStride ), m_sError );
@@ -862,6 +1003,12 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( cudaEventCreate ( &m_tEv0 ), m_sError );
 	CUDA_TRY ( cudaEventCreate ( &m_tEv1 ), m_sError );
 	CUDA_TRY ( cudaEventCreate ( &m_tEv2 ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEvHot ), m_sError );
+	for ( int c=0; c<NUM_CLASSES; ++c )
+		CUDA_TRY ( cudaEventCreate ( &m_dEvClass[c] ), m_sError );
+	m_tStats.queries_dense = (int32_t)( dOrder[0].size()+dOrder[3].size() );
+	m_tStats.queries_hits = (int32_t)dOrder[1].size();
+	m_tStats.queries_and = (int32_t)dOrder[2].size();
 	return MGPU_OK;
 }
 
@@ -873,14 +1020,38 @@ int Batch_c::Run()
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	cudaStream_t s = pIndex->m_tStream;
 
-	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, 2*sizeof(int32_t), s ), m_sError );
+	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
 
-	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
+	// K0: decode the batch's hot keywords once into the dense store
+	DevHotStore_t tHot {};
 	int nLaunches = 1;
-	for ( int c=0; c<2; ++c )
+	CUDA_TRY ( cudaEventRecord ( m_tEvHot, s ), m_sError );
+	if ( !m_dHotTerms.empty() )
+	{
+		CUDA_TRY ( cudaMemsetAsync ( m_dHotData.m_p, 0, m_dHotTerms.size()*(size_t)m_iHotStride*2, s ), m_sError );
+		CUDA_TRY ( cudaMemsetAsync ( m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
+		HotDecodeParams_t H {};
+		H.m_tIndex = pIndex->m_tDev;
+		H.m_pTerms = m_dHotDesc.m_p;
+		H.m_nHot = (int)m_dHotTerms.size();
+		H.m_iEscapeCap = m_iHotEscapeCap;
+		H.m_pData = m_dHotData.m_p;
+		H.m_pEscape = m_dHotEscape.m_p;
+		H.m_pEscapeCount = m_dHotEscapeCount.m_p;
+		H.m_iStride = m_iHotStride;
+		CUDA_TRY ( LaunchHotDecode ( H, pIndex->m_nSMs*8, s ), m_sError );
+		++nLaunches;
+		tHot.m_pData = m_dHotData.m_p;
+		tHot.m_pEscape = m_dHotEscape.m_p;
+		tHot.m_pEscapeCount = m_dHotEscapeCount.m_p;
+		tHot.m_iStride = m_iHotStride;
+		tHot.m_nHot = (int)m_dHotTerms.size();
+	}
+	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
+	for ( int c=0; c<NUM_CLASSES; ++c )
 	{
 		const int iFirst = m_dFirstItem[c];
-		const int nClassItems = ( c==0 ? m_dFirstItem[1] : (int)m_dItems.size() ) - iFirst;
+		const int nClassItems = m_dFirstItem[c+1] - iFirst;
 		if ( nClassItems<=0 )
 			continue;
 		EvalParams_t P {};
@@ -895,7 +1066,17 @@ int Batch_c::Run()
 		P.m_pCounter = m_dCounter.m_p + c;
 		P.m_iKMax = m_iKMax;
 		P.m_pHitpos = m_dHitpos.m_p;
-		CUDA_TRY ( LaunchEval ( P, m_dStack[c], c==1, m_dCtas[c], s ), m_sError );
+		P.m_pPre = m_dPre.m_p;
+		P.m_pPreHitpos = m_dPreHitpos.m_p;
+		P.m_tHot = tHot;
+		if ( c==2 )
+			CUDA_TRY ( LaunchAnd ( P, m_dCtas[c], s ), m_sError );
+		else if ( ( c==0 || c==3 ) && m_bStream )
+			CUDA_TRY ( LaunchStream ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
+		else
+			CUDA_TRY ( LaunchEval ( P, m_dStack[c], c==1, m_dCtas[c], s ), m_sError );
+		CUDA_TRY ( cudaEventRecord ( m_dEvClass[c], s ), m_sError );
+		m_dClassRan[c] = true;
 		++nLaunches;
 	}
 	CUDA_TRY ( cudaEventRecord ( m_tEv1, s ), m_sError );
@@ -930,6 +1111,19 @@ int Batch_c::Sync()
 	if ( m_bRan && !m_dDevQueries.empty() )
 	{
 		cudaEventElapsedTime ( &m_tStats.eval_kernel_ms, m_tEv0, m_tEv1 );
+		cudaEventElapsedTime ( &m_tStats.hot_decode_ms, m_tEvHot, m_tEv0 );
+		m_tStats.hot_terms = (int32_t)m_dHotTerms.size();
+		cudaEvent_t tPrev = m_tEv0;
+		float dMs[NUM_CLASSES] = { 0.0f, 0.0f, 0.0f, 0.0f };
+		for ( int c=0; c<NUM_CLASSES; ++c )
+			if ( m_dClassRan[c] )
+			{
+				cudaEventElapsedTime ( &dMs[c], tPrev, m_dEvClass[c] );
+				tPrev = m_dEvClass[c];
+			}
+		m_tStats.dense_kernel_ms = dMs[0]+dMs[3];
+		m_tStats.hits_kernel_ms = dMs[1];
+		m_tStats.and_kernel_ms = dMs[2];
 		cudaEventElapsedTime ( &m_tStats.merge_kernel_ms, m_tEv1, m_tEv2 );
 	}
 	return MGPU_OK;

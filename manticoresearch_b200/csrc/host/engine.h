@@ -95,6 +95,7 @@ struct PlannedQuery_t
 	int64_t			m_iCost = 0;			///< sum of df over leaves (postings)
 	int64_t			m_iAlgBytes = 0;		///< SURVEY 8(d) algorithmic bytes (doclists + skiplists)
 	std::vector<mgpu_wordstat> m_dWordStats;
+	std::vector<const TermInfo_t*> m_dLeafTerms;	///< dictionary entry of every leaf (null = keyword not in the index)
 	int				m_iFirstIntKeyShift = -1;
 	int				m_iFirstIntKeyBits = 0;
 	bool			m_bFirstIntKeyDesc = false;
@@ -111,9 +112,13 @@ public:
 	std::vector<DevQuery_t>		m_dDevQueries;	///< only the runnable ones, in order
 	std::vector<int>			m_dDevToQuery;	///< device query -> batch query index
 	std::vector<DevWorkItem_t>	m_dItems;
-	int		m_dStack[2] = { 1, 1 };		///< per launch class: [0] doc-only queries, [1] hit-consuming queries
-	int		m_dCtas[2] = { 0, 0 };
-	int		m_dFirstItem[2] = { 0, 0 };
+	/// launch classes: [0] doc-only queries with a single-level program (stream_kernel<512>), [1] hit-consuming queries
+	/// (eval_kernel<true>), [2] pure AND queries led by a sparse keyword (and_kernel), [3] deeper doc-only programs (stream_kernel<256>)
+	static const int NUM_CLASSES = 4;
+	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1 };
+	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0 };
+	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0 };
+	bool	m_bStream = true;			///< class 0 runs on stream_kernel (eval_kernel<false> only for A/B comparisons)
 	int		m_iKMax = 1;
 	int		m_iPoolCap = 0;
 	int		m_iScratchStride = 0;
@@ -126,6 +131,20 @@ public:
 	DevBuf_T<int64_t>		m_dOutDocid, m_dOutTotal;
 	DevBuf_T<int32_t>		m_dOutCount, m_dOutSlot;
 	DevBuf_T<uint64_t>		m_dHitpos;		///< hit stage scratch: hitlist position per (CTA, leaf, tile slot)
+	DevBuf_T<PreEntry_t>	m_dPre;			///< tile predecode scratch
+	DevBuf_T<uint64_t>		m_dPreHitpos;
+
+	// dense hot-term store of this batch (rebuilt by every Run(): decode once per batch instead of once per query)
+	std::vector<DevLeaf_t>	m_dHotTerms;
+	DevBuf_T<DevLeaf_t>		m_dHotDesc;
+	DevBuf_T<uint16_t>		m_dHotData;
+	DevBuf_T<uint32_t>		m_dHotEscape;
+	DevBuf_T<int32_t>		m_dHotEscapeCount;
+	int64_t					m_iHotStride = 0;
+	int						m_iHotEscapeCap = 0;
+	cudaEvent_t				m_tEvHot = nullptr;
+	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr };
+	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false };
 
 	cudaEvent_t		m_tEv0 = nullptr, m_tEv1 = nullptr, m_tEv2 = nullptr;
 	mgpu_batch_stats m_tStats {};
@@ -143,6 +162,11 @@ public:
 size_t		EvalDynSmemBytes ( int nStack, bool bHits );
 int			EvalOccupancy ( int nStack, bool bHits );
 cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, bool bHits, int nCtas, cudaStream_t tStream );
+cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );
+int			StreamOccupancy ( int nStack );
+cudaError_t	LaunchAnd ( const EvalParams_t & P, int nCtas, cudaStream_t tStream );
+int			AndOccupancy();
+cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
 				Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream );

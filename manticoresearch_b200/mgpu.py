@@ -71,7 +71,9 @@ class c_result(C.Structure):
 class c_batch_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("work_items", C.c_int64), ("algorithmic_bytes", C.c_int64),
                 ("postings", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float)]
+                ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float), ("hot_decode_ms", C.c_float), ("hot_terms", C.c_int32),
+                ("dense_kernel_ms", C.c_float), ("hits_kernel_ms", C.c_float), ("and_kernel_ms", C.c_float),
+                ("queries_dense", C.c_int32), ("queries_hits", C.c_int32), ("queries_and", C.c_int32)]
 
 
 class c_build_doc_input(C.Structure):

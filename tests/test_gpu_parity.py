@@ -152,6 +152,43 @@ def test_hit_rankers_over_random_trees(synth):
     assert _compare_batch(synth, queries, allow_unsupported=0.05) <= 15
 
 
+def test_hot_store_escape_and_plain_format(tmp_path):
+    """dense hot-term store edge cases: documents with >= 255 hits of a shared keyword (escape list), a keyword present in
+    every row, ragged last tile; plus the same corpus written with hit_format=plain"""
+    import random
+    rng = random.Random(7)
+    docs = []
+    for i in range(4500):
+        body = [("common", p + 1) for p in range(rng.choice([1, 1, 2, 3, 300 if i % 911 == 0 else 4]))]
+        n0 = len(body)
+        if i % 3 == 0:
+            body += [("third", n0 + 1), ("third", n0 + 2)]
+        if i % 7 == 0:
+            body.append(("seventh", len(body) + 1))
+        title = [("common", 1)] if i % 5 == 0 else [("rare%d" % (i % 40), 1)]
+        docs.append({"id": 10 + i, "fields": [title, body], "attrs": []})
+    for inline in (True, False):
+        prefix = str(tmp_path / ("hot_%d" % inline))
+        M.build_index(prefix, ["title", "body"], docs, hit_format_inline=inline)
+        gpu, cpu = M.Index(prefix, device=0), helpers.OracleIndex(prefix)
+        try:
+            qs = [M.Query(M.OR(M.kw("common", 1), M.kw("seventh", 2)), ranker=M.RANK_BM25, field_weights=[3, 1], max_matches=5000),
+                  M.Query(M.AND(M.kw("common", 1), M.kw("third", 2)), ranker=M.RANK_BM25, max_matches=100),
+                  M.Query(M.ANDNOT(M.kw("common", 1), M.kw("third", 2)), ranker=M.RANK_BM25, max_matches=100),
+                  M.Query(M.MAYBE(M.kw("seventh", 1), M.kw("common", 2)), ranker=M.RANK_BM25, max_matches=100),
+                  M.Query(M.OR(M.AND(M.kw("third", 1), M.kw("rare3", 2)), M.AND(M.kw("common", 3).fields(1), M.kw("seventh", 4))), ranker=M.RANK_BM25, max_matches=100),
+                  M.Query(M.AND(M.kw("rare7", 1), M.kw("third", 2), M.kw("common", 3)), ranker=M.RANK_BM25, max_matches=100),
+                  M.Query(M.AND(M.kw("common", 1), M.kw("third", 2)), ranker=M.RANK_PROXIMITY_BM25, max_matches=100),
+                  M.Query(M.PHRASE([("common", 1), ("third", 2)]), ranker=M.RANK_PROXIMITY_BM25, max_matches=100)]
+            g, c = gpu.search(qs), cpu.search(qs)
+            for i in range(len(qs)):
+                helpers.assert_same_results(g.get(i), c.get(i), ctx="hot store, inline=%s, query %d" % (inline, i))
+            assert g.get(0)["total_found"] == 4500
+        finally:
+            gpu.close()
+            cpu.close()
+
+
 def test_golden_vectors_on_gpu(golden_cases, golden_indexes):
     """the reference's own golden results (model.bin of test_019/037/322/116/114 + gtest WeightBoundary): every query must run on the CUDA path"""
     ran = 0
