@@ -210,6 +210,7 @@ def run_ours(args):
     index.set_stream(stream.cuda_stream)
 
     # ---- queries; global IDF inputs when sharded (CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs)
+    from manticoresearch_b200 import distributed as D
     queries = workload.cfg2_queries(n=args.queries, max_matches=100)
     if args.only:
         def shape(q):
@@ -220,34 +221,15 @@ def run_ours(args):
         queries = [q for q in queries if shape(q) == args.only]
     K = 100
     if world > 1:
-        words = sorted({k.word for q in queries for k in q.keywords()})
-        df = torch.tensor([(index.word_stats(w) or (0, 0))[0] for w in words], dtype=torch.int64, device=dev)
-        dist.all_reduce(df)
-        gdf = dict(zip(words, df.tolist()))
-        for q in queries:
-            q.total_docs = args.docs
-            q.word_docs = [gdf[k.word] for k in q.keywords()]
+        gdf = D.global_keyword_docs(lambda w: (index.word_stats(w) or (0, 0))[0], queries, dev)
+        D.apply_global_idf(queries, args.docs, gdf)
 
     nq = len(queries)
-    keys = torch.zeros((nq, K, 2), dtype=torch.int64, device=dev)
-    counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
-    totals = torch.zeros((nq,), dtype=torch.int64, device=dev)
-    if world > 1:
-        all_keys = torch.zeros((world, nq, K, 2), dtype=torch.int64, device=dev)
-        all_counts = torch.zeros((world, nq), dtype=torch.int32, device=dev)
-        out_keys = torch.zeros((nq, K, 2), dtype=torch.int64, device=dev)
-        out_counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
-    lib = M.lib()
+    merger = D.ShardMerger(nq, K, dev, local_rank, stream) if world > 1 else None
 
     def merge_step(batch):
         """local top-K keys -> NCCL all-gather -> GPU merge; total_found via all-reduce"""
-        batch.export_keys(keys.data_ptr(), counts.data_ptr(), totals.data_ptr(), K)
-        dist.all_gather_into_tensor(all_keys, keys)
-        dist.all_gather_into_tensor(all_counts, counts)
-        dist.all_reduce(totals)
-        rc = lib.mgpu_merge_shard_keys(local_rank, all_keys.data_ptr(), all_counts.data_ptr(), world, nq, K,
-                                       out_keys.data_ptr(), out_counts.data_ptr(), stream.cuda_stream)
-        assert rc == 0
+        merger.merge(batch)
 
     def barrier():
         if world > 1:
@@ -296,21 +278,23 @@ def run_ours(args):
     job_bytes, job_postings = float(agg[0].item()), float(agg[1].item())
 
     # ---- end to end through the C ABI with host buffers: plan + H2D + kernels + D2H every step
+    packed = M.pack_queries(queries)            # the caller's host buffers: flattened XQNode trees in, result arrays out
+    host_results = M.ResultSet(queries)
     barrier()
     e2e_t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(args.steps):
         if world == 1:
-            rs = index.search(queries)          # mgpu_search_batch
+            rs = index.search_packed(packed, nq, host_results)          # mgpu_search_batch
             assert rs.results[0].status == 0
             b2 = None
         else:
             b2 = index.prepare(queries)
             b2.run()
             merge_step(b2)
-            host_keys = out_keys.cpu()
-            host_counts = out_counts.cpu()
-            host_totals = totals.cpu()
+            host_keys = merger.out_keys.cpu()
+            host_counts = merger.out_counts.cpu()
+            host_totals = merger.totals.cpu()
             d2h = host_keys.numel() * 8 + host_counts.numel() * 4 + host_totals.numel() * 8
             h2d = b2.stats()["h2d_bytes"]
             b2.free()
@@ -326,6 +310,7 @@ def run_ours(args):
         b3.fetch()
         s3 = b3.stats()
         h2d, d2h = s3["h2d_bytes"], s3["d2h_bytes"]
+        host_ms = {k: s3[k] for k in ("host_plan_ms", "host_setup_ms", "host_fetch_ms")}
         b3.free()
 
     if rank == 0:
@@ -342,7 +327,8 @@ def run_ours(args):
                        "index_build_s": round(build_s, 1), "index_load_s": round(load_s, 1), "unsupported_queries": n_unsupported},
             "postings_per_sec": job_postings / (ms_per_step / 1000.0),
             "compressed_GBps": job_bytes / (ms_per_step / 1000.0) / 1e9,
-            "e2e": {"value": nq / (e2e_s / args.steps), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": nq / (e2e_s / args.steps), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1000.0 * e2e_s / args.steps, "host_ms": host_ms if world == 1 else None},
             "gpu_launches": int(args.steps * (st["kernel_launches"] + (1 if world > 1 else 0))),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": "eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -216,6 +216,8 @@ typedef struct mgpu_batch_stats {
 	/* per launch class: dense-tile kernel (doc-only queries), hit-stage kernel, intersection kernel (pure AND queries) */
 	float			dense_kernel_ms, hits_kernel_ms, and_kernel_ms;
 	int32_t			queries_dense, queries_hits, queries_and;
+	/* host wall-clock of the batch: query planning, buffer setup + plan upload, result download + unpack */
+	float			host_plan_ms, host_setup_ms, host_fetch_ms;
 } mgpu_batch_stats;
 int				mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out );
 

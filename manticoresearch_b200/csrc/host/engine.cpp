@@ -5,9 +5,11 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -797,9 +799,32 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 {
 	m_pIndex = pIndex;
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
+	const auto tStart = std::chrono::steady_clock::now();
 	m_dPlans.resize ( nQueries );
-	for ( int i=0; i<nQueries; ++i )
-		PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
+	{
+		// planning is per query and read-only on the index: spread big batches over the host cores
+		int nThreads = (int)std::min<unsigned> ( std::max ( 1u, std::thread::hardware_concurrency() ), 16u );
+		nThreads = std::max ( 1, std::min ( nThreads, nQueries/512 ) );
+		if ( getenv ( "MGPU_PLAN_THREADS" ) )
+			nThreads = std::max ( 1, atoi ( getenv ( "MGPU_PLAN_THREADS" ) ) );
+		auto fnPlan = [&] ( int iFrom, int iTo )
+		{
+			for ( int i=iFrom; i<iTo; ++i )
+				PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
+		};
+		if ( nThreads<=1 )
+			fnPlan ( 0, nQueries );
+		else
+		{
+			std::vector<std::thread> dThreads;
+			for ( int t=0; t<nThreads; ++t )
+				dThreads.emplace_back ( fnPlan, (int)( (int64_t)nQueries*t/nThreads ), (int)( (int64_t)nQueries*( t+1 )/nThreads ) );
+			for ( auto & t : dThreads )
+				t.join();
+		}
+	}
+	const auto tPlanned = std::chrono::steady_clock::now();
+	m_tStats.host_plan_ms = std::chrono::duration<float,std::milli> ( tPlanned-tStart ).count();
 
 	// runnable queries; three launch classes (see engine.h)
 	std::vector<int> dDocOnly, dOrder[NUM_CLASSES];
@@ -969,16 +994,13 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( m_dQ.Alloc ( nDevQ ), m_sError );
 	CUDA_TRY ( m_dI.Alloc ( nItems ), m_sError );
 	CUDA_TRY ( m_dCounter.Alloc ( NUM_CLASSES ), m_sError );
-	CUDA_TRY ( m_dPool.Alloc ( (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3] } )*2*m_iPoolCap ), m_sError );
-	CUDA_TRY ( m_dHitpos.Alloc ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W ), m_sError );
-	CUDA_TRY ( m_dPre.Alloc ( (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32 ), m_sError );
-	CUDA_TRY ( m_dPreHitpos.Alloc ( (size_t)m_dCtas[1]*PRE_BLOCKS*32 ), m_sError );
+	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3] } )*2*m_iPoolCap;
+	m_nHitpos = (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W;
+	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32;
+	m_nPreHitpos = (size_t)m_dCtas[1]*PRE_BLOCKS*32;
 	if ( !m_dHotTerms.empty() )
 	{
 		CUDA_TRY ( m_dHotDesc.Alloc ( m_dHotTerms.size() ), m_sError );
-		CUDA_TRY ( m_dHotData.Alloc ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
-		CUDA_TRY ( m_dHotEscape.Alloc ( (size_t)m_iHotEscapeCap*3 ), m_sError );
-		CUDA_TRY ( m_dHotEscapeCount.Alloc ( 1 ), m_sError );
 		CUDA_TRY ( cudaMemcpy ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice ), m_sError );
 	}
 	CUDA_TRY ( m_dItemKeys.Alloc ( (size_t)nItems*m_iKMax ), m_sError );
@@ -1009,6 +1031,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	m_tStats.queries_dense = (int32_t)( dOrder[0].size()+dOrder[3].size() );
 	m_tStats.queries_hits = (int32_t)dOrder[1].size();
 	m_tStats.queries_and = (int32_t)dOrder[2].size();
+	m_tStats.host_setup_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tPlanned ).count();
 	return MGPU_OK;
 }
 
@@ -1022,28 +1045,41 @@ int Batch_c::Run()
 
 	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
 
+	// run-time scratch comes from the index (grow-only, shared by all batches; runs are serialised on the index stream)
+	Index_c::RunScratch_t & tScr = pIndex->m_tScratch;
+	CUDA_TRY ( tScr.m_dPool.Grow ( m_nPool ), m_sError );
+	CUDA_TRY ( tScr.m_dHitpos.Grow ( m_nHitpos ), m_sError );
+	CUDA_TRY ( tScr.m_dPre.Grow ( m_nPre ), m_sError );
+	CUDA_TRY ( tScr.m_dPreHitpos.Grow ( m_nPreHitpos ), m_sError );
+	if ( !m_dHotTerms.empty() )
+	{
+		CUDA_TRY ( tScr.m_dHotData.Grow ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
+		CUDA_TRY ( tScr.m_dHotEscape.Grow ( (size_t)m_iHotEscapeCap*3 ), m_sError );
+		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1 ), m_sError );
+	}
+
 	// K0: decode the batch's hot keywords once into the dense store
 	DevHotStore_t tHot {};
 	int nLaunches = 1;
 	CUDA_TRY ( cudaEventRecord ( m_tEvHot, s ), m_sError );
 	if ( !m_dHotTerms.empty() )
 	{
-		CUDA_TRY ( cudaMemsetAsync ( m_dHotData.m_p, 0, m_dHotTerms.size()*(size_t)m_iHotStride*2, s ), m_sError );
-		CUDA_TRY ( cudaMemsetAsync ( m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
+		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotData.m_p, 0, m_dHotTerms.size()*(size_t)m_iHotStride*2, s ), m_sError );
+		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
 		HotDecodeParams_t H {};
 		H.m_tIndex = pIndex->m_tDev;
 		H.m_pTerms = m_dHotDesc.m_p;
 		H.m_nHot = (int)m_dHotTerms.size();
 		H.m_iEscapeCap = m_iHotEscapeCap;
-		H.m_pData = m_dHotData.m_p;
-		H.m_pEscape = m_dHotEscape.m_p;
-		H.m_pEscapeCount = m_dHotEscapeCount.m_p;
+		H.m_pData = tScr.m_dHotData.m_p;
+		H.m_pEscape = tScr.m_dHotEscape.m_p;
+		H.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
 		H.m_iStride = m_iHotStride;
 		CUDA_TRY ( LaunchHotDecode ( H, pIndex->m_nSMs*8, s ), m_sError );
 		++nLaunches;
-		tHot.m_pData = m_dHotData.m_p;
-		tHot.m_pEscape = m_dHotEscape.m_p;
-		tHot.m_pEscapeCount = m_dHotEscapeCount.m_p;
+		tHot.m_pData = tScr.m_dHotData.m_p;
+		tHot.m_pEscape = tScr.m_dHotEscape.m_p;
+		tHot.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
 		tHot.m_iStride = m_iHotStride;
 		tHot.m_nHot = (int)m_dHotTerms.size();
 	}
@@ -1060,14 +1096,14 @@ int Batch_c::Run()
 		P.m_pItems = m_dI.m_p + iFirst;
 		P.m_nItems = nClassItems;
 		P.m_iPoolCap = m_iPoolCap;
-		P.m_pPool = m_dPool.m_p;
+		P.m_pPool = tScr.m_dPool.m_p;
 		P.m_pItemKeys = m_dItemKeys.m_p + (size_t)iFirst*m_iKMax;
 		P.m_pItemOut = m_dItemOut.m_p + iFirst;
 		P.m_pCounter = m_dCounter.m_p + c;
 		P.m_iKMax = m_iKMax;
-		P.m_pHitpos = m_dHitpos.m_p;
-		P.m_pPre = m_dPre.m_p;
-		P.m_pPreHitpos = m_dPreHitpos.m_p;
+		P.m_pHitpos = tScr.m_dHitpos.m_p;
+		P.m_pPre = tScr.m_dPre.m_p;
+		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;
 		if ( c==2 )
 			CUDA_TRY ( LaunchAnd ( P, m_dCtas[c], s ), m_sError );
@@ -1131,6 +1167,12 @@ int Batch_c::Sync()
 
 int Batch_c::Fetch ( mgpu_result * pResults )
 {
+	struct FetchTimer_t
+	{
+		mgpu_batch_stats & m_tStats;
+		std::chrono::steady_clock::time_point m_tStart = std::chrono::steady_clock::now();
+		~FetchTimer_t() { m_tStats.host_fetch_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-m_tStart ).count(); }
+	} tTimer { m_tStats };
 	const int nQueries = (int)m_dPlans.size();
 	for ( int i=0; i<nQueries; ++i )
 	{

@@ -41,6 +41,11 @@ struct DevBuf_T
 			return cudaSuccess;
 		return cudaMalloc ( (void**)&m_p, n*sizeof(T) );
 	}
+	/// grow-only: keeps the allocation when it is already big enough (scratch reused across batches)
+	cudaError_t Grow ( size_t n )
+	{
+		return n<=m_n ? cudaSuccess : Alloc ( n );
+	}
 	void Free()
 	{
 		if ( m_p )
@@ -67,6 +72,18 @@ public:
 	std::mutex		m_tLock;		///< serialises batches on this handle
 
 	std::unordered_map<std::string,TermInfo_t> m_hTerms;
+
+	/// Scratch that only lives during a batch run (candidate pools, predecode lists, hit positions, the dense hot-term
+	/// store): owned by the index and re-used by every batch, so a batch costs no big cudaMalloc. Contents never survive a run.
+	struct RunScratch_t
+	{
+		DevBuf_T<Key128_t>		m_dPool;
+		DevBuf_T<uint64_t>		m_dHitpos, m_dPreHitpos;
+		DevBuf_T<PreEntry_t>	m_dPre;
+		DevBuf_T<uint16_t>		m_dHotData;
+		DevBuf_T<uint32_t>		m_dHotEscape;
+		DevBuf_T<int32_t>		m_dHotEscapeCount;
+	} m_tScratch;
 
 	DevBuf_T<uint8_t>	m_dSpd, m_dSpp;
 	DevBuf_T<uint32_t>	m_dSpa, m_dDead;
@@ -126,20 +143,15 @@ public:
 	DevBuf_T<DevQuery_t>	m_dQ;
 	DevBuf_T<DevWorkItem_t>	m_dI;
 	DevBuf_T<int32_t>		m_dCounter;
-	DevBuf_T<Key128_t>		m_dPool, m_dItemKeys, m_dScratch, m_dOutKeys;
+	DevBuf_T<Key128_t>		m_dItemKeys, m_dScratch, m_dOutKeys;
+	size_t	m_nPool = 0, m_nHitpos = 0, m_nPre = 0, m_nPreHitpos = 0;	///< what Run() needs from the index's RunScratch_t
 	DevBuf_T<DevItemOut_t>	m_dItemOut;
 	DevBuf_T<int64_t>		m_dOutDocid, m_dOutTotal;
 	DevBuf_T<int32_t>		m_dOutCount, m_dOutSlot;
-	DevBuf_T<uint64_t>		m_dHitpos;		///< hit stage scratch: hitlist position per (CTA, leaf, tile slot)
-	DevBuf_T<PreEntry_t>	m_dPre;			///< tile predecode scratch
-	DevBuf_T<uint64_t>		m_dPreHitpos;
 
 	// dense hot-term store of this batch (rebuilt by every Run(): decode once per batch instead of once per query)
 	std::vector<DevLeaf_t>	m_dHotTerms;
 	DevBuf_T<DevLeaf_t>		m_dHotDesc;
-	DevBuf_T<uint16_t>		m_dHotData;
-	DevBuf_T<uint32_t>		m_dHotEscape;
-	DevBuf_T<int32_t>		m_dHotEscapeCount;
 	int64_t					m_iHotStride = 0;
 	int						m_iHotEscapeCap = 0;
 	cudaEvent_t				m_tEvHot = nullptr;

@@ -73,7 +73,8 @@ class c_batch_stats(C.Structure):
                 ("postings", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float), ("hot_decode_ms", C.c_float), ("hot_terms", C.c_int32),
                 ("dense_kernel_ms", C.c_float), ("hits_kernel_ms", C.c_float), ("and_kernel_ms", C.c_float),
-                ("queries_dense", C.c_int32), ("queries_hits", C.c_int32), ("queries_and", C.c_int32)]
+                ("queries_dense", C.c_int32), ("queries_hits", C.c_int32), ("queries_and", C.c_int32),
+                ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float)]
 
 
 class c_build_doc_input(C.Structure):
@@ -417,6 +418,13 @@ class Index:
         if rc != MGPU_OK:
             self._err(rc)
         return rs
+
+    def search_packed(self, packed, n, result_set):
+        """mgpu_search_batch on already marshalled host buffers (pack_queries / ResultSet): the bare C-ABI call"""
+        rc = self._lib.mgpu_search_batch(self._h, packed, n, result_set.results)
+        if rc != MGPU_OK:
+            self._err(rc)
+        return result_set
 
     def prepare(self, queries):
         return Batch(self, queries)

@@ -227,3 +227,61 @@ def test_full_size_properties(synth):
     assert r_or == r_or2
     w = r_or["weight"]
     assert all(w[i] > w[i + 1] or (w[i] == w[i + 1] and r_or["rowid"][i] < r_or["rowid"][i + 1]) for i in range(len(w) - 1))
+
+
+def test_rowid_range_shards_merge_equals_unsharded(tmp_path):
+    """config 4 shape on one GPU: 3 logical rowid-range shards searched separately (global IDF inputs, global rowids in the
+    keys), K keys per shard merged by shard_merge_kernel == the unsharded oracle, for doc-only and hit-ranked queries"""
+    import torch
+    from manticoresearch_b200 import distributed as D
+    total, world, K = 30000, 3, 64
+    full = str(tmp_path / "full")
+    M.build_synthetic(full, M.SynthParams(total, vocab=1 << 15))
+    cpu = helpers.OracleIndex(full)
+    shards = []
+    for r in range(world):
+        first, n = D.shard_range(total, r, world)
+        prefix = str(tmp_path / ("shard%d" % r))
+        M.build_synthetic(prefix, M.SynthParams(n, first_doc=first, vocab=1 << 15))
+        shards.append(M.Index(prefix, device=0, rowid_base=first))
+    try:
+        def make():
+            return (workload.cfg2_queries(n=120, max_rank=8000, max_matches=K, with_andnot=0.15)
+                    + workload.cfg1_queries(n=40, max_matches=K) + workload.cfg3_queries(M.SynthParams(total, vocab=1 << 15), n=40, max_matches=K))
+        queries, plain = make(), make()
+        words = sorted({k.word for q in queries for k in q.keywords()})
+        gdf = {w: sum((s.word_stats(w) or (0, 0))[0] for s in shards) for w in words}
+        D.apply_global_idf(queries, total, gdf)
+        nq = len(queries)
+        dev = torch.device("cuda", 0)
+        stream = torch.cuda.current_stream()
+        all_keys = torch.zeros((world, nq, K, 2), dtype=torch.int64, device=dev)
+        all_counts = torch.zeros((world, nq), dtype=torch.int32, device=dev)
+        totals = torch.zeros((world, nq), dtype=torch.int64, device=dev)
+        for r, s in enumerate(shards):
+            b = s.prepare(queries)
+            b.run()
+            b.export_keys(all_keys[r].data_ptr(), all_counts[r].data_ptr(), totals[r].data_ptr(), K)
+            b.free()
+        out_keys = torch.zeros((nq, K, 2), dtype=torch.int64, device=dev)
+        out_counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        rc = M.lib().mgpu_merge_shard_keys(0, all_keys.data_ptr(), all_counts.data_ptr(), world, nq, K, out_keys.data_ptr(), out_counts.data_ptr(), stream.cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        keys = out_keys.cpu().numpy().astype("uint64")
+        counts = out_counts.cpu().tolist()
+        tot = totals.sum(0).cpu().tolist()
+        ref = cpu.search(plain)
+        nonempty = 0
+        for qi in range(nq):
+            e = ref.get(qi)
+            got = [D.unpack_key(int(keys[qi, i, 0]), int(keys[qi, i, 1])) for i in range(counts[qi])]
+            assert [g[0] for g in got] == e["rowid"], ("rowid/order", qi)
+            assert [g[1] for g in got] == e["weight"], ("weight", qi)
+            assert tot[qi] == e["total_found"], ("total_found", qi)
+            nonempty += e["total_found"] > 0
+        assert nonempty > nq // 2
+    finally:
+        for s in shards:
+            s.close()
+        cpu.close()
