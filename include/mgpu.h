@@ -213,9 +213,12 @@ typedef struct mgpu_batch_stats {
 	float			merge_kernel_ms;
 	float			hot_decode_ms;       /* K0: the batch's shared hot keywords decoded once into the dense store */
 	int32_t			hot_terms;
-	/* per launch class: dense-tile kernel (doc-only queries), hit-stage kernel, intersection kernel (pure AND queries) */
-	float			dense_kernel_ms, hits_kernel_ms, and_kernel_ms;
-	int32_t			queries_dense, queries_hits, queries_and;
+	/* per launch class: [0] stream_kernel<512> (doc-only queries, single-level programs), [1] eval_kernel<hits> (hit-consuming
+	 * rankers, phrase/proximity), [2] and_kernel (pure AND queries led by a sparse keyword), [3] stream_kernel<256> (deeper programs) */
+	float			class_ms[4];
+	int64_t			class_bytes[4];      /* algorithmic bytes of the class's queries */
+	int32_t			class_queries[4];
+	int32_t			pad0;
 	/* host wall-clock of the batch: query planning, buffer setup + plan upload, result download + unpack */
 	float			host_plan_ms, host_setup_ms, host_fetch_ms;
 } mgpu_batch_stats;

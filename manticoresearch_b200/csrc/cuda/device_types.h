@@ -23,6 +23,7 @@ static const int STAGE_BYTES = 896;		///< per-warp staging: 15 B alignment head 
 static const int MAX_PHRASE_WORDS = 16;	///< keywords per phrase/proximity node on the GPU path
 static const int MAX_NWAY = 4;			///< phrase/proximity nodes per query
 static const int PRE_BLOCKS = MAX_LEAVES*( TILE_W/32+2 );	///< predecode scratch per CTA: a keyword has at most TILE_W/32+2 blocks overlapping a tile
+static const int MAX_GROUPS = 8;		///< AND groups of a DNF program handled by the intersection kernel
 static const int NWAY_MAX_SPAN = 31;	///< max (last atom pos - first atom pos) of a phrase/proximity node: bounds the FSM state
 
 struct DevIndex_t
@@ -158,6 +159,9 @@ struct DevQuery_t
 	uint32_t	m_uOrigMask;			///< leaves whose op can bring a document into the result (SET / OR operands)
 	int32_t		m_bOrigHot;				///< one of those is a hot (dense) keyword: every mini-tile has to be visited
 	int32_t		m_iPad;
+	int32_t		m_nGroups;				///< >0: the program is an OR of AND groups (DNF; 1 = pure AND): op ranges below
+	uint8_t		m_dGroupOp0[MAX_GROUPS];
+	uint8_t		m_dGroupOps[MAX_GROUPS];
 	int32_t		m_iDriverLeaf;			///< pure AND program opened by this (sparse) keyword: tiles without its postings are skipped; -1 = none
 };
 

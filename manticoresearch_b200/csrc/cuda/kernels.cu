@@ -1130,6 +1130,101 @@ struct AndShared_t
 	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
 };
 
+/// Does the keyword hold the lane's candidate row? Warp-cooperative: hot keywords are probed in the dense store; sparse ones by a
+/// binary search of the resident block table per candidate (FindSpan, src/sphinx.cpp:407-451), then only the distinct blocks that
+/// may hold a candidate are decoded (each once per warp) and searched. Returns the queried field mask (0 = absent) and the hit count.
+__device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, const DevHotStore_t & tHot, const DevLeaf_t & tLeaf, uint32_t uRowid, bool bActive,
+	AndShared_t & S, int iWarp, int iLane, uint32_t & uHitsOut )
+{
+	uint32_t uHits = 0, uF = 0;
+	if ( tLeaf.m_iHot>=0 )
+	{
+		if ( bActive )
+		{
+			const uint32_t v = __ldg ( tHot.m_pData + (size_t)tLeaf.m_iHot*tHot.m_iStride + uRowid );
+			uHits = v & 255u;
+			uF = uHits ? ( ( v>>8 ) & tLeaf.m_uQueriedFields ) : 0u;
+			if ( uF && uHits==255u )
+				uHits = HotEscapeHits ( tHot, tLeaf.m_iHot, uRowid );
+		}
+	} else if ( tLeaf.m_nBlocks )
+	{
+		const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
+		uint32_t uBlk = 0;
+		if ( bActive )
+		{
+			uint32_t lo = 0, hi = tLeaf.m_nBlocks;	// first index with base > rowid
+			while ( lo<hi )
+			{
+				const uint32_t mid = lo + ( ( hi-lo )>>1 );
+				if ( __ldg ( pBase+mid )>uRowid ) hi = mid; else lo = mid+1;
+			}
+			uBlk = lo-1;	// base of block 0 is 0, so lo>=1
+		}
+		unsigned uTodo = __ballot_sync ( FULL_MASK, bActive );
+		while ( uTodo )
+		{
+			const int iLeader = __ffs ( uTodo )-1;
+			const uint32_t uSel = __shfl_sync ( FULL_MASK, uBlk, iLeader );
+			DecodedDoc_t tOther;
+			DecodeBlock<false> ( tIdx, tLeaf, uSel, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tOther );
+			S.m_dRows[iWarp][iLane] = tOther.m_bValid ? tOther.m_uRowid : 0xFFFFFFFFu;
+			S.m_dHits[iWarp][iLane] = tOther.m_uHits;
+			S.m_dFields[iWarp][iLane] = tOther.m_uFields;
+			__syncwarp();
+			const bool bMine = bActive && uBlk==uSel;
+			if ( bMine )
+			{
+				// rows ascend (invalid tail = 0xFFFFFFFF): lower bound over 32 entries
+				int l = 0;
+				#pragma unroll
+				for ( int iStep=16; iStep; iStep>>=1 )
+					if ( S.m_dRows[iWarp][l+iStep-1]<uRowid )
+						l += iStep;
+				if ( S.m_dRows[iWarp][l]==uRowid )
+				{
+					uHits = S.m_dHits[iWarp][l];
+					uF = S.m_dFields[iWarp][l] & tLeaf.m_uQueriedFields;
+				}
+			}
+			uTodo &= ~__ballot_sync ( FULL_MASK, bMine );
+			__syncwarp();
+		}
+	}
+	uHitsOut = uHits;
+	return uF;
+}
+
+/// one AND group (ops [iOp0, iOp0+nOps) = SET, AND, AND...) evaluated on the lanes' candidate rows by probing, in the reference's
+/// rarest-first order; iSkipOp = op whose keyword is already accounted for (the driver), -1 = probe all. Accumulates into fT / uFields.
+__device__ __forceinline__ bool ProbeGroup ( const DevIndex_t & tIdx, const DevHotStore_t & tHot, const DevQuery_t & q, int iOp0, int nOps, int iSkipOp,
+	uint32_t uRowid, bool bActive, AndShared_t & S, int iWarp, int iLane, float & fT, uint32_t & uFields )
+{
+	for ( int iOp=iOp0; iOp<iOp0+nOps; ++iOp )
+	{
+		if ( iOp==iSkipOp )
+			continue;
+		if ( !__any_sync ( FULL_MASK, bActive ) )
+			break;
+		const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+		uint32_t uHits;
+		const uint32_t uF = WarpProbeKeyword ( tIdx, tHot, tLeaf, uRowid, bActive, S, iWarp, iLane, uHits );
+		if ( bActive )
+		{
+			if ( uF )
+			{
+				// ExtMultiAnd_T::GetDocsChunk, src/searchnode.cpp:2821-2832
+				const float fHits = __uint2float_rn ( uHits );
+				const float fTf = __fmul_rn ( uHits<255 ? S.m_dTf[uHits & 255u] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
+				fT = ( iOp==iOp0 ) ? fTf : __fadd_rn ( fT, fTf );
+				uFields |= uF;
+			} else
+				bActive = false;
+		}
+	}
+	return bActive;
+}
+
 /// Work item = (query, range of the rarest keyword's 32-doc blocks). A warp decodes one driver block: 32 candidate rows, one
 /// per lane, kept in registers. For every other keyword, in the reference's rarest-first order: hot keywords are probed in the
 /// dense store; sparse ones by a binary search of the resident skiplist (block table) per candidate, then only the blocks that
@@ -1180,7 +1275,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 			S.m_dRankTab[tid] = uSum;
 		}
 		int iMyTotal = 0;
-		const DevLeaf_t & tDrv = q.m_dLeaves[q.m_dOps[0].m_uLeaf];
+		// the item's AND group (DNF programs: OR of AND groups; a pure AND query is one group) and its driver = rarest keyword
+		const int iGroup = (int)tItem.m_uPad;
+		const int iOp0 = q.m_dGroupOp0[iGroup], nGroupOps = q.m_dGroupOps[iGroup];
+		const DevLeaf_t & tDrv = q.m_dLeaves[q.m_dOps[iOp0].m_uLeaf];
 
 		for ( uint32_t uChunk=tItem.m_uRowLo; uChunk<tItem.m_uRowHi; uChunk+=AND_CHUNK_BLOCKS )
 		{
@@ -1219,78 +1317,29 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 					fTfidf = __fmul_rn ( tDoc.m_uHits<255 ? S.m_dTf[tDoc.m_uHits & 255u] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tDrv.m_fIDF );
 				}
 
-				for ( int iOp=1; iOp<q.m_nOps; ++iOp )
+				// the rest of this group
+				bAlive = ProbeGroup ( tIdx, P.m_tHot, q, iOp0, nGroupOps, iOp0, uRowid, bAlive, S, iWarp, iLane, fTfidf, uFields );
+
+				// DNF: a document that also matches an earlier group is emitted by that group's items; later groups that match add
+				// their TF*IDF in group order (ExtOr_c: left + right, src/searchnode.cpp:3486-3504)
+				for ( int g=0; g<q.m_nGroups && q.m_nGroups>1; ++g )
 				{
+					if ( g==iGroup )
+						continue;
 					if ( !__any_sync ( FULL_MASK, bAlive ) )
 						break;
-					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
-					uint32_t uHits = 0, uF = 0;
-					if ( tLeaf.m_iHot>=0 )
+					float fT = 0.0f;
+					uint32_t uF = 0;
+					const bool bMatch = ProbeGroup ( tIdx, P.m_tHot, q, q.m_dGroupOp0[g], q.m_dGroupOps[g], -1, uRowid, bAlive, S, iWarp, iLane, fT, uF );
+					if ( bMatch )
 					{
-						if ( bAlive )
-						{
-							const uint32_t v = __ldg ( P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride + uRowid );
-							uHits = v & 255u;
-							uF = uHits ? ( ( v>>8 ) & tLeaf.m_uQueriedFields ) : 0u;
-							if ( uF && uHits==255u )
-								uHits = HotEscapeHits ( P.m_tHot, tLeaf.m_iHot, uRowid );
-						}
-					} else if ( tLeaf.m_nBlocks )
-					{
-						// block that may hold the candidate: the last one whose base rowid <= candidate (FindSpan, src/sphinx.cpp:407-451)
-						const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
-						uint32_t uBlk = 0;
-						if ( bAlive )
-						{
-							uint32_t lo = 0, hi = tLeaf.m_nBlocks;	// first index with base > rowid
-							while ( lo<hi )
-							{
-								const uint32_t mid = lo + ( ( hi-lo )>>1 );
-								if ( __ldg ( pBase+mid )>uRowid ) hi = mid; else lo = mid+1;
-							}
-							uBlk = lo-1;	// base of block 0 is 0, so lo>=1
-						}
-						unsigned uTodo = __ballot_sync ( FULL_MASK, bAlive );
-						while ( uTodo )
-						{
-							const int iLeader = __ffs ( uTodo )-1;
-							const uint32_t uSel = __shfl_sync ( FULL_MASK, uBlk, iLeader );
-							DecodedDoc_t tOther;
-							DecodeBlock<false> ( tIdx, tLeaf, uSel, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tOther );
-							S.m_dRows[iWarp][iLane] = tOther.m_bValid ? tOther.m_uRowid : 0xFFFFFFFFu;
-							S.m_dHits[iWarp][iLane] = tOther.m_uHits;
-							S.m_dFields[iWarp][iLane] = tOther.m_uFields;
-							__syncwarp();
-							const bool bMine = bAlive && uBlk==uSel;
-							if ( bMine )
-							{
-								// rows ascend (invalid tail = 0xFFFFFFFF): lower bound over 32 entries
-								int l = 0;
-								#pragma unroll
-								for ( int iStep=16; iStep; iStep>>=1 )
-									if ( S.m_dRows[iWarp][l+iStep-1]<uRowid )
-										l += iStep;
-								if ( S.m_dRows[iWarp][l]==uRowid )
-								{
-									uHits = S.m_dHits[iWarp][l];
-									uF = S.m_dFields[iWarp][l] & tLeaf.m_uQueriedFields;
-								}
-							}
-							uTodo &= ~__ballot_sync ( FULL_MASK, bMine );
-							__syncwarp();
-						}
-					}
-					if ( bAlive )
-					{
-						if ( uF )
-						{
-							// ExtMultiAnd_T::GetDocsChunk, src/searchnode.cpp:2821-2832
-							const float fHits = __uint2float_rn ( uHits );
-							const float fBase = uHits<255 ? S.m_dTf[uHits & 255u] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
-							fTfidf = __fadd_rn ( fTfidf, __fmul_rn ( fBase, tLeaf.m_fIDF ) );
-							uFields |= uF;
-						} else
+						if ( g<iGroup )
 							bAlive = false;
+						else
+						{
+							fTfidf = __fadd_rn ( fTfidf, fT );
+							uFields |= uF;
+						}
 					}
 				}
 

@@ -655,6 +655,48 @@ struct Planner_c
 		if ( !getenv ( "MGPU_NO_JUMP" ) && d.m_nOps>0 && d.m_dOps[0].m_eCode==OP_TERM_SET && (int)d.m_dOps[0].m_uSrc==d.m_nOps+1 )
 			d.m_iDriverLeaf = d.m_dOps[0].m_uLeaf;
 
+		// DNF shape: [SET AND*] then ( [SET AND*] on level 1 + VEC_OR(0,1) | TERM_OR on level 0 )*  -> groups for the intersection kernel
+		{
+			int i = 0, nGroups = 0;
+			bool bOk = d.m_nOps>0;
+			auto fnGroup = [&] ( int iDst ) -> bool
+			{
+				if ( i>=d.m_nOps || d.m_dOps[i].m_eCode!=OP_TERM_SET || d.m_dOps[i].m_uDst!=iDst || nGroups>=MAX_GROUPS )
+					return false;
+				int j = i+1;
+				while ( j<d.m_nOps && d.m_dOps[j].m_eCode==OP_TERM_AND && d.m_dOps[j].m_uDst==iDst )
+					++j;
+				d.m_dGroupOp0[nGroups] = (uint8_t)i;
+				d.m_dGroupOps[nGroups] = (uint8_t)( j-i );
+				++nGroups;
+				i = j;
+				return true;
+			};
+			bOk = bOk && fnGroup ( 0 );
+			while ( bOk && i<d.m_nOps )
+			{
+				if ( d.m_dOps[i].m_eCode==OP_TERM_OR && d.m_dOps[i].m_uDst==0 && nGroups<MAX_GROUPS )
+				{
+					d.m_dGroupOp0[nGroups] = (uint8_t)i;
+					d.m_dGroupOps[nGroups] = 1;
+					++nGroups;
+					++i;
+				} else if ( fnGroup ( 1 ) && i<d.m_nOps && d.m_dOps[i].m_eCode==OP_VEC_OR && d.m_dOps[i].m_uDst==0 && d.m_dOps[i].m_uSrc==1 )
+					++i;
+				else
+					bOk = false;
+			}
+			bool bAnyMulti = false;
+			for ( int g=0; g<nGroups; ++g )
+				bAnyMulti |= d.m_dGroupOps[g]>1;
+			d.m_nGroups = ( bOk && bAnyMulti && !getenv ( "MGPU_NO_DNF" ) ) ? nGroups : ( d.m_iDriverLeaf>=0 ? 1 : 0 );
+			if ( d.m_nGroups==1 && d.m_iDriverLeaf>=0 )
+			{
+				d.m_dGroupOp0[0] = 0;
+				d.m_dGroupOps[0] = (uint8_t)d.m_nOps;
+			}
+		}
+
 		d.m_nLeaves = (int)m_dLeaves.size();
 		m_tOut.m_dLeafTerms.assign ( m_dLeaves.size(), nullptr );
 		for ( size_t i=0; i<m_dLeaves.size(); ++i )
@@ -903,7 +945,16 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
 	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
 	for ( int i : dDocOnly )
-		dOrder [ ( m_dPlans[i].m_tDev.m_iDriverLeaf>=0 && !bNoAndKernel ) ? 2 : ( m_dPlans[i].m_nStack>1 && m_bStream ) ? 3 : 0 ].push_back ( i );
+	{
+		// intersection kernel: DNF programs (1 group = pure AND) whose every group is led by a sparse keyword
+		DevQuery_t & q = m_dPlans[i].m_tDev;
+		bool bDnf = q.m_nGroups>0 && !bNoAndKernel;
+		for ( int g=0; g<q.m_nGroups && bDnf; ++g )
+			bDnf = q.m_dLeaves[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf].m_iHot<0;
+		if ( !bDnf )
+			q.m_nGroups = 0;
+		dOrder [ bDnf ? 2 : ( m_dPlans[i].m_nStack>1 && m_bStream ) ? 3 : 0 ].push_back ( i );
+	}
 
 	// estimated work of a query in its class (decides how many items it is cut into)
 	auto fnWork = [&] ( const PlannedQuery_t & p, int c ) -> int64_t
@@ -911,8 +962,12 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		int64_t iWork = 0;
 		if ( c==2 )
 		{
-			const TermInfo_t * pDrv = p.m_dLeafTerms[p.m_tDev.m_iDriverLeaf];
-			return pDrv ? (int64_t)pDrv->m_iDocs*p.m_tDev.m_nLeaves : 0;
+			for ( int g=0; g<p.m_tDev.m_nGroups; ++g )
+			{
+				const TermInfo_t * pDrv = p.m_dLeafTerms[p.m_tDev.m_dOps[p.m_tDev.m_dGroupOp0[g]].m_uLeaf];
+				iWork += pDrv ? (int64_t)pDrv->m_iDocs*p.m_tDev.m_nLeaves : 0;
+			}
+			return iWork;
 		}
 		for ( int l=0; l<p.m_tDev.m_nLeaves; ++l )
 			iWork += ( ( c==0 || c==3 ) && p.m_tDev.m_dLeaves[l].m_iHot>=0 ) ? (int64_t)uRows/4 : ( p.m_dLeafTerms[l] ? p.m_dLeafTerms[l]->m_iDocs : 0 );
@@ -945,10 +1000,15 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			int64_t nUnits = nTiles;
 			if ( c==2 )
 			{
-				const TermInfo_t * pDrv = p.m_dLeafTerms[p.m_tDev.m_iDriverLeaf];
-				nUnits = pDrv ? ( pDrv->m_nBlocks+AND_CHUNK-1 )/AND_CHUNK : 1;
+				nUnits = 0;
+				for ( int g=0; g<p.m_tDev.m_nGroups; ++g )
+				{
+					const TermInfo_t * pDrv = p.m_dLeafTerms[p.m_tDev.m_dOps[p.m_tDev.m_dGroupOp0[g]].m_uLeaf];
+					nUnits += pDrv ? ( pDrv->m_nBlocks+AND_CHUNK-1 )/AND_CHUNK : 0;
+				}
+				nUnits = std::max<int64_t> ( nUnits, p.m_tDev.m_nGroups );
 			}
-			nParts = std::max<int64_t> ( 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, iCap } ) ) );
+			nParts = std::max<int64_t> ( c==2 ? p.m_tDev.m_nGroups : 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, std::max ( iCap, c==2 ? p.m_tDev.m_nGroups : 1 ) } ) ) );
 			dParts.push_back ( { i, (int)nParts, iWork/nParts } );
 		}
 		std::stable_sort ( dParts.begin(), dParts.end(), [] ( const Part_t & a, const Part_t & b ) { return a.m_iCostPerPart>b.m_iCostPerPart; } );
@@ -962,11 +1022,37 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			int64_t nUnits = nTiles, iUnit = TILE_W, iLimit = uRows;
 			if ( c==2 )
 			{
-				// units = chunks of the driver keyword's blocks
-				const TermInfo_t * pDrv = m_dPlans[t.m_iQuery].m_dLeafTerms[q.m_iDriverLeaf];
-				iLimit = pDrv ? pDrv->m_nBlocks : 0;
-				nUnits = ( iLimit+AND_CHUNK-1 )/AND_CHUNK;
-				iUnit = AND_CHUNK;
+				// items = ranges of each group's driver blocks; the parts are shared out between the groups by their block counts
+				int64_t dBlocks[MAX_GROUPS], nTotalBlocks = 0;
+				for ( int g=0; g<q.m_nGroups; ++g )
+				{
+					const TermInfo_t * pDrv = m_dPlans[t.m_iQuery].m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
+					dBlocks[g] = pDrv ? pDrv->m_nBlocks : 0;
+					nTotalBlocks += dBlocks[g];
+				}
+				int nLeft = t.m_nParts - q.m_nGroups;	// every group gets one item, the rest go by size
+				int nMade = 0;
+				for ( int g=0; g<q.m_nGroups; ++g )
+				{
+					int nMine = 1 + ( nTotalBlocks ? (int)( (int64_t)nLeft*dBlocks[g]/nTotalBlocks ) : 0 );
+					const int64_t nChunks = std::max<int64_t> ( 1, ( dBlocks[g]+AND_CHUNK-1 )/AND_CHUNK );
+					nMine = (int)std::min<int64_t> ( nMine, nChunks );
+					for ( int p=0; p<nMine; ++p )
+					{
+						DevWorkItem_t tItem;
+						tItem.m_uQuery = (uint32_t)iDevQuery;
+						tItem.m_uRowLo = (uint32_t)( nChunks*p/nMine*AND_CHUNK );
+						tItem.m_uRowHi = (uint32_t)std::min<int64_t> ( nChunks*( p+1 )/nMine*AND_CHUNK, dBlocks[g] );
+						tItem.m_uPad = (uint32_t)g;
+						m_dItems.push_back ( tItem );
+						++nMade;
+					}
+				}
+				q.m_nItems = nMade;
+				iMaxKeysPerQuery = std::max ( iMaxKeysPerQuery, nMade*q.m_iMaxMatches );
+				m_dDevQueries.push_back ( q );
+				m_dDevToQuery.push_back ( t.m_iQuery );
+				continue;
 			}
 			for ( int p=0; p<t.m_nParts; ++p )
 			{
@@ -1028,9 +1114,13 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( cudaEventCreate ( &m_tEvHot ), m_sError );
 	for ( int c=0; c<NUM_CLASSES; ++c )
 		CUDA_TRY ( cudaEventCreate ( &m_dEvClass[c] ), m_sError );
-	m_tStats.queries_dense = (int32_t)( dOrder[0].size()+dOrder[3].size() );
-	m_tStats.queries_hits = (int32_t)dOrder[1].size();
-	m_tStats.queries_and = (int32_t)dOrder[2].size();
+	for ( int c=0; c<NUM_CLASSES; ++c )
+	{
+		m_tStats.class_queries[c] = (int32_t)dOrder[c].size();
+		m_tStats.class_bytes[c] = 0;
+		for ( int i : dOrder[c] )
+			m_tStats.class_bytes[c] += m_dPlans[i].m_iAlgBytes;
+	}
 	m_tStats.host_setup_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tPlanned ).count();
 	return MGPU_OK;
 }
@@ -1150,16 +1240,15 @@ int Batch_c::Sync()
 		cudaEventElapsedTime ( &m_tStats.hot_decode_ms, m_tEvHot, m_tEv0 );
 		m_tStats.hot_terms = (int32_t)m_dHotTerms.size();
 		cudaEvent_t tPrev = m_tEv0;
-		float dMs[NUM_CLASSES] = { 0.0f, 0.0f, 0.0f, 0.0f };
 		for ( int c=0; c<NUM_CLASSES; ++c )
+		{
+			m_tStats.class_ms[c] = 0.0f;
 			if ( m_dClassRan[c] )
 			{
-				cudaEventElapsedTime ( &dMs[c], tPrev, m_dEvClass[c] );
+				cudaEventElapsedTime ( &m_tStats.class_ms[c], tPrev, m_dEvClass[c] );
 				tPrev = m_dEvClass[c];
 			}
-		m_tStats.dense_kernel_ms = dMs[0]+dMs[3];
-		m_tStats.hits_kernel_ms = dMs[1];
-		m_tStats.and_kernel_ms = dMs[2];
+		}
 		cudaEventElapsedTime ( &m_tStats.merge_kernel_ms, m_tEv1, m_tEv2 );
 	}
 	return MGPU_OK;

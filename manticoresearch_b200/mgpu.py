@@ -72,8 +72,7 @@ class c_batch_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("work_items", C.c_int64), ("algorithmic_bytes", C.c_int64),
                 ("postings", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float), ("hot_decode_ms", C.c_float), ("hot_terms", C.c_int32),
-                ("dense_kernel_ms", C.c_float), ("hits_kernel_ms", C.c_float), ("and_kernel_ms", C.c_float),
-                ("queries_dense", C.c_int32), ("queries_hits", C.c_int32), ("queries_and", C.c_int32),
+                ("class_ms", C.c_float * 4), ("class_bytes", C.c_int64 * 4), ("class_queries", C.c_int32 * 4), ("pad0", C.c_int32),
                 ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float)]
 
 
@@ -488,7 +487,7 @@ class Batch:
     def stats(self):
         st = c_batch_stats()
         self._lib.mgpu_batch_get_stats(self._h, C.byref(st))
-        return {k: getattr(st, k) for k, _ in c_batch_stats._fields_}
+        return {k: (list(getattr(st, k)) if k.startswith("class_") else getattr(st, k)) for k, _ in c_batch_stats._fields_}
 
     def export_keys(self, dev_keys_ptr, dev_counts_ptr, dev_total_ptr, k):
         rc = self._lib.mgpu_batch_export_keys(self._h, dev_keys_ptr, dev_counts_ptr, dev_total_ptr, k)
