@@ -210,6 +210,7 @@ struct EvalParams_t
 	int32_t					m_iKMax;		///< stride of m_pItemKeys
 	int32_t					m_iPad;
 	uint64_t *				m_pHitpos;		///< hit stage only: [gridDim.x][MAX_LEAVES][TILE_W] hitlist position of (leaf, tile slot)
+	unsigned long long *	m_pQueryThr;	///< [nQueries] shared lower bound of each query's K-th best key (hi word), zeroed per run
 	PreEntry_t *			m_pPre;			///< [gridDim.x][PRE_BLOCKS*32] tile predecode scratch
 	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]
 	DevHotStore_t			m_tHot;

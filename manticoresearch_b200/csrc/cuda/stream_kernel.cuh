@@ -206,7 +206,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 		// this warp's contiguous share of the item
 		const uint32_t nMinis = ( tItem.m_uRowHi-tItem.m_uRowLo+MINI_W-1 )/MINI_W;
 		const uint32_t uMini0 = (uint32_t)( (uint64_t)nMinis*iWarp/EVAL_WARPS ), uMini1 = (uint32_t)( (uint64_t)nMinis*( iWarp+1 )/EVAL_WARPS );
-		const uint32_t nRounds = ( ( nMinis+EVAL_WARPS-1 )/EVAL_WARPS + SYNC_MINIS-1 )/SYNC_MINIS + 1;	// +1: shares differ by one mini-tile
+		// rounds of SYNC_MINIS mini-tiles per warp between barriers, after two warm-up rounds of ONE mini-tile each: the CTA learns a
+		// K-th-best threshold after 4K rows instead of 32K
+		const uint32_t nPerWarp = ( nMinis+EVAL_WARPS-1 )/EVAL_WARPS;
+		const uint32_t nRounds = 2 + ( ( nPerWarp>2 ? nPerWarp-2 : 0 ) + SYNC_MINIS-1 )/SYNC_MINIS + 1;	// +1: shares differ by one mini-tile
 		uint32_t uMini = uMini0;
 		const uint8_t uAliveRoot = (uint8_t)q.m_uAliveRoot;
 		const bool bFastRank = q.m_eRanker==1 && !q.m_nFilters && !q.m_nSortKeys && q.m_nWeights<=4 && !tIdx.m_pDead;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 			__syncthreads();
 			const int iPoolNow = S.m_iPoolCnt;
 			__syncthreads();	// nobody pushes before everybody has read the level
-			if ( iPoolNow+STREAM_POOL_SLACK>P.m_iPoolCap )
+			if ( iPoolNow+STREAM_POOL_SLACK>P.m_iPoolCap || ( uRound<=2 && iPoolNow>iK ) )
 			{
 				Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 				Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
@@ -227,12 +230,23 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 					S.m_tThr = tNewThr;
 					S.m_iPoolCnt = iK;
 					S.m_iPoolBuf ^= 1;
+					// K keys of this item are >= tNewThr, so the query's global K-th best is too: share the bound with the other items
+					atomicMax ( P.m_pQueryThr+tItem.m_uQuery, (unsigned long long)tNewThr.m_uHi );
 				}
 				__syncthreads();
 			}
-			const Key128_t tThr = S.m_tThr;
+			Key128_t tThr = S.m_tThr;
+			{
+				// another item of this query may already know a better lower bound of the K-th best key (hi word; lo = 0 keeps it a bound)
+				const unsigned long long uShared = *( (volatile unsigned long long *)( P.m_pQueryThr+tItem.m_uQuery ) );
+				if ( uShared>tThr.m_uHi )
+				{
+					tThr.m_uHi = uShared;
+					tThr.m_uLo = 0;
+				}
+			}
 			Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
-			const uint32_t uRoundEnd = min ( uMini1, uMini0 + ( uRound+1 )*SYNC_MINIS );
+			const uint32_t uRoundEnd = min ( uMini1, uMini0 + ( uRound<2 ? uRound+1 : 2+( uRound-1 )*SYNC_MINIS ) );
 
 			while ( uMini<uRoundEnd )
 			{

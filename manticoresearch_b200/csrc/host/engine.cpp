@@ -1080,6 +1080,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( m_dQ.Alloc ( nDevQ ), m_sError );
 	CUDA_TRY ( m_dI.Alloc ( nItems ), m_sError );
 	CUDA_TRY ( m_dCounter.Alloc ( NUM_CLASSES ), m_sError );
+	CUDA_TRY ( m_dQueryThr.Alloc ( nDevQ ), m_sError );
 	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3] } )*2*m_iPoolCap;
 	m_nHitpos = (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W;
 	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32;
@@ -1134,6 +1135,7 @@ int Batch_c::Run()
 	cudaStream_t s = pIndex->m_tStream;
 
 	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
+	CUDA_TRY ( cudaMemsetAsync ( m_dQueryThr.m_p, 0, m_dDevQueries.size()*sizeof(unsigned long long), s ), m_sError );
 
 	// run-time scratch comes from the index (grow-only, shared by all batches; runs are serialised on the index stream)
 	Index_c::RunScratch_t & tScr = pIndex->m_tScratch;
@@ -1192,6 +1194,7 @@ int Batch_c::Run()
 		P.m_pCounter = m_dCounter.m_p + c;
 		P.m_iKMax = m_iKMax;
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
+		P.m_pQueryThr = m_dQueryThr.m_p;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;

@@ -143,6 +143,7 @@ public:
 	DevBuf_T<DevQuery_t>	m_dQ;
 	DevBuf_T<DevWorkItem_t>	m_dI;
 	DevBuf_T<int32_t>		m_dCounter;
+	DevBuf_T<unsigned long long> m_dQueryThr;	///< per device query: shared K-th-best bound of its items
 	DevBuf_T<Key128_t>		m_dItemKeys, m_dScratch, m_dOutKeys;
 	size_t	m_nPool = 0, m_nHitpos = 0, m_nPre = 0, m_nPreHitpos = 0;	///< what Run() needs from the index's RunScratch_t
 	DevBuf_T<DevItemOut_t>	m_dItemOut;

@@ -87,6 +87,22 @@ def test_cfg2_mix_bm25(synth):
     _compare_batch(synth, queries)
 
 
+def test_or_queries_small_k_and_odd_weights(synth):
+    """pure OR queries mixing hot and sparse keywords, K from 1 to 100, negative / swapped field weights, index weights:
+    exercises the candidate-pool threshold logic (shared per-query bound, warm-up rounds) of stream_kernel"""
+    import random
+    rng = random.Random(99)
+    qs = []
+    for i in range(160):
+        ranks = rng.sample(range(1, 40), rng.randint(1, 3)) + [int(10 ** rng.uniform(2, 4.5)) for _ in range(rng.randint(1, 4))]
+        rng.shuffle(ranks)
+        leaves = [M.kw(M.synth_keyword(r - 1), p + 1) for p, r in enumerate(ranks)]
+        fw = rng.choice([[10, 1], [1, 1], [1, 10], [3, -2], None])
+        qs.append(M.Query(M.OR(*leaves), ranker=M.RANK_BM25, field_weights=fw, max_matches=rng.choice([1, 3, 20, 100]), index_weight=rng.choice([1, 1, 2])))
+    # the same keywords again so that every frequent one is shared by >= 2 queries (hot store)
+    assert _compare_batch(synth, qs + qs[:40]) == 0
+
+
 def test_cfg4_mix_with_andnot(synth):
     queries = workload.cfg2_queries(n=200, seed=77, max_rank=50000, max_matches=1000, with_andnot=0.2)
     _compare_batch(synth, queries)
