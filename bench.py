@@ -312,8 +312,9 @@ def run_ours(args):
         b3.fetch()
         s3 = b3.stats()
         h2d, d2h = s3["h2d_bytes"], s3["d2h_bytes"]
-        host_ms = {k: s3[k] for k in ("host_plan_ms", "host_setup_ms", "host_fetch_ms")}
         b3.free()
+        ls = index.last_search_stats()      # of the last timed mgpu_search_batch call
+        host_ms = {k: round(ls[k], 2) for k in ("host_total_ms", "host_plan_ms", "host_setup_ms", "host_wait_ms", "host_fetch_ms")}
 
     if rank == 0:
         qps = nq / (ms_per_step / 1000.0)

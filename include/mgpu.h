@@ -221,8 +221,12 @@ typedef struct mgpu_batch_stats {
 	int32_t			pad0;
 	/* host wall-clock of the batch: query planning, buffer setup + plan upload, result download + unpack */
 	float			host_plan_ms, host_setup_ms, host_fetch_ms;
+	float			host_wait_ms;        /* part of host_fetch_ms spent waiting for the kernels */
+	float			host_total_ms;       /* mgpu_search_batch only: the whole call incl. freeing the batch */
 } mgpu_batch_stats;
 int				mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out );
+/* stats of the last mgpu_search_batch() call on this handle (that call frees its batch before returning) */
+int				mgpu_index_last_search_stats ( const mgpu_index * idx, mgpu_batch_stats * out );
 
 /* ------------------------------------------------------------------------------------- */
 /* distributed-local merge: replaces MergeAllMatches/KillPlainDupes for disjoint rowid-range shards

@@ -2,6 +2,7 @@
 #include "engine.h"
 #include "index_writer.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -154,6 +155,7 @@ int mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out )
 
 int mgpu_search_batch ( mgpu_index * idx, const mgpu_query * queries, int n_queries, mgpu_result * results )
 {
+	const auto tStart = std::chrono::steady_clock::now();
 	mgpu_batch * b = nullptr;
 	int iRes = mgpu_batch_prepare ( idx, queries, n_queries, &b );
 	if ( iRes!=MGPU_OK )
@@ -161,8 +163,22 @@ int mgpu_search_batch ( mgpu_index * idx, const mgpu_query * queries, int n_quer
 	iRes = mgpu_batch_run ( b );
 	if ( iRes==MGPU_OK )
 		iRes = mgpu_batch_fetch ( b, results );
+	mgpu_batch_stats tStats = b->m_t.m_tStats;
 	mgpu_batch_free ( b );
+	tStats.host_total_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tStart ).count();
+	{
+		std::lock_guard<std::mutex> tGuard ( idx->m_t.m_tLock );
+		idx->m_t.m_tLastSearchStats = tStats;
+	}
 	return iRes;
+}
+
+int mgpu_index_last_search_stats ( const mgpu_index * idx, mgpu_batch_stats * out )
+{
+	if ( !idx || !out )
+		return MGPU_E_BAD_QUERY;
+	*out = idx->m_t.m_tLastSearchStats;
+	return MGPU_OK;
 }
 
 int mgpu_batch_export_keys ( mgpu_batch * b, void * dev_keys, void * dev_counts, void * dev_total_found, int K )

@@ -69,8 +69,25 @@ int Upload ( DevBuf_T<T> & tDst, const void * pSrc, size_t nBytes, size_t nPadBy
 } // namespace
 
 
+void * Index_c::Pinned ( size_t nBytes )
+{
+	if ( nBytes>m_nPinned )
+	{
+		if ( m_pPinned )
+			cudaFreeHost ( m_pPinned );
+		m_pPinned = nullptr;
+		m_nPinned = 0;
+		if ( cudaHostAlloc ( &m_pPinned, nBytes, cudaHostAllocDefault )!=cudaSuccess )
+			return nullptr;
+		m_nPinned = nBytes;
+	}
+	return m_pPinned;
+}
+
 Index_c::~Index_c()
 {
+	if ( m_pPinned )
+		cudaFreeHost ( m_pPinned );
 	if ( m_tOwnStream )
 	{
 		cudaSetDevice ( m_iDevice );
@@ -261,6 +278,15 @@ int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
 
 	CUDA_TRY ( cudaStreamCreateWithFlags ( &m_tOwnStream, cudaStreamNonBlocking ), m_sError );
 	m_tStream = m_tOwnStream;
+	{
+		// per-batch buffers come from the device's stream-ordered pool: keep freed memory cached instead of returning it to the driver
+		cudaMemPool_t tPool;
+		if ( cudaDeviceGetDefaultMemPool ( &tPool, iDevice )==cudaSuccess )
+		{
+			uint64_t uKeep = ~0ull;
+			cudaMemPoolSetAttribute ( tPool, cudaMemPoolAttrReleaseThreshold, &uKeep );
+		}
+	}
 	return MGPU_OK;
 }
 
@@ -1074,32 +1100,33 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 
 	const int nDevQ = (int)m_dDevQueries.size();
 	const int nItems = (int)m_dItems.size();
+	cudaStream_t tAllocStream = pIndex->m_tStream;
 	m_iPoolCap = m_iKMax + 32768;	// >= K + what one round of any kernel can push (stream: 8 mini-tiles x 8 warps x 512 rows)
 	m_iScratchStride = 2*Pow2Ceil ( iMaxKeysPerQuery );
 
-	CUDA_TRY ( m_dQ.Alloc ( nDevQ ), m_sError );
-	CUDA_TRY ( m_dI.Alloc ( nItems ), m_sError );
-	CUDA_TRY ( m_dCounter.Alloc ( NUM_CLASSES ), m_sError );
-	CUDA_TRY ( m_dQueryThr.Alloc ( nDevQ ), m_sError );
+	CUDA_TRY ( m_dQ.AllocAsync ( nDevQ, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dI.AllocAsync ( nItems, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dCounter.AllocAsync ( NUM_CLASSES, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
 	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3] } )*2*m_iPoolCap;
 	m_nHitpos = (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W;
 	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32;
 	m_nPreHitpos = (size_t)m_dCtas[1]*PRE_BLOCKS*32;
 	if ( !m_dHotTerms.empty() )
 	{
-		CUDA_TRY ( m_dHotDesc.Alloc ( m_dHotTerms.size() ), m_sError );
-		CUDA_TRY ( cudaMemcpy ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice ), m_sError );
+		CUDA_TRY ( m_dHotDesc.AllocAsync ( m_dHotTerms.size(), tAllocStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, tAllocStream ), m_sError );
 	}
-	CUDA_TRY ( m_dItemKeys.Alloc ( (size_t)nItems*m_iKMax ), m_sError );
-	CUDA_TRY ( m_dItemOut.Alloc ( nItems ), m_sError );
-	CUDA_TRY ( m_dScratch.Alloc ( (size_t)nDevQ*m_iScratchStride ), m_sError );
-	CUDA_TRY ( m_dOutKeys.Alloc ( (size_t)nQueries*m_iKMax ), m_sError );
-	CUDA_TRY ( m_dOutDocid.Alloc ( (size_t)nQueries*m_iKMax ), m_sError );
-	CUDA_TRY ( m_dOutCount.Alloc ( nQueries ), m_sError );
-	CUDA_TRY ( m_dOutTotal.Alloc ( nQueries ), m_sError );
-	CUDA_TRY ( m_dOutSlot.Alloc ( nDevQ ), m_sError );
-	CUDA_TRY ( cudaMemset ( m_dOutCount.m_p, 0, (size_t)nQueries*4 ), m_sError );
-	CUDA_TRY ( cudaMemset ( m_dOutTotal.m_p, 0, (size_t)nQueries*8 ), m_sError );
+	CUDA_TRY ( m_dItemKeys.AllocAsync ( (size_t)nItems*m_iKMax, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dItemOut.AllocAsync ( nItems, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dScratch.AllocAsync ( (size_t)nDevQ*m_iScratchStride, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dOutKeys.AllocAsync ( (size_t)nQueries*m_iKMax, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dOutDocid.AllocAsync ( (size_t)nQueries*m_iKMax, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dOutCount.AllocAsync ( nQueries, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dOutTotal.AllocAsync ( nQueries, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dOutSlot.AllocAsync ( nDevQ, tAllocStream ), m_sError );
+	CUDA_TRY ( cudaMemsetAsync ( m_dOutCount.m_p, 0, (size_t)nQueries*4, tAllocStream ), m_sError );
+	CUDA_TRY ( cudaMemsetAsync ( m_dOutTotal.m_p, 0, (size_t)nQueries*8, tAllocStream ), m_sError );
 
 	cudaStream_t s = pIndex->m_tStream;
 	CUDA_TRY ( cudaMemcpyAsync ( m_dQ.m_p, m_dDevQueries.data(), (size_t)nDevQ*sizeof(DevQuery_t), cudaMemcpyHostToDevice, s ), m_sError );
@@ -1278,21 +1305,33 @@ int Batch_c::Fetch ( mgpu_result * pResults )
 	}
 	if ( m_dDevQueries.empty() )
 		return MGPU_OK;
+	const auto tWait = std::chrono::steady_clock::now();
 	int iRes = Sync();
+	m_tStats.host_wait_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tWait ).count();
 	if ( iRes!=MGPU_OK )
 		return iRes;
 
-	std::vector<int32_t> dCount ( nQueries );
-	std::vector<int64_t> dTotal ( nQueries );
+	// download through the index's pinned staging buffer (serialised by the index lock)
+	std::lock_guard<std::mutex> tGuard ( m_pIndex->m_tLock );
+	const size_t nSlots = (size_t)nQueries*m_iKMax;
+	const size_t iOffDocid = nSlots*sizeof(Key128_t), iOffTotal = iOffDocid + nSlots*8, iOffCount = iOffTotal + (size_t)nQueries*8;
+	uint8_t * pStage = (uint8_t *)m_pIndex->Pinned ( iOffCount + (size_t)nQueries*4 );
+	if ( !pStage )
+	{
+		m_sError = "cudaHostAlloc failed";
+		return MGPU_E_NOMEM;
+	}
+	const Key128_t * dKeys = (const Key128_t *)pStage;
+	const int64_t * dDocid = (const int64_t *)( pStage+iOffDocid );
+	const int64_t * dTotal = (const int64_t *)( pStage+iOffTotal );
+	const int32_t * dCount = (const int32_t *)( pStage+iOffCount );
 	cudaStream_t s = m_pIndex->m_tStream;
-	CUDA_TRY ( cudaMemcpyAsync ( dCount.data(), m_dOutCount.m_p, (size_t)nQueries*4, cudaMemcpyDeviceToHost, s ), m_sError );
-	CUDA_TRY ( cudaMemcpyAsync ( dTotal.data(), m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToHost, s ), m_sError );
-	std::vector<Key128_t> dKeys ( (size_t)nQueries*m_iKMax );
-	std::vector<int64_t> dDocid ( (size_t)nQueries*m_iKMax );
-	CUDA_TRY ( cudaMemcpyAsync ( dKeys.data(), m_dOutKeys.m_p, dKeys.size()*sizeof(Key128_t), cudaMemcpyDeviceToHost, s ), m_sError );
-	CUDA_TRY ( cudaMemcpyAsync ( dDocid.data(), m_dOutDocid.m_p, dDocid.size()*8, cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( pStage, m_dOutKeys.m_p, nSlots*sizeof(Key128_t), cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( pStage+iOffDocid, m_dOutDocid.m_p, nSlots*8, cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( pStage+iOffTotal, m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToHost, s ), m_sError );
+	CUDA_TRY ( cudaMemcpyAsync ( pStage+iOffCount, m_dOutCount.m_p, (size_t)nQueries*4, cudaMemcpyDeviceToHost, s ), m_sError );
 	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
-	m_tStats.d2h_bytes = (int64_t)nQueries*12 + (int64_t)dKeys.size()*24;
+	m_tStats.d2h_bytes = (int64_t)nQueries*12 + (int64_t)nSlots*24;
 
 	for ( int iQuery=0; iQuery<nQueries; ++iQuery )
 	{

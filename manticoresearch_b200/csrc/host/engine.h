@@ -33,6 +33,7 @@ struct DevBuf_T
 {
 	T *		m_p = nullptr;
 	size_t	m_n = 0;
+	cudaStream_t m_tPoolStream = nullptr;	///< set: the buffer came from the stream-ordered pool (cudaMallocAsync) of this stream
 	cudaError_t Alloc ( size_t n )
 	{
 		Free();
@@ -40,6 +41,16 @@ struct DevBuf_T
 		if ( !n )
 			return cudaSuccess;
 		return cudaMalloc ( (void**)&m_p, n*sizeof(T) );
+	}
+	/// per-batch buffers: stream-ordered pool allocation, no device-wide synchronisation on alloc or free
+	cudaError_t AllocAsync ( size_t n, cudaStream_t tStream )
+	{
+		Free();
+		m_n = n;
+		if ( !n )
+			return cudaSuccess;
+		m_tPoolStream = tStream;
+		return cudaMallocAsync ( (void**)&m_p, n*sizeof(T), tStream );
 	}
 	/// grow-only: keeps the allocation when it is already big enough (scratch reused across batches)
 	cudaError_t Grow ( size_t n )
@@ -49,9 +60,15 @@ struct DevBuf_T
 	void Free()
 	{
 		if ( m_p )
-			cudaFree ( m_p );
+		{
+			if ( m_tPoolStream )
+				cudaFreeAsync ( m_p, m_tPoolStream );
+			else
+				cudaFree ( m_p );
+		}
 		m_p = nullptr;
 		m_n = 0;
+		m_tPoolStream = nullptr;
 	}
 	~DevBuf_T() { Free(); }
 	DevBuf_T() = default;
@@ -70,6 +87,7 @@ public:
 	cudaStream_t	m_tOwnStream = nullptr;
 	int				m_nSMs = 148;
 	std::mutex		m_tLock;		///< serialises batches on this handle
+	mgpu_batch_stats m_tLastSearchStats {};
 
 	std::unordered_map<std::string,TermInfo_t> m_hTerms;
 
@@ -84,6 +102,11 @@ public:
 		DevBuf_T<uint32_t>		m_dHotEscape;
 		DevBuf_T<int32_t>		m_dHotEscapeCount;
 	} m_tScratch;
+
+	/// pinned host staging for result downloads (grow-only; used under m_tLock)
+	void *	m_pPinned = nullptr;
+	size_t	m_nPinned = 0;
+	void *	Pinned ( size_t nBytes );
 
 	DevBuf_T<uint8_t>	m_dSpd, m_dSpp;
 	DevBuf_T<uint32_t>	m_dSpa, m_dDead;

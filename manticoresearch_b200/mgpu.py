@@ -73,7 +73,8 @@ class c_batch_stats(C.Structure):
                 ("postings", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float), ("hot_decode_ms", C.c_float), ("hot_terms", C.c_int32),
                 ("class_ms", C.c_float * 4), ("class_bytes", C.c_int64 * 4), ("class_queries", C.c_int32 * 4), ("pad0", C.c_int32),
-                ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float)]
+                ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float),
+                ("host_wait_ms", C.c_float), ("host_total_ms", C.c_float)]
 
 
 class c_build_doc_input(C.Structure):
@@ -132,6 +133,7 @@ def load_library(path=None):
         "mgpu_batch_fetch": (C.c_int, [vp, C.POINTER(c_result)]),
         "mgpu_batch_free": (None, [vp]),
         "mgpu_batch_get_stats": (C.c_int, [vp, C.POINTER(c_batch_stats)]),
+        "mgpu_index_last_search_stats": (C.c_int, [vp, C.POINTER(c_batch_stats)]),
         "mgpu_batch_export_keys": (C.c_int, [vp, vp, vp, vp, C.c_int]),
         "mgpu_merge_shard_keys": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
@@ -157,7 +159,7 @@ EXPORTED_SYMBOLS = [
     "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_index_set_stream", "mgpu_last_error", "mgpu_index_total_docs",
     "mgpu_index_num_fields", "mgpu_index_field_index", "mgpu_index_attr_index", "mgpu_index_word_stats",
     "mgpu_index_word_bytes", "mgpu_search_batch", "mgpu_batch_prepare", "mgpu_batch_run", "mgpu_batch_sync",
-    "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_batch_export_keys",
+    "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_index_last_search_stats", "mgpu_batch_export_keys",
     "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist", "mgpu_build_index",
     "mgpu_build_synthetic", "mgpu_synth_field_len", "mgpu_synth_token",
 ]
@@ -424,6 +426,11 @@ class Index:
         if rc != MGPU_OK:
             self._err(rc)
         return result_set
+
+    def last_search_stats(self):
+        st = c_batch_stats()
+        self._lib.mgpu_index_last_search_stats(self._h, C.byref(st))
+        return {k: (list(getattr(st, k)) if k.startswith("class_") else getattr(st, k)) for k, _ in c_batch_stats._fields_}
 
     def prepare(self, queries):
         return Batch(self, queries)
