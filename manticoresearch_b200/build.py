@@ -90,7 +90,7 @@ def _build_locked(verbose):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB + ".tmp"] + objs + ["-lpthread"]
+    cmd = [nvcc, "-shared", "-cudart", "static", "-Xlinker", "--no-undefined", "-o", LIB + ".tmp"] + objs + ["-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -280,14 +280,14 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 	}
 }
 
-/// opens the cursors of n-way node j on the document in tile slot `s` and produces its first folded hit
-__device__ void NWayOpen ( const DevIndex_t & tIdx, const DevQuery_t & q, int j, const uint64_t * pHitpos, int s, DocHits_t & H )
+/// opens the cursors of n-way node j on the document in slot `s` (hitlist positions at pHitpos[leaf*iStride+s]) and produces its first folded hit
+__device__ void NWayOpen ( const DevIndex_t & tIdx, const DevQuery_t & q, int j, const uint64_t * pHitpos, int iStride, int s, DocHits_t & H )
 {
 	const DevNWay_t & n = q.m_dNWay[j];
 	for ( int w=0; w<n.m_nWords; ++w )
 	{
 		const int l = n.m_dLeaf[w];
-		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*TILE_W+s] );
+		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*iStride+s] );
 		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields );
 	}
 	H.m_dNWay[j].m_bAny = false;
@@ -375,7 +375,7 @@ __device__ __forceinline__ void RankUpdate ( const DevQuery_t & q, RankState_t &
 /// Streams the document's hits (root CollectHits order) through the ranker state.
 /// uEmit = emitters sitting on this document (plain leaves + n-way nodes). Returns false if the document yields no
 /// hits (ExtRanker_State_T skips it, src/sphinxsearch.cpp:1299-1304); else iWeight = final weight before index weight.
-__device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, uint32_t uEmit, const uint64_t * pHitpos, int s,
+__device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, uint32_t uEmit, const uint64_t * pHitpos, int iStride, int s,
 	int iSeedWeight, DocHits_t & H, int & iWeight )
 {
 	uint32_t uLeaves = uEmit & 0xFFFFu;
@@ -383,11 +383,11 @@ __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, u
 	for ( uint32_t m=uLeaves; m; m&=m-1 )
 	{
 		const int l = __ffs ( m )-1;
-		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*TILE_W+s] );
+		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*iStride+s] );
 		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields );
 	}
 	for ( uint32_t m=uNWays; m; m&=m-1 )
-		NWayOpen ( tIdx, q, __ffs ( m )-1, pHitpos, s, H );
+		NWayOpen ( tIdx, q, __ffs ( m )-1, pHitpos, iStride, s, H );
 
 	RankState_t R;
 	RankInit ( R );

@@ -910,7 +910,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 						{
 							const int s = V.m_pList[i];
 							DocHits_t H;
-							NWayOpen ( tIdx, q, j, pHitpos, s, H );
+							NWayOpen ( tIdx, q, j, pHitpos, TILE_W, s, H );
 							if ( H.m_dNWay[j].m_tHead.m_uHitpos )
 							{
 								V.Fields ( d, s ) = 1u<<( ( H.m_dNWay[j].m_uFirstRawHit>>24 ) & 31u );
@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								if constexpr ( HITS )
 								{
 									DocHits_t H;
-									bOk = RankDocByHits ( tIdx, q, V.Emit ( 0, s ), pHitpos, s, iSeed, H, iWeight );
+									bOk = RankDocByHits ( tIdx, q, V.Emit ( 0, s ), pHitpos, TILE_W, s, iSeed, H, iWeight );
 								}
 							} else
 							{
@@ -1126,6 +1126,7 @@ struct AndShared_t
 	uint32_t		m_dRows[EVAL_WARPS][32];	///< the other keyword's decoded block, for the candidates' lookups
 	uint32_t		m_dHits[EVAL_WARPS][32];
 	uint32_t		m_dFields[EVAL_WARPS][32];
+	uint64_t		m_dHitposSm[EVAL_WARPS][32];	///< hit variant: hitlist positions of the probed block
 	uint16_t		m_dRecStart[EVAL_WARPS][34];
 	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
 };
@@ -1133,11 +1134,17 @@ struct AndShared_t
 /// Does the keyword hold the lane's candidate row? Warp-cooperative: hot keywords are probed in the dense store; sparse ones by a
 /// binary search of the resident block table per candidate (FindSpan, src/sphinx.cpp:407-451), then only the distinct blocks that
 /// may hold a candidate are decoded (each once per warp) and searched. Returns the queried field mask (0 = absent) and the hit count.
+/// per-thread hit machinery only exists in the hit variant
+template<bool HITS> struct HitsState_T { struct Type_t {}; };
+template<> struct HitsState_T<true> { typedef DocHits_t Type_t; };
+
+template<bool HITS>
 __device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, const DevHotStore_t & tHot, const DevLeaf_t & tLeaf, uint32_t uRowid, bool bActive,
-	AndShared_t & S, int iWarp, int iLane, uint32_t & uHitsOut )
+	AndShared_t & S, int iWarp, int iLane, uint32_t & uHitsOut, uint64_t & uHitposOut )
 {
 	uint32_t uHits = 0, uF = 0;
-	if ( tLeaf.m_iHot>=0 )
+	uint64_t uHitpos = 0;
+	if ( !HITS && tLeaf.m_iHot>=0 )
 	{
 		if ( bActive )
 		{
@@ -1167,10 +1174,12 @@ __device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, con
 			const int iLeader = __ffs ( uTodo )-1;
 			const uint32_t uSel = __shfl_sync ( FULL_MASK, uBlk, iLeader );
 			DecodedDoc_t tOther;
-			DecodeBlock<false> ( tIdx, tLeaf, uSel, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tOther );
+			DecodeBlock<HITS> ( tIdx, tLeaf, uSel, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tOther );
 			S.m_dRows[iWarp][iLane] = tOther.m_bValid ? tOther.m_uRowid : 0xFFFFFFFFu;
 			S.m_dHits[iWarp][iLane] = tOther.m_uHits;
 			S.m_dFields[iWarp][iLane] = tOther.m_uFields;
+			if ( HITS )
+				S.m_dHitposSm[iWarp][iLane] = tOther.m_uHitlistPos;
 			__syncwarp();
 			const bool bMine = bActive && uBlk==uSel;
 			if ( bMine )
@@ -1185,6 +1194,8 @@ __device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, con
 				{
 					uHits = S.m_dHits[iWarp][l];
 					uF = S.m_dFields[iWarp][l] & tLeaf.m_uQueriedFields;
+					if ( HITS )
+						uHitpos = S.m_dHitposSm[iWarp][l];
 				}
 			}
 			uTodo &= ~__ballot_sync ( FULL_MASK, bMine );
@@ -1192,13 +1203,15 @@ __device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, con
 		}
 	}
 	uHitsOut = uHits;
+	uHitposOut = uHitpos;
 	return uF;
 }
 
 /// one AND group (ops [iOp0, iOp0+nOps) = SET, AND, AND...) evaluated on the lanes' candidate rows by probing, in the reference's
 /// rarest-first order; iSkipOp = op whose keyword is already accounted for (the driver), -1 = probe all. Accumulates into fT / uFields.
+template<bool HITS>
 __device__ __forceinline__ bool ProbeGroup ( const DevIndex_t & tIdx, const DevHotStore_t & tHot, const DevQuery_t & q, int iOp0, int nOps, int iSkipOp,
-	uint32_t uRowid, bool bActive, AndShared_t & S, int iWarp, int iLane, float & fT, uint32_t & uFields )
+	uint32_t uRowid, bool bActive, AndShared_t & S, int iWarp, int iLane, float & fT, uint32_t & uFields, uint64_t * pLaneHitpos )
 {
 	for ( int iOp=iOp0; iOp<iOp0+nOps; ++iOp )
 	{
@@ -1208,11 +1221,14 @@ __device__ __forceinline__ bool ProbeGroup ( const DevIndex_t & tIdx, const DevH
 			break;
 		const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
 		uint32_t uHits;
-		const uint32_t uF = WarpProbeKeyword ( tIdx, tHot, tLeaf, uRowid, bActive, S, iWarp, iLane, uHits );
+		uint64_t uHitpos;
+		const uint32_t uF = WarpProbeKeyword<HITS> ( tIdx, tHot, tLeaf, uRowid, bActive, S, iWarp, iLane, uHits, uHitpos );
 		if ( bActive )
 		{
 			if ( uF )
 			{
+				if ( HITS )
+					pLaneHitpos[(size_t)q.m_dOps[iOp].m_uLeaf*32] = uHitpos;
 				// ExtMultiAnd_T::GetDocsChunk, src/searchnode.cpp:2821-2832
 				const float fHits = __uint2float_rn ( uHits );
 				const float fTf = __fmul_rn ( uHits<255 ? S.m_dTf[uHits & 255u] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
@@ -1229,12 +1245,15 @@ __device__ __forceinline__ bool ProbeGroup ( const DevIndex_t & tIdx, const DevH
 /// per lane, kept in registers. For every other keyword, in the reference's rarest-first order: hot keywords are probed in the
 /// dense store; sparse ones by a binary search of the resident skiplist (block table) per candidate, then only the blocks that
 /// hold a candidate are decoded (each once per warp) and searched. TF*IDF accumulates in that same order.
+template<bool HITS>
 __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 {
 	__shared__ AndShared_t S;
 	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
 	const DevIndex_t & tIdx = P.m_tIndex;
 	Key128_t * pPool0 = P.m_pPool + (size_t)blockIdx.x*2*P.m_iPoolCap;
+	// hit variant: hitlist position of (keyword, candidate lane), [MAX_LEAVES][32] per warp, in the CTA's hit scratch
+	uint64_t * pLaneHitpos = HITS ? P.m_pHitpos + ( (size_t)blockIdx.x*EVAL_WARPS+iWarp )*MAX_LEAVES*32 + iLane : nullptr;
 	{
 		const float fHits = __uint2float_rn ( (uint32_t)tid );
 		S.m_dTf[tid & 255] = __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
@@ -1306,11 +1325,14 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 			for ( uint32_t b=uChunk+iWarp; b<uChunkEnd; b+=EVAL_WARPS )
 			{
 				// the driver block: 32 candidates
+				typename HitsState_T<HITS>::Type_t tHits;
 				DecodedDoc_t tDoc;
-				DecodeBlock<false> ( tIdx, tDrv, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
+				DecodeBlock<HITS> ( tIdx, tDrv, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
 				const uint32_t uRowid = tDoc.m_uRowid;
 				uint32_t uFields = tDoc.m_uFields & tDrv.m_uQueriedFields;
 				bool bAlive = tDoc.m_bValid && uFields;
+				if ( HITS )
+					pLaneHitpos[(size_t)q.m_dOps[iOp0].m_uLeaf*32] = tDoc.m_uHitlistPos;
 				float fTfidf;
 				{
 					const float fHits = __uint2float_rn ( tDoc.m_uHits );
@@ -1318,7 +1340,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 				}
 
 				// the rest of this group
-				bAlive = ProbeGroup ( tIdx, P.m_tHot, q, iOp0, nGroupOps, iOp0, uRowid, bAlive, S, iWarp, iLane, fTfidf, uFields );
+				bAlive = ProbeGroup<HITS> ( tIdx, P.m_tHot, q, iOp0, nGroupOps, iOp0, uRowid, bAlive, S, iWarp, iLane, fTfidf, uFields, pLaneHitpos );
 
 				// DNF: a document that also matches an earlier group is emitted by that group's items; later groups that match add
 				// their TF*IDF in group order (ExtOr_c: left + right, src/searchnode.cpp:3486-3504)
@@ -1330,7 +1352,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 						break;
 					float fT = 0.0f;
 					uint32_t uF = 0;
-					const bool bMatch = ProbeGroup ( tIdx, P.m_tHot, q, q.m_dGroupOp0[g], q.m_dGroupOps[g], -1, uRowid, bAlive, S, iWarp, iLane, fT, uF );
+					const bool bMatch = ProbeGroup<false> ( tIdx, P.m_tHot, q, q.m_dGroupOp0[g], q.m_dGroupOps[g], -1, uRowid, bAlive, S, iWarp, iLane, fT, uF, nullptr );
 					if ( bMatch )
 					{
 						if ( g<iGroup )
@@ -1340,6 +1362,26 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 							fTfidf = __fadd_rn ( fTfidf, fT );
 							uFields |= uF;
 						}
+					}
+				}
+
+				// hit variant: the phrase / proximity acceptor over the chain's keywords (ExtNWay_T::GetDocsChunk, src/searchnode.cpp:3805-3848),
+				// then ranking by the document's hit stream; one candidate document per lane
+				uint32_t uEmit = 0;
+				if constexpr ( HITS )
+				{
+					for ( int iOp=iOp0; iOp<iOp0+nGroupOps; ++iOp )
+						uEmit |= 1u<<q.m_dOps[iOp].m_uLeaf;
+					if ( q.m_nNWay>0 && bAlive )
+					{
+						const int j = q.m_dOps[iOp0+nGroupOps].m_uArg;
+						NWayOpen ( tIdx, q, j, pLaneHitpos-iLane, 32, iLane, tHits );
+						if ( tHits.m_dNWay[j].m_tHead.m_uHitpos )
+						{
+							uFields = 1u<<( ( tHits.m_dNWay[j].m_uFirstRawHit>>24 ) & 31u );
+							uEmit = 1u<<( EMIT_NWAY_SHIFT+j );
+						} else
+							bAlive = false;
 					}
 				}
 
@@ -1353,16 +1395,23 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 					if ( bOk && q.m_eRanker!=2 )
 					{
 						const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( fTfidf, 0.5f ), 1000.0f ) );
-						uint32_t uRank = 0;
-						if ( !uFields )
-							uRank = 1;
-						else if ( q.m_nWeights<=4 )
-							uRank = S.m_dRankTab[uFields & 15u];
-						else
-							for ( int i=0; i<q.m_nWeights; ++i )
-								if ( uFields & ( 1u<<i ) )
-									uRank += (uint32_t)q.m_dWeights[i];
-						iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+						if ( HITS && q.m_bStateRanker )
+						{
+							if constexpr ( HITS )
+								bOk = RankDocByHits ( tIdx, q, uEmit, pLaneHitpos-iLane, 32, iLane, iSeed, tHits, iWeight );
+						} else
+						{
+							uint32_t uRank = 0;
+							if ( !uFields )
+								uRank = 1;
+							else if ( q.m_nWeights<=4 )
+								uRank = S.m_dRankTab[uFields & 15u];
+							else
+								for ( int i=0; i<q.m_nWeights; ++i )
+									if ( uFields & ( 1u<<i ) )
+										uRank += (uint32_t)q.m_dWeights[i];
+							iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+						}
 					}
 					if ( bOk && tIdx.m_pDead )
 						bOk = !( ( __ldg ( tIdx.m_pDead+( uRowid>>5 ) )>>( uRowid & 31 ) ) & 1u );
@@ -1671,16 +1720,22 @@ int StreamOccupancy ( int nStack )
 	return n>0 ? n : 1;
 }
 
-cudaError_t LaunchAnd ( const EvalParams_t & P, int nCtas, cudaStream_t tStream )
+cudaError_t LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream )
 {
-	and_kernel<<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
+	if ( bHits )
+		and_kernel<true><<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
+	else
+		and_kernel<false><<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
 	return cudaGetLastError();
 }
 
-int AndOccupancy()
+int AndOccupancy ( bool bHits )
 {
 	int n = 0;
-	if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, and_kernel, EVAL_THREADS, 0 )!=cudaSuccess )
+	cudaError_t e = bHits
+		? cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, and_kernel<true>, EVAL_THREADS, 0 )
+		: cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, and_kernel<false>, EVAL_THREADS, 0 );
+	if ( e!=cudaSuccess )
 		return 1;
 	return n>0 ? n : 1;
 }

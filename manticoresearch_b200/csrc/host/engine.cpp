@@ -699,6 +699,12 @@ struct Planner_c
 				return true;
 			};
 			bOk = bOk && fnGroup ( 0 );
+			bool bChainNWay = false;
+			if ( bOk && i==d.m_nOps-1 && d.m_dOps[i].m_eCode==OP_NWAY && d.m_dOps[i].m_uDst==0 )
+			{
+				bChainNWay = true;	// a phrase / proximity node alone: AND chain + acceptor
+				++i;
+			}
 			while ( bOk && i<d.m_nOps )
 			{
 				if ( d.m_dOps[i].m_eCode==OP_TERM_OR && d.m_dOps[i].m_uDst==0 && nGroups<MAX_GROUPS )
@@ -719,8 +725,10 @@ struct Planner_c
 			if ( d.m_nGroups==1 && d.m_iDriverLeaf>=0 )
 			{
 				d.m_dGroupOp0[0] = 0;
-				d.m_dGroupOps[0] = (uint8_t)d.m_nOps;
+				d.m_dGroupOps[0] = (uint8_t)( d.m_nOps - ( bChainNWay ? 1 : 0 ) );
 			}
+			if ( d.m_bNeedHits && d.m_nGroups>1 )
+				d.m_nGroups = 0;	// hit-consuming DNF stays on dense tiles
 		}
 
 		d.m_nLeaves = (int)m_dLeaves.size();
@@ -900,14 +908,14 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
 		{
 			if ( m_dPlans[i].m_tDev.m_bNeedHits )
-				dOrder[1].push_back ( i );
+				dOrder [ ( m_dPlans[i].m_tDev.m_nGroups==1 && !getenv ( "MGPU_NO_AND" ) ) ? 4 : 1 ].push_back ( i );
 			else
 				dDocOnly.push_back ( i );
 			m_iKMax = std::max ( m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
 			m_tStats.algorithmic_bytes += m_dPlans[i].m_iAlgBytes;
 			m_tStats.postings += m_dPlans[i].m_iCost;
 		}
-	if ( dDocOnly.empty() && dOrder[1].empty() )
+	if ( dDocOnly.empty() && dOrder[1].empty() && dOrder[4].empty() )
 		return MGPU_OK;
 
 	const uint32_t uRows = pIndex->m_tDev.m_uRows;
@@ -986,7 +994,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	auto fnWork = [&] ( const PlannedQuery_t & p, int c ) -> int64_t
 	{
 		int64_t iWork = 0;
-		if ( c==2 )
+		if ( c==2 || c==4 )
 		{
 			for ( int g=0; g<p.m_tDev.m_nGroups; ++g )
 			{
@@ -1011,7 +1019,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			iTotalWork += fnWork ( m_dPlans[i], c );
 			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
 		}
-		const int iOcc = c==2 ? AndOccupancy() : ( ( c==0 || c==3 ) && m_bStream ) ? StreamOccupancy ( m_dStack[c] ) : EvalOccupancy ( m_dStack[c], c==1 );
+		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( ( c==0 || c==3 ) && m_bStream ) ? StreamOccupancy ( m_dStack[c] ) : EvalOccupancy ( m_dStack[c], c==1 );
 		const int nMaxCtas = pIndex->m_nSMs*iOcc;
 		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
 
@@ -1024,7 +1032,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			int64_t nParts = ( iWork+iTarget-1 )/iTarget;
 			int iCap = std::max ( 1, 131072/std::max ( 1, p.m_tDev.m_iMaxMatches ) );
 			int64_t nUnits = nTiles;
-			if ( c==2 )
+			if ( c==2 || c==4 )
 			{
 				nUnits = 0;
 				for ( int g=0; g<p.m_tDev.m_nGroups; ++g )
@@ -1034,7 +1042,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				}
 				nUnits = std::max<int64_t> ( nUnits, p.m_tDev.m_nGroups );
 			}
-			nParts = std::max<int64_t> ( c==2 ? p.m_tDev.m_nGroups : 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, std::max ( iCap, c==2 ? p.m_tDev.m_nGroups : 1 ) } ) ) );
+			nParts = std::max<int64_t> ( ( c==2 || c==4 ) ? p.m_tDev.m_nGroups : 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, std::max ( iCap, ( c==2 || c==4 ) ? p.m_tDev.m_nGroups : 1 ) } ) ) );
 			dParts.push_back ( { i, (int)nParts, iWork/nParts } );
 		}
 		std::stable_sort ( dParts.begin(), dParts.end(), [] ( const Part_t & a, const Part_t & b ) { return a.m_iCostPerPart>b.m_iCostPerPart; } );
@@ -1046,7 +1054,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			q.m_nItems = t.m_nParts;
 			const int iDevQuery = (int)m_dDevQueries.size();
 			int64_t nUnits = nTiles, iUnit = TILE_W, iLimit = uRows;
-			if ( c==2 )
+			if ( c==2 || c==4 )
 			{
 				// items = ranges of each group's driver blocks; the parts are shared out between the groups by their block counts
 				int64_t dBlocks[MAX_GROUPS], nTotalBlocks = 0;
@@ -1108,8 +1116,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( m_dI.AllocAsync ( nItems, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dCounter.AllocAsync ( NUM_CLASSES, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
-	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3] } )*2*m_iPoolCap;
-	m_nHitpos = (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W;
+	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4] } )*2*m_iPoolCap;
+	m_nHitpos = std::max ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W, (size_t)m_dCtas[4]*EVAL_WARPS*MAX_LEAVES*32 );
 	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32;
 	m_nPreHitpos = (size_t)m_dCtas[1]*PRE_BLOCKS*32;
 	if ( !m_dHotTerms.empty() )
@@ -1225,8 +1233,8 @@ int Batch_c::Run()
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;
-		if ( c==2 )
-			CUDA_TRY ( LaunchAnd ( P, m_dCtas[c], s ), m_sError );
+		if ( c==2 || c==4 )
+			CUDA_TRY ( LaunchAnd ( P, c==4, m_dCtas[c], s ), m_sError );
 		else if ( ( c==0 || c==3 ) && m_bStream )
 			CUDA_TRY ( LaunchStream ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
 		else

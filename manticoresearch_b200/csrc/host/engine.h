@@ -152,12 +152,13 @@ public:
 	std::vector<DevQuery_t>		m_dDevQueries;	///< only the runnable ones, in order
 	std::vector<int>			m_dDevToQuery;	///< device query -> batch query index
 	std::vector<DevWorkItem_t>	m_dItems;
-	/// launch classes: [0] doc-only queries with a single-level program (stream_kernel<512>), [1] hit-consuming queries
-	/// (eval_kernel<true>), [2] pure AND queries led by a sparse keyword (and_kernel), [3] deeper doc-only programs (stream_kernel<256>)
-	static const int NUM_CLASSES = 4;
-	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1 };
-	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0 };
-	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0 };
+	/// launch classes: [0] doc-only queries with a single-level program (stream_kernel<512>), [1] hit-consuming queries on dense
+	/// tiles (eval_kernel<true>), [2] doc-only DNF / pure AND queries led by sparse keywords (and_kernel<false>), [3] deeper doc-only
+	/// programs (stream_kernel<256>), [4] hit-consuming pure AND chains incl. phrase / proximity (and_kernel<true>)
+	static const int NUM_CLASSES = 5;
+	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1, 1 };
+	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0, 0 };
+	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0, 0 };
 	bool	m_bStream = true;			///< class 0 runs on stream_kernel (eval_kernel<false> only for A/B comparisons)
 	int		m_iKMax = 1;
 	int		m_iPoolCap = 0;
@@ -179,8 +180,8 @@ public:
 	int64_t					m_iHotStride = 0;
 	int						m_iHotEscapeCap = 0;
 	cudaEvent_t				m_tEvHot = nullptr;
-	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr };
-	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false };
+	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false, false };
 
 	cudaEvent_t		m_tEv0 = nullptr, m_tEv1 = nullptr, m_tEv2 = nullptr;
 	mgpu_batch_stats m_tStats {};
@@ -200,8 +201,8 @@ int			EvalOccupancy ( int nStack, bool bHits );
 cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, bool bHits, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );
 int			StreamOccupancy ( int nStack );
-cudaError_t	LaunchAnd ( const EvalParams_t & P, int nCtas, cudaStream_t tStream );
-int			AndOccupancy();
+cudaError_t	LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream );
+int			AndOccupancy ( bool bHits );
 cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
