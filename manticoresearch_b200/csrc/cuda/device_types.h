@@ -55,7 +55,7 @@ struct DevLeaf_t
 	uint16_t	m_uAtomPos;
 	uint16_t	m_uNodePos;
 	int32_t		m_iHot;				///< slot in the batch's dense hot-term store, -1 = evaluate from the compressed doclist
-	int32_t		m_iPad;
+	int32_t		m_iTermPos;			///< ExtTermPos_T filter: low 3 bits = TermPosFilter_e (0 none, 1 field start, 2 field end, 3 both, 4 field limit), rest = m_iFieldMaxPos
 };
 
 /// Dense hot-term store, rebuilt by hot_decode_kernel at the start of every batch run: keywords that many queries of the

@@ -42,8 +42,24 @@ __device__ __forceinline__ void SeekHitlist ( HitCursor_t & c, const uint8_t * p
 	}
 }
 
-/// next hit that lies in a queried field (ExtTerm_T::CollectHits, src/searchnode.cpp:1971-2010); 0 = EMPTY_HIT
-__device__ __forceinline__ uint32_t NextHit ( HitCursor_t & c, uint32_t uQueriedFields )
+/// TermAcceptor_T<..>::IsAcceptableHit (src/searchnode.cpp:2264-2285): ^keyword, keyword$, both, @field[N]
+__device__ __forceinline__ bool AcceptHit ( uint32_t h, int iTermPos )
+{
+	const uint32_t uPos = h & 0x7FFFFFu;
+	const bool bEnd = ( h>>23 ) & 1u;
+	switch ( iTermPos & 7 )
+	{
+	case 1:		return uPos==1;
+	case 2:		return bEnd;
+	case 3:		return uPos==1 && bEnd;
+	case 4:		return (int)uPos<=( iTermPos>>3 );
+	default:	return true;
+	}
+}
+
+/// next hit that lies in a queried field and passes the keyword's position filter (ExtTerm_T::CollectHits,
+/// src/searchnode.cpp:1971-2010; ExtConditional_T :2331-2400); 0 = EMPTY_HIT
+__device__ __forceinline__ uint32_t NextHit ( HitCursor_t & c, uint32_t uQueriedFields, int iTermPos=0 )
 {
 	while ( true )
 	{
@@ -66,9 +82,17 @@ __device__ __forceinline__ uint32_t NextHit ( HitCursor_t & c, uint32_t uQueried
 		} else
 			return 0;
 		const uint32_t f = h>>24;
-		if ( f<32 && ( ( uQueriedFields>>f ) & 1u ) )
+		if ( f<32 && ( ( uQueriedFields>>f ) & 1u ) && AcceptHit ( h, iTermPos ) )
 			return h;
 	}
+}
+
+/// ExtConditional_T::GetDocsChunk: does the document (hitlist at uHitlistPos) hold an acceptable hit of this keyword?
+__device__ __forceinline__ bool HasAcceptableHit ( const uint8_t * pSpp, uint64_t uHitlistPos, uint32_t uQueriedFields, int iTermPos )
+{
+	HitCursor_t c;
+	SeekHitlist ( c, pSpp, uHitlistPos );
+	return NextHit ( c, uQueriedFields, iTermPos )!=0;
 }
 
 /// one hit as the ranker sees it (ExtHit_t, src/sphinxint.h:725-736)
@@ -264,7 +288,7 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 			s.m_tHead.m_uHitpos = 0;
 			return;
 		}
-		H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields );
+		H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields, q.m_dLeaves[iBest].m_iTermPos );
 		const bool bEmit = n.m_bProximity
 			? ProximityFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead )
 			: PhraseFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead );
@@ -288,7 +312,7 @@ __device__ void NWayOpen ( const DevIndex_t & tIdx, const DevQuery_t & q, int j,
 	{
 		const int l = n.m_dLeaf[w];
 		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*iStride+s] );
-		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields );
+		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields, q.m_dLeaves[l].m_iTermPos );
 	}
 	H.m_dNWay[j].m_bAny = false;
 	H.m_dNWay[j].m_uFirstRawHit = 0;
@@ -384,7 +408,7 @@ __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, u
 	{
 		const int l = __ffs ( m )-1;
 		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*iStride+s] );
-		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields );
+		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields, q.m_dLeaves[l].m_iTermPos );
 	}
 	for ( uint32_t m=uNWays; m; m&=m-1 )
 		NWayOpen ( tIdx, q, __ffs ( m )-1, pHitpos, iStride, s, H );
@@ -427,7 +451,7 @@ __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, u
 		if ( iBest<MAX_LEAVES )
 		{
 			t.m_uHitpos = uBestHit; t.m_uQpos = uBestQpos; t.m_uSpanlen = 1; t.m_uWeight = 1;
-			H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields );
+			H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields, q.m_dLeaves[iBest].m_iTermPos );
 		} else
 		{
 			t = H.m_dNWay[iBest-MAX_LEAVES].m_tHead;

@@ -743,7 +743,9 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 					DecodedDoc_t tDoc;
 					DecodeBlock<HITS> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
 					const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
-					const bool bOk = tDoc.m_bValid && uFields;
+					bool bOk = tDoc.m_bValid && uFields;
+					if ( HITS && bOk && tLeaf.m_iTermPos && tDoc.m_uRowid>=uTileLo && tDoc.m_uRowid<uTileHi )
+						bOk = HasAcceptableHit ( tIdx.m_pSpp, tDoc.m_uHitlistPos, tLeaf.m_uQueriedFields, tLeaf.m_iTermPos );
 					if ( bOk && tDoc.m_uRowid>=uTileHi && q.m_iDriverLeaf==l )
 						atomicMin ( &S.m_uNextRow, tDoc.m_uRowid );	// exact next candidate of a pure AND query: tiles in between are skipped
 					PreEntry_t tEntry;
@@ -885,6 +887,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								DecodeBlock<HITS> ( tIdx, tLeaf, b, S.m_dStage[iWarp], S.m_dRecStart[iWarp], iLane, tDoc );
 								const uint32_t uFields = tDoc.m_uFields & tLeaf.m_uQueriedFields;
 								if ( !tDoc.m_bValid || tDoc.m_uRowid<uTileLo || tDoc.m_uRowid>=uTileHi || !uFields )
+									continue;
+								if ( HITS && tLeaf.m_iTermPos && !HasAcceptableHit ( tIdx.m_pSpp, tDoc.m_uHitlistPos, tLeaf.m_uQueriedFields, tLeaf.m_iTermPos ) )
 									continue;
 								const int s = (int)( tDoc.m_uRowid-uTileLo );
 								// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946

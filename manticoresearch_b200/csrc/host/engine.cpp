@@ -321,6 +321,7 @@ struct PLeaf_t
 	int					m_iNodePos = 0;
 	bool				m_bNotWeighted = false;
 	bool				m_bOwnsIDF = false;		///< first occurrence of the word in eval-tree order
+	int					m_iTermPos = 0;
 	int					Docs() const { return m_pTerm ? m_pTerm->m_iDocs : 0; }
 };
 
@@ -342,6 +343,7 @@ struct Planner_c
 	std::vector<PNode_t> m_dNodes;
 	int					m_iError = MGPU_OK;
 	int					m_iMaxSp = 0;
+	bool				m_bAnyTermPos = false;
 
 	struct Qword_t { int m_iDocs; float m_fBoost; int m_iFirstWord; float m_fIDF; };
 	std::unordered_map<std::string,Qword_t> m_hQwords;
@@ -355,8 +357,6 @@ struct Planner_c
 		if ( iWord<0 || iWord>=m_q.n_words || !m_q.words[iWord].word )
 			return Fail ( MGPU_E_BAD_QUERY );
 		const mgpu_xqkeyword & tWord = m_q.words[iWord];
-		if ( tWord.field_start || tWord.field_end || tNode.field_max_pos )
-			return Fail ( MGPU_E_UNSUPPORTED );	// ExtTermPos_T filters are not on the GPU path yet
 		if ( (int)m_dLeaves.size()>=MAX_LEAVES )
 			return Fail ( MGPU_E_UNSUPPORTED );
 		PLeaf_t t;
@@ -366,6 +366,15 @@ struct Planner_c
 		t.m_iAtomPos = tWord.atom_pos;
 		t.m_iNodePos = iNodePos;
 		t.m_bNotWeighted = tNode.not_weighted!=0;
+		// ExtTermPos_T: ^keyword / keyword$ / @field[N] (src/searchnode.cpp:875-878, 1145-1146)
+		t.m_iTermPos = ( tWord.field_start && tWord.field_end ) ? 3 : tWord.field_start ? 1 : tWord.field_end ? 2 : 0;
+		if ( tNode.field_max_pos )
+		{
+			if ( tNode.field_max_pos<0 || tNode.field_max_pos>=( 1<<23 ) )
+				return Fail ( MGPU_E_BAD_QUERY );
+			t.m_iTermPos = 4 | ( tNode.field_max_pos<<3 );
+		}
+		m_bAnyTermPos |= t.m_iTermPos!=0;
 		m_dLeaves.push_back ( t );
 		return (int)m_dLeaves.size()-1;
 	}
@@ -611,7 +620,7 @@ struct Planner_c
 			eRanker = MGPU_RANK_BM25;	// ExtRanker_WeightSum_c<WITH_BM25>
 		d.m_eRanker = eRanker;
 		d.m_bStateRanker = ( eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_WORDCOUNT ) ? 1 : 0;	// ExtRanker_State_T
-		d.m_bNeedHits = ( d.m_bStateRanker || d.m_nNWay>0 ) ? 1 : 0;
+		d.m_bNeedHits = ( d.m_bStateRanker || d.m_nNWay>0 || m_bAnyTermPos ) ? 1 : 0;	// position filters look at the hits too
 		const bool bUseBM25 = ( eRanker==MGPU_RANK_BM25 || eRanker==MGPU_RANK_PROXIMITY_BM25 );
 		{
 			// HasQwordDupes, src/sphinxsearch.cpp:4148-4164
@@ -727,8 +736,8 @@ struct Planner_c
 				d.m_dGroupOp0[0] = 0;
 				d.m_dGroupOps[0] = (uint8_t)( d.m_nOps - ( bChainNWay ? 1 : 0 ) );
 			}
-			if ( d.m_bNeedHits && d.m_nGroups>1 )
-				d.m_nGroups = 0;	// hit-consuming DNF stays on dense tiles
+			if ( ( d.m_bNeedHits && d.m_nGroups>1 ) || m_bAnyTermPos )
+				d.m_nGroups = 0;	// hit-consuming DNF and position-filtered keywords stay on dense tiles
 		}
 
 		d.m_nLeaves = (int)m_dLeaves.size();
@@ -749,6 +758,7 @@ struct Planner_c
 				m_tOut.m_iAlgBytes += l.m_pTerm->m_iDoclistLength + l.m_pTerm->m_iSkiplistBytes;
 			}
 			t.m_uQueriedFields = l.m_uFields;
+			t.m_iTermPos = l.m_iTermPos;
 			t.m_fIDF = 0.0f;
 			if ( bUseBM25 && l.m_bOwnsIDF )
 				t.m_fIDF = m_hQwords.at ( m_q.words[l.m_iWord].word ).m_fIDF;

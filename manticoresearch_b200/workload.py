@@ -166,7 +166,10 @@ def random_hit_queries(params, n, seed, max_matches=200):
 
         def leaf(word=None):
             pos[0] += 1
-            node = M.kw(word or M.synth_keyword(sampler.sample(rng) - 1), pos[0])
+            v = rng.random()      # position filters: ^word, word$, ^word$, @field[N] (ExtTermPos_T)
+            node = M.kw(word or M.synth_keyword(sampler.sample(rng) - 1), pos[0], field_start=(v < 0.08 or 0.16 <= v < 0.18), field_end=(0.08 <= v < 0.18))
+            if 0.18 <= v < 0.26:
+                node.field_max_pos = rng.choice([1, 3, 10, 50])
             u = rng.random()
             if u < 0.1:
                 node.field_mask = 1

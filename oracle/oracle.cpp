@@ -547,6 +547,28 @@ struct TermNode_c : Node_c
 	int m_iWordIdx = 0;
 	uint64_t m_uCurHitlistPos = 0;
 	RowID_t m_tCurRowID = INVALID_ROWID;
+	int m_iTermPos = 0;			// TermPosFilter_e: 0 none, 1 field start, 2 field end, 3 both, 4 field limit (src/searchnode.cpp:875-878, 1145-1146)
+	int m_iMaxFieldPos = 0;
+
+	// TermAcceptor_T<..>::IsAcceptableHit, src/searchnode.cpp:2264-2285
+	bool IsAcceptableHit ( Hitpos_t uHit ) const
+	{
+		const DWORD uPos = uHit & 0x7FFFFFu;
+		const bool bEnd = ( uHit>>23 ) & 1u;
+		switch ( m_iTermPos )
+		{
+		case 1:		return uPos==1;
+		case 2:		return bEnd;
+		case 3:		return uPos==1 && bEnd;
+		case 4:		return (int)uPos<=m_iMaxFieldPos;
+		default:	return true;
+		}
+	}
+	bool HitFits ( Hitpos_t uHit ) const
+	{
+		int iField = HitField ( uHit );
+		return iField<32 && ( m_uQueriedFields & ( 1u<<iField ) ) && IsAcceptableHit ( uHit );
+	}
 
 	bool Next ( ExtDoc_t & tDoc ) override
 	{
@@ -562,6 +584,16 @@ struct TermNode_c : Node_c
 			}
 			if ( !( m_tQword.m_uFields & m_uQueriedFields ) )
 				continue;
+			if ( m_iTermPos )
+			{
+				// ExtConditional_T::GetDocsChunk, src/searchnode.cpp:2331-2400: the document survives iff it has an acceptable hit
+				bool bAny = false;
+				m_tQword.SeekHitlist ( m_tQword.m_iHitlistPos );
+				for ( Hitpos_t uHit = m_tQword.GetNextHit(); uHit!=EMPTY_HIT; uHit = m_tQword.GetNextHit() )
+					bAny |= HitFits ( uHit );
+				if ( !bAny )
+					continue;
+			}
 			tDoc.m_tRowID = m_tQword.m_tRowID;
 			tDoc.m_uDocFields = m_tQword.m_uFields & m_uQueriedFields;
 			tDoc.m_fTFIDF = 0.0f;
@@ -581,8 +613,7 @@ struct TermNode_c : Node_c
 			Hitpos_t uHit = m_tQword.GetNextHit();
 			if ( uHit==EMPTY_HIT )
 				break;
-			int iField = HitField ( uHit );
-			if ( iField>=32 || !( m_uQueriedFields & ( 1u<<iField ) ) )
+			if ( !HitFits ( uHit ) )
 				continue;
 			dHits.push_back ( { m_tCurRowID, uHit, (WORD)m_iAtomPos, 0, 1, 1, 1, 0 } );
 		}
@@ -1138,12 +1169,13 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup );
 static TermNode_c * CreateTerm ( const mgpu_xqnode & tNode, int iWord, Setup_t & tSetup )
 {
 	const mgpu_xqkeyword & tWord = tSetup.m_pQuery->words[iWord];
-	if ( tWord.field_start || tWord.field_end || tNode.field_max_pos )
-	{
-		tSetup.m_iError = MGPU_E_UNSUPPORTED;
-		return nullptr;
-	}
 	TermNode_c * p = new TermNode_c;
+	p->m_iTermPos = ( tWord.field_start && tWord.field_end ) ? 3 : tWord.field_start ? 1 : tWord.field_end ? 2 : 0;
+	if ( tNode.field_max_pos )
+	{
+		p->m_iTermPos = 4;
+		p->m_iMaxFieldPos = tNode.field_max_pos;
+	}
 	p->m_tQword.Setup ( tSetup.m_pIndex, tWord.word );
 	p->m_tQword.m_sWord = tWord.word;
 	p->m_tQword.m_iAtomPos = tWord.atom_pos;
@@ -1238,7 +1270,32 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 	bool bAndTerms = ( tNode.op==MGPU_OP_AND );
 	for ( int i=0; i<nChildren && bAndTerms; ++i )
 		bAndTerms = ( q.nodes[pChildren[i]].n_words==1 );
-	if ( bAndTerms && nChildren>1 )
+	bool bMultiAnd = bAndTerms && nChildren>1;
+	for ( int i=0; i<nChildren && bMultiAnd; ++i )
+	{
+		const mgpu_xqnode & tChild = q.nodes[pChildren[i]];
+		const mgpu_xqkeyword & tWord = q.words[tChild.first_word];
+		if ( tWord.field_start || tWord.field_end || tChild.field_max_pos )
+			bMultiAnd = false;	// src/searchnode.cpp:1716-1727
+	}
+	if ( bAndTerms && nChildren>1 && !bMultiAnd )
+	{
+		// terms sorted by frequency, chained with ExtAnd_c (src/searchnode.cpp:1734-1762)
+		std::vector<Node_c*> dTerms;
+		for ( int i=0; i<nChildren; ++i )
+			dTerms.push_back ( CreateNode ( pChildren[i], tSetup ) );
+		RefSort ( dTerms, [] ( Node_c * a, Node_c * b ) { return a->GetDocsCount()<b->GetDocsCount(); } );
+		Node_c * pCur = dTerms[0];
+		for ( size_t i=1; i<dTerms.size(); ++i )
+		{
+			AndNode_c * pAnd = new AndNode_c;
+			pAnd->m_pLeft.reset ( pCur );
+			pAnd->m_pRight.reset ( dTerms[i] );
+			pCur = pAnd;
+		}
+		return pCur;
+	}
+	if ( bMultiAnd )
 	{
 		auto * p = new MultiAndNode_c;
 		p->m_bUseBM25 = tSetup.m_bUseBM25;

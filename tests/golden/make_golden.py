@@ -153,6 +153,26 @@ for qi, tree in [(0, ["phrase", [["aaaa", 1], ["bbbb", 2]]]), (1, ["phrase", [["
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------
+# test_055 "position anchors": ^word / word$ (ExtTermPos_T, TERM_POS_FIELD_START / FIELD_END), incl. a 600-hit document
+# rows in insertion order (the self-joins copy rows with document_id>=10 six times)
+# ---------------------------------------------------------------------------------------------
+rows_055 = [(1, "", "one"), (2, "", "one and two"), (3, "", "one but not the other one"), (4, "", "two and one"), (9, "", "other three")]
+rows_055 += [(i, "", "three") for i in range(10, 20)]
+for shift in (10, 20, 40, 80, 160, 320):
+    rows_055 += [(d + shift, t, b) for d, t, b in rows_055 if d >= 10]
+rows_055.append((2000, "badger " * 600, "badger badger mushroom"))
+rows_055 += [(1000, "", "other"), (1001, "", "other three blind mice")]
+m55 = model("test_055")
+case = {"name": "test_055", "fields": ["title", "body"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1], d[2]]} for d in rows_055], "queries": []}
+for qi, tree in [(0, ["and", ["kw", "one", 1, ALL, {"start": 1}], ["kw", "two", 2]]),
+                 (1, ["and", ["kw", "other", 1, ALL, {"start": 1}], ["kw", "three", 2]]),
+                 (2, ["kw", "three", 1, ALL, {"end": 1}]),
+                 (3, ["kw", "badger", 1, ALL, {"start": 1}])]:
+    case["queries"].append({"text": m55[qi]["query"], "tree": tree, "ranker": "proximity_bm25", "limit": 20, "expect": api_expect(m55[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
 # RTN.WeightBoundary, src/gtests/gtests_rtstuff.cpp:244-335: 1 doc, `@title cat` -> rowid 0, weight 1500
 # ---------------------------------------------------------------------------------------------
 out["cases"].append({

@@ -145,9 +145,12 @@ def tokenize(text, min_word_len=1):
 def tree_to_node(t):
     kind = t[0]
     if kind == "kw":
-        n = M.kw(t[1], t[2])
+        mods = t[4] if len(t) > 4 else {}
+        n = M.kw(t[1], t[2], field_start=bool(mods.get("start")), field_end=bool(mods.get("end")))
         if len(t) > 3:
             n.field_mask = t[3]
+        if mods.get("max_pos"):
+            n.field_max_pos = mods["max_pos"]
         return n
     if kind in ("and", "or", "andnot", "maybe"):
         op = {"and": M.OP_AND, "or": M.OP_OR, "andnot": M.OP_ANDNOT, "maybe": M.OP_MAYBE}[kind]
