@@ -152,6 +152,35 @@ def cpu_oracle_qps(prefix, queries, seconds, threads):
     return n / dt if dt > 0 else 0.0, n, dt
 
 
+def parity_sample(prefix, queries, fetched, n):
+    """full-size spot check outside the timed region: n queries of the batch re-run on the CPU oracle (the checker), compared
+    bit-exactly (rowids, weights, order, total_found) with what the CUDA path returned"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    idx = helpers.OracleIndex(prefix)
+    pick = list(range(0, len(queries), max(1, len(queries) // n)))[:n]
+    bad = []
+    lock = threading.Lock()
+
+    def work(t, nt):
+        for j in range(t, len(pick), nt):
+            qi = pick[j]
+            c = idx.search([queries[qi]]).get(0)
+            g = fetched.get(qi)
+            if (g["status"], g["total_found"], g["rowid"], g["weight"]) != (c["status"], c["total_found"], c["rowid"], c["weight"]):
+                with lock:
+                    bad.append(qi)
+
+    nt = min(16, os.cpu_count() or 1)
+    ths = [threading.Thread(target=work, args=(t, nt)) for t in range(nt)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    idx.close()
+    return {"checked": len(pick), "mismatches": len(bad), "bad_queries": bad[:8], "checker": "oracle/oracle.cpp at full size (10M docs)"}
+
+
 def run_reference(args):
     import manticoresearch_b200.mgpu as M
     from manticoresearch_b200 import workload
@@ -291,7 +320,7 @@ def run_ours(args):
             assert rs.results[0].status == 0
             b2 = None
         else:
-            b2 = index.prepare(queries)
+            b2 = index.prepare(queries, packed)
             b2.run()
             merge_step(b2)
             host_keys = merger.out_keys.cpu()
@@ -351,6 +380,7 @@ def run_ours(args):
                          "frac_of_nominal_8TBs": achieved / 8000.0},
         }
         if world == 1 and not args.no_cpu_baseline:
+            line["parity_sample"] = parity_sample(prefix, queries, fetched, 48)
             threads = os.cpu_count() or 1
             cqps, cn, cdt = cpu_oracle_qps(prefix, queries, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": cqps, "unit": "queries/s", "cores": threads, "kind": "port",

@@ -432,8 +432,8 @@ class Index:
         self._lib.mgpu_index_last_search_stats(self._h, C.byref(st))
         return {k: (list(getattr(st, k)) if k.startswith("class_") else getattr(st, k)) for k, _ in c_batch_stats._fields_}
 
-    def prepare(self, queries):
-        return Batch(self, queries)
+    def prepare(self, queries, packed=None):
+        return Batch(self, queries, packed)
 
     def decode_doclist(self, word):
         import numpy as np
@@ -464,10 +464,10 @@ class Index:
 
 class Batch:
     """mgpu_batch: plan uploaded once; run() may be repeated (the device-resident timed region)."""
-    def __init__(self, index, queries):
+    def __init__(self, index, queries, packed=None):
         self.index, self.queries = index, queries
         self._lib = index._lib
-        self._arr = pack_queries(queries)
+        self._arr = packed if packed is not None else pack_queries(queries)     # `packed`: already marshalled host buffers
         h = C.c_void_p()
         rc = self._lib.mgpu_batch_prepare(index._h, self._arr, len(queries), C.byref(h))
         if rc != MGPU_OK:
