@@ -159,6 +159,8 @@ struct DevQuery_t
 	uint32_t	m_uOrigMask;			///< leaves whose op can bring a document into the result (SET / OR operands)
 	int32_t		m_bOrigHot;				///< one of those is a hot (dense) keyword: every mini-tile has to be visited
 	int32_t		m_iPad;
+	int32_t		m_bPureOr;				///< the program is SET, OR, OR... over keywords (single level): eligible for the register path of stream_kernel
+	int32_t		m_iPad2;
 	int32_t		m_nGroups;				///< >0: the program is an OR of AND groups (DNF; 1 = pure AND): op ranges below
 	uint8_t		m_dGroupOp0[MAX_GROUPS];
 	uint8_t		m_dGroupOps[MAX_GROUPS];
@@ -210,6 +212,7 @@ struct EvalParams_t
 	int32_t					m_iKMax;		///< stride of m_pItemKeys
 	int32_t					m_iPad;
 	uint64_t *				m_pHitpos;		///< hit stage only: [gridDim.x][MAX_LEAVES][TILE_W] hitlist position of (leaf, tile slot)
+	PreEntry_t *			m_pOrList;		///< [gridDim.x][8 warps][512*MAX_LEAVES] sparse postings of the current mini-tile (register-OR path), or null
 	unsigned long long *	m_pQueryThr;	///< [nQueries] shared lower bound of each query's K-th best key (hi word), zeroed per run
 	PreEntry_t *			m_pPre;			///< [gridDim.x][PRE_BLOCKS*32] tile predecode scratch
 	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]

@@ -15,6 +15,7 @@
 #pragma once
 // (included from kernels.cu inside namespace mgpu: uses its DecodeBlock / ApplyTermOp / CtaSelectTopK / MakeKey helpers)
 
+static const int OR_LIST_CAP = 512*MAX_LEAVES;	///< register-OR path: a mini-tile holds at most 512 postings of each of <=16 sparse keywords
 static const int CHUNK_K = 8;				///< rows per lane handled at once (register arrays)
 static const int STREAM_POOL_SLACK = 32768;	///< candidates one round (SYNC_MINIS mini-tiles per warp) can add to the pool
 
@@ -43,6 +44,7 @@ struct StreamShared_t
 	float			m_dTf[256];
 	uint32_t		m_dCur[EVAL_WARPS][MAX_LEAVES];		///< current block of each sparse keyword, per warp
 	uint32_t		m_dCached[EVAL_WARPS][MAX_LEAVES];	///< which block sits in the warp's cache (0xFFFFFFFF = none)
+	uint16_t		m_dOpStart[EVAL_WARPS][MAX_LEAVES+2];	///< register-OR path: first list entry of each op's sparse postings in this mini-tile
 	uint32_t		m_dNext[EVAL_WARPS][MAX_LEAVES];	///< lower bound of the keyword's next rowid at/after the warp's position (exact once its block was examined)
 	uint16_t		m_dRecStart[EVAL_WARPS][34];
 	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 		uint32_t uMini = uMini0;
 		const uint8_t uAliveRoot = (uint8_t)q.m_uAliveRoot;
 		const bool bFastRank = q.m_eRanker==1 && !q.m_nFilters && !q.m_nSortKeys && q.m_nWeights<=4 && !tIdx.m_pDead;
+		const bool bRegOr = bFastRank && q.m_bPureOr && P.m_pOrList;
 
 		for ( uint32_t uRound=0; uRound<nRounds; ++uRound )
 		{
@@ -269,6 +272,166 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 							uMini = max ( uMini+1, ( uNext-tItem.m_uRowLo )/MINI_W );
 						continue;
 					}
+				}
+
+				// Pure OR programs under BM25 relevance (the bulk of class 0): the whole tile program runs in REGISTERS, 8 rows per lane at
+				// a time. Sparse keywords' postings of this mini-tile are first gathered into a short per-warp list (in op order); hot keywords
+				// are read straight from the dense store; nothing touches the shared-memory vectors.
+				if ( MINI_W==512 && bRegOr )
+				{
+					PreEntry_t * pList = P.m_pOrList + ( (size_t)blockIdx.x*EVAL_WARPS+iWarp )*OR_LIST_CAP;
+					int nList = 0;
+					for ( int iOp=0; iOp<q.m_nOps; ++iOp )
+					{
+						const int l = q.m_dOps[iOp].m_uLeaf;
+						const DevLeaf_t & tLeaf = q.m_dLeaves[l];
+						if ( iLane==0 )
+							S.m_dOpStart[iWarp][iOp] = (uint16_t)nList;
+						if ( tLeaf.m_iHot>=0 || S.m_dNext[iWarp][l]>=uHi )
+							continue;
+						const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
+						uint32_t b = tLeaf.m_nBlocks ? StreamSeek ( pBase, tLeaf.m_nBlocks, S.m_dCur[iWarp][l], uLo, iLane ) : 0;
+						uint32_t uNextRow = 0xFFFFFFFFu;
+						while ( b<tLeaf.m_nBlocks )
+						{
+							const uint32_t uBase = __ldg ( pBase+b );
+							if ( uBase>=uHi )
+							{
+								uNextRow = uBase;
+								break;
+							}
+							const uint32_t uNextBase = b+1<tLeaf.m_nBlocks ? __ldg ( pBase+b+1 ) : 0xFFFFFFFFu;
+							StreamCacheBlock ( tIdx, tLeaf, b, &S.m_dCached[iWarp][l], pCache0+l*32, pStage, pRecStart, S.m_dTf, iLane );
+							PreEntry_t tEntry = pCache0[l*32+iLane];
+							const bool bIn = tEntry.m_uRowid>=uLo && tEntry.m_uRowid<uHi;
+							const unsigned m = __ballot_sync ( FULL_MASK, bIn );
+							if ( bIn )
+							{
+								tEntry.m_uRowid -= uLo;	// slot inside the mini-tile
+								pList[nList + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tEntry;
+							}
+							nList += __popc ( m );
+							if ( uNextBase>uHi )
+							{
+								const uint32_t r = pCache0[l*32+iLane].m_uRowid;
+								uint32_t uMin = ( r!=0xFFFFFFFFu && r>=uHi ) ? r : 0xFFFFFFFFu;
+								#pragma unroll
+								for ( int iStep=16; iStep; iStep>>=1 )
+									uMin = min ( uMin, __shfl_xor_sync ( FULL_MASK, uMin, iStep ) );
+								uNextRow = min ( uMin, uNextBase );
+								break;
+							}
+							++b;
+						}
+						__syncwarp();
+						if ( iLane==0 )
+						{
+							S.m_dCur[iWarp][l] = b;
+							S.m_dNext[iWarp][l] = uNextRow;
+						}
+					}
+					if ( iLane==0 )
+						S.m_dOpStart[iWarp][q.m_nOps] = (uint16_t)nList;
+					__syncwarp();
+
+					const uint32_t uThrWx = (uint32_t)( tThr.m_uHi>>32 ), uThrRow = ~(uint32_t)( tThr.m_uLo>>32 );
+					const int nValid = (int)( uHi-uLo );
+					#pragma unroll 1
+					for ( int c=0; c<MINI_W/32/CHUNK_K; ++c )
+					{
+						float dT[CHUNK_K];
+						uint32_t dF[CHUNK_K];
+						uint32_t uPres = 0;
+						#pragma unroll
+						for ( int k=0; k<CHUNK_K; ++k )
+						{
+							dT[k] = 0.0f; dF[k] = 0;
+						}
+						const int iRow0 = c*CHUNK_K*32 + iLane;	// this lane's rows: iRow0 + 32k
+						for ( int iOp=0; iOp<q.m_nOps; ++iOp )
+						{
+							const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+							if ( tLeaf.m_iHot>=0 )
+							{
+								const uint16_t * pD = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride + uLo + iRow0;
+								uint32_t dRaw[CHUNK_K];
+								#pragma unroll
+								for ( int k=0; k<CHUNK_K; ++k )
+									dRaw[k] = __ldg ( pD + k*32 );
+								#pragma unroll
+								for ( int k=0; k<CHUNK_K; ++k )
+								{
+									const uint32_t uHits = dRaw[k] & 255u;
+									const uint32_t uFields = ( dRaw[k]>>8 ) & tLeaf.m_uQueriedFields;
+									if ( !uHits || !uFields )
+										continue;
+									float fBase = S.m_dTf[uHits];
+									if ( uHits==255 )
+										fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+iRow0+k*32 );
+									const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+									// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
+									dT[k] = ( uPres>>k ) & 1u ? __fadd_rn ( dT[k], fTf ) : fTf;
+									dF[k] |= uFields;
+									uPres |= 1u<<k;
+								}
+							} else
+							{
+								const int iTo = S.m_dOpStart[iWarp][iOp+1];
+								for ( int e=S.m_dOpStart[iWarp][iOp]; e<iTo; ++e )
+								{
+									const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
+									const int sRow = (int)tEntry.m_uRowid;
+									if ( ( sRow>>8 )!=c || ( sRow & 31 )!=iLane )
+										continue;
+									const int kk = ( sRow>>5 ) & ( CHUNK_K-1 );
+									#pragma unroll
+									for ( int k=0; k<CHUNK_K; ++k )
+										if ( k==kk )
+										{
+											dT[k] = ( uPres>>k ) & 1u ? __fadd_rn ( dT[k], tEntry.m_fTf ) : tEntry.m_fTf;
+											dF[k] |= tEntry.m_uFields;
+											uPres |= 1u<<k;
+										}
+								}
+							}
+						}
+
+						// rank + threshold + push, straight from the registers
+						#pragma unroll
+						for ( int k=0; k<CHUNK_K; ++k )
+						{
+							bool bPush = false;
+							uint32_t uW = 0;
+							const int sRow = iRow0+k*32;
+							if ( ( ( uPres>>k ) & 1u ) && sRow<nValid )
+							{
+								const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( dT[k], 0.5f ), 1000.0f ) );
+								const uint32_t uRank = dF[k] ? S.m_dRankTab[dF[k] & 15u] : 1u;
+								uW = ( (uint32_t)iSeed + uRank*1000u )*(uint32_t)q.m_iIndexWeight;
+								++iMyTotal;
+								const uint32_t uWx = uW ^ 0x80000000u;
+								bPush = uWx>uThrWx || ( uWx==uThrWx && uLo+sRow+tIdx.m_uRowidBase<=uThrRow );
+							}
+							const unsigned m = __ballot_sync ( FULL_MASK, bPush );
+							if ( m )
+							{
+								int iBase = 0;
+								if ( iLane==0 )
+									iBase = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
+								iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
+								if ( bPush )
+								{
+									Key128_t tKey;
+									tKey.m_uHi = (uint64_t)( uW ^ 0x80000000u )<<32;
+									tKey.m_uLo = ( (uint64_t)( ~( uLo+sRow+tIdx.m_uRowidBase ) )<<32 ) | uW;
+									pPool[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+								}
+							}
+						}
+					}
+					__syncwarp();
+					++uMini;
+					continue;
 				}
 
 				// run the tile program on this warp's private vectors

@@ -686,6 +686,9 @@ struct Planner_c
 		for ( int i=0; i<d.m_nOps; ++i )
 			if ( d.m_dOps[i].m_eCode==OP_TERM_SET || d.m_dOps[i].m_eCode==OP_TERM_OR )
 				d.m_uOrigMask |= 1u<<d.m_dOps[i].m_uLeaf;
+		d.m_bPureOr = ( m_iMaxSp==0 && d.m_nOps>0 && !getenv ( "MGPU_NO_REGOR" ) ) ? 1 : 0;
+		for ( int i=0; i<d.m_nOps && d.m_bPureOr; ++i )
+			d.m_bPureOr = ( d.m_dOps[i].m_eCode==( i ? OP_TERM_OR : OP_TERM_SET ) && d.m_dOps[i].m_uDst==0 ) ? 1 : 0;
 		d.m_iDriverLeaf = -1;
 		if ( !getenv ( "MGPU_NO_JUMP" ) && d.m_nOps>0 && d.m_dOps[0].m_eCode==OP_TERM_SET && (int)d.m_dOps[0].m_uSrc==d.m_nOps+1 )
 			d.m_iDriverLeaf = d.m_dOps[0].m_uLeaf;
@@ -932,13 +935,16 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	const int nTiles = (int)( ( (uint64_t)uRows+TILE_W-1 )/TILE_W );
 	int iMaxKeysPerQuery = 1;
 
-	// hot keywords of the batch: shared by >= 2 doc-only queries and present in >= 1/8 of the rows -> dense store
+	// hot keywords of the batch: shared by >= 2 doc-only queries and present in >= 1/iHotDiv of the rows -> dense store
+	// (2 B/row read per query beats walking the compressed doclist from ~2 postings per 512-row mini-tile on)
+	const int64_t iHotDiv = getenv ( "MGPU_HOT_DIV" ) ? std::max ( 1, atoi ( getenv ( "MGPU_HOT_DIV" ) ) ) : 200;
+	const int64_t iHotGB = getenv ( "MGPU_HOT_GB" ) ? std::max ( 1, atoi ( getenv ( "MGPU_HOT_GB" ) ) ) : 24;
 	if ( pIndex->m_tHdr.m_dFields.size()<=8 && !getenv ( "MGPU_NO_HOT" ) )
 	{
 		std::unordered_map<const TermInfo_t*,int> hUse;
 		for ( int i : dDocOnly )
 			for ( const TermInfo_t * p : m_dPlans[i].m_dLeafTerms )
-				if ( p && (int64_t)p->m_iDocs*8>=(int64_t)uRows )
+				if ( p && (int64_t)p->m_iDocs*iHotDiv>=(int64_t)uRows )
 					++hUse[p];
 		std::vector<std::pair<int64_t,const TermInfo_t*>> dHot;
 		for ( const auto & kv : hUse )
@@ -946,7 +952,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				dHot.push_back ( { (int64_t)kv.second*kv.first->m_iDocs, kv.first } );
 		std::sort ( dHot.begin(), dHot.end(), [] ( const auto & a, const auto & b ) { return a.first>b.first || ( a.first==b.first && a.second->m_uFirstBlk<b.second->m_uFirstBlk ); } );
 		m_iHotStride = (int64_t)nTiles*TILE_W;
-		const size_t nMaxHot = std::min<size_t> ( 256, ( (size_t)4<<30 )/( 2*(size_t)m_iHotStride ) );	// <= 4 GB of store
+		const size_t nMaxHot = std::min<size_t> ( 4096, ( (size_t)iHotGB<<30 )/( 2*(size_t)m_iHotStride ) );	// <= iHotGB of store
 		if ( dHot.size()>nMaxHot )
 			dHot.resize ( nMaxHot );
 		std::unordered_map<const TermInfo_t*,int> hSlot;
@@ -994,7 +1000,11 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		DevQuery_t & q = m_dPlans[i].m_tDev;
 		bool bDnf = q.m_nGroups>0 && !bNoAndKernel;
 		for ( int g=0; g<q.m_nGroups && bDnf; ++g )
-			bDnf = q.m_dLeaves[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf].m_iHot<0;
+		{
+			// the group's driver (its rarest keyword) is walked block by block from the compressed doclist: fine unless it is dense
+			const TermInfo_t * pDrv = m_dPlans[i].m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
+			bDnf = !pDrv || (int64_t)pDrv->m_iDocs*8<(int64_t)uRows;
+		}
 		if ( !bDnf )
 			q.m_nGroups = 0;
 		dOrder [ bDnf ? 2 : ( m_dPlans[i].m_nStack>1 && m_bStream ) ? 3 : 0 ].push_back ( i );
@@ -1187,6 +1197,8 @@ int Batch_c::Run()
 	CUDA_TRY ( tScr.m_dPool.Grow ( m_nPool ), m_sError );
 	CUDA_TRY ( tScr.m_dHitpos.Grow ( m_nHitpos ), m_sError );
 	CUDA_TRY ( tScr.m_dPre.Grow ( m_nPre ), m_sError );
+	if ( m_dCtas[0] )
+		CUDA_TRY ( tScr.m_dOrList.Grow ( (size_t)m_dCtas[0]*EVAL_WARPS*512*MAX_LEAVES ), m_sError );
 	CUDA_TRY ( tScr.m_dPreHitpos.Grow ( m_nPreHitpos ), m_sError );
 	if ( !m_dHotTerms.empty() )
 	{
@@ -1240,6 +1252,7 @@ int Batch_c::Run()
 		P.m_iKMax = m_iKMax;
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
 		P.m_pQueryThr = m_dQueryThr.m_p;
+		P.m_pOrList = c==0 ? tScr.m_dOrList.m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;

@@ -97,7 +97,7 @@ public:
 	{
 		DevBuf_T<Key128_t>		m_dPool;
 		DevBuf_T<uint64_t>		m_dHitpos, m_dPreHitpos;
-		DevBuf_T<PreEntry_t>	m_dPre;
+		DevBuf_T<PreEntry_t>	m_dPre, m_dOrList;
 		DevBuf_T<uint16_t>		m_dHotData;
 		DevBuf_T<uint32_t>		m_dHotEscape;
 		DevBuf_T<int32_t>		m_dHotEscapeCount;
