@@ -236,7 +236,10 @@ def run_ours(args):
     t0 = time.time()
     index = M.Index(prefix, device=local_rank, rowid_base=first_doc)
     load_s = time.time() - t0
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the index's kernels, torch's NCCL collectives and the timing events
+    # (torch's default stream has handle 0, which mgpu_index_set_stream reads as "use the index's private stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     index.set_stream(stream.cuda_stream)
 
     # ---- queries; global IDF inputs when sharded (CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs)
@@ -280,16 +283,23 @@ def run_ours(args):
         for _ in range(args.steps):
             batch.run()
             if world > 1:
-                merge_step(batch)
+                merge_step(batch)       # asynchronous: export + all_gather + merge are stream-ordered, no host sync per step
             else:
                 batch.sync()
-            st = batch.stats()
-            eval_ms.append(st["eval_kernel_ms"])
-            merge_ms.append(st["merge_kernel_ms"])
-            hot_ms.append(st["hot_decode_ms"])
-            class_ms.append(st["class_ms"])
+                st = batch.stats()
+                eval_ms.append(st["eval_kernel_ms"])
+                merge_ms.append(st["merge_kernel_ms"])
+                hot_ms.append(st["hot_decode_ms"])
+                class_ms.append(st["class_ms"])
         ev1.record(stream)
         barrier()
+    if world > 1:
+        batch.sync()                    # kernel times of the last timed step
+        st = batch.stats()
+        eval_ms.append(st["eval_kernel_ms"])
+        merge_ms.append(st["merge_kernel_ms"])
+        hot_ms.append(st["hot_decode_ms"])
+        class_ms.append(st["class_ms"])
     total_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -233,6 +233,7 @@ int				mgpu_index_last_search_stats ( const mgpu_index * idx, mgpu_batch_stats *
  * (src/searchd.cpp:3910-3952, 4653-4738).  Each shard exports, per query, its K best packed
  * 128-bit keys {hi = sort key, lo = ~global_rowid:32 | weight:32} to DEVICE memory (for an NCCL
  * all-gather by the caller); the merge kernel selects the global K best. */
+/* both calls are ASYNCHRONOUS on the index stream / the given stream (stream-ordered after mgpu_batch_run): no host sync inside */
 int				mgpu_batch_export_keys ( mgpu_batch * b, void * dev_keys /* [nq][K][2] u64 */, void * dev_counts /* [nq] i32 */, void * dev_total_found /* [nq] i64 */, int K );
 int				mgpu_merge_shard_keys ( int device, const void * dev_keys /* [n_shards][nq][K][2] u64 */, const void * dev_counts /* [n_shards][nq] i32 */,
 					int n_shards, int nq, int K, void * dev_out_keys /* [nq][K][2] u64 */, void * dev_out_counts /* [nq] i32 */, void * stream );

@@ -185,9 +185,7 @@ int mgpu_batch_export_keys ( mgpu_batch * b, void * dev_keys, void * dev_counts,
 {
 	if ( !b || !dev_keys || !dev_counts || !dev_total_found || K<1 )
 		return MGPU_E_BAD_QUERY;
-	int iRes = b->m_t.Sync();
-	if ( iRes==MGPU_OK )
-		iRes = b->m_t.ExportKeys ( dev_keys, dev_counts, dev_total_found, K );
+	int iRes = b->m_t.ExportKeys ( dev_keys, dev_counts, dev_total_found, K );	// asynchronous, ordered on the index stream
 	if ( iRes!=MGPU_OK )
 		b->m_t.m_pIndex->m_sError = b->m_t.m_sError;
 	return iRes;
@@ -205,15 +203,14 @@ int mgpu_merge_shard_keys ( int device, const void * dev_keys, const void * dev_
 	int iStride = 2;
 	while ( iStride<2*n_shards*K )
 		iStride <<= 1;
-	Key128_t * pScratch = nullptr;
-	if ( cudaMalloc ( (void**)&pScratch, (size_t)nq*iStride*sizeof(Key128_t) )!=cudaSuccess )
-		return MGPU_E_NOMEM;
+	// stream-ordered scratch from the device pool: asynchronous, no device-wide synchronisation (the caller orders on `stream`)
 	cudaStream_t s = (cudaStream_t)stream;
+	Key128_t * pScratch = nullptr;
+	if ( cudaMallocAsync ( (void**)&pScratch, (size_t)nq*iStride*sizeof(Key128_t), s )!=cudaSuccess )
+		return MGPU_E_NOMEM;
 	cudaError_t e = LaunchShardMerge ( (const Key128_t*)dev_keys, (const int32_t*)dev_counts, n_shards, nq, K, pScratch, iStride,
 		(Key128_t*)dev_out_keys, (int32_t*)dev_out_counts, nq<1184 ? nq : 1184, s );
-	if ( e==cudaSuccess )
-		e = cudaStreamSynchronize ( s );
-	cudaFree ( pScratch );
+	cudaFreeAsync ( pScratch, s );
 	return e==cudaSuccess ? MGPU_OK : MGPU_E_CUDA;
 }
 

@@ -1421,7 +1421,6 @@ int Batch_c::ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, 
 		CUDA_TRY ( cudaMemcpyAsync ( pDevCounts, m_dOutCount.m_p, (size_t)nQueries*4, cudaMemcpyDeviceToDevice, s ), m_sError );
 		CUDA_TRY ( cudaMemcpyAsync ( pDevTotal, m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToDevice, s ), m_sError );
 	}
-	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
 	return MGPU_OK;
 }
 

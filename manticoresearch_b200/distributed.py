@@ -68,7 +68,9 @@ def unpack_key(hi, lo):
 
 
 class ShardMerger:
-    """device buffers + the NCCL exchange of one rank; merge(batch) leaves the global top-K keys on every rank"""
+    """device buffers + the NCCL exchange of one rank; merge(batch) leaves the global top-K keys on every rank.
+    Everything is asynchronous and ordered on `stream`, which must be the stream the index runs on
+    (Index.set_stream(stream.cuda_stream)) and torch's current stream (NCCL collectives)."""
 
     def __init__(self, n_queries, k, device, local_rank, stream):
         self.nq, self.k, self.device, self.local_rank, self.stream = n_queries, k, device, local_rank, stream

@@ -278,6 +278,7 @@ def test_rowid_range_shards_merge_equals_unsharded(tmp_path):
             b = s.prepare(queries)
             b.run()
             b.export_keys(all_keys[r].data_ptr(), all_counts[r].data_ptr(), totals[r].data_ptr(), K)
+            b.sync()        # export is asynchronous on the index's own stream; the merge below runs on torch's stream
             b.free()
         out_keys = torch.zeros((nq, K, 2), dtype=torch.int64, device=dev)
         out_counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
