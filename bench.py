@@ -117,8 +117,8 @@ def measured_peak():
 
 
 def ncu_traffic(kernel):
-    """dram bytes (read+write) per launch of `kernel` from the committed ncu --set full capture (profiles/kernel_traffic.json);
-    NB that capture runs a 1000-query batch, so it is scaled to this run by the class's algorithmic bytes by the reader, not here"""
+    """dram bytes (read+write) per launch of `kernel` from the committed ncu --set full capture of this command at N=1
+    (profiles/kernel_traffic.json, see profiles/r01_v8_summary.md)"""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(kernel, {}).get("dram_bytes_per_launch")
     except Exception:
