@@ -29,6 +29,10 @@ WORKLOAD = ("configs[1]: 10M-doc synthetic Zipfian plain index (seed 0x5EED0001,
             "10k-query batch of 2-8 term AND/OR/(a b)|(c d) mixes, SPH_RANK_BM25 field_weights=(title=10,body=1), top-100")
 
 
+WORKLOAD_CFG4 = ("configs[3]: synthetic Zipfian plain index sharded by rowid range (seed 0x5EED0001, V=2^20), 10k-query batch of 2-8 term "
+                 "AND/OR/(a b)|(c d) mixes with 10% ANDNOT, SPH_RANK_BM25 field_weights=(title=10,body=1), top-1000, local top-K + NCCL merge")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,6 +44,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="", choices=["", "and", "or", "mix"], help="analysis only: keep one query shape of the batch")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
+                    help="cfg2 = the bench line (BASELINE.json configs[1]); cfg4 = configs[3] shape for extra runs: same mix + 10%% ANDNOT, top-1000 (use with --docs 100000000 --gpus 8)")
     return ap.parse_args()
 
 
@@ -244,7 +250,11 @@ def run_ours(args):
 
     # ---- queries; global IDF inputs when sharded (CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs)
     from manticoresearch_b200 import distributed as D
-    queries = workload.cfg2_queries(n=args.queries, max_matches=100)
+    K = 100
+    queries = workload.cfg2_queries(n=args.queries, max_matches=K)
+    if args.workload == "cfg4":
+        K = 1000
+        queries = workload.cfg2_queries(n=args.queries, max_matches=K, with_andnot=0.1)
     if args.only:
         def shape(q):
             r = q.root
@@ -252,7 +262,6 @@ def run_ours(args):
                 return "and"
             return "mix" if any(c.children for c in r.children) else "or"
         queries = [q for q in queries if shape(q) == args.only]
-    K = 100
     if world > 1:
         gdf = D.global_keyword_docs(lambda w: (index.word_stats(w) or (0, 0))[0], queries, dev)
         D.apply_global_idf(queries, args.docs, gdf)
@@ -370,7 +379,7 @@ def run_ours(args):
             "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD + (" [ANALYSIS SUBSET: only %s queries]" % args.only if args.only else ""), "docs": args.docs, "queries_per_batch": nq, "parallelism": "rowid-range shards x%d" % world,
+            "config": {"workload": (WORKLOAD if args.workload == "cfg2" else WORKLOAD_CFG4) + (" [ANALYSIS SUBSET: only %s queries]" % args.only if args.only else ""), "docs": args.docs, "queries_per_batch": nq, "parallelism": "rowid-range shards x%d" % world,
                        "l2": "inputs >> L2 (%.1f GB algorithmic bytes per step)" % (job_bytes / 1e9),
                        "index_build_s": round(build_s, 1), "index_load_s": round(load_s, 1), "unsupported_queries": n_unsupported},
             "postings_per_sec": job_postings / (ms_per_step / 1000.0),
