@@ -216,6 +216,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 		const uint8_t uAliveRoot = (uint8_t)q.m_uAliveRoot;
 		const bool bFastRank = q.m_eRanker==1 && !q.m_nFilters && !q.m_nSortKeys && q.m_nWeights<=4 && !tIdx.m_pDead;
 		const bool bRegOr = bFastRank && q.m_bPureOr && P.m_pOrList;
+		const bool bAnyEscape = P.m_tHot.m_pEscapeCount && __ldg ( P.m_tHot.m_pEscapeCount )!=0;	// documents with >= 255 hits of a hot keyword exist
 
 		for ( uint32_t uRound=0; uRound<nRounds; ++uRound )
 		{
@@ -358,17 +359,21 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 								#pragma unroll
 								for ( int k=0; k<CHUNK_K; ++k )
 									dRaw[k] = __ldg ( pD + k*32 );
+								const uint32_t uQueried = tLeaf.m_uQueriedFields;
+								const float fIDF = tLeaf.m_fIDF;
 								#pragma unroll
 								for ( int k=0; k<CHUNK_K; ++k )
 								{
+									if ( !dRaw[k] )
+										continue;	// keyword absent from this row (a present row has hits >= 1)
 									const uint32_t uHits = dRaw[k] & 255u;
-									const uint32_t uFields = ( dRaw[k]>>8 ) & tLeaf.m_uQueriedFields;
-									if ( !uHits || !uFields )
+									const uint32_t uFields = ( dRaw[k]>>8 ) & uQueried;
+									if ( !uFields )
 										continue;
 									float fBase = S.m_dTf[uHits];
-									if ( uHits==255 )
+									if ( bAnyEscape && uHits==255 )
 										fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+iRow0+k*32 );
-									const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+									const float fTf = __fmul_rn ( fBase, fIDF );
 									// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
 									dT[k] = ( uPres>>k ) & 1u ? __fadd_rn ( dT[k], fTf ) : fTf;
 									dF[k] |= uFields;
@@ -396,35 +401,47 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 							}
 						}
 
-						// rank + threshold + push, straight from the registers
+						// rank + threshold, straight from the registers; rows that beat the K-th best so far are rare after warm-up, so the
+						// warp votes once per chunk and only then walks the rows to push
+						uint32_t uValid = uPres;
+						#pragma unroll
+						for ( int k=0; k<CHUNK_K; ++k )
+							if ( iRow0+k*32>=nValid )
+								uValid &= ~( 1u<<k );
+						iMyTotal += __popc ( uValid );
+						uint32_t dW[CHUNK_K];
+						uint32_t uPush = 0;
 						#pragma unroll
 						for ( int k=0; k<CHUNK_K; ++k )
 						{
-							bool bPush = false;
-							uint32_t uW = 0;
-							const int sRow = iRow0+k*32;
-							if ( ( ( uPres>>k ) & 1u ) && sRow<nValid )
+							// seed weight src/sphinxsearch.cpp:1070, ExtRanker_WeightSum_c :1112-1129
+							const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( dT[k], 0.5f ), 1000.0f ) );
+							const uint32_t uRank = dF[k] ? S.m_dRankTab[dF[k] & 15u] : 1u;
+							dW[k] = ( (uint32_t)iSeed + uRank*1000u )*(uint32_t)q.m_iIndexWeight;
+							const uint32_t uWx = dW[k] ^ 0x80000000u;
+							if ( ( ( uValid>>k ) & 1u ) && ( uWx>uThrWx || ( uWx==uThrWx && uLo+iRow0+k*32+tIdx.m_uRowidBase<=uThrRow ) ) )
+								uPush |= 1u<<k;
+						}
+						if ( __any_sync ( FULL_MASK, uPush!=0 ) )
+						{
+							#pragma unroll
+							for ( int k=0; k<CHUNK_K; ++k )
 							{
-								const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( dT[k], 0.5f ), 1000.0f ) );
-								const uint32_t uRank = dF[k] ? S.m_dRankTab[dF[k] & 15u] : 1u;
-								uW = ( (uint32_t)iSeed + uRank*1000u )*(uint32_t)q.m_iIndexWeight;
-								++iMyTotal;
-								const uint32_t uWx = uW ^ 0x80000000u;
-								bPush = uWx>uThrWx || ( uWx==uThrWx && uLo+sRow+tIdx.m_uRowidBase<=uThrRow );
-							}
-							const unsigned m = __ballot_sync ( FULL_MASK, bPush );
-							if ( m )
-							{
-								int iBase = 0;
-								if ( iLane==0 )
-									iBase = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
-								iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
-								if ( bPush )
+								const bool bPush = ( uPush>>k ) & 1u;
+								const unsigned m = __ballot_sync ( FULL_MASK, bPush );
+								if ( m )
 								{
-									Key128_t tKey;
-									tKey.m_uHi = (uint64_t)( uW ^ 0x80000000u )<<32;
-									tKey.m_uLo = ( (uint64_t)( ~( uLo+sRow+tIdx.m_uRowidBase ) )<<32 ) | uW;
-									pPool[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+									int iBase = 0;
+									if ( iLane==0 )
+										iBase = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
+									iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
+									if ( bPush )
+									{
+										Key128_t tKey;
+										tKey.m_uHi = (uint64_t)( dW[k] ^ 0x80000000u )<<32;
+										tKey.m_uLo = ( (uint64_t)( ~( uLo+iRow0+k*32+tIdx.m_uRowidBase ) )<<32 ) | dW[k];
+										pPool[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+									}
 								}
 							}
 						}
