@@ -1636,41 +1636,28 @@ __global__ void __launch_bounds__ ( 256 ) shard_merge_kernel ( const Key128_t * 
 // host-callable launchers (engine.cpp is plain C++ and never sees <<< >>>)
 //////////////////////////////////////////////////////////////////////////
 
-size_t EvalDynSmemBytes ( int nStack, bool bHits )
+/// the CTA-per-tile evaluator is only instantiated for hit-consuming queries; doc-only ones run on stream_kernel / and_kernel
+size_t EvalDynSmemBytes ( int nStack )
 {
-	return bHits ? (size_t)nStack*TILE_W*13 + (size_t)TILE_W*2 : (size_t)nStack*TILE_W*9;
+	return (size_t)nStack*TILE_W*13 + (size_t)TILE_W*2;
 }
 
-cudaError_t LaunchEval ( const EvalParams_t & P, int nStack, bool bHits, int nCtas, cudaStream_t tStream )
+cudaError_t LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream )
 {
-	size_t iDyn = EvalDynSmemBytes ( nStack, bHits );
-	cudaError_t e = bHits
-		? cudaFuncSetAttribute ( eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn )
-		: cudaFuncSetAttribute ( eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	size_t iDyn = EvalDynSmemBytes ( nStack );
+	cudaError_t e = cudaFuncSetAttribute ( eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
 	if ( e!=cudaSuccess )
 		return e;
-	if ( bHits )
-		eval_kernel<true><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
-	else
-		eval_kernel<false><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
+	eval_kernel<true><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
 	return cudaGetLastError();
 }
 
-int EvalOccupancy ( int nStack, bool bHits )
+int EvalOccupancy ( int nStack )
 {
 	int n = 0;
-	size_t iDyn = EvalDynSmemBytes ( nStack, bHits );
-	cudaError_t e;
-	if ( bHits )
-	{
-		cudaFuncSetAttribute ( eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel<true>, EVAL_THREADS, iDyn );
-	} else
-	{
-		cudaFuncSetAttribute ( eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel<false>, EVAL_THREADS, iDyn );
-	}
-	if ( e!=cudaSuccess )
+	size_t iDyn = EvalDynSmemBytes ( nStack );
+	cudaFuncSetAttribute ( eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, eval_kernel<true>, EVAL_THREADS, iDyn )!=cudaSuccess )
 		return 1;
 	return n>0 ? n : 1;
 }

@@ -991,7 +991,6 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			}
 	}
 
-	m_bStream = getenv ( "MGPU_OLD_DENSE" )==nullptr;
 	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
 	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
 	for ( int i : dDocOnly )
@@ -1007,7 +1006,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 		if ( !bDnf )
 			q.m_nGroups = 0;
-		dOrder [ bDnf ? 2 : ( m_dPlans[i].m_nStack>1 && m_bStream ) ? 3 : 0 ].push_back ( i );
+		dOrder [ bDnf ? 2 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
 	}
 
 	// estimated work of a query in its class (decides how many items it is cut into)
@@ -1039,7 +1038,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			iTotalWork += fnWork ( m_dPlans[i], c );
 			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
 		}
-		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( ( c==0 || c==3 ) && m_bStream ) ? StreamOccupancy ( m_dStack[c] ) : EvalOccupancy ( m_dStack[c], c==1 );
+		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 ) ? StreamOccupancy ( m_dStack[c] ) : EvalOccupancy ( m_dStack[c] );
 		const int nMaxCtas = pIndex->m_nSMs*iOcc;
 		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
 
@@ -1258,10 +1257,10 @@ int Batch_c::Run()
 		P.m_tHot = tHot;
 		if ( c==2 || c==4 )
 			CUDA_TRY ( LaunchAnd ( P, c==4, m_dCtas[c], s ), m_sError );
-		else if ( ( c==0 || c==3 ) && m_bStream )
+		else if ( c==0 || c==3 )
 			CUDA_TRY ( LaunchStream ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
 		else
-			CUDA_TRY ( LaunchEval ( P, m_dStack[c], c==1, m_dCtas[c], s ), m_sError );
+			CUDA_TRY ( LaunchEval ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
 		CUDA_TRY ( cudaEventRecord ( m_dEvClass[c], s ), m_sError );
 		m_dClassRan[c] = true;
 		++nLaunches;

@@ -159,7 +159,6 @@ public:
 	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1, 1 };
 	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0, 0 };
 	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0, 0 };
-	bool	m_bStream = true;			///< class 0 runs on stream_kernel (eval_kernel<false> only for A/B comparisons)
 	int		m_iKMax = 1;
 	int		m_iPoolCap = 0;
 	int		m_iScratchStride = 0;
@@ -196,9 +195,9 @@ public:
 };
 
 // kernels.cu launchers
-size_t		EvalDynSmemBytes ( int nStack, bool bHits );
-int			EvalOccupancy ( int nStack, bool bHits );
-cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, bool bHits, int nCtas, cudaStream_t tStream );
+size_t		EvalDynSmemBytes ( int nStack );
+int			EvalOccupancy ( int nStack );
+cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );	///< eval_kernel<hits>
 cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );
 int			StreamOccupancy ( int nStack );
 cudaError_t	LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream );
