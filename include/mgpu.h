@@ -53,7 +53,11 @@ enum {
 	MGPU_RANK_PROXIMITY_BM25 = 0,
 	MGPU_RANK_BM25 = 1,
 	MGPU_RANK_NONE = 2,
-	MGPU_RANK_WORDCOUNT = 3
+	MGPU_RANK_WORDCOUNT = 3,
+	MGPU_RANK_PROXIMITY = 4,   /* SPH_RANK_PROXIMITY (SPH01): RankerState_Proximity_fn<false,..> */
+	MGPU_RANK_MATCHANY = 5,    /* SPH_RANK_MATCHANY (SPH02): RankerState_MatchAny_fn */
+	MGPU_RANK_FIELDMASK = 6,   /* SPH_RANK_FIELDMASK: RankerState_Fieldmask_fn */
+	MGPU_RANK_SPH04 = 7        /* SPH_RANK_SPH04: RankerState_ProximityBM25Exact_fn */
 };
 
 /* ---- sort key parts: ESphSortKeyPart (src/sortsetup.h:19-57) ---- */

@@ -159,6 +159,8 @@ struct DevQuery_t
 	uint32_t	m_uOrigMask;			///< leaves whose op can bring a document into the result (SET / OR operands)
 	int32_t		m_bOrigHot;				///< one of those is a hot (dense) keyword: every mini-tile has to be visited
 	int32_t		m_iPad;
+	int32_t		m_iMaxQpos;				///< ExtRanker_c::m_iMaxQpos (SPH04 exact-hit test)
+	int32_t		m_nQwords;				///< ExtRanker_c::m_iQwords (MATCHANY phrase factor)
 	int32_t		m_bPureOr;				///< the program is SET, OR, OR... over keywords (single level): eligible for the register path of stream_kernel
 	int32_t		m_iPad2;
 	int32_t		m_nGroups;				///< >0: the program is an OR of AND groups (DNF; 1 = pure AND): op ranges below

@@ -328,19 +328,25 @@ struct RankState_t
 	int			m_iExpDelta;
 	int			m_iLastHitPosWithField;
 	uint32_t	m_uLcsTailPos, m_uLcsTailQposMask, m_uCurQposMask, m_uCurPos;
-	uint32_t	m_uWordcount;
+	uint32_t	m_uWordcount;				///< WORDCOUNT sum / FIELDMASK bits
+	uint32_t	m_uHeadHit, m_uExactHit, m_uMinExpPos;	///< SPH04 (RankerState_ProximityBM25Exact_fn)
+	uint8_t		m_uMatchMask[MAX_FIELDS];	///< MATCHANY
 };
 
-__device__ __forceinline__ void RankInit ( RankState_t & r )
+__device__ __forceinline__ void RankInit ( RankState_t & r, int eRanker )
 {
 	#pragma unroll
 	for ( int i=0; i<MAX_FIELDS; ++i )
 		r.m_uLCS[i] = 0;
 	r.m_uCurLCS = 0;
-	r.m_iExpDelta = -1;
+	r.m_iExpDelta = eRanker==7 ? -2147483647 : -1;
 	r.m_iLastHitPosWithField = -1;
 	r.m_uLcsTailPos = 0; r.m_uLcsTailQposMask = 0; r.m_uCurQposMask = 0; r.m_uCurPos = 0;
 	r.m_uWordcount = 0;
+	r.m_uHeadHit = 0; r.m_uExactHit = 0; r.m_uMinExpPos = 0;
+	#pragma unroll
+	for ( int i=0; i<MAX_FIELDS; ++i )
+		r.m_uMatchMask[i] = 0;
 }
 
 __device__ __forceinline__ void RankUpdate ( const DevQuery_t & q, RankState_t & r, const RankHit_t & h )
@@ -351,7 +357,46 @@ __device__ __forceinline__ void RankUpdate ( const DevQuery_t & q, RankState_t &
 		r.m_uWordcount += (uint32_t)q.m_dWeights[uField];	// src/sphinxsearch.cpp:1620-1643
 		return;
 	}
-	if ( !q.m_bDupes )
+	if ( q.m_eRanker==6 )
+	{
+		r.m_uWordcount |= 1u<<uField;	// RankerState_Fieldmask_fn, src/sphinxsearch.cpp:1648-1668
+		return;
+	}
+	if ( q.m_eRanker==7 )
+	{
+		// RankerState_ProximityBM25Exact_fn::Update, src/sphinxsearch.cpp:1476-1514. The state starts every document with
+		// m_iExpDelta = -INT_MAX: the reference's stale m_uMinExpPos makes a document's first hit take the same branch.
+		const int iPosWithField = (int)( h.m_uHitpos & ~( 1u<<23 ) );
+		const int iDelta = iPosWithField - (int)h.m_uQpos;
+		const uint32_t uPos = h.m_uHitpos & 0x7FFFFFu;
+		const bool bEnd = ( h.m_uHitpos>>23 ) & 1u;
+		if ( iDelta==r.m_iExpDelta && (uint32_t)iPosWithField>=r.m_uMinExpPos )
+		{
+			if ( iPosWithField>r.m_iLastHitPosWithField )
+				r.m_uCurLCS = (uint8_t)( r.m_uCurLCS + h.m_uWeight );
+			if ( bEnd && (int)h.m_uQpos==q.m_iMaxQpos && (int)uPos==q.m_iMaxQpos )
+				r.m_uExactHit |= 1u<<uField;
+		} else
+		{
+			if ( iPosWithField>r.m_iLastHitPosWithField )
+				r.m_uCurLCS = (uint8_t)h.m_uWeight;
+			if ( uPos==1 )
+			{
+				r.m_uHeadHit |= 1u<<uField;
+				if ( bEnd && q.m_iMaxQpos==1 )
+					r.m_uExactHit |= 1u<<uField;
+			}
+		}
+		if ( r.m_uCurLCS>r.m_uLCS[uField] )
+			r.m_uLCS[uField] = r.m_uCurLCS;
+		r.m_iExpDelta = iDelta + (int)h.m_uSpanlen - 1;
+		r.m_iLastHitPosWithField = iPosWithField;
+		r.m_uMinExpPos = (uint32_t)iPosWithField + 1;
+		return;
+	}
+	if ( q.m_eRanker==5 )
+		r.m_uMatchMask[uField] |= (uint8_t)( 1u<<( ( h.m_uQpos-1 ) & 31u ) );	// RankerState_MatchAny_fn::Update (BYTE mask)
+	if ( !q.m_bDupes || q.m_eRanker==5 )
 	{
 		// src/sphinxsearch.cpp:1357-1367
 		const int iPosWithField = (int)( h.m_uHitpos & ~( 1u<<23 ) );
@@ -414,7 +459,7 @@ __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, u
 		NWayOpen ( tIdx, q, __ffs ( m )-1, pHitpos, iStride, s, H );
 
 	RankState_t R;
-	RankInit ( R );
+	RankInit ( R, q.m_eRanker );
 	bool bAny = false;
 	while ( true )
 	{
@@ -462,9 +507,34 @@ __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, u
 	if ( !bAny )
 		return false;
 
-	if ( q.m_eRanker==3 )
+	if ( q.m_eRanker==3 || q.m_eRanker==6 )
 		iWeight = (int)R.m_uWordcount;
-	else
+	else if ( q.m_eRanker==7 )
+	{
+		// RankerState_ProximityBM25Exact_fn::Finalize, src/sphinxsearch.cpp:1516-1535
+		uint32_t uRank = 0;
+		for ( int i=0; i<q.m_nWeights; ++i )
+			uRank += ( 4u*R.m_uLCS[i] + 2u*( ( R.m_uHeadHit>>i ) & 1u ) + ( ( R.m_uExactHit>>i ) & 1u ) )*(uint32_t)q.m_dWeights[i];
+		iWeight = (int)( (uint32_t)iSeedWeight + uRank*1000u );
+	} else if ( q.m_eRanker==5 )
+	{
+		// RankerState_MatchAny_fn::Finalize, src/sphinxsearch.cpp:1604-1621
+		uint32_t uPhraseK = 0;
+		for ( int i=0; i<q.m_nWeights; ++i )
+			uPhraseK += (uint32_t)q.m_dWeights[i]*(uint32_t)q.m_nQwords;
+		uint32_t uRank = 0;
+		for ( int i=0; i<q.m_nWeights; ++i )
+			if ( R.m_uMatchMask[i] )
+				uRank += ( (uint32_t)__popc ( R.m_uMatchMask[i] ) + ( (uint32_t)R.m_uLCS[i]-1u )*uPhraseK )*(uint32_t)q.m_dWeights[i];
+		iWeight = (int)uRank;
+	} else if ( q.m_eRanker==4 )
+	{
+		// RankerState_Proximity_fn<false,..>::Finalize: the bare rank
+		uint32_t uRank = 0;
+		for ( int i=0; i<q.m_nWeights; ++i )
+			uRank += (uint32_t)R.m_uLCS[i]*(uint32_t)q.m_dWeights[i];
+		iWeight = (int)uRank;
+	} else
 	{
 		// Finalize, src/sphinxsearch.cpp:1415-1437
 		uint32_t uRank = 0;

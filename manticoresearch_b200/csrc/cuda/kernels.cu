@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 									for ( int i=0; i<q.m_nWeights; ++i )
 										if ( uMask & ( 1u<<i ) )
 											uRank += (uint32_t)q.m_dWeights[i];
-								iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+								iWeight = q.m_eRanker==4 ? (int)uRank : (int)( (uint32_t)iSeed + uRank*1000u );	// ExtRanker_WeightSum_c<false> under SPH_RANK_PROXIMITY
 							}
 						}
 						if ( bOk && tIdx.m_pDead )
@@ -1414,7 +1414,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 								for ( int i=0; i<q.m_nWeights; ++i )
 									if ( uFields & ( 1u<<i ) )
 										uRank += (uint32_t)q.m_dWeights[i];
-							iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+							iWeight = q.m_eRanker==4 ? (int)uRank : (int)( (uint32_t)iSeed + uRank*1000u );	// ExtRanker_WeightSum_c<false> under SPH_RANK_PROXIMITY
 						}
 					}
 					if ( bOk && tIdx.m_pDead )

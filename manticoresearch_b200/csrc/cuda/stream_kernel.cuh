@@ -690,7 +690,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 								for ( int i=0; i<q.m_nWeights; ++i )
 									if ( uMask & ( 1u<<i ) )
 										uRank += (uint32_t)q.m_dWeights[i];
-							iWeight = (int)( (uint32_t)iSeed + uRank*1000u );
+							iWeight = q.m_eRanker==4 ? (int)uRank : (int)( (uint32_t)iSeed + uRank*1000u );	// ExtRanker_WeightSum_c<false> under SPH_RANK_PROXIMITY
 						}
 						if ( bOk && tIdx.m_pDead )
 							bOk = !( ( __ldg ( tIdx.m_pDead+( uRowid>>5 ) )>>( uRowid & 31 ) ) & 1u );

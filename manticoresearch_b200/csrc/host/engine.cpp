@@ -602,8 +602,8 @@ struct Planner_c
 					m_tOut.m_dWordStats[i].hits = p->m_iHits;
 				}
 
-		if ( m_q.ranker!=MGPU_RANK_BM25 && m_q.ranker!=MGPU_RANK_NONE && m_q.ranker!=MGPU_RANK_PROXIMITY_BM25 && m_q.ranker!=MGPU_RANK_WORDCOUNT )
-			return MGPU_E_UNSUPPORTED;
+		if ( m_q.ranker<MGPU_RANK_PROXIMITY_BM25 || m_q.ranker>MGPU_RANK_SPH04 )
+			return MGPU_E_UNSUPPORTED;	// EXPR / EXPORT / PLUGIN rankers need the expression engine
 
 		int iRoot = -1;
 		if ( m_q.n_nodes>0 && m_q.root>=0 )
@@ -619,9 +619,11 @@ struct Planner_c
 		if ( eRanker==MGPU_RANK_PROXIMITY_BM25 && bSingleWord )
 			eRanker = MGPU_RANK_BM25;	// ExtRanker_WeightSum_c<WITH_BM25>
 		d.m_eRanker = eRanker;
-		d.m_bStateRanker = ( eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_WORDCOUNT ) ? 1 : 0;	// ExtRanker_State_T
+		// ExtRanker_State_T (src/sphinxsearch.cpp:4189-4232); a single keyword under PROXIMITY / PROXIMITY_BM25 gets ExtRanker_WeightSum_c
+		d.m_bStateRanker = ( eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_WORDCOUNT || eRanker==MGPU_RANK_MATCHANY
+			|| eRanker==MGPU_RANK_FIELDMASK || eRanker==MGPU_RANK_SPH04 || ( eRanker==MGPU_RANK_PROXIMITY && !bSingleWord ) ) ? 1 : 0;
 		d.m_bNeedHits = ( d.m_bStateRanker || d.m_nNWay>0 || m_bAnyTermPos ) ? 1 : 0;	// position filters look at the hits too
-		const bool bUseBM25 = ( eRanker==MGPU_RANK_BM25 || eRanker==MGPU_RANK_PROXIMITY_BM25 );
+		const bool bUseBM25 = ( eRanker==MGPU_RANK_BM25 || eRanker==MGPU_RANK_PROXIMITY_BM25 || eRanker==MGPU_RANK_SPH04 );
 		{
 			// HasQwordDupes, src/sphinxsearch.cpp:4148-4164
 			std::unordered_map<std::string,int> hSeen;
@@ -635,6 +637,10 @@ struct Planner_c
 			GetQwords ( iRoot );
 			// IDF, src/sphinxsearch.cpp:4293-4361
 			const int iQwords = (int)m_hQwords.size();
+			d.m_nQwords = iQwords;
+			d.m_iMaxQpos = -1;	// max in-query position over the non-excluded keywords (ExtTerm_T::GetQwords return value)
+			for ( const PLeaf_t & l : m_dLeaves )
+				d.m_iMaxQpos = std::max ( d.m_iMaxQpos, m_q.words[l.m_iWord].excluded ? -1 : l.m_iAtomPos );
 			const int64_t iTotalDocuments = m_q.total_docs>0 ? m_q.total_docs : (int64_t)m_tIndex.m_tHdr.m_iTotalDocuments;
 			for ( auto & kv : m_hQwords )
 			{

@@ -235,7 +235,8 @@ def random_hit_queries(params, n, seed, max_matches=200):
             root = M.AND(leaf(w), leaf(), leaf(w)) if rng.random() < 0.5 else M.OR(leaf(w), M.AND(leaf(w), leaf()))
         else:
             root = M.OR(M.ANDNOT(leaf(), leaf()), M.MAYBE(leaf(), leaf()))
-        ranker = rng.choice([M.RANK_PROXIMITY_BM25] * 5 + [M.RANK_WORDCOUNT] * 2 + [M.RANK_BM25, M.RANK_NONE])
+        ranker = rng.choice([M.RANK_PROXIMITY_BM25] * 5 + [M.RANK_WORDCOUNT] * 2 + [M.RANK_BM25, M.RANK_NONE]
+                            + [M.RANK_SPH04] * 3 + [M.RANK_PROXIMITY] * 2 + [M.RANK_MATCHANY] * 2 + [M.RANK_FIELDMASK])
         fw = [rng.choice([1, 2, 10, 0, -3]) for _ in range(2)] if rng.random() < 0.5 else None
         out.append(M.Query(root, ranker=ranker, field_weights=fw, max_matches=rng.choice([5, max_matches, 1000]),
                            index_weight=rng.choice([1, 1, 2])))

@@ -1456,6 +1456,73 @@ struct ProximityState_t
 	}
 };
 
+/// RankerState_ProximityBM25Exact_fn (SPH04), src/sphinxsearch.cpp:1443-1536. NB m_uMinExpPos survives Finalize, like in the reference
+struct Sph04State_t
+{
+	BYTE m_uLCS[256];
+	BYTE m_uCurLCS = 0;
+	int m_iExpDelta = -INT_MAX;
+	int m_iLastHitPos = -1;
+	DWORD m_uMinExpPos = 0;
+	int m_iFields = 0;
+	const int * m_pWeights = nullptr;
+	DWORD m_uHeadHit = 0, m_uExactHit = 0;
+	int m_iMaxQuerypos = 0;
+
+	void Init ( int iFields, const int * pWeights, int iMaxQpos )
+	{
+		memset ( m_uLCS, 0, sizeof(m_uLCS) );
+		m_iFields = iFields;
+		m_pWeights = pWeights;
+		m_iMaxQuerypos = iMaxQpos;
+	}
+	void Update ( const ExtHit_t * pHlist )
+	{
+		DWORD uField = (DWORD)HitField ( pHlist->m_uHitpos );
+		int iPosWithField = (int)HitPosWithField ( pHlist->m_uHitpos );
+		int iDelta = iPosWithField - pHlist->m_uQuerypos;
+		const DWORD uPos = pHlist->m_uHitpos & 0x7FFFFFu;
+		const bool bEnd = ( pHlist->m_uHitpos>>23 ) & 1u;
+		if ( iDelta==m_iExpDelta && HitPosWithField ( pHlist->m_uHitpos )>=m_uMinExpPos )
+		{
+			if ( iPosWithField>m_iLastHitPos )
+				m_uCurLCS = (BYTE)( m_uCurLCS + pHlist->m_uWeight );
+			if ( bEnd && (int)pHlist->m_uQuerypos==m_iMaxQuerypos && (int)uPos==m_iMaxQuerypos )
+				m_uExactHit |= ( 1UL<<uField );
+		} else
+		{
+			if ( iPosWithField>m_iLastHitPos )
+				m_uCurLCS = BYTE(pHlist->m_uWeight);
+			if ( uPos==1 )
+			{
+				m_uHeadHit |= ( 1UL<<uField );
+				if ( bEnd && m_iMaxQuerypos==1 )
+					m_uExactHit |= ( 1UL<<uField );
+			}
+		}
+		if ( m_uCurLCS>m_uLCS[uField] )
+			m_uLCS[uField] = m_uCurLCS;
+		m_iExpDelta = iDelta + pHlist->m_uSpanlen - 1;
+		m_iLastHitPos = iPosWithField;
+		m_uMinExpPos = HitPosWithField ( pHlist->m_uHitpos ) + 1;
+	}
+	int Finalize ( int iSeedWeight )
+	{
+		m_uCurLCS = 0;
+		m_iExpDelta = -1;
+		m_iLastHitPos = -1;
+		int iRank = 0;
+		for ( int i=0; i<m_iFields; i++ )
+		{
+			iRank += (int)( 4*m_uLCS[i] + 2*( ( m_uHeadHit>>i ) & 1 ) + ( ( m_uExactHit>>i ) & 1 ) )*m_pWeights[i];
+			m_uLCS[i] = 0;
+		}
+		m_uHeadHit = 0;
+		m_uExactHit = 0;
+		return iSeedWeight + iRank*SPH_BM25_SCALE;
+	}
+};
+
 struct Match_t
 {
 	RowID_t m_tRowID;
@@ -1569,10 +1636,14 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 	const bool bHitRanker = ( q.ranker==MGPU_RANK_PROXIMITY_BM25 || q.ranker==MGPU_RANK_WORDCOUNT );
 	const mgpu_xqnode & tRoot = q.nodes[q.root];
 	const bool bSingleWord = ( tRoot.n_words==1 && tRoot.n_children==0 );	// XQQuery_t::m_bSingleWord
-	const bool bStateRanker = ( q.ranker==MGPU_RANK_WORDCOUNT ) || ( q.ranker==MGPU_RANK_PROXIMITY_BM25 && !bSingleWord );
+	// sphCreateRanker, src/sphinxsearch.cpp:4189-4232
+	const bool bStateRanker = q.ranker==MGPU_RANK_WORDCOUNT || q.ranker==MGPU_RANK_MATCHANY || q.ranker==MGPU_RANK_FIELDMASK || q.ranker==MGPU_RANK_SPH04
+		|| ( ( q.ranker==MGPU_RANK_PROXIMITY_BM25 || q.ranker==MGPU_RANK_PROXIMITY ) && !bSingleWord );
 	(void)bHitRanker;
+	if ( q.ranker<MGPU_RANK_PROXIMITY_BM25 || q.ranker>MGPU_RANK_SPH04 )
+		return MGPU_E_UNSUPPORTED;
 
-	Setup_t tSetup { &tIndex, &q, q.ranker==MGPU_RANK_PROXIMITY_BM25 || q.ranker==MGPU_RANK_BM25 };
+	Setup_t tSetup { &tIndex, &q, q.ranker==MGPU_RANK_PROXIMITY_BM25 || q.ranker==MGPU_RANK_BM25 || q.ranker==MGPU_RANK_SPH04 };
 	std::unique_ptr<Node_c> pRoot ( CreateNode ( q.root, tSetup ) );
 	if ( tSetup.m_iError!=MGPU_OK )
 		return tSetup.m_iError;
@@ -1590,7 +1661,7 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 
 	// IDFs: sphCreateRanker, src/sphinxsearch.cpp:4293-4378
 	QwordsHash_t hQwords;
-	pRoot->GetQwords ( hQwords );
+	const int iMaxQpos = pRoot->GetQwords ( hQwords );
 	const int iQwords = (int)hQwords.size();
 	int64_t iTotalDocuments = q.total_docs>0 ? q.total_docs : tIndex.m_iTotalDocs;
 	for ( auto & kv : hQwords )
@@ -1646,7 +1717,15 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 	const int iIndexWeight = q.index_weight ? q.index_weight : 1;
 
 	ProximityState_t tProx;
-	tProx.Init ( iFields, dWeights.data(), HasQwordDupes ( q ) );
+	tProx.Init ( iFields, dWeights.data(), HasQwordDupes ( q ) && q.ranker!=MGPU_RANK_MATCHANY );	// MatchAny derives from <false,false>
+	Sph04State_t tSph04;
+	tSph04.Init ( iFields, dWeights.data(), iMaxQpos );
+	// RankerState_MatchAny_fn, src/sphinxsearch.cpp:1582-1622
+	int iPhraseK = 0;
+	for ( int i=0; i<iFields; i++ )
+		iPhraseK += dWeights[i]*iQwords;
+	BYTE dMatchMask[256];
+	memset ( dMatchMask, 0, sizeof(dMatchMask) );
 	std::vector<ExtHit_t> dHits;
 	const int iWeights = std::min ( iFields, 32 );
 
@@ -1692,15 +1771,58 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 				for ( const ExtHit_t & h : dHits )
 					iRank += dWeights [ HitField ( h.m_uHitpos ) ];
 				iWeight = iRank;
+			} else if ( q.ranker==MGPU_RANK_FIELDMASK )
+			{
+				// RankerState_Fieldmask_fn, src/sphinxsearch.cpp:1648-1668
+				DWORD uRank = 0;
+				for ( const ExtHit_t & h : dHits )
+					uRank |= 1UL<<HitField ( h.m_uHitpos );
+				iWeight = (int)uRank;
+			} else if ( q.ranker==MGPU_RANK_SPH04 )
+			{
+				for ( const ExtHit_t & h : dHits )
+					tSph04.Update ( &h );
+				iWeight = tSph04.Finalize ( iWeight );
+			} else if ( q.ranker==MGPU_RANK_MATCHANY )
+			{
+				for ( const ExtHit_t & h : dHits )
+				{
+					tProx.Update ( &h );
+					dMatchMask [ HitField ( h.m_uHitpos ) ] |= (BYTE)( 1<<( h.m_uQuerypos-1 ) );
+				}
+				// Finalize: the LCS state is reset by ProximityState_t::Finalize, so take the ranks first
+				int iRank = 0;
+				for ( int i=0; i<iFields; i++ )
+				{
+					if ( dMatchMask[i] )
+						iRank += (int)( __builtin_popcount ( dMatchMask[i] ) + ( tProx.m_uLCS[i]-1 )*iPhraseK )*dWeights[i];
+					dMatchMask[i] = 0;
+				}
+				tProx.Finalize ( 0 );
+				iWeight = iRank;
 			} else
 			{
 				for ( const ExtHit_t & h : dHits )
 					tProx.Update ( &h );
 				iWeight = tProx.Finalize ( iWeight );
+				if ( q.ranker==MGPU_RANK_PROXIMITY )
+					iWeight /= SPH_BM25_SCALE;	// RankerState_Proximity_fn<false,..>::Finalize returns the bare rank (seed is 0 without BM25)
 			}
 		} else if ( q.ranker==MGPU_RANK_NONE )
 			iWeight = 1;
-		else
+		else if ( q.ranker==MGPU_RANK_PROXIMITY )
+		{
+			// single keyword: ExtRanker_WeightSum_c<false>, src/sphinxsearch.cpp:1131-1134
+			DWORD uRank = 0;
+			DWORD uMask = tDoc.m_uDocFields;
+			if ( !uMask )
+				uRank = 1;
+			else
+				for ( int i=0; i<iWeights; i++ )
+					if ( uMask & ( 1u<<i ) )
+						uRank += (DWORD)dWeights[i];
+			iWeight = (int)uRank;
+		} else
 		{
 			// ExtRanker_WeightSum_c, :1096-1141
 			DWORD uRank = 0;

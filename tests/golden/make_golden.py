@@ -106,6 +106,14 @@ for qi, tree, ranker in [(0, ph, "proximity_bm25"), (1, ph, "bm25"), (2, ph, "no
     case["queries"].append({"text": m37[qi]["query"], "tree": tree, "ranker": ranker, "expect": api_expect(m37[qi])})
 out["cases"].append(case)
 
+# test_037 index `test2` (docs 11..16): `market street` ranked by SPH04 (RankerState_ProximityBM25Exact_fn: LCS*4 + head*2 + exact)
+docs_037b = [(11, "market street", ""), (12, "market street west", ""), (13, "north market street", ""),
+             (14, "farmers market street north", ""), (15, "flower street market", ""), (16, "market street is so very market street", "")]
+case = {"name": "test_037_test2", "fields": ["title", "body"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1], d[2]]} for d in docs_037b], "queries": []}
+case["queries"].append({"text": m37[5]["query"], "tree": ["and", ["kw", "market", 1], ["kw", "street", 2]], "ranker": "sph04", "expect": api_expect(m37[5])})
+out["cases"].append(case)
+
 # ---------------------------------------------------------------------------------------------
 # test_322 "field weights" (fields title, body, spam; default ranker = proximity_bm25; negative weights)
 # ---------------------------------------------------------------------------------------------

@@ -165,7 +165,8 @@ def tree_to_node(t):
     raise ValueError(kind)
 
 
-RANKERS = {"proximity_bm25": M.RANK_PROXIMITY_BM25, "bm25": M.RANK_BM25, "none": M.RANK_NONE, "wordcount": M.RANK_WORDCOUNT}
+RANKERS = {"proximity_bm25": M.RANK_PROXIMITY_BM25, "bm25": M.RANK_BM25, "none": M.RANK_NONE, "wordcount": M.RANK_WORDCOUNT,
+           "proximity": M.RANK_PROXIMITY, "matchany": M.RANK_MATCHANY, "fieldmask": M.RANK_FIELDMASK, "sph04": M.RANK_SPH04}
 
 
 def load_golden():

@@ -115,7 +115,9 @@ def test_random_boolean_trees(synth):
 
 
 def test_rank_none_and_single_word(synth):
-    qs = [M.Query(M.kw("t0000005", 1), ranker=M.RANK_NONE, max_matches=10),
+    qs = [M.Query(M.kw("t0000005", 1), ranker=r, max_matches=10, field_weights=[3, 2])
+          for r in (M.RANK_PROXIMITY, M.RANK_MATCHANY, M.RANK_FIELDMASK, M.RANK_SPH04, M.RANK_WORDCOUNT)]   # single keyword under every ranker
+    qs += [M.Query(M.kw("t0000005", 1), ranker=M.RANK_NONE, max_matches=10),
           M.Query(M.kw("t0000005", 1), ranker=M.RANK_BM25, max_matches=10),
           M.Query(M.kw("t0000005", 1), ranker=M.RANK_PROXIMITY_BM25, max_matches=10),   # single word -> WeightSum ranker
           M.Query(M.kw("nosuchword", 1), ranker=M.RANK_BM25, max_matches=10),
