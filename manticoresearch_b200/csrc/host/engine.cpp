@@ -310,7 +310,7 @@ void RefSort ( std::vector<T> & d, LESS fnLess )
 		}
 }
 
-enum { PN_TERM, PN_MULTIAND, PN_AND, PN_OR, PN_MAYBE, PN_ANDNOT, PN_NWAY };
+enum { PN_TERM, PN_MULTIAND, PN_AND, PN_OR, PN_MAYBE, PN_ANDNOT, PN_NWAY, PN_MULTIOR };
 
 struct PLeaf_t
 {
@@ -395,6 +395,28 @@ struct Planner_c
 				t.m_eKind = PN_TERM;
 				t.m_iLeaf = AddLeaf ( tNode, tNode.first_word, 0 );
 				return t.m_iLeaf<0 ? -1 : NewNode ( t );
+			}
+			if ( tNode.op==MGPU_OP_QUORUM )
+			{
+				// degenerate quorums (src/searchnode.cpp:1638-1688): threshold >= words -> AND, threshold 1 -> OR, over the keywords sorted by
+				// doc count (chains of ExtAnd_c / ExtOr_c); a real ExtQuorum_c is not on the GPU path
+				const int iCount = tNode.n_words, iThr = tNode.oparg;
+				const bool bOr = ( iThr<iCount && iCount<=256 && iThr==1 );
+				if ( iThr<iCount && iCount<=256 && iThr!=1 )
+					return Fail ( MGPU_E_UNSUPPORTED );
+				if ( tNode.first_word<0 || tNode.first_word+iCount>m_q.n_words )
+					return Fail ( MGPU_E_BAD_QUERY );
+				PNode_t t;
+				t.m_eKind = bOr ? PN_MULTIOR : PN_MULTIAND;
+				for ( int i=0; i<iCount; ++i )
+				{
+					int iLeaf = AddLeaf ( tNode, tNode.first_word+i, i );
+					if ( iLeaf<0 )
+						return -1;
+					t.m_dLeaves.push_back ( iLeaf );
+				}
+				RefSort ( t.m_dLeaves, [this] ( int a, int b ) { return m_dLeaves[a].Docs()<m_dLeaves[b].Docs(); } );
+				return NewNode ( t );
 			}
 			if ( tNode.op!=MGPU_OP_PHRASE && tNode.op!=MGPU_OP_PROXIMITY )
 				return Fail ( MGPU_E_UNSUPPORTED );
@@ -507,6 +529,7 @@ struct Planner_c
 		{
 		case PN_TERM:		Register ( t.m_iLeaf ); break;
 		case PN_MULTIAND:
+		case PN_MULTIOR:
 		case PN_NWAY:		for ( int l : t.m_dLeaves ) Register ( l ); break;
 		default:			GetQwords ( t.m_iLeft ); GetQwords ( t.m_iRight ); break;
 		}
@@ -538,6 +561,13 @@ struct Planner_c
 		case PN_TERM:
 			AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_iLeaf, 1 );
 			return 1;
+		case PN_MULTIOR:
+			{
+				AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_dLeaves[0], 1 );
+				for ( size_t i=1; i<t.m_dLeaves.size(); ++i )
+					AddOp ( OP_TERM_OR, iSp, 0, 1, 0, t.m_dLeaves[i], 1 );
+				return 1;
+			}
 		case PN_MULTIAND:
 		case PN_NWAY:
 			{

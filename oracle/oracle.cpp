@@ -1257,6 +1257,31 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 		{
 		case MGPU_OP_PHRASE:	return CreateMultiNode<FSMphrase_c> ( tNode, tSetup );
 		case MGPU_OP_PROXIMITY:	return CreateMultiNode<FSMproximity_c> ( tNode, tSetup );
+		case MGPU_OP_QUORUM:
+			{
+				// degenerate quorums only (src/searchnode.cpp:1638-1688): threshold >= words -> AND, threshold 1 -> OR;
+				// keywords sorted by doc count, chained with ExtAnd_c / ExtOr_c. A real ExtQuorum_c is out of scope.
+				const int iCount = tNode.n_words, iThr = tNode.oparg;
+				const bool bOr = ( iThr<iCount && iCount<=256 && iThr==1 );
+				if ( iThr<iCount && iCount<=256 && iThr!=1 )
+				{
+					tSetup.m_iError = MGPU_E_UNSUPPORTED;
+					return nullptr;
+				}
+				std::vector<Node_c*> dTerms;
+				for ( int i=0; i<iCount; ++i )
+					dTerms.push_back ( CreateTerm ( tNode, tNode.first_word+i, tSetup ) );
+				RefSort ( dTerms, [] ( Node_c * a, Node_c * b ) { return a->GetDocsCount()<b->GetDocsCount(); } );
+				Node_c * pCur = dTerms[0];
+				for ( size_t i=1; i<dTerms.size(); ++i )
+				{
+					TwoferNode_c * pTwo = bOr ? (TwoferNode_c*)new OrNode_c : (TwoferNode_c*)new AndNode_c;
+					pTwo->m_pLeft.reset ( pCur );
+					pTwo->m_pRight.reset ( dTerms[i] );
+					pCur = pTwo;
+				}
+				return pCur;
+			}
 		default:				tSetup.m_iError = MGPU_E_UNSUPPORTED; return nullptr;
 		}
 	}

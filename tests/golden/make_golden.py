@@ -69,6 +69,8 @@ q019 = [
     (0, "basic query", ["and", ["kw", "basic", 1], ["kw", "query", 2]]),
     (1, '"phrase query"', ["phrase", [["phrase", 1], ["query", 2]]]),
     (3, "@title sample @body world", ["and", ["kw", "sample", 1, TITLE], ["kw", "world", 2, BODY]]),
+    (4, '"quorum query test"/1', ["quorum", 1, [["quorum", 1], ["query", 2], ["test", 3]]]),
+    (5, '"quorum query test"/4', ["quorum", 4, [["quorum", 1], ["query", 2], ["test", 3]]]),
     (6, '"hello program"~3', ["prox", 3, [["hello", 1], ["program", 2]]]),
     (7, '"hello program"~4', ["prox", 4, [["hello", 1], ["program", 2]]]),
     (8, "吐", ["kw", "吐", 1]),

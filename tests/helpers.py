@@ -162,6 +162,8 @@ def tree_to_node(t):
         return n
     if kind == "prox":
         return M.PROXIMITY([(w, p) for w, p in t[2]], t[1])
+    if kind == "quorum":
+        return M.Node(M.OP_QUORUM, words=[M.Keyword(w, p) for w, p in t[2]], oparg=t[1])
     raise ValueError(kind)
 
 
