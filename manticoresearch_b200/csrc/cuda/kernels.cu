@@ -593,7 +593,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecode
 			DecodeBlock<false> ( P.m_tIndex, tLeaf, b, dStage[iWarp], dRecStart[iWarp], iLane, d );
 			if ( !d.m_bValid )
 				continue;
-			pD[d.m_uRowid] = (uint16_t)( min ( d.m_uHits, 255u ) | ( ( d.m_uFields & 255u )<<8 ) );
+			const uint32_t uHits = min ( d.m_uHits, 255u );
+			// tf class = ceil ( 15*h/(h+1.2) ) in exact integers: class/15 >= tf, the share of the weight bound of stream_kernel's register-OR path
+			const uint32_t uClass = P.m_bTfClass ? ( 150u*uHits + 10u*uHits+11u )/( 10u*uHits+12u ) : 0u;
+			pD[d.m_uRowid] = (uint16_t)( uHits | ( ( d.m_uFields & 255u )<<8 ) | ( uClass<<12 ) );
 			if ( d.m_uHits>=255u )
 			{
 				const int i = atomicAdd ( P.m_pEscapeCount, 1 );

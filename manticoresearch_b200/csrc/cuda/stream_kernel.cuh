@@ -41,6 +41,18 @@ struct StreamShared_t
 	int				m_iPoolCnt;
 	int				m_iPoolBuf;
 	uint32_t		m_dRankTab[16];
+	int32_t			m_dRankUb[16];						///< bound pass: ( field-weight sum*1000 + 500 )*256 + rounding margin, per matched-field mask
+	const uint16_t * m_dOpPtr[MAX_LEAVES];				///< bound pass: the op's row of the dense store (null = sparse keyword)
+	uint8_t			m_dHotLeaf[MAX_LEAVES];				///< exact pass: hot keywords only (compacted, op order): the keyword's leaf
+	const uint16_t * m_dHotPtr[MAX_LEAVES+4];			///< ... and its row of the dense store
+	int32_t			m_nHotOps;
+	uint2			m_dPosMaskUb[MAX_LEAVES];			///< bound pass, hot keywords with idf > 0: x = field-nibble mask of a row pair, y = bound per tf class
+	const uint16_t * m_dPosPtr[MAX_LEAVES+4];
+	uint2			m_dNegMaskUb[MAX_LEAVES];			///< bound pass, hot keywords with idf < 0: y = |idf| share per tf class, rounded down
+	const uint16_t * m_dNegPtr[MAX_LEAVES];
+	int32_t			m_nPosOps, m_nNegOps;
+	int32_t			m_iNegConst;						///< 14 * sum of the negative keywords' shares: what the bound pass adds to every row on their behalf
+	int32_t			m_bBound;							///< the integer weight bound is usable (no overflow, sane idf); else every present row is evaluated exactly
 	float			m_dTf[256];
 	uint32_t		m_dCur[EVAL_WARPS][MAX_LEAVES];		///< current block of each sparse keyword, per warp
 	uint32_t		m_dCached[EVAL_WARPS][MAX_LEAVES];	///< which block sits in the warp's cache (0xFFFFFFFF = none)
@@ -202,6 +214,68 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 				if ( tid & ( 1<<i ) )
 					uSum += (uint32_t)q.m_dWeights[i];
 			S.m_dRankTab[tid] = uSum;
+			// Is the integer weight bound of the register-OR path usable? ( seed + field-weight sum*1000 )*index weight must stay far
+			// from 2^31, every idf must be a sane number, and two rows' bound sums share a register: the sum over the keywords must
+			// fit 16 bits (|idf| <= 0.5/keywords for any sane collection statistics). If not, every present row takes the exact pass.
+			bool bOk = q.m_iIndexWeight>=1 && q.m_iIndexWeight<=1024 && q.m_nLeaves<=MAX_LEAVES;
+			for ( int i=0; i<4 && i<q.m_nWeights; ++i )
+				bOk = bOk && q.m_dWeights[i]>=0 && q.m_dWeights[i]<=250;
+			float fSum = 0.0f;
+			for ( int l=0; l<q.m_nLeaves && l<MAX_LEAVES; ++l )
+			{
+				const float fIDF = q.m_dLeaves[l].m_fIDF;
+				bOk = bOk && fIDF<=1.0f && fIDF>=-1.0f;
+				fSum += fabsf ( fIDF );
+			}
+			bOk = bOk && fSum<1.0f && P.m_tHot.m_bTfClass;
+			// ( field-weight sum*1000 + 500 )*64 + a margin for the fp32 roundings; no matched field = never a candidate
+			S.m_dRankUb[tid] = !tid ? -( 1<<30 ) : bOk ? (int32_t)( ( uSum*1000u + 500u )*64u + 2u ) : 0;
+			if ( !tid )
+				S.m_bBound = bOk ? 1 : 0;
+		}
+		if ( tid==32 )
+		{
+			// per-op constants of the register-OR path (pure OR programs: one op per keyword); hot keywords are also listed compactly
+			int nHot = 0, nPos = 0, nNeg = 0, iNegConst = 0;
+			for ( int iOp=0; iOp<MAX_LEAVES; ++iOp )
+			{
+				const uint16_t * pRow = nullptr;
+				if ( q.m_bPureOr && iOp<q.m_nOps )
+				{
+					const int l = q.m_dOps[iOp].m_uLeaf;
+					const DevLeaf_t & tLeaf = q.m_dLeaves[l];
+					if ( tLeaf.m_iHot>=0 )
+					{
+						// The store holds c = ceil ( 15*tf ) per row (tf class). idf > 0: tf*idf <= c*idf/15, share rounded up.
+						// idf < 0: tf > (c-1)/15, so tf*idf <= -(c-1)*|idf|/15, share rounded down; the bound pass adds ( 14-(c-1) )*share
+						// per present row and 14*share per absent one, and the threshold moves up by the constant 14*share.
+						const float fIDF = tLeaf.m_fIDF;
+						pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
+						const uint32_t m = tLeaf.m_uQueriedFields & 0xFu;	// this path runs for indexes with <= 4 fields only
+						const uint32_t uMask = ( m<<8 ) | ( m<<24 );
+						const float fShare = __fmul_rn ( fminf ( fabsf ( fIDF ), 1.0f ), 64000.0f/15.0f );
+						if ( fIDF>=0.0f )
+						{
+							S.m_dPosMaskUb[nPos] = make_uint2 ( uMask, (uint32_t)ceilf ( fShare )+1u );
+							S.m_dPosPtr[nPos++] = pRow;
+						} else
+						{
+							const uint32_t uShare = fShare>=2.0f ? (uint32_t)floorf ( fShare )-1u : 0u;
+							S.m_dNegMaskUb[nNeg] = make_uint2 ( uMask, uShare );
+							S.m_dNegPtr[nNeg++] = pRow;
+							iNegConst += 14*(int)uShare;
+						}
+						S.m_dHotPtr[nHot] = pRow;
+						S.m_dHotLeaf[nHot] = (uint8_t)l;
+						++nHot;
+					}
+				}
+				S.m_dOpPtr[iOp] = pRow;
+			}
+			S.m_nHotOps = nHot;
+			S.m_nPosOps = nPos;
+			S.m_nNegOps = nNeg;
+			S.m_iNegConst = iNegConst;
 		}
 		int iMyTotal = 0;
 
@@ -218,13 +292,83 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 		const bool bRegOr = bFastRank && q.m_bPureOr && P.m_pOrList;
 		const bool bAnyEscape = P.m_tHot.m_pEscapeCount && __ldg ( P.m_tHot.m_pEscapeCount )!=0;	// documents with >= 255 hits of a hot keyword exist
 
+		__syncthreads();	// S.m_nHotOps and friends
+		// register-OR path state: the warp's queue of candidate rows waiting for an exact pass, the next row a sparse keyword can touch
+		uint32_t * pQueue = reinterpret_cast<uint32_t *>( dDyn + (size_t)iWarp*nStack*MINI_W*9 ) + MINI_W + 64;	// [32+256], after overlay + pCand
+		int nQueue = 0;
+		uint32_t uNextSparse = 0;
+		const int nOps = q.m_nOps, nHotOps = S.m_nHotOps, nPosOps = S.m_nPosOps, nNegOps = S.m_nNegOps;
+		const int iIndexWeight = q.m_iIndexWeight;
+
+		// ranks one evaluated row and pushes it if it beats the K-th best key so far (one row per lane)
+		auto fnRankPush = [&] ( bool bRow, float fT, uint32_t uF, uint32_t uRow, Key128_t * pPool, uint32_t uThrWx, uint32_t uThrRow )
+		{
+			// seed weight src/sphinxsearch.cpp:1070, ExtRanker_WeightSum_c :1112-1129
+			const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( fT, 0.5f ), 1000.0f ) );
+			const uint32_t uRank = uF ? S.m_dRankTab[uF & 15u] : 1u;
+			const uint32_t uW = ( (uint32_t)iSeed + uRank*1000u )*(uint32_t)iIndexWeight;
+			const uint32_t uWx = uW ^ 0x80000000u;
+			const uint32_t uGlobal = uRow+tIdx.m_uRowidBase;
+			const bool bPush = bRow && ( uWx>uThrWx || ( uWx==uThrWx && uGlobal<=uThrRow ) );
+			const unsigned m = __ballot_sync ( FULL_MASK, bPush );
+			if ( m )
+			{
+				int iSlot = 0;
+				if ( iLane==0 )
+					iSlot = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
+				iSlot = __shfl_sync ( FULL_MASK, iSlot, 0 );
+				if ( bPush )
+				{
+					Key128_t tKey;
+					tKey.m_uHi = (uint64_t)uWx<<32;
+					tKey.m_uLo = ( (uint64_t)( ~uGlobal )<<32 ) | uW;
+					pPool[iSlot + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+				}
+			}
+		};
+		// exact TF*IDF of one queued row per lane from the hot keywords alone (the row holds no sparse posting), in op order
+		auto fnExactHot = [&] ( bool bAct, uint32_t uRow, Key128_t * pPool, uint32_t uThrWx, uint32_t uThrRow )
+		{
+			float fT = 0.0f;
+			uint32_t uF = 0;
+			bool bPres = false;
+			for ( int h0=0; h0<nHotOps; h0+=4 )
+			{
+				uint32_t dRaw[4];
+				#pragma unroll
+				for ( int i=0; i<4; ++i )
+					dRaw[i] = ( bAct && h0+i<nHotOps ) ? __ldg ( S.m_dHotPtr[h0+i]+uRow ) : 0u;
+				#pragma unroll
+				for ( int i=0; i<4; ++i )
+				{
+					const uint32_t uHits = dRaw[i] & 255u;
+					if ( !uHits )
+						continue;
+					const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dHotLeaf[h0+i]];
+					const uint32_t uFields = ( dRaw[i]>>8 ) & tLeaf.m_uQueriedFields;
+					if ( !uFields )
+						continue;
+					float fBase = S.m_dTf[uHits];
+					if ( bAnyEscape && uHits==255 )
+						fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
+					const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+					// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
+					fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
+					uF |= uFields;
+					bPres = true;
+				}
+			}
+			fnRankPush ( bAct && bPres, fT, uF, uRow, pPool, uThrWx, uThrRow );
+		};
+
 		for ( uint32_t uRound=0; uRound<nRounds; ++uRound )
 		{
 			// all warps meet here; compact the candidate pool if this round could overflow it
 			__syncthreads();
 			const int iPoolNow = S.m_iPoolCnt;
 			__syncthreads();	// nobody pushes before everybody has read the level
-			if ( iPoolNow+STREAM_POOL_SLACK>P.m_iPoolCap || ( uRound<=2 && iPoolNow>iK ) )
+			// (register-OR path: a fresh K-th-best bound is what keeps rows out of the exact pass, so compact early and often)
+			if ( iPoolNow+STREAM_POOL_SLACK>P.m_iPoolCap || ( uRound<=2 && iPoolNow>iK ) || ( bRegOr && iPoolNow>=2*iK+1024 ) )
 			{
 				Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 				Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
@@ -250,6 +394,18 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 				}
 			}
 			Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
+			const uint32_t uThrWx = (uint32_t)( tThr.m_uHi>>32 ), uThrRow = ~(uint32_t)( tThr.m_uLo>>32 );
+			// threshold of the bound pass in its own fixed point: ( bound>>6 )*index weight >= K-th best weight
+			int iThrFx = -( 1<<29 ), iThrFxTie = -( 1<<29 );	// no threshold yet / no usable bound: every present row is a candidate
+			if ( bRegOr && S.m_bBound && uThrWx )
+			{
+				const int iW = q.m_iIndexWeight;
+				const long long iThr = (long long)(int)( uThrWx ^ 0x80000000u );
+				long long iQ = iThr>=0 ? ( iThr+iW-1 )/iW : -( ( -iThr )/iW );	// ceil ( thr / index weight )
+				iQ = iQ<-( 1<<22 ) ? -( 1<<22 ) : iQ>( 1<<24 ) ? ( 1<<24 ) : iQ;
+				iThrFx = (int)( iQ*64 ) + S.m_iNegConst;
+				iThrFxTie = iW==1 ? iThrFx+64 : iThrFx;	// a tie with the K-th best weight only counts at a lower rowid
+			}
 			const uint32_t uRoundEnd = min ( uMini1, uMini0 + ( uRound<2 ? uRound+1 : 2+( uRound-1 )*SYNC_MINIS ) );
 
 			while ( uMini<uRoundEnd )
@@ -280,171 +436,273 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 				// are read straight from the dense store; nothing touches the shared-memory vectors.
 				if ( MINI_W==512 && bRegOr )
 				{
+					// Sparse keywords' postings of this mini-tile are first gathered into a short per-warp list (in op order). Then the
+					// mini-tile is evaluated in two passes of 256 rows, 8 CONSECUTIVE rows per lane (one 128-bit load per hot keyword):
+					//  A. bound pass, integers only: OR of the matched-field masks, exact presence count (total_found), and an upper bound of
+					//     the weight: hot keywords contribute ( tf class of the row )*( idf share ), sparse postings their exact tf*idf rounded up;
+					//  B. exact pass, only for rows whose bound reaches the K-th best weight so far: TF*IDF in the reference's order, one
+					//     lane per candidate row. Rows holding a sparse posting are evaluated right away (they need the mini-tile's list);
+					//     the others wait in a per-warp queue until 32 of them fill a pass.
+					// Rows at/after the item's end are never present: the dense store is zero there and the sparse list holds [uLo,uHi) only.
 					PreEntry_t * pList = P.m_pOrList + ( (size_t)blockIdx.x*EVAL_WARPS+iWarp )*OR_LIST_CAP;
 					int nList = 0;
-					for ( int iOp=0; iOp<q.m_nOps; ++iOp )
+					if ( uNextSparse<uHi )
 					{
-						const int l = q.m_dOps[iOp].m_uLeaf;
-						const DevLeaf_t & tLeaf = q.m_dLeaves[l];
-						if ( iLane==0 )
-							S.m_dOpStart[iWarp][iOp] = (uint16_t)nList;
-						if ( tLeaf.m_iHot>=0 || S.m_dNext[iWarp][l]>=uHi )
-							continue;
-						const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
-						uint32_t b = tLeaf.m_nBlocks ? StreamSeek ( pBase, tLeaf.m_nBlocks, S.m_dCur[iWarp][l], uLo, iLane ) : 0;
-						uint32_t uNextRow = 0xFFFFFFFFu;
-						while ( b<tLeaf.m_nBlocks )
-						{
-							const uint32_t uBase = __ldg ( pBase+b );
-							if ( uBase>=uHi )
-							{
-								uNextRow = uBase;
-								break;
-							}
-							const uint32_t uNextBase = b+1<tLeaf.m_nBlocks ? __ldg ( pBase+b+1 ) : 0xFFFFFFFFu;
-							StreamCacheBlock ( tIdx, tLeaf, b, &S.m_dCached[iWarp][l], pCache0+l*32, pStage, pRecStart, S.m_dTf, iLane );
-							PreEntry_t tEntry = pCache0[l*32+iLane];
-							const bool bIn = tEntry.m_uRowid>=uLo && tEntry.m_uRowid<uHi;
-							const unsigned m = __ballot_sync ( FULL_MASK, bIn );
-							if ( bIn )
-							{
-								tEntry.m_uRowid -= uLo;	// slot inside the mini-tile
-								pList[nList + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tEntry;
-							}
-							nList += __popc ( m );
-							if ( uNextBase>uHi )
-							{
-								const uint32_t r = pCache0[l*32+iLane].m_uRowid;
-								uint32_t uMin = ( r!=0xFFFFFFFFu && r>=uHi ) ? r : 0xFFFFFFFFu;
-								#pragma unroll
-								for ( int iStep=16; iStep; iStep>>=1 )
-									uMin = min ( uMin, __shfl_xor_sync ( FULL_MASK, uMin, iStep ) );
-								uNextRow = min ( uMin, uNextBase );
-								break;
-							}
-							++b;
-						}
-						__syncwarp();
-						if ( iLane==0 )
-						{
-							S.m_dCur[iWarp][l] = b;
-							S.m_dNext[iWarp][l] = uNextRow;
-						}
-					}
-					if ( iLane==0 )
-						S.m_dOpStart[iWarp][q.m_nOps] = (uint16_t)nList;
-					__syncwarp();
-
-					const uint32_t uThrWx = (uint32_t)( tThr.m_uHi>>32 ), uThrRow = ~(uint32_t)( tThr.m_uLo>>32 );
-					const int nValid = (int)( uHi-uLo );
-					#pragma unroll 1
-					for ( int c=0; c<MINI_W/32/CHUNK_K; ++c )
-					{
-						float dT[CHUNK_K];
-						uint32_t dF[CHUNK_K];
-						uint32_t uPres = 0;
-						#pragma unroll
-						for ( int k=0; k<CHUNK_K; ++k )
-						{
-							dT[k] = 0.0f; dF[k] = 0;
-						}
-						const int iRow0 = c*CHUNK_K*32 + iLane;	// this lane's rows: iRow0 + 32k
 						for ( int iOp=0; iOp<q.m_nOps; ++iOp )
 						{
-							const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
-							if ( tLeaf.m_iHot>=0 )
+							const int l = q.m_dOps[iOp].m_uLeaf;
+							const DevLeaf_t & tLeaf = q.m_dLeaves[l];
+							if ( iLane==0 )
+								S.m_dOpStart[iWarp][iOp] = (uint16_t)nList;
+							if ( tLeaf.m_iHot>=0 || S.m_dNext[iWarp][l]>=uHi )
+								continue;
+							const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
+							uint32_t b = tLeaf.m_nBlocks ? StreamSeek ( pBase, tLeaf.m_nBlocks, S.m_dCur[iWarp][l], uLo, iLane ) : 0;
+							uint32_t uNextRow = 0xFFFFFFFFu;
+							while ( b<tLeaf.m_nBlocks )
 							{
-								const uint16_t * pD = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride + uLo + iRow0;
-								uint32_t dRaw[CHUNK_K];
-								#pragma unroll
-								for ( int k=0; k<CHUNK_K; ++k )
-									dRaw[k] = __ldg ( pD + k*32 );
-								const uint32_t uQueried = tLeaf.m_uQueriedFields;
-								const float fIDF = tLeaf.m_fIDF;
-								#pragma unroll
-								for ( int k=0; k<CHUNK_K; ++k )
+								const uint32_t uBase = __ldg ( pBase+b );
+								if ( uBase>=uHi )
 								{
-									if ( !dRaw[k] )
-										continue;	// keyword absent from this row (a present row has hits >= 1)
-									const uint32_t uHits = dRaw[k] & 255u;
-									const uint32_t uFields = ( dRaw[k]>>8 ) & uQueried;
-									if ( !uFields )
+									uNextRow = uBase;
+									break;
+								}
+								const uint32_t uNextBase = b+1<tLeaf.m_nBlocks ? __ldg ( pBase+b+1 ) : 0xFFFFFFFFu;
+								StreamCacheBlock ( tIdx, tLeaf, b, &S.m_dCached[iWarp][l], pCache0+l*32, pStage, pRecStart, S.m_dTf, iLane );
+								PreEntry_t tEntry = pCache0[l*32+iLane];
+								const bool bIn = tEntry.m_uRowid>=uLo && tEntry.m_uRowid<uHi;
+								const unsigned m = __ballot_sync ( FULL_MASK, bIn );
+								if ( bIn )
+								{
+									tEntry.m_uRowid -= uLo;	// slot inside the mini-tile
+									// the posting's share of the weight bound: its exact tf*idf, 6 fractional bits, rounded up
+									tEntry.m_uPad = tEntry.m_fTf>0.0f ? (uint32_t)ceilf ( __fmul_rn ( fminf ( tEntry.m_fTf, 1.0f ), 64000.0f ) )+1u : 0u;
+									pList[nList + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tEntry;
+								}
+								nList += __popc ( m );
+								if ( uNextBase>uHi )
+								{
+									const uint32_t r = pCache0[l*32+iLane].m_uRowid;
+									uint32_t uMin = ( r!=0xFFFFFFFFu && r>=uHi ) ? r : 0xFFFFFFFFu;
+									#pragma unroll
+									for ( int iStep=16; iStep; iStep>>=1 )
+										uMin = min ( uMin, __shfl_xor_sync ( FULL_MASK, uMin, iStep ) );
+									uNextRow = min ( uMin, uNextBase );
+									break;
+								}
+								++b;
+							}
+							__syncwarp();
+							if ( iLane==0 )
+							{
+								S.m_dCur[iWarp][l] = b;
+								S.m_dNext[iWarp][l] = uNextRow;
+							}
+						}
+						if ( iLane==0 )
+							S.m_dOpStart[iWarp][q.m_nOps] = (uint16_t)nList;
+						__syncwarp();
+						// the next mini-tile any sparse keyword can touch
+						uNextSparse = 0xFFFFFFFFu;
+						for ( int iOp=0; iOp<q.m_nOps; ++iOp )
+							if ( !S.m_dOpPtr[iOp] )
+								uNextSparse = min ( uNextSparse, S.m_dNext[iWarp][q.m_dOps[iOp].m_uLeaf] );
+					}
+
+					// the next mini-tile's rows of the hot keywords: 8 lines of 128 B each, asked for one mini-tile ahead
+					if ( uLo+2*MINI_W<=tItem.m_uRowHi )
+						for ( int h=iLane>>3; h<nHotOps; h+=4 )
+							asm volatile ( "prefetch.global.L2 [%0];" :: "l" ( S.m_dHotPtr[h]+uLo+MINI_W+( iLane & 7 )*64 ) );
+
+					uint32_t * pOv = reinterpret_cast<uint32_t *>( dDyn + (size_t)iWarp*nStack*MINI_W*9 );	// [512] sparse overlay: bound<<8 | fields
+					uint8_t * pCand = reinterpret_cast<uint8_t *>( pOv + MINI_W );							// [256] candidate rows of the chunk
+					if ( nList )
+					{
+						const uint4 tZero = make_uint4 ( 0, 0, 0, 0 );
+						#pragma unroll
+						for ( int i=0; i<MINI_W/128; ++i )
+							reinterpret_cast<uint4 *>( pOv )[i*32+iLane] = tZero;
+						__syncwarp();
+						for ( int e=iLane; e<nList; e+=32 )
+						{
+							const PreEntry_t tEntry = pList[e];
+							atomicAdd ( pOv+tEntry.m_uRowid, tEntry.m_uPad<<8 );
+							atomicOr ( pOv+tEntry.m_uRowid, tEntry.m_uFields & 0xFFu );
+						}
+						__syncwarp();
+					}
+
+					#pragma unroll 1
+					for ( int c=0; c<MINI_W/256; ++c )
+					{
+						const uint32_t uRowC = uLo + c*256 + iLane*8;	// the first of this lane's 8 rows
+						uint32_t dF[4] = { 0, 0, 0, 0 };					// two rows per word: field masks at bits 8..11 and 24..27
+						uint64_t dUb[4] = { 0, 0, 0, 0 };					// two rows per word: 16-bit bound sums at bits 12..27 and 28..43
+						// four keywords at a time, all four 128-bit loads in flight before the first use
+						for ( int h0=0; h0<nPosOps; h0+=4 )
+						{
+							uint4 dRaw[4];
+							#pragma unroll
+							for ( int i=0; i<4; ++i )
+								if ( h0+i<nPosOps )
+									dRaw[i] = __ldg ( reinterpret_cast<const uint4 *>( S.m_dPosPtr[h0+i]+uRowC ) );
+							#pragma unroll
+							for ( int i=0; i<4; ++i )
+								if ( h0+i<nPosOps )
+								{
+									const uint2 tMaskUb = S.m_dPosMaskUb[h0+i];
+									const uint32_t dW[4] = { dRaw[i].x, dRaw[i].y, dRaw[i].z, dRaw[i].w };
+									#pragma unroll
+									for ( int j=0; j<4; ++j )
+									{
+										dF[j] |= dW[j] & tMaskUb.x;	// a present row has a non-empty field mask
+										dUb[j] += (uint64_t)( dW[j] & 0xF000F000u )*tMaskUb.y;	// tf classes at bits 12..15 / 28..31: one IMAD.WIDE per row pair
+									}
+								}
+						}
+						#pragma unroll 2
+						for ( int h=0; h<nNegOps; ++h )
+						{
+							const uint4 tRaw = __ldg ( reinterpret_cast<const uint4 *>( S.m_dNegPtr[h]+uRowC ) );
+							const uint2 tMaskUb = S.m_dNegMaskUb[h];
+							const uint32_t dW[4] = { tRaw.x, tRaw.y, tRaw.z, tRaw.w };
+							#pragma unroll
+							for ( int j=0; j<4; ++j )
+							{
+								const uint32_t x = dW[j] & tMaskUb.x;
+								dF[j] |= x;
+								// nibble+15 carries into bit 12 / 28 iff the row matches a queried field: 14 - ( class-1 ) if so, else 14
+								const uint32_t uPres = ( x+0x0F000F00u ) & 0x10001000u;
+								const uint32_t uClass = uPres*15u & dW[j];	// class bits of the present rows only
+								dUb[j] += (uint64_t)( 0xE000E000u + uPres - uClass )*tMaskUb.y;
+							}
+						}
+						uint32_t uSparseRows = 0;
+						if ( nList )
+						{
+							const uint4 tOv0 = reinterpret_cast<const uint4 *>( pOv )[c*64+iLane*2], tOv1 = reinterpret_cast<const uint4 *>( pOv )[c*64+iLane*2+1];
+							const uint32_t dO[CHUNK_K] = { tOv0.x, tOv0.y, tOv0.z, tOv0.w, tOv1.x, tOv1.y, tOv1.z, tOv1.w };
+							if ( tOv0.x | tOv0.y | tOv0.z | tOv0.w | tOv1.x | tOv1.y | tOv1.z | tOv1.w )
+							{
+								#pragma unroll
+								for ( int j=0; j<4; ++j )
+								{
+									dUb[j] += ( (uint64_t)( dO[2*j]>>8 )<<12 ) + ( (uint64_t)( dO[2*j+1]>>8 )<<28 );
+									dF[j] |= ( ( dO[2*j] & 0xFu )<<8 ) | ( ( dO[2*j+1] & 0xFu )<<24 );
+								}
+								#pragma unroll
+								for ( int k=0; k<CHUNK_K; ++k )
+									if ( dO[k] )
+										uSparseRows |= 1u<<k;
+							}
+						}
+
+						const int iThrLane = uRowC+tIdx.m_uRowidBase<=uThrRow ? iThrFx : iThrFxTie;	// (conservative: this lane's first row)
+						uint32_t uCand = 0, uPresent = 0;
+						#pragma unroll
+						for ( int j=0; j<4; ++j )
+						{
+							const int iLo = (int)( (uint32_t)( dUb[j]>>12 ) & 0xFFFFu ) + S.m_dRankUb[( dF[j]>>8 ) & 15u];
+							const int iHi = (int)( (uint32_t)( dUb[j]>>28 ) & 0xFFFFu ) + S.m_dRankUb[( dF[j]>>24 ) & 15u];
+							if ( iLo>=iThrLane )
+								uCand |= 1u<<( 2*j );
+							if ( iHi>=iThrLane )
+								uCand |= 2u<<( 2*j );
+							uPresent |= ( ( ( dF[j] & 0x0F000F00u )+0x0F000F00u ) & 0x10001000u )>>j;
+						}
+						iMyTotal += __popc ( uPresent );
+						if ( !__any_sync ( FULL_MASK, uCand!=0 ) )
+							continue;
+
+						// B1. candidate rows without a sparse posting join the warp's queue (row = index-local rowid); full passes run now
+						{
+							const uint32_t uQ = uCand & ~uSparseRows;
+							int iOff = __popc ( uQ );
+							#pragma unroll
+							for ( int d=1; d<32; d<<=1 )
+							{
+								const int t = __shfl_up_sync ( FULL_MASK, iOff, d );
+								if ( iLane>=d )
+									iOff += t;
+							}
+							const int nNew = __shfl_sync ( FULL_MASK, iOff, 31 );
+							if ( nNew )
+							{
+								iOff += nQueue - __popc ( uQ );
+								for ( uint32_t m=uQ; m; m&=m-1 )
+									pQueue[iOff++] = uRowC + __ffs ( m )-1;
+								nQueue += nNew;
+								__syncwarp();
+								while ( nQueue>=32 )
+								{
+									nQueue -= 32;
+									fnExactHot ( true, pQueue[nQueue+iLane], pPool, uThrWx, uThrRow );
+								}
+								__syncwarp();
+							}
+						}
+
+						// B2. candidate rows holding a sparse posting: compact them and evaluate now, one lane per row, all ops in order
+						const uint32_t uNow = uCand & uSparseRows;
+						if ( !__any_sync ( FULL_MASK, uNow!=0 ) )
+							continue;
+						int iOff = __popc ( uNow );
+						#pragma unroll
+						for ( int d=1; d<32; d<<=1 )
+						{
+							const int t = __shfl_up_sync ( FULL_MASK, iOff, d );
+							if ( iLane>=d )
+								iOff += t;
+						}
+						const int nCand = __shfl_sync ( FULL_MASK, iOff, 31 );
+						iOff -= __popc ( uNow );
+						for ( uint32_t m=uNow; m; m&=m-1 )
+							pCand[iOff++] = (uint8_t)( iLane*8 + __ffs ( m )-1 );
+						__syncwarp();
+						for ( int iBase=0; iBase<nCand; iBase+=32 )
+						{
+							const bool bAct = iBase+iLane<nCand;
+							const int sRow = c*256 + ( bAct ? (int)pCand[iBase+iLane] : 0 );	// slot inside the mini-tile
+							float fT = 0.0f;
+							uint32_t uF = 0;
+							bool bPres = false;
+							for ( int iOp=0; iOp<nOps; ++iOp )
+							{
+								const uint16_t * pRow = S.m_dOpPtr[iOp];
+								if ( pRow )
+								{
+									const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+									const uint32_t uRaw = bAct ? __ldg ( pRow+uLo+sRow ) : 0u;
+									const uint32_t uHits = uRaw & 255u;
+									const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
+									if ( !uHits || !uFields )
 										continue;
 									float fBase = S.m_dTf[uHits];
 									if ( bAnyEscape && uHits==255 )
-										fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+iRow0+k*32 );
-									const float fTf = __fmul_rn ( fBase, fIDF );
+										fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+sRow );
+									const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
 									// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
-									dT[k] = ( uPres>>k ) & 1u ? __fadd_rn ( dT[k], fTf ) : fTf;
-									dF[k] |= uFields;
-									uPres |= 1u<<k;
-								}
-							} else
-							{
-								const int iTo = S.m_dOpStart[iWarp][iOp+1];
-								for ( int e=S.m_dOpStart[iWarp][iOp]; e<iTo; ++e )
+									fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
+									uF |= uFields;
+									bPres = true;
+								} else
 								{
-									const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
-									const int sRow = (int)tEntry.m_uRowid;
-									if ( ( sRow>>8 )!=c || ( sRow & 31 )!=iLane )
-										continue;
-									const int kk = ( sRow>>5 ) & ( CHUNK_K-1 );
-									#pragma unroll
-									for ( int k=0; k<CHUNK_K; ++k )
-										if ( k==kk )
-										{
-											dT[k] = ( uPres>>k ) & 1u ? __fadd_rn ( dT[k], tEntry.m_fTf ) : tEntry.m_fTf;
-											dF[k] |= tEntry.m_uFields;
-											uPres |= 1u<<k;
-										}
-								}
-							}
-						}
-
-						// rank + threshold, straight from the registers; rows that beat the K-th best so far are rare after warm-up, so the
-						// warp votes once per chunk and only then walks the rows to push
-						uint32_t uValid = uPres;
-						#pragma unroll
-						for ( int k=0; k<CHUNK_K; ++k )
-							if ( iRow0+k*32>=nValid )
-								uValid &= ~( 1u<<k );
-						iMyTotal += __popc ( uValid );
-						uint32_t dW[CHUNK_K];
-						uint32_t uPush = 0;
-						#pragma unroll
-						for ( int k=0; k<CHUNK_K; ++k )
-						{
-							// seed weight src/sphinxsearch.cpp:1070, ExtRanker_WeightSum_c :1112-1129
-							const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( dT[k], 0.5f ), 1000.0f ) );
-							const uint32_t uRank = dF[k] ? S.m_dRankTab[dF[k] & 15u] : 1u;
-							dW[k] = ( (uint32_t)iSeed + uRank*1000u )*(uint32_t)q.m_iIndexWeight;
-							const uint32_t uWx = dW[k] ^ 0x80000000u;
-							if ( ( ( uValid>>k ) & 1u ) && ( uWx>uThrWx || ( uWx==uThrWx && uLo+iRow0+k*32+tIdx.m_uRowidBase<=uThrRow ) ) )
-								uPush |= 1u<<k;
-						}
-						if ( __any_sync ( FULL_MASK, uPush!=0 ) )
-						{
-							#pragma unroll
-							for ( int k=0; k<CHUNK_K; ++k )
-							{
-								const bool bPush = ( uPush>>k ) & 1u;
-								const unsigned m = __ballot_sync ( FULL_MASK, bPush );
-								if ( m )
-								{
-									int iBase = 0;
-									if ( iLane==0 )
-										iBase = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
-									iBase = __shfl_sync ( FULL_MASK, iBase, 0 );
-									if ( bPush )
+									const int iTo = S.m_dOpStart[iWarp][iOp+1];
+									for ( int e=S.m_dOpStart[iWarp][iOp]; e<iTo; ++e )
 									{
-										Key128_t tKey;
-										tKey.m_uHi = (uint64_t)( dW[k] ^ 0x80000000u )<<32;
-										tKey.m_uLo = ( (uint64_t)( ~( uLo+iRow0+k*32+tIdx.m_uRowidBase ) )<<32 ) | dW[k];
-										pPool[iBase + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
+										const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
+										if ( bAct && (int)tEntry.m_uRowid==sRow )
+										{
+											fT = bPres ? __fadd_rn ( fT, tEntry.m_fTf ) : tEntry.m_fTf;
+											uF |= tEntry.m_uFields;
+											bPres = true;
+										}
 									}
 								}
 							}
+							fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, uThrWx, uThrRow );
 						}
+						__syncwarp();
 					}
 					__syncwarp();
 					++uMini;
@@ -715,6 +973,13 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 				}
 				__syncwarp();
 				++uMini;
+			}
+			// register-OR path: the queued candidate rows are evaluated against this round's threshold and pool buffer
+			if ( nQueue )
+			{
+				fnExactHot ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, uThrWx, uThrRow );
+				nQueue = 0;
+				__syncwarp();
 			}
 		}
 		__syncthreads();

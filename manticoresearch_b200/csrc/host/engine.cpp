@@ -780,6 +780,7 @@ struct Planner_c
 		}
 
 		d.m_nLeaves = (int)m_dLeaves.size();
+		const unsigned nIndexFields = (unsigned)m_tIndex.m_tHdr.m_dFields.size();
 		m_tOut.m_dLeafTerms.assign ( m_dLeaves.size(), nullptr );
 		for ( size_t i=0; i<m_dLeaves.size(); ++i )
 		{
@@ -796,7 +797,8 @@ struct Planner_c
 				m_tOut.m_iCost += l.m_pTerm->m_iDocs;
 				m_tOut.m_iAlgBytes += l.m_pTerm->m_iDoclistLength + l.m_pTerm->m_iSkiplistBytes;
 			}
-			t.m_uQueriedFields = l.m_uFields;
+			// fields the index does not have never match; keeping the mask tight lets the dense store use the spare field bits
+			t.m_uQueriedFields = l.m_uFields & ( nIndexFields>=32 ? 0xFFFFFFFFu : ( ( 1u<<nIndexFields )-1u ) );
 			t.m_iTermPos = l.m_iTermPos;
 			t.m_fIDF = 0.0f;
 			if ( bUseBM25 && l.m_bOwnsIDF )
@@ -1259,6 +1261,7 @@ int Batch_c::Run()
 		H.m_pEscape = tScr.m_dHotEscape.m_p;
 		H.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
 		H.m_iStride = m_iHotStride;
+		H.m_bTfClass = pIndex->m_tHdr.m_dFields.size()<=4 ? 1 : 0;
 		CUDA_TRY ( LaunchHotDecode ( H, pIndex->m_nSMs*8, s ), m_sError );
 		++nLaunches;
 		tHot.m_pData = tScr.m_dHotData.m_p;
@@ -1266,6 +1269,7 @@ int Batch_c::Run()
 		tHot.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
 		tHot.m_iStride = m_iHotStride;
 		tHot.m_nHot = (int)m_dHotTerms.size();
+		tHot.m_bTfClass = H.m_bTfClass;
 	}
 	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
 	for ( int c=0; c<NUM_CLASSES; ++c )
