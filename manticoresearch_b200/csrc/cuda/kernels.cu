@@ -1671,47 +1671,55 @@ static int StreamMiniWidth ( int nStack )
 	return nStack<=1 ? 512 : 256;
 }
 
-size_t StreamDynSmemBytes ( int nStack )
+/// the register-OR class needs per warp: sparse overlay 512*4 + candidate rows 256 + queue (32+256)*4
+static const size_t OR_WARP_SMEM = 512*4 + 256 + 288*4;
+
+size_t StreamDynSmemBytes ( int nStack, bool bOrOnly )
 {
+	if ( bOrOnly )
+		return (size_t)EVAL_WARPS*512*9;	// (the kernel strides its warps by nStack*MINI_W*9 = 4608 >= OR_WARP_SMEM)
 	return (size_t)nStack*EVAL_WARPS*StreamMiniWidth ( nStack )*9;
 }
 
-cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream )
+template<typename KERNEL>
+static cudaError_t LaunchStreamT ( KERNEL fnKernel, const EvalParams_t & P, int nStack, size_t iDyn, int nCtas, cudaStream_t tStream )
 {
-	size_t iDyn = StreamDynSmemBytes ( nStack );
-	if ( StreamMiniWidth ( nStack )==512 )
-	{
-		cudaError_t e = cudaFuncSetAttribute ( stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-		if ( e!=cudaSuccess )
-			return e;
-		stream_kernel<512><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
-	} else
-	{
-		cudaError_t e = cudaFuncSetAttribute ( stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-		if ( e!=cudaSuccess )
-			return e;
-		stream_kernel<256><<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
-	}
+	cudaError_t e = cudaFuncSetAttribute ( fnKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	if ( e!=cudaSuccess )
+		return e;
+	fnKernel<<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P, nStack );
 	return cudaGetLastError();
 }
 
-int StreamOccupancy ( int nStack )
+cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, bool bOrOnly, int nCtas, cudaStream_t tStream )
+{
+	static_assert ( OR_WARP_SMEM<=512*9, "register-OR scratch must fit the warp's slice" );
+	const size_t iDyn = StreamDynSmemBytes ( nStack, bOrOnly );
+	if ( bOrOnly )
+		return LaunchStreamT ( stream_kernel<512,true>, P, 1, iDyn, nCtas, tStream );
+	if ( StreamMiniWidth ( nStack )==512 )
+		return LaunchStreamT ( stream_kernel<512,false>, P, nStack, iDyn, nCtas, tStream );
+	return LaunchStreamT ( stream_kernel<256,false>, P, nStack, iDyn, nCtas, tStream );
+}
+
+template<typename KERNEL>
+static int StreamOccupancyT ( KERNEL fnKernel, size_t iDyn )
 {
 	int n = 0;
-	size_t iDyn = StreamDynSmemBytes ( nStack );
-	cudaError_t e;
-	if ( StreamMiniWidth ( nStack )==512 )
-	{
-		cudaFuncSetAttribute ( stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, stream_kernel<512>, EVAL_THREADS, iDyn );
-	} else
-	{
-		cudaFuncSetAttribute ( stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, stream_kernel<256>, EVAL_THREADS, iDyn );
-	}
-	if ( e!=cudaSuccess )
+	cudaFuncSetAttribute ( fnKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+	if ( cudaOccupancyMaxActiveBlocksPerMultiprocessor ( &n, fnKernel, EVAL_THREADS, iDyn )!=cudaSuccess )
 		return 1;
 	return n>0 ? n : 1;
+}
+
+int StreamOccupancy ( int nStack, bool bOrOnly )
+{
+	const size_t iDyn = StreamDynSmemBytes ( nStack, bOrOnly );
+	if ( bOrOnly )
+		return StreamOccupancyT ( stream_kernel<512,true>, iDyn );
+	if ( StreamMiniWidth ( nStack )==512 )
+		return StreamOccupancyT ( stream_kernel<512,false>, iDyn );
+	return StreamOccupancyT ( stream_kernel<256,false>, iDyn );
 }
 
 cudaError_t LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream )

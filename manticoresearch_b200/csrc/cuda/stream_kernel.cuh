@@ -149,8 +149,10 @@ __device__ __forceinline__ void StreamDenseOp ( float * pT, uint32_t * pF, uint8
 	}
 }
 
-template<int MINI_W>
-__global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams_t P, int nStack )
+/// ORONLY = the class of pure OR programs under BM25 relevance with no filters (the host routes exactly those here): only the
+/// register-OR path is compiled in, so the compiler does not have to share 64 registers with the general tile program
+template<int MINI_W, bool ORONLY>
+__global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel ( EvalParams_t P, int nStack )
 {
 	constexpr int MINI_K = MINI_W/32;							///< rows per lane
 	constexpr int SYNC_MINIS = STREAM_POOL_SLACK/( EVAL_WARPS*MINI_W );	///< mini-tiles per warp between two CTA barriers
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 		uint32_t uMini = uMini0;
 		const uint8_t uAliveRoot = (uint8_t)q.m_uAliveRoot;
 		const bool bFastRank = q.m_eRanker==1 && !q.m_nFilters && !q.m_nSortKeys && q.m_nWeights<=4 && !tIdx.m_pDead;
-		const bool bRegOr = bFastRank && q.m_bPureOr && P.m_pOrList;
+		const bool bRegOr = ORONLY;	// (the host's test: Batch_c::Prepare; bFastRank && pure OR)
 		const bool bAnyEscape = P.m_tHot.m_pEscapeCount && __ldg ( P.m_tHot.m_pEscapeCount )!=0;	// documents with >= 255 hits of a hot keyword exist
 
 		__syncthreads();	// S.m_nHotOps and friends
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 				// Pure OR programs under BM25 relevance (the bulk of class 0): the whole tile program runs in REGISTERS, 8 rows per lane at
 				// a time. Sparse keywords' postings of this mini-tile are first gathered into a short per-warp list (in op order); hot keywords
 				// are read straight from the dense store; nothing touches the shared-memory vectors.
-				if ( MINI_W==512 && bRegOr )
+				if constexpr ( ORONLY )
 				{
 					// Sparse keywords' postings of this mini-tile are first gathered into a short per-warp list (in op order). Then the
 					// mini-tile is evaluated in two passes of 256 rows, 8 CONSECUTIVE rows per lane (one 128-bit load per hot keyword):
@@ -709,6 +711,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 					continue;
 				}
 
+				if constexpr ( !ORONLY )
+				{
 				// run the tile program on this warp's private vectors
 				for ( int iOp=0; iOp<q.m_nOps; ++iOp )
 				{
@@ -973,6 +977,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 4 ) stream_kernel ( EvalParams
 				}
 				__syncwarp();
 				++uMini;
+							}
 			}
 			// register-OR path: the queued candidate rows are evaluated against this round's threshold and pool buffer
 			if ( nQueue )

@@ -1044,7 +1044,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 		if ( !bDnf )
 			q.m_nGroups = 0;
-		dOrder [ bDnf ? 2 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
+		// pure OR programs under BM25 relevance, no filters / sort keys / dead rows, <= 4 fields: the bound + exact pass kernel
+		const bool bOrClass = !bDnf && q.m_bPureOr && q.m_eRanker==1 && !q.m_nFilters && !q.m_nSortKeys && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead;
+		dOrder [ bDnf ? 2 : bOrClass ? 5 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
 	}
 
 	// estimated work of a query in its class (decides how many items it is cut into)
@@ -1061,8 +1063,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			return iWork;
 		}
 		for ( int l=0; l<p.m_tDev.m_nLeaves; ++l )
-			iWork += ( ( c==0 || c==3 ) && p.m_tDev.m_dLeaves[l].m_iHot>=0 ) ? (int64_t)uRows/4 : ( p.m_dLeafTerms[l] ? p.m_dLeafTerms[l]->m_iDocs : 0 );
-		return ( c==0 || c==3 ) ? iWork + uRows/16 : iWork;
+			iWork += ( ( c==0 || c==3 || c==5 ) && p.m_tDev.m_dLeaves[l].m_iHot>=0 ) ? (int64_t)uRows/4 : ( p.m_dLeafTerms[l] ? p.m_dLeafTerms[l]->m_iDocs : 0 );
+		return ( c==0 || c==3 || c==5 ) ? iWork + uRows/16 : iWork;
 	};
 
 	for ( int c=0; c<NUM_CLASSES; ++c )
@@ -1076,9 +1078,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			iTotalWork += fnWork ( m_dPlans[i], c );
 			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
 		}
-		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 ) ? StreamOccupancy ( m_dStack[c] ) : EvalOccupancy ( m_dStack[c] );
+		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 || c==5 ) ? StreamOccupancy ( m_dStack[c], c==5 ) : EvalOccupancy ( m_dStack[c] );
 		const int nMaxCtas = pIndex->m_nSMs*iOcc;
-		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
+		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 || c==5 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
 
 		struct Part_t { int m_iQuery; int m_nParts; int64_t m_iCostPerPart; };
 		std::vector<Part_t> dParts;
@@ -1173,9 +1175,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( m_dI.AllocAsync ( nItems, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dCounter.AllocAsync ( NUM_CLASSES, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
-	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4] } )*2*m_iPoolCap;
+	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4], m_dCtas[5] } )*2*m_iPoolCap;
 	m_nHitpos = std::max ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W, (size_t)m_dCtas[4]*EVAL_WARPS*MAX_LEAVES*32 );
-	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3] } )*PRE_BLOCKS*32;
+	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3], m_dCtas[5] } )*PRE_BLOCKS*32;
 	m_nPreHitpos = (size_t)m_dCtas[1]*PRE_BLOCKS*32;
 	if ( !m_dHotTerms.empty() )
 	{
@@ -1234,8 +1236,8 @@ int Batch_c::Run()
 	CUDA_TRY ( tScr.m_dPool.Grow ( m_nPool ), m_sError );
 	CUDA_TRY ( tScr.m_dHitpos.Grow ( m_nHitpos ), m_sError );
 	CUDA_TRY ( tScr.m_dPre.Grow ( m_nPre ), m_sError );
-	if ( m_dCtas[0] )
-		CUDA_TRY ( tScr.m_dOrList.Grow ( (size_t)m_dCtas[0]*EVAL_WARPS*512*MAX_LEAVES ), m_sError );
+	if ( m_dCtas[5] )
+		CUDA_TRY ( tScr.m_dOrList.Grow ( (size_t)m_dCtas[5]*EVAL_WARPS*512*MAX_LEAVES ), m_sError );
 	CUDA_TRY ( tScr.m_dPreHitpos.Grow ( m_nPreHitpos ), m_sError );
 	if ( !m_dHotTerms.empty() )
 	{
@@ -1291,14 +1293,14 @@ int Batch_c::Run()
 		P.m_iKMax = m_iKMax;
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
 		P.m_pQueryThr = m_dQueryThr.m_p;
-		P.m_pOrList = c==0 ? tScr.m_dOrList.m_p : nullptr;
+		P.m_pOrList = c==5 ? tScr.m_dOrList.m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;
 		if ( c==2 || c==4 )
 			CUDA_TRY ( LaunchAnd ( P, c==4, m_dCtas[c], s ), m_sError );
-		else if ( c==0 || c==3 )
-			CUDA_TRY ( LaunchStream ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
+		else if ( c==0 || c==3 || c==5 )
+			CUDA_TRY ( LaunchStream ( P, m_dStack[c], c==5, m_dCtas[c], s ), m_sError );
 		else
 			CUDA_TRY ( LaunchEval ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
 		CUDA_TRY ( cudaEventRecord ( m_dEvClass[c], s ), m_sError );

@@ -154,11 +154,12 @@ public:
 	std::vector<DevWorkItem_t>	m_dItems;
 	/// launch classes: [0] doc-only queries with a single-level program (stream_kernel<512>), [1] hit-consuming queries on dense
 	/// tiles (eval_kernel<true>), [2] doc-only DNF / pure AND queries led by sparse keywords (and_kernel<false>), [3] deeper doc-only
-	/// programs (stream_kernel<256>), [4] hit-consuming pure AND chains incl. phrase / proximity (and_kernel<true>)
-	static const int NUM_CLASSES = 5;
-	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1, 1 };
-	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0, 0 };
-	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0, 0 };
+	/// programs (stream_kernel<256>), [4] hit-consuming pure AND chains incl. phrase / proximity (and_kernel<true>),
+	/// [5] pure OR programs under BM25 relevance without filters (stream_kernel<512,ORONLY>: bound pass + exact pass)
+	static const int NUM_CLASSES = 6;
+	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1, 1, 1 };
+	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0, 0, 0 };
+	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0, 0, 0 };
 	int		m_iKMax = 1;
 	int		m_iPoolCap = 0;
 	int		m_iScratchStride = 0;
@@ -179,8 +180,8 @@ public:
 	int64_t					m_iHotStride = 0;
 	int						m_iHotEscapeCap = 0;
 	cudaEvent_t				m_tEvHot = nullptr;
-	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false, false };
+	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false, false, false };
 
 	cudaEvent_t		m_tEv0 = nullptr, m_tEv1 = nullptr, m_tEv2 = nullptr;
 	mgpu_batch_stats m_tStats {};
@@ -198,8 +199,8 @@ public:
 size_t		EvalDynSmemBytes ( int nStack );
 int			EvalOccupancy ( int nStack );
 cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );	///< eval_kernel<hits>
-cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );
-int			StreamOccupancy ( int nStack );
+cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, bool bOrOnly, int nCtas, cudaStream_t tStream );
+int			StreamOccupancy ( int nStack, bool bOrOnly );
 cudaError_t	LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream );
 int			AndOccupancy ( bool bHits );
 cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream );
