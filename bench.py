@@ -330,6 +330,9 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers: plan + H2D + kernels + D2H every step
     packed = M.pack_queries(queries)            # the caller's host buffers: flattened XQNode trees in, result arrays out
     host_results = M.ResultSet(queries)
+    if world == 1:
+        for _ in range(min(args.warmup, 2)):        # untimed: first-call costs of this path (pinned staging, pool growth)
+            index.search_packed(packed, nq, host_results)
     barrier()
     e2e_t0 = time.perf_counter()
     h2d = d2h = 0

@@ -51,6 +51,8 @@ struct StreamShared_t
 	uint2			m_dNegMaskUb[MAX_LEAVES];			///< bound pass, hot keywords with idf < 0: y = |idf| share per tf class, rounded down
 	const uint16_t * m_dNegPtr[MAX_LEAVES];
 	int32_t			m_nPosOps, m_nNegOps;
+	uint8_t			m_dSparseOp[MAX_LEAVES];			///< register-OR path: ops whose keyword is walked from the compressed doclist, in op order
+	int32_t			m_nSparseOps;
 	int32_t			m_iNegConst;						///< 14 * sum of the negative keywords' shares: what the bound pass adds to every row on their behalf
 	int32_t			m_bBound;							///< the integer weight bound is usable (no overflow, sane idf); else every present row is evaluated exactly
 	float			m_dTf[256];
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 		if ( tid==32 )
 		{
 			// per-op constants of the register-OR path (pure OR programs: one op per keyword); hot keywords are also listed compactly
-			int nHot = 0, nPos = 0, nNeg = 0, iNegConst = 0;
+			int nHot = 0, nPos = 0, nNeg = 0, nSparse = 0, iNegConst = 0;
 			for ( int iOp=0; iOp<MAX_LEAVES; ++iOp )
 			{
 				const uint16_t * pRow = nullptr;
@@ -270,11 +272,13 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 						S.m_dHotPtr[nHot] = pRow;
 						S.m_dHotLeaf[nHot] = (uint8_t)l;
 						++nHot;
-					}
+					} else
+						S.m_dSparseOp[nSparse++] = (uint8_t)iOp;
 				}
 				S.m_dOpPtr[iOp] = pRow;
 			}
 			S.m_nHotOps = nHot;
+			S.m_nSparseOps = nSparse;
 			S.m_nPosOps = nPos;
 			S.m_nNegOps = nNeg;
 			S.m_iNegConst = iNegConst;
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 		uint32_t * pQueue = reinterpret_cast<uint32_t *>( dDyn + (size_t)iWarp*nStack*MINI_W*9 ) + MINI_W + 64;	// [32+256], after overlay + pCand
 		int nQueue = 0;
 		uint32_t uNextSparse = 0;
-		const int nOps = q.m_nOps, nHotOps = S.m_nHotOps, nPosOps = S.m_nPosOps, nNegOps = S.m_nNegOps;
+		const int nOps = q.m_nOps, nHotOps = S.m_nHotOps, nPosOps = S.m_nPosOps, nNegOps = S.m_nNegOps, nSparseOps = S.m_nSparseOps;
 		const int iIndexWeight = q.m_iIndexWeight;
 
 		// ranks one evaluated row and pushes it if it beats the K-th best key so far (one row per lane)
@@ -363,14 +367,23 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 			fnRankPush ( bAct && bPres, fT, uF, uRow, pPool, uThrWx, uThrRow );
 		};
 
-		for ( uint32_t uRound=0; uRound<nRounds; ++uRound )
+		// Register-OR class: no fixed rounds. A fresh K-th-best bound is what keeps rows out of the exact pass, so the pool is compacted
+		// whenever it holds iTrigger keys: every warp looks at the level before each mini-tile and comes to the barrier when it is reached
+		// (a warp adds at most 512+288 keys in between, far below the pool's slack); after the warm-up pushes are rare and so are barriers.
+		const int iTrigger = min ( 2*iK+1024, iK+16384 );
+		for ( uint32_t uRound=0; ORONLY || uRound<nRounds; ++uRound )
 		{
 			// all warps meet here; compact the candidate pool if this round could overflow it
 			__syncthreads();
 			const int iPoolNow = S.m_iPoolCnt;
-			__syncthreads();	// nobody pushes before everybody has read the level
-			// (register-OR path: a fresh K-th-best bound is what keeps rows out of the exact pass, so compact early and often)
-			if ( iPoolNow+STREAM_POOL_SLACK>P.m_iPoolCap || ( uRound<=2 && iPoolNow>iK ) || ( bRegOr && iPoolNow>=2*iK+1024 ) )
+			// nobody pushes before everybody has read the level
+			if constexpr ( ORONLY )
+			{
+				if ( !__syncthreads_or ( uMini<uMini1 ) )
+					break;	// every warp has finished its share
+			} else
+				__syncthreads();
+			if ( ORONLY ? iPoolNow>=iTrigger : ( iPoolNow+STREAM_POOL_SLACK>P.m_iPoolCap || ( uRound<=2 && iPoolNow>iK ) ) )
 			{
 				Key128_t * pIn = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 				Key128_t * pOut = pPool0 + (size_t)( S.m_iPoolBuf^1 )*P.m_iPoolCap;
@@ -396,22 +409,41 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 				}
 			}
 			Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
-			const uint32_t uThrWx = (uint32_t)( tThr.m_uHi>>32 ), uThrRow = ~(uint32_t)( tThr.m_uLo>>32 );
-			// threshold of the bound pass in its own fixed point: ( bound>>6 )*index weight >= K-th best weight
-			int iThrFx = -( 1<<29 ), iThrFxTie = -( 1<<29 );	// no threshold yet / no usable bound: every present row is a candidate
-			if ( bRegOr && S.m_bBound && uThrWx )
+			uint32_t uThrWx, uThrRow;
+			int iThrFx, iThrFxTie;
+			auto fnSetThr = [&] ( uint64_t uHiWord, uint64_t uLoWord )
 			{
-				const int iW = q.m_iIndexWeight;
-				const long long iThr = (long long)(int)( uThrWx ^ 0x80000000u );
-				long long iQ = iThr>=0 ? ( iThr+iW-1 )/iW : -( ( -iThr )/iW );	// ceil ( thr / index weight )
-				iQ = iQ<-( 1<<22 ) ? -( 1<<22 ) : iQ>( 1<<24 ) ? ( 1<<24 ) : iQ;
-				iThrFx = (int)( iQ*64 ) + S.m_iNegConst;
-				iThrFxTie = iW==1 ? iThrFx+64 : iThrFx;	// a tie with the K-th best weight only counts at a lower rowid
-			}
-			const uint32_t uRoundEnd = min ( uMini1, uMini0 + ( uRound<2 ? uRound+1 : 2+( uRound-1 )*SYNC_MINIS ) );
+				uThrWx = (uint32_t)( uHiWord>>32 );
+				uThrRow = ~(uint32_t)( uLoWord>>32 );
+				// threshold of the bound pass in its own fixed point: ( bound>>6 )*index weight >= K-th best weight
+				iThrFx = iThrFxTie = -( 1<<29 );	// no threshold yet / no usable bound: every present row is a candidate
+				if ( bRegOr && S.m_bBound && uThrWx )
+				{
+					const int iW = q.m_iIndexWeight;
+					const long long iThr = (long long)(int)( uThrWx ^ 0x80000000u );
+					long long iQ = iThr>=0 ? ( iThr+iW-1 )/iW : -( ( -iThr )/iW );	// ceil ( thr / index weight )
+					iQ = iQ<-( 1<<22 ) ? -( 1<<22 ) : iQ>( 1<<24 ) ? ( 1<<24 ) : iQ;
+					iThrFx = (int)( iQ*64 ) + S.m_iNegConst;
+					iThrFxTie = iW==1 ? iThrFx+64 : iThrFx;	// a tie with the K-th best weight only counts at a lower rowid
+				}
+			};
+			fnSetThr ( tThr.m_uHi, tThr.m_uLo );
+			const uint32_t uRoundEnd = ORONLY ? uMini1 : min ( uMini1, uMini0 + ( uRound<2 ? uRound+1 : 2+( uRound-1 )*SYNC_MINIS ) );
 
 			while ( uMini<uRoundEnd )
 			{
+				if constexpr ( ORONLY )
+				{
+					if ( *( (volatile int *)&S.m_iPoolCnt )>=iTrigger )
+						break;	// time to compact the pool: all warps meet at the barrier above
+					if ( ( uMini & 7u )==7u )
+					{
+						// another item of this query may have raised the shared lower bound of the K-th best key meanwhile
+						const unsigned long long uShared = *( (volatile unsigned long long *)( P.m_pQueryThr+tItem.m_uQuery ) );
+						if ( uShared>( (unsigned long long)uThrWx<<32 ) )
+							fnSetThr ( uShared, 0 );
+					}
+				}
 				const uint32_t uLo = tItem.m_uRowLo + uMini*MINI_W;
 				const uint32_t uHi = min ( uLo+(uint32_t)MINI_W, tItem.m_uRowHi );
 
@@ -450,13 +482,13 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 					int nList = 0;
 					if ( uNextSparse<uHi )
 					{
-						for ( int iOp=0; iOp<q.m_nOps; ++iOp )
+						for ( int iSp=0; iSp<nSparseOps; ++iSp )
 						{
-							const int l = q.m_dOps[iOp].m_uLeaf;
+							const int l = q.m_dOps[S.m_dSparseOp[iSp]].m_uLeaf;
 							const DevLeaf_t & tLeaf = q.m_dLeaves[l];
 							if ( iLane==0 )
-								S.m_dOpStart[iWarp][iOp] = (uint16_t)nList;
-							if ( tLeaf.m_iHot>=0 || S.m_dNext[iWarp][l]>=uHi )
+								S.m_dOpStart[iWarp][iSp] = (uint16_t)nList;
+							if ( S.m_dNext[iWarp][l]>=uHi )
 								continue;
 							const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
 							uint32_t b = tLeaf.m_nBlocks ? StreamSeek ( pBase, tLeaf.m_nBlocks, S.m_dCur[iWarp][l], uLo, iLane ) : 0;
@@ -502,13 +534,12 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 							}
 						}
 						if ( iLane==0 )
-							S.m_dOpStart[iWarp][q.m_nOps] = (uint16_t)nList;
+							S.m_dOpStart[iWarp][nSparseOps] = (uint16_t)nList;
 						__syncwarp();
 						// the next mini-tile any sparse keyword can touch
 						uNextSparse = 0xFFFFFFFFu;
-						for ( int iOp=0; iOp<q.m_nOps; ++iOp )
-							if ( !S.m_dOpPtr[iOp] )
-								uNextSparse = min ( uNextSparse, S.m_dNext[iWarp][q.m_dOps[iOp].m_uLeaf] );
+						for ( int iSp=0; iSp<nSparseOps; ++iSp )
+							uNextSparse = min ( uNextSparse, S.m_dNext[iWarp][q.m_dOps[S.m_dSparseOp[iSp]].m_uLeaf] );
 					}
 
 					// the next mini-tile's rows of the hot keywords: 8 lines of 128 B each, asked for one mini-tile ahead
@@ -668,6 +699,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 							float fT = 0.0f;
 							uint32_t uF = 0;
 							bool bPres = false;
+							int iSp = 0;
 							for ( int iOp=0; iOp<nOps; ++iOp )
 							{
 								const uint16_t * pRow = S.m_dOpPtr[iOp];
@@ -689,8 +721,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 									bPres = true;
 								} else
 								{
-									const int iTo = S.m_dOpStart[iWarp][iOp+1];
-									for ( int e=S.m_dOpStart[iWarp][iOp]; e<iTo; ++e )
+									const int iTo = S.m_dOpStart[iWarp][iSp+1];
+									for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
 									{
 										const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
 										if ( bAct && (int)tEntry.m_uRowid==sRow )
@@ -700,6 +732,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 											bPres = true;
 										}
 									}
+									++iSp;
 								}
 							}
 							fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, uThrWx, uThrRow );

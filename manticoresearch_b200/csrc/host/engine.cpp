@@ -1031,6 +1031,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 
 	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
 	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
+	// a group's driver may sit in at most iDnfMul/iDnfDiv of the rows (MGPU_DNF_PCT: percent, for experiments)
+	const int64_t iDnfDiv = 100, iDnfMul = getenv ( "MGPU_DNF_PCT" ) ? std::max ( 1, atoi ( getenv ( "MGPU_DNF_PCT" ) ) ) : 12;
 	for ( int i : dDocOnly )
 	{
 		// intersection kernel: DNF programs (1 group = pure AND) whose every group is led by a sparse keyword
@@ -1040,7 +1042,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		{
 			// the group's driver (its rarest keyword) is walked block by block from the compressed doclist: fine unless it is dense
 			const TermInfo_t * pDrv = m_dPlans[i].m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
-			bDnf = !pDrv || (int64_t)pDrv->m_iDocs*8<(int64_t)uRows;
+			bDnf = !pDrv || (int64_t)pDrv->m_iDocs*iDnfDiv<(int64_t)uRows*iDnfMul;
 		}
 		if ( !bDnf )
 			q.m_nGroups = 0;
