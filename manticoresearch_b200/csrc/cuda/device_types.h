@@ -220,6 +220,7 @@ struct EvalParams_t
 	PreEntry_t *			m_pPre;			///< [gridDim.x][PRE_BLOCKS*32] tile predecode scratch
 	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]
 	DevHotStore_t			m_tHot;
+	const int32_t *			m_pItemOrder;	///< stream_kernel: the k-th item taken from the queue is item m_pItemOrder[k] (null = k)
 };
 
 struct HotDecodeParams_t

@@ -183,7 +183,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 	{
 		__syncthreads();
 		if ( tid==0 )
-			S.m_iItem = atomicAdd ( P.m_pCounter, 1 );
+		{
+			const int k = atomicAdd ( P.m_pCounter, 1 );
+			S.m_iItem = ( k<P.m_nItems && P.m_pItemOrder ) ? __ldg ( P.m_pItemOrder+k ) : k;
+		}
 		__syncthreads();
 		const int iItem = S.m_iItem;
 		if ( iItem>=P.m_nItems )

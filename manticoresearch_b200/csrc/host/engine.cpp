@@ -84,8 +84,25 @@ void * Index_c::Pinned ( size_t nBytes )
 	return m_pPinned;
 }
 
+void * Index_c::PinnedUpload ( size_t nBytes )
+{
+	if ( nBytes>m_nPinnedUp )
+	{
+		if ( m_pPinnedUp )
+			cudaFreeHost ( m_pPinnedUp );
+		m_pPinnedUp = nullptr;
+		m_nPinnedUp = 0;
+		if ( cudaHostAlloc ( &m_pPinnedUp, nBytes+nBytes/4, cudaHostAllocDefault )!=cudaSuccess )
+			return nullptr;
+		m_nPinnedUp = nBytes+nBytes/4;
+	}
+	return m_pPinnedUp;
+}
+
 Index_c::~Index_c()
 {
+	if ( m_pPinnedUp )
+		cudaFreeHost ( m_pPinnedUp );
 	if ( m_pPinned )
 		cudaFreeHost ( m_pPinned );
 	if ( m_tOwnStream )
@@ -951,6 +968,16 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 	}
 	const auto tPlanned = std::chrono::steady_clock::now();
+	const bool bTiming = getenv ( "MGPU_TIMING" )!=nullptr;
+	auto tMark = tPlanned;
+	auto fnMark = [&] ( const char * sWhat )
+	{
+		if ( !bTiming )
+			return;
+		const auto tNow = std::chrono::steady_clock::now();
+		fprintf ( stderr, "[mgpu setup] %-24s %7.2f ms\n", sWhat, std::chrono::duration<float,std::milli> ( tNow-tMark ).count() );
+		tMark = tNow;
+	};
 	m_tStats.host_plan_ms = std::chrono::duration<float,std::milli> ( tPlanned-tStart ).count();
 
 	// runnable queries; three launch classes (see engine.h)
@@ -969,6 +996,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	if ( dDocOnly.empty() && dOrder[1].empty() && dOrder[4].empty() )
 		return MGPU_OK;
 
+	m_dSlots.reserve ( nQueries );
+	m_dDevToQuery.reserve ( nQueries );
+	m_dItems.reserve ( (size_t)nQueries*4 );
 	const uint32_t uRows = pIndex->m_tDev.m_uRows;
 	const int nTiles = (int)( ( (uint64_t)uRows+TILE_W-1 )/TILE_W );
 	int iMaxKeysPerQuery = 1;
@@ -1029,7 +1059,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			}
 	}
 
+	fnMark ( "hot keywords" );
 	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
+	const int64_t OR_RANGE_TILES = getenv ( "MGPU_OR_RANGE_TILES" ) ? std::max ( 1, atoi ( getenv ( "MGPU_OR_RANGE_TILES" ) ) ) : 1024;	// 1024 x 2048 = 2M rows per item of class 5 (per-item costs outweigh finer ranges: 262144 rows was 25 % slower)
 	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
 	// a group's driver may sit in at most iDnfMul/iDnfDiv of the rows (MGPU_DNF_PCT: percent, for experiments)
 	const int64_t iDnfDiv = 100, iDnfMul = getenv ( "MGPU_DNF_PCT" ) ? std::max ( 1, atoi ( getenv ( "MGPU_DNF_PCT" ) ) ) : 12;
@@ -1103,6 +1135,12 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				}
 				nUnits = std::max<int64_t> ( nUnits, p.m_tDev.m_nGroups );
 			}
+			if ( c==5 )
+			{
+				// fixed rowid ranges (OR_RANGE_TILES tiles) for every query of the class: the kernel takes the items range by range, so
+				// concurrent CTAs read the same rows of the dense store (L2 hits) and later ranges inherit the query's K-th-best bound
+				nParts = std::max<int64_t> ( 1, std::min<int64_t> ( { ( nTiles+OR_RANGE_TILES-1 )/OR_RANGE_TILES, (int64_t)iCap, nUnits } ) );
+			} else
 			nParts = std::max<int64_t> ( ( c==2 || c==4 ) ? p.m_tDev.m_nGroups : 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, std::max ( iCap, ( c==2 || c==4 ) ? p.m_tDev.m_nGroups : 1 ) } ) ) );
 			dParts.push_back ( { i, (int)nParts, iWork/nParts } );
 		}
@@ -1110,10 +1148,10 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 
 		for ( const Part_t & t : dParts )
 		{
-			DevQuery_t q = m_dPlans[t.m_iQuery].m_tDev;
-			q.m_iFirstItem = (int)m_dItems.size();
-			q.m_nItems = t.m_nParts;
-			const int iDevQuery = (int)m_dDevQueries.size();
+			// (the 3 KB device query itself is copied once, in parallel, straight into the pinned upload buffer below)
+			const DevQuery_t & q = m_dPlans[t.m_iQuery].m_tDev;
+			DevSlot_t tSlot { t.m_iQuery, (int)m_dItems.size(), t.m_nParts };
+			const int iDevQuery = (int)m_dSlots.size();
 			int64_t nUnits = nTiles, iUnit = TILE_W, iLimit = uRows;
 			if ( c==2 || c==4 )
 			{
@@ -1143,9 +1181,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 						++nMade;
 					}
 				}
-				q.m_nItems = nMade;
+				tSlot.m_nItems = nMade;
 				iMaxKeysPerQuery = std::max ( iMaxKeysPerQuery, nMade*q.m_iMaxMatches );
-				m_dDevQueries.push_back ( q );
+				m_dSlots.push_back ( tSlot );
 				m_dDevToQuery.push_back ( t.m_iQuery );
 				continue;
 			}
@@ -1160,14 +1198,24 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				m_dItems.push_back ( tItem );
 			}
 			iMaxKeysPerQuery = std::max ( iMaxKeysPerQuery, t.m_nParts*q.m_iMaxMatches );
-			m_dDevQueries.push_back ( q );
+			m_dSlots.push_back ( tSlot );
 			m_dDevToQuery.push_back ( t.m_iQuery );
 		}
 		m_dCtas[c] = std::min ( nMaxCtas, (int)m_dItems.size()-m_dFirstItem[c] );
+		if ( c==5 )
+		{
+			const int iFirst = m_dFirstItem[c], n = (int)m_dItems.size()-iFirst;
+			m_dItemOrder.resize ( n );
+			for ( int i=0; i<n; ++i )
+				m_dItemOrder[i] = i;
+			std::stable_sort ( m_dItemOrder.begin(), m_dItemOrder.end(), [&] ( int a, int b ) { return m_dItems[iFirst+a].m_uRowLo<m_dItems[iFirst+b].m_uRowLo; } );
+		}
 	}
 	m_dFirstItem[NUM_CLASSES] = (int)m_dItems.size();
+	fnMark ( "classes + items" );
 
-	const int nDevQ = (int)m_dDevQueries.size();
+	const int nDevQ = (int)m_dSlots.size();
+	m_nDevQueries = nDevQ;
 	const int nItems = (int)m_dItems.size();
 	cudaStream_t tAllocStream = pIndex->m_tStream;
 	m_iPoolCap = m_iKMax + 32768;	// >= K + what one round of any kernel can push (stream: 8 mini-tiles x 8 warps x 512 rows)
@@ -1176,6 +1224,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( m_dQ.AllocAsync ( nDevQ, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dI.AllocAsync ( nItems, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dCounter.AllocAsync ( NUM_CLASSES, tAllocStream ), m_sError );
+	if ( !m_dItemOrder.empty() )
+		CUDA_TRY ( m_dOrder.AllocAsync ( m_dItemOrder.size(), tAllocStream ), m_sError );
 	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
 	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4], m_dCtas[5] } )*2*m_iPoolCap;
 	m_nHitpos = std::max ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W, (size_t)m_dCtas[4]*EVAL_WARPS*MAX_LEAVES*32 );
@@ -1197,11 +1247,45 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( cudaMemsetAsync ( m_dOutCount.m_p, 0, (size_t)nQueries*4, tAllocStream ), m_sError );
 	CUDA_TRY ( cudaMemsetAsync ( m_dOutTotal.m_p, 0, (size_t)nQueries*8, tAllocStream ), m_sError );
 
+	fnMark ( "device allocations" );
 	cudaStream_t s = pIndex->m_tStream;
-	CUDA_TRY ( cudaMemcpyAsync ( m_dQ.m_p, m_dDevQueries.data(), (size_t)nDevQ*sizeof(DevQuery_t), cudaMemcpyHostToDevice, s ), m_sError );
+	{
+		// device queries: gathered by a few threads into the index's pinned upload buffer (grow-only, free again once this call's
+		// copy has completed below), then one DMA
+		DevQuery_t * pStage = (DevQuery_t *)pIndex->PinnedUpload ( (size_t)nDevQ*sizeof(DevQuery_t) );
+		if ( !pStage )
+		{
+			m_sError = "cudaHostAlloc failed";
+			return MGPU_E_NOMEM;
+		}
+		auto fnFill = [&] ( int iFrom, int iTo )
+		{
+			for ( int i=iFrom; i<iTo; ++i )
+			{
+				memcpy ( pStage+i, &m_dPlans[m_dSlots[i].m_iQuery].m_tDev, sizeof(DevQuery_t) );
+				pStage[i].m_iFirstItem = m_dSlots[i].m_iFirstItem;
+				pStage[i].m_nItems = m_dSlots[i].m_nItems;
+			}
+		};
+		const int nThreads = std::max ( 1, std::min ( { (int)std::thread::hardware_concurrency(), 8, nDevQ/256 } ) );
+		if ( nThreads<=1 )
+			fnFill ( 0, nDevQ );
+		else
+		{
+			std::vector<std::thread> dThreads;
+			for ( int t=0; t<nThreads; ++t )
+				dThreads.emplace_back ( fnFill, (int)( (int64_t)nDevQ*t/nThreads ), (int)( (int64_t)nDevQ*( t+1 )/nThreads ) );
+			for ( auto & t : dThreads )
+				t.join();
+		}
+		CUDA_TRY ( cudaMemcpyAsync ( m_dQ.m_p, pStage, (size_t)nDevQ*sizeof(DevQuery_t), cudaMemcpyHostToDevice, s ), m_sError );
+	}
 	CUDA_TRY ( cudaMemcpyAsync ( m_dI.m_p, m_dItems.data(), (size_t)nItems*sizeof(DevWorkItem_t), cudaMemcpyHostToDevice, s ), m_sError );
 	CUDA_TRY ( cudaMemcpyAsync ( m_dOutSlot.m_p, m_dDevToQuery.data(), (size_t)nDevQ*4, cudaMemcpyHostToDevice, s ), m_sError );
+	if ( !m_dItemOrder.empty() )
+		CUDA_TRY ( cudaMemcpyAsync ( m_dOrder.m_p, m_dItemOrder.data(), m_dItemOrder.size()*4, cudaMemcpyHostToDevice, s ), m_sError );
 	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
+	fnMark ( "upload + sync" );
 	m_tStats.h2d_bytes = (int64_t)nDevQ*sizeof(DevQuery_t) + (int64_t)nItems*sizeof(DevWorkItem_t);
 	m_tStats.work_items = nItems;
 
@@ -1218,20 +1302,21 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		for ( int i : dOrder[c] )
 			m_tStats.class_bytes[c] += m_dPlans[i].m_iAlgBytes;
 	}
+	fnMark ( "events + stats" );
 	m_tStats.host_setup_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tPlanned ).count();
 	return MGPU_OK;
 }
 
 int Batch_c::Run()
 {
-	if ( m_dDevQueries.empty() )
+	if ( !m_nDevQueries )
 		return MGPU_OK;
 	Index_c * pIndex = m_pIndex;
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	cudaStream_t s = pIndex->m_tStream;
 
 	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
-	CUDA_TRY ( cudaMemsetAsync ( m_dQueryThr.m_p, 0, m_dDevQueries.size()*sizeof(unsigned long long), s ), m_sError );
+	CUDA_TRY ( cudaMemsetAsync ( m_dQueryThr.m_p, 0, (size_t)m_nDevQueries*sizeof(unsigned long long), s ), m_sError );
 
 	// run-time scratch comes from the index (grow-only, shared by all batches; runs are serialised on the index stream)
 	Index_c::RunScratch_t & tScr = pIndex->m_tScratch;
@@ -1296,6 +1381,7 @@ int Batch_c::Run()
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
 		P.m_pQueryThr = m_dQueryThr.m_p;
 		P.m_pOrList = c==5 ? tScr.m_dOrList.m_p : nullptr;
+		P.m_pItemOrder = ( c==5 && !m_dItemOrder.empty() ) ? m_dOrder.m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;
@@ -1314,7 +1400,7 @@ int Batch_c::Run()
 	MergeParams_t M {};
 	M.m_tIndex = pIndex->m_tDev;
 	M.m_pQueries = m_dQ.m_p;
-	M.m_nQueries = (int)m_dDevQueries.size();
+	M.m_nQueries = m_nDevQueries;
 	M.m_iKMax = m_iKMax;
 	M.m_pItemKeys = m_dItemKeys.m_p;
 	M.m_pItemOut = m_dItemOut.m_p;
@@ -1338,7 +1424,7 @@ int Batch_c::Sync()
 		return MGPU_OK;
 	CUDA_TRY ( cudaSetDevice ( m_pIndex->m_iDevice ), m_sError );
 	CUDA_TRY ( cudaStreamSynchronize ( m_pIndex->m_tStream ), m_sError );
-	if ( m_bRan && !m_dDevQueries.empty() )
+	if ( m_bRan && m_nDevQueries )
 	{
 		cudaEventElapsedTime ( &m_tStats.eval_kernel_ms, m_tEv0, m_tEv1 );
 		cudaEventElapsedTime ( &m_tStats.hot_decode_ms, m_tEvHot, m_tEv0 );
@@ -1377,7 +1463,7 @@ int Batch_c::Fetch ( mgpu_result * pResults )
 			for ( size_t w=0; w<m_dPlans[i].m_dWordStats.size(); ++w )
 				r.word_stats[w] = m_dPlans[i].m_dWordStats[w];
 	}
-	if ( m_dDevQueries.empty() )
+	if ( !m_nDevQueries )
 		return MGPU_OK;
 	const auto tWait = std::chrono::steady_clock::now();
 	int iRes = Sync();
@@ -1452,7 +1538,7 @@ int Batch_c::ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, 
 	const int nQueries = (int)m_dPlans.size();
 	CUDA_TRY ( cudaSetDevice ( m_pIndex->m_iDevice ), m_sError );
 	cudaStream_t s = m_pIndex->m_tStream;
-	if ( m_dDevQueries.empty() )
+	if ( !m_nDevQueries )
 	{
 		CUDA_TRY ( cudaMemsetAsync ( pDevCounts, 0, (size_t)nQueries*4, s ), m_sError );
 		CUDA_TRY ( cudaMemsetAsync ( pDevTotal, 0, (size_t)nQueries*8, s ), m_sError );

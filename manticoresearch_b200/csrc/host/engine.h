@@ -107,6 +107,10 @@ public:
 	void *	m_pPinned = nullptr;
 	size_t	m_nPinned = 0;
 	void *	Pinned ( size_t nBytes );
+	/// pinned host staging for the per-batch plan upload (grow-only; used under m_tLock, free again when Prepare returns)
+	void *	m_pPinnedUp = nullptr;
+	size_t	m_nPinnedUp = 0;
+	void *	PinnedUpload ( size_t nBytes );
 
 	DevBuf_T<uint8_t>	m_dSpd, m_dSpp;
 	DevBuf_T<uint32_t>	m_dSpa, m_dDead;
@@ -149,7 +153,9 @@ public:
 	Index_c *		m_pIndex = nullptr;
 	std::string		m_sError;
 	std::vector<PlannedQuery_t> m_dPlans;
-	std::vector<DevQuery_t>		m_dDevQueries;	///< only the runnable ones, in order
+	struct DevSlot_t { int m_iQuery, m_iFirstItem, m_nItems; };
+	std::vector<DevSlot_t>		m_dSlots;		///< device queries = only the runnable ones, in launch order: batch query + its work items
+	int							m_nDevQueries = 0;
 	std::vector<int>			m_dDevToQuery;	///< device query -> batch query index
 	std::vector<DevWorkItem_t>	m_dItems;
 	/// launch classes: [0] doc-only queries with a single-level program (stream_kernel<512>), [1] hit-consuming queries on dense
@@ -167,6 +173,8 @@ public:
 	DevBuf_T<DevQuery_t>	m_dQ;
 	DevBuf_T<DevWorkItem_t>	m_dI;
 	DevBuf_T<int32_t>		m_dCounter;
+	std::vector<int32_t>	m_dItemOrder;	///< class 5: items in rowid-range-major order (index relative to the class's first item)
+	DevBuf_T<int32_t>		m_dOrder;
 	DevBuf_T<unsigned long long> m_dQueryThr;	///< per device query: shared K-th-best bound of its items
 	DevBuf_T<Key128_t>		m_dItemKeys, m_dScratch, m_dOutKeys;
 	size_t	m_nPool = 0, m_nHitpos = 0, m_nPre = 0, m_nPreHitpos = 0;	///< what Run() needs from the index's RunScratch_t
