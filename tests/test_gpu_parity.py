@@ -103,6 +103,47 @@ def test_or_queries_small_k_and_odd_weights(synth):
     assert _compare_batch(synth, qs + qs[:40]) == 0
 
 
+def test_or_class_bound_pass_edges(synth):
+    """stream_kernel<512,ORONLY> (launch class 5): the integer weight bound must never drop a row the exact ranking would keep.
+    Edges: stop-word-only queries (negative idf everywhere, weights tie massively), keywords limited to one field, K from 1 to
+    3000, index weights up to the bound's validity limit and beyond it (bound switched off), field weights 0 / 250 / 251,
+    overridden collection statistics (global IDF inputs of the sharded path: idf signs flip), duplicated keywords"""
+    import random
+    rng = random.Random(4242)
+    title, body = 1, 2
+    qs = []
+    for i in range(220):
+        shape = i % 5
+        if shape == 0:      # stop words only: every idf <= 0
+            ranks = rng.sample(range(1, 8), rng.randint(2, 4))
+        elif shape == 1:    # hot + sparse + very rare
+            ranks = rng.sample(range(1, 60), 2) + [int(10 ** rng.uniform(2.5, 5.2)) for _ in range(rng.randint(1, 3))]
+        elif shape == 2:    # hot only, mid density
+            ranks = rng.sample(range(5, 400), rng.randint(2, 6))
+        elif shape == 3:    # a keyword twice (same qpos semantics as two leaves)
+            r = rng.randint(2, 200)
+            ranks = [r, rng.randint(2, 3000), r]
+        else:
+            ranks = rng.sample(range(1, 2000), rng.randint(2, 8))
+        leaves = []
+        for p, r in enumerate(ranks):
+            n = M.kw(M.synth_keyword(r - 1), p + 1)
+            if rng.random() < 0.3:
+                n.fields(rng.choice([title, body]))
+            leaves.append(n)
+        kwargs = {}
+        if i % 7 == 3:      # what apply_global_idf would pass on a shard: other totals, other doc counts
+            kwargs = dict(total_docs=rng.choice([N_DOCS // 3, N_DOCS * 5]),
+                          word_docs=[max(1, int(N_DOCS * rng.uniform(0.0001, 0.9))) for _ in ranks])
+        qs.append(M.Query(M.OR(*leaves), ranker=M.RANK_BM25, field_weights=rng.choice([[10, 1], [1, 1], [0, 5], [250, 1], [251, 7], None]),
+                          max_matches=rng.choice([1, 2, 10, 100, 3000]), index_weight=rng.choice([1, 1, 1, 7, 1024, 1025]), **kwargs))
+    batch = synth["gpu"].prepare(qs + qs[:60])      # repeated keywords -> hot store
+    st = batch.stats()
+    batch.free()
+    assert st["class_queries"][5] >= 200, st["class_queries"]
+    assert _compare_batch(synth, qs + qs[:60]) == 0
+
+
 def test_cfg4_mix_with_andnot(synth):
     queries = workload.cfg2_queries(n=200, seed=77, max_rank=50000, max_matches=1000, with_andnot=0.2)
     _compare_batch(synth, queries)
