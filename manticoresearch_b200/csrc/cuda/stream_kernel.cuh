@@ -308,17 +308,24 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 		uint32_t uNextSparse = 0;
 		const int nOps = q.m_nOps, nHotOps = S.m_nHotOps, nPosOps = S.m_nPosOps, nNegOps = S.m_nNegOps, nSparseOps = S.m_nSparseOps;
 		const int iIndexWeight = q.m_iIndexWeight;
+		const bool bAttr = q.m_nFilters || q.m_nSortKeys;	// filters and / or attribute sort keys: rows are filtered in the bound pass, keys compared whole
 
 		// ranks one evaluated row and pushes it if it beats the K-th best key so far (one row per lane)
-		auto fnRankPush = [&] ( bool bRow, float fT, uint32_t uF, uint32_t uRow, Key128_t * pPool, uint32_t uThrWx, uint32_t uThrRow )
+		auto fnRankPush = [&] ( bool bRow, float fT, uint32_t uF, uint32_t uRow, Key128_t * pPool, const Key128_t & tThr )
 		{
 			// seed weight src/sphinxsearch.cpp:1070, ExtRanker_WeightSum_c :1112-1129
 			const int iSeed = __float2int_rz ( __fmul_rn ( __fadd_rn ( fT, 0.5f ), 1000.0f ) );
 			const uint32_t uRank = uF ? S.m_dRankTab[uF & 15u] : 1u;
 			const uint32_t uW = ( (uint32_t)iSeed + uRank*1000u )*(uint32_t)iIndexWeight;
-			const uint32_t uWx = uW ^ 0x80000000u;
-			const uint32_t uGlobal = uRow+tIdx.m_uRowidBase;
-			const bool bPush = bRow && ( uWx>uThrWx || ( uWx==uThrWx && uGlobal<=uThrRow ) );
+			Key128_t tKey;
+			if ( bAttr )
+				tKey = MakeKey ( tIdx, q, bRow ? uRow : 0u, (int)uW );	// (filters were applied before the row was queued)
+			else
+			{
+				tKey.m_uHi = (uint64_t)( uW ^ 0x80000000u )<<32;
+				tKey.m_uLo = ( (uint64_t)( ~( uRow+tIdx.m_uRowidBase ) )<<32 ) | uW;
+			}
+			const bool bPush = bRow && !KeyLess ( tKey, tThr );
 			const unsigned m = __ballot_sync ( FULL_MASK, bPush );
 			if ( m )
 			{
@@ -327,16 +334,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 					iSlot = atomicAdd ( &S.m_iPoolCnt, __popc ( m ) );
 				iSlot = __shfl_sync ( FULL_MASK, iSlot, 0 );
 				if ( bPush )
-				{
-					Key128_t tKey;
-					tKey.m_uHi = (uint64_t)uWx<<32;
-					tKey.m_uLo = ( (uint64_t)( ~uGlobal )<<32 ) | uW;
 					pPool[iSlot + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
-				}
 			}
 		};
 		// exact TF*IDF of one queued row per lane from the hot keywords alone (the row holds no sparse posting), in op order
-		auto fnExactHot = [&] ( bool bAct, uint32_t uRow, Key128_t * pPool, uint32_t uThrWx, uint32_t uThrRow )
+		auto fnExactHot = [&] ( bool bAct, uint32_t uRow, Key128_t * pPool, const Key128_t & tThr )
 		{
 			float fT = 0.0f;
 			uint32_t uF = 0;
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 					bPres = true;
 				}
 			}
-			fnRankPush ( bAct && bPres, fT, uF, uRow, pPool, uThrWx, uThrRow );
+			fnRankPush ( bAct && bPres, fT, uF, uRow, pPool, tThr );
 		};
 
 		// Register-OR class: no fixed rounds. A fresh K-th-best bound is what keeps rows out of the exact pass, so the pool is compacted
@@ -414,13 +416,16 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 			Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 			uint32_t uThrWx, uThrRow;
 			int iThrFx, iThrFxTie;
+			Key128_t tThrCur;	// the warp's current bound of the K-th best key (attribute-sorted queries compare whole keys)
 			auto fnSetThr = [&] ( uint64_t uHiWord, uint64_t uLoWord )
 			{
+				tThrCur.m_uHi = uHiWord;
+				tThrCur.m_uLo = uLoWord;
 				uThrWx = (uint32_t)( uHiWord>>32 );
 				uThrRow = ~(uint32_t)( uLoWord>>32 );
 				// threshold of the bound pass in its own fixed point: ( bound>>6 )*index weight >= K-th best weight
 				iThrFx = iThrFxTie = -( 1<<29 );	// no threshold yet / no usable bound: every present row is a candidate
-				if ( bRegOr && S.m_bBound && uThrWx )
+				if ( bRegOr && S.m_bBound && uThrWx && !q.m_nSortKeys )	// (attribute sort: the weight is no part of the key)
 				{
 					const int iW = q.m_iIndexWeight;
 					const long long iThr = (long long)(int)( uThrWx ^ 0x80000000u );
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 					{
 						// another item of this query may have raised the shared lower bound of the K-th best key meanwhile
 						const unsigned long long uShared = *( (volatile unsigned long long *)( P.m_pQueryThr+tItem.m_uQuery ) );
-						if ( uShared>( (unsigned long long)uThrWx<<32 ) )
+						if ( uShared>tThrCur.m_uHi )
 							fnSetThr ( uShared, 0 );
 					}
 				}
@@ -646,6 +651,28 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 								uCand |= 2u<<( 2*j );
 							uPresent |= ( ( ( dF[j] & 0x0F000F00u )+0x0F000F00u ) & 0x10001000u )>>j;
 						}
+						if ( bAttr )
+						{
+							// filters (EarlyReject, src/sphinx.cpp:11903) run on every present row: total_found counts what passes them.
+							// With attribute sort keys the key does not depend on the weight: compare it whole, rank only what may enter.
+							uint32_t uRows = 0;
+							#pragma unroll
+							for ( int k=0; k<CHUNK_K; ++k )
+								if ( ( dF[k>>1]>>( ( k & 1 ) ? 24 : 8 ) ) & 0xFu )
+									uRows |= 1u<<k;
+							uint32_t uKeep = 0, uPass = 0;
+							for ( uint32_t m=uRows; m; m&=m-1 )
+							{
+								const int k = __ffs ( m )-1;
+								if ( !PassFilters ( tIdx, q, uRowC+k ) )
+									continue;
+								uKeep |= 1u<<k;
+								if ( q.m_nSortKeys ? !KeyLess ( MakeKey ( tIdx, q, uRowC+k, 0x7FFFFFFF ), tThrCur ) : ( ( uCand>>k ) & 1u )!=0 )
+									uPass |= 1u<<k;
+							}
+							uPresent = uKeep;
+							uCand = uPass;
+						}
 						iMyTotal += __popc ( uPresent );
 						if ( !__any_sync ( FULL_MASK, uCand!=0 ) )
 							continue;
@@ -672,7 +699,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 								while ( nQueue>=32 )
 								{
 									nQueue -= 32;
-									fnExactHot ( true, pQueue[nQueue+iLane], pPool, uThrWx, uThrRow );
+									fnExactHot ( true, pQueue[nQueue+iLane], pPool, tThrCur );
 								}
 								__syncwarp();
 							}
@@ -738,7 +765,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 									++iSp;
 								}
 							}
-							fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, uThrWx, uThrRow );
+							fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, tThrCur );
 						}
 						__syncwarp();
 					}
@@ -1018,7 +1045,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 			// register-OR path: the queued candidate rows are evaluated against this round's threshold and pool buffer
 			if ( nQueue )
 			{
-				fnExactHot ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, uThrWx, uThrRow );
+				fnExactHot ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, tThrCur );
 				nQueue = 0;
 				__syncwarp();
 			}

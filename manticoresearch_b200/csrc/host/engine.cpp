@@ -1078,8 +1078,12 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 		if ( !bDnf )
 			q.m_nGroups = 0;
-		// pure OR programs under BM25 relevance, no filters / sort keys / dead rows, <= 4 fields: the bound + exact pass kernel
-		const bool bOrClass = !bDnf && q.m_bPureOr && q.m_eRanker==1 && !q.m_nFilters && !q.m_nSortKeys && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead;
+		// pure OR programs under BM25, no dead rows, <= 4 fields, ordered by relevance or by attributes alone (a sort key on the
+		// weight would need the bound inside the key): the bound + exact pass kernel; filters run inside its bound pass
+		bool bWeightKey = false;
+		for ( int k=0; k<q.m_nSortKeys; ++k )
+			bWeightKey |= q.m_dSortKeys[k].m_eKind==1;
+		const bool bOrClass = !bDnf && q.m_bPureOr && q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !getenv ( "MGPU_NO_ORCLASS" );
 		dOrder [ bDnf ? 2 : bOrClass ? 5 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
 	}
 

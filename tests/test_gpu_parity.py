@@ -107,7 +107,8 @@ def test_or_class_bound_pass_edges(synth):
     """stream_kernel<512,ORONLY> (launch class 5): the integer weight bound must never drop a row the exact ranking would keep.
     Edges: stop-word-only queries (negative idf everywhere, weights tie massively), keywords limited to one field, K from 1 to
     3000, index weights up to the bound's validity limit and beyond it (bound switched off), field weights 0 / 250 / 251,
-    overridden collection statistics (global IDF inputs of the sharded path: idf signs flip), duplicated keywords"""
+    overridden collection statistics (global IDF inputs of the sharded path: idf signs flip), duplicated keywords, range / values /
+    exclude filters and attribute or rowid sort keys"""
     import random
     rng = random.Random(4242)
     title, body = 1, 2
@@ -135,6 +136,12 @@ def test_or_class_bound_pass_edges(synth):
         if i % 7 == 3:      # what apply_global_idf would pass on a shard: other totals, other doc counts
             kwargs = dict(total_docs=rng.choice([N_DOCS // 3, N_DOCS * 5]),
                           word_docs=[max(1, int(N_DOCS * rng.uniform(0.0001, 0.9))) for _ in ranks])
+        if i % 4 == 1:      # filters inside the bound pass; attribute / rowid sort keys (whole-key compare, weight only for the result)
+            gid, ts = synth["gpu"].attr_index("gid"), synth["gpu"].attr_index("ts")
+            kwargs["filters"] = rng.choice([[M.Filter(gid, 100, 299)], [M.Filter(gid, values=[5, 17, 900, 901])],
+                                            [M.Filter(gid, 0, 499, exclude=True), M.Filter(ts, 0, 1 << 30)], []])
+            kwargs["sort_keys"] = rng.choice([[], [M.SortKey(M.KEYPART_INT, ts, True)], [M.SortKey(M.KEYPART_INT, gid, False), M.SortKey(M.KEYPART_INT, ts, True)],
+                                              [M.SortKey(M.KEYPART_ROWID, 0, True)]])
         qs.append(M.Query(M.OR(*leaves), ranker=M.RANK_BM25, field_weights=rng.choice([[10, 1], [1, 1], [0, 5], [250, 1], [251, 7], None]),
                           max_matches=rng.choice([1, 2, 10, 100, 3000]), index_weight=rng.choice([1, 1, 1, 7, 1024, 1025]), **kwargs))
     batch = synth["gpu"].prepare(qs + qs[:60])      # repeated keywords -> hot store
