@@ -373,7 +373,7 @@ def run_ours(args):
         eval_avg_ms = statistics.mean(eval_ms)
         # roofline of the DOMINANT kernel: the launch class with the largest share of the step; its own algorithmic bytes
         # (.spd + .spe extents of every keyword of its queries) over its own CUDA-event duration
-        names = ["stream_kernel<512>", "eval_kernel<hits>", "and_kernel", "stream_kernel<256>", "and_kernel<hits>", "stream_kernel<512,or>"]
+        names = ["stream_kernel<512>", "eval_kernel<hits>", "and_kernel", "stream_kernel<256>", "and_kernel<hits>", "stream_kernel<512,or>", "stream_kernel<512,dnf>"]
         NC = len(names)
         cms = [statistics.mean(x[c] for x in class_ms) for c in range(NC)]
         dom = max(range(NC), key=lambda c: cms[c])

@@ -220,10 +220,11 @@ typedef struct mgpu_batch_stats {
 	/* per launch class: [0] stream_kernel<512> (doc-only queries, single-level programs), [1] eval_kernel<hits> (hit-consuming
 	 * queries on dense tiles), [2] and_kernel (doc-only DNF / pure AND queries), [3] stream_kernel<256> (deeper programs),
 	 * [4] and_kernel<hits> (hit-consuming pure AND chains: PROXIMITY_BM25 over AND, phrase, proximity),
-	 * [5] stream_kernel<512,or> (pure OR programs under BM25 relevance without filters: bound pass + exact pass) */
-	float			class_ms[6];
-	int32_t			class_queries[6];
-	int64_t			class_bytes[6];      /* algorithmic bytes of the class's queries */
+	 * [5] stream_kernel<512,or> (pure OR programs under BM25: bound pass + exact pass),
+	 * [6] stream_kernel<512,dnf> (OR-of-AND-groups programs whose multi-keyword groups are all hot: the same passes) */
+	float			class_ms[7];
+	int32_t			class_queries[7];
+	int64_t			class_bytes[7];      /* algorithmic bytes of the class's queries */
 	/* host wall-clock of the batch: query planning, buffer setup + plan upload, result download + unpack */
 	float			host_plan_ms, host_setup_ms, host_fetch_ms;
 	float			host_wait_ms;        /* part of host_fetch_ms spent waiting for the kernels */

@@ -1674,9 +1674,9 @@ static int StreamMiniWidth ( int nStack )
 /// the register-OR class needs per warp: sparse overlay 512*4 + candidate rows 256 + queue (32+256)*4
 static const size_t OR_WARP_SMEM = 512*4 + 256 + 288*4;
 
-size_t StreamDynSmemBytes ( int nStack, bool bOrOnly )
+size_t StreamDynSmemBytes ( int nStack, int iMode )
 {
-	if ( bOrOnly )
+	if ( iMode )
 		return (size_t)EVAL_WARPS*512*9;	// (the kernel strides its warps by nStack*MINI_W*9 = 4608 >= OR_WARP_SMEM)
 	return (size_t)nStack*EVAL_WARPS*StreamMiniWidth ( nStack )*9;
 }
@@ -1691,15 +1691,18 @@ static cudaError_t LaunchStreamT ( KERNEL fnKernel, const EvalParams_t & P, int 
 	return cudaGetLastError();
 }
 
-cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, bool bOrOnly, int nCtas, cudaStream_t tStream )
+/// iMode: 0 = general tile program, 1 = pure OR programs, 2 = DNF programs with hot multi-keyword groups (bound + exact pass)
+cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, int iMode, int nCtas, cudaStream_t tStream )
 {
 	static_assert ( OR_WARP_SMEM<=512*9, "register-OR scratch must fit the warp's slice" );
-	const size_t iDyn = StreamDynSmemBytes ( nStack, bOrOnly );
-	if ( bOrOnly )
-		return LaunchStreamT ( stream_kernel<512,true>, P, 1, iDyn, nCtas, tStream );
+	const size_t iDyn = StreamDynSmemBytes ( nStack, iMode );
+	if ( iMode==1 )
+		return LaunchStreamT ( stream_kernel<512,1>, P, 1, iDyn, nCtas, tStream );
+	if ( iMode==2 )
+		return LaunchStreamT ( stream_kernel<512,2>, P, 1, iDyn, nCtas, tStream );
 	if ( StreamMiniWidth ( nStack )==512 )
-		return LaunchStreamT ( stream_kernel<512,false>, P, nStack, iDyn, nCtas, tStream );
-	return LaunchStreamT ( stream_kernel<256,false>, P, nStack, iDyn, nCtas, tStream );
+		return LaunchStreamT ( stream_kernel<512,0>, P, nStack, iDyn, nCtas, tStream );
+	return LaunchStreamT ( stream_kernel<256,0>, P, nStack, iDyn, nCtas, tStream );
 }
 
 template<typename KERNEL>
@@ -1712,14 +1715,16 @@ static int StreamOccupancyT ( KERNEL fnKernel, size_t iDyn )
 	return n>0 ? n : 1;
 }
 
-int StreamOccupancy ( int nStack, bool bOrOnly )
+int StreamOccupancy ( int nStack, int iMode )
 {
-	const size_t iDyn = StreamDynSmemBytes ( nStack, bOrOnly );
-	if ( bOrOnly )
-		return StreamOccupancyT ( stream_kernel<512,true>, iDyn );
+	const size_t iDyn = StreamDynSmemBytes ( nStack, iMode );
+	if ( iMode==1 )
+		return StreamOccupancyT ( stream_kernel<512,1>, iDyn );
+	if ( iMode==2 )
+		return StreamOccupancyT ( stream_kernel<512,2>, iDyn );
 	if ( StreamMiniWidth ( nStack )==512 )
-		return StreamOccupancyT ( stream_kernel<512,false>, iDyn );
-	return StreamOccupancyT ( stream_kernel<256,false>, iDyn );
+		return StreamOccupancyT ( stream_kernel<512,0>, iDyn );
+	return StreamOccupancyT ( stream_kernel<256,0>, iDyn );
 }
 
 cudaError_t LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream )

@@ -53,6 +53,13 @@ struct StreamShared_t
 	int32_t			m_nPosOps, m_nNegOps;
 	uint8_t			m_dSparseOp[MAX_LEAVES];			///< register-OR path: ops whose keyword is walked from the compressed doclist, in op order
 	int32_t			m_nSparseOps;
+	// DNF mode: multi-keyword AND groups (hot keywords only), entries in op order; x bit 0 = negative idf
+	uint2			m_dMultiMaskUb[MAX_LEAVES];
+	const uint16_t * m_dMultiPtr[MAX_LEAVES];
+	uint8_t			m_dMultiStart[MAX_GROUPS+1];
+	int32_t			m_dMultiNeg[MAX_GROUPS];			///< 14 * sum of the group's negative shares: owed by rows the group does not match
+	int32_t			m_nMultiGroups;
+	const uint16_t * m_dLeafPtr[MAX_LEAVES];			///< DNF mode, exact pass: the leaf's row of the dense store (null = sparse keyword)
 	int32_t			m_iNegConst;						///< 14 * sum of the negative keywords' shares: what the bound pass adds to every row on their behalf
 	int32_t			m_bBound;							///< the integer weight bound is usable (no overflow, sane idf); else every present row is evaluated exactly
 	float			m_dTf[256];
@@ -151,11 +158,15 @@ __device__ __forceinline__ void StreamDenseOp ( float * pT, uint32_t * pF, uint8
 	}
 }
 
-/// ORONLY = the class of pure OR programs under BM25 relevance with no filters (the host routes exactly those here): only the
-/// register-OR path is compiled in, so the compiler does not have to share 64 registers with the general tile program
-template<int MINI_W, bool ORONLY>
-__global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel ( EvalParams_t P, int nStack )
+/// MODE 0 = the general tile program. MODE 1 (ORONLY) = the class of pure OR programs under BM25 (the host routes exactly those
+/// here): only the bound + exact pass path is compiled in, so the compiler does not have to share 64 registers with the general tile
+/// program, relevance order, no filters. MODE 2 (DNF) = the same path with run-time options: OR-of-AND-groups programs whose
+/// multi-keyword groups consist of hot keywords only, filters inside the bound pass, attribute / rowid sort keys.
+template<int MINI_W, int MODE>
+__global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel ( EvalParams_t P, int nStack )
 {
+	constexpr bool ORONLY = MODE!=0;
+	constexpr bool DNF = MODE==2;
 	constexpr int MINI_K = MINI_W/32;							///< rows per lane
 	constexpr int SYNC_MINIS = STREAM_POOL_SLACK/( EVAL_WARPS*MINI_W );	///< mini-tiles per warp between two CTA barriers
 	extern __shared__ __align__(16) uint8_t dDyn[];
@@ -240,46 +251,73 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 			if ( !tid )
 				S.m_bBound = bOk ? 1 : 0;
 		}
-		if ( tid==32 )
+		if ( ORONLY && tid==32 )
 		{
-			// per-op constants of the register-OR path (pure OR programs: one op per keyword); hot keywords are also listed compactly
-			int nHot = 0, nPos = 0, nNeg = 0, nSparse = 0, iNegConst = 0;
-			for ( int iOp=0; iOp<MAX_LEAVES; ++iOp )
+			// Per-keyword constants of the bound pass; hot keywords are also listed compactly. MODE 1: one op per keyword (pure OR).
+			// MODE 2: the program is an OR of AND groups (q.m_dGroupOp0 / m_dGroupOps); one-keyword groups are handled exactly like the
+			// operands of a pure OR, the keywords of bigger groups (all hot: the host's test) go to the multi-group lists.
+			// The store holds c = ceil ( 15*tf ) per row (tf class). idf > 0: tf*idf <= c*idf/15, share rounded up.
+			// idf < 0: tf > (c-1)/15, so tf*idf <= -(c-1)*|idf|/15, share rounded down; the bound pass adds ( 14-(c-1) )*share
+			// per present row and 14*share per absent one, and the threshold moves up by the constant 14*share.
+			int nHot = 0, nPos = 0, nNeg = 0, nSparse = 0, iNegConst = 0, nMulti = 0, nMultiGroups = 0;
+			for ( int i=0; i<MAX_LEAVES; ++i )
 			{
-				const uint16_t * pRow = nullptr;
-				if ( q.m_bPureOr && iOp<q.m_nOps )
+				S.m_dOpPtr[i] = nullptr;
+				S.m_dLeafPtr[i] = nullptr;
+			}
+			const bool bGroups = DNF && q.m_nGroups>0;
+			const int nUnits = bGroups ? q.m_nGroups : q.m_nOps;
+			for ( int u=0; u<nUnits && u<MAX_LEAVES; ++u )
+			{
+				const int iOp0 = bGroups ? q.m_dGroupOp0[u] : u, nUnitOps = bGroups ? q.m_dGroupOps[u] : 1;
+				int iGroupNeg = 0;
+				if ( nUnitOps>1 )
+					S.m_dMultiStart[nMultiGroups] = (uint8_t)nMulti;
+				for ( int iOp=iOp0; iOp<iOp0+nUnitOps; ++iOp )
 				{
 					const int l = q.m_dOps[iOp].m_uLeaf;
 					const DevLeaf_t & tLeaf = q.m_dLeaves[l];
-					if ( tLeaf.m_iHot>=0 )
+					if ( tLeaf.m_iHot<0 )
 					{
-						// The store holds c = ceil ( 15*tf ) per row (tf class). idf > 0: tf*idf <= c*idf/15, share rounded up.
-						// idf < 0: tf > (c-1)/15, so tf*idf <= -(c-1)*|idf|/15, share rounded down; the bound pass adds ( 14-(c-1) )*share
-						// per present row and 14*share per absent one, and the threshold moves up by the constant 14*share.
-						const float fIDF = tLeaf.m_fIDF;
-						pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
-						const uint32_t m = tLeaf.m_uQueriedFields & 0xFu;	// this path runs for indexes with <= 4 fields only
-						const uint32_t uMask = ( m<<8 ) | ( m<<24 );
-						const float fShare = __fmul_rn ( fminf ( fabsf ( fIDF ), 1.0f ), 64000.0f/15.0f );
-						if ( fIDF>=0.0f )
-						{
-							S.m_dPosMaskUb[nPos] = make_uint2 ( uMask, (uint32_t)ceilf ( fShare )+1u );
-							S.m_dPosPtr[nPos++] = pRow;
-						} else
-						{
-							const uint32_t uShare = fShare>=2.0f ? (uint32_t)floorf ( fShare )-1u : 0u;
-							S.m_dNegMaskUb[nNeg] = make_uint2 ( uMask, uShare );
-							S.m_dNegPtr[nNeg++] = pRow;
-							iNegConst += 14*(int)uShare;
-						}
-						S.m_dHotPtr[nHot] = pRow;
-						S.m_dHotLeaf[nHot] = (uint8_t)l;
-						++nHot;
+						S.m_dSparseOp[nSparse++] = (uint8_t)iOp;	// (one-keyword units only)
+						continue;
+					}
+					const float fIDF = tLeaf.m_fIDF;
+					const uint16_t * pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
+					const uint32_t m = tLeaf.m_uQueriedFields & 0xFu;	// this path runs for indexes with <= 4 fields only
+					const uint32_t uMask = ( m<<8 ) | ( m<<24 );
+					const float fShare = __fmul_rn ( fminf ( fabsf ( fIDF ), 1.0f ), 64000.0f/15.0f );
+					const uint32_t uShare = fIDF>=0.0f ? (uint32_t)ceilf ( fShare )+1u : ( fShare>=2.0f ? (uint32_t)floorf ( fShare )-1u : 0u );
+					if ( fIDF<0.0f )
+					{
+						iNegConst += 14*(int)uShare;
+						iGroupNeg += 14*(int)uShare;
+					}
+					if ( nUnitOps>1 )
+					{
+						S.m_dMultiMaskUb[nMulti] = make_uint2 ( uMask | ( fIDF<0.0f ? 1u : 0u ), uShare );
+						S.m_dMultiPtr[nMulti++] = pRow;
+					} else if ( fIDF>=0.0f )
+					{
+						S.m_dPosMaskUb[nPos] = make_uint2 ( uMask, uShare );
+						S.m_dPosPtr[nPos++] = pRow;
 					} else
-						S.m_dSparseOp[nSparse++] = (uint8_t)iOp;
+					{
+						S.m_dNegMaskUb[nNeg] = make_uint2 ( uMask, uShare );
+						S.m_dNegPtr[nNeg++] = pRow;
+					}
+					S.m_dHotPtr[nHot] = pRow;
+					S.m_dHotLeaf[nHot] = (uint8_t)l;
+					++nHot;
+					S.m_dLeafPtr[l] = pRow;
+					if ( !DNF )
+						S.m_dOpPtr[iOp] = pRow;
 				}
-				S.m_dOpPtr[iOp] = pRow;
+				if ( nUnitOps>1 )
+					S.m_dMultiNeg[nMultiGroups++] = iGroupNeg;
 			}
+			S.m_dMultiStart[nMultiGroups] = (uint8_t)nMulti;
+			S.m_nMultiGroups = nMultiGroups;
 			S.m_nHotOps = nHot;
 			S.m_nSparseOps = nSparse;
 			S.m_nPosOps = nPos;
@@ -306,9 +344,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 		uint32_t * pQueue = reinterpret_cast<uint32_t *>( dDyn + (size_t)iWarp*nStack*MINI_W*9 ) + MINI_W + 64;	// [32+256], after overlay + pCand
 		int nQueue = 0;
 		uint32_t uNextSparse = 0;
-		const int nOps = q.m_nOps, nHotOps = S.m_nHotOps, nPosOps = S.m_nPosOps, nNegOps = S.m_nNegOps, nSparseOps = S.m_nSparseOps;
+		const int nOps = q.m_nOps, nHotOps = S.m_nHotOps, nPosOps = S.m_nPosOps, nNegOps = S.m_nNegOps, nSparseOps = S.m_nSparseOps, nMultiGroups = S.m_nMultiGroups;
 		const int iIndexWeight = q.m_iIndexWeight;
-		const bool bAttr = q.m_nFilters || q.m_nSortKeys;	// filters and / or attribute sort keys: rows are filtered in the bound pass, keys compared whole
+		// filters and / or attribute sort keys (MODE 2 only): rows are filtered in the bound pass, keys compared whole
+		const bool bAttr = DNF && ( q.m_nFilters || q.m_nSortKeys );
+		const bool bGroups = DNF && q.m_nGroups>0;	// units of the OR fold = AND groups (else: every op is a one-keyword unit)
 
 		// ranks one evaluated row and pushes it if it beats the K-th best key so far (one row per lane)
 		auto fnRankPush = [&] ( bool bRow, float fT, uint32_t uF, uint32_t uRow, Key128_t * pPool, const Key128_t & tThr )
@@ -366,6 +406,78 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 					// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
 					fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
 					uF |= uFields;
+					bPres = true;
+				}
+			}
+			fnRankPush ( bAct && bPres, fT, uF, uRow, pPool, tThr );
+		};
+
+		// DNF mode: exact TF*IDF of one candidate row per lane, unit by unit in program order. A group counts when all its keywords sit on
+		// the row: its sum is folded keyword by keyword (ExtAnd_c / ExtMultiAnd_T: left + right), the groups' sums are folded in group
+		// order (ExtOr_c, src/searchnode.cpp:3486-3504). sSlot = the row's slot in the current mini-tile when its sparse postings are at
+		// hand in pList (-1: the row holds none).
+		auto fnExactDnf = [&] ( bool bAct, uint32_t uRow, int sSlot, const PreEntry_t * pList, Key128_t * pPool, const Key128_t & tThr )
+		{
+			float fT = 0.0f;
+			uint32_t uF = 0;
+			bool bPres = false;
+			int iSp = 0;
+			const int nUnits = bGroups ? q.m_nGroups : nOps;
+			for ( int g=0; g<nUnits; ++g )
+			{
+				const int iOp0 = bGroups ? q.m_dGroupOp0[g] : g, nGroupOps = bGroups ? q.m_dGroupOps[g] : 1;
+				float fG = 0.0f;
+				uint32_t uFG = 0;
+				bool bAll = true, bFirst = true;
+				for ( int iOp=iOp0; iOp<iOp0+nGroupOps; ++iOp )
+				{
+					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+					const uint16_t * pRow = S.m_dLeafPtr[q.m_dOps[iOp].m_uLeaf];
+					if ( pRow )
+					{
+						const uint32_t uRaw = bAct ? __ldg ( pRow+uRow ) : 0u;
+						const uint32_t uHits = uRaw & 255u;
+						const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
+						if ( !uHits || !uFields )
+						{
+							bAll = false;
+							continue;
+						}
+						float fBase = S.m_dTf[uHits];
+						if ( bAnyEscape && uHits==255 )
+							fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
+						const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+						fG = bFirst ? fTf : __fadd_rn ( fG, fTf );
+						uFG |= uFields;
+						bFirst = false;
+					} else
+					{
+						bool bFound = false;
+						if ( sSlot>=0 )
+						{
+							const int iTo = S.m_dOpStart[iWarp][iSp+1];
+							for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
+							{
+								const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
+								if ( bAct && (int)tEntry.m_uRowid==sSlot )
+								{
+									fG = tEntry.m_fTf;
+									uFG = tEntry.m_uFields;
+									bFound = true;
+								}
+							}
+						}
+						++iSp;
+						if ( bFound )
+							bFirst = false;
+						else
+							bAll = false;
+					}
+				}
+				if ( bAll && !bFirst )
+				{
+					fT = bPres ? __fadd_rn ( fT, fG ) : fG;
+					uF |= uFG;
 					bPres = true;
 				}
 			}
@@ -618,6 +730,46 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 								dUb[j] += (uint64_t)( 0xE000E000u + uPres - uClass )*tMaskUb.y;
 							}
 						}
+						if constexpr ( DNF )
+						{
+							// multi-keyword AND groups: presence flags are ANDed over the group's keywords, the group's field masks and bound
+							// sums only count where the whole group sits on the row
+							#pragma unroll 1
+							for ( int g=0; g<nMultiGroups; ++g )
+							{
+								uint32_t dA[4] = { 0x10001000u, 0x10001000u, 0x10001000u, 0x10001000u }, dFg[4] = { 0, 0, 0, 0 };
+								uint64_t dUg[4] = { 0, 0, 0, 0 };
+								const int iTo = S.m_dMultiStart[g+1];
+								#pragma unroll 2
+								for ( int h=S.m_dMultiStart[g]; h<iTo; ++h )
+								{
+									const uint4 tRaw = __ldg ( reinterpret_cast<const uint4 *>( S.m_dMultiPtr[h]+uRowC ) );
+									const uint2 tMaskUb = S.m_dMultiMaskUb[h];
+									const uint32_t uMask = tMaskUb.x & ~1u;
+									const bool bNeg = ( tMaskUb.x & 1u )!=0;
+									const uint32_t dW[4] = { tRaw.x, tRaw.y, tRaw.z, tRaw.w };
+									#pragma unroll
+									for ( int j=0; j<4; ++j )
+									{
+										const uint32_t x = dW[j] & uMask;
+										const uint32_t z = ( x+0x0F000F00u ) & 0x10001000u;	// bit 12 / 28: the keyword sits on the row
+										dA[j] &= z;
+										dFg[j] |= x;
+										const uint32_t v = bNeg ? ( 0xE000E000u + z - ( z*15u & dW[j] ) ) : ( dW[j] & 0xF000F000u );
+										dUg[j] += (uint64_t)v*tMaskUb.y;
+									}
+								}
+								const uint32_t uOwed = (uint32_t)S.m_dMultiNeg[g];
+								#pragma unroll
+								for ( int j=0; j<4; ++j )
+								{
+									const uint32_t a = dA[j];
+									dF[j] |= dFg[j] & ( ( a>>4 )*15u );
+									const uint64_t uGate = (uint64_t)( ( a & 0x1000u )*0xFFFFu ) | ( (uint64_t)( ( a>>28 )*0xFFFFu )<<28 );
+									dUb[j] += ( dUg[j] & uGate ) + (uint64_t)( a ^ 0x10001000u )*uOwed;
+								}
+							}
+						}
 						uint32_t uSparseRows = 0;
 						if ( nList )
 						{
@@ -699,7 +851,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 								while ( nQueue>=32 )
 								{
 									nQueue -= 32;
-									fnExactHot ( true, pQueue[nQueue+iLane], pPool, tThrCur );
+									if constexpr ( DNF )
+										fnExactDnf ( true, pQueue[nQueue+iLane], -1, nullptr, pPool, tThrCur );
+									else
+										fnExactHot ( true, pQueue[nQueue+iLane], pPool, tThrCur );
 								}
 								__syncwarp();
 							}
@@ -726,46 +881,51 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 						{
 							const bool bAct = iBase+iLane<nCand;
 							const int sRow = c*256 + ( bAct ? (int)pCand[iBase+iLane] : 0 );	// slot inside the mini-tile
-							float fT = 0.0f;
-							uint32_t uF = 0;
-							bool bPres = false;
-							int iSp = 0;
-							for ( int iOp=0; iOp<nOps; ++iOp )
+							if constexpr ( DNF )
+								fnExactDnf ( bAct, uLo+sRow, sRow, pList, pPool, tThrCur );
+							else
 							{
-								const uint16_t * pRow = S.m_dOpPtr[iOp];
-								if ( pRow )
+								float fT = 0.0f;
+								uint32_t uF = 0;
+								bool bPres = false;
+								int iSp = 0;
+								for ( int iOp=0; iOp<nOps; ++iOp )
 								{
-									const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
-									const uint32_t uRaw = bAct ? __ldg ( pRow+uLo+sRow ) : 0u;
-									const uint32_t uHits = uRaw & 255u;
-									const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
-									if ( !uHits || !uFields )
-										continue;
-									float fBase = S.m_dTf[uHits];
-									if ( bAnyEscape && uHits==255 )
-										fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+sRow );
-									const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
-									// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
-									fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
-									uF |= uFields;
-									bPres = true;
-								} else
-								{
-									const int iTo = S.m_dOpStart[iWarp][iSp+1];
-									for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
+									const uint16_t * pRow = S.m_dOpPtr[iOp];
+									if ( pRow )
 									{
-										const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
-										if ( bAct && (int)tEntry.m_uRowid==sRow )
+										const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+										const uint32_t uRaw = bAct ? __ldg ( pRow+uLo+sRow ) : 0u;
+										const uint32_t uHits = uRaw & 255u;
+										const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
+										if ( !uHits || !uFields )
+											continue;
+										float fBase = S.m_dTf[uHits];
+										if ( bAnyEscape && uHits==255 )
+											fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+sRow );
+										const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+										// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
+										fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
+										uF |= uFields;
+										bPres = true;
+									} else
+									{
+										const int iTo = S.m_dOpStart[iWarp][iSp+1];
+										for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
 										{
-											fT = bPres ? __fadd_rn ( fT, tEntry.m_fTf ) : tEntry.m_fTf;
-											uF |= tEntry.m_uFields;
-											bPres = true;
+											const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
+											if ( bAct && (int)tEntry.m_uRowid==sRow )
+											{
+												fT = bPres ? __fadd_rn ( fT, tEntry.m_fTf ) : tEntry.m_fTf;
+												uF |= tEntry.m_uFields;
+												bPres = true;
+											}
 										}
+										++iSp;
 									}
-									++iSp;
 								}
+	fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, tThrCur );
 							}
-							fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, tThrCur );
 						}
 						__syncwarp();
 					}
@@ -1045,7 +1205,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, ORONLY ? 3 : 4 ) stream_kernel
 			// register-OR path: the queued candidate rows are evaluated against this round's threshold and pool buffer
 			if ( nQueue )
 			{
-				fnExactHot ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, tThrCur );
+				if constexpr ( DNF )
+					fnExactDnf ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], -1, nullptr, pPool, tThrCur );
+				else
+					fnExactHot ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, tThrCur );
 				nQueue = 0;
 				__syncwarp();
 			}

@@ -1076,15 +1076,24 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			const TermInfo_t * pDrv = m_dPlans[i].m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
 			bDnf = !pDrv || (int64_t)pDrv->m_iDocs*iDnfDiv<(int64_t)uRows*iDnfMul;
 		}
-		if ( !bDnf )
-			q.m_nGroups = 0;
 		// pure OR programs under BM25, no dead rows, <= 4 fields, ordered by relevance or by attributes alone (a sort key on the
 		// weight would need the bound inside the key): the bound + exact pass kernel; filters run inside its bound pass
 		bool bWeightKey = false;
 		for ( int k=0; k<q.m_nSortKeys; ++k )
 			bWeightKey |= q.m_dSortKeys[k].m_eKind==1;
-		const bool bOrClass = !bDnf && q.m_bPureOr && q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !getenv ( "MGPU_NO_ORCLASS" );
-		dOrder [ bDnf ? 2 : bOrClass ? 5 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
+		const bool bBoundOk = !bDnf && q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !getenv ( "MGPU_NO_ORCLASS" );
+		const bool bOrClass = bBoundOk && q.m_bPureOr && !q.m_nFilters && !q.m_nSortKeys;	// the lean instantiation: relevance order, no filters
+		// ... and the same passes with run-time options (class 6): pure OR programs with filters / attribute sort keys, and
+		// OR-of-AND-groups programs (a dense driver kept them off the intersection kernel) when every keyword of the
+		// multi-keyword groups sits in the dense store
+		bool bHotDnf = bBoundOk && !bOrClass && ( q.m_bPureOr || q.m_nGroups>0 ) && !getenv ( "MGPU_NO_DNFCLASS" );
+		if ( bHotDnf && !q.m_bPureOr )
+			for ( int g=0; g<q.m_nGroups && bHotDnf; ++g )
+				for ( int iOp=q.m_dGroupOp0[g]; iOp<q.m_dGroupOp0[g]+q.m_dGroupOps[g] && bHotDnf; ++iOp )
+					bHotDnf = q.m_dGroupOps[g]==1 || q.m_dLeaves[q.m_dOps[iOp].m_uLeaf].m_iHot>=0;
+		if ( ( !bDnf && !bHotDnf ) || ( bHotDnf && q.m_bPureOr ) )
+			q.m_nGroups = 0;
+		dOrder [ bDnf ? 2 : bOrClass ? 5 : bHotDnf ? 6 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
 	}
 
 	// estimated work of a query in its class (decides how many items it is cut into)
@@ -1101,8 +1110,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			return iWork;
 		}
 		for ( int l=0; l<p.m_tDev.m_nLeaves; ++l )
-			iWork += ( ( c==0 || c==3 || c==5 ) && p.m_tDev.m_dLeaves[l].m_iHot>=0 ) ? (int64_t)uRows/4 : ( p.m_dLeafTerms[l] ? p.m_dLeafTerms[l]->m_iDocs : 0 );
-		return ( c==0 || c==3 || c==5 ) ? iWork + uRows/16 : iWork;
+			iWork += ( ( c==0 || c==3 || c>=5 ) && p.m_tDev.m_dLeaves[l].m_iHot>=0 ) ? (int64_t)uRows/4 : ( p.m_dLeafTerms[l] ? p.m_dLeafTerms[l]->m_iDocs : 0 );
+		return ( c==0 || c==3 || c>=5 ) ? iWork + uRows/16 : iWork;
 	};
 
 	for ( int c=0; c<NUM_CLASSES; ++c )
@@ -1116,9 +1125,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			iTotalWork += fnWork ( m_dPlans[i], c );
 			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
 		}
-		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 || c==5 ) ? StreamOccupancy ( m_dStack[c], c==5 ) : EvalOccupancy ( m_dStack[c] );
+		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 || c>=5 ) ? StreamOccupancy ( m_dStack[c], c>=5 ? c-4 : 0 ) : EvalOccupancy ( m_dStack[c] );
 		const int nMaxCtas = pIndex->m_nSMs*iOcc;
-		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 || c==5 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
+		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 || c>=5 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
 
 		struct Part_t { int m_iQuery; int m_nParts; int64_t m_iCostPerPart; };
 		std::vector<Part_t> dParts;
@@ -1139,7 +1148,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				}
 				nUnits = std::max<int64_t> ( nUnits, p.m_tDev.m_nGroups );
 			}
-			if ( c==5 )
+			if ( c>=5 )
 			{
 				// fixed rowid ranges (OR_RANGE_TILES tiles) for every query of the class: the kernel takes the items range by range, so
 				// concurrent CTAs read the same rows of the dense store (L2 hits) and later ranges inherit the query's K-th-best bound
@@ -1206,13 +1215,14 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			m_dDevToQuery.push_back ( t.m_iQuery );
 		}
 		m_dCtas[c] = std::min ( nMaxCtas, (int)m_dItems.size()-m_dFirstItem[c] );
-		if ( c==5 )
+		if ( c>=5 )
 		{
 			const int iFirst = m_dFirstItem[c], n = (int)m_dItems.size()-iFirst;
-			m_dItemOrder.resize ( n );
+			std::vector<int32_t> & dOrd = m_dItemOrder[c-5];
+			dOrd.resize ( n );
 			for ( int i=0; i<n; ++i )
-				m_dItemOrder[i] = i;
-			std::stable_sort ( m_dItemOrder.begin(), m_dItemOrder.end(), [&] ( int a, int b ) { return m_dItems[iFirst+a].m_uRowLo<m_dItems[iFirst+b].m_uRowLo; } );
+				dOrd[i] = i;
+			std::stable_sort ( dOrd.begin(), dOrd.end(), [&] ( int a, int b ) { return m_dItems[iFirst+a].m_uRowLo<m_dItems[iFirst+b].m_uRowLo; } );
 		}
 	}
 	m_dFirstItem[NUM_CLASSES] = (int)m_dItems.size();
@@ -1228,12 +1238,13 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( m_dQ.AllocAsync ( nDevQ, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dI.AllocAsync ( nItems, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dCounter.AllocAsync ( NUM_CLASSES, tAllocStream ), m_sError );
-	if ( !m_dItemOrder.empty() )
-		CUDA_TRY ( m_dOrder.AllocAsync ( m_dItemOrder.size(), tAllocStream ), m_sError );
+	for ( int i=0; i<2; ++i )
+		if ( !m_dItemOrder[i].empty() )
+			CUDA_TRY ( m_dOrder[i].AllocAsync ( m_dItemOrder[i].size(), tAllocStream ), m_sError );
 	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
-	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4], m_dCtas[5] } )*2*m_iPoolCap;
+	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4], m_dCtas[5], m_dCtas[6] } )*2*m_iPoolCap;
 	m_nHitpos = std::max ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W, (size_t)m_dCtas[4]*EVAL_WARPS*MAX_LEAVES*32 );
-	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3], m_dCtas[5] } )*PRE_BLOCKS*32;
+	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3], m_dCtas[5], m_dCtas[6] } )*PRE_BLOCKS*32;
 	m_nPreHitpos = (size_t)m_dCtas[1]*PRE_BLOCKS*32;
 	if ( !m_dHotTerms.empty() )
 	{
@@ -1286,8 +1297,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	}
 	CUDA_TRY ( cudaMemcpyAsync ( m_dI.m_p, m_dItems.data(), (size_t)nItems*sizeof(DevWorkItem_t), cudaMemcpyHostToDevice, s ), m_sError );
 	CUDA_TRY ( cudaMemcpyAsync ( m_dOutSlot.m_p, m_dDevToQuery.data(), (size_t)nDevQ*4, cudaMemcpyHostToDevice, s ), m_sError );
-	if ( !m_dItemOrder.empty() )
-		CUDA_TRY ( cudaMemcpyAsync ( m_dOrder.m_p, m_dItemOrder.data(), m_dItemOrder.size()*4, cudaMemcpyHostToDevice, s ), m_sError );
+	for ( int i=0; i<2; ++i )
+		if ( !m_dItemOrder[i].empty() )
+			CUDA_TRY ( cudaMemcpyAsync ( m_dOrder[i].m_p, m_dItemOrder[i].data(), m_dItemOrder[i].size()*4, cudaMemcpyHostToDevice, s ), m_sError );
 	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
 	fnMark ( "upload + sync" );
 	m_tStats.h2d_bytes = (int64_t)nDevQ*sizeof(DevQuery_t) + (int64_t)nItems*sizeof(DevWorkItem_t);
@@ -1327,8 +1339,8 @@ int Batch_c::Run()
 	CUDA_TRY ( tScr.m_dPool.Grow ( m_nPool ), m_sError );
 	CUDA_TRY ( tScr.m_dHitpos.Grow ( m_nHitpos ), m_sError );
 	CUDA_TRY ( tScr.m_dPre.Grow ( m_nPre ), m_sError );
-	if ( m_dCtas[5] )
-		CUDA_TRY ( tScr.m_dOrList.Grow ( (size_t)m_dCtas[5]*EVAL_WARPS*512*MAX_LEAVES ), m_sError );
+	if ( m_dCtas[5] || m_dCtas[6] )
+		CUDA_TRY ( tScr.m_dOrList.Grow ( (size_t)std::max ( m_dCtas[5], m_dCtas[6] )*EVAL_WARPS*512*MAX_LEAVES ), m_sError );
 	CUDA_TRY ( tScr.m_dPreHitpos.Grow ( m_nPreHitpos ), m_sError );
 	if ( !m_dHotTerms.empty() )
 	{
@@ -1384,15 +1396,15 @@ int Batch_c::Run()
 		P.m_iKMax = m_iKMax;
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
 		P.m_pQueryThr = m_dQueryThr.m_p;
-		P.m_pOrList = c==5 ? tScr.m_dOrList.m_p : nullptr;
-		P.m_pItemOrder = ( c==5 && !m_dItemOrder.empty() ) ? m_dOrder.m_p : nullptr;
+		P.m_pOrList = c>=5 ? tScr.m_dOrList.m_p : nullptr;
+		P.m_pItemOrder = ( c>=5 && !m_dItemOrder[c-5].empty() ) ? m_dOrder[c-5].m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
 		P.m_tHot = tHot;
 		if ( c==2 || c==4 )
 			CUDA_TRY ( LaunchAnd ( P, c==4, m_dCtas[c], s ), m_sError );
-		else if ( c==0 || c==3 || c==5 )
-			CUDA_TRY ( LaunchStream ( P, m_dStack[c], c==5, m_dCtas[c], s ), m_sError );
+		else if ( c==0 || c==3 || c>=5 )
+			CUDA_TRY ( LaunchStream ( P, m_dStack[c], c>=5 ? c-4 : 0, m_dCtas[c], s ), m_sError );
 		else
 			CUDA_TRY ( LaunchEval ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
 		CUDA_TRY ( cudaEventRecord ( m_dEvClass[c], s ), m_sError );

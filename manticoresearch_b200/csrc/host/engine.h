@@ -161,11 +161,12 @@ public:
 	/// launch classes: [0] doc-only queries with a single-level program (stream_kernel<512>), [1] hit-consuming queries on dense
 	/// tiles (eval_kernel<true>), [2] doc-only DNF / pure AND queries led by sparse keywords (and_kernel<false>), [3] deeper doc-only
 	/// programs (stream_kernel<256>), [4] hit-consuming pure AND chains incl. phrase / proximity (and_kernel<true>),
-	/// [5] pure OR programs under BM25 relevance without filters (stream_kernel<512,ORONLY>: bound pass + exact pass)
-	static const int NUM_CLASSES = 6;
-	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1, 1, 1 };
-	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0, 0, 0 };
-	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0, 0, 0 };
+	/// [5] pure OR programs under BM25 (stream_kernel<512,1>: bound pass + exact pass), [6] OR-of-AND-groups programs whose
+	/// multi-keyword groups are all hot (stream_kernel<512,2>: the same passes with gated groups)
+	static const int NUM_CLASSES = 7;
+	int		m_dStack[NUM_CLASSES] = { 1, 1, 1, 1, 1, 1, 1 };
+	int		m_dCtas[NUM_CLASSES] = { 0, 0, 0, 0, 0, 0, 0 };
+	int		m_dFirstItem[NUM_CLASSES+1] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	int		m_iKMax = 1;
 	int		m_iPoolCap = 0;
 	int		m_iScratchStride = 0;
@@ -173,8 +174,8 @@ public:
 	DevBuf_T<DevQuery_t>	m_dQ;
 	DevBuf_T<DevWorkItem_t>	m_dI;
 	DevBuf_T<int32_t>		m_dCounter;
-	std::vector<int32_t>	m_dItemOrder;	///< class 5: items in rowid-range-major order (index relative to the class's first item)
-	DevBuf_T<int32_t>		m_dOrder;
+	std::vector<int32_t>	m_dItemOrder[2];	///< classes 5, 6: items in rowid-range-major order (index relative to the class's first item)
+	DevBuf_T<int32_t>		m_dOrder[2];
 	DevBuf_T<unsigned long long> m_dQueryThr;	///< per device query: shared K-th-best bound of its items
 	DevBuf_T<Key128_t>		m_dItemKeys, m_dScratch, m_dOutKeys;
 	size_t	m_nPool = 0, m_nHitpos = 0, m_nPre = 0, m_nPreHitpos = 0;	///< what Run() needs from the index's RunScratch_t
@@ -188,8 +189,8 @@ public:
 	int64_t					m_iHotStride = 0;
 	int						m_iHotEscapeCap = 0;
 	cudaEvent_t				m_tEvHot = nullptr;
-	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false, false, false };
+	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false, false, false, false };
 
 	cudaEvent_t		m_tEv0 = nullptr, m_tEv1 = nullptr, m_tEv2 = nullptr;
 	mgpu_batch_stats m_tStats {};
@@ -207,8 +208,8 @@ public:
 size_t		EvalDynSmemBytes ( int nStack );
 int			EvalOccupancy ( int nStack );
 cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );	///< eval_kernel<hits>
-cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, bool bOrOnly, int nCtas, cudaStream_t tStream );
-int			StreamOccupancy ( int nStack, bool bOrOnly );
+cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, int iMode, int nCtas, cudaStream_t tStream );	///< 0 general, 1 pure OR, 2 hot DNF
+int			StreamOccupancy ( int nStack, int iMode );
 cudaError_t	LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream );
 int			AndOccupancy ( bool bHits );
 cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream );

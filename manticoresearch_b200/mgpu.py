@@ -72,7 +72,7 @@ class c_batch_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("work_items", C.c_int64), ("algorithmic_bytes", C.c_int64),
                 ("postings", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float), ("hot_decode_ms", C.c_float), ("hot_terms", C.c_int32),
-                ("class_ms", C.c_float * 6), ("class_queries", C.c_int32 * 6), ("class_bytes", C.c_int64 * 6),
+                ("class_ms", C.c_float * 7), ("class_queries", C.c_int32 * 7), ("class_bytes", C.c_int64 * 7),
                 ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float),
                 ("host_wait_ms", C.c_float), ("host_total_ms", C.c_float)]
 

@@ -3,7 +3,7 @@
 bench.py reads the dominant kernel's dram bytes per launch from that file (roofline.traffic)."""
 import csv, io, json, subprocess, sys
 
-NAMES = {"stream_kernel<512, 1>": "stream_kernel<512,or>", "stream_kernel<512, 0>": "stream_kernel<512>",
+NAMES = {"stream_kernel<512, 1>": "stream_kernel<512,or>", "stream_kernel<512, 2>": "stream_kernel<512,dnf>", "stream_kernel<512, 0>": "stream_kernel<512>",
          "stream_kernel<256, 0>": "stream_kernel<256>", "and_kernel<0>": "and_kernel", "and_kernel<1>": "and_kernel<hits>",
          "eval_kernel<1>": "eval_kernel<hits>", "hot_decode_kernel": "hot_decode_kernel", "merge_kernel": "merge_kernel"}
 

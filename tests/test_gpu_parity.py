@@ -147,8 +147,60 @@ def test_or_class_bound_pass_edges(synth):
     batch = synth["gpu"].prepare(qs + qs[:60])      # repeated keywords -> hot store
     st = batch.stats()
     batch.free()
-    assert st["class_queries"][5] >= 200, st["class_queries"]
+    assert st["class_queries"][5] >= 150 and st["class_queries"][5] + st["class_queries"][6] >= 270, st["class_queries"]
     assert _compare_batch(synth, qs + qs[:60]) == 0
+
+
+def test_hot_dnf_class_edges(synth):
+    """stream_kernel<512,2> (launch class 6): OR-of-AND-groups programs whose multi-keyword groups are hot keywords only: all-dense
+    ANDs, (a b)|(c d), (a b c)|d with a sparse or a hot single, three groups, field limits, negative-idf keywords inside groups,
+    filters / attribute sort, K from 1 to 3000"""
+    import random
+    rng = random.Random(777)
+    title, body = 1, 2
+    gid, ts = synth["gpu"].attr_index("gid"), synth["gpu"].attr_index("ts")
+
+    def leaf(r, p):
+        n = M.kw(M.synth_keyword(r - 1), p)
+        if rng.random() < 0.2:
+            n.fields(rng.choice([title, body]))
+        return n
+
+    qs = []
+    for i in range(240):
+        shape = i % 6
+        pos = [0]
+
+        def group(lo, hi, n):
+            out = []
+            for r in rng.sample(range(lo, hi), n):
+                pos[0] += 1
+                out.append(leaf(r, pos[0]))
+            return M.AND(*out) if n > 1 else out[0]
+
+        if shape == 0:      # all-dense AND (dense driver: not for the intersection kernel)
+            root = group(1, 25, rng.randint(2, 5))
+        elif shape == 1:    # two dense groups
+            root = M.OR(group(1, 30, rng.randint(2, 3)), group(1, 30, rng.randint(2, 3)))
+        elif shape == 2:    # dense group | hot-but-sparser group
+            root = M.OR(group(1, 20, 2), group(20, 300, 2))
+        elif shape == 3:    # dense group | single sparse keyword | single hot keyword
+            root = M.OR(group(1, 20, rng.randint(2, 3)), group(2000, 60000, 1), group(1, 200, 1))
+        elif shape == 4:    # three groups
+            root = M.OR(group(1, 15, 2), group(1, 40, 2), group(5, 60, 3))
+        else:               # single first, then groups
+            root = M.OR(group(1, 300, 1), group(1, 25, 2), group(1, 25, 2))
+        kwargs = {}
+        if i % 5 == 2:
+            kwargs["filters"] = rng.choice([[M.Filter(gid, 100, 299)], [M.Filter(gid, values=[5, 17, 900, 901])], []])
+            kwargs["sort_keys"] = rng.choice([[], [M.SortKey(M.KEYPART_INT, ts, True)], [M.SortKey(M.KEYPART_ROWID, 0, True)]])
+        qs.append(M.Query(root, ranker=M.RANK_BM25, field_weights=rng.choice([[10, 1], [1, 1], [0, 5], None]),
+                          max_matches=rng.choice([1, 5, 100, 3000]), index_weight=rng.choice([1, 1, 3]), **kwargs))
+    batch = synth["gpu"].prepare(qs + qs[:80])
+    st = batch.stats()
+    batch.free()
+    assert st["class_queries"][6] >= 150, st["class_queries"]
+    assert _compare_batch(synth, qs + qs[:80]) == 0
 
 
 def test_cfg4_mix_with_andnot(synth):
