@@ -53,6 +53,8 @@ struct StreamShared_t
 	int32_t			m_nPosOps, m_nNegOps;
 	uint8_t			m_dSparseOp[MAX_LEAVES];			///< register-OR path: ops whose keyword is walked from the compressed doclist, in op order
 	int32_t			m_nSparseOps;
+	uint8_t			m_dSparseUnit[MAX_LEAVES];			///< DNF mode: the AND group this sparse keyword drives (its other keywords are hot), 0xFF = a one-keyword unit
+	uint8_t			m_dUnitList[MAX_LEAVES];			///< DNF mode: the unit's postings come from the mini-tile's sparse list (sparse single / sparse-driven group)
 	// DNF mode: multi-keyword AND groups (hot keywords only), entries in op order; x bit 0 = negative idf
 	uint2			m_dMultiMaskUb[MAX_LEAVES];
 	const uint16_t * m_dMultiPtr[MAX_LEAVES];
@@ -271,7 +273,15 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 			{
 				const int iOp0 = bGroups ? q.m_dGroupOp0[u] : u, nUnitOps = bGroups ? q.m_dGroupOps[u] : 1;
 				int iGroupNeg = 0;
-				if ( nUnitOps>1 )
+				// a group with ONE sparse keyword is driven by it: its postings are gathered per mini-tile, the group's other (hot)
+				// keywords are looked up at those rows only and the list entry carries the whole group's exact sum (the host's test
+				// admits no group with two sparse keywords)
+				int nUnitSparse = 0;
+				for ( int iOp=iOp0; iOp<iOp0+nUnitOps; ++iOp )
+					nUnitSparse += q.m_dLeaves[q.m_dOps[iOp].m_uLeaf].m_iHot<0 ? 1 : 0;
+				const bool bListUnit = nUnitSparse>0;
+				S.m_dUnitList[u] = bListUnit ? 1 : 0;
+				if ( nUnitOps>1 && !bListUnit )
 					S.m_dMultiStart[nMultiGroups] = (uint8_t)nMulti;
 				for ( int iOp=iOp0; iOp<iOp0+nUnitOps; ++iOp )
 				{
@@ -279,11 +289,17 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 					const DevLeaf_t & tLeaf = q.m_dLeaves[l];
 					if ( tLeaf.m_iHot<0 )
 					{
-						S.m_dSparseOp[nSparse++] = (uint8_t)iOp;	// (one-keyword units only)
+						S.m_dSparseUnit[nSparse] = nUnitOps>1 ? (uint8_t)u : (uint8_t)0xFF;
+						S.m_dSparseOp[nSparse++] = (uint8_t)iOp;
 						continue;
 					}
 					const float fIDF = tLeaf.m_fIDF;
 					const uint16_t * pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
+					if ( bListUnit )
+					{
+						S.m_dLeafPtr[l] = pRow;	// probed at the driver's postings only; its bound comes with the list entry
+						continue;
+					}
 					const uint32_t m = tLeaf.m_uQueriedFields & 0xFu;	// this path runs for indexes with <= 4 fields only
 					const uint32_t uMask = ( m<<8 ) | ( m<<24 );
 					const float fShare = __fmul_rn ( fminf ( fabsf ( fIDF ), 1.0f ), 64000.0f/15.0f );
@@ -313,7 +329,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 					if ( !DNF )
 						S.m_dOpPtr[iOp] = pRow;
 				}
-				if ( nUnitOps>1 )
+				if ( nUnitOps>1 && !bListUnit )
 					S.m_dMultiNeg[nMultiGroups++] = iGroupNeg;
 			}
 			S.m_dMultiStart[nMultiGroups] = (uint8_t)nMulti;
@@ -429,50 +445,46 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 				float fG = 0.0f;
 				uint32_t uFG = 0;
 				bool bAll = true, bFirst = true;
+				if ( S.m_dUnitList[g] )
+				{
+					// sparse single or sparse-driven group: the mini-tile's list holds the unit's exact sum at the rows it matches
+					bAll = false;
+					if ( sSlot>=0 )
+					{
+						const int iTo = S.m_dOpStart[iWarp][iSp+1];
+						for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
+						{
+							const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
+							if ( bAct && (int)tEntry.m_uRowid==sSlot )
+							{
+								fG = tEntry.m_fTf;
+								uFG = tEntry.m_uFields;
+								bAll = true;
+								bFirst = false;
+							}
+						}
+					}
+					++iSp;
+				} else
 				for ( int iOp=iOp0; iOp<iOp0+nGroupOps; ++iOp )
 				{
 					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
 					const uint16_t * pRow = S.m_dLeafPtr[q.m_dOps[iOp].m_uLeaf];
-					if ( pRow )
+					const uint32_t uRaw = ( bAct && pRow ) ? __ldg ( pRow+uRow ) : 0u;
+					const uint32_t uHits = uRaw & 255u;
+					const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
+					if ( !uHits || !uFields )
 					{
-						const uint32_t uRaw = bAct ? __ldg ( pRow+uRow ) : 0u;
-						const uint32_t uHits = uRaw & 255u;
-						const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
-						if ( !uHits || !uFields )
-						{
-							bAll = false;
-							continue;
-						}
-						float fBase = S.m_dTf[uHits];
-						if ( bAnyEscape && uHits==255 )
-							fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
-						const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
-						fG = bFirst ? fTf : __fadd_rn ( fG, fTf );
-						uFG |= uFields;
-						bFirst = false;
-					} else
-					{
-						bool bFound = false;
-						if ( sSlot>=0 )
-						{
-							const int iTo = S.m_dOpStart[iWarp][iSp+1];
-							for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
-							{
-								const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
-								if ( bAct && (int)tEntry.m_uRowid==sSlot )
-								{
-									fG = tEntry.m_fTf;
-									uFG = tEntry.m_uFields;
-									bFound = true;
-								}
-							}
-						}
-						++iSp;
-						if ( bFound )
-							bFirst = false;
-						else
-							bAll = false;
+						bAll = false;
+						continue;
 					}
+					float fBase = S.m_dTf[uHits];
+					if ( bAnyEscape && uHits==255 )
+						fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
+					const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+					fG = bFirst ? fTf : __fadd_rn ( fG, fTf );
+					uFG |= uFields;
+					bFirst = false;
 				}
 				if ( bAll && !bFirst )
 				{
@@ -624,7 +636,47 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 								const uint32_t uNextBase = b+1<tLeaf.m_nBlocks ? __ldg ( pBase+b+1 ) : 0xFFFFFFFFu;
 								StreamCacheBlock ( tIdx, tLeaf, b, &S.m_dCached[iWarp][l], pCache0+l*32, pStage, pRecStart, S.m_dTf, iLane );
 								PreEntry_t tEntry = pCache0[l*32+iLane];
-								const bool bIn = tEntry.m_uRowid>=uLo && tEntry.m_uRowid<uHi;
+								bool bIn = tEntry.m_uRowid>=uLo && tEntry.m_uRowid<uHi;
+								if constexpr ( DNF )
+								{
+									const int iUnit = S.m_dSparseUnit[iSp];
+									if ( iUnit!=0xFF )
+									{
+										// this keyword drives an AND group: look its hot keywords up at the posting's row and fold the group's
+										// sum in op order (ExtAnd_c: left + right); the entry then stands for the whole group
+										const int iOp0 = q.m_dGroupOp0[iUnit], nGroupOps = q.m_dGroupOps[iUnit];
+										float fG = 0.0f;
+										uint32_t uFG = 0;
+										bool bFirst = true;
+										for ( int iOp=iOp0; iOp<iOp0+nGroupOps; ++iOp )
+										{
+											const int iLeaf = q.m_dOps[iOp].m_uLeaf;
+											float fTf = tEntry.m_fTf;
+											uint32_t uFl = tEntry.m_uFields;
+											if ( iLeaf!=l )
+											{
+												const DevLeaf_t & tOther = q.m_dLeaves[iLeaf];
+												const uint32_t uRaw = bIn ? __ldg ( S.m_dLeafPtr[iLeaf]+tEntry.m_uRowid ) : 0u;
+												const uint32_t uHits = uRaw & 255u;
+												uFl = ( uRaw>>8 ) & tOther.m_uQueriedFields;
+												if ( !uHits || !uFl )
+												{
+													bIn = false;
+													continue;
+												}
+												float fBase = S.m_dTf[uHits];
+												if ( bAnyEscape && uHits==255 )
+													fBase = HotEscapeTf ( P.m_tHot, tOther.m_iHot, tEntry.m_uRowid );
+												fTf = __fmul_rn ( fBase, tOther.m_fIDF );
+											}
+											fG = bFirst ? fTf : __fadd_rn ( fG, fTf );
+											uFG |= uFl;
+											bFirst = false;
+										}
+										tEntry.m_fTf = fG;
+										tEntry.m_uFields = uFG;
+									}
+								}
 								const unsigned m = __ballot_sync ( FULL_MASK, bIn );
 								if ( bIn )
 								{

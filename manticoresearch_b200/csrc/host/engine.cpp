@@ -1084,13 +1084,18 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		const bool bBoundOk = !bDnf && q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !getenv ( "MGPU_NO_ORCLASS" );
 		const bool bOrClass = bBoundOk && q.m_bPureOr && !q.m_nFilters && !q.m_nSortKeys;	// the lean instantiation: relevance order, no filters
 		// ... and the same passes with run-time options (class 6): pure OR programs with filters / attribute sort keys, and
-		// OR-of-AND-groups programs (a dense driver kept them off the intersection kernel) when every keyword of the
-		// multi-keyword groups sits in the dense store
+		// OR-of-AND-groups programs (a dense driver kept them off the intersection kernel) whose multi-keyword groups hold at most
+		// one keyword outside the dense store
 		bool bHotDnf = bBoundOk && !bOrClass && ( q.m_bPureOr || q.m_nGroups>0 ) && !getenv ( "MGPU_NO_DNFCLASS" );
 		if ( bHotDnf && !q.m_bPureOr )
 			for ( int g=0; g<q.m_nGroups && bHotDnf; ++g )
-				for ( int iOp=q.m_dGroupOp0[g]; iOp<q.m_dGroupOp0[g]+q.m_dGroupOps[g] && bHotDnf; ++iOp )
-					bHotDnf = q.m_dGroupOps[g]==1 || q.m_dLeaves[q.m_dOps[iOp].m_uLeaf].m_iHot>=0;
+			{
+				// a multi-keyword group may hold one sparse keyword (it then drives the group), the rest must be hot
+				int nSparse = 0;
+				for ( int iOp=q.m_dGroupOp0[g]; iOp<q.m_dGroupOp0[g]+q.m_dGroupOps[g]; ++iOp )
+					nSparse += q.m_dLeaves[q.m_dOps[iOp].m_uLeaf].m_iHot<0 ? 1 : 0;
+				bHotDnf = q.m_dGroupOps[g]==1 || nSparse<=1;
+			}
 		if ( ( !bDnf && !bHotDnf ) || ( bHotDnf && q.m_bPureOr ) )
 			q.m_nGroups = 0;
 		dOrder [ bDnf ? 2 : bOrClass ? 5 : bHotDnf ? 6 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );

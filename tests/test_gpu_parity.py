@@ -153,7 +153,7 @@ def test_or_class_bound_pass_edges(synth):
 
 def test_hot_dnf_class_edges(synth):
     """stream_kernel<512,2> (launch class 6): OR-of-AND-groups programs whose multi-keyword groups are hot keywords only: all-dense
-    ANDs, (a b)|(c d), (a b c)|d with a sparse or a hot single, three groups, field limits, negative-idf keywords inside groups,
+    ANDs, (a b)|(c d), (a b)|(c SPARSE d), (a b c)|d with a sparse or a hot single, three groups, field limits, negative-idf keywords inside groups,
     filters / attribute sort, K from 1 to 3000"""
     import random
     rng = random.Random(777)
@@ -182,8 +182,16 @@ def test_hot_dnf_class_edges(synth):
             root = group(1, 25, rng.randint(2, 5))
         elif shape == 1:    # two dense groups
             root = M.OR(group(1, 30, rng.randint(2, 3)), group(1, 30, rng.randint(2, 3)))
-        elif shape == 2:    # dense group | hot-but-sparser group
-            root = M.OR(group(1, 20, 2), group(20, 300, 2))
+        elif shape == 2:    # dense group | hot-but-sparser group, or a group driven by ONE sparse keyword (hot keywords probed at its postings)
+            if i % 12 == 2:
+                root = M.OR(group(1, 20, 2), group(20, 300, 2))
+            else:
+                pos[0] += 3
+                mixed = [leaf(rng.randint(1, 40), pos[0] - 2), leaf(rng.randint(1500, 30000), pos[0] - 1)]
+                if rng.random() < 0.5:
+                    mixed.append(leaf(rng.randint(1, 200), pos[0]))
+                rng.shuffle(mixed)
+                root = M.OR(group(1, 20, 2), M.AND(*mixed))
         elif shape == 3:    # dense group | single sparse keyword | single hot keyword
             root = M.OR(group(1, 20, rng.randint(2, 3)), group(2000, 60000, 1), group(1, 200, 1))
         elif shape == 4:    # three groups
