@@ -39,6 +39,11 @@ def main():
                     "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                     "registers": val(r, "launch__registers_per_thread"), "l2_hit_pct": val(r, "lts__t_sector_hit_rate.pct"),
                     "capture": capture}
+    import math
+    for v in res.values():
+        for a, b in list(v.items()):
+            if isinstance(b, float) and math.isnan(b):
+                v[a] = None      # ncu could not collect this counter for the launch
     json.dump(res, open(dst, "w"), indent=1)
     for k, v in res.items():
         print(k, v)
