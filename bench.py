@@ -124,7 +124,7 @@ def measured_peak():
 
 def ncu_traffic(kernel):
     """dram bytes (read+write) per launch of `kernel` from the committed ncu --set full capture of this command at N=1
-    (profiles/kernel_traffic.json, see profiles/r01_v8_summary.md)"""
+    (profiles/kernel_traffic.json, see profiles/r01_v21_summary.md)"""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(kernel, {}).get("dram_bytes_per_launch")
     except Exception:

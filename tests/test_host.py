@@ -83,6 +83,24 @@ def test_synthetic_index_roundtrip(tmp_path):
         idx.close()
 
 
+def test_ctypes_mirrors_match_the_header(tmp_path):
+    """sizeof / last-field offset of every public struct as gcc sees include/mgpu.h == the ctypes mirror the tests and bench.py use
+    (a stale mirror would read garbage stats or mis-marshal queries without failing loudly)"""
+    import subprocess
+    pairs = [("mgpu_xqkeyword", M.c_xqkeyword), ("mgpu_xqnode", M.c_xqnode), ("mgpu_sortkey", M.c_sortkey), ("mgpu_filter", M.c_filter),
+             ("mgpu_query", M.c_query), ("mgpu_wordstat", M.c_wordstat), ("mgpu_result", M.c_result), ("mgpu_batch_stats", M.c_batch_stats),
+             ("mgpu_build_doc_input", M.c_build_doc_input), ("mgpu_synth_params", M.SynthParams)]
+    src = tmp_path / "sizes.c"
+    body = "".join('printf("%%s %%zu %%zu\\n", "%s", sizeof(%s), offsetof(%s, %s));\n' % (c, c, c, py._fields_[-1][0]) for c, py in pairs)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mgpu.h"\nint main(void){\n' + body + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {l.split()[0]: (int(l.split()[1]), int(l.split()[2])) for l in out if l.strip()}
+    for c, py in pairs:
+        assert got[c] == (C.sizeof(py), getattr(py, py._fields_[-1][0]).offset), (c, got[c], C.sizeof(py))
+
+
 def test_same_corpus_any_thread_count(tmp_path):
     """the parallel builder is deterministic: 1 thread and 5 threads write identical bytes"""
     a, b = str(tmp_path / "a"), str(tmp_path / "b")
