@@ -94,6 +94,20 @@ for qi, text, tree in q019:
     case["queries"].append({"text": text, "tree": tree, "ranker": "proximity_bm25", "expect": api_expect(m19[qi], text)})
 out["cases"].append(case)
 
+# test_019 index `fld` (documents 1000..1010 of the same table): the "regression for ranker fieldmask" query. SPH_RANK_FIELDMASK
+# (RankerState_Fieldmask_fn, src/sphinxsearch.cpp:1582-1610): weight = bit mask of the fields the keywords hit.
+docs_019f = [(1000, "spec1", "dummy1"), (1001, "spec1 dummy1", ""), (1002, "", "spec1 dummy1"), (1003, "spec2 dummy2 text2", ""),
+             (1004, "spec2", "dummy2 text2"), (1005, "spec3", "dummy3 text3"), (1006, "spec3 dummy3 text3", "spec3"),
+             (1007, "spec4 dummy4", "text4"), (1008, "spec4", "dummy4 text4"), (1009, "spec5 of my", "dummy5"), (1010, "spec5", "of my text5")]
+case = {"name": "test_019_fld", "fields": ["title", "body"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1], d[2]]} for d in docs_019f], "queries": []}
+r = m19[52]
+assert "ranker='fieldmask'" in r["sphinxql"] and "'spec1 | dummy1'" in r["sphinxql"]
+case["queries"].append({"text": r["sphinxql"], "tree": ["or", ["kw", "spec1", 1], ["kw", "dummy1", 2]], "ranker": "fieldmask", "sort": "id_asc",
+                        "expect": {"matches": [[int(row["id"]), int(row["weight()"])] for row in r["rows"].values()],
+                                   "total_found": int(r["total_rows"]), "words": {}}})
+out["cases"].append(case)
+
 # ---------------------------------------------------------------------------------------------
 # test_037 "rankers", index `test` (stem_ru/stem_en: both doc and query words are stemmed alike, so
 # treating the Russian words as opaque tokens gives the same postings; word stats are NOT compared)

@@ -184,7 +184,9 @@ def build_golden_index(case, prefix):
 
 
 def golden_query(case, q):
-    return M.Query(tree_to_node(q["tree"]), ranker=RANKERS[q["ranker"]], field_weights=q.get("field_weights"), max_matches=1000)
+    # "sort": "id_asc" = SphinxQL `order by id asc`: documents are indexed in id order, so that is rowid ascending
+    sort_keys = [M.SortKey(M.KEYPART_ROWID, 0, False)] if q.get("sort") == "id_asc" else None
+    return M.Query(tree_to_node(q["tree"]), ranker=RANKERS[q["ranker"]], field_weights=q.get("field_weights"), sort_keys=sort_keys, max_matches=1000)
 
 
 def assert_same_results(a, b, ctx=""):
