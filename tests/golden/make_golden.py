@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_019,037,114,116,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_016,017,019,037,055,114,116,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -106,6 +106,37 @@ assert "ranker='fieldmask'" in r["sphinxql"] and "'spec1 | dummy1'" in r["sphinx
 case["queries"].append({"text": r["sphinxql"], "tree": ["or", ["kw", "spec1", 1], ["kw", "dummy1", 2]], "ranker": "fieldmask", "sort": "id_asc",
                         "expect": {"matches": [[int(row["id"]), int(row["weight()"])] for row in r["rows"].values()],
                                    "total_found": int(r["total_rows"]), "words": {}}})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_016 "expr sorting vs filters": legacy SPH_MATCH_ANY. PrepareQueryEmulation (src/searchd.cpp:2140-2185) rewrites the raw
+# query `test it` into `"test it"/1` and picks SPH_RANK_MATCHANY (RankerState_MatchAny_fn, src/sphinxsearch.cpp:1611-1668); the
+# threshold-1 quorum becomes an OR chain over the keywords (src/searchnode.cpp:1638-1688). sortmode=expr "@weight" is relevance order,
+# "-@weight" is weight ascending.
+# ---------------------------------------------------------------------------------------------
+docs_016 = [(111, 1, "this is test"), (222, 1, "just a test"), (333, 2, "for test-ing purposes"), (444, 1, "lets test it")]
+m16 = model("test_016")
+any_tree = ["quorum", 1, [["test", 1], ["it", 2]]]
+case = {"name": "test_016", "fields": ["body"], "attrs": ["group_id"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[2]], "attrs": [d[1]]} for d in docs_016], "queries": []}
+case["queries"].append({"text": m16[0]["query"], "tree": any_tree, "ranker": "matchany", "filters": [["group_id", 1, 1]], "expect": api_expect(m16[0], "test it")})
+case["queries"].append({"text": m16[1]["query"], "tree": any_tree, "ranker": "matchany", "sort": "weight_asc", "expect": api_expect(m16[1], "test it")})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_017 "phrase matching vs stop words and short words" (stopwords a/the/and/of, min_word_len=3; both consume a position, in the
+# documents and in the query). Legacy SPH_MATCH_PHRASE = `"..."` ranked by SPH_RANK_PROXIMITY (PrepareQueryEmulation,
+# src/searchd.cpp:2140-2185; ExtRanker_State_T<RankerState_Proximity_fn<false,...>>: weight = sum of field weight * LCS, no BM25);
+# the same phrases in extended2 mode are ranked by the default PROXIMITY_BM25.
+# ---------------------------------------------------------------------------------------------
+docs_017 = [(1, "walking shoes"), (2, "try walking in my shoes"), (3, "Microsoft. The Office."), (4, "Microsoft Office")]
+m17 = model("test_017")
+ph17 = [["phrase", [["walking", 1], ["shoes", 2]]], ["phrase", [["walking", 1], ["shoes", 4]]],
+        ["phrase", [["microsoft", 1], ["office", 2]]], ["phrase", [["microsoft", 1], ["office", 3]]]]
+case = {"name": "test_017", "fields": ["body"], "min_word_len": 3, "stopwords": ["a", "the", "and", "of"],
+        "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_017], "queries": []}
+for qi in range(8):
+    case["queries"].append({"text": m17[qi]["query"], "tree": ph17[qi % 4], "ranker": "proximity" if qi < 4 else "proximity_bm25", "expect": api_expect(m17[qi])})
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------

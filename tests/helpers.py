@@ -117,15 +117,15 @@ def _is_word_char(ch):
     return ch.isascii() and (ch.isalnum() or ch == "_") or 0x410 <= o <= 0x44F
 
 
-def tokenize(text, min_word_len=1):
-    """-> [(keyword, pos)], pos 1-based; overshort tokens consume a position (overshort_step=1)"""
+def tokenize(text, min_word_len=1, stopwords=()):
+    """-> [(keyword, pos)], pos 1-based; overshort tokens and stop words consume a position (overshort_step=1, stopword_step=1)"""
     out, pos, cur = [], 0, ""
 
     def flush():
         nonlocal cur, pos
         if cur:
             pos += 1
-            if len(cur) >= min_word_len:
+            if len(cur) >= min_word_len and cur not in stopwords:
                 out.append((cur, pos))
             cur = ""
 
@@ -179,14 +179,18 @@ def load_golden():
 def build_golden_index(case, prefix):
     docs = []
     for d in case["docs"]:
-        docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1)) for t in d["fields"]], "attrs": []})
-    M.build_index(prefix, case["fields"], docs)
+        docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ())) for t in d["fields"]], "attrs": d.get("attrs", [])})
+    M.build_index(prefix, case["fields"], docs, attr_names=case.get("attrs", ()))
 
 
 def golden_query(case, q):
     # "sort": "id_asc" = SphinxQL `order by id asc`: documents are indexed in id order, so that is rowid ascending
-    sort_keys = [M.SortKey(M.KEYPART_ROWID, 0, False)] if q.get("sort") == "id_asc" else None
-    return M.Query(tree_to_node(q["tree"]), ranker=RANKERS[q["ranker"]], field_weights=q.get("field_weights"), sort_keys=sort_keys, max_matches=1000)
+    # "sort": "weight_asc" = sortmode expr "-@weight" (ties by id ascending, as every comparator of the reference ends)
+    sort_keys = {"id_asc": [M.SortKey(M.KEYPART_ROWID, 0, False)], "weight_asc": [M.SortKey(M.KEYPART_WEIGHT, 0, False)]}.get(q.get("sort"))
+    # "filters": [[attribute name, min, max]...] (attribute 0 of a v62 schema is the document id, the case's "attrs" follow)
+    filters = [M.Filter(1 + case["attrs"].index(a), lo, hi) for a, lo, hi in q.get("filters", [])]
+    return M.Query(tree_to_node(q["tree"]), ranker=RANKERS[q["ranker"]], field_weights=q.get("field_weights"), sort_keys=sort_keys,
+                   filters=filters, max_matches=1000)
 
 
 def assert_same_results(a, b, ctx=""):
