@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_016,017,019,037,055,114,116,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,055,059,094,114,116,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -137,6 +137,65 @@ case = {"name": "test_017", "fields": ["body"], "min_word_len": 3, "stopwords": 
         "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_017], "queries": []}
 for qi in range(8):
     case["queries"].append({"text": m17[qi]["query"], "tree": ph17[qi % 4], "ranker": "proximity" if qi < 4 else "proximity_bm25", "expect": api_expect(m17[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_015 "phrase matching vs duplicate keywords" (stop word "2" consumes a position; '-' separates): phrases and a long AND with
+# repeated keywords (HasQwordDupes: RankerState_Proximity_fn<*,true>), legacy phrase mode (SPH_RANK_PROXIMITY) and extended2
+# (PROXIMITY_BM25)
+# ---------------------------------------------------------------------------------------------
+docs_015 = [(111, "lets test foo bar baz bar stuff"), (222, "bar baz foo"), (333, "foo baz bar"), (444, "i i did it it"),
+            (555, "zee lord of zee rings"), (666, "Braun 370-2 3702 370 2 Braun Series 3 - 370 Shaver")]
+m15 = model("test_015")
+ph15 = [["phrase", [["bar", 1], ["baz", 2], ["bar", 3]]], ["phrase", [["foo", 1], ["bar", 2], ["baz", 3], ["bar", 4]]],
+        ["phrase", [["i", 1], ["did", 2], ["it", 3]]], ["phrase", [["zee", 1], ["lord", 2], ["of", 3], ["zee", 4], ["rings", 5]]]]
+case = {"name": "test_015", "fields": ["body"], "min_word_len": 1, "stopwords": ["2"],
+        "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_015], "queries": []}
+for qi in range(8):
+    case["queries"].append({"text": m15[qi]["query"], "tree": ph15[qi % 4], "ranker": "proximity" if qi < 4 else "proximity_bm25", "expect": api_expect(m15[qi])})
+braun = ["and"] + [["kw", w, p] for w, p in [("braun", 1), ("370", 2), ("3702", 4), ("370", 5), ("braun", 7), ("series", 8), ("3", 9), ("370", 10), ("shaver", 11)]]
+case["queries"].append({"text": m15[8]["query"], "tree": braun, "ranker": "proximity_bm25", "expect": api_expect(m15[8])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_030 "ext2 ranking" (stopwords a/the/and/of, min_word_len=3): AND queries under PROXIMITY_BM25, a stop word inside the query
+# keeps its atom position
+# ---------------------------------------------------------------------------------------------
+docs_030 = [(1, "one two three"), (2, "one two three four"), (3, "one then two then three then four"),
+            (4, "senior pastor of Riverside church"), (5, "senior pastor and the Riverside church")]
+m30 = model("test_030")
+case = {"name": "test_030", "fields": ["body"], "min_word_len": 3, "stopwords": ["a", "the", "and", "of"],
+        "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_030], "queries": []}
+case["queries"].append({"text": m30[0]["query"], "tree": ["and", ["kw", "one", 1], ["kw", "two", 2], ["kw", "three", 3]],
+                        "ranker": "proximity_bm25", "expect": api_expect(m30[0], "one two three")})
+case["queries"].append({"text": m30[1]["query"], "tree": ["and", ["kw", "senior", 1], ["kw", "pastor", 2], ["kw", "riverside", 4], ["kw", "church", 5]],
+                        "ranker": "proximity_bm25", "expect": api_expect(m30[1], "senior pastor of riverside church")})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_094 "proximity queries": 257 repetitions of `one two` in one document (BYTE LCS wraps: weight 255500), 6-keyword proximities
+# in and out of query order
+# ---------------------------------------------------------------------------------------------
+docs_094 = [(1, "one two " * 257), (2, "two one"), (3, "aa bb cc dd ee ff")]
+m94 = model("test_094")
+case = {"name": "test_094", "fields": ["body"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_094], "queries": []}
+for qi, words in [(0, ["one", "two"]), (1, ["aa", "bb", "cc", "dd", "ee", "ff"]), (2, ["aa", "bb", "dd", "cc", "ee", "ff"]), (3, ["aa", "bb", "ee", "ff"])]:
+    case["queries"].append({"text": m94[qi]["query"], "tree": ["prox", 10, [[w, i + 1] for i, w in enumerate(words)]],
+                            "ranker": "proximity_bm25", "expect": api_expect(m94[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_059 "phrase boundaries" (phrase_boundary = '.', phrase_boundary_step = 10: `one. two` puts 10 extra positions between the
+# words), index `test`: field-start anchor, phrase and proximity across the boundary
+# ---------------------------------------------------------------------------------------------
+docs_059 = [(1, "first."), (2, " second"), (3, "one. two three"), (4, "one two three")]
+m59 = model("test_059")
+case = {"name": "test_059", "fields": ["body"], "min_word_len": 1, "phrase_boundary": ".", "phrase_boundary_step": 10,
+        "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_059], "queries": []}
+for qi, tree in [(0, ["kw", "second", 1, ALL, {"start": 1}]), (1, ["phrase", [["one", 1], ["two", 2]]]),
+                 (2, ["prox", 10, [["one", 1], ["two", 2]]]), (3, ["prox", 11, [["one", 1], ["two", 2]]])]:
+    case["queries"].append({"text": m59[qi]["query"], "tree": tree, "ranker": "proximity_bm25", "expect": api_expect(m59[qi])})
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------

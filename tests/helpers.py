@@ -117,8 +117,9 @@ def _is_word_char(ch):
     return ch.isascii() and (ch.isalnum() or ch == "_") or 0x410 <= o <= 0x44F
 
 
-def tokenize(text, min_word_len=1, stopwords=()):
-    """-> [(keyword, pos)], pos 1-based; overshort tokens and stop words consume a position (overshort_step=1, stopword_step=1)"""
+def tokenize(text, min_word_len=1, stopwords=(), phrase_boundary="", phrase_boundary_step=0):
+    """-> [(keyword, pos)], pos 1-based; overshort tokens and stop words consume a position (overshort_step=1, stopword_step=1);
+    a phrase_boundary character followed by a separator (or the end) advances the position by phrase_boundary_step"""
     out, pos, cur = [], 0, ""
 
     def flush():
@@ -129,7 +130,7 @@ def tokenize(text, min_word_len=1, stopwords=()):
                 out.append((cur, pos))
             cur = ""
 
-    for ch in text:
+    for i, ch in enumerate(text):
         if _is_cjk(ch):
             flush()
             pos += 1
@@ -138,6 +139,8 @@ def tokenize(text, min_word_len=1, stopwords=()):
             cur += ch.lower()
         else:
             flush()
+            if ch in phrase_boundary and (i + 1 == len(text) or not (_is_word_char(text[i + 1]) or _is_cjk(text[i + 1]))):
+                pos += phrase_boundary_step
     flush()
     return out
 
@@ -179,7 +182,8 @@ def load_golden():
 def build_golden_index(case, prefix):
     docs = []
     for d in case["docs"]:
-        docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ())) for t in d["fields"]], "attrs": d.get("attrs", [])})
+        docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ()), case.get("phrase_boundary", ""), case.get("phrase_boundary_step", 0))
+                                                for t in d["fields"]], "attrs": d.get("attrs", [])})
     M.build_index(prefix, case["fields"], docs, attr_names=case.get("attrs", ()))
 
 
