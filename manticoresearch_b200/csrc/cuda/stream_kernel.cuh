@@ -1,8 +1,10 @@
-// K2/K3/K6/K7/K8 for doc-only queries: the warp-autonomous streaming evaluator.
+// K2/K3/K6/K7/K8 for doc-only queries: the warp-autonomous streaming evaluators (three instantiations of one kernel).
 //
 // A work item = (query, rowid range). The CTA cuts the range into 8 contiguous sub-ranges, one per warp; every warp walks
-// its sub-range in 256-row mini-tiles with private dense vectors in shared memory and NO CTA-wide barrier inside the
-// tile program, so that an SM has 30-60 independent latency chains in flight instead of one per CTA:
+// its sub-range in 256- or 512-row mini-tiles with NO CTA-wide barrier inside a mini-tile, so that an SM has 24-32 independent
+// latency chains in flight instead of one per CTA.
+//
+// MODE 0 (general tile program, launch classes 0 and 3): private dense vectors {tfidf, fields, cnt} in shared memory;
 //   - hot keywords: 8 rows per lane straight from the batch's dense store (u16 per row);
 //   - sparse keywords: a per-(warp, keyword) cursor over the resident block table; the current 32-doc block is decoded once
 //     per warp into an L1/L2-resident cache and re-used by all the mini-tiles it spans; AND chains test the candidates'
@@ -10,12 +12,19 @@
 //   - mini-tiles that no document-originating keyword touches are jumped over using the exact next rowid;
 //   - survivors are ranked per lane and pushed into the CTA's candidate pool; warps meet at one barrier every 8 mini-tiles,
 //     where the pool is compacted to K by the CTA radix select if it could overflow.
+// MODE 1 / 2 (bound pass + exact pass, launch classes 5 and 6): no vectors at all. A top-K query has to COUNT every
+//   matching row but only has to RANK rows that can still enter the top K: an integer pass over 8 consecutive rows per lane (one
+//   128-bit load per hot keyword) yields presence, matched fields and an upper bound of the weight from the store's per-row tf
+//   classes; only rows whose bound reaches the K-th best weight so far get their exact TF*IDF (one lane per row, 32 at a time).
+//   MODE 1 = pure OR programs in relevance order without filters (the lean instantiation); MODE 2 adds OR-of-AND-groups programs
+//   (hot groups: ANDed presence flags gate the group's sums; groups driven by one sparse keyword), filters inside the bound pass
+//   and attribute / rowid sort keys. The pool is compacted on demand instead of at fixed rounds.
 // Semantics per op are those of eval_kernel (ApplyTermOp): ExtTerm_T / ExtAnd_c / ExtMultiAnd_T / ExtOr_c / ExtAndNot_c /
 // ExtMaybe_c of src/searchnode.cpp, TF*IDF in the reference's association order.
 #pragma once
 // (included from kernels.cu inside namespace mgpu: uses its DecodeBlock / ApplyTermOp / CtaSelectTopK / MakeKey helpers)
 
-static const int OR_LIST_CAP = 512*MAX_LEAVES;	///< register-OR path: a mini-tile holds at most 512 postings of each of <=16 sparse keywords
+static const int OR_LIST_CAP = 512*MAX_LEAVES;	///< MODE 1 / 2: a mini-tile holds at most 512 postings of each of <=16 sparse keywords
 static const int CHUNK_K = 8;				///< rows per lane handled at once (register arrays)
 static const int STREAM_POOL_SLACK = 32768;	///< candidates one round (SYNC_MINIS mini-tiles per warp) can add to the pool
 
