@@ -1156,6 +1156,191 @@ struct NWayNode_c : Node_c, FSM
 // factory: ExtNode_i::Create, src/searchnode.cpp:1599-1811
 //////////////////////////////////////////////////////////////////////////
 
+/// ExtQuorum_c, src/searchnode.cpp:4319-4650: a document matches when at least m_iThresh of the keywords occur in it (a keyword
+/// repeated in the query counts as often as it is repeated, but only up to its number of hits in the document).
+/// The children vector keeps the reference's dynamic order: keywords sorted by query position, an exhausted keyword is removed
+/// with RemoveFast (the last one takes its slot), and TF*IDF is summed in that order.
+struct QuorumNode_c : Node_c
+{
+	struct Child_t
+	{
+		std::shared_ptr<TermNode_c> m_pTerm;
+		int m_iCount = 1;
+		ExtDoc_t m_tDoc { INVALID_ROWID, 0, 0.0f };
+		bool m_bHas = false;
+	};
+	std::vector<Child_t> m_dInitial, m_dChildren;
+	int m_iThresh = 1;
+	bool m_bHasDupes = false;
+	bool m_bWarm = false;
+	int m_iQuorumLeft = 0;
+	std::vector<ExtHit_t> m_dCurHits, m_dTmp;
+
+	/// ctor, :4342-4404: fold repeated keywords into one child with a count (the first occurrence stays), sort back by query position
+	void Init ( std::vector<TermNode_c*> & dTerms, int iThresh )
+	{
+		m_iThresh = std::max ( iThresh, 1 );
+		m_iAtomPos = dTerms[0]->m_iAtomPos;
+		for ( size_t i=0; i<dTerms.size(); ++i )
+		{
+			size_t iParent = m_dInitial.size();
+			for ( size_t j=0; j<m_dInitial.size(); ++j )
+				if ( m_dInitial[j].m_pTerm->m_tQword.m_sWord==dTerms[i]->m_tQword.m_sWord )
+					iParent = j;
+			if ( iParent<m_dInitial.size() )
+			{
+				m_dInitial[iParent].m_iCount++;
+				m_bHasDupes = true;
+				delete dTerms[i];
+			} else
+			{
+				Child_t t;
+				t.m_pTerm.reset ( dTerms[i] );
+				m_dInitial.push_back ( t );
+			}
+		}
+		std::sort ( m_dInitial.begin(), m_dInitial.end(), [] ( const Child_t & a, const Child_t & b ) { return a.m_pTerm->m_iAtomPos<b.m_pTerm->m_iAtomPos; } );
+		m_dChildren = m_dInitial;
+	}
+
+	void RemoveFast ( size_t i )
+	{
+		m_dChildren[i] = m_dChildren.back();
+		m_dChildren.pop_back();
+	}
+	bool Pull ( Child_t & t )
+	{
+		t.m_bHas = t.m_pTerm->Next ( t.m_tDoc );
+		return t.m_bHas;
+	}
+	/// CountQuorum, :4574-4595
+	int CountQuorum ( bool bFixDupes )
+	{
+		if ( !m_bHasDupes )
+			return (int)m_dChildren.size();
+		int iSum = 0;
+		bool bHasDupes = false;
+		for ( auto & t : m_dChildren )
+		{
+			iSum += t.m_iCount;
+			bHasDupes |= ( t.m_iCount>1 );
+		}
+		m_bHasDupes = bFixDupes ? bHasDupes : m_bHasDupes;
+		return iSum;
+	}
+	/// CollectMatchingHits, :4602-4650; the hits of every keyword on the row end up in m_dCurHits
+	bool CollectMatchingHits ( RowID_t tRowID )
+	{
+		m_dCurHits.clear();
+		int iQuorum = 0;
+		bool bCounting = m_bHasDupes;
+		for ( auto & t : m_dChildren )
+		{
+			if ( !t.m_bHas || t.m_tDoc.m_tRowID!=tRowID )
+				continue;
+			m_dTmp.clear();
+			t.m_pTerm->CollectHits ( m_dTmp );
+			if ( bCounting )
+			{
+				// matched hits count only up to the keyword's repeat count
+				iQuorum += std::min<int> ( t.m_iCount, (int)m_dTmp.size() );
+				if ( iQuorum>=m_iThresh )
+					bCounting = false;
+			}
+			m_dCurHits.insert ( m_dCurHits.end(), m_dTmp.begin(), m_dTmp.end() );
+		}
+		if ( m_bHasDupes && iQuorum<m_iThresh )
+		{
+			m_dCurHits.clear();
+			return false;
+		}
+		// CollectHits: QuorumCmpHitPos_fn, :4543-4565
+		std::stable_sort ( m_dCurHits.begin(), m_dCurHits.end(), [] ( const ExtHit_t & a, const ExtHit_t & b )
+		{
+			DWORD uA = HitPosWithField ( a.m_uHitpos ), uB = HitPosWithField ( b.m_uHitpos );
+			return uA<uB || ( uA==uB && a.m_uQuerypos<b.m_uQuerypos );
+		});
+		return true;
+	}
+
+	/// GetDocsChunk, :4466-4541, one document per call
+	bool Next ( ExtDoc_t & tDoc ) override
+	{
+		if ( !m_bWarm )
+		{
+			m_bWarm = true;
+			for ( size_t i=0; i<m_dChildren.size(); ++i )
+				if ( !Pull ( m_dChildren[i] ) )
+				{
+					RemoveFast ( i );
+					--i;
+				}
+			m_iQuorumLeft = CountQuorum ( true );
+		}
+		while ( m_iQuorumLeft>=m_iThresh )
+		{
+			ExtDoc_t tCand { INVALID_ROWID, 0, 0.0f };
+			int iQuorum = 0;
+			for ( auto & t : m_dChildren )
+			{
+				if ( t.m_tDoc.m_tRowID<tCand.m_tRowID )
+				{
+					tCand = t.m_tDoc;
+					iQuorum = t.m_iCount;
+				} else if ( t.m_tDoc.m_tRowID==tCand.m_tRowID )
+				{
+					tCand.m_uDocFields |= t.m_tDoc.m_uDocFields;
+					tCand.m_fTFIDF += t.m_tDoc.m_fTFIDF;
+					iQuorum += t.m_iCount;
+				}
+			}
+			const bool bMatch = iQuorum>=m_iThresh && CollectMatchingHits ( tCand.m_tRowID );
+
+			// advance the children that sat on the candidate
+			const size_t nBefore = m_dChildren.size();
+			for ( size_t i=0; i<m_dChildren.size(); ++i )
+			{
+				if ( m_dChildren[i].m_tDoc.m_tRowID!=tCand.m_tRowID )
+					continue;
+				if ( !Pull ( m_dChildren[i] ) )
+				{
+					RemoveFast ( i );
+					--i;
+				}
+			}
+			if ( nBefore!=m_dChildren.size() )
+				m_iQuorumLeft = CountQuorum ( false );
+			if ( bMatch )
+			{
+				tDoc = tCand;
+				return true;
+			}
+		}
+		return false;
+	}
+	void HintRowID ( RowID_t tRowID ) override
+	{
+		for ( auto & t : m_dChildren )
+			t.m_pTerm->HintRowID ( tRowID );
+	}
+	void CollectHits ( std::vector<ExtHit_t> & dHits ) override
+	{
+		dHits.insert ( dHits.end(), m_dCurHits.begin(), m_dCurHits.end() );
+	}
+	int GetQwords ( QwordsHash_t & h ) override
+	{
+		int iMax = -1;
+		for ( auto & t : m_dChildren )
+			iMax = std::max ( iMax, t.m_pTerm->GetQwords ( h ) );
+		return iMax;
+	}
+	void SetQwordsIDF ( const QwordsHash_t & h ) override
+	{
+		for ( auto & t : m_dChildren )
+			t.m_pTerm->SetQwordsIDF ( h );
+	}
+};
+
 struct Setup_t
 {
 	const Index_t * m_pIndex;
@@ -1259,14 +1444,18 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 		case MGPU_OP_PROXIMITY:	return CreateMultiNode<FSMproximity_c> ( tNode, tSetup );
 		case MGPU_OP_QUORUM:
 			{
-				// degenerate quorums only (src/searchnode.cpp:1638-1688): threshold >= words -> AND, threshold 1 -> OR;
-				// keywords sorted by doc count, chained with ExtAnd_c / ExtOr_c. A real ExtQuorum_c is out of scope.
+				// src/searchnode.cpp:1638-1688: threshold >= words (or > 256 words) -> AND chain, threshold 1 -> OR chain over the keywords
+				// sorted by doc count; everything else (incl. a percent threshold that rounds to 0) is a real ExtQuorum_c
 				const int iCount = tNode.n_words, iThr = tNode.oparg;
 				const bool bOr = ( iThr<iCount && iCount<=256 && iThr==1 );
 				if ( iThr<iCount && iCount<=256 && iThr!=1 )
 				{
-					tSetup.m_iError = MGPU_E_UNSUPPORTED;
-					return nullptr;
+					std::vector<TermNode_c*> dWords;
+					for ( int i=0; i<iCount; ++i )
+						dWords.push_back ( CreateTerm ( tNode, tNode.first_word+i, tSetup ) );
+					QuorumNode_c * pQuorum = new QuorumNode_c;
+					pQuorum->Init ( dWords, iThr );
+					return pQuorum;
 				}
 				std::vector<Node_c*> dTerms;
 				for ( int i=0; i<iCount; ++i )

@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,055,059,094,114,116,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,054,055,059,094,114,116,138,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -196,6 +196,43 @@ case = {"name": "test_059", "fields": ["body"], "min_word_len": 1, "phrase_bound
 for qi, tree in [(0, ["kw", "second", 1, ALL, {"start": 1}]), (1, ["phrase", [["one", 1], ["two", 2]]]),
                  (2, ["prox", 10, [["one", 1], ["two", 2]]]), (3, ["prox", 11, [["one", 1], ["two", 2]]])]:
     case["queries"].append({"text": m59[qi]["query"], "tree": tree, "ranker": "proximity_bm25", "expect": api_expect(m59[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_054 "quorum", index `test`: real ExtQuorum_c nodes (src/searchnode.cpp:4319-4650) incl. repeated keywords and percent
+# thresholds (the caller resolves "/0.59" to an absolute count: ExtQuorum_c::GetThreshold with the parser's truncated percent;
+# 0 = "rounds to nothing", which still builds a quorum node with threshold 1). The CUDA path implements only the degenerate
+# quorums (threshold 1 -> OR, threshold >= words -> AND) and must answer MGPU_E_UNSUPPORTED for the others: "gpu_unsupported".
+# ---------------------------------------------------------------------------------------------
+docs_054 = [(1, "hello world"), (2, "one two three four five")]      # source test1: document_id in (1, 2)
+m54 = model("test_054")
+case = {"name": "test_054", "fields": ["text"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1]]} for d in docs_054], "queries": []}
+for qi, thr, words in [(0, 1, "hello heaven"), (1, 2, "hello from above"), (2, 3, "one two foo bar"), (3, 3, "one two two bar"),
+                       (4, 2, "one two two bar"), (5, 3, "two two one three"), (6, 3, "two two one foo"), (18, 0, "one world"),
+                       (19, 2, "five tree oak one two hive"), (20, 3, "five tree oak one two hive"), (21, 4, "five tree oak one two hive")]:
+    ws = words.split()
+    q = {"text": m54[qi]["query"].strip(), "tree": ["quorum", thr, [[w, i + 1] for i, w in enumerate(ws)]], "ranker": "proximity_bm25",
+         "expect": api_expect(m54[qi])}
+    if thr != 1 and thr < len(ws):
+        q["gpu_unsupported"] = True
+    case["queries"].append(q)
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_138 "quorum vs decreased matched word": keywords run out while the quorum node walks on (ExtQuorum_c drops an exhausted
+# keyword with RemoveFast and recounts what is left); test2 holds 512 copies of `world space` = several document chunks
+# ---------------------------------------------------------------------------------------------
+data_138 = {1: "world space", 2: "one", 3: "two", 4: "world", 5: "space", 6: "unused1", 7: "unused2"}
+m138 = model("test_138")
+q138 = ["quorum", 2, [[w, i + 1] for i, w in enumerate("one two unused1 unused2 space world".split())]]
+case = {"name": "test_138_test1", "fields": ["text"], "min_word_len": 1,
+        "docs": [{"id": k, "fields": [v]} for k, v in data_138.items()], "queries": []}
+case["queries"].append({"text": m138[0]["query"], "tree": q138, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m138[0])})
+out["cases"].append(case)
+case = {"name": "test_138_test2", "fields": ["text"], "min_word_len": 1,
+        "docs": [{"id": i, "fields": [data_138[1]]} for i in range(1, 513)] + [{"id": 600 + k, "fields": [v]} for k, v in data_138.items()], "queries": []}
+case["queries"].append({"text": m138[1]["query"], "tree": q138, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m138[1])})
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------
