@@ -1116,6 +1116,215 @@ struct FSMproximity_c
 	}
 };
 
+/// FSMmultinear_c, src/searchnode.cpp:680-720, 4080-4316: `a NEAR/N b NEAR/N c` (children are nodes: keywords, phrases, groups, other
+/// NEAR nodes). Hits arrive ordered by position; m_uNodepos tells which child a hit belongs to. A chain grows while every next hit
+/// starts within N positions after the previous one ended and belongs to a child not seen in the chain yet; two children: every
+/// adjacent pair is emitted (chains may overlap), more children: the chain is emitted when all of them are in and then starts over.
+/// Quirks kept: ResetFSM() leaves the smallest query position seen so far (n-way chains) and the node-position list alone.
+struct FSMmultinear_c
+{
+	int m_iNear = 1;
+	DWORD m_uPrelastP = 0, m_uPrelastML = 0, m_uPrelastSL = 0, m_uPrelastW = 0;
+	DWORD m_uLastP = 0, m_uLastML = 0, m_uLastSL = 0, m_uLastW = 0;
+	DWORD m_uWordsExpected = 0, m_uWeight = 0, m_uFirstHit = 0;
+	WORD m_uFirstNpos = 0, m_uFirstQpos = 65535;
+	std::vector<WORD> m_dNpos;
+	std::vector<ExtHit_t> m_dRing;
+	int m_iRing = 0;
+	bool m_bTwofer = false, m_bQposMask = false;
+
+	void InitNear ( int nNodes, int iNear, bool bQposMask )
+	{
+		m_iNear = iNear;
+		m_uWordsExpected = (DWORD)nNodes;
+		m_bQposMask = bQposMask;
+		m_bTwofer = ( nNodes==2 );
+		if ( !m_bTwofer )
+			m_dRing.resize ( nNodes );
+	}
+	void ResetFSM()				{ m_iRing = 0; m_uLastP = 0; m_uPrelastP = 0; }
+	int RingTail() const		{ return ( m_iRing + (int)m_dNpos.size() - 1 ) % (int)m_uWordsExpected; }
+	void Add2Ring ( const ExtHit_t * pHit )	{ if ( !m_bTwofer ) m_dRing[RingTail()] = *pHit; }
+	void ShiftRing()			{ if ( ++m_iRing==(int)m_uWordsExpected ) m_iRing = 0; }
+	void StartChain ( const ExtHit_t * pHit, DWORD uPos )
+	{
+		m_uFirstHit = m_uLastP = uPos;
+		m_uLastML = pHit->m_uMatchlen;
+		m_uLastSL = pHit->m_uSpanlen;
+		m_uWeight = m_uLastW = pHit->m_uWeight;
+	}
+
+	bool HitFSM ( const ExtHit_t * pHit, std::vector<ExtHit_t> & dHits )
+	{
+		const DWORD uPos = HitPosWithField ( pHit->m_uHitpos );
+		const WORD uNpos = pHit->m_uNodepos, uQpos = pHit->m_uQuerypos;
+
+		// a second hit at the position of the last one (an OR child, `a NEAR/2 a`...), :4103-4134
+		if ( m_uLastP==uPos )
+		{
+			if ( m_bTwofer && uNpos<m_uFirstNpos )
+			{
+				m_uFirstQpos = uQpos;	// keep the leftmost child of the query
+				m_uFirstNpos = uNpos;
+				return false;
+			}
+			if ( !m_bTwofer && uNpos<m_dRing[RingTail()].m_uNodepos )
+			{
+				if ( !std::binary_search ( m_dNpos.begin(), m_dNpos.end(), uNpos ) )
+				{
+					auto it = std::lower_bound ( m_dNpos.begin(), m_dNpos.end(), m_dRing[RingTail()].m_uNodepos );
+					*it = uNpos;
+					std::sort ( m_dNpos.begin(), m_dNpos.end() );
+					m_dRing[RingTail()].m_uNodepos = uNpos;
+					m_dRing[RingTail()].m_uQuerypos = uQpos;
+				}
+				return false;
+			}
+			if ( m_uPrelastP && m_uLastML<pHit->m_uMatchlen )
+			{
+				// the last hit was a part of this longer one: step back to the one before it
+				m_uLastML = m_uPrelastML;
+				m_uLastSL = m_uPrelastSL;
+				m_uFirstHit = m_uLastP = m_uPrelastP;
+				m_uWeight = m_uWeight - m_uLastW + m_uPrelastW;
+			} else
+				return false;
+		}
+
+		// too far from the previous hit (or no previous hit): a new chain starts here, :4137-4154
+		if ( m_uLastP==0 || ( m_uLastP + m_uLastML + m_iNear )<=uPos )
+		{
+			StartChain ( pHit, uPos );
+			if ( m_bTwofer )
+			{
+				m_uFirstQpos = uQpos;
+				m_uFirstNpos = uNpos;
+			} else
+			{
+				m_dNpos.assign ( 1, uNpos );
+				Add2Ring ( pHit );
+			}
+			return false;
+		}
+
+		if ( m_bTwofer )
+		{
+			// overlapping hits of different length: restart from the new one, :4160-4172
+			if ( ( m_uFirstHit + m_uLastML )>uPos && ( m_uFirstHit + m_uLastML )<( uPos + pHit->m_uMatchlen ) && m_uLastML!=pHit->m_uMatchlen )
+			{
+				StartChain ( pHit, uPos );
+				m_uFirstQpos = uQpos;
+				m_uFirstNpos = uNpos;
+				return false;
+			}
+			// the same child again: it becomes the head of the chain, :4173-4190
+			if ( uNpos==m_uFirstNpos )
+			{
+				if ( m_uLastP<uPos )
+				{
+					m_uPrelastML = m_uLastML;
+					m_uPrelastSL = m_uLastSL;
+					m_uPrelastP = m_uLastP;
+					m_uPrelastW = pHit->m_uWeight;
+					m_uFirstHit = m_uLastP = uPos;
+					m_uLastML = pHit->m_uMatchlen;
+					m_uLastSL = pHit->m_uSpanlen;
+					m_uWeight = m_uLastW = m_uPrelastW;
+					m_uFirstQpos = uQpos;
+					m_uFirstNpos = uNpos;
+				}
+				return false;
+			}
+		} else
+		{
+			// n-way: the chain keeps a sorted list of the children it holds and a ring of their hits, :4193-4247
+			if ( uNpos<m_dNpos.front() )
+			{
+				m_uFirstQpos = std::min ( m_uFirstQpos, uQpos );
+				m_dNpos.insert ( m_dNpos.begin(), uNpos );
+			} else if ( uNpos>m_dNpos.back() )
+			{
+				m_uFirstQpos = std::min ( m_uFirstQpos, uQpos );
+				m_dNpos.push_back ( uNpos );
+			} else if ( uNpos!=m_dNpos.front() && uNpos!=m_dNpos.back() )
+			{
+				int iEnd = (int)m_dNpos.size(), iStart = 0;
+				while ( iEnd-iStart>1 )
+				{
+					const int iMid = ( iStart+iEnd )/2;
+					if ( uNpos==m_dNpos[iMid] )
+					{
+						const ExtHit_t & tHead = m_dRing[m_iRing];
+						if ( uNpos==tHead.m_uNodepos )
+						{
+							// the child at the head of the chain again: drop the head
+							m_uWeight -= tHead.m_uWeight;
+							m_uFirstHit = HitPosWithField ( tHead.m_uHitpos );
+							ShiftRing();
+						} else if ( uNpos==m_dRing[RingTail()].m_uNodepos )
+							m_uWeight -= m_dRing[RingTail()].m_uWeight;	// the child at the tail again: the new hit replaces it
+						else
+							return false;
+					}
+					if ( uNpos<m_dNpos[iMid] )
+						iEnd = iMid;
+					else
+						iStart = iMid;
+				}
+				m_dNpos.insert ( m_dNpos.begin()+iEnd, uNpos );
+				m_uFirstQpos = std::min ( m_uFirstQpos, uQpos );
+			} else if ( uNpos==m_dRing[m_iRing].m_uNodepos )
+			{
+				m_uWeight -= m_dRing[m_iRing].m_uWeight;
+				m_uFirstHit = HitPosWithField ( m_dRing[m_iRing].m_uHitpos );
+				ShiftRing();
+			} else if ( uNpos==m_dRing[RingTail()].m_uNodepos )
+				m_uWeight -= m_dRing[RingTail()].m_uWeight;
+			else
+				return false;
+		}
+
+		m_uWeight += pHit->m_uWeight;
+		m_uLastML = pHit->m_uMatchlen;
+		m_uLastSL = pHit->m_uSpanlen;
+		Add2Ring ( pHit );
+
+		// the whole chain is there: emit it, :4254-4286
+		if ( m_bTwofer || m_uWordsExpected==(DWORD)m_dNpos.size() )
+		{
+			ExtHit_t t;
+			t.m_tRowID = pHit->m_tRowID;
+			t.m_uHitpos = m_uFirstHit;
+			t.m_uNodepos = 0;
+			t.m_uMatchlen = (WORD)( uPos - m_uFirstHit + m_uLastML );
+			t.m_uWeight = m_uWeight;
+			m_uPrelastP = 0;
+			t.m_uQuerypos = std::min ( m_uFirstQpos, pHit->m_uQuerypos );
+			if ( m_bTwofer )
+			{
+				// two children may overlap: the chain shifts instead of starting over
+				t.m_uSpanlen = 2;
+				t.m_uQposMask = 1u<<( std::max ( m_uFirstQpos, pHit->m_uQuerypos ) - t.m_uQuerypos );
+				m_uFirstHit = m_uLastP = uPos;
+				m_uWeight = pHit->m_uWeight;
+				m_uFirstQpos = pHit->m_uQuerypos;
+			} else
+			{
+				t.m_uSpanlen = (WORD)m_dNpos.size();
+				t.m_uQposMask = 0;
+				m_uLastP = 0;
+				if ( m_bQposMask && t.m_uSpanlen>1 )
+					for ( WORD uN : m_dNpos )
+						t.m_uQposMask |= 1u<<( uN - t.m_uQuerypos );
+			}
+			dHits.push_back ( t );
+			return true;
+		}
+		m_uLastP = uPos;
+		return false;
+	}
+};
+
 /// ExtNWay_T<FSM>, src/searchnode.cpp:3767-3848
 template<typename FSM>
 struct NWayNode_c : Node_c, FSM
@@ -1546,6 +1755,53 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 	}
 	if ( bAndTerms )
 		return CreateNode ( pChildren[0], tSetup );	// degenerate 1-child AND: generic create returns the child
+
+	if ( tNode.op==MGPU_OP_NEAR )
+	{
+		// CreateMultiNode<ExtMultinear_c> (children branch, src/searchnode.cpp:933-978) + ExtNWay_T ctor / ConstructNode (:3767-3802):
+		// the children, sorted by doc count, are chained with ExtAnd_c that stamp each hit with its child's 1-based position
+		std::vector<Node_c*> dNodes;
+		for ( int i=0; i<nChildren; ++i )
+		{
+			Node_c * p = CreateNode ( pChildren[i], tSetup );
+			if ( tSetup.m_iError!=MGPU_OK )
+			{
+				for ( auto q2 : dNodes ) delete q2;
+				return nullptr;
+			}
+			if ( p )
+				dNodes.push_back ( p );
+		}
+		if ( dNodes.size()<2 )
+		{
+			for ( auto q2 : dNodes ) delete q2;
+			return nullptr;	// "can't create phrase node, hitlists unavailable"
+		}
+		std::vector<WORD> dPositions ( dNodes.size() );
+		for ( size_t i=0; i<dPositions.size(); ++i )
+			dPositions[i] = (WORD)i;
+		RefSort ( dPositions, [&] ( WORD a, WORD b ) { return dNodes[a]->GetDocsCount()<dNodes[b]->GetDocsCount(); } );
+		WORD uLPos = dPositions[0];
+		Node_c * pChain = dNodes[uLPos++];
+		AndNode_c * pLastAnd = nullptr;
+		for ( size_t i=1; i<dNodes.size(); ++i )
+		{
+			WORD uRPos = dPositions[i];
+			pLastAnd = new AndNode_c;
+			pLastAnd->m_pLeft.reset ( pChain );
+			pLastAnd->m_pRight.reset ( dNodes[uRPos++] );
+			pLastAnd->m_uNodePosL = uLPos;
+			pLastAnd->m_uNodePosR = uRPos;
+			uLPos = 0;
+			pChain = pLastAnd;
+		}
+		pLastAnd->m_bQPosReverse = true;
+		auto * pNear = new NWayNode_c<FSMmultinear_c>;
+		pNear->m_pNode.reset ( pChain );
+		pNear->m_iAtomPos = dNodes[0]->m_iAtomPos;
+		pNear->InitNear ( (int)dNodes.size(), tNode.oparg, false );
+		return pNear;
+	}
 
 	if ( tNode.op==MGPU_OP_AND )
 	{

@@ -10,7 +10,7 @@ nodes with word lists, atom positions 1,2,3.. in query order, src/sphinxquery.cp
 because the parser itself needs bison and is out of scope.
 
 Tree notation: ["kw", word, atompos, fieldmask?], ["and"|"or"|"andnot"|"maybe", child...],
-["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]].
+["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...].
 """
 import json
 import os
@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,054,055,059,094,114,116,138,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,054,055,059,094,114,115,116,138,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -233,6 +233,52 @@ out["cases"].append(case)
 case = {"name": "test_138_test2", "fields": ["text"], "min_word_len": 1,
         "docs": [{"id": i, "fields": [data_138[1]]} for i in range(1, 513)] + [{"id": 600 + k, "fields": [v]} for k, v in data_138.items()], "queries": []}
 case["queries"].append({"text": m138[1]["query"], "tree": q138, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m138[1])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_115 "NEAR syntax", index `idx` (documents with id < 100; blend_chars '-' only adds whole-token variants, the parts keep the
+# positions a plain split gives them, so '-' is indexed as a separator here). NEAR trees arrive in the shape TransformNear
+# (src/sphinx.cpp:15046-15100) leaves them in: `(a b c) NEAR/3 d` is the 4-way `a NEAR/3 b NEAR/3 c NEAR/3 d`; equal distances chain
+# into one n-ary node (XQParser_t::AddOp), different ones nest. Oracle only (FSMmultinear_c); the CUDA path must refuse NEAR.
+# ---------------------------------------------------------------------------------------------
+import re  # noqa: E402
+xml115 = open(os.path.join(REF, "test_115", "test.xml"), encoding="utf-8").read()
+ins115 = xml115[xml115.index("<db_insert>"):xml115.index("</db_insert>")]
+docs_115 = [(int(m.group(1)), m.group(2)) for m in re.finditer(r"\(\s*(\d+),\s*'((?:[^']|'')*)'\s*\)", ins115) if int(m.group(1)) < 100]
+docs_115.append((21, "zwei " + "oy vey ho ho ho " * 1024))
+docs_115.sort()
+assert [d[0] for d in docs_115] == list(range(1, 18)) + [20, 21, 22]
+m115 = model("test_115")
+
+
+def K(w, p):
+    return ["kw", w, p]
+
+
+def PH(ws, p0):
+    return ["phrase", [[w, p0 + i] for i, w in enumerate(ws)]]
+
+
+q115 = [(0, ["near", 2, PH("ab", 1), PH("cd", 3)]),
+        (1, ["near", 2, PH("cd", 1), PH("ab", 3)]),
+        (2, ["and", K("a", 1), ["near", 2, K("b", 2), K("c", 3)], K("d", 4)]),
+        (3, ["near", 2, ["near", 5, ["near", 2, K("a", 1), K("b", 2)], K("c", 3)], K("d", 4)]),
+        (4, ["near", 3, K("a", 1), K("b", 2), K("c", 3), K("d", 4)]),
+        (5, ["near", 3, K("a", 1), K("d", 2), K("b", 3), K("c", 4)]),
+        (6, ["near", 3, K("a", 1), K("b", 2), K("c", 3), K("d", 4)]),
+        (7, ["near", 2, K("burden", 1), K("financial", 2), K("share", 3)]),
+        (8, ["near", 2, K("burden", 1), K("share", 2), K("financial", 3)]),
+        (9, ["near", 2, K("share", 1), K("financial", 2), K("burden", 3)]),
+        (10, ["near", 2, K("financial", 1), K("share", 2), K("burden", 3)]),
+        (11, ["near", 2, PH("ab", 1), PH("cd", 3), PH("fg", 5)]),
+        (12, ["near", 3, K("a", 1), K("b", 2), K("c", 3), K("d", 4)]),
+        (18, ["near", 3, K("five", 1), K("one", 2)]),
+        (19, ["near", 3, K("six", 1), K("one", 2)]),
+        (20, ["near", 3, ["or", K("five", 1), K("six", 2)], K("one", 3)])]
+case = {"name": "test_115", "fields": ["title"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1].replace("-", " ")]} for d in docs_115], "queries": []}
+for qi, tree in q115:
+    case["queries"].append({"text": m115[qi]["query"].strip(), "tree": tree, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m115[qi])})
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------
