@@ -1550,6 +1550,156 @@ struct QuorumNode_c : Node_c
 	}
 };
 
+/// ExtOrder_c, src/searchnode.cpp:4657-4935: `a << b << c`. A document has to hold every child; its hits are walked in position order
+/// (the lowest child wins a tie) and two trackers, the longest prefix of the child sequence found so far and the most recent attempt,
+/// look for the children in query order inside ONE field; every complete sequence is emitted. The document carries child 0's
+/// TF*IDF and field mask only (:4914).
+struct OrderNode_c : Node_c
+{
+	std::vector<std::unique_ptr<Node_c>> m_dChildren;
+	std::vector<ExtDoc_t> m_dDoc;
+	std::vector<char> m_dHas;
+	bool m_bDone = false;
+	std::vector<std::vector<ExtHit_t>> m_dChildHits;
+	std::vector<ExtHit_t> m_dCurHits;
+
+	bool Pull ( size_t i )
+	{
+		m_dHas[i] = m_dChildren[i]->Next ( m_dDoc[i] ) ? 1 : 0;
+		return m_dHas[i]!=0;
+	}
+	/// GetMatchingHits, :4734-4829
+	bool GetMatchingHits()
+	{
+		const size_t n = m_dChildren.size();
+		std::vector<size_t> dCur ( n, 0 );
+		std::vector<ExtHit_t> dLongest, dRecent;
+		int iPosLongest = 0, iPosRecent = 0, iField = -1;
+		m_dCurHits.clear();
+		while ( true )
+		{
+			// next hit in position order; the lowest child wins ties (:4706-4731)
+			int iChild = -1;
+			DWORD uMin = UINT_MAX;
+			for ( size_t i=0; i<n; ++i )
+				if ( dCur[i]<m_dChildHits[i].size() && HitPosWithField ( m_dChildHits[i][dCur[i]].m_uHitpos )<uMin )
+				{
+					uMin = HitPosWithField ( m_dChildHits[i][dCur[i]].m_uHitpos );
+					iChild = (int)i;
+				}
+			if ( iChild<0 )
+				break;
+			const ExtHit_t & tHit = m_dChildHits[iChild][dCur[iChild]++];
+			const int iHitField = HitField ( tHit.m_uHitpos ), iHitPos = (int)( tHit.m_uHitpos & 0x7FFFFFu );
+			if ( iHitField!=iField )
+			{
+				// another field: both trackers start over; only child 0 can seed (and only then the field is remembered)
+				dLongest.clear();
+				dRecent.clear();
+				if ( iChild==0 )
+				{
+					dLongest.push_back ( tHit );
+					iPosLongest = iHitPos + tHit.m_uSpanlen;
+					iField = iHitField;
+				}
+			} else if ( iChild==(int)dLongest.size() && iHitPos>=iPosLongest )
+			{
+				dLongest.push_back ( tHit );
+				iPosLongest = iHitPos + tHit.m_uSpanlen;
+				if ( dLongest.size()==n )
+				{
+					m_dCurHits.insert ( m_dCurHits.end(), dLongest.begin(), dLongest.end() );
+					dLongest.clear();
+					dRecent.clear();
+					iPosRecent = iPosLongest;
+				}
+			} else if ( iChild==0 )
+			{
+				dRecent.assign ( 1, tHit );
+				iPosRecent = iHitPos + tHit.m_uSpanlen;
+				if ( dLongest.empty() )
+				{
+					dLongest.push_back ( tHit );
+					iPosLongest = iHitPos + tHit.m_uSpanlen;
+				}
+			} else if ( iChild==(int)dRecent.size() && iHitPos>=iPosRecent )
+			{
+				dRecent.push_back ( tHit );
+				iPosRecent = iHitPos + tHit.m_uSpanlen;
+				if ( dRecent.size()==dLongest.size() )
+				{
+					dLongest.swap ( dRecent );
+					dRecent.clear();
+					iPosLongest = iPosRecent;
+				}
+			}
+		}
+		return !m_dCurHits.empty();
+	}
+	/// GetDocsChunk, :4832-4929, one document per call
+	bool Next ( ExtDoc_t & tDoc ) override
+	{
+		const size_t n = m_dChildren.size();
+		while ( !m_bDone )
+		{
+			for ( size_t i=0; i<n; ++i )
+				if ( !m_dHas[i] && !Pull ( i ) )
+				{
+					m_bDone = true;
+					return false;
+				}
+			// the next document that holds every child
+			RowID_t tRowID = m_dDoc[0].m_tRowID;
+			size_t iChild = 1;
+			while ( iChild<n )
+			{
+				while ( m_dDoc[iChild].m_tRowID<tRowID )
+					if ( !Pull ( iChild ) )
+					{
+						m_bDone = true;
+						return false;
+					}
+				if ( m_dDoc[iChild].m_tRowID>tRowID )
+				{
+					tRowID = m_dDoc[iChild].m_tRowID;
+					iChild = 0;
+					continue;
+				}
+				++iChild;
+			}
+			for ( size_t i=0; i<n; ++i )
+			{
+				m_dChildHits[i].clear();
+				m_dChildren[i]->CollectHits ( m_dChildHits[i] );
+			}
+			const bool bMatch = GetMatchingHits();
+			tDoc = m_dDoc[0];
+			m_dHas[0] = 0;	// advance child 0; the others catch up on the next call
+			if ( bMatch )
+				return true;
+		}
+		return false;
+	}
+	void HintRowID ( RowID_t t ) override
+	{
+		for ( auto & p : m_dChildren )
+			p->HintRowID ( t );
+	}
+	void CollectHits ( std::vector<ExtHit_t> & dHits ) override	{ dHits.insert ( dHits.end(), m_dCurHits.begin(), m_dCurHits.end() ); }
+	int GetQwords ( QwordsHash_t & h ) override
+	{
+		int iMax = -1;
+		for ( auto & p : m_dChildren )
+			iMax = std::max ( iMax, p->GetQwords ( h ) );
+		return iMax;
+	}
+	void SetQwordsIDF ( const QwordsHash_t & h ) override
+	{
+		for ( auto & p : m_dChildren )
+			p->SetQwordsIDF ( h );
+	}
+};
+
 struct Setup_t
 {
 	const Index_t * m_pIndex;
@@ -1755,6 +1905,29 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 	}
 	if ( bAndTerms )
 		return CreateNode ( pChildren[0], tSetup );	// degenerate 1-child AND: generic create returns the child
+
+	if ( tNode.op==MGPU_OP_BEFORE )
+	{
+		// CreateOrderNode, src/searchnode.cpp:1044-1074
+		if ( nChildren<2 )
+			return nullptr;	// "order node requires at least two children"
+		auto * pOrder = new OrderNode_c;
+		for ( int i=0; i<nChildren; ++i )
+		{
+			Node_c * p = CreateNode ( pChildren[i], tSetup );
+			if ( !p || tSetup.m_iError!=MGPU_OK )
+			{
+				delete pOrder;
+				return nullptr;	// "failed to create order node, hitlist unavailable"
+			}
+			pOrder->m_dChildren.emplace_back ( p );
+		}
+		pOrder->m_dDoc.assign ( nChildren, ExtDoc_t { INVALID_ROWID, 0, 0.0f } );
+		pOrder->m_dHas.assign ( nChildren, 0 );
+		pOrder->m_dChildHits.resize ( nChildren );
+		pOrder->m_iAtomPos = pOrder->m_dChildren[0]->m_iAtomPos;
+		return pOrder;
+	}
 
 	if ( tNode.op==MGPU_OP_NEAR )
 	{

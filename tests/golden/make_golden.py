@@ -10,7 +10,7 @@ nodes with word lists, atom positions 1,2,3.. in query order, src/sphinxquery.cp
 because the parser itself needs bison and is out of scope.
 
 Tree notation: ["kw", word, atompos, fieldmask?], ["and"|"or"|"andnot"|"maybe", child...],
-["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...].
+["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...], ["before", child...].
 """
 import json
 import os
@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,054,055,059,094,114,115,116,138,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,052,054,055,059,094,114,115,116,138,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -279,6 +279,58 @@ case = {"name": "test_115", "fields": ["title"], "min_word_len": 1,
         "docs": [{"id": d[0], "fields": [d[1].replace("-", " ")]} for d in docs_115], "queries": []}
 for qi, tree in q115:
     case["queries"].append({"text": m115[qi]["query"].strip(), "tree": tree, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m115[qi])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_052 "before operator", index `test` (documents 1..5, fields title / text): ExtOrder_c (src/searchnode.cpp:4657-4935) over keywords,
+# phrases, OR groups, anchored keywords and a degenerate quorum. Note the query position after `"zzz aaa"/1`: the threshold token takes
+# a position of its own (the parser only rewinds it for proximity, FixupAtomPos), so `bbb` sits at 4. Oracle only (OrderNode_c); the
+# CUDA path must refuse BEFORE.
+# ---------------------------------------------------------------------------------------------
+docs_052 = [(1, "aaa bbb", "ccc ddd"), (2, "xxx", "ccc ddd eee fff ggg"), (3, "yyy", "one one one two three"),
+            (4, "zzz", "one two three one three one two four one two three four"), (5, "", "a b c d e f g")]
+m52 = model("test_052")
+
+
+def KM(w, p, **mods):
+    return ["kw", w, p, ALL, mods]
+
+
+def BF(*children):
+    return ["before"] + list(children)
+
+
+def SEQ(words):
+    return BF(*[K(w, i + 1) for i, w in enumerate(words.split())])
+
+
+q52 = {0: SEQ("aaa ccc"), 1: SEQ("aaa bbb ccc"), 2: SEQ("aaa ccc ddd"), 3: SEQ("ccc ddd"), 4: SEQ("ccc eee fff"), 5: SEQ("ccc ddd ggg"),
+       6: SEQ("ccc ddd xxx"), 7: SEQ("eee ddd ggg"), 8: SEQ("one two three"), 9: SEQ("one three"), 10: SEQ("one one three"),
+       11: SEQ("one one one three"), 12: SEQ("one one one one three"), 13: SEQ("one two three four"),
+       14: BF(PH("abc", 1), K("b", 4), K("c", 5), K("d", 6)), 15: BF(PH("abc", 1), K("c", 4), K("d", 5), K("e", 6)),
+       16: BF(PH("abc", 1), K("e", 4), K("f", 5), K("g", 6)), 17: BF(K("a", 1), PH("bcd", 2), K("e", 5)),
+       18: BF(PH("abcd", 1), PH("def", 5)), 19: BF(PH("abcd", 1), PH("efg", 5)),
+       20: BF(["or", K("ccc", 1), ["phrase", [["ddd", 2], ["eee", 3]]]], ["or", K("ddd", 4), K("ggg", 5)]),
+       21: BF(K("ccc", 1), KM("ddd", 2, end=1)), 22: BF(KM("one", 1, start=1), K("two", 2), KM("three", 3, end=1)),
+       23: BF(KM("one", 1, start=1), ["phrase", [["one", 2], ["one", 3]]], K("two", 4), KM("three", 5, end=1)),
+       24: BF(["quorum", 1, [["zzz", 1], ["aaa", 2]]], K("bbb", 4)), 25: BF(["quorum", 1, [["zzz", 1], ["aaa", 2]]], K("ddd", 4))}
+case = {"name": "test_052", "fields": ["title", "text"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1], d[2]]} for d in docs_052], "queries": []}
+for qi, tree in q52.items():
+    case["queries"].append({"text": m52[qi]["query"].strip(), "tree": tree, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m52[qi])})
+out["cases"].append(case)
+
+# test_052 index `test1` (document 6): NEAR nodes over a phrase and an OR group as the operands of BEFORE
+case = {"name": "test_052_test1", "fields": ["title", "text"], "min_word_len": 1,
+        "docs": [{"id": 6, "fields": ["", "h1 h2 h3 h4 h5"]}], "queries": []}
+
+
+def NR52(p0):
+    return ["near", 5, ["phrase", [["h1", p0], ["h2", p0 + 1]]], ["or", K("h3", p0 + 2), K("h4", p0 + 3), K("h5", p0 + 4)]]
+
+
+case["queries"].append({"text": m52[26]["query"].strip(), "tree": BF(NR52(1), NR52(6)), "ranker": "proximity_bm25", "gpu_unsupported": True,
+                        "expect": api_expect(m52[26])})
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------

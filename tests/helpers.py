@@ -169,6 +169,8 @@ def tree_to_node(t):
         return M.Node(M.OP_QUORUM, words=[M.Keyword(w, p) for w, p in t[2]], oparg=t[1])
     if kind == "near":
         return M.Node(M.OP_NEAR, children=[tree_to_node(c) for c in t[2:]], oparg=t[1])
+    if kind == "before":
+        return M.Node(M.OP_BEFORE, children=[tree_to_node(c) for c in t[1:]])
     raise ValueError(kind)
 
 
