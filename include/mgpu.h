@@ -44,8 +44,9 @@ enum {
 	MGPU_OP_BEFORE = 5,
 	MGPU_OP_PHRASE = 6,     /* SPH_QUERY_PHRASE */
 	MGPU_OP_PROXIMITY = 7,  /* SPH_QUERY_PROXIMITY, oparg = N of "..."~N */
-	MGPU_OP_QUORUM = 8,
-	MGPU_OP_NEAR = 9
+	MGPU_OP_QUORUM = 8,     /* SPH_QUERY_QUORUM, oparg = threshold (absolute) */
+	MGPU_OP_NEAR = 9,       /* SPH_QUERY_NEAR, oparg = distance; n-ary */
+	MGPU_OP_NOTNEAR = 10    /* SPH_QUERY_NOTNEAR, oparg = distance; two children: must, not */
 };
 
 /* ---- ESphRankMode (src/sphinx.h:2388-2404) ---- */

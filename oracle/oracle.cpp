@@ -1700,6 +1700,61 @@ struct OrderNode_c : Node_c
 	}
 };
 
+/// ExtNotNear_c, src/searchnode.cpp:5325-5478: `must NOTNEAR/N not`. Every MUST document stays; where the NOT child holds the document
+/// too, a MUST hit survives when the first NOT hit at or after it starts more than N positions past its end (NOT hits before it do
+/// not count), and the document stays when at least one MUST hit survives. It carries the MUST child's TF*IDF and fields.
+struct NotNearNode_c : TwoferNode_c
+{
+	int m_iDist = 1;
+	std::vector<ExtHit_t> m_dCurHits;
+
+	bool Next ( ExtDoc_t & tDoc ) override
+	{
+		while ( PullL() )
+		{
+			m_pRight->HintRowID ( m_tL.m_tRowID );
+			while ( PullR() && m_tR.m_tRowID<m_tL.m_tRowID )
+				m_bHasR = false;
+			m_dTmpL.clear();
+			m_pLeft->CollectHits ( m_dTmpL );
+			m_dCurHits.clear();
+			bool bMatched = true;
+			if ( m_bHasR && m_tR.m_tRowID==m_tL.m_tRowID )
+			{
+				// FilterHits, :5352-5380
+				m_dTmpR.clear();
+				m_pRight->CollectHits ( m_dTmpR );
+				size_t iNot = 0;
+				for ( size_t iMust=0; iMust<m_dTmpL.size(); ++iMust )
+				{
+					const DWORD uPosMust = HitPosWithField ( m_dTmpL[iMust].m_uHitpos );
+					while ( iNot<m_dTmpR.size() && HitPosWithField ( m_dTmpR[iNot].m_uHitpos )<uPosMust )
+						++iNot;
+					if ( iNot==m_dTmpR.size() )
+					{
+						// no NOT hit behind this one: it and the rest of the MUST hits stay
+						m_dCurHits.insert ( m_dCurHits.end(), m_dTmpL.begin()+iMust, m_dTmpL.end() );
+						break;
+					}
+					// (the field sits in the top byte, so the distance can be added to the position as it is)
+					if ( uPosMust + m_dTmpL[iMust].m_uMatchlen - 1 + m_iDist<HitPosWithField ( m_dTmpR[iNot].m_uHitpos ) )
+						m_dCurHits.push_back ( m_dTmpL[iMust] );
+				}
+				bMatched = !m_dCurHits.empty();
+				m_bHasR = false;
+			} else
+				m_dCurHits = m_dTmpL;
+			tDoc = m_tL;
+			m_bHasL = false;
+			if ( bMatched )
+				return true;
+		}
+		return false;
+	}
+	void HintRowID ( RowID_t t ) override	{ m_pLeft->HintRowID ( t ); }
+	void CollectHits ( std::vector<ExtHit_t> & dHits ) override	{ dHits.insert ( dHits.end(), m_dCurHits.begin(), m_dCurHits.end() ); }
+};
+
 struct Setup_t
 {
 	const Index_t * m_pIndex;
@@ -1905,6 +1960,32 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 	}
 	if ( bAndTerms )
 		return CreateNode ( pChildren[0], tSetup );	// degenerate 1-child AND: generic create returns the child
+
+	if ( tNode.op==MGPU_OP_NOTNEAR )
+	{
+		// generic create, src/searchnode.cpp:1785-1806: ExtNotNear_c ( must, not, distance )
+		if ( nChildren!=2 )
+		{
+			tSetup.m_iError = MGPU_E_BAD_QUERY;
+			return nullptr;
+		}
+		Node_c * pMust = CreateNode ( pChildren[0], tSetup );
+		Node_c * pNot = tSetup.m_iError==MGPU_OK ? CreateNode ( pChildren[1], tSetup ) : nullptr;
+		if ( tSetup.m_iError!=MGPU_OK )
+		{
+			delete pMust;
+			delete pNot;
+			return nullptr;
+		}
+		if ( !pMust || !pNot )
+			return pMust ? pMust : pNot;	// an empty child drops out of the fold (:1788-1794)
+		auto * pRes = new NotNearNode_c;
+		pRes->m_pLeft.reset ( pMust );
+		pRes->m_pRight.reset ( pNot );
+		pRes->m_iDist = tNode.oparg;
+		pRes->m_iAtomPos = pMust->m_iAtomPos;
+		return pRes;
+	}
 
 	if ( tNode.op==MGPU_OP_BEFORE )
 	{

@@ -10,7 +10,7 @@ nodes with word lists, atom positions 1,2,3.. in query order, src/sphinxquery.cp
 because the parser itself needs bison and is out of scope.
 
 Tree notation: ["kw", word, atompos, fieldmask?], ["and"|"or"|"andnot"|"maybe", child...],
-["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...], ["before", child...].
+["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...], ["before", child...], ["notnear", N, must, not].
 """
 import json
 import os
@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,052,054,055,059,094,114,115,116,138,322 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,052,054,055,059,094,114,115,116,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -331,6 +331,49 @@ def NR52(p0):
 
 case["queries"].append({"text": m52[26]["query"].strip(), "tree": BF(NR52(1), NR52(6)), "ranker": "proximity_bm25", "gpu_unsupported": True,
                         "expect": api_expect(m52[26])})
+out["cases"].append(case)
+
+# ---------------------------------------------------------------------------------------------
+# test_349 "NOTNEAR", index `idx`: `select * ... order by id asc` results carry no weights, so these pin the matched document sets only
+# ("ids_only"). ExtNotNear_c (src/searchnode.cpp:5325-5478) over keywords, phrases, proximity, OR groups and a nested NOTNEAR.
+# Oracle only (NotNearNode_c); the CUDA path must refuse NOTNEAR.
+# ---------------------------------------------------------------------------------------------
+xml349 = open(os.path.join(REF, "test_349", "test.xml"), encoding="utf-8").read()
+a349 = xml349.index("INSERT INTO `test_table` VALUES")
+ins349 = xml349[a349:xml349.index("</db_insert>", a349)]
+docs_349 = [(int(m.group(1)), m.group(2)) for m in re.finditer(r"\(\s*(\d+),\s*'((?:[^']|'')*)'\s*\)", ins349)]
+docs_349.append((21, "zwei " + "oy vey ho ho ho " * 1023 + "oy vey ho h"))
+docs_349.sort()
+assert [d[0] for d in docs_349] == list(range(1, 18)) + [20, 21, 22]
+m349 = model("test_349")
+
+
+def NN(n, left, right):
+    return ["notnear", n, left, right]
+
+
+def PW(words, p0):
+    return ["phrase", [[w, p0 + i] for i, w in enumerate(words.split())]]
+
+
+q349 = {0: NN(1, K("a", 1), K("c", 2)), 1: NN(2, K("a", 1), K("c", 2)), 2: NN(3, K("a", 1), K("c", 2)), 3: NN(5, K("a", 1), K("c", 2)),
+        4: NN(6, K("a", 1), K("c", 2)), 5: NN(7, K("a", 1), K("c", 2)), 6: NN(15, K("a", 1), K("c", 2)),
+        7: NN(1, K("b", 1), K("c", 2)), 8: NN(2, K("b", 1), K("c", 2)), 9: NN(2, PH("ab", 1), K("c", 3)), 10: NN(3, PH("ab", 1), K("c", 3)),
+        11: NN(3, K("a", 1), ["or", K("c", 2), K("d", 3)]),
+        13: NN(3, K("a", 1), PW("c x d", 2)), 14: NN(9, K("a", 1), PW("c x d", 2)), 15: NN(11, K("a", 1), PW("c x x d", 2)),
+        16: NN(1, K("oy", 1), K("ho", 2)), 17: NN(2, K("oy", 1), K("ho", 2)), 18: NN(2, K("zwei", 1), K("ho", 2)), 19: NN(4, K("zwei", 1), K("ho", 2)),
+        20: NN(1, K("zwei", 1), K("vey", 2)), 21: NN(2, K("zwei", 1), K("vey", 2)), 22: NN(1, K("vey", 1), K("ho", 2)), 23: NN(1, K("vey", 1), K("oy", 2)),
+        24: NN(1, K("d", 1), K("a", 2)), 25: NN(3, K("d", 1), K("a", 2)), 26: NN(1, K("c", 1), K("x", 2)), 27: NN(2, K("c", 1), K("x", 2)),
+        28: NN(3, K("c", 1), K("x", 2)), 29: NN(2, K("x", 1), K("c", 2)),
+        30: NN(2, NN(3, PH("ab", 1), ["or", K("d", 3), K("e", 4)]), K("c", 5)),
+        31: NN(1, ["prox", 4, [["a", 1], ["b", 2]]], K("c", 3)),
+        32: NN(1, ["or", PH("ab", 1), PW("a x b", 3)], K("c", 6))}
+case = {"name": "test_349", "fields": ["title"], "attrs": ["gid"], "min_word_len": 1,
+        "docs": [{"id": d[0], "fields": [d[1].replace("-", " ")], "attrs": [11]} for d in docs_349], "queries": []}
+for qi, tree in q349.items():
+    r = m349[qi]
+    case["queries"].append({"text": r["sphinxql"].strip(), "tree": tree, "ranker": "proximity_bm25", "sort": "id_asc", "ids_only": True, "gpu_unsupported": True,
+                            "expect": {"matches": [[int(row["id"]), 0] for row in (r.get("rows") or {}).values()], "total_found": int(r["total_rows"]), "words": {}}})
 out["cases"].append(case)
 
 # ---------------------------------------------------------------------------------------------

@@ -171,6 +171,8 @@ def tree_to_node(t):
         return M.Node(M.OP_NEAR, children=[tree_to_node(c) for c in t[2:]], oparg=t[1])
     if kind == "before":
         return M.Node(M.OP_BEFORE, children=[tree_to_node(c) for c in t[1:]])
+    if kind == "notnear":
+        return M.Node(M.OP_NOTNEAR, children=[tree_to_node(t[2]), tree_to_node(t[3])], oparg=t[1])
     raise ValueError(kind)
 
 
