@@ -1063,6 +1063,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
 	const int64_t OR_RANGE_TILES = getenv ( "MGPU_OR_RANGE_TILES" ) ? std::max ( 1, atoi ( getenv ( "MGPU_OR_RANGE_TILES" ) ) ) : 1024;	// 1024 x 2048 = 2M rows per item of class 5 (per-item costs outweigh finer ranges: 262144 rows was 25 % slower)
 	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
+	const bool bNoOrClass = getenv ( "MGPU_NO_ORCLASS" )!=nullptr, bNoDnfClass = getenv ( "MGPU_NO_DNFCLASS" )!=nullptr;	// (experiments)
 	// a group's driver may sit in at most iDnfMul/iDnfDiv of the rows (MGPU_DNF_PCT: percent, for experiments)
 	const int64_t iDnfDiv = 100, iDnfMul = getenv ( "MGPU_DNF_PCT" ) ? std::max ( 1, atoi ( getenv ( "MGPU_DNF_PCT" ) ) ) : 12;
 	for ( int i : dDocOnly )
@@ -1081,12 +1082,12 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		bool bWeightKey = false;
 		for ( int k=0; k<q.m_nSortKeys; ++k )
 			bWeightKey |= q.m_dSortKeys[k].m_eKind==1;
-		const bool bBoundOk = !bDnf && q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !getenv ( "MGPU_NO_ORCLASS" );
+		const bool bBoundOk = !bDnf && q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !bNoOrClass;
 		const bool bOrClass = bBoundOk && q.m_bPureOr && !q.m_nFilters && !q.m_nSortKeys;	// the lean instantiation: relevance order, no filters
 		// ... and the same passes with run-time options (class 6): pure OR programs with filters / attribute sort keys, and
 		// OR-of-AND-groups programs (a dense driver kept them off the intersection kernel) whose multi-keyword groups hold at most
 		// one keyword outside the dense store
-		bool bHotDnf = bBoundOk && !bOrClass && ( q.m_bPureOr || q.m_nGroups>0 ) && !getenv ( "MGPU_NO_DNFCLASS" );
+		bool bHotDnf = bBoundOk && !bOrClass && ( q.m_bPureOr || q.m_nGroups>0 ) && !bNoDnfClass;
 		if ( bHotDnf && !q.m_bPureOr )
 			for ( int g=0; g<q.m_nGroups && bHotDnf; ++g )
 			{
