@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=int(os.environ.get("MGPU_BENCH_QUERIES", 10_000)))
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine option for mgpu_index_set_option (A/B switches, e.g. --opt or_bits=0 --opt stats=1)")
     ap.add_argument("--only", default="", choices=["", "and", "or", "mix"], help="analysis only: keep one query shape of the batch")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
                     help="cfg2 = the bench line (BASELINE.json configs[1]); cfg4 = configs[3] shape for extra runs: same mix + 10%% ANDNOT, top-1000 (use with --docs 100000000 --gpus 8)")
@@ -243,6 +245,9 @@ def run_ours(args):
     prefix, first_doc, n_docs, build_s = ensure_index(M, args.docs, rank, world)
     t0 = time.time()
     index = M.Index(prefix, device=local_rank, rowid_base=first_doc)
+    for kv in args.opt:
+        name, _, value = kv.partition("=")
+        index.set_option(name, int(value))
     load_s = time.time() - t0
     # one explicit stream for everything: the index's kernels, torch's NCCL collectives and the timing events
     # (torch's default stream has handle 0, which mgpu_index_set_stream reads as "use the index's private stream")

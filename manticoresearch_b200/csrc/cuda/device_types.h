@@ -71,6 +71,12 @@ struct DevHotStore_t
 	int64_t				m_iStride;		///< rows rounded up to TILE_W
 	int32_t				m_nHot;
 	int32_t				m_bTfClass;		///< indexes with <= 4 fields: bits 12..15 of a row hold its tf class (consumers mask fields by the queried fields)
+	const uint32_t *	m_pBits;		///< [nHot][m_nBitFields][m_iBitStride]: presence bitmap per (hot keyword, field), 1 bit per row (indexes with <= 4 fields; else null)
+	int64_t				m_iBitStride;	///< words per bitmap = m_iStride/32
+	int32_t				m_nBitFields;	///< fields of the index (1..4)
+	int32_t				m_iPad;
+	const int32_t *		m_pLvlSlot;		///< [nHot] slot in m_pLvlBits, -1 = none: keywords in >= 1/3 of the rows (the ones whose idf can be negative)
+	const uint32_t *	m_pLvlBits;		///< [slots][2][m_iBitStride]: rows with >= 2 hits, rows with >= 4 hits (tf levels of orbits_kernel's penalty classes)
 };
 
 enum DevOpCode_e : uint8_t
@@ -221,12 +227,14 @@ struct EvalParams_t
 	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]
 	DevHotStore_t			m_tHot;
 	const int32_t *			m_pItemOrder;	///< stream_kernel: the k-th item taken from the queue is item m_pItemOrder[k] (null = k)
+	unsigned long long *	m_pDebug;		///< [8] work counters of the bound + exact pass kernels (option "stats"), or null
 };
 
 struct HotDecodeParams_t
 {
 	DevIndex_t				m_tIndex;
 	const DevLeaf_t *		m_pTerms;		///< [nHot] doclist descriptors
+	const uint32_t *		m_pBlkStart;	///< [nHot+1] prefix sums of the keywords' block counts (the flat block list)
 	int32_t					m_nHot;
 	int32_t					m_iEscapeCap;
 	uint16_t *				m_pData;
@@ -234,7 +242,10 @@ struct HotDecodeParams_t
 	int32_t *				m_pEscapeCount;
 	int64_t					m_iStride;
 	int32_t					m_bTfClass;
-	int32_t					m_iPad;
+	int32_t					m_nBitFields;	///< > 0: also build the per-field presence bitmaps
+	uint32_t *				m_pBits;		///< [nHot][m_nBitFields][m_iStride/32], zeroed by the caller
+	const int32_t *			m_pLvlSlot;		///< [nHot] or null
+	uint32_t *				m_pLvlBits;		///< [slots][2][m_iStride/32], zeroed by the caller
 };
 
 struct MergeParams_t

@@ -576,33 +576,90 @@ __device__ uint32_t HotEscapeHits ( const DevHotStore_t & tHot, int iHot, uint32
 	return 255u;
 }
 
-/// K0: decodes every hot keyword's doclist ONCE per batch into the dense store (warp per 32-doc block)
+/// K0: decodes every hot keyword's doclist ONCE per batch into the dense store (warp per 32-doc block). The blocks of all hot
+/// keywords form one flat list (P.m_pBlkStart = prefix sums of the keywords' block counts): a warp takes HOT_CHUNK consecutive
+/// blocks at a time, so short doclists keep every warp busy (a 0.5 % keyword on a 1.25M-row shard has 195 blocks).
+/// Next to the u16 row {hits, fields, tf class} the kernel sets the row's bit in the keyword's per-field presence bitmaps
+/// (orbits_kernel); lanes of a block whose rows share a bitmap word combine their bits before the one atomic per word.
+static const int HOT_CHUNK = 8;
+
 __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecodeParams_t P )
 {
 	__shared__ __align__(16) uint8_t dStage[EVAL_WARPS][STAGE_BYTES];
 	__shared__ uint16_t dRecStart[EVAL_WARPS][34];
 	const int iWarp = threadIdx.x>>5, iLane = threadIdx.x & 31;
 	const uint32_t uWarpGlobal = blockIdx.x*EVAL_WARPS+iWarp, nWarps = gridDim.x*EVAL_WARPS;
-	for ( int h=0; h<P.m_nHot; ++h )
+	const uint32_t nTotalBlocks = __ldg ( P.m_pBlkStart+P.m_nHot );
+	const size_t iBitStride = (size_t)( P.m_iStride>>5 );
+	for ( uint32_t g0=uWarpGlobal*HOT_CHUNK; g0<nTotalBlocks; g0+=nWarps*HOT_CHUNK )
 	{
-		const DevLeaf_t tLeaf = P.m_pTerms[h];
-		uint16_t * pD = P.m_pData + (size_t)h*P.m_iStride;
-		for ( uint32_t b=uWarpGlobal; b<tLeaf.m_nBlocks; b+=nWarps )
+		// the keyword holding flat block g0: last h with start[h] <= g0
+		int h = 0;
 		{
-			DecodedDoc_t d;
-			DecodeBlock<false> ( P.m_tIndex, tLeaf, b, dStage[iWarp], dRecStart[iWarp], iLane, d );
-			if ( !d.m_bValid )
-				continue;
-			const uint32_t uHits = min ( d.m_uHits, 255u );
-			// tf class = ceil ( 15*h/(h+1.2) ) in exact integers: class/15 >= tf, the share of the weight bound of stream_kernel's register-OR path
-			const uint32_t uClass = P.m_bTfClass ? ( 150u*uHits + 10u*uHits+11u )/( 10u*uHits+12u ) : 0u;
-			pD[d.m_uRowid] = (uint16_t)( uHits | ( ( d.m_uFields & 255u )<<8 ) | ( uClass<<12 ) );
-			if ( d.m_uHits>=255u )
+			int lo = 0, hi = P.m_nHot;
+			while ( hi-lo>1 )
 			{
-				const int i = atomicAdd ( P.m_pEscapeCount, 1 );
-				if ( i<P.m_iEscapeCap )
+				const int mid = ( lo+hi )>>1;
+				if ( __ldg ( P.m_pBlkStart+mid )<=g0 ) lo = mid; else hi = mid;
+			}
+			h = lo;
+		}
+		const uint32_t g1 = min ( g0+(uint32_t)HOT_CHUNK, nTotalBlocks );
+		for ( uint32_t g=g0; g<g1; ++g )
+		{
+			while ( g>=__ldg ( P.m_pBlkStart+h+1 ) )
+				++h;
+			const DevLeaf_t tLeaf = P.m_pTerms[h];
+			uint16_t * pD = P.m_pData + (size_t)h*P.m_iStride;
+			DecodedDoc_t d;
+			DecodeBlock<false> ( P.m_tIndex, tLeaf, g-__ldg ( P.m_pBlkStart+h ), dStage[iWarp], dRecStart[iWarp], iLane, d );
+			const bool bValid = d.m_bValid && d.m_uRowid<P.m_tIndex.m_uRows;	// (a corrupt doclist must not write outside the store)
+			if ( bValid )
+			{
+				const uint32_t uHits = min ( d.m_uHits, 255u );
+				// tf class = ceil ( 15*h/(h+1.2) ) in exact integers: class/15 >= tf, the share of the weight bound of stream_kernel's register-OR path
+				const uint32_t uClass = P.m_bTfClass ? ( 150u*uHits + 10u*uHits+11u )/( 10u*uHits+12u ) : 0u;
+				pD[d.m_uRowid] = (uint16_t)( uHits | ( ( d.m_uFields & 255u )<<8 ) | ( uClass<<12 ) );
+				if ( d.m_uHits>=255u )
 				{
-					P.m_pEscape[3*i] = (uint32_t)h; P.m_pEscape[3*i+1] = d.m_uRowid; P.m_pEscape[3*i+2] = d.m_uHits;
+					const int i = atomicAdd ( P.m_pEscapeCount, 1 );
+					if ( i<P.m_iEscapeCap )
+					{
+						P.m_pEscape[3*i] = (uint32_t)h; P.m_pEscape[3*i+1] = d.m_uRowid; P.m_pEscape[3*i+2] = d.m_uHits;
+					}
+				}
+			}
+			if ( P.m_nBitFields )
+			{
+				// rowids ascend inside a block: lanes of the same 32-row word are neighbours; the first of each run owns the atomic
+				const unsigned uAct = __ballot_sync ( FULL_MASK, bValid );
+				if ( bValid )
+				{
+					const uint32_t uWord = d.m_uRowid>>5;
+					const unsigned uPeers = __match_any_sync ( uAct, uWord );
+					const uint32_t uBit = 1u<<( d.m_uRowid & 31u );
+					uint32_t * pB = P.m_pBits + (size_t)h*P.m_nBitFields*iBitStride + uWord;
+					for ( int f=0; f<P.m_nBitFields; ++f )
+					{
+						const uint32_t uMine = ( ( d.m_uFields>>f ) & 1u ) ? uBit : 0u;
+						const uint32_t uAll = __reduce_or_sync ( uPeers, uMine );
+						if ( uAll && iLane==__ffs ( uPeers )-1 )
+							atomicOr ( pB + f*iBitStride, uAll );
+					}
+					const int iLvl = P.m_pLvlSlot ? __ldg ( P.m_pLvlSlot+h ) : -1;
+					if ( iLvl>=0 )
+					{
+						uint32_t * pL = P.m_pLvlBits + (size_t)iLvl*2*iBitStride + uWord;
+						const uint32_t uAll2 = __reduce_or_sync ( uPeers, d.m_uHits>=2u ? uBit : 0u );
+						const uint32_t uAll4 = __reduce_or_sync ( uPeers, d.m_uHits>=4u ? uBit : 0u );
+						if ( iLane==__ffs ( uPeers )-1 )
+						{
+							if ( uAll2 )
+								atomicOr ( pL, uAll2 );
+							if ( uAll4 )
+								atomicOr ( pL+iBitStride, uAll4 );
+						}
+					}
 				}
 			}
 		}
@@ -1111,6 +1168,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 }
 
 #include "stream_kernel.cuh"
+#include "orbits_kernel.cuh"
 
 //////////////////////////////////////////////////////////////////////////
 // K2: driver-led intersection kernel for pure AND queries (ExtMultiAnd_T::AdvanceQwords, src/searchnode.cpp:2864-2889;
@@ -1674,8 +1732,16 @@ static int StreamMiniWidth ( int nStack )
 /// the register-OR class needs per warp: sparse overlay 512*4 + candidate rows 256 + queue (32+256)*4
 static const size_t OR_WARP_SMEM = 512*4 + 256 + 288*4;
 
+/// sparse postings one mini-tile of the bound + exact pass kernels can hold, per warp (sizes EvalParams_t::m_pOrList)
+int StreamOrListCap ( int iMode )
+{
+	return iMode==3 ? OB_LIST_CAP : OR_LIST_CAP;
+}
+
 size_t StreamDynSmemBytes ( int nStack, int iMode )
 {
+	if ( iMode==3 )
+		return (size_t)EVAL_WARPS*OB_WARP_SMEM;
 	if ( iMode )
 		return (size_t)EVAL_WARPS*512*9;	// (the kernel strides its warps by nStack*MINI_W*9 = 4608 >= OR_WARP_SMEM)
 	return (size_t)nStack*EVAL_WARPS*StreamMiniWidth ( nStack )*9;
@@ -1691,11 +1757,20 @@ static cudaError_t LaunchStreamT ( KERNEL fnKernel, const EvalParams_t & P, int 
 	return cudaGetLastError();
 }
 
-/// iMode: 0 = general tile program, 1 = pure OR programs, 2 = DNF programs with hot multi-keyword groups (bound + exact pass)
+/// iMode: 0 = general tile program, 1 = pure OR programs, 2 = DNF programs with hot multi-keyword groups (bound + exact pass),
+/// 3 = pure OR programs over the presence bitmaps (orbits_kernel)
 cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, int iMode, int nCtas, cudaStream_t tStream )
 {
 	static_assert ( OR_WARP_SMEM<=512*9, "register-OR scratch must fit the warp's slice" );
 	const size_t iDyn = StreamDynSmemBytes ( nStack, iMode );
+	if ( iMode==3 )
+	{
+		cudaError_t e = cudaFuncSetAttribute ( orbits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		if ( e!=cudaSuccess )
+			return e;
+		orbits_kernel<<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P );
+		return cudaGetLastError();
+	}
 	if ( iMode==1 )
 		return LaunchStreamT ( stream_kernel<512,1>, P, 1, iDyn, nCtas, tStream );
 	if ( iMode==2 )
@@ -1718,6 +1793,8 @@ static int StreamOccupancyT ( KERNEL fnKernel, size_t iDyn )
 int StreamOccupancy ( int nStack, int iMode )
 {
 	const size_t iDyn = StreamDynSmemBytes ( nStack, iMode );
+	if ( iMode==3 )
+		return StreamOccupancyT ( orbits_kernel, iDyn );
 	if ( iMode==1 )
 		return StreamOccupancyT ( stream_kernel<512,1>, iDyn );
 	if ( iMode==2 )

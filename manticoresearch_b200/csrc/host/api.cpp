@@ -62,6 +62,19 @@ int mgpu_index_set_stream ( mgpu_index * idx, void * cuda_stream )
 	return MGPU_OK;
 }
 
+int mgpu_index_set_option ( mgpu_index * idx, const char * name, int64_t value )
+{
+	if ( !idx || !name )
+		return MGPU_E_BAD_QUERY;
+	std::lock_guard<std::mutex> tGuard ( idx->m_t.m_tLock );
+	if ( !idx->m_t.m_tOpt.Set ( name, value ) )
+	{
+		idx->m_t.m_sError = std::string ( "unknown option or value out of range: " ) + name;
+		return MGPU_E_BAD_QUERY;
+	}
+	return MGPU_OK;
+}
+
 const char * mgpu_last_error ( const mgpu_index * idx )
 {
 	return idx ? idx->m_t.m_sError.c_str() : g_sLastOpenError.c_str();

@@ -729,7 +729,7 @@ struct Planner_c
 				d.m_dOps[i].m_uSrc = (uint8_t)( 1+j );
 			}
 
-		if ( getenv ( "MGPU_NO_CHAIN" ) )
+		if ( !m_tIndex.m_tOpt.m_bChain )
 			for ( int i=0; i<d.m_nOps; ++i )
 				if ( d.m_dOps[i].m_eCode<=OP_TERM_MAYBE )
 					d.m_dOps[i].m_uSrc = 0;
@@ -739,11 +739,11 @@ struct Planner_c
 		for ( int i=0; i<d.m_nOps; ++i )
 			if ( d.m_dOps[i].m_eCode==OP_TERM_SET || d.m_dOps[i].m_eCode==OP_TERM_OR )
 				d.m_uOrigMask |= 1u<<d.m_dOps[i].m_uLeaf;
-		d.m_bPureOr = ( m_iMaxSp==0 && d.m_nOps>0 && !getenv ( "MGPU_NO_REGOR" ) ) ? 1 : 0;
+		d.m_bPureOr = ( m_iMaxSp==0 && d.m_nOps>0 && m_tIndex.m_tOpt.m_bRegOr ) ? 1 : 0;
 		for ( int i=0; i<d.m_nOps && d.m_bPureOr; ++i )
 			d.m_bPureOr = ( d.m_dOps[i].m_eCode==( i ? OP_TERM_OR : OP_TERM_SET ) && d.m_dOps[i].m_uDst==0 ) ? 1 : 0;
 		d.m_iDriverLeaf = -1;
-		if ( !getenv ( "MGPU_NO_JUMP" ) && d.m_nOps>0 && d.m_dOps[0].m_eCode==OP_TERM_SET && (int)d.m_dOps[0].m_uSrc==d.m_nOps+1 )
+		if ( m_tIndex.m_tOpt.m_bJump && d.m_nOps>0 && d.m_dOps[0].m_eCode==OP_TERM_SET && (int)d.m_dOps[0].m_uSrc==d.m_nOps+1 )
 			d.m_iDriverLeaf = d.m_dOps[0].m_uLeaf;
 
 		// DNF shape: [SET AND*] then ( [SET AND*] on level 1 + VEC_OR(0,1) | TERM_OR on level 0 )*  -> groups for the intersection kernel
@@ -786,7 +786,7 @@ struct Planner_c
 			bool bAnyMulti = false;
 			for ( int g=0; g<nGroups; ++g )
 				bAnyMulti |= d.m_dGroupOps[g]>1;
-			d.m_nGroups = ( bOk && bAnyMulti && !getenv ( "MGPU_NO_DNF" ) ) ? nGroups : ( d.m_iDriverLeaf>=0 ? 1 : 0 );
+			d.m_nGroups = ( bOk && bAnyMulti && m_tIndex.m_tOpt.m_bDnf ) ? nGroups : ( d.m_iDriverLeaf>=0 ? 1 : 0 );
 			if ( d.m_nGroups==1 && d.m_iDriverLeaf>=0 )
 			{
 				d.m_dGroupOp0[0] = 0;
@@ -916,6 +916,43 @@ int PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_
 }
 
 //////////////////////////////////////////////////////////////////////////
+// engine options
+//////////////////////////////////////////////////////////////////////////
+
+bool EngineOptions_t::Set ( const char * szName, int64_t iValue )
+{
+	struct Opt_t { const char * m_szName; int EngineOptions_t::* m_pField; int64_t m_iMin, m_iMax; };
+	static const Opt_t dOpts[] =
+	{
+		{ "plan_threads",	&EngineOptions_t::m_iPlanThreads,	0, 256 },
+		{ "timing",			&EngineOptions_t::m_bTiming,		0, 1 },
+		{ "stats",			&EngineOptions_t::m_bStats,			0, 1 },
+		{ "hot_store",		&EngineOptions_t::m_bHotStore,		0, 1 },
+		{ "hot_div",		&EngineOptions_t::m_iHotDiv,		1, 1<<20 },
+		{ "hot_gb",			&EngineOptions_t::m_iHotGB,			1, 160 },
+		{ "or_range_tiles",	&EngineOptions_t::m_iOrRangeTiles,	1, 1<<20 },
+		{ "dnf_pct",		&EngineOptions_t::m_iDnfPct,		1, 100 },
+		{ "or_bits",		&EngineOptions_t::m_bOrBits,		0, 1 },
+		{ "or_class",		&EngineOptions_t::m_bOrClass,		0, 1 },
+		{ "dnf_class",		&EngineOptions_t::m_bDnfClass,		0, 1 },
+		{ "and_kernel",		&EngineOptions_t::m_bAndKernel,		0, 1 },
+		{ "dnf",			&EngineOptions_t::m_bDnf,			0, 1 },
+		{ "chain",			&EngineOptions_t::m_bChain,			0, 1 },
+		{ "reg_or",			&EngineOptions_t::m_bRegOr,			0, 1 },
+		{ "jump",			&EngineOptions_t::m_bJump,			0, 1 },
+	};
+	for ( const Opt_t & t : dOpts )
+		if ( !strcmp ( t.m_szName, szName ) )
+		{
+			if ( iValue<t.m_iMin || iValue>t.m_iMax )
+				return false;
+			this->*( t.m_pField ) = (int)iValue;
+			return true;
+		}
+	return false;
+}
+
+//////////////////////////////////////////////////////////////////////////
 // batch executor
 //////////////////////////////////////////////////////////////////////////
 
@@ -942,6 +979,7 @@ static int Pow2Ceil ( int n )
 int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries )
 {
 	m_pIndex = pIndex;
+	const EngineOptions_t tOpt = pIndex->m_tOpt;	// one consistent copy per batch
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	const auto tStart = std::chrono::steady_clock::now();
 	m_dPlans.resize ( nQueries );
@@ -949,8 +987,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		// planning is per query and read-only on the index: spread big batches over the host cores
 		int nThreads = (int)std::min<unsigned> ( std::max ( 1u, std::thread::hardware_concurrency() ), 16u );
 		nThreads = std::max ( 1, std::min ( nThreads, nQueries/512 ) );
-		if ( getenv ( "MGPU_PLAN_THREADS" ) )
-			nThreads = std::max ( 1, atoi ( getenv ( "MGPU_PLAN_THREADS" ) ) );
+		if ( tOpt.m_iPlanThreads>0 )
+			nThreads = tOpt.m_iPlanThreads;
 		auto fnPlan = [&] ( int iFrom, int iTo )
 		{
 			for ( int i=iFrom; i<iTo; ++i )
@@ -968,7 +1006,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 	}
 	const auto tPlanned = std::chrono::steady_clock::now();
-	const bool bTiming = getenv ( "MGPU_TIMING" )!=nullptr;
+	const bool bTiming = tOpt.m_bTiming!=0;
 	auto tMark = tPlanned;
 	auto fnMark = [&] ( const char * sWhat )
 	{
@@ -986,7 +1024,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
 		{
 			if ( m_dPlans[i].m_tDev.m_bNeedHits )
-				dOrder [ ( m_dPlans[i].m_tDev.m_nGroups==1 && !getenv ( "MGPU_NO_AND" ) ) ? 4 : 1 ].push_back ( i );
+				dOrder [ ( m_dPlans[i].m_tDev.m_nGroups==1 && tOpt.m_bAndKernel ) ? 4 : 1 ].push_back ( i );
 			else
 				dDocOnly.push_back ( i );
 			m_iKMax = std::max ( m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
@@ -1005,9 +1043,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 
 	// hot keywords of the batch: shared by >= 2 doc-only queries and present in >= 1/iHotDiv of the rows -> dense store
 	// (2 B/row read per query beats walking the compressed doclist from ~2 postings per 512-row mini-tile on)
-	const int64_t iHotDiv = getenv ( "MGPU_HOT_DIV" ) ? std::max ( 1, atoi ( getenv ( "MGPU_HOT_DIV" ) ) ) : 200;
-	const int64_t iHotGB = getenv ( "MGPU_HOT_GB" ) ? std::max ( 1, atoi ( getenv ( "MGPU_HOT_GB" ) ) ) : 24;
-	if ( pIndex->m_tHdr.m_dFields.size()<=8 && !getenv ( "MGPU_NO_HOT" ) )
+	const int64_t iHotDiv = std::max ( 1, tOpt.m_iHotDiv );
+	const int64_t iHotGB = std::max ( 1, tOpt.m_iHotGB );
+	if ( pIndex->m_tHdr.m_dFields.size()<=8 && tOpt.m_bHotStore )
 	{
 		std::unordered_map<const TermInfo_t*,int> hUse;
 		for ( int i : dDocOnly )
@@ -1040,6 +1078,17 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			iEscapeCap += std::min<int64_t> ( p->m_iDocs, p->m_iHits/255 );	// at most hits/255 documents can hold >= 255 hits
 		}
 		m_iHotEscapeCap = (int)std::min<int64_t> ( iEscapeCap, 1<<26 );
+		m_dHotBlkStart.assign ( 1, 0u );
+		for ( const DevLeaf_t & t : m_dHotTerms )
+			m_dHotBlkStart.push_back ( m_dHotBlkStart.back()+t.m_nBlocks );
+		// indexes with <= 4 fields: per-field presence bitmaps next to the u16 rows (orbits_kernel)
+		m_nHotBitFields = ( pIndex->m_tHdr.m_dFields.size()<=4 && !pIndex->m_tHdr.m_dFields.empty() ) ? (int)pIndex->m_tHdr.m_dFields.size() : 0;
+		// keywords in >= 1/3 of the rows (any keyword whose idf can turn negative) also get two tf-level bitmaps
+		m_dHotLvlSlot.assign ( m_dHotTerms.size(), -1 );
+		if ( m_nHotBitFields )
+			for ( size_t h=0; h<m_dHotTerms.size(); ++h )
+				if ( (int64_t)m_dHotTerms[h].m_nDocs*3>=(int64_t)uRows )
+					m_dHotLvlSlot[h] = m_nHotLvl++;
 		if ( !m_dHotTerms.empty() )
 			for ( int i : dDocOnly )
 			{
@@ -1059,13 +1108,15 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			}
 	}
 
+	// launch class 5 runs on the presence bitmaps when the store has them (every index class 5 admits has <= 4 fields)
+	m_iOrMode = ( tOpt.m_bOrBits && m_nHotBitFields>0 && !m_dHotTerms.empty() ) ? 3 : 1;
 	fnMark ( "hot keywords" );
 	// pure AND queries led by a sparse keyword go to the intersection kernel, the rest of the doc-only ones to dense tiles
-	const int64_t OR_RANGE_TILES = getenv ( "MGPU_OR_RANGE_TILES" ) ? std::max ( 1, atoi ( getenv ( "MGPU_OR_RANGE_TILES" ) ) ) : 1024;	// 1024 x 2048 = 2M rows per item of class 5 (per-item costs outweigh finer ranges: 262144 rows was 25 % slower)
-	const bool bNoAndKernel = getenv ( "MGPU_NO_AND" )!=nullptr;
-	const bool bNoOrClass = getenv ( "MGPU_NO_ORCLASS" )!=nullptr, bNoDnfClass = getenv ( "MGPU_NO_DNFCLASS" )!=nullptr;	// (experiments)
-	// a group's driver may sit in at most iDnfMul/iDnfDiv of the rows (MGPU_DNF_PCT: percent, for experiments)
-	const int64_t iDnfDiv = 100, iDnfMul = getenv ( "MGPU_DNF_PCT" ) ? std::max ( 1, atoi ( getenv ( "MGPU_DNF_PCT" ) ) ) : 12;
+	const int64_t OR_RANGE_TILES = std::max ( 1, tOpt.m_iOrRangeTiles );	// 1024 x 2048 = 2M rows per item of class 5 (per-item costs outweigh finer ranges: 262144 rows was 25 % slower)
+	const bool bNoAndKernel = !tOpt.m_bAndKernel;
+	const bool bNoOrClass = !tOpt.m_bOrClass, bNoDnfClass = !tOpt.m_bDnfClass;	// (experiments)
+	// a group's driver may sit in at most iDnfMul/iDnfDiv of the rows (option dnf_pct: percent, for experiments)
+	const int64_t iDnfDiv = 100, iDnfMul = std::max ( 1, tOpt.m_iDnfPct );
 	for ( int i : dDocOnly )
 	{
 		// intersection kernel: DNF programs (1 group = pure AND) whose every group is led by a sparse keyword
@@ -1131,7 +1182,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			iTotalWork += fnWork ( m_dPlans[i], c );
 			m_dStack[c] = std::max ( m_dStack[c], m_dPlans[i].m_nStack );
 		}
-		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 || c>=5 ) ? StreamOccupancy ( m_dStack[c], c>=5 ? c-4 : 0 ) : EvalOccupancy ( m_dStack[c] );
+		const int iOcc = ( c==2 || c==4 ) ? AndOccupancy ( c==4 ) : ( c==0 || c==3 || c>=5 ) ? StreamOccupancy ( m_dStack[c], c==5 ? m_iOrMode : c==6 ? 2 : 0 ) : EvalOccupancy ( m_dStack[c] );
 		const int nMaxCtas = pIndex->m_nSMs*iOcc;
 		const int64_t iTarget = std::max<int64_t> ( ( c==0 || c==3 || c>=5 ) ? 262144 : 32768, iTotalWork/( (int64_t)nMaxCtas*4 ) );
 
@@ -1248,6 +1299,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		if ( !m_dItemOrder[i].empty() )
 			CUDA_TRY ( m_dOrder[i].AllocAsync ( m_dItemOrder[i].size(), tAllocStream ), m_sError );
 	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
+	if ( tOpt.m_bStats )
+		CUDA_TRY ( m_dDebug.AllocAsync ( 8, tAllocStream ), m_sError );
 	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4], m_dCtas[5], m_dCtas[6] } )*2*m_iPoolCap;
 	m_nHitpos = std::max ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W, (size_t)m_dCtas[4]*EVAL_WARPS*MAX_LEAVES*32 );
 	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3], m_dCtas[5], m_dCtas[6] } )*PRE_BLOCKS*32;
@@ -1256,6 +1309,10 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	{
 		CUDA_TRY ( m_dHotDesc.AllocAsync ( m_dHotTerms.size(), tAllocStream ), m_sError );
 		CUDA_TRY ( cudaMemcpyAsync ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, tAllocStream ), m_sError );
+		CUDA_TRY ( m_dHotLvlSlotDev.AllocAsync ( m_dHotLvlSlot.size(), tAllocStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dHotLvlSlotDev.m_p, m_dHotLvlSlot.data(), m_dHotLvlSlot.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
+		CUDA_TRY ( m_dHotBlkStartDev.AllocAsync ( m_dHotBlkStart.size(), tAllocStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dHotBlkStartDev.m_p, m_dHotBlkStart.data(), m_dHotBlkStart.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
 	}
 	CUDA_TRY ( m_dItemKeys.AllocAsync ( (size_t)nItems*m_iKMax, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dItemOut.AllocAsync ( nItems, tAllocStream ), m_sError );
@@ -1339,6 +1396,8 @@ int Batch_c::Run()
 
 	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
 	CUDA_TRY ( cudaMemsetAsync ( m_dQueryThr.m_p, 0, (size_t)m_nDevQueries*sizeof(unsigned long long), s ), m_sError );
+	if ( m_dDebug.m_p )
+		CUDA_TRY ( cudaMemsetAsync ( m_dDebug.m_p, 0, 8*sizeof(unsigned long long), s ), m_sError );
 
 	// run-time scratch comes from the index (grow-only, shared by all batches; runs are serialised on the index stream)
 	Index_c::RunScratch_t & tScr = pIndex->m_tScratch;
@@ -1346,13 +1405,17 @@ int Batch_c::Run()
 	CUDA_TRY ( tScr.m_dHitpos.Grow ( m_nHitpos ), m_sError );
 	CUDA_TRY ( tScr.m_dPre.Grow ( m_nPre ), m_sError );
 	if ( m_dCtas[5] || m_dCtas[6] )
-		CUDA_TRY ( tScr.m_dOrList.Grow ( (size_t)std::max ( m_dCtas[5], m_dCtas[6] )*EVAL_WARPS*512*MAX_LEAVES ), m_sError );
+		CUDA_TRY ( tScr.m_dOrList.Grow ( std::max ( (size_t)m_dCtas[5]*StreamOrListCap ( m_iOrMode ), (size_t)m_dCtas[6]*StreamOrListCap ( 2 ) )*EVAL_WARPS ), m_sError );
 	CUDA_TRY ( tScr.m_dPreHitpos.Grow ( m_nPreHitpos ), m_sError );
 	if ( !m_dHotTerms.empty() )
 	{
 		CUDA_TRY ( tScr.m_dHotData.Grow ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
 		CUDA_TRY ( tScr.m_dHotEscape.Grow ( (size_t)m_iHotEscapeCap*3 ), m_sError );
 		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1 ), m_sError );
+		if ( m_nHotBitFields )
+			CUDA_TRY ( tScr.m_dHotBits.Grow ( m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 ) ), m_sError );
+		if ( m_nHotLvl )
+			CUDA_TRY ( tScr.m_dHotLvlBits.Grow ( (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 ) ), m_sError );
 	}
 
 	// K0: decode the batch's hot keywords once into the dense store
@@ -1373,6 +1436,15 @@ int Batch_c::Run()
 		H.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
 		H.m_iStride = m_iHotStride;
 		H.m_bTfClass = pIndex->m_tHdr.m_dFields.size()<=4 ? 1 : 0;
+		H.m_pBlkStart = m_dHotBlkStartDev.m_p;
+		H.m_nBitFields = m_nHotBitFields;
+		H.m_pBits = m_nHotBitFields ? tScr.m_dHotBits.m_p : nullptr;
+		H.m_pLvlSlot = m_nHotLvl ? m_dHotLvlSlotDev.m_p : nullptr;
+		H.m_pLvlBits = m_nHotLvl ? tScr.m_dHotLvlBits.m_p : nullptr;
+		if ( m_nHotLvl )
+			CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotLvlBits.m_p, 0, (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 )*4, s ), m_sError );
+		if ( m_nHotBitFields )
+			CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotBits.m_p, 0, m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 )*4, s ), m_sError );
 		CUDA_TRY ( LaunchHotDecode ( H, pIndex->m_nSMs*8, s ), m_sError );
 		++nLaunches;
 		tHot.m_pData = tScr.m_dHotData.m_p;
@@ -1381,6 +1453,11 @@ int Batch_c::Run()
 		tHot.m_iStride = m_iHotStride;
 		tHot.m_nHot = (int)m_dHotTerms.size();
 		tHot.m_bTfClass = H.m_bTfClass;
+		tHot.m_pBits = H.m_pBits;
+		tHot.m_iBitStride = m_iHotStride/32;
+		tHot.m_nBitFields = m_nHotBitFields;
+		tHot.m_pLvlSlot = H.m_pLvlSlot;
+		tHot.m_pLvlBits = H.m_pLvlBits;
 	}
 	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
 	for ( int c=0; c<NUM_CLASSES; ++c )
@@ -1403,6 +1480,7 @@ int Batch_c::Run()
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
 		P.m_pQueryThr = m_dQueryThr.m_p;
 		P.m_pOrList = c>=5 ? tScr.m_dOrList.m_p : nullptr;
+		P.m_pDebug = c==5 ? m_dDebug.m_p : nullptr;
 		P.m_pItemOrder = ( c>=5 && !m_dItemOrder[c-5].empty() ) ? m_dOrder[c-5].m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;
@@ -1410,7 +1488,7 @@ int Batch_c::Run()
 		if ( c==2 || c==4 )
 			CUDA_TRY ( LaunchAnd ( P, c==4, m_dCtas[c], s ), m_sError );
 		else if ( c==0 || c==3 || c>=5 )
-			CUDA_TRY ( LaunchStream ( P, m_dStack[c], c>=5 ? c-4 : 0, m_dCtas[c], s ), m_sError );
+			CUDA_TRY ( LaunchStream ( P, m_dStack[c], c==5 ? m_iOrMode : c==6 ? 2 : 0, m_dCtas[c], s ), m_sError );
 		else
 			CUDA_TRY ( LaunchEval ( P, m_dStack[c], m_dCtas[c], s ), m_sError );
 		CUDA_TRY ( cudaEventRecord ( m_dEvClass[c], s ), m_sError );
@@ -1462,6 +1540,13 @@ int Batch_c::Sync()
 			}
 		}
 		cudaEventElapsedTime ( &m_tStats.merge_kernel_ms, m_tEv1, m_tEv2 );
+		if ( m_dDebug.m_p )
+		{
+			unsigned long long dDbg[8];
+			if ( cudaMemcpy ( dDbg, m_dDebug.m_p, sizeof(dDbg), cudaMemcpyDeviceToHost )==cudaSuccess )
+				fprintf ( stderr, "[mgpu stats] class 5: %d queries, mini-tiles %llu, candidate rows hot-only %llu, with sparse postings %llu, present rows %llu, %.2f ms\n",
+					m_tStats.class_queries[5], dDbg[0], dDbg[1], dDbg[2], dDbg[4], m_tStats.class_ms[5] );
+		}
 	}
 	return MGPU_OK;
 }

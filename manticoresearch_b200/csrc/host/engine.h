@@ -76,10 +76,34 @@ struct DevBuf_T
 	DevBuf_T & operator= ( const DevBuf_T & ) = delete;
 };
 
+/// Engine options of one index handle (mgpu_index_set_option). The library never reads tuning from the environment: the
+/// embedding process sets what it wants once after mgpu_index_open; the experiment switches exist for A/B measurements.
+struct EngineOptions_t
+{
+	int		m_iPlanThreads = 0;			///< "plan_threads": host threads planning a batch (0 = by batch size, at most 16)
+	int		m_bStats = 0;				///< "stats": print the work counters of the bound + exact pass kernels to stderr after every batch
+	int		m_bTiming = 0;				///< "timing": print the host setup phases of every batch to stderr
+	int		m_bHotStore = 1;			///< "hot_store": decode keywords shared by >= 2 queries once per batch into the dense store
+	int		m_iHotDiv = 200;			///< "hot_div": a hot keyword sits in >= 1/hot_div of the rows
+	int		m_iHotGB = 24;				///< "hot_gb": cap of the dense store
+	int		m_iOrRangeTiles = 1024;		///< "or_range_tiles": rows/2048 per work item of the bound + exact pass classes
+	int		m_iDnfPct = 12;				///< "dnf_pct": a group driver of the intersection kernel sits in < dnf_pct % of the rows
+	int		m_bOrBits = 1;				///< "or_bits": pure OR programs run on orbits_kernel (0: stream_kernel<512,1>)
+	int		m_bOrClass = 1;				///< "or_class": launch class 5 exists (0: its queries take the general tile program)
+	int		m_bDnfClass = 1;			///< "dnf_class": launch class 6 exists
+	int		m_bAndKernel = 1;			///< "and_kernel": the intersection kernel exists
+	int		m_bDnf = 1;					///< "dnf": OR-of-AND-groups programs are recognised
+	int		m_bChain = 1;				///< "chain": AND chains skip ahead when a tile has no candidate left
+	int		m_bRegOr = 1;				///< "reg_or": pure OR programs are recognised
+	int		m_bJump = 1;				///< "jump": pure AND programs jump over tiles by their driver keyword
+	bool	Set ( const char * szName, int64_t iValue );
+};
+
 class Index_c
 {
 public:
 	std::string		m_sError;
+	EngineOptions_t	m_tOpt;
 	IndexHeader_t	m_tHdr;
 	int				m_iDevice = 0;
 	uint32_t		m_uRowidBase = 0;
@@ -99,6 +123,7 @@ public:
 		DevBuf_T<uint64_t>		m_dHitpos, m_dPreHitpos;
 		DevBuf_T<PreEntry_t>	m_dPre, m_dOrList;
 		DevBuf_T<uint16_t>		m_dHotData;
+		DevBuf_T<uint32_t>		m_dHotBits, m_dHotLvlBits;
 		DevBuf_T<uint32_t>		m_dHotEscape;
 		DevBuf_T<int32_t>		m_dHotEscapeCount;
 	} m_tScratch;
@@ -176,6 +201,7 @@ public:
 	DevBuf_T<int32_t>		m_dCounter;
 	std::vector<int32_t>	m_dItemOrder[2];	///< classes 5, 6: items in rowid-range-major order (index relative to the class's first item)
 	DevBuf_T<int32_t>		m_dOrder[2];
+	DevBuf_T<unsigned long long> m_dDebug;		///< option "stats": work counters
 	DevBuf_T<unsigned long long> m_dQueryThr;	///< per device query: shared K-th-best bound of its items
 	DevBuf_T<Key128_t>		m_dItemKeys, m_dScratch, m_dOutKeys;
 	size_t	m_nPool = 0, m_nHitpos = 0, m_nPre = 0, m_nPreHitpos = 0;	///< what Run() needs from the index's RunScratch_t
@@ -186,6 +212,13 @@ public:
 	// dense hot-term store of this batch (rebuilt by every Run(): decode once per batch instead of once per query)
 	std::vector<DevLeaf_t>	m_dHotTerms;
 	DevBuf_T<DevLeaf_t>		m_dHotDesc;
+	std::vector<uint32_t>	m_dHotBlkStart;		///< prefix sums of the hot keywords' block counts
+	DevBuf_T<uint32_t>		m_dHotBlkStartDev;
+	std::vector<int32_t>	m_dHotLvlSlot;		///< per hot keyword: slot of its tf-level bitmaps (keywords in >= 1/3 of the rows), -1 = none
+	DevBuf_T<int32_t>		m_dHotLvlSlotDev;
+	int						m_nHotLvl = 0;
+	int						m_nHotBitFields = 0;	///< > 0: the store also holds per-field presence bitmaps (indexes with <= 4 fields)
+	int						m_iOrMode = 1;			///< kernel of launch class 5: 3 = orbits_kernel, 1 = stream_kernel<512,1>
 	int64_t					m_iHotStride = 0;
 	int						m_iHotEscapeCap = 0;
 	cudaEvent_t				m_tEvHot = nullptr;
@@ -210,6 +243,7 @@ int			EvalOccupancy ( int nStack );
 cudaError_t	LaunchEval ( const EvalParams_t & P, int nStack, int nCtas, cudaStream_t tStream );	///< eval_kernel<hits>
 cudaError_t	LaunchStream ( const EvalParams_t & P, int nStack, int iMode, int nCtas, cudaStream_t tStream );	///< 0 general, 1 pure OR, 2 hot DNF
 int			StreamOccupancy ( int nStack, int iMode );
+int			StreamOrListCap ( int iMode );
 cudaError_t	LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream );
 int			AndOccupancy ( bool bHits );
 cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream );

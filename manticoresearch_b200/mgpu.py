@@ -119,6 +119,7 @@ def load_library(path=None):
         "mgpu_index_open": (C.c_int, [C.c_char_p, C.c_int, u32, C.POINTER(vp)]),
         "mgpu_index_close": (None, [vp]),
         "mgpu_index_set_stream": (C.c_int, [vp, vp]),
+        "mgpu_index_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
         "mgpu_last_error": (C.c_char_p, [vp]),
         "mgpu_index_total_docs": (i64, [vp]),
         "mgpu_index_num_fields": (i32, [vp]),
@@ -156,7 +157,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_index_set_stream", "mgpu_last_error", "mgpu_index_total_docs",
+    "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_index_set_stream", "mgpu_index_set_option", "mgpu_last_error", "mgpu_index_total_docs",
     "mgpu_index_num_fields", "mgpu_index_field_index", "mgpu_index_attr_index", "mgpu_index_word_stats",
     "mgpu_index_word_bytes", "mgpu_search_batch", "mgpu_batch_prepare", "mgpu_batch_run", "mgpu_batch_sync",
     "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_index_last_search_stats", "mgpu_batch_export_keys",
@@ -384,6 +385,12 @@ class Index:
     def set_stream(self, cuda_stream_handle):
         """run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None = private stream"""
         self._lib.mgpu_index_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0))
+
+    def set_option(self, name, value):
+        """engine option of this handle (mgpu_index_set_option): tuning and the A/B switches of the launch classes"""
+        rc = self._lib.mgpu_index_set_option(self._h, name.encode(), int(value))
+        if rc != 0:
+            self._err(rc)
 
     @property
     def total_docs(self):
