@@ -56,6 +56,8 @@ struct DevLeaf_t
 	uint16_t	m_uNodePos;
 	int32_t		m_iHot;				///< slot in the batch's dense hot-term store, -1 = evaluate from the compressed doclist
 	int32_t		m_iTermPos;			///< ExtTermPos_T filter: low 3 bits = TermPosFilter_e (0 none, 1 field start, 2 field end, 3 both, 4 field limit), rest = m_iFieldMaxPos
+	uint32_t	m_uListOff;			///< launch class 5, keywords outside the hot store: first entry of the keyword's decoded posting list (DevPostingLists_t)
+	uint32_t	m_uPad;
 };
 
 /// Dense hot-term store, rebuilt by hot_decode_kernel at the start of every batch run: keywords that many queries of the
@@ -77,6 +79,25 @@ struct DevHotStore_t
 	int32_t				m_iPad;
 	const int32_t *		m_pLvlSlot;		///< [nHot] slot in m_pLvlBits, -1 = none: keywords in >= 1/3 of the rows (the ones whose idf can be negative)
 	const uint32_t *	m_pLvlBits;		///< [slots][2][m_iBitStride]: rows with >= 2 hits, rows with >= 4 hits (tf levels of orbits_kernel's penalty classes)
+};
+
+/// Decoded posting lists of the batch's non-hot keywords that launch class 5 reads (sparse_decode_kernel, once per batch run):
+/// rowids ascending per keyword, value = hits (24 bits, clamped) | field mask<<24 (indexes with <= 8 fields)
+struct DevPostingLists_t
+{
+	const uint32_t *	m_pRows;
+	const uint32_t *	m_pVals;
+};
+
+struct SparseDecodeParams_t
+{
+	DevIndex_t				m_tIndex;
+	const DevLeaf_t *		m_pTerms;		///< [nTerms] doclist descriptors; m_uListOff = where the keyword's list starts
+	const uint32_t *		m_pBlkStart;	///< [nTerms+1] prefix sums of the keywords' block counts
+	int32_t					m_nTerms;
+	int32_t					m_iPad;
+	uint32_t *				m_pRows;
+	uint32_t *				m_pVals;
 };
 
 enum DevOpCode_e : uint8_t
@@ -227,6 +248,7 @@ struct EvalParams_t
 	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]
 	DevHotStore_t			m_tHot;
 	const int32_t *			m_pItemOrder;	///< stream_kernel: the k-th item taken from the queue is item m_pItemOrder[k] (null = k)
+	DevPostingLists_t		m_tLists;
 	unsigned long long *	m_pDebug;		///< [8] work counters of the bound + exact pass kernels (option "stats"), or null
 };
 

@@ -17,6 +17,7 @@
 #include "hit_stage.cuh"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 
 namespace mgpu
@@ -661,6 +662,46 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecode
 						}
 					}
 				}
+			}
+		}
+	}
+}
+
+/// K0b: decodes the non-hot keywords of launch class 5 ONCE per batch into plain posting lists (rowid, hits | fields<<24).
+/// Same flat (keyword, block) walk as K0; block b of a keyword lands at entries [32b, 32b+32) of its list: coalesced stores.
+__global__ void __launch_bounds__ ( EVAL_THREADS ) sparse_decode_kernel ( SparseDecodeParams_t P )
+{
+	__shared__ __align__(16) uint8_t dStage[EVAL_WARPS][STAGE_BYTES];
+	__shared__ uint16_t dRecStart[EVAL_WARPS][34];
+	const int iWarp = threadIdx.x>>5, iLane = threadIdx.x & 31;
+	const uint32_t uWarpGlobal = blockIdx.x*EVAL_WARPS+iWarp, nWarps = gridDim.x*EVAL_WARPS;
+	const uint32_t nTotalBlocks = __ldg ( P.m_pBlkStart+P.m_nTerms );
+	for ( uint32_t g0=uWarpGlobal*HOT_CHUNK; g0<nTotalBlocks; g0+=nWarps*HOT_CHUNK )
+	{
+		int h = 0;
+		{
+			int lo = 0, hi = P.m_nTerms;
+			while ( hi-lo>1 )
+			{
+				const int mid = ( lo+hi )>>1;
+				if ( __ldg ( P.m_pBlkStart+mid )<=g0 ) lo = mid; else hi = mid;
+			}
+			h = lo;
+		}
+		const uint32_t g1 = min ( g0+(uint32_t)HOT_CHUNK, nTotalBlocks );
+		for ( uint32_t g=g0; g<g1; ++g )
+		{
+			while ( g>=__ldg ( P.m_pBlkStart+h+1 ) )
+				++h;
+			const DevLeaf_t tLeaf = P.m_pTerms[h];
+			const uint32_t b = g-__ldg ( P.m_pBlkStart+h );
+			DecodedDoc_t d;
+			DecodeBlock<false> ( P.m_tIndex, tLeaf, b, dStage[iWarp], dRecStart[iWarp], iLane, d );
+			if ( d.m_bValid )
+			{
+				const size_t i = (size_t)tLeaf.m_uListOff + 32u*b + iLane;
+				P.m_pRows[i] = d.m_uRowid;
+				P.m_pVals[i] = min ( d.m_uHits, 0xFFFFFFu ) | ( ( d.m_uFields & 255u )<<24 );
 			}
 		}
 	}
@@ -1735,7 +1776,7 @@ static const size_t OR_WARP_SMEM = 512*4 + 256 + 288*4;
 /// sparse postings one mini-tile of the bound + exact pass kernels can hold, per warp (sizes EvalParams_t::m_pOrList)
 int StreamOrListCap ( int iMode )
 {
-	return iMode==3 ? OB_LIST_CAP : OR_LIST_CAP;
+	return iMode==3 ? 0 : OR_LIST_CAP;	// (orbits_kernel reads the decoded posting lists)
 }
 
 size_t StreamDynSmemBytes ( int nStack, int iMode )
@@ -1765,10 +1806,11 @@ cudaError_t LaunchStream ( const EvalParams_t & P, int nStack, int iMode, int nC
 	const size_t iDyn = StreamDynSmemBytes ( nStack, iMode );
 	if ( iMode==3 )
 	{
-		cudaError_t e = cudaFuncSetAttribute ( orbits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
+		auto fnKernel = P.m_tHot.m_nBitFields<=2 ? orbits_kernel<2> : orbits_kernel<4>;
+		cudaError_t e = cudaFuncSetAttribute ( fnKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iDyn );
 		if ( e!=cudaSuccess )
 			return e;
-		orbits_kernel<<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P );
+		fnKernel<<<nCtas, EVAL_THREADS, iDyn, tStream>>> ( P );
 		return cudaGetLastError();
 	}
 	if ( iMode==1 )
@@ -1794,7 +1836,7 @@ int StreamOccupancy ( int nStack, int iMode )
 {
 	const size_t iDyn = StreamDynSmemBytes ( nStack, iMode );
 	if ( iMode==3 )
-		return StreamOccupancyT ( orbits_kernel, iDyn );
+		return std::min ( StreamOccupancyT ( orbits_kernel<2>, iDyn ), StreamOccupancyT ( orbits_kernel<4>, iDyn ) );
 	if ( iMode==1 )
 		return StreamOccupancyT ( stream_kernel<512,1>, iDyn );
 	if ( iMode==2 )
@@ -1827,6 +1869,12 @@ int AndOccupancy ( bool bHits )
 cudaError_t LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream )
 {
 	hot_decode_kernel<<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
+	return cudaGetLastError();
+}
+
+cudaError_t LaunchSparseDecode ( const SparseDecodeParams_t & P, int nCtas, cudaStream_t tStream )
+{
+	sparse_decode_kernel<<<nCtas, EVAL_THREADS, 0, tStream>>> ( P );
 	return cudaGetLastError();
 }
 

@@ -6,33 +6,37 @@
 // mini-tiles, one 32-bit word (32 rows) per lane and bitmap:
 //
 //  1. bitmap pass, ~1 instruction per 32 rows and keyword: per-field ORs give the matched-field mask F(row) bit-parallel, the
-//     per-keyword presence words P_i go to shared memory; popc ( present ) is the exact total_found.
+//     per-keyword presence words P_i go to shared memory; popc ( present ) is the exact total_found. Keywords outside the hot
+//     store were decoded once per batch run into plain posting lists (sparse_decode_kernel): a per-warp cursor per keyword sets
+//     the bits of the mini-tile's postings in a small shared-memory overlay (per field + "row holds a listed posting").
 //  2. candidate selection, MaxScore style (Turtle & Flood), bit-parallel: a row's weight is at most
 //     rank ( F )*1000 + 500 + 1000*sum over the PRESENT keywords of max ( idf_i, 0 ) (tf < 1; ExtRanker_WeightSum_c,
 //     src/sphinxsearch.cpp:1096-1141). For every rank class fv (value of F) the warp knows how much TF*IDF a row of that class needs
-//     to reach the K-th best weight so far (T); with the hot keywords sorted by their bound, the rows that can still make it are
-//     those holding ALL keywords of a prefix ("required": without one of them the rest cannot reach T) or, if none is required,
-//     ANY keyword of the "essential" prefix (the rest together stays below T). Rows holding a sparse keyword's posting always
+//     to reach the K-th best weight so far; with the hot keywords sorted by their bound, the rows that can still make it are
+//     those holding ALL keywords of a prefix ("required": without one of them the rest cannot reach it) or, if none is required,
+//     ANY keyword of the "essential" prefix (the rest together stays below it). Rows holding a listed posting always
 //     qualify while their class can reach the threshold at all.
 //     Keywords with a NEGATIVE idf (df > N/2: the stop words) lower the weight of nearly every row by about as much as the
 //     rare keywords raise it, so ignoring them leaves ~20 % of the rows as candidates (scripts/or_bound_study.py). Up to two of
 //     them refine the classes by their tf level on the row (absent / 1 hit / 2-3 hits / >= 4 hits, from two more bitmaps the
 //     store keeps for keywords in >= 1/3 of the rows): a row of level l owes at least tf_min ( l )*|idf|, which raises the
-//     TF*IDF its positive keywords must bring. The reachable (rank class, level, level) combinations are listed whenever the
-//     warp's threshold moves; ~1 % of the rows stay candidates.
-//  3. exact pass for the candidate rows only, one lane per row, TF*IDF in op order (ExtOr_c left fold,
-//     src/searchnode.cpp:3486-3504) from the u16 store / the mini-tile's list of sparse postings, ranked and pushed as in K3.
+//     TF*IDF its positive keywords must bring. Selections only get stricter as the levels go up, so a class is listed as
+//     "rows of levels <= (a, b)" and dropped when a neighbour (a+1, b) / (a, b+1) selects the same way; the list is rebuilt
+//     whenever the warp's threshold moves. ~1 % of the rows stay candidates.
+//  3. exact pass for the candidate rows only, 32 at a time, one lane per row, TF*IDF in op order (ExtOr_c left fold,
+//     src/searchnode.cpp:3486-3504): hot keywords from the u16 store, listed ones by a binary search of the part of the posting
+//     list the warp has walked; ranked and pushed as in K3.
 //
-// Everything around it (work items, sparse keyword cursors, candidate pool, on-demand CTA radix select, the query's shared
-// K-th-best bound) is that of stream_kernel<512,1>, which stays available for A/B runs (mgpu_index_set_option "or_bits" = 0).
+// Everything around it (work items, candidate pool, on-demand CTA radix select, the query's shared K-th-best bound) is that
+// of stream_kernel<512,1>, which stays available for A/B runs (mgpu_index_set_option "or_bits" = 0).
 #pragma once
 // (included from kernels.cu inside namespace mgpu, after stream_kernel.cuh)
 
 static const int OB_MINI = 1024;					///< rows per warp step: one bitmap word per lane
-static const int OB_LIST_CAP = OB_MINI*MAX_LEAVES;	///< sparse postings of one mini-tile
-static const int OB_QUEUE = 32 + OB_MINI;			///< per-warp queue of candidate rows (its free tail doubles as the compaction scratch)
+static const int OB_QUEUE = 32 + OB_MINI;			///< per-warp queue of candidate rows
 static const size_t OB_WARP_SMEM = ( MAX_LEAVES*32 + OB_QUEUE )*4;
-static const int OB_MAX_CLASSES = 96;				///< reachable (rank class, level, level) combinations listed per warp; more -> levels are ignored
+static const int OB_MAX_CLASSES = 64;				///< (rank class, level, level) combinations listed per warp; more -> levels are ignored
+static const uint32_t OB_LISTED = 0x80000000u;		///< queue entry: the row holds a listed (non-hot) posting
 
 struct OrBitsShared_t
 {
@@ -53,44 +57,77 @@ struct OrBitsShared_t
 	int32_t			m_dSuffix[MAX_LEAVES+1];			///< sum of m_dUb[i..]
 	uint8_t			m_dSortLeaf[MAX_LEAVES];			///< the sorted entry's leaf
 	int32_t			m_nHot;
-	int32_t			m_iUbSparse;						///< the same bound summed over the sparse keywords
+	int32_t			m_iUbListed;						///< the same bound summed over the listed keywords
 	// penalty classes: up to two hot keywords with idf < 0 that own tf-level bitmaps
 	int32_t			m_nNeg;
 	int32_t			m_dNegPsm[2];						///< the keyword's entry in the sorted list (its presence word)
 	const uint32_t * m_dNegLvl[2];						///< its ">= 2 hits" bitmap (">= 4 hits": + bit stride)
 	int32_t			m_dNegPen[2][4];					///< what a row of tf level l owes at least, in the bound's fixed point
-	uint32_t		m_dClass[EVAL_WARPS][OB_MAX_CLASSES];	///< fv | l1<<4 | l2<<7 | mode<<10 | prefix length<<16 (level 4 = any)
+	uint32_t		m_dClass[EVAL_WARPS][OB_MAX_CLASSES];	///< fv | a<<4 | b<<7 | mode<<10 | prefix length<<16: rows of rank class fv and levels <= (a, b)
 	// exact pass: op order
-	const uint16_t * m_dOpPtr[MAX_LEAVES];				///< the op's row of the u16 store (null = sparse keyword)
+	const uint16_t * m_dOpPtr[MAX_LEAVES];				///< the op's row of the u16 store (null = listed keyword)
+	uint8_t			m_dOpList[MAX_LEAVES];				///< listed keyword: its entry in the arrays below
 	uint8_t			m_dHotLeaf[MAX_LEAVES];
 	const uint16_t * m_dHotPtr[MAX_LEAVES+4];
 	int32_t			m_nHotOps;
-	uint8_t			m_dSparseOp[MAX_LEAVES];
-	int32_t			m_nSparseOps;
+	// listed keywords
+	uint8_t			m_dListLeaf[MAX_LEAVES];
+	uint32_t		m_dListEnd[MAX_LEAVES];				///< one past the keyword's last entry
+	int32_t			m_nListed;
+	uint32_t		m_dListBeg[EVAL_WARPS][MAX_LEAVES];	///< first entry at/after the warp's first row
+	uint32_t		m_dListCur[EVAL_WARPS][MAX_LEAVES];	///< first entry at/after the warp's position
+	uint32_t		m_dListNext[EVAL_WARPS][MAX_LEAVES];	///< its rowid (0xFFFFFFFF = exhausted)
 	float			m_dTf[256];
-	uint32_t		m_dCur[EVAL_WARPS][MAX_LEAVES];
-	uint32_t		m_dCached[EVAL_WARPS][MAX_LEAVES];
-	uint16_t		m_dOpStart[EVAL_WARPS][MAX_LEAVES+2];
-	uint32_t		m_dNext[EVAL_WARPS][MAX_LEAVES];
-	uint32_t		m_dOv[EVAL_WARPS][5][32];			///< sparse postings of the mini-tile: per-field bitmaps [0..3], rows holding any [4]
-	uint16_t		m_dRecStart[EVAL_WARPS][34];
-	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
+	uint32_t		m_dOv[EVAL_WARPS][5][32];			///< listed postings of the mini-tile: per-field bitmaps [0..3], rows holding any [4]
 };
 
+/// first entry of pRows[uFrom, uTo) with a rowid >= uRow (uTo if none); every lane gets the result
+__device__ __forceinline__ uint32_t ListLowerBound ( const uint32_t * __restrict__ pRows, uint32_t uFrom, uint32_t uTo, uint32_t uRow, int iLane )
+{
+	uint32_t a = uFrom, b = uTo;
+	while ( b-a>32u )
+	{
+		// 32 probes split [a, b) into 33 parts
+		const uint32_t uStep = ( b-a )/33u + 1u;
+		const uint32_t i = a + ( iLane+1 )*uStep;
+		const bool bGe = i>=b || __ldg ( pRows+i )>=uRow;
+		const unsigned m = __ballot_sync ( FULL_MASK, bGe );
+		const int k = m ? __ffs ( m )-1 : 32;	// probes 0..k-1 are below uRow, probe k is not
+		const uint32_t uNewA = k ? a + k*uStep + 1u : a;
+		b = k<32 ? min ( b, a + ( k+1 )*uStep ) : b;
+		a = min ( uNewA, b );
+	}
+	const uint32_t i = a+iLane;
+	const bool bGe = i>=b || __ldg ( pRows+i )>=uRow;
+	const unsigned m = __ballot_sync ( FULL_MASK, bGe );
+	return min ( b, a + ( m ? __ffs ( m )-1 : 32 ) );
+}
+
+/// one lane: value of rowid uRow in pRows[uFrom, uTo) (sorted), 0 if absent
+__device__ __forceinline__ uint32_t ListFind ( const DevPostingLists_t & tLists, uint32_t uFrom, uint32_t uTo, uint32_t uRow )
+{
+	uint32_t lo = uFrom, hi = uTo;
+	while ( lo<hi )
+	{
+		const uint32_t mid = lo + ( ( hi-lo )>>1 );
+		if ( __ldg ( tLists.m_pRows+mid )<uRow ) lo = mid+1; else hi = mid;
+	}
+	return ( lo<uTo && __ldg ( tLists.m_pRows+lo )==uRow ) ? __ldg ( tLists.m_pVals+lo ) : 0u;
+}
+
+/// NF = 2: indexes with <= 2 fields, 4: three or four
+template<int NF>
 __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams_t P )
 {
 	extern __shared__ __align__(16) uint8_t dDyn[];
 	__shared__ OrBitsShared_t S;
 	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
 	const DevIndex_t & tIdx = P.m_tIndex;
+	const DevPostingLists_t & tLists = P.m_tLists;
 
 	uint32_t * pPsm = reinterpret_cast<uint32_t *>( dDyn + (size_t)iWarp*OB_WARP_SMEM );	// [MAX_LEAVES][32] presence words of the hot keywords
 	uint32_t * pQueue = pPsm + MAX_LEAVES*32;												// [OB_QUEUE]
 	Key128_t * pPool0 = P.m_pPool + (size_t)blockIdx.x*2*P.m_iPoolCap;
-	PreEntry_t * pCache0 = P.m_pPre + ( (size_t)blockIdx.x*EVAL_WARPS+iWarp )*MAX_LEAVES*32;
-	PreEntry_t * pList = P.m_pOrList + ( (size_t)blockIdx.x*EVAL_WARPS+iWarp )*OB_LIST_CAP;
-	uint8_t * pStage = S.m_dStage[iWarp];
-	uint16_t * pRecStart = S.m_dRecStart[iWarp];
 	uint32_t ( &dOv )[5][32] = S.m_dOv[iWarp];
 	const size_t iBitStride = (size_t)P.m_tHot.m_iBitStride;
 	{
@@ -124,12 +161,6 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 			S.m_tThr.m_uHi = 0; S.m_tThr.m_uLo = 0;
 			S.m_uTotal = 0;
 		}
-		if ( iLane<MAX_LEAVES )
-		{
-			S.m_dCur[iWarp][iLane] = 0;
-			S.m_dCached[iWarp][iLane] = 0xFFFFFFFFu;
-			S.m_dNext[iWarp][iLane] = 0;
-		}
 		__syncthreads();
 		const DevQuery_t & q = S.m_tQ;
 		const int iK = q.m_iMaxMatches;
@@ -159,7 +190,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 		}
 		if ( tid==32 )
 		{
-			int nHot = 0, nHotOps = 0, nSparse = 0, iUbSparse = 0;
+			int nHot = 0, nHotOps = 0, nListed = 0, iUbListed = 0;
 			const uint32_t uIndexFields = ( 1u<<P.m_tHot.m_nBitFields )-1u;
 			for ( int iOp=0; iOp<q.m_nOps && iOp<MAX_LEAVES; ++iOp )
 			{
@@ -171,8 +202,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 				S.m_dOpPtr[iOp] = nullptr;
 				if ( tLeaf.m_iHot<0 )
 				{
-					S.m_dSparseOp[nSparse++] = (uint8_t)iOp;
-					iUbSparse += iUb;
+					S.m_dOpList[iOp] = (uint8_t)nListed;
+					S.m_dListLeaf[nListed] = (uint8_t)l;
+					S.m_dListEnd[nListed] = tLeaf.m_nBlocks ? tLeaf.m_uListOff+tLeaf.m_nDocs : 0u;	// (a keyword the index does not hold has no list)
+					++nListed;
+					iUbListed += iUb;
 					continue;
 				}
 				const uint16_t * pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
@@ -227,11 +261,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 			S.m_nNeg = nNeg;
 			S.m_nHot = nHot;
 			S.m_nHotOps = nHotOps;
-			S.m_nSparseOps = nSparse;
-			S.m_iUbSparse = iUbSparse;
+			S.m_nListed = nListed;
+			S.m_iUbListed = iUbListed;
 		}
 		int iMyTotal = 0;
-		uint32_t uDbgMinis = 0, uDbgHot = 0, uDbgSparse = 0;
+		uint32_t uDbgMinis = 0, uDbgHot = 0, uDbgListed = 0;
 
 		// this warp's contiguous share of the item
 		const uint32_t nMinis = ( tItem.m_uRowHi-tItem.m_uRowLo+OB_MINI-1 )/OB_MINI;
@@ -241,13 +275,35 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 
 		__syncthreads();	// S.m_nHot and friends
 		int nQueue = 0;
-		uint32_t uNextSparse = 0;
-		const int nOps = q.m_nOps, nHot = S.m_nHot, nHotOps = S.m_nHotOps, nSparseOps = S.m_nSparseOps;
-		const int iUbHot = S.m_dSuffix[0], iUbSparse = S.m_iUbSparse;
+		const int nOps = q.m_nOps, nHot = S.m_nHot, nHotOps = S.m_nHotOps, nListed = S.m_nListed;
+		const int iUbHot = S.m_dSuffix[0], iUbListed = S.m_iUbListed;
 		const int iIndexWeight = q.m_iIndexWeight;
 		const int nFv = 1<<P.m_tHot.m_nBitFields;
 		const int nNeg = S.m_nNeg;
 		uint32_t * pClass = S.m_dClass[iWarp];
+
+		// listed keywords: where this warp's rows start in each posting list
+		uint32_t uNextListed = 0xFFFFFFFFu;
+		for ( int iSp=0; iSp<nListed; ++iSp )
+		{
+			const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dListLeaf[iSp]];
+			const uint32_t uEnd = S.m_dListEnd[iSp];
+			uint32_t uBeg = uEnd, uNext = 0xFFFFFFFFu;
+			if ( uEnd && uMini0<uMini1 )
+			{
+				uBeg = ListLowerBound ( tLists.m_pRows, tLeaf.m_uListOff, uEnd, tItem.m_uRowLo + uMini0*OB_MINI, iLane );
+				if ( uBeg<uEnd )
+					uNext = __ldg ( tLists.m_pRows+uBeg );
+			}
+			if ( iLane==0 )
+			{
+				S.m_dListBeg[iWarp][iSp] = uBeg;
+				S.m_dListCur[iWarp][iSp] = uBeg;
+				S.m_dListNext[iWarp][iSp] = uNext;
+			}
+			uNextListed = min ( uNextListed, uNext );
+		}
+		__syncwarp();
 
 		// ranks one evaluated row and pushes it if it beats the K-th best key so far (one row per lane)
 		auto fnRankPush = [&] ( bool bRow, float fT, uint32_t uF, uint32_t uRow, Key128_t * pPool, const Key128_t & tThr )
@@ -271,33 +327,72 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 					pPool[iSlot + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tKey;
 			}
 		};
-		// exact TF*IDF of one queued row per lane from the hot keywords alone (the row holds no sparse posting), in op order
-		auto fnExactHot = [&] ( bool bAct, uint32_t uRow, Key128_t * pPool, const Key128_t & tThr )
+		// exact TF*IDF of one queued row per lane, in op order. Rows without a listed posting (the bulk) only read the hot keywords.
+		auto fnExact = [&] ( bool bAct, uint32_t uEntry, Key128_t * pPool, const Key128_t & tThr )
 		{
+			const uint32_t uRow = uEntry & ~OB_LISTED;
 			float fT = 0.0f;
 			uint32_t uF = 0;
 			bool bPres = false;
-			for ( int h0=0; h0<nHotOps; h0+=4 )
+			if ( !__any_sync ( FULL_MASK, bAct && ( uEntry & OB_LISTED ) ) )
 			{
-				uint32_t dRaw[4];
-				#pragma unroll
-				for ( int i=0; i<4; ++i )
-					dRaw[i] = ( bAct && h0+i<nHotOps ) ? __ldg ( S.m_dHotPtr[h0+i]+uRow ) : 0u;
-				#pragma unroll
-				for ( int i=0; i<4; ++i )
+				for ( int h0=0; h0<nHotOps; h0+=4 )
 				{
-					const uint32_t uHits = dRaw[i] & 255u;
-					if ( !uHits )
+					uint32_t dRaw[4];
+					#pragma unroll
+					for ( int i=0; i<4; ++i )
+						dRaw[i] = ( bAct && h0+i<nHotOps ) ? __ldg ( S.m_dHotPtr[h0+i]+uRow ) : 0u;
+					#pragma unroll
+					for ( int i=0; i<4; ++i )
+					{
+						const uint32_t uHits = dRaw[i] & 255u;
+						if ( !uHits )
+							continue;
+						const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dHotLeaf[h0+i]];
+						const uint32_t uFields = ( dRaw[i]>>8 ) & tLeaf.m_uQueriedFields;
+						if ( !uFields )
+							continue;
+						float fBase = S.m_dTf[uHits];
+						if ( bAnyEscape && uHits==255 )
+							fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
+						const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+						// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
+						fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
+						uF |= uFields;
+						bPres = true;
+					}
+				}
+			} else
+			{
+				const bool bListed = bAct && ( uEntry & OB_LISTED );
+				for ( int iOp=0; iOp<nOps; ++iOp )
+				{
+					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+					const uint16_t * pRow = S.m_dOpPtr[iOp];
+					uint32_t uHits = 0, uFields = 0;
+					float fBase = 0.0f;
+					if ( pRow )
+					{
+						const uint32_t uRaw = bAct ? __ldg ( pRow+uRow ) : 0u;
+						uHits = uRaw & 255u;
+						uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
+						fBase = S.m_dTf[uHits];
+						if ( bAnyEscape && uHits==255 )
+							fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
+					} else if ( bListed )
+					{
+						// the row lies in the part of the list this warp has walked
+						const int iSp = S.m_dOpList[iOp];
+						const uint32_t uVal = ListFind ( tLists, S.m_dListBeg[iWarp][iSp], S.m_dListCur[iWarp][iSp], uRow );
+						uHits = uVal & 0xFFFFFFu;
+						uFields = ( uVal>>24 ) & tLeaf.m_uQueriedFields;
+						// ExtTerm_T::GetDocsChunk, src/searchnode.cpp:1946
+						const float fHits = __uint2float_rn ( uHits );
+						fBase = uHits<255u ? S.m_dTf[uHits] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
+					}
+					if ( !uHits || !uFields )
 						continue;
-					const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dHotLeaf[h0+i]];
-					const uint32_t uFields = ( dRaw[i]>>8 ) & tLeaf.m_uQueriedFields;
-					if ( !uFields )
-						continue;
-					float fBase = S.m_dTf[uHits];
-					if ( bAnyEscape && uHits==255 )
-						fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
 					const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
-					// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
 					fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
 					uF |= uFields;
 					bPres = true;
@@ -343,15 +438,15 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 			}
 			Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 			Key128_t tThrCur;	// the warp's current bound of the K-th best key
-			int nClasses = 0;	// reachable (rank class, tf level of negative keyword 1, of negative keyword 2) combinations in pClass
+			int nClasses = 0;	// listed (rank class, level bound of negative keyword 1, of negative keyword 2) combinations in pClass
 			// how the rows of a class are selected given the TF*IDF its positive keywords must bring: mode 0 = no row can reach the
-			// threshold, 1 = only rows holding a sparse posting, 2 = every row, 3 = rows holding all of the first n hot keywords,
-			// 4 = rows holding any of the first n hot keywords (3, 4: or a sparse posting)
+			// threshold, 1 = only rows holding a listed posting, 2 = every row, 3 = rows holding all of the first n hot keywords,
+			// 4 = rows holding any of the first n hot keywords (3, 4: or a listed posting). Stricter as the need grows.
 			auto fnMode = [&] ( int iNeed ) -> uint32_t
 			{
 				if ( iNeed<=0 )
 					return 2u<<10;
-				if ( iNeed>iUbHot+iUbSparse )
+				if ( iNeed>iUbHot+iUbListed )
 					return 0u;
 				if ( iNeed>iUbHot )
 					return 1u<<10;
@@ -393,18 +488,18 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 						uint32_t uEntry = 0;
 						if ( c<nCombos )
 						{
-							const int fv = 1 + c/( nL1*nL2 ), l1 = ( c/nL2 ) % nL1, l2 = c % nL2;
+							const int fv = 1 + c/( nL1*nL2 ), a = ( c/nL2 ) % nL1, b = c % nL2;
 							const int iBaseNeed = iThrFx - S.m_dRankUb[fv];
-							// even the rows owing the most need nothing: one class for the whole rank class
-							const bool bAll = iBaseNeed + ( nL1>1 ? S.m_dNegPen[0][3] : 0 ) + ( nL2>1 ? S.m_dNegPen[1][3] : 0 )<=0;
-							if ( bAll )
-								uEntry = ( l1 | l2 ) ? 0u : ( (uint32_t)fv | ( 4u<<4 ) | ( 4u<<7 ) | ( 2u<<10 ) );
-							else
-							{
-								const uint32_t uMode = fnMode ( iBaseNeed + ( nL1>1 ? S.m_dNegPen[0][l1] : 0 ) + ( nL2>1 ? S.m_dNegPen[1][l2] : 0 ) );
-								if ( uMode )
-									uEntry = (uint32_t)fv | ( (uint32_t)( nL1>1 ? l1 : 4 )<<4 ) | ( (uint32_t)( nL2>1 ? l2 : 4 )<<7 ) | uMode;
-							}
+							const int iPenA = nL1>1 ? S.m_dNegPen[0][a] : 0, iPenB = nL2>1 ? S.m_dNegPen[1][b] : 0;
+							const uint32_t uMode = fnMode ( iBaseNeed + iPenA + iPenB );
+							// rows of levels <= (a, b) under this selection; the same selection one level up covers them
+							bool bKeep = uMode!=0;
+							if ( bKeep && a+1<nL1 )
+								bKeep = fnMode ( iBaseNeed + S.m_dNegPen[0][a+1] + iPenB )!=uMode;
+							if ( bKeep && b+1<nL2 )
+								bKeep = fnMode ( iBaseNeed + iPenA + S.m_dNegPen[1][b+1] )!=uMode;
+							if ( bKeep )
+								uEntry = (uint32_t)fv | ( (uint32_t)( nL1>1 ? a : 3 )<<4 ) | ( (uint32_t)( nL2>1 ? b : 3 )<<7 ) | uMode;
 						}
 						const unsigned m = __ballot_sync ( FULL_MASK, uEntry!=0 );
 						const int iSlot = n + __popc ( m & ( ( 1u<<iLane )-1u ) );
@@ -434,121 +529,90 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 				const uint32_t uLo = tItem.m_uRowLo + uMini*OB_MINI;
 				const uint32_t uHi = min ( uLo+(uint32_t)OB_MINI, tItem.m_uRowHi );
 
-				// no hot keyword: jump to the next mini-tile a sparse keyword touches
-				if ( !nHot )
+				// no hot keyword: jump to the next mini-tile a listed keyword touches
+				if ( !nHot && uNextListed>=uHi )
 				{
-					uint32_t uNext = 0xFFFFFFFFu;
-					for ( int iSp=0; iSp<nSparseOps; ++iSp )
-						uNext = min ( uNext, S.m_dNext[iWarp][q.m_dOps[S.m_dSparseOp[iSp]].m_uLeaf] );
-					if ( uNext>=uHi )
-					{
-						if ( uNext==0xFFFFFFFFu || uNext>=tItem.m_uRowHi )
-							uMini = uMini1;
-						else
-							uMini = max ( uMini+1, ( uNext-tItem.m_uRowLo )/OB_MINI );
-						continue;
-					}
-				}
-
-				// sparse keywords' postings of this mini-tile, gathered into a short per-warp list in op order
-				int nList = 0;
-				if ( uNextSparse<uHi )
-				{
-					for ( int iSp=0; iSp<nSparseOps; ++iSp )
-					{
-						const int l = q.m_dOps[S.m_dSparseOp[iSp]].m_uLeaf;
-						const DevLeaf_t & tLeaf = q.m_dLeaves[l];
-						if ( iLane==0 )
-							S.m_dOpStart[iWarp][iSp] = (uint16_t)nList;
-						if ( S.m_dNext[iWarp][l]>=uHi )
-							continue;
-						const uint32_t * pBase = tIdx.m_pBlkRowid + tLeaf.m_uFirstBlk;
-						uint32_t b = tLeaf.m_nBlocks ? StreamSeek ( pBase, tLeaf.m_nBlocks, S.m_dCur[iWarp][l], uLo, iLane ) : 0;
-						uint32_t uNextRow = 0xFFFFFFFFu;
-						while ( b<tLeaf.m_nBlocks )
-						{
-							const uint32_t uBase = __ldg ( pBase+b );
-							if ( uBase>=uHi )
-							{
-								uNextRow = uBase;
-								break;
-							}
-							const uint32_t uNextBase = b+1<tLeaf.m_nBlocks ? __ldg ( pBase+b+1 ) : 0xFFFFFFFFu;
-							StreamCacheBlock ( tIdx, tLeaf, b, &S.m_dCached[iWarp][l], pCache0+l*32, pStage, pRecStart, S.m_dTf, iLane );
-							PreEntry_t tEntry = pCache0[l*32+iLane];
-							const bool bIn = tEntry.m_uRowid>=uLo && tEntry.m_uRowid<uHi;
-							const unsigned m = __ballot_sync ( FULL_MASK, bIn );
-							if ( bIn )
-							{
-								tEntry.m_uRowid -= uLo;	// slot inside the mini-tile
-								pList[nList + __popc ( m & ( ( 1u<<iLane )-1u ) )] = tEntry;
-							}
-							nList += __popc ( m );
-							if ( uNextBase>uHi )
-							{
-								const uint32_t r = pCache0[l*32+iLane].m_uRowid;
-								uint32_t uMin = ( r!=0xFFFFFFFFu && r>=uHi ) ? r : 0xFFFFFFFFu;
-								#pragma unroll
-								for ( int iStep=16; iStep; iStep>>=1 )
-									uMin = min ( uMin, __shfl_xor_sync ( FULL_MASK, uMin, iStep ) );
-								uNextRow = min ( uMin, uNextBase );
-								break;
-							}
-							++b;
-						}
-						__syncwarp();
-						if ( iLane==0 )
-						{
-							S.m_dCur[iWarp][l] = b;
-							S.m_dNext[iWarp][l] = uNextRow;
-						}
-					}
-					if ( iLane==0 )
-						S.m_dOpStart[iWarp][nSparseOps] = (uint16_t)nList;
-					__syncwarp();
-					// the next mini-tile any sparse keyword can touch
-					uNextSparse = 0xFFFFFFFFu;
-					for ( int iSp=0; iSp<nSparseOps; ++iSp )
-						uNextSparse = min ( uNextSparse, S.m_dNext[iWarp][q.m_dOps[S.m_dSparseOp[iSp]].m_uLeaf] );
+					if ( uNextListed==0xFFFFFFFFu || uNextListed>=tItem.m_uRowHi )
+						uMini = uMini1;
+					else
+						uMini = max ( uMini+1, ( uNextListed-tItem.m_uRowLo )/OB_MINI );
+					continue;
 				}
 
 				// the bitmap lines two mini-tiles ahead (one 128 B line per keyword and field)
 				const uint32_t uWord = ( uLo>>5 ) + iLane;
 				if ( uLo+3*OB_MINI<=tItem.m_uRowHi )
-					for ( int i=iLane; i<nHot*4; i+=32 )
-						if ( ( S.m_dBitFields[i>>2]>>( i & 3 ) ) & 1u )
-							asm volatile ( "prefetch.global.L2 [%0];" :: "l" ( S.m_dBitPtr[i>>2] + ( i & 3 )*iBitStride + ( uLo>>5 ) + 64 ) );
+					for ( int i=iLane; i<nHot*NF; i+=32 )
+						if ( ( S.m_dBitFields[i/NF]>>( i%NF ) ) & 1u )
+							asm volatile ( "prefetch.global.L2 [%0];" :: "l" ( S.m_dBitPtr[i/NF] + ( i%NF )*iBitStride + ( uLo>>5 ) + 64 ) );
 
-				// sparse overlay: per-field bitmaps of the listed postings, and the rows holding any
-				uint32_t dF[4] = { 0, 0, 0, 0 };
-				uint32_t uSparseRows = 0;
-				if ( nList )
+				// listed keywords' postings of this mini-tile -> overlay: per-field bitmaps, and the rows holding any
+				uint32_t dF[NF];
+				#pragma unroll
+				for ( int f=0; f<NF; ++f )
+					dF[f] = 0;
+				uint32_t uListedRows = 0;
+				if ( uNextListed<uHi )
 				{
 					#pragma unroll
 					for ( int k=0; k<5; ++k )
 						dOv[k][iLane] = 0;
 					__syncwarp();
-					for ( int e=iLane; e<nList; e+=32 )
+					uNextListed = 0xFFFFFFFFu;
+					for ( int iSp=0; iSp<nListed; ++iSp )
 					{
-						const uint32_t uSlot = pList[e].m_uRowid, uFields = pList[e].m_uFields;
-						const uint32_t uBit = 1u<<( uSlot & 31u );
-						atomicOr ( &dOv[4][uSlot>>5], uBit );
-						#pragma unroll
-						for ( int f=0; f<4; ++f )
-							if ( ( uFields>>f ) & 1u )
-								atomicOr ( &dOv[f][uSlot>>5], uBit );
+						uint32_t uNext = S.m_dListNext[iWarp][iSp];
+						if ( uNext<uHi )
+						{
+							const uint32_t uQueried = q.m_dLeaves[S.m_dListLeaf[iSp]].m_uQueriedFields;
+							const uint32_t uEnd = S.m_dListEnd[iSp];
+							uint32_t uCur = S.m_dListCur[iWarp][iSp];
+							while ( true )
+							{
+								const uint32_t i = uCur+iLane;
+								const uint32_t r = i<uEnd ? __ldg ( tLists.m_pRows+i ) : 0xFFFFFFFFu;
+								const bool bIn = r<uHi;
+								if ( bIn )
+								{
+									const uint32_t uFields = ( __ldg ( tLists.m_pVals+i )>>24 ) & uQueried;
+									if ( uFields )
+									{
+										const uint32_t uSlot = r-uLo, uBit = 1u<<( uSlot & 31u );
+										atomicOr ( &dOv[4][uSlot>>5], uBit );
+										#pragma unroll
+										for ( int f=0; f<NF; ++f )
+											if ( ( uFields>>f ) & 1u )
+												atomicOr ( &dOv[f][uSlot>>5], uBit );
+									}
+								}
+								const int n = __popc ( __ballot_sync ( FULL_MASK, bIn ) );
+								uCur += n;
+								if ( n<32 )
+								{
+									uNext = __shfl_sync ( FULL_MASK, r, n );
+									break;
+								}
+							}
+							__syncwarp();
+							if ( iLane==0 )
+							{
+								S.m_dListCur[iWarp][iSp] = uCur;
+								S.m_dListNext[iWarp][iSp] = uNext;
+							}
+						}
+						uNextListed = min ( uNextListed, uNext );
 					}
 					__syncwarp();
 					#pragma unroll
-					for ( int f=0; f<4; ++f )
+					for ( int f=0; f<NF; ++f )
 						dF[f] = dOv[f][iLane];
-					uSparseRows = dOv[4][iLane];
+					uListedRows = dOv[4][iLane];
 				}
 
 				// 1. bitmap pass: four keywords at a time, all their loads in flight before the first use
 				for ( int i0=0; i0<nHot; i0+=4 )
 				{
-					uint32_t dW[4][4];
+					uint32_t dW[4][NF];
 					#pragma unroll
 					for ( int j=0; j<4; ++j )
 					{
@@ -556,59 +620,67 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 						const uint32_t uMask = b ? S.m_dBitFields[i0+j] : 0u;
 						const uint32_t * p = S.m_dBitPtr[b ? i0+j : 0] + uWord;
 						#pragma unroll
-						for ( int f=0; f<4; ++f )
+						for ( int f=0; f<NF; ++f )
 							dW[j][f] = ( ( uMask>>f ) & 1u ) ? __ldg ( p + f*iBitStride ) : 0u;
 					}
 					#pragma unroll
 					for ( int j=0; j<4; ++j )
 						if ( i0+j<nHot )
 						{
+							uint32_t uAny = 0;
 							#pragma unroll
-							for ( int f=0; f<4; ++f )
+							for ( int f=0; f<NF; ++f )
+							{
 								dF[f] |= dW[j][f];
-							pPsm[( i0+j )*32+iLane] = dW[j][0] | dW[j][1] | dW[j][2] | dW[j][3];
+								uAny |= dW[j][f];
+							}
+							pPsm[( i0+j )*32+iLane] = uAny;
 						}
 				}
 				++uDbgMinis;
-				const uint32_t uPresent = dF[0] | dF[1] | dF[2] | dF[3];
-				iMyTotal += __popc ( uPresent );	// rows at/after the item's end are never present: store and bitmaps are zero there
+				uint32_t uPresent = 0;
+				#pragma unroll
+				for ( int f=0; f<NF; ++f )
+					uPresent |= dF[f];
+				iMyTotal += __popc ( uPresent );	// rows at/after the item's end are never present: store, bitmaps and lists hold none
 
-				// 2. candidate rows per reachable class
+				// 2. candidate rows per listed class
 				uint32_t uCand = 0;
 				if ( __any_sync ( FULL_MASK, uPresent!=0 ) )
 				{
-					// tf levels of the negative keywords on this lane's rows: absent / 1 hit / 2-3 hits / >= 4 hits
-					uint32_t dL1[4] = { 0, 0, 0, 0 }, dL2[4] = { 0, 0, 0, 0 };
+					// rows whose negative keywords sit at tf level <= 0 (absent), <= 1 (1 hit), <= 2 (2-3 hits), any
+					uint32_t dT1[3] = { 0, 0, 0 }, dT2[3] = { 0, 0, 0 };
 					if ( nNeg>=1 )
 					{
 						const uint32_t uP = pPsm[S.m_dNegPsm[0]*32+iLane], u2 = __ldg ( S.m_dNegLvl[0]+uWord ), u4 = __ldg ( S.m_dNegLvl[0]+iBitStride+uWord );
-						dL1[0] = ~uP; dL1[1] = uP & ~u2; dL1[2] = uP & u2 & ~u4; dL1[3] = uP & u4;
+						dT1[0] = ~uP; dT1[1] = ~( uP & u2 ); dT1[2] = ~( uP & u4 );
 					}
 					if ( nNeg>=2 )
 					{
 						const uint32_t uP = pPsm[S.m_dNegPsm[1]*32+iLane], u2 = __ldg ( S.m_dNegLvl[1]+uWord ), u4 = __ldg ( S.m_dNegLvl[1]+iBitStride+uWord );
-						dL2[0] = ~uP; dL2[1] = uP & ~u2; dL2[2] = uP & u2 & ~u4; dL2[3] = uP & u4;
+						dT2[0] = ~uP; dT2[1] = ~( uP & u2 ); dT2[2] = ~( uP & u4 );
 					}
 					int iPrevFv = 0;
 					uint32_t uFvRows = 0;
 					for ( int iCls=0; iCls<nClasses; ++iCls )
 					{
 						const uint32_t uCode = pClass[iCls];	// (same address in every lane)
-						const int fv = (int)( uCode & 15u ), l1 = (int)( ( uCode>>4 ) & 7u ), l2 = (int)( ( uCode>>7 ) & 7u );
+						const int fv = (int)( uCode & 15u ), a = (int)( ( uCode>>4 ) & 7u ), b = (int)( ( uCode>>7 ) & 7u );
 						const uint32_t uSelMode = ( uCode>>10 ) & 7u;
 						if ( fv!=iPrevFv )
 						{
 							uFvRows = uPresent;
 							#pragma unroll
-							for ( int f=0; f<4; ++f )
+							for ( int f=0; f<NF; ++f )
 								uFvRows &= ( ( fv>>f ) & 1 ) ? dF[f] : ~dF[f];
 							iPrevFv = fv;
 						}
 						uint32_t m = uFvRows;
-						m &= l1==0 ? dL1[0] : l1==1 ? dL1[1] : l1==2 ? dL1[2] : l1==3 ? dL1[3] : 0xFFFFFFFFu;
-						m &= l2==0 ? dL2[0] : l2==1 ? dL2[1] : l2==2 ? dL2[2] : l2==3 ? dL2[3] : 0xFFFFFFFFu;
+						m &= a==0 ? dT1[0] : a==1 ? dT1[1] : a==2 ? dT1[2] : 0xFFFFFFFFu;
+						m &= b==0 ? dT2[0] : b==1 ? dT2[1] : b==2 ? dT2[2] : 0xFFFFFFFFu;
+						m &= ~uCand;
 						if ( uSelMode==1 )
-							m &= uSparseRows;
+							m &= uListedRows;
 						if ( !__any_sync ( FULL_MASK, m!=0 ) )
 							continue;
 						if ( uSelMode>=3 )
@@ -621,85 +693,18 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 							else
 								for ( int i=1; i<n; ++i )
 									uSel |= pPsm[i*32+iLane];
-							m &= uSel | uSparseRows;
+							m &= uSel | uListedRows;
 						}
 						uCand |= m;
 					}
 				}
 
+				// 3. the candidate rows join the warp's queue (index-local rowid, flag: holds a listed posting); full passes of 32 run now
 				if ( __any_sync ( FULL_MASK, uCand!=0 ) )
 				{
-					// 3a. candidate rows holding a sparse posting: compacted into the queue's free tail and evaluated now, all ops in order
-					const uint32_t uNow = uCand & uSparseRows;
-					uDbgSparse += __popc ( uNow );
-					uDbgHot += __popc ( uCand & ~uSparseRows );
-					if ( __any_sync ( FULL_MASK, uNow!=0 ) )
-					{
-						uint32_t * pCand = pQueue + 32;
-						int iOff = __popc ( uNow );
-						#pragma unroll
-						for ( int d=1; d<32; d<<=1 )
-						{
-							const int t = __shfl_up_sync ( FULL_MASK, iOff, d );
-							if ( iLane>=d )
-								iOff += t;
-						}
-						const int nCand = __shfl_sync ( FULL_MASK, iOff, 31 );
-						iOff -= __popc ( uNow );
-						for ( uint32_t m=uNow; m; m&=m-1 )
-							pCand[iOff++] = (uint32_t)( iLane*32 + __ffs ( m )-1 );
-						__syncwarp();
-						for ( int iBase=0; iBase<nCand; iBase+=32 )
-						{
-							const bool bAct = iBase+iLane<nCand;
-							const int sRow = bAct ? (int)pCand[iBase+iLane] : 0;	// slot inside the mini-tile
-							float fT = 0.0f;
-							uint32_t uF = 0;
-							bool bPres = false;
-							int iSp = 0;
-							for ( int iOp=0; iOp<nOps; ++iOp )
-							{
-								const uint16_t * pRow = S.m_dOpPtr[iOp];
-								if ( pRow )
-								{
-									const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
-									const uint32_t uRaw = bAct ? __ldg ( pRow+uLo+sRow ) : 0u;
-									const uint32_t uHits = uRaw & 255u;
-									const uint32_t uFields = ( uRaw>>8 ) & tLeaf.m_uQueriedFields;
-									if ( !uHits || !uFields )
-										continue;
-									float fBase = S.m_dTf[uHits];
-									if ( bAnyEscape && uHits==255 )
-										fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uLo+sRow );
-									const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
-									// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
-									fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
-									uF |= uFields;
-									bPres = true;
-								} else
-								{
-									const int iTo = S.m_dOpStart[iWarp][iSp+1];
-									for ( int e=S.m_dOpStart[iWarp][iSp]; e<iTo; ++e )
-									{
-										const PreEntry_t tEntry = pList[e];	// same address in every lane: a broadcast
-										if ( bAct && (int)tEntry.m_uRowid==sRow )
-										{
-											fT = bPres ? __fadd_rn ( fT, tEntry.m_fTf ) : tEntry.m_fTf;
-											uF |= tEntry.m_uFields;
-											bPres = true;
-										}
-									}
-									++iSp;
-								}
-							}
-							fnRankPush ( bAct && bPres, fT, uF, uLo+sRow, pPool, tThrCur );
-						}
-						__syncwarp();
-					}
-
-					// 3b. the other candidate rows join the warp's queue (index-local rowids); full passes of 32 rows run now
-					const uint32_t uQ = uCand & ~uSparseRows;
-					int iOff = __popc ( uQ );
+					uDbgListed += __popc ( uCand & uListedRows );
+					uDbgHot += __popc ( uCand & ~uListedRows );
+					int iOff = __popc ( uCand );
 					#pragma unroll
 					for ( int d=1; d<32; d<<=1 )
 					{
@@ -708,27 +713,27 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 							iOff += t;
 					}
 					const int nNew = __shfl_sync ( FULL_MASK, iOff, 31 );
-					if ( nNew )
+					iOff += nQueue - __popc ( uCand );
+					for ( uint32_t m=uCand; m; m&=m-1 )
 					{
-						iOff += nQueue - __popc ( uQ );
-						for ( uint32_t m=uQ; m; m&=m-1 )
-							pQueue[iOff++] = uLo + iLane*32 + __ffs ( m )-1;
-						nQueue += nNew;
-						__syncwarp();
-						while ( nQueue>=32 )
-						{
-							nQueue -= 32;
-							fnExactHot ( true, pQueue[nQueue+iLane], pPool, tThrCur );
-						}
-						__syncwarp();
+						const int k = __ffs ( m )-1;
+						pQueue[iOff++] = ( uLo + iLane*32 + k ) | ( ( ( uListedRows>>k ) & 1u ) ? OB_LISTED : 0u );
 					}
+					nQueue += nNew;
+					__syncwarp();
+					while ( nQueue>=32 )
+					{
+						nQueue -= 32;
+						fnExact ( true, pQueue[nQueue+iLane], pPool, tThrCur );
+					}
+					__syncwarp();
 				}
 				++uMini;
 			}
 			// the queued candidate rows are evaluated against this round's threshold and pool buffer
 			if ( nQueue )
 			{
-				fnExactHot ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, tThrCur );
+				fnExact ( iLane<nQueue, pQueue[iLane<nQueue ? iLane : 0], pPool, tThrCur );
 				nQueue = 0;
 				__syncwarp();
 			}
@@ -758,13 +763,13 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 				for ( int d=16; d; d>>=1 )
 				{
 					uDbgHot += __shfl_xor_sync ( FULL_MASK, uDbgHot, d );
-					uDbgSparse += __shfl_xor_sync ( FULL_MASK, uDbgSparse, d );
+					uDbgListed += __shfl_xor_sync ( FULL_MASK, uDbgListed, d );
 				}
 				if ( iLane==0 )
 				{
 					atomicAdd ( P.m_pDebug+0, (unsigned long long)uDbgMinis );
 					atomicAdd ( P.m_pDebug+1, (unsigned long long)uDbgHot );
-					atomicAdd ( P.m_pDebug+2, (unsigned long long)uDbgSparse );
+					atomicAdd ( P.m_pDebug+2, (unsigned long long)uDbgListed );
 					atomicAdd ( P.m_pDebug+4, (unsigned long long)iMyTotal );
 				}
 			}

@@ -1153,6 +1153,45 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		dOrder [ bDnf ? 2 : bOrClass ? 5 : bHotDnf ? 6 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
 	}
 
+	// class 5 on orbits_kernel: every keyword outside the hot store is decoded once per run into a plain posting list
+	if ( m_iOrMode==3 && !dOrder[5].empty() )
+	{
+		std::unordered_map<const TermInfo_t*,uint32_t> hOff;
+		uint64_t uEntries = 0;
+		for ( int i : dOrder[5] )
+		{
+			PlannedQuery_t & p = m_dPlans[i];
+			for ( size_t l=0; l<p.m_dLeafTerms.size(); ++l )
+			{
+				const TermInfo_t * pTerm = p.m_dLeafTerms[l];
+				if ( p.m_tDev.m_dLeaves[l].m_iHot>=0 || !pTerm )
+					continue;
+				auto it = hOff.find ( pTerm );
+				if ( it==hOff.end() )
+				{
+					it = hOff.emplace ( pTerm, (uint32_t)std::min<uint64_t> ( uEntries, 0xFFFFFFFFu ) ).first;
+					DevLeaf_t tLeaf = p.m_tDev.m_dLeaves[l];
+					tLeaf.m_uListOff = it->second;
+					m_dListTerms.push_back ( tLeaf );
+					uEntries += ( (uint64_t)pTerm->m_nBlocks*32 + 31 ) & ~31ull;
+				}
+				p.m_tDev.m_dLeaves[l].m_uListOff = it->second;
+			}
+		}
+		if ( uEntries>=( 1ull<<30 ) || uRows>=( 1u<<31 ) )
+		{
+			// (the lists would not fit / the candidate queue's flag bit is taken: the class stays on stream_kernel<512,1>)
+			m_dListTerms.clear();
+			m_iOrMode = 1;
+		} else
+		{
+			m_nListEntries = (size_t)uEntries;
+			m_dListBlkStart.assign ( 1, 0u );
+			for ( const DevLeaf_t & t : m_dListTerms )
+				m_dListBlkStart.push_back ( m_dListBlkStart.back()+t.m_nBlocks );
+		}
+	}
+
 	// estimated work of a query in its class (decides how many items it is cut into)
 	auto fnWork = [&] ( const PlannedQuery_t & p, int c ) -> int64_t
 	{
@@ -1314,6 +1353,13 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		CUDA_TRY ( m_dHotBlkStartDev.AllocAsync ( m_dHotBlkStart.size(), tAllocStream ), m_sError );
 		CUDA_TRY ( cudaMemcpyAsync ( m_dHotBlkStartDev.m_p, m_dHotBlkStart.data(), m_dHotBlkStart.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
 	}
+	if ( !m_dListTerms.empty() )
+	{
+		CUDA_TRY ( m_dListDesc.AllocAsync ( m_dListTerms.size(), tAllocStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dListDesc.m_p, m_dListTerms.data(), m_dListTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, tAllocStream ), m_sError );
+		CUDA_TRY ( m_dListBlkStartDev.AllocAsync ( m_dListBlkStart.size(), tAllocStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dListBlkStartDev.m_p, m_dListBlkStart.data(), m_dListBlkStart.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
+	}
 	CUDA_TRY ( m_dItemKeys.AllocAsync ( (size_t)nItems*m_iKMax, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dItemOut.AllocAsync ( nItems, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dScratch.AllocAsync ( (size_t)nDevQ*m_iScratchStride, tAllocStream ), m_sError );
@@ -1414,6 +1460,11 @@ int Batch_c::Run()
 		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1 ), m_sError );
 		if ( m_nHotBitFields )
 			CUDA_TRY ( tScr.m_dHotBits.Grow ( m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 ) ), m_sError );
+		if ( m_nListEntries )
+		{
+			CUDA_TRY ( tScr.m_dListRows.Grow ( m_nListEntries+64 ), m_sError );
+			CUDA_TRY ( tScr.m_dListVals.Grow ( m_nListEntries+64 ), m_sError );
+		}
 		if ( m_nHotLvl )
 			CUDA_TRY ( tScr.m_dHotLvlBits.Grow ( (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 ) ), m_sError );
 	}
@@ -1459,6 +1510,22 @@ int Batch_c::Run()
 		tHot.m_pLvlSlot = H.m_pLvlSlot;
 		tHot.m_pLvlBits = H.m_pLvlBits;
 	}
+	DevPostingLists_t tLists {};
+	if ( !m_dListTerms.empty() )
+	{
+		// K0b: posting lists of class 5's keywords outside the hot store
+		SparseDecodeParams_t L {};
+		L.m_tIndex = pIndex->m_tDev;
+		L.m_pTerms = m_dListDesc.m_p;
+		L.m_pBlkStart = m_dListBlkStartDev.m_p;
+		L.m_nTerms = (int)m_dListTerms.size();
+		L.m_pRows = tScr.m_dListRows.m_p;
+		L.m_pVals = tScr.m_dListVals.m_p;
+		CUDA_TRY ( LaunchSparseDecode ( L, pIndex->m_nSMs*8, s ), m_sError );
+		++nLaunches;
+		tLists.m_pRows = L.m_pRows;
+		tLists.m_pVals = L.m_pVals;
+	}
 	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
 	for ( int c=0; c<NUM_CLASSES; ++c )
 	{
@@ -1481,6 +1548,7 @@ int Batch_c::Run()
 		P.m_pQueryThr = m_dQueryThr.m_p;
 		P.m_pOrList = c>=5 ? tScr.m_dOrList.m_p : nullptr;
 		P.m_pDebug = c==5 ? m_dDebug.m_p : nullptr;
+		P.m_tLists = tLists;
 		P.m_pItemOrder = ( c>=5 && !m_dItemOrder[c-5].empty() ) ? m_dOrder[c-5].m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
 		P.m_pPreHitpos = tScr.m_dPreHitpos.m_p;

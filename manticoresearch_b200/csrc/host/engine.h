@@ -124,6 +124,7 @@ public:
 		DevBuf_T<PreEntry_t>	m_dPre, m_dOrList;
 		DevBuf_T<uint16_t>		m_dHotData;
 		DevBuf_T<uint32_t>		m_dHotBits, m_dHotLvlBits;
+		DevBuf_T<uint32_t>		m_dListRows, m_dListVals;	///< decoded posting lists of class 5's non-hot keywords
 		DevBuf_T<uint32_t>		m_dHotEscape;
 		DevBuf_T<int32_t>		m_dHotEscapeCount;
 	} m_tScratch;
@@ -214,6 +215,12 @@ public:
 	DevBuf_T<DevLeaf_t>		m_dHotDesc;
 	std::vector<uint32_t>	m_dHotBlkStart;		///< prefix sums of the hot keywords' block counts
 	DevBuf_T<uint32_t>		m_dHotBlkStartDev;
+	// class 5 on orbits_kernel: its non-hot keywords are decoded once per run into plain posting lists
+	std::vector<DevLeaf_t>	m_dListTerms;
+	std::vector<uint32_t>	m_dListBlkStart;
+	DevBuf_T<DevLeaf_t>		m_dListDesc;
+	DevBuf_T<uint32_t>		m_dListBlkStartDev;
+	size_t					m_nListEntries = 0;
 	std::vector<int32_t>	m_dHotLvlSlot;		///< per hot keyword: slot of its tf-level bitmaps (keywords in >= 1/3 of the rows), -1 = none
 	DevBuf_T<int32_t>		m_dHotLvlSlotDev;
 	int						m_nHotLvl = 0;
@@ -247,6 +254,7 @@ int			StreamOrListCap ( int iMode );
 cudaError_t	LaunchAnd ( const EvalParams_t & P, bool bHits, int nCtas, cudaStream_t tStream );
 int			AndOccupancy ( bool bHits );
 cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream_t tStream );
+cudaError_t	LaunchSparseDecode ( const SparseDecodeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
 				Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream );
