@@ -592,6 +592,13 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecode
 	const uint32_t uWarpGlobal = blockIdx.x*EVAL_WARPS+iWarp, nWarps = gridDim.x*EVAL_WARPS;
 	const uint32_t nTotalBlocks = __ldg ( P.m_pBlkStart+P.m_nHot );
 	const size_t iBitStride = (size_t)( P.m_iStride>>5 );
+	// tf class = ceil ( 15*h/(h+1.2) ) in exact integers: class/15 >= tf, the share of the weight bound of stream_kernel<512,2>
+	__shared__ uint8_t dClass[256];
+	{
+		const uint32_t uH = threadIdx.x & 255u;
+		dClass[uH] = P.m_bTfClass ? (uint8_t)( ( 150u*uH + 10u*uH+11u )/( 10u*uH+12u ) ) : 0;
+	}
+	__syncthreads();
 	for ( uint32_t g0=uWarpGlobal*HOT_CHUNK; g0<nTotalBlocks; g0+=nWarps*HOT_CHUNK )
 	{
 		// the keyword holding flat block g0: last h with start[h] <= g0
@@ -618,9 +625,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecode
 			if ( bValid )
 			{
 				const uint32_t uHits = min ( d.m_uHits, 255u );
-				// tf class = ceil ( 15*h/(h+1.2) ) in exact integers: class/15 >= tf, the share of the weight bound of stream_kernel's register-OR path
-				const uint32_t uClass = P.m_bTfClass ? ( 150u*uHits + 10u*uHits+11u )/( 10u*uHits+12u ) : 0u;
-				pD[d.m_uRowid] = (uint16_t)( uHits | ( ( d.m_uFields & 255u )<<8 ) | ( uClass<<12 ) );
+				pD[d.m_uRowid] = (uint16_t)( uHits | ( ( d.m_uFields & 255u )<<8 ) | ( (uint32_t)dClass[uHits]<<12 ) );
 				if ( d.m_uHits>=255u )
 				{
 					const int i = atomicAdd ( P.m_pEscapeCount, 1 );
@@ -632,36 +637,57 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecode
 			}
 			if ( P.m_nBitFields )
 			{
-				// rowids ascend inside a block: lanes of the same 32-row word are neighbours; the first of each run owns the atomic
-				const unsigned uAct = __ballot_sync ( FULL_MASK, bValid );
-				if ( bValid )
+				// Rowids ascend inside a block, so the lanes of one 32-row bitmap word are neighbours. Sparse keywords: (nearly) every
+				// lane has a word of its own and sets its bits directly. Dense ones: the block spans a few words; per word one
+				// full-mask redux per bitmap and one atomic by the run's first lane.
+				const uint32_t uWord = bValid ? ( d.m_uRowid>>5 ) : 0xFFFFFFFFu;
+				const uint32_t uPrevWord = __shfl_up_sync ( FULL_MASK, uWord, 1 );
+				const bool bHead = bValid && ( iLane==0 || uPrevWord!=uWord );
+				const unsigned uHeads = __ballot_sync ( FULL_MASK, bHead );
+				const uint32_t uBit = 1u<<( d.m_uRowid & 31u );
+				const int iLvl = P.m_pLvlSlot ? __ldg ( P.m_pLvlSlot+h ) : -1;
+				uint32_t * pB = P.m_pBits + (size_t)h*P.m_nBitFields*iBitStride;
+				uint32_t * pL = iLvl>=0 ? P.m_pLvlBits + (size_t)iLvl*2*iBitStride : nullptr;
+				if ( __popc ( uHeads )>8 )
 				{
-					const uint32_t uWord = d.m_uRowid>>5;
-					const unsigned uPeers = __match_any_sync ( uAct, uWord );
-					const uint32_t uBit = 1u<<( d.m_uRowid & 31u );
-					uint32_t * pB = P.m_pBits + (size_t)h*P.m_nBitFields*iBitStride + uWord;
-					for ( int f=0; f<P.m_nBitFields; ++f )
+					// (a few lanes may share a word: their atomics simply hit it twice)
+					if ( bValid )
 					{
-						const uint32_t uMine = ( ( d.m_uFields>>f ) & 1u ) ? uBit : 0u;
-						const uint32_t uAll = __reduce_or_sync ( uPeers, uMine );
-						if ( uAll && iLane==__ffs ( uPeers )-1 )
-							atomicOr ( pB + f*iBitStride, uAll );
-					}
-					const int iLvl = P.m_pLvlSlot ? __ldg ( P.m_pLvlSlot+h ) : -1;
-					if ( iLvl>=0 )
-					{
-						uint32_t * pL = P.m_pLvlBits + (size_t)iLvl*2*iBitStride + uWord;
-						const uint32_t uAll2 = __reduce_or_sync ( uPeers, d.m_uHits>=2u ? uBit : 0u );
-						const uint32_t uAll4 = __reduce_or_sync ( uPeers, d.m_uHits>=4u ? uBit : 0u );
-						if ( iLane==__ffs ( uPeers )-1 )
+						for ( int f=0; f<P.m_nBitFields; ++f )
+							if ( ( d.m_uFields>>f ) & 1u )
+								atomicOr ( pB + f*iBitStride + uWord, uBit );
+						if ( pL && d.m_uHits>=2u )
 						{
-							if ( uAll2 )
-								atomicOr ( pL, uAll2 );
-							if ( uAll4 )
-								atomicOr ( pL+iBitStride, uAll4 );
+							atomicOr ( pL + uWord, uBit );
+							if ( d.m_uHits>=4u )
+								atomicOr ( pL + iBitStride + uWord, uBit );
 						}
 					}
-				}
+				} else
+					for ( unsigned m=uHeads; m; m&=m-1 )
+					{
+						const int iHeadLane = __ffs ( m )-1;
+						const uint32_t uRunWord = __shfl_sync ( FULL_MASK, uWord, iHeadLane );
+						const uint32_t uMine = ( bValid && uWord==uRunWord ) ? uBit : 0u;
+						for ( int f=0; f<P.m_nBitFields; ++f )
+						{
+							const uint32_t uAll = __reduce_or_sync ( FULL_MASK, ( ( d.m_uFields>>f ) & 1u ) ? uMine : 0u );
+							if ( uAll && iLane==iHeadLane )
+								atomicOr ( pB + f*iBitStride + uRunWord, uAll );
+						}
+						if ( pL )
+						{
+							const uint32_t uAll2 = __reduce_or_sync ( FULL_MASK, d.m_uHits>=2u ? uMine : 0u );
+							const uint32_t uAll4 = __reduce_or_sync ( FULL_MASK, d.m_uHits>=4u ? uMine : 0u );
+							if ( iLane==iHeadLane )
+							{
+								if ( uAll2 )
+									atomicOr ( pL + uRunWord, uAll2 );
+								if ( uAll4 )
+									atomicOr ( pL + iBitStride + uRunWord, uAll4 );
+							}
+						}
+					}
 			}
 		}
 	}

@@ -1,7 +1,8 @@
 """per-source-line share of samples / instructions from an ncu report (needs -lineinfo); usage: ncu_lines.py rep [top]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+extra = sys.argv[3:]
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = next(r for r in rows if r and r[0] == "Line No")
 iS, iI = hdr.index("# Samples"), hdr.index("Instructions Executed")
