@@ -140,7 +140,11 @@ typedef struct mgpu_query {
 	int32_t					index_weight;   /* iIndexWeight of MatchExtended (sphinx.cpp:12222); 0 -> 1 */
 	uint8_t					plain_idf;      /* m_bPlainIDF */
 	uint8_t					unnormalized_tfidf; /* !m_bNormalizedTFIDF */
-	uint8_t					pad[2];
+	uint8_t					shard_of_global;    /* this index is one rowid-range shard and word_docs holds the statistics of the whole index:
+	                                             order the keywords of multi-AND / phrase / quorum nodes (GetDocsCount, src/searchnode.cpp:2791)
+	                                             and with them the fp32 TF*IDF additions by word_docs, as the unsharded index would
+	                                             (SURVEY 8(e)); 0 = the reference's own per-index order */
+	uint8_t					pad[1];
 
 	/* CSphMultiQueryArgs::m_iTotalDocs / m_pLocalDocs (global IDF inputs for sharded indexes) */
 	int64_t					total_docs;     /* 0 = use the index's own document count */
@@ -239,6 +243,40 @@ typedef struct mgpu_batch_stats {
 int				mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out );
 /* stats of the last mgpu_search_batch() call on this handle (that call frees its batch before returning) */
 int				mgpu_index_last_search_stats ( const mgpu_index * idx, mgpu_batch_stats * out );
+
+/* ------------------------------------------------------------------------------------- */
+/* Rowid-range shards of one index behind one handle, one GPU per shard: replaces the distributed-local fan-out
+ * RunLocalSearches (src/searchd.cpp:5596-5814: a thread per local index, each with its own sorter) + MergeAllMatches
+ * (:4653-4738) + SetupLocalDF (:5869: global IDF statistics).  path_prefixes[s] is shard s = the s-th contiguous docid
+ * range (its rowid base is the row count of the shards before it); devices[s] its CUDA ordinal.  One process, one host
+ * thread per shard; the batch is planned once; the K keys per query and shard are exchanged with ncclSend/ncclRecv over
+ * NVLink (libnccl is loaded at run time) when every shard has a GPU of its own, with stream-ordered device copies when
+ * they share GPUs.  Results are those of the UNSHARDED index; mgpu_result.rowid holds GLOBAL rowids. */
+typedef struct mgpu_sharded mgpu_sharded;
+int				mgpu_sharded_open ( const char * const * path_prefixes, const int * devices, int n_shards, mgpu_sharded ** out );
+void			mgpu_sharded_close ( mgpu_sharded * sh );
+int				mgpu_sharded_search_batch ( mgpu_sharded * sh, const mgpu_query * queries, int n_queries, mgpu_result * results );
+int				mgpu_sharded_set_option ( mgpu_sharded * sh, const char * name, int64_t value );   /* mgpu_index_set_option on every shard */
+int64_t			mgpu_sharded_total_docs ( const mgpu_sharded * sh );
+int				mgpu_sharded_word_docs ( const mgpu_sharded * sh, const char * word, int64_t * docs );   /* global df; returns 1 if found */
+const char *	mgpu_sharded_last_error ( const mgpu_sharded * sh );   /* sh may be NULL: last open error */
+typedef struct mgpu_sharded_stats {
+	int32_t			n_shards;
+	int32_t			nccl;                /* 1 = the last exchange went through ncclSend/ncclRecv */
+	float			host_total_ms;       /* the whole mgpu_sharded_search_batch call */
+	float			host_plan_ms;        /* global statistics + planning (once) */
+	float			host_setup_ms;       /* shard threads: bind + upload + launch */
+	float			host_wait_ms;        /* exchange, merge, download: until the results are on the host */
+	float			host_fetch_ms;       /* unpacking into the caller's buffers */
+	float			max_eval_kernel_ms;  /* slowest shard */
+	float			max_hot_decode_ms;
+	int32_t			kernel_launches;     /* all shards + the merge */
+	int64_t			h2d_bytes;
+	int64_t			d2h_bytes;
+	int64_t			algorithmic_bytes;   /* SURVEY 8(d), summed over the shards */
+	int64_t			postings;
+} mgpu_sharded_stats;
+int				mgpu_sharded_get_stats ( const mgpu_sharded * sh, mgpu_sharded_stats * out );
 
 /* ------------------------------------------------------------------------------------- */
 /* distributed-local merge: replaces MergeAllMatches/KillPlainDupes for disjoint rowid-range shards

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgpu.so")
 
 CUDA_SOURCES = ["cuda/kernels.cu"]
-HOST_SOURCES = ["host/index_format.cpp", "host/index_writer.cpp", "host/engine.cpp", "host/api.cpp"]
+HOST_SOURCES = ["host/index_format.cpp", "host/index_writer.cpp", "host/engine.cpp", "host/sharded.cpp", "host/api.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

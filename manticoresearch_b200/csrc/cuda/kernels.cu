@@ -1711,7 +1711,8 @@ __global__ void __launch_bounds__ ( 256 ) merge_kernel ( MergeParams_t P )
 //////////////////////////////////////////////////////////////////////////
 
 __global__ void __launch_bounds__ ( 256 ) shard_merge_kernel ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
-	Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts )
+	Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts,
+	const int64_t * pDocids, const uint32_t * pShardBase, int64_t * pOutDocid )
 {
 	__shared__ SelectSmem_t tSel;
 	__shared__ int iTotalKeys;
@@ -1753,7 +1754,27 @@ __global__ void __launch_bounds__ ( 256 ) shard_merge_kernel ( const Key128_t * 
 		__syncthreads();
 		CtaBitonicSortDesc ( pCur, nPad );
 		for ( int i=tid; i<n; i+=blockDim.x )
-			pOutKeys[(size_t)iQuery*iK+i] = pCur[i];
+		{
+			const Key128_t tKey = pCur[i];
+			pOutKeys[(size_t)iQuery*iK+i] = tKey;
+			if ( pDocids )
+			{
+				// the match's document id travels with its shard's list: the owner follows from the global rowid, the entry from a
+				// binary search of that (best-first) list
+				const uint32_t uRow = ~(uint32_t)( tKey.m_uLo>>32 );
+				int s = 0;
+				while ( s+1<nShards && uRow>=pShardBase[s+1] )
+					++s;
+				const Key128_t * pSrc = pKeys + ( (size_t)s*nQueries+iQuery )*iK;
+				int lo = 0, hi = min ( pCounts[(size_t)s*nQueries+iQuery], iK );
+				while ( lo<hi )
+				{
+					const int mid = ( lo+hi )>>1;
+					if ( KeyLess ( tKey, pSrc[mid] ) ) lo = mid+1; else hi = mid;
+				}
+				pOutDocid[(size_t)iQuery*iK+i] = pDocids [ ( (size_t)s*nQueries+iQuery )*iK + lo ];
+			}
+		}
 		if ( tid==0 )
 			pOutCounts[iQuery] = n;
 		__syncthreads();
@@ -1911,9 +1932,11 @@ cudaError_t LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStre
 }
 
 cudaError_t LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
-	Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream )
+	Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream,
+	const int64_t * pDocids, const uint32_t * pShardBase, int64_t * pOutDocid )
 {
-	shard_merge_kernel<<<nCtas, 256, 0, tStream>>> ( pKeys, pCounts, nShards, nQueries, iK, pScratch, iScratchStride, pOutKeys, pOutCounts );
+	shard_merge_kernel<<<nCtas, 256, 0, tStream>>> ( pKeys, pCounts, nShards, nQueries, iK, pScratch, iScratchStride, pOutKeys, pOutCounts,
+		pDocids, pShardBase, pOutDocid );
 	return cudaGetLastError();
 }
 

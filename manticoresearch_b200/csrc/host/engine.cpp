@@ -339,7 +339,9 @@ struct PLeaf_t
 	bool				m_bNotWeighted = false;
 	bool				m_bOwnsIDF = false;		///< first occurrence of the word in eval-tree order
 	int					m_iTermPos = 0;
-	int					Docs() const { return m_pTerm ? m_pTerm->m_iDocs : 0; }
+	int64_t				m_iOrderDocs = 0;		///< what the reference's GetDocsCount() order sees: the caller's global df when given (shards), else the dictionary's
+	int64_t				Docs() const { return m_iOrderDocs; }
+	int					LocalDocs() const { return m_pTerm ? m_pTerm->m_iDocs : 0; }
 };
 
 struct PNode_t
@@ -361,6 +363,7 @@ struct Planner_c
 	int					m_iError = MGPU_OK;
 	int					m_iMaxSp = 0;
 	bool				m_bAnyTermPos = false;
+	int					m_nVisits = 0;			///< Create() calls: a well-formed tree visits every node once
 
 	struct Qword_t { int m_iDocs; float m_fBoost; int m_iFirstWord; float m_fIDF; };
 	std::unordered_map<std::string,Qword_t> m_hQwords;
@@ -379,6 +382,8 @@ struct Planner_c
 		PLeaf_t t;
 		t.m_iWord = iWord;
 		t.m_pTerm = m_tIndex.FindTerm ( tWord.word );
+		// a rowid-range shard must order its keywords (and with them the fp32 TF*IDF additions) like the unsharded index would
+		t.m_iOrderDocs = ( m_q.shard_of_global && m_q.word_docs && m_q.word_docs[iWord]>=0 ) ? m_q.word_docs[iWord] : t.LocalDocs();
 		t.m_uFields = tNode.field_mask;
 		t.m_iAtomPos = tWord.atom_pos;
 		t.m_iNodePos = iNodePos;
@@ -402,6 +407,9 @@ struct Planner_c
 	int Create ( int iNode )
 	{
 		if ( iNode<0 || iNode>=m_q.n_nodes )
+			return Fail ( MGPU_E_BAD_QUERY );
+		// a child list naming its own node or an ancestor (or a DAG blown up into an exponential tree) must not recurse forever
+		if ( ++m_nVisits>m_q.n_nodes )
 			return Fail ( MGPU_E_BAD_QUERY );
 		const mgpu_xqnode & tNode = m_q.nodes[iNode];
 		if ( tNode.n_words )
@@ -560,7 +568,7 @@ struct Planner_c
 		if ( l.m_bNotWeighted || it!=m_hQwords.end() )
 			return;
 		l.m_bOwnsIDF = true;
-		m_hQwords.emplace ( w.word, Qword_t { l.Docs(), w.boost, l.m_iWord, 0.0f } );
+		m_hQwords.emplace ( w.word, Qword_t { l.LocalDocs(), w.boost, l.m_iWord, 0.0f } );
 	}
 
 	/// emits the tile program; returns the alive value of v[iSp]
@@ -641,7 +649,7 @@ struct Planner_c
 		DevQuery_t & d = m_tOut.m_tDev;
 		memset ( &d, 0, sizeof(d) );
 		m_tOut.m_dWordStats.assign ( std::max ( m_q.n_words, 0 ), mgpu_wordstat { 0, 0 } );
-		for ( int i=0; i<m_q.n_words; ++i )
+		for ( int i=0; i<m_q.n_words && m_q.words; ++i )
 			if ( m_q.words[i].word )
 				if ( const TermInfo_t * p = m_tIndex.FindTerm ( m_q.words[i].word ) )
 				{
@@ -651,6 +659,11 @@ struct Planner_c
 
 		if ( m_q.ranker<MGPU_RANK_PROXIMITY_BM25 || m_q.ranker>MGPU_RANK_SPH04 )
 			return MGPU_E_UNSUPPORTED;	// EXPR / EXPORT / PLUGIN rankers need the expression engine
+		// counts without arrays
+		if ( ( m_q.n_nodes>0 && !m_q.nodes ) || ( m_q.n_children>0 && !m_q.children ) || ( m_q.n_words>0 && !m_q.words )
+			|| ( m_q.n_filters>0 && !m_q.filters ) || ( m_q.n_sort_keys>0 && !m_q.sort_keys ) || ( m_q.n_field_weights>0 && !m_q.field_weights )
+			|| m_q.n_nodes<0 || m_q.n_children<0 || m_q.n_words<0 || m_q.n_filters<0 || m_q.n_sort_keys<0 || m_q.n_field_weights<0 )
+			return MGPU_E_BAD_QUERY;
 
 		int iRoot = -1;
 		if ( m_q.n_nodes>0 && m_q.root>=0 )
@@ -799,12 +812,14 @@ struct Planner_c
 		d.m_nLeaves = (int)m_dLeaves.size();
 		const unsigned nIndexFields = (unsigned)m_tIndex.m_tHdr.m_dFields.size();
 		m_tOut.m_dLeafTerms.assign ( m_dLeaves.size(), nullptr );
+		m_tOut.m_dLeafWord.assign ( m_dLeaves.size(), 0 );
 		for ( size_t i=0; i<m_dLeaves.size(); ++i )
 		{
 			const PLeaf_t & l = m_dLeaves[i];
 			DevLeaf_t & t = d.m_dLeaves[i];
 			t.m_iHot = -1;
 			m_tOut.m_dLeafTerms[i] = l.m_pTerm;
+			m_tOut.m_dLeafWord[i] = l.m_iWord;
 			if ( l.m_pTerm )
 			{
 				t.m_uFirstBlk = l.m_pTerm->m_uFirstBlk;
@@ -852,6 +867,8 @@ struct Planner_c
 			t.m_iBitCount = (int)a.m_iBitCount;
 			if ( f.kind==MGPU_FILTER_VALUES )
 			{
+				if ( f.n_values<0 || ( f.n_values>0 && !f.values ) )
+					return MGPU_E_BAD_QUERY;
 				if ( f.n_values>MAX_FILTER_VALUES )
 					return MGPU_E_UNSUPPORTED;
 				t.m_nValues = f.n_values;
@@ -915,6 +932,44 @@ int PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_
 	return tOut.m_iStatus;
 }
 
+/// A plan made on one rowid-range shard, re-bound to another shard of the same index: the program, IDFs (global statistics), weights,
+/// filters and sort keys do not depend on the shard; the keywords' dictionary entries and the statistics derived from them do.
+/// Only valid for queries that carry global word_docs (so that no keyword order was decided from shard-local counts).
+void RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan )
+{
+	for ( size_t i=0; i<tPlan.m_dWordStats.size(); ++i )
+	{
+		tPlan.m_dWordStats[i] = mgpu_wordstat { 0, 0 };
+		if ( tQuery.words && tQuery.words[i].word )
+			if ( const TermInfo_t * p = tIndex.FindTerm ( tQuery.words[i].word ) )
+			{
+				tPlan.m_dWordStats[i].docs = p->m_iDocs;
+				tPlan.m_dWordStats[i].hits = p->m_iHits;
+			}
+	}
+	if ( tPlan.m_iStatus!=MGPU_OK )
+		return;
+	tPlan.m_iCost = 0;
+	tPlan.m_iAlgBytes = 0;
+	for ( size_t l=0; l<tPlan.m_dLeafTerms.size(); ++l )
+	{
+		const TermInfo_t * pTerm = tIndex.FindTerm ( tQuery.words[tPlan.m_dLeafWord[l]].word );
+		tPlan.m_dLeafTerms[l] = pTerm;
+		DevLeaf_t & t = tPlan.m_tDev.m_dLeaves[l];
+		t.m_uFirstBlk = pTerm ? pTerm->m_uFirstBlk : 0;
+		t.m_nBlocks = pTerm ? pTerm->m_nBlocks : 0;
+		t.m_nDocs = pTerm ? (uint32_t)pTerm->m_iDocs : 0;
+		t.m_uDoclistEnd = pTerm ? (uint64_t)( pTerm->m_iDoclistOffset+pTerm->m_iDoclistLength-1 ) : 0;
+		t.m_iHot = -1;
+		t.m_uListOff = 0;
+		if ( pTerm )
+		{
+			tPlan.m_iCost += pTerm->m_iDocs;
+			tPlan.m_iAlgBytes += pTerm->m_iDoclistLength + pTerm->m_iSkiplistBytes;
+		}
+	}
+}
+
 //////////////////////////////////////////////////////////////////////////
 // engine options
 //////////////////////////////////////////////////////////////////////////
@@ -976,7 +1031,7 @@ static int Pow2Ceil ( int n )
 	return p;
 }
 
-int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries )
+int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads )
 {
 	m_pIndex = pIndex;
 	const EngineOptions_t tOpt = pIndex->m_tOpt;	// one consistent copy per batch
@@ -989,10 +1044,18 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		nThreads = std::max ( 1, std::min ( nThreads, nQueries/512 ) );
 		if ( tOpt.m_iPlanThreads>0 )
 			nThreads = tOpt.m_iPlanThreads;
+		if ( nMaxThreads>0 )
+			nThreads = std::min ( nThreads, nMaxThreads );
 		auto fnPlan = [&] ( int iFrom, int iTo )
 		{
 			for ( int i=iFrom; i<iTo; ++i )
-				PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
+				if ( pTemplate )
+				{
+					// planned once for all shards (sharded.cpp): take the plan and bind its keywords to this shard's dictionary
+					m_dPlans[i] = (*pTemplate)[i];
+					RebindPlan ( *pIndex, pQueries[i], m_dPlans[i] );
+				} else
+					PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
 		};
 		if ( nThreads<=1 )
 			fnPlan ( 0, nQueries );
@@ -1327,7 +1390,10 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	const int nDevQ = (int)m_dSlots.size();
 	m_nDevQueries = nDevQ;
 	const int nItems = (int)m_dItems.size();
-	cudaStream_t tAllocStream = pIndex->m_tStream;
+	// the stream of this batch: captured here and used for its allocations, kernels, copies and frees (mgpu_index_set_stream
+	// between prepare and run / free must not split them over two streams)
+	m_tStream = pIndex->m_tStream;
+	cudaStream_t tAllocStream = m_tStream;
 	m_iPoolCap = m_iKMax + 32768;	// >= K + what one round of any kernel can push (stream: 8 mini-tiles x 8 warps x 512 rows)
 	m_iScratchStride = 2*Pow2Ceil ( iMaxKeysPerQuery );
 
@@ -1372,7 +1438,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( cudaMemsetAsync ( m_dOutTotal.m_p, 0, (size_t)nQueries*8, tAllocStream ), m_sError );
 
 	fnMark ( "device allocations" );
-	cudaStream_t s = pIndex->m_tStream;
+	cudaStream_t s = m_tStream;
 	{
 		// device queries: gathered by a few threads into the index's pinned upload buffer (grow-only, free again once this call's
 		// copy has completed below), then one DMA
@@ -1438,7 +1504,7 @@ int Batch_c::Run()
 		return MGPU_OK;
 	Index_c * pIndex = m_pIndex;
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
-	cudaStream_t s = pIndex->m_tStream;
+	cudaStream_t s = m_tStream;
 
 	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
 	CUDA_TRY ( cudaMemsetAsync ( m_dQueryThr.m_p, 0, (size_t)m_nDevQueries*sizeof(unsigned long long), s ), m_sError );
@@ -1591,7 +1657,7 @@ int Batch_c::Sync()
 	if ( !m_pIndex )
 		return MGPU_OK;
 	CUDA_TRY ( cudaSetDevice ( m_pIndex->m_iDevice ), m_sError );
-	CUDA_TRY ( cudaStreamSynchronize ( m_pIndex->m_tStream ), m_sError );
+	CUDA_TRY ( cudaStreamSynchronize ( m_tStream ), m_sError );
 	if ( m_bRan && m_nDevQueries )
 	{
 		cudaEventElapsedTime ( &m_tStats.eval_kernel_ms, m_tEv0, m_tEv1 );
@@ -1660,7 +1726,7 @@ int Batch_c::Fetch ( mgpu_result * pResults )
 	const int64_t * dDocid = (const int64_t *)( pStage+iOffDocid );
 	const int64_t * dTotal = (const int64_t *)( pStage+iOffTotal );
 	const int32_t * dCount = (const int32_t *)( pStage+iOffCount );
-	cudaStream_t s = m_pIndex->m_tStream;
+	cudaStream_t s = m_tStream;
 	CUDA_TRY ( cudaMemcpyAsync ( pStage, m_dOutKeys.m_p, nSlots*sizeof(Key128_t), cudaMemcpyDeviceToHost, s ), m_sError );
 	CUDA_TRY ( cudaMemcpyAsync ( pStage+iOffDocid, m_dOutDocid.m_p, nSlots*8, cudaMemcpyDeviceToHost, s ), m_sError );
 	CUDA_TRY ( cudaMemcpyAsync ( pStage+iOffTotal, m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToHost, s ), m_sError );
@@ -1707,12 +1773,12 @@ int Batch_c::Fetch ( mgpu_result * pResults )
 	return MGPU_OK;
 }
 
-int Batch_c::ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, int iK )
+int Batch_c::ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, int iK, void * pDevDocids )
 {
 	// device-to-device repack of the per-query keys [nq][KMax] -> [nq][iK]; outputs are already in the caller's query order
 	const int nQueries = (int)m_dPlans.size();
 	CUDA_TRY ( cudaSetDevice ( m_pIndex->m_iDevice ), m_sError );
-	cudaStream_t s = m_pIndex->m_tStream;
+	cudaStream_t s = m_nDevQueries ? m_tStream : m_pIndex->m_tStream;
 	if ( !m_nDevQueries )
 	{
 		CUDA_TRY ( cudaMemsetAsync ( pDevCounts, 0, (size_t)nQueries*4, s ), m_sError );
@@ -1722,6 +1788,8 @@ int Batch_c::ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, 
 		const int iW = std::min ( iK, m_iKMax );
 		CUDA_TRY ( cudaMemcpy2DAsync ( pDevKeys, (size_t)iK*sizeof(Key128_t), m_dOutKeys.m_p, (size_t)m_iKMax*sizeof(Key128_t),
 			(size_t)iW*sizeof(Key128_t), nQueries, cudaMemcpyDeviceToDevice, s ), m_sError );
+		if ( pDevDocids )
+			CUDA_TRY ( cudaMemcpy2DAsync ( pDevDocids, (size_t)iK*8, m_dOutDocid.m_p, (size_t)m_iKMax*8, (size_t)iW*8, nQueries, cudaMemcpyDeviceToDevice, s ), m_sError );
 		CUDA_TRY ( cudaMemcpyAsync ( pDevCounts, m_dOutCount.m_p, (size_t)nQueries*4, cudaMemcpyDeviceToDevice, s ), m_sError );
 		CUDA_TRY ( cudaMemcpyAsync ( pDevTotal, m_dOutTotal.m_p, (size_t)nQueries*8, cudaMemcpyDeviceToDevice, s ), m_sError );
 	}

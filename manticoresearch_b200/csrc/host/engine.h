@@ -166,17 +166,20 @@ struct PlannedQuery_t
 	int64_t			m_iAlgBytes = 0;		///< SURVEY 8(d) algorithmic bytes (doclists + skiplists)
 	std::vector<mgpu_wordstat> m_dWordStats;
 	std::vector<const TermInfo_t*> m_dLeafTerms;	///< dictionary entry of every leaf (null = keyword not in the index)
+	std::vector<int>			m_dLeafWord;	///< index of every leaf's keyword in mgpu_query::words
 	int				m_iFirstIntKeyShift = -1;
 	int				m_iFirstIntKeyBits = 0;
 	bool			m_bFirstIntKeyDesc = false;
 };
 
 int		PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut );
+void	RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan );
 
 class Batch_c
 {
 public:
 	Index_c *		m_pIndex = nullptr;
+	cudaStream_t	m_tStream = nullptr;	///< the index's stream when the batch was prepared: everything of this batch is ordered on it
 	std::string		m_sError;
 	std::vector<PlannedQuery_t> m_dPlans;
 	struct DevSlot_t { int m_iQuery, m_iFirstItem, m_nItems; };
@@ -236,11 +239,12 @@ public:
 	mgpu_batch_stats m_tStats {};
 	bool			m_bRan = false;
 
-	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries );
+	/// pTemplate: plans made once on another shard of the same index (re-bound here instead of planning again); nMaxThreads caps the host threads
+	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate=nullptr, int nMaxThreads=0 );
 	int		Run();
 	int		Sync();
 	int		Fetch ( mgpu_result * pResults );
-	int		ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, int iK );
+	int		ExportKeys ( void * pDevKeys, void * pDevCounts, void * pDevTotal, int iK, void * pDevDocids=nullptr );
 	~Batch_c();
 };
 
@@ -257,7 +261,8 @@ cudaError_t	LaunchHotDecode ( const HotDecodeParams_t & P, int nCtas, cudaStream
 cudaError_t	LaunchSparseDecode ( const SparseDecodeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchMerge ( const MergeParams_t & P, int nCtas, cudaStream_t tStream );
 cudaError_t	LaunchShardMerge ( const Key128_t * pKeys, const int32_t * pCounts, int nShards, int nQueries, int iK,
-				Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream );
+				Key128_t * pScratch, int iScratchStride, Key128_t * pOutKeys, int32_t * pOutCounts, int nCtas, cudaStream_t tStream,
+				const int64_t * pDocids=nullptr, const uint32_t * pShardBase=nullptr, int64_t * pOutDocid=nullptr );	///< + the matches' document ids
 cudaError_t	LaunchDecodeDoclist ( const DevIndex_t & tIdx, const DevLeaf_t & tLeaf, uint32_t * pRowid, uint32_t * pHits, uint32_t * pFields,
 				uint64_t * pHitlistPos, unsigned long long * pChecksum, int nCtas, cudaStream_t tStream );
 

@@ -41,6 +41,7 @@ def apply_global_idf(queries, total_docs, gdf):
     for q in queries:
         q.total_docs = total_docs
         q.word_docs = [gdf[k.word] for k in q.keywords()]
+        q.shard_of_global = True     # keyword order (and the fp32 summation order) of the unsharded index
 
 
 def pack_key(weight, global_rowid, sort_hi=None):

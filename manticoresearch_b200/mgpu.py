@@ -54,7 +54,7 @@ class c_query(C.Structure):
                 ("sort_keys", C.POINTER(c_sortkey)), ("n_sort_keys", C.c_int32),
                 ("filters", C.POINTER(c_filter)), ("n_filters", C.c_int32),
                 ("max_matches", C.c_int32), ("index_weight", C.c_int32),
-                ("plain_idf", C.c_uint8), ("unnormalized_tfidf", C.c_uint8), ("pad", C.c_uint8 * 2),
+                ("plain_idf", C.c_uint8), ("unnormalized_tfidf", C.c_uint8), ("shard_of_global", C.c_uint8), ("pad", C.c_uint8 * 1),
                 ("total_docs", C.c_int64), ("word_docs", C.POINTER(C.c_int64))]
 
 
@@ -75,6 +75,13 @@ class c_batch_stats(C.Structure):
                 ("class_ms", C.c_float * 7), ("class_queries", C.c_int32 * 7), ("class_bytes", C.c_int64 * 7),
                 ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float),
                 ("host_wait_ms", C.c_float), ("host_total_ms", C.c_float)]
+
+
+class c_sharded_stats(C.Structure):
+    _fields_ = [("n_shards", C.c_int32), ("nccl", C.c_int32), ("host_total_ms", C.c_float), ("host_plan_ms", C.c_float),
+                ("host_setup_ms", C.c_float), ("host_wait_ms", C.c_float), ("host_fetch_ms", C.c_float),
+                ("max_eval_kernel_ms", C.c_float), ("max_hot_decode_ms", C.c_float), ("kernel_launches", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("algorithmic_bytes", C.c_int64), ("postings", C.c_int64)]
 
 
 class c_build_doc_input(C.Structure):
@@ -136,6 +143,14 @@ def load_library(path=None):
         "mgpu_batch_get_stats": (C.c_int, [vp, C.POINTER(c_batch_stats)]),
         "mgpu_index_last_search_stats": (C.c_int, [vp, C.POINTER(c_batch_stats)]),
         "mgpu_batch_export_keys": (C.c_int, [vp, vp, vp, vp, C.c_int]),
+        "mgpu_sharded_open": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "mgpu_sharded_close": (None, [vp]),
+        "mgpu_sharded_search_batch": (C.c_int, [vp, C.POINTER(c_query), C.c_int, C.POINTER(c_result)]),
+        "mgpu_sharded_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+        "mgpu_sharded_total_docs": (i64, [vp]),
+        "mgpu_sharded_word_docs": (C.c_int, [vp, C.c_char_p, C.POINTER(i64)]),
+        "mgpu_sharded_last_error": (C.c_char_p, [vp]),
+        "mgpu_sharded_get_stats": (C.c_int, [vp, C.POINTER(c_sharded_stats)]),
         "mgpu_merge_shard_keys": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
         "mgpu_decode_doclist": (C.c_int, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), i64, C.POINTER(i64)]),
@@ -163,6 +178,8 @@ EXPORTED_SYMBOLS = [
     "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_index_last_search_stats", "mgpu_batch_export_keys",
     "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist", "mgpu_build_index",
     "mgpu_build_synthetic", "mgpu_synth_field_len", "mgpu_synth_token",
+    "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
+    "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
 ]
 
 # ---------------------------------------------------------------------------------------------
@@ -240,11 +257,13 @@ class Filter:
 class Query:
     """CSphQuery subset + the parsed tree."""
     def __init__(self, root, ranker=RANK_PROXIMITY_BM25, field_weights=None, sort_keys=None, filters=None,
-                 max_matches=1000, index_weight=1, plain_idf=False, unnormalized_tfidf=False, total_docs=0, word_docs=None):
+                 max_matches=1000, index_weight=1, plain_idf=False, unnormalized_tfidf=False, total_docs=0, word_docs=None,
+                 shard_of_global=False):
         self.root, self.ranker, self.field_weights = root, ranker, field_weights
         self.sort_keys, self.filters = sort_keys or [], filters or []
         self.max_matches, self.index_weight = max_matches, index_weight
         self.plain_idf, self.unnormalized_tfidf = plain_idf, unnormalized_tfidf
+        self.shard_of_global = shard_of_global
         self.total_docs, self.word_docs = total_docs, word_docs
         self._keep = []
 
@@ -312,6 +331,7 @@ class Query:
             q.filters, q.n_filters = None, 0
         q.max_matches, q.index_weight = self.max_matches, self.index_weight
         q.plain_idf, q.unnormalized_tfidf = int(self.plain_idf), int(self.unnormalized_tfidf)
+        q.shard_of_global = int(self.shard_of_global)
         q.total_docs = self.total_docs
         if self.word_docs is not None:
             a_d = (C.c_int64 * len(self.word_docs))(*self.word_docs)
@@ -467,6 +487,66 @@ class Index:
         if rc != MGPU_OK:
             self._err(rc)
         return nout.value
+
+
+class ShardedIndex:
+    """Rowid-range shards of one index behind one handle, one GPU per shard (mgpu_sharded): plan once, one host thread per
+    shard, NCCL exchange of the K keys per query, results of the unsharded index (rowid = global rowid)."""
+    def __init__(self, path_prefixes, devices):
+        self._lib = lib()
+        n = len(path_prefixes)
+        arr = (C.c_char_p * n)(*[p.encode() for p in path_prefixes])
+        dev = (C.c_int * n)(*devices)
+        h = C.c_void_p()
+        rc = self._lib.mgpu_sharded_open(arr, dev, n, C.byref(h))
+        if rc != MGPU_OK:
+            raise MgpuError(rc, (self._lib.mgpu_sharded_last_error(None) or b"").decode())
+        self._h = h
+        self.n_shards = n
+
+    def close(self):
+        if self._h:
+            self._lib.mgpu_sharded_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc):
+        raise MgpuError(rc, (self._lib.mgpu_sharded_last_error(self._h) or b"").decode())
+
+    def set_option(self, name, value):
+        rc = self._lib.mgpu_sharded_set_option(self._h, name.encode(), int(value))
+        if rc != 0:
+            self._err(rc)
+
+    @property
+    def total_docs(self):
+        return self._lib.mgpu_sharded_total_docs(self._h)
+
+    def word_docs(self, word):
+        d = C.c_int64()
+        return d.value if self._lib.mgpu_sharded_word_docs(self._h, word.encode("utf-8"), C.byref(d)) else 0
+
+    def search(self, queries):
+        arr = pack_queries(queries)
+        rs = ResultSet(queries)
+        return self.search_packed(arr, len(queries), rs)
+
+    def search_packed(self, packed, n, result_set):
+        """mgpu_sharded_search_batch on already marshalled host buffers: the bare C-ABI call"""
+        rc = self._lib.mgpu_sharded_search_batch(self._h, packed, n, result_set.results)
+        if rc != MGPU_OK:
+            self._err(rc)
+        return result_set
+
+    def stats(self):
+        st = c_sharded_stats()
+        self._lib.mgpu_sharded_get_stats(self._h, C.byref(st))
+        return {k: getattr(st, k) for k, _ in c_sharded_stats._fields_}
 
 
 class Batch:

@@ -416,3 +416,78 @@ def test_rowid_range_shards_merge_equals_unsharded(tmp_path):
         for s in shards:
             s.close()
         cpu.close()
+
+
+def test_sharded_handle_equals_unsharded_oracle(tmp_path):
+    """mgpu_sharded_open / mgpu_sharded_search_batch (C++: plan once, a host thread per shard, key exchange + shard_merge_kernel):
+    3 rowid-range shards on one GPU (stream-ordered device copies stand in for ncclSend/ncclRecv) == the UNSHARDED oracle:
+    global rowids, weights, order, total_found, document ids, keyword statistics; cfg2 mix incl. ANDNOT, hit-ranked queries,
+    attribute sort + filter; keyword order decided from the global df even where a shard's local counts invert it"""
+    from manticoresearch_b200 import distributed as D
+    total, world, K = 30000, 3, 64
+    params = M.SynthParams(total, vocab=1 << 15)
+    full = str(tmp_path / "full")
+    M.build_synthetic(full, params)
+    cpu = helpers.OracleIndex(full)
+    prefixes = []
+    for r in range(world):
+        first, n = D.shard_range(total, r, world)
+        prefixes.append(str(tmp_path / ("shard%d" % r)))
+        M.build_synthetic(prefixes[-1], M.SynthParams(n, first_doc=first, vocab=1 << 15))
+    sh = M.ShardedIndex(prefixes, [0] * world)
+    single = M.Index(full, device=0)
+    try:
+        assert sh.total_docs == total
+        queries = (workload.cfg2_queries(n=150, max_rank=8000, max_matches=K, with_andnot=0.15)
+                   + workload.cfg1_queries(n=40, max_matches=K) + workload.cfg3_queries(params, n=40, max_matches=K)
+                   + workload.cfg5_queries(single, n=20, max_matches=200))
+        # AND queries over keywords of nearly equal df: shard-local counts order them differently than the whole index does
+        mids = [M.synth_keyword(r) for r in range(400, 440)]
+        for i in range(0, 36, 3):
+            queries.append(M.Query(M.AND(*[M.kw(w, j + 1) for j, w in enumerate(mids[i:i + 4])]), ranker=M.RANK_BM25, field_weights=[3, 1], max_matches=K))
+        got = sh.search(queries)
+        ref = cpu.search(queries)
+        nonempty = 0
+        for qi, q in enumerate(queries):
+            g, e = got.get(qi), ref.get(qi)
+            helpers.assert_same_results(g, e, ctx="sharded query %d" % qi)
+            assert g["docid"] == e["docid"], ("docid", qi)
+            nw = len(q.keywords())
+            assert got.word_stats(qi, nw) == ref.word_stats(qi, nw), ("word stats", qi)
+            nonempty += e["total_found"] > 0
+        assert nonempty > len(queries) // 2
+        st = sh.stats()
+        assert st["n_shards"] == world and st["kernel_launches"] > world
+        # a second batch on the same handle (buffers are reused)
+        again = sh.search(queries[:50])
+        for qi in range(50):
+            helpers.assert_same_results(again.get(qi), ref.get(qi), ctx="sharded query %d, second batch" % qi)
+    finally:
+        sh.close()
+        single.close()
+        cpu.close()
+
+
+def test_malformed_queries_are_rejected_not_crashed(synth):
+    """the C ABI takes caller-built flattened trees: a child list naming its own node (or an ancestor), counts without arrays and
+    negative counts come back as MGPU_E_BAD_QUERY for that query; the rest of the batch still runs"""
+    good = M.Query(M.OR(M.kw("t0000100", 1), M.kw("t0002000", 2)), ranker=M.RANK_BM25, max_matches=20)
+    cyc = M.Query(M.OR(M.AND(M.kw("t0000100", 1), M.OR(M.kw("t0000200", 2), M.kw("t0000300", 3))), M.kw("t0002000", 4)), ranker=M.RANK_BM25, max_matches=20)
+    nofilt = M.Query(M.OR(M.kw("t0000100", 1), M.kw("t0002000", 2)), ranker=M.RANK_BM25, max_matches=20)
+    negvals = M.Query(M.kw("t0000100", 1), ranker=M.RANK_BM25, max_matches=20, filters=[M.Filter(0, values=[1, 2])])
+    queries = [good, cyc, nofilt, negvals, good]
+    arr = M.pack_queries(queries)
+    # query 1: make the inner OR node list the root among its children -> a cycle
+    kids = arr[1].children
+    inner = [i for i in range(arr[1].n_nodes) if arr[1].nodes[i].n_children == 2 and i != arr[1].root][-1]
+    kids[arr[1].nodes[inner].first_child] = arr[1].root
+    arr[2].n_filters = 2            # a count without an array
+    arr[3].filters[0].n_values = -5
+    rs = M.ResultSet(queries)
+    synth["gpu"].search_packed(arr, len(queries), rs)
+    ref = synth["cpu"].search([good])
+    assert rs.get(1)["status"] == M.MGPU_E_BAD_QUERY
+    assert rs.get(2)["status"] == M.MGPU_E_BAD_QUERY
+    assert rs.get(3)["status"] == M.MGPU_E_BAD_QUERY
+    for i in (0, 4):
+        helpers.assert_same_results(rs.get(i), ref.get(0), ctx="good query %d next to malformed ones" % i)
