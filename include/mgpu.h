@@ -239,6 +239,9 @@ typedef struct mgpu_batch_stats {
 	float			host_plan_ms, host_setup_ms, host_fetch_ms;
 	float			host_wait_ms;        /* part of host_fetch_ms spent waiting for the kernels */
 	float			host_total_ms;       /* mgpu_search_batch only: the whole call incl. freeing the batch */
+	int32_t			or_kernel;           /* kernel of launch class 5: 3 = orbits_kernel (presence bitmaps), 1 = stream_kernel<512,1> */
+	int64_t			hitlist_bytes;       /* .spp bytes of the matched documents' hitlists read by the hit stage */
+	int64_t			attr_rows;           /* rows whose attributes the bound pass read for filters / sort keys (x attribute bytes) */
 } mgpu_batch_stats;
 int				mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out );
 /* stats of the last mgpu_search_batch() call on this handle (that call frees its batch before returning) */
@@ -295,44 +298,6 @@ void			mgpu_unpack_key ( const uint64_t key[2], uint32_t * global_rowid, int32_t
  * arrays; used by the parity tests of the VByte block decoder against the oracle's
  * DiskIndexQword_c::ReadNext restatement (src/sphinx.cpp:511-549). host arrays sized docs. */
 int				mgpu_decode_doclist ( mgpu_index * idx, const char * word, uint32_t * rowid, uint32_t * hits, uint32_t * fields, uint64_t * hitlist_pos, int64_t capacity, int64_t * n_out );
-
-/* ------------------------------------------------------------------------------------- */
-/* index writer (format v62): the byte layout of CSphHitBuilder::cidxHit/cidxDone + IndexWriteHeader +
- * CSphDictKeywords (src/sphinx.cpp:8297-8936, 19374-19700).  Host-only; SURVEY 8(f) rank 1. */
-typedef struct mgpu_build_doc_input {
-	int32_t			n_docs;
-	int32_t			n_fields;
-	const char * const * field_names;
-	int32_t			n_attrs;          /* uint32 attributes besides `id` */
-	const char * const * attr_names;
-	const int64_t *	docids;           /* [n_docs] ascending */
-	const uint32_t *attrs;            /* [n_docs][n_attrs] */
-	int32_t			n_keywords;
-	const char * const * keywords;    /* dictionary forms */
-	const int64_t *	field_tok_offsets;/* [n_docs*n_fields+1] into tok_* */
-	const int32_t *	tok_keyword;      /* keyword index */
-	const int32_t *	tok_pos;          /* 1-based position inside the field (gaps allowed) */
-	int32_t			skiplist_block;   /* 0 -> 32 */
-	int32_t			hit_format_inline;/* 1 = inline (default), 0 = plain */
-} mgpu_build_doc_input;
-int				mgpu_build_index ( const char * path_prefix, const mgpu_build_doc_input * in, char * err, int errlen );
-
-/* synthetic Zipfian corpus: docs [first_doc, first_doc+n_docs) of the seeded corpus are
- * written as a self-contained index with local rowids from 0 (a contiguous rowid-range shard). */
-typedef struct mgpu_synth_params {
-	uint64_t		seed;
-	int64_t			first_doc;
-	int64_t			n_docs;
-	int32_t			vocab;            /* number of distinct terms, Zipf(s=1) */
-	int32_t			title_min, title_max;
-	int32_t			body_min, body_max;
-	float			body_mu, body_sigma; /* lognormal */
-	int32_t			threads;          /* 0 = all */
-} mgpu_synth_params;
-int				mgpu_build_synthetic ( const char * path_prefix, const mgpu_synth_params * p, char * err, int errlen );
-/* token at (doc, field, pos0) of the synthetic corpus, and field length; lets query generators sample phrases */
-int32_t			mgpu_synth_field_len ( const mgpu_synth_params * p, int64_t doc, int field );
-int32_t			mgpu_synth_token ( const mgpu_synth_params * p, int64_t doc, int field, int pos0 );
 
 int				mgpu_abi_version ( void );
 

@@ -12,7 +12,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgpu.so")
 
 CUDA_SOURCES = ["cuda/kernels.cu"]
-HOST_SOURCES = ["host/index_format.cpp", "host/index_writer.cpp", "host/engine.cpp", "host/sharded.cpp", "host/api.cpp"]
+HOST_SOURCES = ["host/index_format.cpp", "host/engine.cpp", "host/sharded.cpp", "host/api.cpp"]
+# the index writer + synthetic corpus: a host-only library of its own (no CUDA), so that the CPU arm of bench.py and the
+# golden-corpus builders never map libmgpu.so
+WRITER_LIB = os.path.join(HERE, "libmgpu_writer.so")
+WRITER_SOURCES = ["host/index_format.cpp", "host/index_writer.cpp", "host/writer_api.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -33,11 +37,16 @@ def _sources():
     return [os.path.join(CSRC, s) for s in CUDA_SOURCES + HOST_SOURCES]
 
 
+def _writer_sources():
+    return [os.path.join(CSRC, s) for s in WRITER_SOURCES]
+
+
 def _deps():
-    deps = list(_sources())
+    deps = list(_sources()) + [os.path.join(CSRC, "host/index_writer.cpp"), os.path.join(CSRC, "host/writer_api.cpp")]
     for root, _, files in os.walk(CSRC):
         deps += [os.path.join(root, f) for f in files if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(HERE, "..", "include", "mgpu.h"))
+    deps.append(os.path.join(HERE, "..", "include", "mgpu_writer.h"))
     return deps
 
 
@@ -56,7 +65,7 @@ def _digest():
 
 def needs_build():
     """content based (mtimes do not survive the snapshot copy to the GPU box)"""
-    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+    if not os.path.exists(LIB) or not os.path.exists(WRITER_LIB) or not os.path.exists(STAMP):
         return True
     return open(STAMP).read().strip() != _digest()
 
@@ -96,6 +105,22 @@ def _build_locked(verbose):
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
     os.replace(LIB + ".tmp", LIB)
+    # the writer library: plain g++ through nvcc's host compiler, no CUDA runtime
+    wobjs = []
+    for src in _writer_sources():
+        obj = os.path.join(objdir, "w_" + os.path.basename(src) + ".o")
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", "-ffp-contract=off", "-I/usr/local/cuda/include",
+                            "-c", src, "-o", obj], capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed on %s" % src)
+        wobjs.append(obj)
+    r = subprocess.run(["g++", "-shared", "-Wl,--no-undefined", "-o", WRITER_LIB + ".tmp"] + wobjs + ["-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link of libmgpu_writer.so failed")
+    os.replace(WRITER_LIB + ".tmp", WRITER_LIB)
     open(STAMP, "w").write(_digest())
     return LIB
 

@@ -248,6 +248,8 @@ struct EvalParams_t
 	uint64_t *				m_pPreHitpos;	///< hit stage only: [gridDim.x][PRE_BLOCKS*32]
 	DevHotStore_t			m_tHot;
 	const int32_t *			m_pItemOrder;	///< stream_kernel: the k-th item taken from the queue is item m_pItemOrder[k] (null = k)
+	unsigned long long *	m_pWork;		///< [2] work counters of the run for the roofline bookkeeping: [0] .spp bytes of the matched
+											///< documents' hitlists that the hit stage read, [1] rows whose attributes the bound pass read (filters / sort keys)
 	DevPostingLists_t		m_tLists;
 	unsigned long long *	m_pDebug;		///< [8] work counters of the bound + exact pass kernels (option "stats"), or null
 };

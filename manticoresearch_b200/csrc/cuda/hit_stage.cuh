@@ -23,6 +23,7 @@ static const uint32_t EMIT_NWAY_SHIFT = 16;		///< emitter mask: bits 0..15 plain
 struct HitCursor_t
 {
 	const uint8_t *	m_p;
+	const uint8_t *	m_pStart;	///< where the document's hitlist starts in .spp (null: inlined hit): m_p - m_pStart = bytes consumed
 	uint32_t		m_uCur;		///< running hitpos (state 0) or the inlined hit (state 1)
 	int				m_iState;	///< 0 = stream from .spp, 1 = inlined hit pending, 2 = done
 };
@@ -34,11 +35,13 @@ __device__ __forceinline__ void SeekHitlist ( HitCursor_t & c, const uint8_t * p
 		c.m_iState = 1;
 		c.m_uCur = (uint32_t)uHitlistPos;
 		c.m_p = nullptr;
+		c.m_pStart = nullptr;
 	} else
 	{
 		c.m_iState = 0;
 		c.m_uCur = 0;
 		c.m_p = pSpp + uHitlistPos;
+		c.m_pStart = c.m_p;
 	}
 }
 
@@ -444,8 +447,9 @@ __device__ __forceinline__ void RankUpdate ( const DevQuery_t & q, RankState_t &
 /// Streams the document's hits (root CollectHits order) through the ranker state.
 /// uEmit = emitters sitting on this document (plain leaves + n-way nodes). Returns false if the document yields no
 /// hits (ExtRanker_State_T skips it, src/sphinxsearch.cpp:1299-1304); else iWeight = final weight before index weight.
+/// uHitBytes += the .spp bytes of the document's hitlists that were read (the hitlist share of the algorithmic bytes).
 __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, uint32_t uEmit, const uint64_t * pHitpos, int iStride, int s,
-	int iSeedWeight, DocHits_t & H, int & iWeight )
+	int iSeedWeight, DocHits_t & H, int & iWeight, unsigned long long & uHitBytes )
 {
 	uint32_t uLeaves = uEmit & 0xFFFFu;
 	uint32_t uNWays = uEmit>>EMIT_NWAY_SHIFT;
@@ -506,6 +510,21 @@ __device__ bool RankDocByHits ( const DevIndex_t & tIdx, const DevQuery_t & q, u
 	}
 	if ( !bAny )
 		return false;
+	{
+		uint32_t uAllLeaves = uLeaves;
+		for ( uint32_t m=uNWays; m; m&=m-1 )
+		{
+			const DevNWay_t & n = q.m_dNWay[__ffs ( m )-1];
+			for ( int w=0; w<n.m_nWords; ++w )
+				uAllLeaves |= 1u<<n.m_dLeaf[w];
+		}
+		for ( uint32_t m=uAllLeaves; m; m&=m-1 )
+		{
+			const HitCursor_t & c = H.m_dCur[__ffs ( m )-1];
+			if ( c.m_pStart )
+				uHitBytes += (unsigned long long)( c.m_p-c.m_pStart );
+		}
+	}
 
 	if ( q.m_eRanker==3 || q.m_eRanker==6 )
 		iWeight = (int)R.m_uWordcount;

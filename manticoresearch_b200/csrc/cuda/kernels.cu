@@ -788,6 +788,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 		const DevQuery_t & q = S.m_tQ;
 		const int iK = q.m_iMaxMatches;
 		int iMyTotal = 0;
+		unsigned long long uMyHitBytes = 0;
 
 		if ( tid<16 )
 		{
@@ -1155,7 +1156,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								if constexpr ( HITS )
 								{
 									DocHits_t H;
-									bOk = RankDocByHits ( tIdx, q, V.Emit ( 0, s ), pHitpos, TILE_W, s, iSeed, H, iWeight );
+									bOk = RankDocByHits ( tIdx, q, V.Emit ( 0, s ), pHitpos, TILE_W, s, iSeed, H, iWeight, uMyHitBytes );
 								}
 							} else
 							{
@@ -1219,6 +1220,14 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 				iMyTotal += __shfl_xor_sync ( FULL_MASK, iMyTotal, d );
 			if ( iLane==0 && iMyTotal )
 				atomicAdd ( &S.m_uTotal, (unsigned long long)iMyTotal );
+			if ( HITS && P.m_pWork )
+			{
+				#pragma unroll
+				for ( int d=16; d; d>>=1 )
+					uMyHitBytes += __shfl_xor_sync ( FULL_MASK, uMyHitBytes, d );
+				if ( iLane==0 && uMyHitBytes )
+					atomicAdd ( P.m_pWork, uMyHitBytes );
+			}
 			__syncthreads();
 			const Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 			Key128_t * pDst = P.m_pItemKeys + (size_t)iItem*P.m_iKMax;
@@ -1426,6 +1435,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 			S.m_dRankTab[tid] = uSum;
 		}
 		int iMyTotal = 0;
+		unsigned long long uMyHitBytes = 0;
 		// the item's AND group (DNF programs: OR of AND groups; a pure AND query is one group) and its driver = rarest keyword
 		const int iGroup = (int)tItem.m_uPad;
 		const int iOp0 = q.m_dGroupOp0[iGroup], nGroupOps = q.m_dGroupOps[iGroup];
@@ -1530,7 +1540,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 						if ( HITS && q.m_bStateRanker )
 						{
 							if constexpr ( HITS )
-								bOk = RankDocByHits ( tIdx, q, uEmit, pLaneHitpos-iLane, 32, iLane, iSeed, tHits, iWeight );
+								bOk = RankDocByHits ( tIdx, q, uEmit, pLaneHitpos-iLane, 32, iLane, iSeed, tHits, iWeight, uMyHitBytes );
 						} else
 						{
 							uint32_t uRank = 0;
@@ -1588,6 +1598,14 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
 				iMyTotal += __shfl_xor_sync ( FULL_MASK, iMyTotal, d );
 			if ( iLane==0 && iMyTotal )
 				atomicAdd ( &S.m_uTotal, (unsigned long long)iMyTotal );
+			if ( HITS && P.m_pWork )
+			{
+				#pragma unroll
+				for ( int d=16; d; d>>=1 )
+					uMyHitBytes += __shfl_xor_sync ( FULL_MASK, uMyHitBytes, d );
+				if ( iLane==0 && uMyHitBytes )
+					atomicAdd ( P.m_pWork, uMyHitBytes );
+			}
 			__syncthreads();
 			const Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 			Key128_t * pDst = P.m_pItemKeys + (size_t)iItem*P.m_iKMax;

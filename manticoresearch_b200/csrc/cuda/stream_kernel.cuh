@@ -350,6 +350,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 			S.m_iNegConst = iNegConst;
 		}
 		int iMyTotal = 0;
+		uint32_t uMyAttrRows = 0;	///< rows whose attributes the filters / sort keys of the bound pass read
 
 		// this warp's contiguous share of the item
 		const uint32_t nMinis = ( tItem.m_uRowHi-tItem.m_uRowLo+MINI_W-1 )/MINI_W;
@@ -874,6 +875,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 								if ( ( dF[k>>1]>>( ( k & 1 ) ? 24 : 8 ) ) & 0xFu )
 									uRows |= 1u<<k;
 							uint32_t uKeep = 0, uPass = 0;
+							uMyAttrRows += __popc ( uRows );
 							for ( uint32_t m=uRows; m; m&=m-1 )
 							{
 								const int k = __ffs ( m )-1;
@@ -1295,6 +1297,14 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, MODE ? 3 : 4 ) stream_kernel (
 				iMyTotal += __shfl_xor_sync ( FULL_MASK, iMyTotal, d );
 			if ( iLane==0 && iMyTotal )
 				atomicAdd ( &S.m_uTotal, (unsigned long long)iMyTotal );
+			if ( DNF && P.m_pWork )
+			{
+				#pragma unroll
+				for ( int d=16; d; d>>=1 )
+					uMyAttrRows += __shfl_xor_sync ( FULL_MASK, uMyAttrRows, d );
+				if ( iLane==0 && uMyAttrRows )
+					atomicAdd ( P.m_pWork+1, (unsigned long long)uMyAttrRows );
+			}
 			__syncthreads();
 			const Key128_t * pPool = pPool0 + (size_t)S.m_iPoolBuf*P.m_iPoolCap;
 			Key128_t * pDst = P.m_pItemKeys + (size_t)iItem*P.m_iKMax;

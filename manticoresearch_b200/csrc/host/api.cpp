@@ -1,6 +1,5 @@
 // The C ABI of include/mgpu.h. Thin: argument checks, handle lifetime, error strings; no logic.
 #include "engine.h"
-#include "index_writer.h"
 
 #include <chrono>
 #include <cstdio>
@@ -283,51 +282,6 @@ int mgpu_decode_doclist ( mgpu_index * idx, const char * word, uint32_t * rowid,
 		return MGPU_E_CUDA;
 	}
 	return MGPU_OK;
-}
-
-int mgpu_build_index ( const char * path_prefix, const mgpu_build_doc_input * in, char * err, int errlen )
-{
-	if ( !path_prefix || !in )
-		return MGPU_E_BAD_QUERY;
-	std::string sError;
-	if ( !BuildIndexFromDocs ( path_prefix, *in, sError ) )
-	{
-		CopyErr ( err, errlen, sError );
-		return MGPU_E_IO;
-	}
-	return MGPU_OK;
-}
-
-int mgpu_build_synthetic ( const char * path_prefix, const mgpu_synth_params * p, char * err, int errlen )
-{
-	if ( !path_prefix || !p )
-		return MGPU_E_BAD_QUERY;
-	std::string sError;
-	if ( !BuildSyntheticIndex ( path_prefix, *p, sError ) )
-	{
-		CopyErr ( err, errlen, sError );
-		return MGPU_E_IO;
-	}
-	return MGPU_OK;
-}
-
-// the corpus object is rebuilt when the parameters change; cached per thread for the query generators
-static thread_local std::unique_ptr<SynthCorpus_c> g_pCorpus;
-static const SynthCorpus_c & GetCorpus ( const mgpu_synth_params * p )
-{
-	if ( !g_pCorpus || memcmp ( &g_pCorpus->m_tP, p, sizeof(*p) )!=0 )
-		g_pCorpus.reset ( new SynthCorpus_c ( *p ) );
-	return *g_pCorpus;
-}
-
-int32_t mgpu_synth_field_len ( const mgpu_synth_params * p, int64_t doc, int field )
-{
-	return p ? GetCorpus ( p ).FieldLen ( doc, field ) : 0;
-}
-
-int32_t mgpu_synth_token ( const mgpu_synth_params * p, int64_t doc, int field, int pos0 )
-{
-	return p ? GetCorpus ( p ).Token ( doc, field, pos0 ) : -1;
 }
 
 } // extern "C"

@@ -1404,6 +1404,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		if ( !m_dItemOrder[i].empty() )
 			CUDA_TRY ( m_dOrder[i].AllocAsync ( m_dItemOrder[i].size(), tAllocStream ), m_sError );
 	CUDA_TRY ( m_dQueryThr.AllocAsync ( nDevQ, tAllocStream ), m_sError );
+	CUDA_TRY ( m_dWork.AllocAsync ( 2, tAllocStream ), m_sError );
 	if ( tOpt.m_bStats )
 		CUDA_TRY ( m_dDebug.AllocAsync ( 8, tAllocStream ), m_sError );
 	m_nPool = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[2], m_dCtas[3], m_dCtas[4], m_dCtas[5], m_dCtas[6] } )*2*m_iPoolCap;
@@ -1508,6 +1509,7 @@ int Batch_c::Run()
 
 	CUDA_TRY ( cudaMemsetAsync ( m_dCounter.m_p, 0, NUM_CLASSES*sizeof(int32_t), s ), m_sError );
 	CUDA_TRY ( cudaMemsetAsync ( m_dQueryThr.m_p, 0, (size_t)m_nDevQueries*sizeof(unsigned long long), s ), m_sError );
+	CUDA_TRY ( cudaMemsetAsync ( m_dWork.m_p, 0, 2*sizeof(unsigned long long), s ), m_sError );
 	if ( m_dDebug.m_p )
 		CUDA_TRY ( cudaMemsetAsync ( m_dDebug.m_p, 0, 8*sizeof(unsigned long long), s ), m_sError );
 
@@ -1614,6 +1616,7 @@ int Batch_c::Run()
 		P.m_pQueryThr = m_dQueryThr.m_p;
 		P.m_pOrList = c>=5 ? tScr.m_dOrList.m_p : nullptr;
 		P.m_pDebug = c==5 ? m_dDebug.m_p : nullptr;
+		P.m_pWork = m_dWork.m_p;
 		P.m_tLists = tLists;
 		P.m_pItemOrder = ( c>=5 && !m_dItemOrder[c-5].empty() ) ? m_dOrder[c-5].m_p : nullptr;
 		P.m_pPre = tScr.m_dPre.m_p;
@@ -1674,6 +1677,15 @@ int Batch_c::Sync()
 			}
 		}
 		cudaEventElapsedTime ( &m_tStats.merge_kernel_ms, m_tEv1, m_tEv2 );
+		{
+			unsigned long long dWork[2] = { 0, 0 };
+			if ( cudaMemcpy ( dWork, m_dWork.m_p, sizeof(dWork), cudaMemcpyDeviceToHost )==cudaSuccess )
+			{
+				m_tStats.hitlist_bytes = (int64_t)dWork[0];
+				m_tStats.attr_rows = (int64_t)dWork[1];
+			}
+		}
+		m_tStats.or_kernel = m_iOrMode;
 		if ( m_dDebug.m_p )
 		{
 			unsigned long long dDbg[8];

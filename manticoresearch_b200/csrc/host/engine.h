@@ -205,6 +205,7 @@ public:
 	DevBuf_T<int32_t>		m_dCounter;
 	std::vector<int32_t>	m_dItemOrder[2];	///< classes 5, 6: items in rowid-range-major order (index relative to the class's first item)
 	DevBuf_T<int32_t>		m_dOrder[2];
+	DevBuf_T<unsigned long long> m_dWork;		///< hitlist bytes read / attribute rows read (roofline bookkeeping)
 	DevBuf_T<unsigned long long> m_dDebug;		///< option "stats": work counters
 	DevBuf_T<unsigned long long> m_dQueryThr;	///< per device query: shared K-th-best bound of its items
 	DevBuf_T<Key128_t>		m_dItemKeys, m_dScratch, m_dOutKeys;

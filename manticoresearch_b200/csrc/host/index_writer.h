@@ -6,6 +6,7 @@
 
 #include "index_format.h"
 #include "../../../include/mgpu.h"
+#include "../../../include/mgpu_writer.h"
 
 namespace mgpu
 {

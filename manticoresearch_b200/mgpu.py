@@ -74,7 +74,8 @@ class c_batch_stats(C.Structure):
                 ("eval_kernel_ms", C.c_float), ("merge_kernel_ms", C.c_float), ("hot_decode_ms", C.c_float), ("hot_terms", C.c_int32),
                 ("class_ms", C.c_float * 7), ("class_queries", C.c_int32 * 7), ("class_bytes", C.c_int64 * 7),
                 ("host_plan_ms", C.c_float), ("host_setup_ms", C.c_float), ("host_fetch_ms", C.c_float),
-                ("host_wait_ms", C.c_float), ("host_total_ms", C.c_float)]
+                ("host_wait_ms", C.c_float), ("host_total_ms", C.c_float),
+                ("or_kernel", C.c_int32), ("hitlist_bytes", C.c_int64), ("attr_rows", C.c_int64)]
 
 
 class c_sharded_stats(C.Structure):
@@ -154,10 +155,6 @@ def load_library(path=None):
         "mgpu_merge_shard_keys": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
         "mgpu_decode_doclist": (C.c_int, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), i64, C.POINTER(i64)]),
-        "mgpu_build_index": (C.c_int, [C.c_char_p, C.POINTER(c_build_doc_input), C.c_char_p, C.c_int]),
-        "mgpu_build_synthetic": (C.c_int, [C.c_char_p, C.POINTER(SynthParams), C.c_char_p, C.c_int]),
-        "mgpu_synth_field_len": (i32, [C.POINTER(SynthParams), i64, C.c_int]),
-        "mgpu_synth_token": (i32, [C.POINTER(SynthParams), i64, C.c_int, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib_, name)
@@ -171,13 +168,45 @@ def lib():
     return load_library()
 
 
+_wlib = None
+
+
+def writer_lib():
+    """libmgpu_writer.so (include/mgpu_writer.h): the v62 index writer + synthetic corpus; host-only, no CUDA"""
+    global _wlib
+    if _wlib is not None:
+        return _wlib
+    from . import build as _build
+    if _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.WRITER_LIB):
+        raise MgpuError(MGPU_E_IO, "libmgpu_writer.so is not built (run python -m manticoresearch_b200.build)")
+    w = C.CDLL(_build.WRITER_LIB)
+    i32, i64 = C.c_int32, C.c_int64
+    sig = {
+        "mgpu_writer_abi_version": (C.c_int, []),
+        "mgpu_build_index": (C.c_int, [C.c_char_p, C.POINTER(c_build_doc_input), C.c_char_p, C.c_int]),
+        "mgpu_build_synthetic": (C.c_int, [C.c_char_p, C.POINTER(SynthParams), C.c_char_p, C.c_int]),
+        "mgpu_synth_field_len": (i32, [C.POINTER(SynthParams), i64, C.c_int]),
+        "mgpu_synth_token": (i32, [C.POINTER(SynthParams), i64, C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(w, name)
+        fn.restype = res
+        fn.argtypes = args
+    _wlib = w
+    return w
+
+
+WRITER_EXPORTED_SYMBOLS = ["mgpu_writer_abi_version", "mgpu_build_index", "mgpu_build_synthetic", "mgpu_synth_field_len", "mgpu_synth_token"]
+
+
 EXPORTED_SYMBOLS = [
     "mgpu_abi_version", "mgpu_index_open", "mgpu_index_close", "mgpu_index_set_stream", "mgpu_index_set_option", "mgpu_last_error", "mgpu_index_total_docs",
     "mgpu_index_num_fields", "mgpu_index_field_index", "mgpu_index_attr_index", "mgpu_index_word_stats",
     "mgpu_index_word_bytes", "mgpu_search_batch", "mgpu_batch_prepare", "mgpu_batch_run", "mgpu_batch_sync",
     "mgpu_batch_fetch", "mgpu_batch_free", "mgpu_batch_get_stats", "mgpu_index_last_search_stats", "mgpu_batch_export_keys",
-    "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist", "mgpu_build_index",
-    "mgpu_build_synthetic", "mgpu_synth_field_len", "mgpu_synth_token",
+    "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist",
     "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
     "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
 ]
@@ -637,24 +666,24 @@ def build_index(path_prefix, field_names, docs, attr_names=(), skiplist_block=32
     inp.field_tok_offsets, inp.tok_keyword, inp.tok_pos = a_off, a_tk, a_tp
     inp.skiplist_block, inp.hit_format_inline = skiplist_block, int(hit_format_inline)
     err = C.create_string_buffer(512)
-    rc = lib().mgpu_build_index(path_prefix.encode(), C.byref(inp), err, 512)
+    rc = writer_lib().mgpu_build_index(path_prefix.encode(), C.byref(inp), err, 512)
     if rc != MGPU_OK:
         raise MgpuError(rc, err.value.decode())
 
 
 def build_synthetic(path_prefix, params):
     err = C.create_string_buffer(512)
-    rc = lib().mgpu_build_synthetic(path_prefix.encode(), C.byref(params), err, 512)
+    rc = writer_lib().mgpu_build_synthetic(path_prefix.encode(), C.byref(params), err, 512)
     if rc != MGPU_OK:
         raise MgpuError(rc, err.value.decode())
 
 
 def synth_field_len(params, doc, field):
-    return lib().mgpu_synth_field_len(C.byref(params), doc, field)
+    return writer_lib().mgpu_synth_field_len(C.byref(params), doc, field)
 
 
 def synth_token(params, doc, field, pos0):
-    return lib().mgpu_synth_token(C.byref(params), doc, field, pos0)
+    return writer_lib().mgpu_synth_token(C.byref(params), doc, field, pos0)
 
 
 def synth_keyword(term):

@@ -279,6 +279,9 @@ struct Qword_t
 	const Index_t * m_pIndex = nullptr;
 	std::string m_sWord;
 	int m_iDocs = 0, m_iHits = 0;
+	int64_t m_iOrderDocs = -1;			// what orders the keywords of multi-keyword nodes (GetDocsCount): the dictionary's count (the reference),
+										// or the whole index's count when this index is one rowid-range shard of it (mgpu_query::shard_of_global)
+	int64_t OrderDocs() const			{ return m_iOrderDocs>=0 ? m_iOrderDocs : m_iDocs; }
 	int m_iAtomPos = 0;
 	float m_fBoost = 1.0f;
 	bool m_bExcluded = false, m_bExpanded = false;
@@ -618,7 +621,7 @@ struct TermNode_c : Node_c
 			dHits.push_back ( { m_tCurRowID, uHit, (WORD)m_iAtomPos, 0, 1, 1, 1, 0 } );
 		}
 	}
-	int GetDocsCount() override			{ return m_tQword.m_iDocs; }
+	int GetDocsCount() override			{ return (int)std::min<int64_t> ( m_tQword.OrderDocs(), INT_MAX-1 ); }
 	int GetQwords ( QwordsHash_t & h ) override			{ return RegisterQword ( m_tQword, m_bNotWeighted, m_fIDF, h, m_iWordIdx ); }
 	void SetQwordsIDF ( const QwordsHash_t & h ) override
 	{
@@ -821,7 +824,7 @@ struct MultiAndNode_c : Node_c
 
 	void Finalize()
 	{
-		RefSort ( m_dNodes, [] ( const NodeInfo_t & a, const NodeInfo_t & b ) { return a.m_tQword.m_iDocs<b.m_tQword.m_iDocs; } );	// :2791
+		RefSort ( m_dNodes, [] ( const NodeInfo_t & a, const NodeInfo_t & b ) { return a.m_tQword.OrderDocs()<b.m_tQword.OrderDocs(); } );	// :2791
 		m_dCurHitlistPos.resize ( m_dNodes.size() );
 	}
 	RowID_t Advance ( int iNode )	// :2845-2855
@@ -1776,6 +1779,8 @@ static TermNode_c * CreateTerm ( const mgpu_xqnode & tNode, int iWord, Setup_t &
 		p->m_iMaxFieldPos = tNode.field_max_pos;
 	}
 	p->m_tQword.Setup ( tSetup.m_pIndex, tWord.word );
+	if ( tSetup.m_pQuery->shard_of_global && tSetup.m_pQuery->word_docs && tSetup.m_pQuery->word_docs[iWord]>=0 )
+		p->m_tQword.m_iOrderDocs = tSetup.m_pQuery->word_docs[iWord];
 	p->m_tQword.m_sWord = tWord.word;
 	p->m_tQword.m_iAtomPos = tWord.atom_pos;
 	p->m_tQword.m_fBoost = tWord.boost;
@@ -1941,6 +1946,8 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 			auto & n = p->m_dNodes.back();
 			if ( n.m_tQword.Setup ( tSetup.m_pIndex, tWord.word ) )
 				p->m_iNodesSet++;
+			if ( q.shard_of_global && q.word_docs && q.word_docs[tChild.first_word]>=0 )
+				n.m_tQword.m_iOrderDocs = q.word_docs[tChild.first_word];
 			n.m_tQword.m_sWord = tWord.word;
 			n.m_tQword.m_pIndex = tSetup.m_pIndex;
 			n.m_tQword.m_iAtomPos = tWord.atom_pos;

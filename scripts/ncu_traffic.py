@@ -3,7 +3,7 @@
 bench.py reads the dominant kernel's dram bytes per launch from that file (roofline.traffic)."""
 import csv, io, json, subprocess, sys
 
-NAMES = {"stream_kernel<512, 1>": "stream_kernel<512,or>", "stream_kernel<512, 2>": "stream_kernel<512,dnf>", "stream_kernel<512, 0>": "stream_kernel<512>",
+NAMES = {"orbits_kernel": "orbits_kernel", "sparse_decode_kernel": "sparse_decode_kernel", "stream_kernel<512, 1>": "stream_kernel<512,or>", "stream_kernel<512, 2>": "stream_kernel<512,dnf>", "stream_kernel<512, 0>": "stream_kernel<512>",
          "stream_kernel<256, 0>": "stream_kernel<256>", "and_kernel<0>": "and_kernel", "and_kernel<1>": "and_kernel<hits>",
          "eval_kernel<1>": "eval_kernel<hits>", "hot_decode_kernel": "hot_decode_kernel", "merge_kernel": "merge_kernel"}
 
@@ -44,9 +44,14 @@ def main():
         for a, b in list(v.items()):
             if isinstance(b, float) and math.isnan(b):
                 v[a] = None      # ncu could not collect this counter for the launch
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    res["kernels_sha"] = bench.kernels_sha()     # bench.py voids these figures as soon as a kernel source changes
     json.dump(res, open(dst, "w"), indent=1)
     for k, v in res.items():
         print(k, v)
+
 
 
 if __name__ == "__main__":

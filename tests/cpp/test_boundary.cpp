@@ -2,6 +2,7 @@
 // build a tiny index, create a sorter, call pIndex->MultiQuery, assert rowid / weight. Plus the field-weight case of
 // test/test_322 (negative weights) and a two-query MultiQueryEx batch. Uses only include/mgpu_adapters.h + libmgpu.so.
 #include "mgpu_adapters.h"
+#include "mgpu_writer.h"
 
 #include <cstdio>
 #include <cstdlib>

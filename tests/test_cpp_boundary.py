@@ -15,7 +15,7 @@ def _build(tmp_path):
     lib = b.build()
     exe = str(tmp_path / "test_boundary")
     subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_boundary.cpp"),
-                    "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+                    "-o", exe, lib, b.WRITER_LIB, "-Wl,-rpath," + os.path.dirname(lib)], check=True)
     return exe
 
 

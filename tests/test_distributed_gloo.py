@@ -42,8 +42,17 @@ def _worker(rank, world, port, tmp, ret):
     M.build_synthetic(prefix, M.SynthParams(n, first_doc=first, vocab=1 << 14, threads=2))
     shard = helpers.OracleIndex(prefix)
 
-    queries = workload.cfg2_queries(n=60, max_rank=3000, max_matches=K, with_andnot=0.2)
-    queries += workload.cfg1_queries(n=20, max_matches=K)
+    def make_queries():
+        qs = workload.cfg2_queries(n=60, max_rank=3000, max_matches=K, with_andnot=0.2)
+        qs += workload.cfg1_queries(n=20, max_matches=K)
+        # multi-keyword ANDs over keywords of nearly equal df: a shard's local counts order them differently than the whole index
+        # does; the order (and with it the fp32 TF*IDF summation) must follow the global df (mgpu_query::shard_of_global)
+        mids = [M.synth_keyword(r) for r in range(30, 70)]
+        for i in range(0, 36, 3):
+            qs.append(M.Query(M.AND(*[M.kw(w, j + 1) for j, w in enumerate(mids[i:i + 4])]), ranker=M.RANK_BM25, field_weights=[3, 1], max_matches=K))
+        return qs
+
+    queries = make_queries()
     gdf = D.global_keyword_docs(lambda w: (shard.word_stats(w) or (0, 0))[0], queries, torch.device("cpu"))
     D.apply_global_idf(queries, TOTAL_DOCS, gdf)
     rs = shard.search(queries)
@@ -70,7 +79,7 @@ def _worker(rank, world, port, tmp, ret):
         full_prefix = os.path.join(tmp, "full")
         M.build_synthetic(full_prefix, M.SynthParams(TOTAL_DOCS, vocab=1 << 14, threads=2))
         full = helpers.OracleIndex(full_prefix)
-        plain = workload.cfg2_queries(n=60, max_rank=3000, max_matches=K, with_andnot=0.2) + workload.cfg1_queries(n=20, max_matches=K)
+        plain = make_queries()
         ref = full.search(plain)
         bad = []
         for qi in range(nq):
@@ -93,8 +102,8 @@ def test_two_shards_over_gloo_equal_unsharded(tmp_path):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), ret), nprocs=2, join=True)
-    assert ret["checked"] == 80
-    assert ret["nonempty"] >= 40
+    assert ret["checked"] == 92
+    assert ret["nonempty"] >= 46
     assert ret["bad"] == [], "sharded != unsharded for queries %s" % ret["bad"]
 
 

@@ -30,6 +30,26 @@ def test_library_exports_every_declared_symbol():
     assert lib.mgpu_abi_version() == 1
 
 
+def test_writer_library_is_separate_and_host_only():
+    """libmgpu_writer.so exports what include/mgpu_writer.h declares and does not depend on CUDA: processes that only build
+    index files (the CPU arm of bench.py) never map the GPU library"""
+    import subprocess
+    from manticoresearch_b200 import build as B
+    w = M.writer_lib()
+    src = open(os.path.join(ROOT, "include", "mgpu_writer.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(mgpu_[a-z_0-9]+)\s*\(", src)))
+    assert declared == sorted(M.WRITER_EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(w, name)
+    assert w.mgpu_writer_abi_version() == 1
+    needed = subprocess.run(["readelf", "-d", B.WRITER_LIB], capture_output=True, text=True).stdout
+    assert "libcuda" not in needed and "libmgpu.so" not in needed
+    lib = M.lib()
+    for name in ("mgpu_build_index", "mgpu_build_synthetic"):
+        assert not hasattr(lib, name), "the writer moved out of libmgpu.so"
+
+
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
 def test_open_fails_loudly_without_gpu(golden_indexes):
     with pytest.raises(M.MgpuError) as e:
@@ -88,11 +108,11 @@ def test_ctypes_mirrors_match_the_header(tmp_path):
     (a stale mirror would read garbage stats or mis-marshal queries without failing loudly)"""
     import subprocess
     pairs = [("mgpu_xqkeyword", M.c_xqkeyword), ("mgpu_xqnode", M.c_xqnode), ("mgpu_sortkey", M.c_sortkey), ("mgpu_filter", M.c_filter),
-             ("mgpu_query", M.c_query), ("mgpu_wordstat", M.c_wordstat), ("mgpu_result", M.c_result), ("mgpu_batch_stats", M.c_batch_stats),
+             ("mgpu_query", M.c_query), ("mgpu_wordstat", M.c_wordstat), ("mgpu_result", M.c_result), ("mgpu_batch_stats", M.c_batch_stats), ("mgpu_sharded_stats", M.c_sharded_stats),
              ("mgpu_build_doc_input", M.c_build_doc_input), ("mgpu_synth_params", M.SynthParams)]
     src = tmp_path / "sizes.c"
     body = "".join('printf("%%s %%zu %%zu\\n", "%s", sizeof(%s), offsetof(%s, %s));\n' % (c, c, c, py._fields_[-1][0]) for c, py in pairs)
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mgpu.h"\nint main(void){\n' + body + "return 0;}\n")
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mgpu.h"\n#include "mgpu_writer.h"\nint main(void){\n' + body + "return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
