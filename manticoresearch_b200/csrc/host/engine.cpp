@@ -1038,6 +1038,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	const auto tStart = std::chrono::steady_clock::now();
 	m_dPlans.resize ( nQueries );
+	if ( tOpt.m_bTiming )
+		fprintf ( stderr, "[mgpu setup] %-24s %7.2f ms (%zu B per plan)\n", "plan array", std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tStart ).count(), sizeof(PlannedQuery_t) );
 	{
 		// planning is per query and read-only on the index: spread big batches over the host cores
 		int nThreads = (int)std::min<unsigned> ( std::max ( 1u, std::thread::hardware_concurrency() ), 16u );

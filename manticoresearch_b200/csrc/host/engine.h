@@ -159,8 +159,9 @@ public:
 /// one planned query: device descriptor + host bookkeeping
 struct PlannedQuery_t
 {
+	PlannedQuery_t() {}						///< (user-provided on purpose: a batch's plan array is not zeroed twice; the planner clears m_tDev itself)
 	int				m_iStatus = MGPU_OK;
-	DevQuery_t		m_tDev {};
+	DevQuery_t		m_tDev;
 	int				m_nStack = 1;
 	int64_t			m_iCost = 0;			///< sum of df over leaves (postings)
 	int64_t			m_iAlgBytes = 0;		///< SURVEY 8(d) algorithmic bytes (doclists + skiplists)
