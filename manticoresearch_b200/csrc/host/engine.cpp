@@ -1014,7 +1014,15 @@ bool EngineOptions_t::Set ( const char * szName, int64_t iValue )
 Batch_c::~Batch_c()
 {
 	if ( m_pIndex )
+	{
 		cudaSetDevice ( m_pIndex->m_iDevice );
+		m_dPlans.clear();
+		if ( m_dPlans.capacity()>m_pIndex->m_dPlanCache.capacity() )
+		{
+			std::lock_guard<std::mutex> tGuard ( m_pIndex->m_tCacheLock );
+			m_dPlans.swap ( m_pIndex->m_dPlanCache );
+		}
+	}
 	if ( m_tEv0 ) cudaEventDestroy ( m_tEv0 );
 	if ( m_tEv1 ) cudaEventDestroy ( m_tEv1 );
 	if ( m_tEv2 ) cudaEventDestroy ( m_tEv2 );
@@ -1037,6 +1045,13 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	const EngineOptions_t tOpt = pIndex->m_tOpt;	// one consistent copy per batch
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	const auto tStart = std::chrono::steady_clock::now();
+	// the plan array of a 10k-query batch is 34 MB: taken over from the previous batch on this handle (mapped pages) instead of
+	// faulting fresh ones in, single-threaded, on every call
+	{
+		std::lock_guard<std::mutex> tGuard ( pIndex->m_tCacheLock );
+		m_dPlans.swap ( pIndex->m_dPlanCache );
+	}
+	m_dPlans.clear();
 	m_dPlans.resize ( nQueries );
 	if ( tOpt.m_bTiming )
 		fprintf ( stderr, "[mgpu setup] %-24s %7.2f ms (%zu B per plan)\n", "plan array", std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tStart ).count(), sizeof(PlannedQuery_t) );
@@ -1118,8 +1133,10 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				if ( p && (int64_t)p->m_iDocs*iHotDiv>=(int64_t)uRows )
 					++hUse[p];
 		std::vector<std::pair<int64_t,const TermInfo_t*>> dHot;
+		// ... or a keyword in >= 1/16 of the rows that only one query uses (small batches): one pass over its doclist into the
+		// store and its bitmaps beats walking it posting by posting
 		for ( const auto & kv : hUse )
-			if ( kv.second>=2 )
+			if ( kv.second>=2 || (int64_t)kv.first->m_iDocs*16>=(int64_t)uRows )
 				dHot.push_back ( { (int64_t)kv.second*kv.first->m_iDocs, kv.first } );
 		std::sort ( dHot.begin(), dHot.end(), [] ( const auto & a, const auto & b ) { return a.first>b.first || ( a.first==b.first && a.second->m_uFirstBlk<b.second->m_uFirstBlk ); } );
 		m_iHotStride = (int64_t)nTiles*TILE_W;
@@ -1313,7 +1330,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			{
 				// fixed rowid ranges (OR_RANGE_TILES tiles) for every query of the class: the kernel takes the items range by range, so
 				// concurrent CTAs read the same rows of the dense store (L2 hits) and later ranges inherit the query's K-th-best bound
-				nParts = std::max<int64_t> ( 1, std::min<int64_t> ( { ( nTiles+OR_RANGE_TILES-1 )/OR_RANGE_TILES, (int64_t)iCap, nUnits } ) );
+				// (small batches: finer ranges, so that the class still fills the GPU; the items of a query share its K-th-best bound)
+				const int64_t iRangeTiles = std::max<int64_t> ( 64, std::min<int64_t> ( OR_RANGE_TILES, (int64_t)nTiles*(int64_t)dOrder[c].size()/( 4*(int64_t)nMaxCtas ) ) );
+				nParts = std::max<int64_t> ( 1, std::min<int64_t> ( { ( nTiles+iRangeTiles-1 )/iRangeTiles, (int64_t)iCap, nUnits } ) );
 			} else
 			nParts = std::max<int64_t> ( ( c==2 || c==4 ) ? p.m_tDev.m_nGroups : 1, std::min<int64_t> ( nParts, std::min<int64_t> ( { nUnits, 64, std::max ( iCap, ( c==2 || c==4 ) ? p.m_tDev.m_nGroups : 1 ) } ) ) );
 			dParts.push_back ( { i, (int)nParts, iWork/nParts } );

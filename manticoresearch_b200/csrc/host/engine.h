@@ -111,6 +111,8 @@ public:
 	cudaStream_t	m_tOwnStream = nullptr;
 	int				m_nSMs = 148;
 	std::mutex		m_tLock;		///< serialises batches on this handle
+	std::mutex		m_tCacheLock;
+	std::vector<struct PlannedQuery_t> m_dPlanCache;	///< the last batch's (cleared) plan array: its memory is reused by the next batch
 	mgpu_batch_stats m_tLastSearchStats {};
 
 	std::unordered_map<std::string,TermInfo_t> m_hTerms;
