@@ -491,3 +491,25 @@ def test_malformed_queries_are_rejected_not_crashed(synth):
     assert rs.get(3)["status"] == M.MGPU_E_BAD_QUERY
     for i in (0, 4):
         helpers.assert_same_results(rs.get(i), ref.get(0), ctx="good query %d next to malformed ones" % i)
+
+
+def test_reference_built_index_on_gpu():
+    """the v57 index the reference's own writer produced (tests/golden/ref_index, from test/test_406): mgpu_index_open takes it,
+    K1 decodes the same postings as the oracle's reader, and a query over it returns the oracle's result"""
+    prefix = os.path.join(helpers.ROOT, "tests", "golden", "ref_index", "index.0")
+    gpu = M.Index(prefix, device=0)
+    cpu = helpers.OracleIndex(prefix)
+    try:
+        assert gpu.total_docs == cpu.total_docs == 1
+        for word in ("doc", "one"):
+            assert gpu.word_stats(word) == cpu.word_stats(word)
+            for a, b in zip(gpu.decode_doclist(word), cpu.decode_doclist(word)):
+                assert (a == b).all()
+        queries = [M.Query(M.AND(M.kw("doc", 1), M.kw("one", 2)), max_matches=5), M.Query(M.OR(M.kw("doc", 1), M.kw("nope", 2)), ranker=M.RANK_BM25, max_matches=5),
+                   M.Query(M.PHRASE([("doc", 1), ("one", 2)]), max_matches=5), M.Query(M.PHRASE([("one", 1), ("doc", 2)]), max_matches=5)]
+        g, c = gpu.search(queries), cpu.search(queries)
+        for i in range(len(queries)):
+            helpers.assert_same_results(g.get(i), c.get(i), ctx="reference-built index, query %d" % i)
+    finally:
+        gpu.close()
+        cpu.close()

@@ -40,3 +40,24 @@ def test_oracle_matches_reference_golden(golden_cases, golden_indexes, case_name
                     assert [docs, hits] == exp["words"][k.word], (q["text"], k.word)
     finally:
         idx.close()
+
+
+def test_reference_built_index_opens():
+    """tests/golden/ref_index: a v57 index written by the reference itself (test/test_406). The oracle's reader must take the real
+    writer's bytes: header, keywords dictionary with its checkpoint + dict-header tail, doclists with inlined hits"""
+    import os
+    import manticoresearch_b200.mgpu as M
+    prefix = os.path.join(helpers.ROOT, "tests", "golden", "ref_index", "index.0")
+    idx = helpers.OracleIndex(prefix)
+    try:
+        assert idx.total_docs == 1
+        for word in ("doc", "one"):
+            assert idx.word_stats(word) == (1, 1)
+            rowid, hits, fields, pos = idx.decode_doclist(word)
+            assert list(rowid) == [0] and list(hits) == [1] and list(fields) == [1]
+            assert int(pos[0]) >> 63 == 1          # the only hit is inlined into the doclist (src/sphinx.cpp:523-530)
+        assert idx.word_stats("two") is None
+        r = idx.search([M.Query(M.AND(M.kw("doc", 1), M.kw("one", 2)), max_matches=5)]).get(0)
+        assert r["total_found"] == 1 and r["rowid"] == [0]
+    finally:
+        idx.close()
