@@ -148,16 +148,28 @@ struct DevSortKey_t
 	int32_t		m_iShift;		///< position of the key's low bit inside the 64-bit packed sort key
 };
 
-/// phrase / proximity node: ExtNWay_T<FSMphrase_c|FSMproximity_c>
+/// kinds of hit-level nodes over plain keywords (the "n-way" slot of the hit stage)
+enum DevNWayKind_e : int32_t
+{
+	NWAY_PHRASE = 0,		///< ExtNWay_T<FSMphrase_c>
+	NWAY_PROXIMITY = 1,		///< ExtNWay_T<FSMproximity_c>
+	NWAY_NEAR = 2,			///< ExtNWay_T<FSMmultinear_c>, src/searchnode.cpp:4080-4315 (children = keywords)
+	NWAY_BEFORE = 3,		///< ExtOrder_c, src/searchnode.cpp:4657-4935 (children = keywords)
+	NWAY_NOTNEAR = 4,		///< ExtNotNear_c, src/searchnode.cpp:5325-5478 (MUST keyword, NOT keyword)
+	NWAY_QUORUM = 5			///< ExtQuorum_c, src/searchnode.cpp:4319-4650
+};
+
+/// phrase / proximity / NEAR / BEFORE / NOTNEAR / quorum node over plain keywords
 struct DevNWay_t
 {
-	int32_t		m_bProximity;
-	int32_t		m_iOpArg;					///< "..."~N
+	int32_t		m_eKind;					///< DevNWayKind_e (0 / 1 = phrase / proximity)
+	int32_t		m_iOpArg;					///< "..."~N, NEAR/N, NOTNEAR/N, quorum threshold
 	int32_t		m_nWords;
 	int32_t		m_iQLen;					///< last atom pos - first atom pos
 	int32_t		m_dLeaf[MAX_PHRASE_WORDS];	///< leaves in query (atom pos) order
 	int32_t		m_dAtomPos[MAX_PHRASE_WORDS+1];
 	int32_t		m_dQposDelta[NWAY_MAX_SPAN+1];	///< FSMphrase_c::m_dQposDelta (src/searchnode.cpp:3884-3899)
+	uint8_t		m_dCount[MAX_PHRASE_WORDS];	///< quorum: how often the query repeats the keyword (ExtQuorum_c::TermTuple_t::m_iCount)
 };
 
 struct DevQuery_t
@@ -242,6 +254,8 @@ struct EvalParams_t
 	int32_t					m_iKMax;		///< stride of m_pItemKeys
 	int32_t					m_iPad;
 	uint64_t *				m_pHitpos;		///< hit stage only: [gridDim.x][MAX_LEAVES][TILE_W] hitlist position of (leaf, tile slot)
+	uint64_t *				m_pLeafTf;		///< hit stage only (eval_kernel): [gridDim.x][MAX_LEAVES][TILE_W] the keyword's own tf*idf bits | queried fields<<32
+											///< on the slot: BEFORE / NOTNEAR / quorum nodes rebuild the document's TF*IDF and field mask from them
 	PreEntry_t *			m_pOrList;		///< [gridDim.x][8 warps][512*MAX_LEAVES] sparse postings of the current mini-tile (register-OR path), or null
 	unsigned long long *	m_pQueryThr;	///< [nQueries] shared lower bound of each query's K-th best key (hi word), zeroed per run
 	PreEntry_t *			m_pPre;			///< [gridDim.x][PRE_BLOCKS*32] tile predecode scratch

@@ -119,12 +119,34 @@ struct NWayState_t
 	RankHit_t	m_tHead;					///< next folded hit (m_uHitpos==0: exhausted)
 	uint32_t	m_uFirstRawHit;				///< raw hit that completed the first match (doc field mask, src/searchnode.cpp:3827-3833)
 	bool		m_bAny;
+	// FSMmultinear_c, two children (NEAR)
+	uint32_t	m_uLastP, m_uFirstHit, m_uChainWeight;
+	uint32_t	m_uFirstQpos, m_uFirstNpos;
+	// ExtOrder_c (BEFORE): m_dVal[0..15] = the longest prefix found so far, m_dVal[16..31] = the most recent attempt (raw hits)
+	int			m_nLongest, m_nRecent, m_iPosLongest, m_iPosRecent, m_iField;
+	uint32_t	m_dEmit[MAX_PHRASE_WORDS];	///< a complete sequence, handed out hit by hit
+	int			m_nEmit, m_iEmitNext;
 };
 
 __device__ __forceinline__ void ResetFSM ( const DevNWay_t & n, NWayState_t & s )
 {
 	s.m_nStates = 0;
-	if ( n.m_bProximity )
+	if ( n.m_eKind==NWAY_NEAR )
+	{
+		// FSMmultinear_c::ResetFSM (m_uFirstQpos / m_uFirstNpos are always set by the chain's first hit before they are read)
+		s.m_uLastP = 0;
+		s.m_uFirstQpos = 65535;
+		s.m_uFirstNpos = 0;
+		s.m_uFirstHit = 0;
+		s.m_uChainWeight = 0;
+	} else if ( n.m_eKind==NWAY_BEFORE )
+	{
+		s.m_nLongest = s.m_nRecent = 0;
+		s.m_iPosLongest = s.m_iPosRecent = 0;
+		s.m_iField = -1;
+		s.m_nEmit = s.m_iEmitNext = 0;
+	}
+	if ( n.m_eKind==NWAY_PROXIMITY )
 	{
 		s.m_uExpPos = 0;
 		s.m_uWords = 0;
@@ -256,6 +278,111 @@ __device__ __forceinline__ bool ProximityFSM ( const DevNWay_t & n, NWayState_t 
 	return true;
 }
 
+/// FSMmultinear_c::HitFSM, src/searchnode.cpp:4098-4290, for TWO children that are plain keywords (`a NEAR/n b`): every raw hit
+/// has match length, span length and weight 1, so the "longer hit at the same position" step back (:4119-4131) and the overlap
+/// restart (:4160-4172) cannot fire. The n-way form (three and more children) keeps m_uFirstQpos across documents in the
+/// reference (ResetFSM leaves it alone), i.e. its hits depend on the documents seen before: that one stays on the CPU.
+/// uNpos = the child's index in the query, uQpos = its query position.
+__device__ __forceinline__ bool NearFSM ( const DevNWay_t & n, NWayState_t & s, uint32_t uHit, uint32_t uQpos, uint32_t uNpos, RankHit_t & tOut )
+{
+	const uint32_t uPos = uHit & ~( 1u<<23 );
+	// a second hit at the position of the last one (the same keyword on both sides), :4103-4134
+	if ( s.m_uLastP==uPos )
+	{
+		if ( uNpos<s.m_uFirstNpos )
+		{
+			s.m_uFirstQpos = uQpos;	// keep the leftmost child of the query
+			s.m_uFirstNpos = uNpos;
+		}
+		return false;
+	}
+	// too far from the previous hit (or no previous hit): a new chain starts here, :4137-4154
+	if ( s.m_uLastP==0 || ( s.m_uLastP + 1 + (uint32_t)n.m_iOpArg )<=uPos )
+	{
+		s.m_uFirstHit = s.m_uLastP = uPos;
+		s.m_uChainWeight = 1;
+		s.m_uFirstQpos = uQpos;
+		s.m_uFirstNpos = uNpos;
+		return false;
+	}
+	// the same child again: it becomes the head of the chain, :4173-4190
+	if ( uNpos==s.m_uFirstNpos )
+	{
+		if ( s.m_uLastP<uPos )
+		{
+			s.m_uFirstHit = s.m_uLastP = uPos;
+			s.m_uChainWeight = 1;
+			s.m_uFirstQpos = uQpos;
+			s.m_uFirstNpos = uNpos;
+		}
+		return false;
+	}
+	// the other child within reach: emit; the chain shifts to this hit instead of starting over, :4254-4275
+	tOut.m_uHitpos = s.m_uFirstHit;
+	tOut.m_uWeight = s.m_uChainWeight+1;
+	tOut.m_uQpos = min ( s.m_uFirstQpos, uQpos );
+	tOut.m_uSpanlen = 2;
+	s.m_uFirstHit = s.m_uLastP = uPos;
+	s.m_uChainWeight = 1;
+	s.m_uFirstQpos = uQpos;
+	return true;
+}
+
+/// ExtOrder_c::GetMatchingHits, src/searchnode.cpp:4734-4829, one raw hit of child iChild (keywords: span length 1). A complete
+/// sequence lands in s.m_dEmit; returns whether one was completed by this hit.
+__device__ __forceinline__ bool OrderFSM ( const DevNWay_t & n, NWayState_t & s, uint32_t uHit, int iChild )
+{
+	const int iHitField = (int)( uHit>>24 ), iHitPos = (int)( uHit & 0x7FFFFFu );
+	uint32_t * pLongest = s.m_dVal, * pRecent = s.m_dVal+MAX_PHRASE_WORDS;
+	if ( iHitField!=s.m_iField )
+	{
+		// another field: both trackers start over; only child 0 can seed (and only then the field is remembered)
+		s.m_nLongest = s.m_nRecent = 0;
+		if ( iChild==0 )
+		{
+			pLongest[s.m_nLongest++] = uHit;
+			s.m_iPosLongest = iHitPos+1;
+			s.m_iField = iHitField;
+		}
+	} else if ( iChild==s.m_nLongest && iHitPos>=s.m_iPosLongest )
+	{
+		pLongest[s.m_nLongest++] = uHit;
+		s.m_iPosLongest = iHitPos+1;
+		if ( s.m_nLongest==n.m_nWords )
+		{
+			for ( int i=0; i<n.m_nWords; ++i )
+				s.m_dEmit[i] = pLongest[i];
+			s.m_nEmit = n.m_nWords;
+			s.m_iEmitNext = 0;
+			s.m_nLongest = s.m_nRecent = 0;
+			s.m_iPosRecent = s.m_iPosLongest;
+			return true;
+		}
+	} else if ( iChild==0 )
+	{
+		pRecent[0] = uHit;
+		s.m_nRecent = 1;
+		s.m_iPosRecent = iHitPos+1;
+		if ( !s.m_nLongest )
+		{
+			pLongest[s.m_nLongest++] = uHit;
+			s.m_iPosLongest = iHitPos+1;
+		}
+	} else if ( iChild==s.m_nRecent && iHitPos>=s.m_iPosRecent )
+	{
+		pRecent[s.m_nRecent++] = uHit;
+		s.m_iPosRecent = iHitPos+1;
+		if ( s.m_nRecent==s.m_nLongest )
+		{
+			for ( int i=0; i<s.m_nRecent; ++i )
+				pLongest[i] = pRecent[i];
+			s.m_nRecent = 0;
+			s.m_iPosLongest = s.m_iPosRecent;
+		}
+	}
+	return false;
+}
+
 /// per-document hit machinery: cursors of every keyword + the n-way generators
 struct DocHits_t
 {
@@ -264,15 +391,64 @@ struct DocHits_t
 	NWayState_t	m_dNWay[MAX_NWAY];
 };
 
-/// advances n-way node j to its next folded hit (ExtNWay_T::GetDocsChunk inner loop, src/searchnode.cpp:3805-3848):
-/// raw hits of its keywords arrive ordered by (hitpos asc, qpos desc)
+static const uint64_t HITPOS_ABSENT = ~0ull;	///< hit scratch: the keyword does not sit on the slot (optional children: NOTNEAR's right side, quorum)
+
+/// advances hit-level node j to its next hit. Phrase / proximity / NEAR (ExtNWay_T::GetDocsChunk inner loop,
+/// src/searchnode.cpp:3805-3848): raw hits of the keywords arrive ordered by (hitpos asc, qpos desc) and go through the acceptor.
+/// BEFORE (ExtOrder_c::GetMatchingHits :4706-4829): by position, the lowest child wins a tie; a complete sequence is handed out
+/// hit by hit. NOTNEAR (ExtNotNear_c::FilterHits :5352-5380): the MUST keyword's hits that no NOT hit follows within N positions.
+/// Quorum (ExtQuorum_c::CollectHits :4543-4565): every hit of the keywords on the document, by (position, qpos).
 __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 {
 	const DevNWay_t & n = q.m_dNWay[j];
 	NWayState_t & s = H.m_dNWay[j];
+	auto fnEmitted = [&] ( uint32_t uRawHit )
+	{
+		if ( !s.m_bAny )
+		{
+			s.m_bAny = true;
+			s.m_uFirstRawHit = uRawHit;
+		}
+	};
+	auto fnNext = [&] ( int l )
+	{
+		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields, q.m_dLeaves[l].m_iTermPos );
+	};
+	if ( n.m_eKind==NWAY_NOTNEAR )
+	{
+		const int lMust = n.m_dLeaf[0], lNot = n.m_dLeaf[1];
+		while ( true )
+		{
+			const uint32_t h = H.m_dHead[lMust];
+			if ( !h )
+			{
+				s.m_tHead.m_uHitpos = 0;
+				return;
+			}
+			const uint32_t uPosMust = h & ~( 1u<<23 );
+			while ( H.m_dHead[lNot] && ( H.m_dHead[lNot] & ~( 1u<<23 ) )<uPosMust )
+				fnNext ( lNot );	// NOT hits before the MUST hit do not count
+			// (the field sits in the top byte, so the distance can be added to the position as it is; a keyword's match length is 1)
+			const bool bKeep = !H.m_dHead[lNot] || uPosMust + (uint32_t)n.m_iOpArg<( H.m_dHead[lNot] & ~( 1u<<23 ) );
+			fnNext ( lMust );
+			if ( bKeep )
+			{
+				s.m_tHead.m_uHitpos = h; s.m_tHead.m_uQpos = q.m_dLeaves[lMust].m_uAtomPos; s.m_tHead.m_uSpanlen = 1; s.m_tHead.m_uWeight = 1;
+				fnEmitted ( h );
+				return;
+			}
+		}
+	}
 	while ( true )
 	{
-		int iBest = -1;
+		if ( n.m_eKind==NWAY_BEFORE && s.m_iEmitNext<s.m_nEmit )
+		{
+			const int i = s.m_iEmitNext++;
+			s.m_tHead.m_uHitpos = s.m_dEmit[i]; s.m_tHead.m_uQpos = (uint32_t)n.m_dAtomPos[i]; s.m_tHead.m_uSpanlen = 1; s.m_tHead.m_uWeight = 1;
+			fnEmitted ( s.m_dEmit[i] );
+			return;
+		}
+		int iBest = -1, iBestW = 0;
 		uint32_t uBestHit = 0, uBestQpos = 0;
 		for ( int w=0; w<n.m_nWords; ++w )
 		{
@@ -281,9 +457,16 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 			if ( !h )
 				continue;
 			const uint32_t uQpos = q.m_dLeaves[l].m_uAtomPos;
-			if ( iBest<0 || h<uBestHit || ( h==uBestHit && uQpos>uBestQpos ) )
+			bool bLess;
+			if ( n.m_eKind==NWAY_BEFORE )
+				bLess = ( h & ~( 1u<<23 ) )<( uBestHit & ~( 1u<<23 ) );
+			else if ( n.m_eKind==NWAY_QUORUM )
+				bLess = ( h & ~( 1u<<23 ) )<( uBestHit & ~( 1u<<23 ) ) || ( ( h & ~( 1u<<23 ) )==( uBestHit & ~( 1u<<23 ) ) && uQpos<uBestQpos );
+			else
+				bLess = h<uBestHit || ( h==uBestHit && uQpos>uBestQpos );
+			if ( iBest<0 || bLess )
 			{
-				iBest = l; uBestHit = h; uBestQpos = uQpos;
+				iBest = l; iBestW = w; uBestHit = h; uBestQpos = uQpos;
 			}
 		}
 		if ( iBest<0 )
@@ -291,30 +474,45 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 			s.m_tHead.m_uHitpos = 0;
 			return;
 		}
-		H.m_dHead[iBest] = NextHit ( H.m_dCur[iBest], q.m_dLeaves[iBest].m_uQueriedFields, q.m_dLeaves[iBest].m_iTermPos );
-		const bool bEmit = n.m_bProximity
-			? ProximityFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead )
-			: PhraseFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead );
+		fnNext ( iBest );
+		bool bEmit;
+		switch ( n.m_eKind )
+		{
+		case NWAY_PROXIMITY:	bEmit = ProximityFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead ); break;
+		case NWAY_NEAR:			bEmit = NearFSM ( n, s, uBestHit, uBestQpos, (uint32_t)iBestW, s.m_tHead ); break;
+		case NWAY_BEFORE:
+			OrderFSM ( n, s, uBestHit, iBestW );
+			continue;	// (a completed sequence is handed out at the top of the loop)
+		case NWAY_QUORUM:
+			s.m_tHead.m_uHitpos = uBestHit; s.m_tHead.m_uQpos = uBestQpos; s.m_tHead.m_uSpanlen = 1; s.m_tHead.m_uWeight = 1;
+			bEmit = true;
+			break;
+		default:				bEmit = PhraseFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead ); break;
+		}
 		if ( bEmit )
 		{
-			if ( !s.m_bAny )
-			{
-				s.m_bAny = true;
-				s.m_uFirstRawHit = uBestHit;
-			}
+			fnEmitted ( uBestHit );
 			return;
 		}
 	}
 }
 
-/// opens the cursors of n-way node j on the document in slot `s` (hitlist positions at pHitpos[leaf*iStride+s]) and produces its first folded hit
+/// opens the cursors of hit-level node j on the document in slot `s` (hitlist positions at pHitpos[leaf*iStride+s]) and produces its first hit
 __device__ void NWayOpen ( const DevIndex_t & tIdx, const DevQuery_t & q, int j, const uint64_t * pHitpos, int iStride, int s, DocHits_t & H )
 {
 	const DevNWay_t & n = q.m_dNWay[j];
 	for ( int w=0; w<n.m_nWords; ++w )
 	{
 		const int l = n.m_dLeaf[w];
-		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, pHitpos[(size_t)l*iStride+s] );
+		const uint64_t uHitpos = pHitpos[(size_t)l*iStride+s];
+		if ( uHitpos==HITPOS_ABSENT && n.m_eKind>=NWAY_NOTNEAR )
+		{
+			H.m_dCur[l].m_iState = 2;
+			H.m_dCur[l].m_p = H.m_dCur[l].m_pStart = nullptr;
+			H.m_dHead[l] = 0;
+			continue;
+		}
+		SeekHitlist ( H.m_dCur[l], tIdx.m_pSpp, uHitpos );
 		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields, q.m_dLeaves[l].m_iTermPos );
 	}
 	H.m_dNWay[j].m_bAny = false;

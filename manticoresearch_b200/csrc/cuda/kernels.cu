@@ -379,6 +379,12 @@ struct EvalShared_t
 	int				m_dPreOff[MAX_LEAVES+1];	///< first predecode block slot of each leaf in this tile
 	uint32_t		m_dRankTab[16];		///< ExtRanker_WeightSum_c: sum of the weights of the fields in a 4-bit mask (indexes with <= 4 fields)
 	uint32_t		m_dAliveBits[TILE_W/32];
+	// quorum node: the children vector's order per rowid interval (ExtQuorum_c removes a keyword with RemoveFast when it runs out of documents)
+	uint32_t		m_dQLast[MAX_PHRASE_WORDS];								///< last rowid of each child (0xFFFFFFFF: no documents)
+	uint32_t		m_dQBound[MAX_PHRASE_WORDS+1];							///< interval k holds the rows <= m_dQBound[k]
+	uint8_t			m_dQOrder[MAX_PHRASE_WORDS+1][MAX_PHRASE_WORDS];
+	uint8_t			m_dQLen[MAX_PHRASE_WORDS+1];
+	int				m_nQIntervals;
 	float			m_dTf[256];			///< float(hits)/float(hits+1.2f), src/searchnode.cpp:1946
 	uint16_t		m_dRecStart[EVAL_WARPS][34];
 	__align__(16) uint8_t m_dStage[EVAL_WARPS][STAGE_BYTES];
@@ -746,6 +752,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 	V.m_pList = reinterpret_cast<uint16_t *>( dDyn + (size_t)nStack*TILE_W*( HITS ? 12 : 8 ) );
 	V.m_pCnt = dDyn + (size_t)nStack*TILE_W*( HITS ? 12 : 8 ) + ( HITS ? TILE_W*2 : 0 );
 	uint64_t * pHitpos = HITS ? P.m_pHitpos + (size_t)blockIdx.x*MAX_LEAVES*TILE_W : nullptr;
+	uint64_t * pLeafTf = HITS ? P.m_pLeafTf + (size_t)blockIdx.x*MAX_LEAVES*TILE_W : nullptr;
 	PreEntry_t * pPre = P.m_pPre + (size_t)blockIdx.x*PRE_BLOCKS*32;
 	uint64_t * pPreHitpos = HITS ? P.m_pPreHitpos + (size_t)blockIdx.x*PRE_BLOCKS*32 : nullptr;
 
@@ -799,6 +806,75 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 			S.m_dRankTab[tid] = uSum;
 		}
 		const bool bJump = q.m_iDriverLeaf>=0;	// pure AND query opened by a sparse keyword: visit only the tiles that keyword touches
+		if constexpr ( HITS )
+		{
+			// a quorum node (the planner admits one per query): the reference sums TF*IDF in the order of its children vector, and
+			// RemoveFast moves the last child into the slot of every keyword that has run out of documents. The order of each
+			// rowid interval follows from the keywords' last rowids.
+			int jq = -1;
+			for ( int j=0; j<q.m_nNWay; ++j )
+				if ( q.m_dNWay[j].m_eKind==NWAY_QUORUM )
+					jq = j;
+			if ( jq>=0 )
+			{
+				const DevNWay_t & tN = q.m_dNWay[jq];
+				if ( iWarp==0 )
+					for ( int w=0; w<tN.m_nWords; ++w )
+					{
+						const DevLeaf_t & tLeaf = q.m_dLeaves[tN.m_dLeaf[w]];
+						uint32_t uLast = 0xFFFFFFFFu;
+						if ( tLeaf.m_nBlocks )
+						{
+							DecodedDoc_t tDoc;
+							DecodeBlock<false> ( tIdx, tLeaf, tLeaf.m_nBlocks-1, S.m_dStage[0], S.m_dRecStart[0], iLane, tDoc );
+							uLast = __shfl_sync ( FULL_MASK, tDoc.m_uRowid, (int)( tLeaf.m_nDocs-32u*( tLeaf.m_nBlocks-1 ) )-1 );
+						}
+						if ( iLane==0 )
+							S.m_dQLast[w] = uLast;
+						__syncwarp();
+					}
+				__syncthreads();
+				if ( tid==0 )
+				{
+					uint8_t dVec[MAX_PHRASE_WORDS];
+					int nLen = tN.m_nWords, nInt = 0;
+					for ( int i=0; i<nLen; ++i )
+						dVec[i] = (uint8_t)i;
+					// warm-up (:4472-4484): children without documents go first
+					for ( int i=0; i<nLen; ++i )
+						if ( S.m_dQLast[dVec[i]]==0xFFFFFFFFu )
+						{
+							dVec[i] = dVec[--nLen];
+							--i;
+						}
+					while ( nLen>0 && nInt<MAX_PHRASE_WORDS+1 )
+					{
+						uint32_t uMin = 0xFFFFFFFFu;
+						for ( int i=0; i<nLen; ++i )
+							uMin = min ( uMin, S.m_dQLast[dVec[i]] );
+						S.m_dQBound[nInt] = uMin;
+						S.m_dQLen[nInt] = (uint8_t)nLen;
+						for ( int i=0; i<nLen; ++i )
+							S.m_dQOrder[nInt][i] = dVec[i];
+						++nInt;
+						for ( int i=0; i<nLen; ++i )
+							if ( S.m_dQLast[dVec[i]]==uMin )
+							{
+								dVec[i] = dVec[--nLen];
+								--i;
+							}
+					}
+					if ( !nInt )
+					{
+						S.m_dQBound[0] = 0xFFFFFFFFu;
+						S.m_dQLen[0] = 0;
+						nInt = 1;
+					}
+					S.m_nQIntervals = nInt;
+				}
+				__syncthreads();
+			}
+		}
 
 		uint32_t uTileLo = tItem.m_uRowLo;
 		while ( uTileLo<tItem.m_uRowHi )
@@ -996,7 +1072,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								const int s = (int)( tEntry.m_uRowid-uTileLo );
 								const bool bOn = ApplyTermOp<HITS> ( V, tOp, d, s, tEntry.m_fTf, tEntry.m_uFields, uEmitBit );
 								if ( HITS && bOn )
+								{
 									pHitpos[(size_t)tOp.m_uLeaf*TILE_W+s] = pPreHitpos[i];
+									pLeafTf[(size_t)tOp.m_uLeaf*TILE_W+s] = (uint64_t)__float_as_uint ( tEntry.m_fTf ) | ( (uint64_t)tEntry.m_uFields<<32 );
+								}
 							}
 						} else
 						{
@@ -1024,7 +1103,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 								const float fTf = __fmul_rn ( __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) ), tLeaf.m_fIDF );
 								const bool bOn = ApplyTermOp<HITS> ( V, tOp, d, s, fTf, uFields, uEmitBit );
 								if ( HITS && bOn )
+								{
 									pHitpos[(size_t)tOp.m_uLeaf*TILE_W+s] = tDoc.m_uHitlistPos;
+									pLeafTf[(size_t)tOp.m_uLeaf*TILE_W+s] = (uint64_t)__float_as_uint ( fTf ) | ( (uint64_t)uFields<<32 );
+								}
 							}
 						}
 						__syncthreads();
@@ -1037,15 +1119,80 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 					if constexpr ( HITS )
 					{
 						const int j = tOp.m_uArg;
+						const DevNWay_t & tN = q.m_dNWay[j];
 						const int n = CompactAlive ( V, d, tOp.m_uAliveDst, TILE_W, &S.m_iListCnt );
 						for ( int i=tid; i<n; i+=EVAL_THREADS )
 						{
 							const int s = V.m_pList[i];
-							DocHits_t H;
-							NWayOpen ( tIdx, q, j, pHitpos, TILE_W, s, H );
-							if ( H.m_dNWay[j].m_tHead.m_uHitpos )
+							const uint32_t uOn = V.Emit ( d, s );	// the keywords sitting on the document
+							bool bOk = true;
+							if ( tN.m_eKind>=NWAY_NOTNEAR )
 							{
-								V.Fields ( d, s ) = 1u<<( ( H.m_dNWay[j].m_uFirstRawHit>>24 ) & 31u );
+								// optional children (NOTNEAR's right side, quorum keywords): mark the absent ones; quorum: count
+								// (ExtQuorum_c: a keyword the query repeats counts as often as it is repeated, up to its hits on the document, :4602-4632)
+								int iQuorum = 0;
+								for ( int w=( tN.m_eKind==NWAY_NOTNEAR ? 1 : 0 ); w<tN.m_nWords; ++w )
+								{
+									const int l = tN.m_dLeaf[w];
+									if ( !( ( uOn>>l ) & 1u ) )
+									{
+										pHitpos[(size_t)l*TILE_W+s] = HITPOS_ABSENT;
+										continue;
+									}
+									int k = 1;
+									if ( tN.m_dCount[w]>1 )
+									{
+										HitCursor_t c;
+										SeekHitlist ( c, tIdx.m_pSpp, pHitpos[(size_t)l*TILE_W+s] );
+										k = 0;
+										while ( k<(int)tN.m_dCount[w] && NextHit ( c, q.m_dLeaves[l].m_uQueriedFields, q.m_dLeaves[l].m_iTermPos ) )
+											++k;
+									}
+									iQuorum += k;
+								}
+								if ( tN.m_eKind==NWAY_QUORUM )
+									bOk = iQuorum>=max ( tN.m_iOpArg, 1 );
+							}
+							DocHits_t H;
+							if ( bOk )
+							{
+								NWayOpen ( tIdx, q, j, pHitpos, TILE_W, s, H );
+								bOk = H.m_dNWay[j].m_tHead.m_uHitpos!=0;
+							}
+							if ( bOk )
+							{
+								if ( tN.m_eKind==NWAY_BEFORE || tN.m_eKind==NWAY_NOTNEAR )
+								{
+									// the document carries its first child's TF*IDF and fields only (ExtOrder_c :4914, ExtNotNear_c :5430)
+									const uint64_t uRec = pLeafTf[(size_t)tN.m_dLeaf[0]*TILE_W+s];
+									V.Tfidf ( d, s ) = __uint_as_float ( (uint32_t)uRec );
+									V.Fields ( d, s ) = (uint32_t)( uRec>>32 );
+								} else if ( tN.m_eKind==NWAY_QUORUM )
+								{
+									// TF*IDF is summed in the order of the reference's children vector, which RemoveFast reshuffles whenever a
+									// keyword runs out of documents (ExtQuorum_c::GetDocsChunk :4486-4537): the order of this rowid's interval
+									const uint32_t uRow = uTileLo+(uint32_t)s;
+									int iInt = 0;
+									while ( iInt+1<S.m_nQIntervals && uRow>S.m_dQBound[iInt] )
+										++iInt;
+									float fT = 0.0f;
+									uint32_t uF = 0;
+									bool bFirst = true;
+									for ( int k=0; k<S.m_dQLen[iInt]; ++k )
+									{
+										const int l = tN.m_dLeaf[S.m_dQOrder[iInt][k]];
+										if ( !( ( uOn>>l ) & 1u ) )
+											continue;
+										const uint64_t uRec = pLeafTf[(size_t)l*TILE_W+s];
+										const float fTf = __uint_as_float ( (uint32_t)uRec );
+										fT = bFirst ? fTf : __fadd_rn ( fT, fTf );
+										uF |= (uint32_t)( uRec>>32 );
+										bFirst = false;
+									}
+									V.Tfidf ( d, s ) = fT;
+									V.Fields ( d, s ) = uF;
+								} else
+									V.Fields ( d, s ) = 1u<<( ( H.m_dNWay[j].m_uFirstRawHit>>24 ) & 31u );
 								V.Emit ( d, s ) = 1u<<( EMIT_NWAY_SHIFT+j );
 								V.Cnt ( d, s ) = tOp.m_uAliveOut;
 							} else

@@ -348,7 +348,8 @@ struct PNode_t
 {
 	int					m_eKind = PN_TERM;
 	int					m_iLeaf = -1;
-	std::vector<int>	m_dLeaves;		///< multi-AND: sorted order; n-way: chain order
+	std::vector<int>	m_dLeaves;		///< multi-AND: sorted order; n-way: chain order (NOTNEAR: must, not; quorum: children by query position)
+	std::vector<int>	m_dRegOrder;	///< hit-level nodes: the order GetQwords() registers the keywords in, when it is not the chain order
 	int					m_iLeft = -1, m_iRight = -1;
 	int					m_iNWay = -1;
 };
@@ -424,13 +425,13 @@ struct Planner_c
 			if ( tNode.op==MGPU_OP_QUORUM )
 			{
 				// degenerate quorums (src/searchnode.cpp:1638-1688): threshold >= words -> AND, threshold 1 -> OR, over the keywords sorted by
-				// doc count (chains of ExtAnd_c / ExtOr_c); a real ExtQuorum_c is not on the GPU path
+				// doc count (chains of ExtAnd_c / ExtOr_c); everything else is a real ExtQuorum_c
 				const int iCount = tNode.n_words, iThr = tNode.oparg;
 				const bool bOr = ( iThr<iCount && iCount<=256 && iThr==1 );
-				if ( iThr<iCount && iCount<=256 && iThr!=1 )
-					return Fail ( MGPU_E_UNSUPPORTED );
 				if ( tNode.first_word<0 || tNode.first_word+iCount>m_q.n_words )
 					return Fail ( MGPU_E_BAD_QUERY );
+				if ( iThr<iCount && iCount<=256 && iThr!=1 )
+					return CreateQuorumNode ( tNode );
 				PNode_t t;
 				t.m_eKind = bOr ? PN_MULTIOR : PN_MULTIAND;
 				for ( int i=0; i<iCount; ++i )
@@ -456,6 +457,9 @@ struct Planner_c
 		for ( int i=0; i<nChildren; ++i )
 			if ( pChildren[i]<0 || pChildren[i]>=m_q.n_nodes )
 				return Fail ( MGPU_E_BAD_QUERY );
+
+		if ( tNode.op==MGPU_OP_NEAR || tNode.op==MGPU_OP_BEFORE || tNode.op==MGPU_OP_NOTNEAR )
+			return CreateKeywordOpNode ( tNode, pChildren, nChildren );
 
 		bool bAndTerms = ( tNode.op==MGPU_OP_AND );
 		for ( int i=0; i<nChildren && bAndTerms; ++i )
@@ -518,7 +522,7 @@ struct Planner_c
 		t.m_eKind = PN_NWAY;
 		t.m_iNWay = d.m_nNWay;
 		DevNWay_t & n = d.m_dNWay[d.m_nNWay++];
-		n.m_bProximity = ( tNode.op==MGPU_OP_PROXIMITY );
+		n.m_eKind = ( tNode.op==MGPU_OP_PROXIMITY ) ? NWAY_PROXIMITY : NWAY_PHRASE;
 		n.m_iOpArg = tNode.oparg;
 		n.m_nWords = tNode.n_words;
 		for ( int i=0; i<tNode.n_words; ++i )
@@ -546,6 +550,104 @@ struct Planner_c
 		return NewNode ( t );
 	}
 
+	/// NEAR / BEFORE / NOTNEAR whose children are plain keywords: hit-level nodes in the n-way slot of the hit stage.
+	/// NEAR = CreateMultiNode<ExtMultinear_c> + ExtNWay_T::ConstructNode (src/searchnode.cpp:933-978, 3767-3802): AND chain over the
+	/// children sorted by doc count, acceptor FSMmultinear_c; only the two-children form (the n-way FSM carries m_uFirstQpos from one
+	/// document to the next in the reference, :4193-4229 vs ResetFSM, so its hits depend on the documents seen before).
+	/// BEFORE = CreateOrderNode / ExtOrder_c (:1044-1074, 4657-4935); NOTNEAR = ExtNotNear_c (:5325-5478).
+	/// Children that are phrases, OR groups or other operators are not on the GPU path.
+	int CreateKeywordOpNode ( const mgpu_xqnode & tNode, const int32_t * pChildren, int nChildren )
+	{
+		DevQuery_t & d = m_tOut.m_tDev;
+		if ( tNode.op!=MGPU_OP_NOTNEAR && nChildren<2 )
+			return -1;	// ("order node requires at least two children" / no phrase node from one child: an empty node)
+		if ( tNode.op==MGPU_OP_NOTNEAR && nChildren!=2 )
+			return Fail ( MGPU_E_BAD_QUERY );
+		for ( int i=0; i<nChildren; ++i )
+		{
+			const mgpu_xqnode & tChild = m_q.nodes[pChildren[i]];
+			if ( tChild.n_words!=1 || tChild.n_children )
+				return Fail ( MGPU_E_UNSUPPORTED );
+		}
+		if ( ( tNode.op==MGPU_OP_NEAR && nChildren>2 ) || nChildren>MAX_PHRASE_WORDS || d.m_nNWay>=MAX_NWAY )
+			return Fail ( MGPU_E_UNSUPPORTED );
+		PNode_t t;
+		t.m_eKind = PN_NWAY;
+		t.m_iNWay = d.m_nNWay;
+		DevNWay_t & n = d.m_dNWay[d.m_nNWay++];
+		n.m_eKind = tNode.op==MGPU_OP_NEAR ? NWAY_NEAR : tNode.op==MGPU_OP_BEFORE ? NWAY_BEFORE : NWAY_NOTNEAR;
+		n.m_iOpArg = tNode.oparg;
+		n.m_nWords = nChildren;
+		for ( int i=0; i<nChildren; ++i )
+		{
+			const mgpu_xqnode & tChild = m_q.nodes[pChildren[i]];
+			int iLeaf = AddLeaf ( tChild, tChild.first_word, i );
+			if ( iLeaf<0 )
+				return -1;
+			t.m_dLeaves.push_back ( iLeaf );
+			n.m_dLeaf[i] = iLeaf;
+			n.m_dAtomPos[i] = m_dLeaves[iLeaf].m_iAtomPos;
+			n.m_dCount[i] = 1;
+		}
+		if ( n.m_eKind==NWAY_BEFORE )
+			t.m_dRegOrder = t.m_dLeaves;	// ExtOrder_c::GetQwords walks the children as written
+		if ( n.m_eKind!=NWAY_NOTNEAR )
+			RefSort ( t.m_dLeaves, [this] ( int a, int b ) { return m_dLeaves[a].Docs()<m_dLeaves[b].Docs(); } );	// the AND chain under the acceptor
+		return NewNode ( t );
+	}
+
+	/// ExtQuorum_c (src/searchnode.cpp:4319-4650): keywords the query repeats fold into the first occurrence with a count (ctor :4342-4404),
+	/// the children are kept by query position; a document matches when the counts of the keywords on it (each up to its hits there)
+	/// reach the threshold. One quorum node per query on the GPU path.
+	int CreateQuorumNode ( const mgpu_xqnode & tNode )
+	{
+		DevQuery_t & d = m_tOut.m_tDev;
+		if ( d.m_nNWay>=MAX_NWAY )
+			return Fail ( MGPU_E_UNSUPPORTED );
+		for ( int j=0; j<d.m_nNWay; ++j )
+			if ( d.m_dNWay[j].m_eKind==NWAY_QUORUM )
+				return Fail ( MGPU_E_UNSUPPORTED );
+		struct Child_t { int m_iWord; int m_iCount; int m_iNodePos; };
+		std::vector<Child_t> dChildren;
+		for ( int i=0; i<tNode.n_words; ++i )
+		{
+			const int iWord = tNode.first_word+i;
+			if ( !m_q.words[iWord].word )
+				return Fail ( MGPU_E_BAD_QUERY );
+			size_t iParent = dChildren.size();
+			for ( size_t k=0; k<dChildren.size(); ++k )
+				if ( !strcmp ( m_q.words[dChildren[k].m_iWord].word, m_q.words[iWord].word ) )
+					iParent = k;
+			if ( iParent<dChildren.size() )
+				dChildren[iParent].m_iCount++;
+			else
+				dChildren.push_back ( { iWord, 1, i } );
+		}
+		std::sort ( dChildren.begin(), dChildren.end(), [this] ( const Child_t & a, const Child_t & b ) { return m_q.words[a.m_iWord].atom_pos<m_q.words[b.m_iWord].atom_pos; } );
+		if ( (int)dChildren.size()>MAX_PHRASE_WORDS )
+			return Fail ( MGPU_E_UNSUPPORTED );
+		PNode_t t;
+		t.m_eKind = PN_NWAY;
+		t.m_iNWay = d.m_nNWay;
+		DevNWay_t & n = d.m_dNWay[d.m_nNWay++];
+		n.m_eKind = NWAY_QUORUM;
+		n.m_iOpArg = tNode.oparg;
+		n.m_nWords = (int)dChildren.size();
+		for ( size_t i=0; i<dChildren.size(); ++i )
+		{
+			if ( dChildren[i].m_iCount>255 )
+				return Fail ( MGPU_E_UNSUPPORTED );
+			int iLeaf = AddLeaf ( tNode, dChildren[i].m_iWord, dChildren[i].m_iNodePos );
+			if ( iLeaf<0 )
+				return -1;
+			t.m_dLeaves.push_back ( iLeaf );
+			n.m_dLeaf[i] = iLeaf;
+			n.m_dAtomPos[i] = m_dLeaves[iLeaf].m_iAtomPos;
+			n.m_dCount[i] = (uint8_t)dChildren[i].m_iCount;
+		}
+		return NewNode ( t );
+	}
+
 	/// ExtNode_i::GetQwords in eval-tree order (src/searchnode.cpp:2030-2057, 3244-3253, ExtTwofer_c)
 	void GetQwords ( int iNode )
 	{
@@ -555,7 +657,7 @@ struct Planner_c
 		case PN_TERM:		Register ( t.m_iLeaf ); break;
 		case PN_MULTIAND:
 		case PN_MULTIOR:
-		case PN_NWAY:		for ( int l : t.m_dLeaves ) Register ( l ); break;
+		case PN_NWAY:		for ( int l : ( t.m_dRegOrder.empty() ? t.m_dLeaves : t.m_dRegOrder ) ) Register ( l ); break;
 		default:			GetQwords ( t.m_iLeft ); GetQwords ( t.m_iRight ); break;
 		}
 	}
@@ -596,10 +698,17 @@ struct Planner_c
 		case PN_MULTIAND:
 		case PN_NWAY:
 			{
+				const int eNWay = t.m_eKind==PN_NWAY ? m_tOut.m_tDev.m_dNWay[t.m_iNWay].m_eKind : -1;
 				AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_dLeaves[0], 1 );
 				int iAlive = 1;
-				for ( size_t i=1; i<t.m_dLeaves.size(); ++i, ++iAlive )
-					AddOp ( OP_TERM_AND, iSp, 0, iAlive, 0, t.m_dLeaves[i], iAlive+1 );
+				if ( eNWay==NWAY_NOTNEAR )
+					AddOp ( OP_TERM_MAYBE, iSp, 0, 1, 0, t.m_dLeaves[1], 1 );	// every MUST document is a candidate; the NOT keyword only brings its hits
+				else if ( eNWay==NWAY_QUORUM )
+					for ( size_t i=1; i<t.m_dLeaves.size(); ++i )
+						AddOp ( OP_TERM_OR, iSp, 0, 1, 0, t.m_dLeaves[i], 1 );	// candidates = documents holding any of the keywords
+				else
+					for ( size_t i=1; i<t.m_dLeaves.size(); ++i, ++iAlive )
+						AddOp ( OP_TERM_AND, iSp, 0, iAlive, 0, t.m_dLeaves[i], iAlive+1 );
 				if ( t.m_eKind==PN_NWAY )
 					AddOp ( OP_NWAY, iSp, 0, iAlive, 0, 0, iAlive, t.m_iNWay );
 				return iAlive;
@@ -805,7 +914,10 @@ struct Planner_c
 				d.m_dGroupOp0[0] = 0;
 				d.m_dGroupOps[0] = (uint8_t)( d.m_nOps - ( bChainNWay ? 1 : 0 ) );
 			}
-			if ( ( d.m_bNeedHits && d.m_nGroups>1 ) || m_bAnyTermPos )
+			bool bTileOnly = false;
+			for ( int j=0; j<d.m_nNWay; ++j )
+				bTileOnly |= d.m_dNWay[j].m_eKind>=NWAY_BEFORE;	// these nodes rebuild the document's TF*IDF from per-slot records of eval_kernel
+			if ( ( d.m_bNeedHits && d.m_nGroups>1 ) || m_bAnyTermPos || bTileOnly )
 				d.m_nGroups = 0;	// hit-consuming DNF and position-filtered keywords stay on dense tiles
 		}
 
@@ -1538,6 +1650,7 @@ int Batch_c::Run()
 	Index_c::RunScratch_t & tScr = pIndex->m_tScratch;
 	CUDA_TRY ( tScr.m_dPool.Grow ( m_nPool ), m_sError );
 	CUDA_TRY ( tScr.m_dHitpos.Grow ( m_nHitpos ), m_sError );
+	CUDA_TRY ( tScr.m_dLeafTf.Grow ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W ), m_sError );
 	CUDA_TRY ( tScr.m_dPre.Grow ( m_nPre ), m_sError );
 	if ( m_dCtas[5] || m_dCtas[6] )
 		CUDA_TRY ( tScr.m_dOrList.Grow ( std::max ( (size_t)m_dCtas[5]*StreamOrListCap ( m_iOrMode ), (size_t)m_dCtas[6]*StreamOrListCap ( 2 ) )*EVAL_WARPS ), m_sError );
@@ -1634,6 +1747,7 @@ int Batch_c::Run()
 		P.m_pCounter = m_dCounter.m_p + c;
 		P.m_iKMax = m_iKMax;
 		P.m_pHitpos = tScr.m_dHitpos.m_p;
+		P.m_pLeafTf = tScr.m_dLeafTf.m_p;
 		P.m_pQueryThr = m_dQueryThr.m_p;
 		P.m_pOrList = c>=5 ? tScr.m_dOrList.m_p : nullptr;
 		P.m_pDebug = c==5 ? m_dDebug.m_p : nullptr;

@@ -122,7 +122,7 @@ public:
 	struct RunScratch_t
 	{
 		DevBuf_T<Key128_t>		m_dPool;
-		DevBuf_T<uint64_t>		m_dHitpos, m_dPreHitpos;
+		DevBuf_T<uint64_t>		m_dHitpos, m_dPreHitpos, m_dLeafTf;
 		DevBuf_T<PreEntry_t>	m_dPre, m_dOrList;
 		DevBuf_T<uint16_t>		m_dHotData;
 		DevBuf_T<uint32_t>		m_dHotBits, m_dHotLvlBits;

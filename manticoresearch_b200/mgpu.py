@@ -273,6 +273,26 @@ def PROXIMITY(words_with_pos, distance, **kwargs):
     return Node(OP_PROXIMITY, words=[Keyword(w, p) for w, p in words_with_pos], oparg=distance, **kwargs)
 
 
+def NEAR(distance, *children):
+    """a NEAR/n b ...: children are nodes (the CUDA path runs the two-keyword form)"""
+    return Node(OP_NEAR, children=list(children), oparg=distance)
+
+
+def BEFORE(*children):
+    """a << b << c"""
+    return Node(OP_BEFORE, children=list(children))
+
+
+def NOTNEAR(distance, must, unwanted):
+    """must NOTNEAR/n unwanted"""
+    return Node(OP_NOTNEAR, children=[must, unwanted], oparg=distance)
+
+
+def QUORUM(words_with_pos, threshold, **kwargs):
+    """"a b c"/N with an ABSOLUTE threshold"""
+    return Node(OP_QUORUM, words=[Keyword(w, p) for w, p in words_with_pos], oparg=threshold, **kwargs)
+
+
 class SortKey:
     def __init__(self, kind, attr=0, desc=True):
         self.kind, self.attr, self.desc = kind, attr, desc

@@ -155,7 +155,7 @@ def random_boolean_queries(n, seed, max_rank=20000, nfields=2, rankers=(M.RANK_B
     return out
 
 
-def random_hit_queries(params, n, seed, max_matches=200):
+def random_hit_queries(params, n, seed, max_matches=200, with_hitops=False):
     """parity fuzz set of the hit stage: phrases / proximities sampled from real docs (some of stop words), combined with
     AND / OR / ANDNOT / MAYBE and plain keywords, ranked by every ranker; some queries repeat a keyword (dupes path)"""
     rng = random.Random(seed)
@@ -213,8 +213,47 @@ def random_hit_queries(params, n, seed, max_matches=200):
                 node.field_mask = 1 << field
             return node
 
+        def hitop():
+            """NEAR / BEFORE / NOTNEAR / quorum over keywords that really sit close together in some document"""
+            while True:
+                doc = params.first_doc + rng.randrange(params.n_docs)
+                field = 1 if rng.random() < 0.8 else 0
+                flen = M.synth_field_len(params, doc, field)
+                if flen >= 10:
+                    break
+            span = min(flen - 1, 12)
+            p0 = rng.randrange(flen - span)
+            k = rng.randint(2, 4)
+            offs = sorted(rng.sample(range(span), k))
+            terms = [M.synth_token(params, doc, field, p0 + o) for o in offs]
+            v = rng.random()
+            if v < 0.3:
+                a, b = rng.sample(terms, 2) if rng.random() < 0.85 else (terms[0], terms[0])
+                return M.NEAR(rng.choice([1, 2, 4, 9]), leaf(M.synth_keyword(a)), leaf(M.synth_keyword(b)))
+            if v < 0.55:
+                if rng.random() < 0.3:
+                    rng.shuffle(terms)
+                if rng.random() < 0.15:
+                    terms[-1] = terms[0]
+                return M.BEFORE(*[leaf(M.synth_keyword(t)) for t in terms])
+            if v < 0.8:
+                other = terms[1] if rng.random() < 0.7 else sampler.sample(rng) - 1
+                return M.NOTNEAR(rng.choice([1, 2, 5, 12]), leaf(M.synth_keyword(terms[0])), leaf(M.synth_keyword(other)))
+            words = list(terms) + [sampler.sample(rng) - 1 for _ in range(rng.randint(0, 2))]
+            if rng.random() < 0.3:
+                words.insert(rng.randrange(len(words) + 1), words[0])    # a repeated keyword: counts up to its hits
+            ws = []
+            for t in words:
+                pos[0] += 1
+                ws.append((M.synth_keyword(t), pos[0]))
+            return M.QUORUM(ws, rng.randint(2, max(2, len(ws) - 1)))
+
         u = rng.random()
-        if u < 0.25:
+        if with_hitops and u < 0.3:
+            h = hitop()
+            v = rng.random()
+            root = h if v < 0.6 else M.OR(h, leaf()) if v < 0.75 else M.AND(h, leaf()) if v < 0.9 else M.ANDNOT(h, leaf())
+        elif u < 0.25:
             root = nway()
         elif u < 0.4:
             root = M.OR(nway(), leaf())

@@ -161,7 +161,8 @@ int main ( int argc, char ** argv )
 		std::vector<std::unique_ptr<GpuXQNode_t>> dKids;
 		dKids.push_back ( GpuXQNode_t::Keyword ( "program", 1 ) );
 		dKids.push_back ( GpuXQNode_t::Keyword ( "flow", 2 ) );
-		tQuery.m_pRoot = GpuXQNode_t::Op ( MGPU_OP_BEFORE, std::move ( dKids ) );
+		dKids.push_back ( GpuXQNode_t::Keyword ( "sample", 3 ) );
+		tQuery.m_pRoot = GpuXQNode_t::Op ( MGPU_OP_NEAR, std::move ( dKids ) );	// n-way NEAR: its FSM is stateful across documents in the reference
 		GpuMatchQueue_c tSorter ( 10 );
 		GpuQueryResultMeta_t tMeta;
 		CHECK ( !tIndex2.MultiQuery ( tMeta, tQuery, &tSorter ) );

@@ -474,6 +474,32 @@ out["cases"].append({
                  "expect": {"matches": [[1, 1500]], "total_found": 1, "words": {}}}],
 })
 
+
+
+# ---------------------------------------------------------------------------------------------
+# Which of these trees does the CUDA path still refuse (MGPU_E_UNSUPPORTED, never a guess)? Round 2 runs quorum nodes, and NEAR /
+# BEFORE / NOTNEAR over plain keywords in the hit stage. Left to the oracle: NEAR with three and more children (the reference's
+# FSMmultinear_c keeps m_uFirstQpos across documents, so the hits of a document depend on the documents before it) and
+# NEAR / BEFORE / NOTNEAR whose children are phrases, OR groups or other operators.
+# ---------------------------------------------------------------------------------------------
+def gpu_refuses(t):
+    kind = t[0]
+    if kind in ("kw", "phrase", "prox", "quorum"):
+        return False
+    kids = t[2:] if kind in ("near", "notnear") else t[1:]
+    if kind in ("near", "before", "notnear"):
+        if any(k[0] != "kw" for k in kids) or (kind == "near" and len(kids) != 2):
+            return True
+        return False
+    return any(gpu_refuses(k) for k in kids)
+
+
+for case in out["cases"]:
+    for q in case["queries"]:
+        q.pop("gpu_unsupported", None)
+        if gpu_refuses(q["tree"]):
+            q["gpu_unsupported"] = True
+
 with open(os.path.join(HERE, "golden_vectors.json"), "w", encoding="utf-8") as f:
     json.dump(out, f, ensure_ascii=False, indent=1)
 print("wrote", sum(len(c["queries"]) for c in out["cases"]), "golden queries in", len(out["cases"]), "cases")

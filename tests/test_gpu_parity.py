@@ -278,6 +278,24 @@ def test_hit_rankers_over_random_trees(synth):
     assert _compare_batch(synth, queries, allow_unsupported=0.05) <= 15
 
 
+def test_hit_level_operators_fuzz(synth):
+    """NEAR (two keywords), BEFORE, NOTNEAR and quorum nodes over keywords that really sit close together, alone and inside
+    AND / OR / ANDNOT trees, with position filters, field limits, repeated keywords, every ranker: the hit stage's FSMs
+    (FSMmultinear_c, ExtOrder_c, ExtNotNear_c, ExtQuorum_c restated in hit_stage.cuh) against the oracle's"""
+    queries = workload.random_hit_queries(synth["params"], 400, seed=977, with_hitops=True)
+    n_ops = sum(1 for q in queries if any(n.op in (M.OP_NEAR, M.OP_BEFORE, M.OP_NOTNEAR, M.OP_QUORUM) for n in _walk(q.root)))
+    assert n_ops > 80
+    assert _compare_batch(synth, queries, allow_unsupported=0.05) <= 20
+    g = synth["gpu"].search(queries)
+    assert sum(1 for i in range(len(queries)) if g.get(i)["total_found"] > 0) > len(queries) // 2
+
+
+def _walk(node):
+    yield node
+    for c in node.children:
+        yield from _walk(c)
+
+
 def test_hot_store_escape_and_plain_format(tmp_path):
     """dense hot-term store edge cases: documents with >= 255 hits of a shared keyword (escape list), a keyword present in
     every row, ragged last tile; plus the same corpus written with hit_format=plain"""
@@ -316,7 +334,9 @@ def test_hot_store_escape_and_plain_format(tmp_path):
 
 
 def test_golden_vectors_on_gpu(golden_cases, golden_indexes):
-    """the reference's own golden results (model.bin of test_019/037/322/116/114 + gtest WeightBoundary): every query must run on the CUDA path"""
+    """the reference's own golden results (17 model.bin files + gtest WeightBoundary): every query runs on the CUDA path, quorum /
+    NEAR / BEFORE / NOTNEAR over plain keywords included; the trees flagged gpu_unsupported (make_golden.py: n-way NEAR, operator
+    children that are not plain keywords) must be refused, never guessed"""
     ran = 0
     for case in golden_cases:
         gpu = M.Index(golden_indexes[case["name"]], device=0)
@@ -326,15 +346,23 @@ def test_golden_vectors_on_gpu(golden_cases, golden_indexes):
                 r = gpu.search([query]).get(0)
                 ran += 1
                 if q.get("gpu_unsupported"):
-                    # operators pinned in the oracle only (real quorum nodes): the CUDA path has to refuse them, never guess
+                    # shapes pinned in the oracle only: the CUDA path has to refuse them, never guess
                     assert r["status"] == M.MGPU_E_UNSUPPORTED, (case["name"], q["text"], r["status"])
                     continue
                 assert r["status"] == 0, (case["name"], q["text"], r["status"])
                 got = list(zip(r["docid"], r["weight"]))
+                if q.get("ids_only"):       # SphinxQL `select *` results: the reference's model holds no weights for these;
+                    got = [(d, 0) for d, _ in got]      # the weights are checked against the oracle below
                 if q.get("limit"):
                     got = got[:q["limit"]]
                 assert got == [tuple(m) for m in q["expect"]["matches"]], (case["name"], q["text"])
                 assert r["total_found"] == q["expect"]["total_found"]
+                if q.get("ids_only"):
+                    cpu = helpers.OracleIndex(golden_indexes[case["name"]])
+                    try:
+                        helpers.assert_same_results(r, cpu.search([query]).get(0), ctx="%s %s" % (case["name"], q["text"]))
+                    finally:
+                        cpu.close()
         finally:
             gpu.close()
     assert ran == sum(len(c["queries"]) for c in golden_cases)
