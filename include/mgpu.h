@@ -26,7 +26,7 @@ extern "C" {
 enum {
 	MGPU_OK = 0,
 	MGPU_E_IO = -1,           /* index files missing / unreadable */
-	MGPU_E_FORMAT = -2,       /* not an index-format v54..v62 plain index, or hitless/unsupported settings */
+	MGPU_E_FORMAT = -2,       /* not an index-format v57..v62 plain index with a keywords dictionary, or hitless/unsupported settings */
 	MGPU_E_UNSUPPORTED = -3,  /* query uses an operator/ranker/sort the CUDA path does not implement */
 	MGPU_E_BAD_QUERY = -4,    /* malformed tree (reference: sphCreateRanker returns nullptr, sphinxsearch.cpp:4377) */
 	MGPU_E_NO_DEVICE = -5,    /* no CUDA device; the product never falls back to the CPU */
@@ -41,12 +41,12 @@ enum {
 	MGPU_OP_MAYBE = 2,      /* SPH_QUERY_MAYBE */
 	MGPU_OP_NOT = 3,        /* SPH_QUERY_NOT (must have been fixed up to ANDNOT by the parser) */
 	MGPU_OP_ANDNOT = 4,     /* SPH_QUERY_ANDNOT */
-	MGPU_OP_BEFORE = 5,
+	MGPU_OP_BEFORE = 5,     /* SPH_QUERY_BEFORE: a << b << c; on the GPU path when every child is a plain keyword */
 	MGPU_OP_PHRASE = 6,     /* SPH_QUERY_PHRASE */
 	MGPU_OP_PROXIMITY = 7,  /* SPH_QUERY_PROXIMITY, oparg = N of "..."~N */
-	MGPU_OP_QUORUM = 8,     /* SPH_QUERY_QUORUM, oparg = threshold (absolute) */
-	MGPU_OP_NEAR = 9,       /* SPH_QUERY_NEAR, oparg = distance; n-ary */
-	MGPU_OP_NOTNEAR = 10    /* SPH_QUERY_NOTNEAR, oparg = distance; two children: must, not */
+	MGPU_OP_QUORUM = 8,     /* SPH_QUERY_QUORUM, oparg = threshold (absolute); one real quorum node per query on the GPU path */
+	MGPU_OP_NEAR = 9,       /* SPH_QUERY_NEAR, oparg = distance; n-ary in the reference, two plain keywords on the GPU path */
+	MGPU_OP_NOTNEAR = 10    /* SPH_QUERY_NOTNEAR, oparg = distance; two children: must, not (plain keywords on the GPU path) */
 };
 
 /* ---- ESphRankMode (src/sphinx.h:2388-2404) ---- */
@@ -79,8 +79,8 @@ typedef struct mgpu_xqkeyword {
 	const char *	word;        /* m_sWord, dictionary form (tokenised, lower-cased by the caller's tokenizer) */
 	int32_t			atom_pos;    /* m_iAtomPos, 1-based in-query position */
 	float			boost;       /* m_fBoost (1.0f default) */
-	uint8_t			field_start; /* m_bFieldStart  -> MGPU_E_UNSUPPORTED for now */
-	uint8_t			field_end;   /* m_bFieldEnd    -> MGPU_E_UNSUPPORTED for now */
+	uint8_t			field_start; /* m_bFieldStart: ^keyword (ExtTermPos_T, hit stage) */
+	uint8_t			field_end;   /* m_bFieldEnd: keyword$ */
 	uint8_t			excluded;    /* m_bExcluded */
 	uint8_t			expanded;    /* m_bExpanded */
 } mgpu_xqkeyword;
@@ -94,7 +94,7 @@ typedef struct mgpu_xqnode {
 	int32_t			first_word;    /* index into mgpu_query.words[] */
 	int32_t			n_words;
 	uint32_t		field_mask;    /* XQLimitSpec_t::m_dFieldMask, fields 0..31; 0xFFFFFFFF = all */
-	int32_t			field_max_pos; /* XQLimitSpec_t::m_iFieldMaxPos; nonzero -> MGPU_E_UNSUPPORTED */
+	int32_t			field_max_pos; /* XQLimitSpec_t::m_iFieldMaxPos: @field[N] (0 = no limit) */
 	uint8_t			not_weighted;  /* m_bNotWeighted */
 	uint8_t			pad[3];
 } mgpu_xqnode;

@@ -50,7 +50,7 @@ struct StreamShared_t
 	int				m_iPoolCnt;
 	int				m_iPoolBuf;
 	uint32_t		m_dRankTab[16];
-	int32_t			m_dRankUb[16];						///< bound pass: ( field-weight sum*1000 + 500 )*256 + rounding margin, per matched-field mask
+	int32_t			m_dRankUb[16];						///< bound pass: ( field-weight sum*1000 + 500 )*64 + rounding margin, per matched-field mask
 	const uint16_t * m_dOpPtr[MAX_LEAVES];				///< bound pass: the op's row of the dense store (null = sparse keyword)
 	uint8_t			m_dHotLeaf[MAX_LEAVES];				///< exact pass: hot keywords only (compacted, op order): the keyword's leaf
 	const uint16_t * m_dHotPtr[MAX_LEAVES+4];			///< ... and its row of the dense store
