@@ -1428,7 +1428,7 @@ template<> struct HitsState_T<true> { typedef DocHits_t Type_t; };
 
 template<bool HITS>
 __device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, const DevHotStore_t & tHot, const DevLeaf_t & tLeaf, uint32_t uRowid, bool bActive,
-	AndShared_t & S, int iWarp, int iLane, uint32_t & uHitsOut, uint64_t & uHitposOut )
+	AndShared_t & S, int iWarp, int iLane, uint32_t & uHitsOut, uint64_t & uHitposOut, uint32_t uPreloaded=0xFFFFFFFFu )
 {
 	uint32_t uHits = 0, uF = 0;
 	uint64_t uHitpos = 0;
@@ -1436,7 +1436,8 @@ __device__ __noinline__ uint32_t WarpProbeKeyword ( const DevIndex_t & tIdx, con
 	{
 		if ( bActive )
 		{
-			const uint32_t v = __ldg ( tHot.m_pData + (size_t)tLeaf.m_iHot*tHot.m_iStride + uRowid );
+			// (uPreloaded: the row's store entry, requested by ProbeGroup before the group's first probe)
+			const uint32_t v = uPreloaded!=0xFFFFFFFFu ? uPreloaded : __ldg ( tHot.m_pData + (size_t)tLeaf.m_iHot*tHot.m_iStride + uRowid );
 			uHits = v & 255u;
 			uF = uHits ? ( ( v>>8 ) & tLeaf.m_uQueriedFields ) : 0u;
 			if ( uF && uHits==255u )

@@ -91,6 +91,11 @@ public:
 	std::vector<NcclComm_t>							m_dComms;		///< one per shard when every shard has a GPU of its own
 	bool											m_bSameDevice = true;
 
+	// host arrays reused from call to call (their pages stay mapped)
+	std::vector<mgpu_query>			m_dQueries;
+	std::vector<int64_t>			m_dWordDocs;
+	std::vector<PlannedQuery_t>		m_dTemplate;
+
 	// exchange buffers on shard 0's GPU (grow-only)
 	DevBuf_T<Key128_t>		m_dGatherKeys, m_dMergeScratch, m_dOutKeys;
 	DevBuf_T<int64_t>		m_dGatherDocid, m_dOutDocid, m_dGatherTotal;
@@ -180,38 +185,19 @@ public:
 		m_tStats = mgpu_sharded_stats {};
 		m_tStats.n_shards = nShards;
 
-		// 1. statistics of the whole index for every query that does not bring its own (SetupLocalDF, src/searchd.cpp:5869)
-		std::vector<mgpu_query> dQueries ( pQueries, pQueries+nQueries );
-		size_t nWords = 0;
+		// 1. statistics of the whole index for every query that does not bring its own (SetupLocalDF, src/searchd.cpp:5869) and
+		// 2. planning, ONCE (shard 0's dictionary; the shard threads re-bind the keywords): both per query, spread over the host threads.
+		// The arrays are members: a 10k-query batch's 34 MB of plans are not page-faulted in again on every call.
+		std::vector<mgpu_query> & dQueries = m_dQueries;
+		dQueries.assign ( pQueries, pQueries+nQueries );
+		std::vector<size_t> dWordOff ( nQueries+1, 0 );
 		for ( int i=0; i<nQueries; ++i )
-			nWords += (size_t)std::max ( dQueries[i].n_words, 0 );
-		std::vector<int64_t> dWordDocs ( nWords );
-		size_t iWord = 0;
-		for ( int i=0; i<nQueries; ++i )
-		{
-			mgpu_query & q = dQueries[i];
-			if ( !q.total_docs )
-				q.total_docs = m_iTotalDocs;
-			if ( !q.word_docs && q.words && q.n_words>0 )
-			{
-				for ( int w=0; w<q.n_words; ++w )
-				{
-					int64_t iDocs = -1;
-					if ( q.words[w].word )
-					{
-						auto it = m_hGlobalDocs.find ( q.words[w].word );
-						iDocs = it==m_hGlobalDocs.end() ? 0 : it->second;
-					}
-					dWordDocs[iWord+w] = iDocs;
-				}
-				q.word_docs = dWordDocs.data()+iWord;
-			}
-			q.shard_of_global = 1;
-			iWord += (size_t)std::max ( q.n_words, 0 );
-		}
-
-		// 2. plan once (shard 0's dictionary; the shard threads re-bind the keywords)
-		std::vector<PlannedQuery_t> dTemplate ( nQueries );
+			dWordOff[i+1] = dWordOff[i] + (size_t)std::max ( dQueries[i].n_words, 0 );
+		std::vector<int64_t> & dWordDocs = m_dWordDocs;
+		dWordDocs.resize ( dWordOff[nQueries] );
+		std::vector<PlannedQuery_t> & dTemplate = m_dTemplate;
+		dTemplate.clear();
+		dTemplate.resize ( nQueries );
 		{
 			int nThreads = (int)std::min<unsigned> ( std::max ( 1u, std::thread::hardware_concurrency() ), 32u );
 			nThreads = std::max ( 1, std::min ( nThreads, nQueries/256 ) );
@@ -220,7 +206,28 @@ public:
 			auto fnPlan = [&] ( int iFrom, int iTo )
 			{
 				for ( int i=iFrom; i<iTo; ++i )
-					PlanQuery ( *m_dShards[0], dQueries[i], dTemplate[i] );
+				{
+					mgpu_query & q = dQueries[i];
+					if ( !q.total_docs )
+						q.total_docs = m_iTotalDocs;
+					if ( !q.word_docs && q.words && q.n_words>0 )
+					{
+						int64_t * pDocs = dWordDocs.data()+dWordOff[i];
+						for ( int w=0; w<q.n_words; ++w )
+						{
+							int64_t iDocs = -1;
+							if ( q.words[w].word )
+							{
+								auto it = m_hGlobalDocs.find ( q.words[w].word );
+								iDocs = it==m_hGlobalDocs.end() ? 0 : it->second;
+							}
+							pDocs[w] = iDocs;
+						}
+						q.word_docs = pDocs;
+					}
+					q.shard_of_global = 1;
+					PlanQuery ( *m_dShards[0], q, dTemplate[i] );
+				}
 			};
 			if ( nThreads<=1 )
 				fnPlan ( 0, nQueries );
@@ -393,7 +400,9 @@ public:
 		const int64_t * dDocid = (const int64_t *)( pStage+iOffDocid );
 		const int64_t * dTotal = (const int64_t *)( pStage+iOffTotal );
 		const int32_t * dCount = (const int32_t *)( pStage+iOffCount );
-		for ( int i=0; i<nQueries; ++i )
+		auto fnUnpack = [&] ( int iFrom, int iTo )
+		{
+		for ( int i=iFrom; i<iTo; ++i )
 		{
 			const PlannedQuery_t & p = dTemplate[i];
 			mgpu_result & r = pResults[i];
@@ -441,6 +450,20 @@ public:
 					}
 					r.sort_attr[k] = v;
 				}
+			}
+		}
+		};
+		{
+			const int nThreads = std::max ( 1, std::min ( { (int)std::thread::hardware_concurrency(), 8, nQueries/512 } ) );
+			if ( nThreads<=1 )
+				fnUnpack ( 0, nQueries );
+			else
+			{
+				std::vector<std::thread> dThreads;
+				for ( int t=0; t<nThreads; ++t )
+					dThreads.emplace_back ( fnUnpack, (int)( (int64_t)nQueries*t/nThreads ), (int)( (int64_t)nQueries*( t+1 )/nThreads ) );
+				for ( auto & t : dThreads )
+					t.join();
 			}
 		}
 		dBatches.clear();
