@@ -1,4 +1,5 @@
-// K3c orbits_kernel: launch class 5, pure OR programs under BM25 in relevance order ("OR over bit planes").
+// K3c orbits_kernel: launch class 5, OR programs under BM25 in relevance order ("OR over bit planes"): pure ORs of keywords, and
+// ORs of AND groups whose keywords all sit in the hot store (a pure AND of hot keywords is one such group).
 //
 // A top-K OR query has to COUNT every matching row (total_found = every push, src/sphinxsort.cpp:724) but only has to RANK the
 // rows that can still enter the top K. The batch's hot-term store carries, next to the u16 {hits, fields, tf class} per row, one
@@ -50,13 +51,16 @@ struct OrBitsShared_t
 	uint32_t		m_dRankTab[16];
 	int32_t			m_dRankUb[16];						///< ( field-weight sum*1000 + 500 )*64 + rounding margin, per matched-field mask
 	int32_t			m_bBound;
-	// bitmap pass: hot keywords sorted by their weight bound, biggest first
-	const uint32_t * m_dBitPtr[MAX_LEAVES];				///< the keyword's field-0 bitmap (field f: + f*bit stride)
-	uint32_t		m_dBitFields[MAX_LEAVES];			///< queried fields the index has
-	int32_t			m_dUb[MAX_LEAVES];					///< ceil ( max ( idf, 0 )*64000 ) + 1
+	// bitmap pass: the program's hot UNITS (a hot keyword of the OR, or an AND group of hot keywords) sorted by their weight bound,
+	// biggest first; their member keywords flat in that order
+	const uint32_t * m_dBitPtr[MAX_LEAVES];				///< member: the keyword's field-0 bitmap (field f: + f*bit stride)
+	uint32_t		m_dBitFields[MAX_LEAVES];			///< member: queried fields the index has
+	uint8_t			m_dMemLast[MAX_LEAVES];				///< member: the last one of its unit
+	int32_t			m_nMembers;
+	int32_t			m_dUb[MAX_LEAVES];					///< unit: sum over its keywords of ceil ( max ( idf, 0 )*64000 ) + 1
 	int32_t			m_dSuffix[MAX_LEAVES+1];			///< sum of m_dUb[i..]
-	uint8_t			m_dSortLeaf[MAX_LEAVES];			///< the sorted entry's leaf
-	int32_t			m_nHot;
+	uint8_t			m_dSortLeaf[MAX_LEAVES];			///< unit: its leaf when it is a single keyword, 0xFF for an AND group
+	int32_t			m_nHot;								///< hot units
 	int32_t			m_iUbListed;						///< the same bound summed over the listed keywords
 	// penalty classes: up to two hot keywords with idf < 0 that own tf-level bitmaps
 	int32_t			m_nNeg;
@@ -67,7 +71,9 @@ struct OrBitsShared_t
 	// exact pass: op order
 	const uint16_t * m_dOpPtr[MAX_LEAVES];				///< the op's row of the u16 store (null = listed keyword)
 	uint8_t			m_dOpList[MAX_LEAVES];				///< listed keyword: its entry in the arrays below
-	uint8_t			m_dHotLeaf[MAX_LEAVES];
+	uint8_t			m_dOpLast[MAX_LEAVES];				///< the op closes its unit
+	uint8_t			m_dHotLeaf[MAX_LEAVES];				///< hot keywords only, op order
+	uint8_t			m_dHotLast[MAX_LEAVES];				///< ... closes its unit
 	const uint16_t * m_dHotPtr[MAX_LEAVES+4];
 	int32_t			m_nHotOps;
 	// listed keywords
@@ -192,41 +198,69 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 		{
 			int nHot = 0, nHotOps = 0, nListed = 0, iUbListed = 0;
 			const uint32_t uIndexFields = ( 1u<<P.m_tHot.m_nBitFields )-1u;
-			for ( int iOp=0; iOp<q.m_nOps && iOp<MAX_LEAVES; ++iOp )
+			// units of the OR fold, in program order: AND groups (hot keywords only: the host's test) or single keywords
+			const bool bGroups = q.m_nGroups>0;
+			const int nUnits = bGroups ? q.m_nGroups : q.m_nOps;
+			uint8_t dUnitOp0[MAX_LEAVES], dUnitOps[MAX_LEAVES], dOrder[MAX_LEAVES];
+			int dUnitUb[MAX_LEAVES];
+			for ( int u=0; u<nUnits && u<MAX_LEAVES; ++u )
 			{
-				const int l = q.m_dOps[iOp].m_uLeaf;
-				const DevLeaf_t & tLeaf = q.m_dLeaves[l];
-				const float fIDF = tLeaf.m_fIDF;
-				// tf < 1: the keyword adds less than idf when it sits on the row, and nothing above 0 when idf <= 0
-				const int iUb = fIDF>0.0f ? (int)ceilf ( __fmul_rn ( fminf ( fIDF, 1.0f ), 64000.0f ) )+1 : 0;
-				S.m_dOpPtr[iOp] = nullptr;
-				if ( tLeaf.m_iHot<0 )
+				const int iOp0 = bGroups ? q.m_dGroupOp0[u] : u, nUnitOps = bGroups ? q.m_dGroupOps[u] : 1;
+				int iUbUnit = 0;
+				bool bListed = false;
+				for ( int iOp=iOp0; iOp<iOp0+nUnitOps; ++iOp )
 				{
-					S.m_dOpList[iOp] = (uint8_t)nListed;
-					S.m_dListLeaf[nListed] = (uint8_t)l;
-					S.m_dListEnd[nListed] = tLeaf.m_nBlocks ? tLeaf.m_uListOff+tLeaf.m_nDocs : 0u;	// (a keyword the index does not hold has no list)
-					++nListed;
-					iUbListed += iUb;
+					const int l = q.m_dOps[iOp].m_uLeaf;
+					const DevLeaf_t & tLeaf = q.m_dLeaves[l];
+					const float fIDF = tLeaf.m_fIDF;
+					// tf < 1: the keyword adds less than idf when it sits on the row, and nothing above 0 when idf <= 0
+					iUbUnit += fIDF>0.0f ? (int)ceilf ( __fmul_rn ( fminf ( fIDF, 1.0f ), 64000.0f ) )+1 : 0;
+					S.m_dOpPtr[iOp] = nullptr;
+					S.m_dOpLast[iOp] = ( iOp==iOp0+nUnitOps-1 ) ? 1 : 0;
+					if ( tLeaf.m_iHot<0 )
+					{
+						// (a single keyword outside the hot store: its postings come from the decoded list)
+						bListed = true;
+						S.m_dOpList[iOp] = (uint8_t)nListed;
+						S.m_dListLeaf[nListed] = (uint8_t)l;
+						S.m_dListEnd[nListed] = tLeaf.m_nBlocks ? tLeaf.m_uListOff+tLeaf.m_nDocs : 0u;	// (a keyword the index does not hold has no list)
+						++nListed;
+						continue;
+					}
+					const uint16_t * pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
+					S.m_dOpPtr[iOp] = pRow;
+					S.m_dHotPtr[nHotOps] = pRow;
+					S.m_dHotLast[nHotOps] = S.m_dOpLast[iOp];
+					S.m_dHotLeaf[nHotOps++] = (uint8_t)l;
+				}
+				if ( bListed )
+				{
+					iUbListed += iUbUnit;
 					continue;
 				}
-				const uint16_t * pRow = P.m_tHot.m_pData + (size_t)tLeaf.m_iHot*P.m_tHot.m_iStride;
-				S.m_dOpPtr[iOp] = pRow;
-				S.m_dHotPtr[nHotOps] = pRow;
-				S.m_dHotLeaf[nHotOps++] = (uint8_t)l;
-				// insertion into the list sorted by bound, biggest first
+				// insertion into the order sorted by bound, biggest first
+				dUnitOp0[nHot] = (uint8_t)iOp0; dUnitOps[nHot] = (uint8_t)nUnitOps; dUnitUb[nHot] = iUbUnit;
 				int j = nHot++;
-				for ( ; j>0 && S.m_dUb[j-1]<iUb; --j )
-				{
-					S.m_dUb[j] = S.m_dUb[j-1];
-					S.m_dBitPtr[j] = S.m_dBitPtr[j-1];
-					S.m_dBitFields[j] = S.m_dBitFields[j-1];
-					S.m_dSortLeaf[j] = S.m_dSortLeaf[j-1];
-				}
-				S.m_dSortLeaf[j] = (uint8_t)l;
-				S.m_dUb[j] = iUb;
-				S.m_dBitPtr[j] = P.m_tHot.m_pBits + (size_t)tLeaf.m_iHot*P.m_tHot.m_nBitFields*iBitStride;
-				S.m_dBitFields[j] = tLeaf.m_uQueriedFields & uIndexFields;
+				for ( ; j>0 && dUnitUb[dOrder[j-1]]<iUbUnit; --j )
+					dOrder[j] = dOrder[j-1];
+				dOrder[j] = (uint8_t)( nHot-1 );
 			}
+			int nMem = 0;
+			for ( int i=0; i<nHot; ++i )
+			{
+				const int u = dOrder[i];
+				S.m_dUb[i] = dUnitUb[u];
+				S.m_dSortLeaf[i] = dUnitOps[u]==1 ? q.m_dOps[dUnitOp0[u]].m_uLeaf : (uint8_t)0xFF;
+				for ( int iOp=dUnitOp0[u]; iOp<dUnitOp0[u]+dUnitOps[u]; ++iOp )
+				{
+					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
+					S.m_dBitPtr[nMem] = P.m_tHot.m_pBits + (size_t)tLeaf.m_iHot*P.m_tHot.m_nBitFields*iBitStride;
+					S.m_dBitFields[nMem] = tLeaf.m_uQueriedFields & uIndexFields;
+					S.m_dMemLast[nMem] = ( iOp==dUnitOp0[u]+dUnitOps[u]-1 ) ? 1 : 0;
+					++nMem;
+				}
+			}
+			S.m_nMembers = nMem;
 			int iSum = 0;
 			S.m_dSuffix[nHot] = 0;
 			for ( int i=nHot-1; i>=0; --i )
@@ -239,6 +273,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 			float dNegIdf[2] = { 0.0f, 0.0f };
 			for ( int i=0; i<nHot; ++i )
 			{
+				if ( S.m_dSortLeaf[i]==0xFF )
+					continue;	// (a stop word inside an AND group only lowers that group's sum: ignored by the bound)
 				const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dSortLeaf[i]];
 				const int iLvl = ( P.m_tHot.m_pLvlSlot && tLeaf.m_fIDF<0.0f ) ? __ldg ( P.m_tHot.m_pLvlSlot+tLeaf.m_iHot ) : -1;
 				if ( iLvl<0 )
@@ -275,7 +311,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 
 		__syncthreads();	// S.m_nHot and friends
 		int nQueue = 0;
-		const int nOps = q.m_nOps, nHot = S.m_nHot, nHotOps = S.m_nHotOps, nListed = S.m_nListed;
+		const int nOps = q.m_nOps, nHot = S.m_nHot, nHotOps = S.m_nHotOps, nListed = S.m_nListed, nMembers = S.m_nMembers;
 		const int iUbHot = S.m_dSuffix[0], iUbListed = S.m_iUbListed;
 		const int iIndexWeight = q.m_iIndexWeight;
 		const int nFv = 1<<P.m_tHot.m_nBitFields;
@@ -336,6 +372,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 			bool bPres = false;
 			if ( !__any_sync ( FULL_MASK, bAct && ( uEntry & OB_LISTED ) ) )
 			{
+				// unit by unit in program order: an AND group counts when all its keywords sit on the row, its sum folded keyword by
+				// keyword (ExtAnd_c / ExtMultiAnd_T: left + right); the units' sums are folded by ExtOr_c (src/searchnode.cpp:3486-3504)
+				float fG = 0.0f;
+				uint32_t uFG = 0;
+				bool bAll = true, bFirst = true;
 				for ( int h0=0; h0<nHotOps; h0+=4 )
 				{
 					uint32_t dRaw[4];
@@ -345,27 +386,45 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 					#pragma unroll
 					for ( int i=0; i<4; ++i )
 					{
+						if ( h0+i>=nHotOps )
+							break;
 						const uint32_t uHits = dRaw[i] & 255u;
-						if ( !uHits )
-							continue;
 						const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dHotLeaf[h0+i]];
 						const uint32_t uFields = ( dRaw[i]>>8 ) & tLeaf.m_uQueriedFields;
-						if ( !uFields )
-							continue;
-						float fBase = S.m_dTf[uHits];
-						if ( bAnyEscape && uHits==255 )
-							fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
-						const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
-						// ExtOr_c: both sides -> sum, one side -> copy (src/searchnode.cpp:3486-3504)
-						fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
-						uF |= uFields;
-						bPres = true;
+						if ( !uHits || !uFields )
+							bAll = false;
+						else
+						{
+							float fBase = S.m_dTf[uHits];
+							if ( bAnyEscape && uHits==255 )
+								fBase = HotEscapeTf ( P.m_tHot, tLeaf.m_iHot, uRow );
+							const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+							fG = bFirst ? fTf : __fadd_rn ( fG, fTf );
+							uFG |= uFields;
+							bFirst = false;
+						}
+						if ( S.m_dHotLast[h0+i] )
+						{
+							if ( bAll && !bFirst )
+							{
+								fT = bPres ? __fadd_rn ( fT, fG ) : fG;
+								uF |= uFG;
+								bPres = true;
+							}
+							fG = 0.0f; uFG = 0; bAll = true; bFirst = true;
+						}
 					}
 				}
 			} else
 			{
 				const bool bListed = bAct && ( uEntry & OB_LISTED );
-				for ( int iOp=0; iOp<nOps; ++iOp )
+				float fG = 0.0f;
+				uint32_t uFG = 0;
+				bool bAll = true, bFirst = true;
+				const bool bGroups = q.m_nGroups>0;
+				const int nUnits = bGroups ? q.m_nGroups : nOps;
+				for ( int u=0; u<nUnits; ++u )
+				for ( int iOp=( bGroups ? q.m_dGroupOp0[u] : u ), iOpEnd=iOp+( bGroups ? q.m_dGroupOps[u] : 1 ); iOp<iOpEnd; ++iOp )
 				{
 					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
 					const uint16_t * pRow = S.m_dOpPtr[iOp];
@@ -391,11 +450,24 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 						fBase = uHits<255u ? S.m_dTf[uHits] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
 					}
 					if ( !uHits || !uFields )
-						continue;
-					const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
-					fT = bPres ? __fadd_rn ( fT, fTf ) : fTf;
-					uF |= uFields;
-					bPres = true;
+						bAll = false;
+					else
+					{
+						const float fTf = __fmul_rn ( fBase, tLeaf.m_fIDF );
+						fG = bFirst ? fTf : __fadd_rn ( fG, fTf );
+						uFG |= uFields;
+						bFirst = false;
+					}
+					if ( S.m_dOpLast[iOp] )
+					{
+						if ( bAll && !bFirst )
+						{
+							fT = bPres ? __fadd_rn ( fT, fG ) : fG;
+							uF |= uFG;
+							bPres = true;
+						}
+						fG = 0.0f; uFG = 0; bAll = true; bFirst = true;
+					}
 				}
 			}
 			fnRankPush ( bAct && bPres, fT, uF, uRow, pPool, tThr );
@@ -542,7 +614,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 				// the bitmap lines two mini-tiles ahead (one 128 B line per keyword and field)
 				const uint32_t uWord = ( uLo>>5 ) + iLane;
 				if ( uLo+3*OB_MINI<=tItem.m_uRowHi )
-					for ( int i=iLane; i<nHot*NF; i+=32 )
+					for ( int i=iLane; i<nMembers*NF; i+=32 )
 						if ( ( S.m_dBitFields[i/NF]>>( i%NF ) ) & 1u )
 							asm volatile ( "prefetch.global.L2 [%0];" :: "l" ( S.m_dBitPtr[i/NF] + ( i%NF )*iBitStride + ( uLo>>5 ) + 64 ) );
 
@@ -609,33 +681,53 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 					uListedRows = dOv[4][iLane];
 				}
 
-				// 1. bitmap pass: four keywords at a time, all their loads in flight before the first use
-				for ( int i0=0; i0<nHot; i0+=4 )
+				// 1. bitmap pass: four keywords at a time, all their loads in flight before the first use. A unit's presence word is the AND of
+				// its keywords' presence words; its fields only count where the whole unit sits on the row.
 				{
-					uint32_t dW[4][NF];
+					uint32_t uUnitP = 0xFFFFFFFFu, dFu[NF];
 					#pragma unroll
-					for ( int j=0; j<4; ++j )
+					for ( int f=0; f<NF; ++f )
+						dFu[f] = 0;
+					int iUnit = 0;
+					for ( int i0=0; i0<nMembers; i0+=4 )
 					{
-						const bool b = i0+j<nHot;
-						const uint32_t uMask = b ? S.m_dBitFields[i0+j] : 0u;
-						const uint32_t * p = S.m_dBitPtr[b ? i0+j : 0] + uWord;
+						uint32_t dW[4][NF];
 						#pragma unroll
-						for ( int f=0; f<NF; ++f )
-							dW[j][f] = ( ( uMask>>f ) & 1u ) ? __ldg ( p + f*iBitStride ) : 0u;
-					}
-					#pragma unroll
-					for ( int j=0; j<4; ++j )
-						if ( i0+j<nHot )
+						for ( int j=0; j<4; ++j )
 						{
-							uint32_t uAny = 0;
+							const bool b = i0+j<nMembers;
+							const uint32_t uMask = b ? S.m_dBitFields[i0+j] : 0u;
+							const uint32_t * p = S.m_dBitPtr[b ? i0+j : 0] + uWord;
 							#pragma unroll
 							for ( int f=0; f<NF; ++f )
-							{
-								dF[f] |= dW[j][f];
-								uAny |= dW[j][f];
-							}
-							pPsm[( i0+j )*32+iLane] = uAny;
+								dW[j][f] = ( ( uMask>>f ) & 1u ) ? __ldg ( p + f*iBitStride ) : 0u;
 						}
+						#pragma unroll
+						for ( int j=0; j<4; ++j )
+							if ( i0+j<nMembers )
+							{
+								uint32_t uAny = 0;
+								#pragma unroll
+								for ( int f=0; f<NF; ++f )
+								{
+									dFu[f] |= dW[j][f];
+									uAny |= dW[j][f];
+								}
+								uUnitP &= uAny;
+								if ( S.m_dMemLast[i0+j] )
+								{
+									#pragma unroll
+									for ( int f=0; f<NF; ++f )
+									{
+										dF[f] |= dFu[f] & uUnitP;
+										dFu[f] = 0;
+									}
+									pPsm[iUnit*32+iLane] = uUnitP;
+									++iUnit;
+									uUnitP = 0xFFFFFFFFu;
+								}
+							}
+					}
 				}
 				++uDbgMinis;
 				uint32_t uPresent = 0;

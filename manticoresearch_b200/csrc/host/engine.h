@@ -89,6 +89,8 @@ struct EngineOptions_t
 	int		m_iOrRangeTiles = 1024;		///< "or_range_tiles": rows/2048 per work item of the bound + exact pass classes
 	int		m_iDnfPct = 12;				///< "dnf_pct": a group driver of the intersection kernel sits in < dnf_pct % of the rows
 	int		m_bOrBits = 1;				///< "or_bits": pure OR programs run on orbits_kernel (0: stream_kernel<512,1>)
+	int		m_iBitsDnfDiv = 0;			///< "bits_dnf_div": > 0 = ... only when the group's rarest keyword sits in at least 1/bits_dnf_div of the rows
+	int		m_bBitsDnf = 1;				///< "bits_dnf": AND groups of hot keywords (and ORs of them) intersect their bitmaps on orbits_kernel (0: and_kernel / class 6)
 	int		m_bOrClass = 1;				///< "or_class": launch class 5 exists (0: its queries take the general tile program)
 	int		m_bDnfClass = 1;			///< "dnf_class": launch class 6 exists
 	int		m_bAndKernel = 1;			///< "and_kernel": the intersection kernel exists

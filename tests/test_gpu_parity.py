@@ -207,8 +207,18 @@ def test_hot_dnf_class_edges(synth):
     batch = synth["gpu"].prepare(qs + qs[:80])
     st = batch.stats()
     batch.free()
-    assert st["class_queries"][6] >= 150, st["class_queries"]
+    assert st["class_queries"][6] + st["class_queries"][5] >= 150, st["class_queries"]     # hot groups: class 6, or the bitmap path of class 5
     assert _compare_batch(synth, qs + qs[:80]) == 0
+    # the same programs with only the groups of dense keywords on the bitmap path of orbits_kernel (normally every all-hot group goes there)
+    synth["gpu"].set_option("bits_dnf_div", 8)
+    try:
+        batch = synth["gpu"].prepare(qs + qs[:80])
+        st = batch.stats()
+        batch.free()
+        assert st["class_queries"][5] >= 100, st["class_queries"]
+        assert _compare_batch(synth, qs + qs[:80]) == 0
+    finally:
+        synth["gpu"].set_option("bits_dnf_div", 0)
 
 
 def test_cfg4_mix_with_andnot(synth):
