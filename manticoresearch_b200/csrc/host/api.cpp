@@ -168,15 +168,27 @@ int mgpu_batch_get_stats ( const mgpu_batch * b, mgpu_batch_stats * out )
 int mgpu_search_batch ( mgpu_index * idx, const mgpu_query * queries, int n_queries, mgpu_result * results )
 {
 	const auto tStart = std::chrono::steady_clock::now();
-	mgpu_batch * b = nullptr;
-	int iRes = mgpu_batch_prepare ( idx, queries, n_queries, &b );
-	if ( iRes!=MGPU_OK )
-		return iRes;
-	iRes = mgpu_batch_run ( b );
-	if ( iRes==MGPU_OK )
-		iRes = mgpu_batch_fetch ( b, results );
+	if ( !idx || n_queries<0 || ( n_queries && ( !queries || !results ) ) )
+		return MGPU_E_BAD_QUERY;
+	std::unique_ptr<mgpu_batch> pBatch ( new mgpu_batch );
+	mgpu_batch * b = pBatch.get();
+	int iRes;
+	{
+		// prepare + run under ONE lock: no other batch of this handle can get between them, so the hot-term store may be
+		// started from inside Prepare (it then overlaps with the rest of the host-side setup)
+		std::lock_guard<std::mutex> tGuard ( idx->m_t.m_tLock );
+		iRes = b->m_t.Prepare ( &idx->m_t, queries, n_queries, nullptr, 0, idx->m_t.m_tOpt.m_bEagerHot!=0 );
+		if ( iRes==MGPU_OK )
+			iRes = b->m_t.Run();
+		if ( iRes!=MGPU_OK )
+		{
+			idx->m_t.m_sError = b->m_t.m_sError;
+			return iRes;
+		}
+	}
+	iRes = mgpu_batch_fetch ( b, results );
 	mgpu_batch_stats tStats = b->m_t.m_tStats;
-	mgpu_batch_free ( b );
+	pBatch.reset();
 	tStats.host_total_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tStart ).count();
 	{
 		std::lock_guard<std::mutex> tGuard ( idx->m_t.m_tLock );

@@ -110,6 +110,11 @@ Index_c::~Index_c()
 		cudaSetDevice ( m_iDevice );
 		cudaStreamDestroy ( m_tOwnStream );
 	}
+	if ( m_tHotStream )
+	{
+		cudaSetDevice ( m_iDevice );
+		cudaStreamDestroy ( m_tHotStream );
+	}
 }
 
 int Index_c::AttrIndex ( const char * szName ) const
@@ -258,8 +263,10 @@ int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
 			}
 			t.m_iSkiplistBytes = (int64_t)( r.m_p-( tSpe.m_p+e.m_iSkiplistOffset ) );
 		}
+		t.m_iOrdinal = (int)m_hTerms.size();
 		m_hTerms.emplace ( e.m_sKeyword, t );
 	}
+	m_dTermUse.assign ( m_hTerms.size()+1, 0 );
 
 	// upload
 	int iRes;
@@ -294,6 +301,7 @@ int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
 	m_tDev.m_uRowidBase = uRowidBase;
 
 	CUDA_TRY ( cudaStreamCreateWithFlags ( &m_tOwnStream, cudaStreamNonBlocking ), m_sError );
+	CUDA_TRY ( cudaStreamCreateWithFlags ( &m_tHotStream, cudaStreamNonBlocking ), m_sError );
 	m_tStream = m_tOwnStream;
 	{
 		// per-batch buffers come from the device's stream-ordered pool: keep freed memory cached instead of returning it to the driver
@@ -1096,9 +1104,11 @@ bool EngineOptions_t::Set ( const char * szName, int64_t iValue )
 		{ "stats",			&EngineOptions_t::m_bStats,			0, 1 },
 		{ "hot_store",		&EngineOptions_t::m_bHotStore,		0, 1 },
 		{ "hot_div",		&EngineOptions_t::m_iHotDiv,		1, 1<<20 },
+		{ "hot_min_uses",	&EngineOptions_t::m_iHotMinUses,	1, 1<<20 },
 		{ "hot_gb",			&EngineOptions_t::m_iHotGB,			1, 160 },
 		{ "or_range_tiles",	&EngineOptions_t::m_iOrRangeTiles,	1, 1<<20 },
 		{ "dnf_pct",		&EngineOptions_t::m_iDnfPct,		1, 100 },
+		{ "eager_hot",		&EngineOptions_t::m_bEagerHot,		0, 1 },
 		{ "or_bits",		&EngineOptions_t::m_bOrBits,		0, 1 },
 		{ "bits_dnf",		&EngineOptions_t::m_bBitsDnf,		0, 1 },
 		{ "bits_dnf_div",	&EngineOptions_t::m_iBitsDnfDiv,	0, 1<<20 },
@@ -1137,6 +1147,10 @@ Batch_c::~Batch_c()
 			m_dPlans.swap ( m_pIndex->m_dPlanCache );
 		}
 	}
+	// (a batch that never ran: its early K0 may still be reading the descriptors freed below, in this stream's order)
+	if ( m_bHotPending && m_tEvHotDone )
+		cudaStreamWaitEvent ( m_tStream, m_tEvHotDone, 0 );
+	if ( m_tEvHotDone ) cudaEventDestroy ( m_tEvHotDone );
 	if ( m_tEv0 ) cudaEventDestroy ( m_tEv0 );
 	if ( m_tEv1 ) cudaEventDestroy ( m_tEv1 );
 	if ( m_tEv2 ) cudaEventDestroy ( m_tEv2 );
@@ -1153,7 +1167,7 @@ static int Pow2Ceil ( int n )
 	return p;
 }
 
-int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads )
+int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads, bool bEagerHot )
 {
 	m_pIndex = pIndex;
 	const EngineOptions_t tOpt = pIndex->m_tOpt;	// one consistent copy per batch
@@ -1228,6 +1242,17 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	if ( dDocOnly.empty() && dOrder[1].empty() && dOrder[4].empty() )
 		return MGPU_OK;
 
+	// the stream of this batch: captured here and used for its allocations, kernels, copies and frees (mgpu_index_set_stream
+	// between prepare and run / free must not split them over two streams)
+	m_tStream = pIndex->m_tStream;
+	CUDA_TRY ( cudaEventCreate ( &m_tEv0 ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEv1 ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEv2 ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEvHot ), m_sError );
+	CUDA_TRY ( cudaEventCreate ( &m_tEvHotDone ), m_sError );
+	for ( int c=0; c<NUM_CLASSES; ++c )
+		CUDA_TRY ( cudaEventCreate ( &m_dEvClass[c] ), m_sError );
+
 	m_dSlots.reserve ( nQueries );
 	m_dDevToQuery.reserve ( nQueries );
 	m_dItems.reserve ( (size_t)nQueries*4 );
@@ -1241,28 +1266,34 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	const int64_t iHotGB = std::max ( 1, tOpt.m_iHotGB );
 	if ( pIndex->m_tHdr.m_dFields.size()<=8 && tOpt.m_bHotStore )
 	{
-		std::unordered_map<const TermInfo_t*,int> hUse;
+		// (use counts and, below, store slots live in a flat per-keyword array of the index: 35k leaves of a 10k-query batch cost
+		// 3 ms through hash maps, on the critical path in front of K0)
+		std::vector<int32_t> & dUse = pIndex->m_dTermUse;
+		std::vector<const TermInfo_t*> dTouched;
 		for ( int i : dDocOnly )
 			for ( const TermInfo_t * p : m_dPlans[i].m_dLeafTerms )
-				if ( p && (int64_t)p->m_iDocs*iHotDiv>=(int64_t)uRows )
-					++hUse[p];
+				if ( p && (int64_t)p->m_iDocs*iHotDiv>=(int64_t)uRows && !dUse[p->m_iOrdinal]++ )
+					dTouched.push_back ( p );
 		std::vector<std::pair<int64_t,const TermInfo_t*>> dHot;
 		// ... or a keyword in >= 1/16 of the rows that only one query uses (small batches): one pass over its doclist into the
 		// store and its bitmaps beats walking it posting by posting
-		for ( const auto & kv : hUse )
-			if ( kv.second>=2 || (int64_t)kv.first->m_iDocs*16>=(int64_t)uRows )
-				dHot.push_back ( { (int64_t)kv.second*kv.first->m_iDocs, kv.first } );
+		for ( const TermInfo_t * p : dTouched )
+		{
+			const int nUse = dUse[p->m_iOrdinal];
+			dUse[p->m_iOrdinal] = 0;
+			if ( nUse>=tOpt.m_iHotMinUses || (int64_t)p->m_iDocs*16>=(int64_t)uRows )
+				dHot.push_back ( { (int64_t)nUse*p->m_iDocs, p } );
+		}
 		std::sort ( dHot.begin(), dHot.end(), [] ( const auto & a, const auto & b ) { return a.first>b.first || ( a.first==b.first && a.second->m_uFirstBlk<b.second->m_uFirstBlk ); } );
 		m_iHotStride = (int64_t)nTiles*TILE_W;
 		const size_t nMaxHot = std::min<size_t> ( 4096, ( (size_t)iHotGB<<30 )/( 2*(size_t)m_iHotStride ) );	// <= iHotGB of store
 		if ( dHot.size()>nMaxHot )
 			dHot.resize ( nMaxHot );
-		std::unordered_map<const TermInfo_t*,int> hSlot;
 		int64_t iEscapeCap = 16;
 		for ( const auto & t : dHot )
 		{
 			const TermInfo_t * p = t.second;
-			hSlot[p] = (int)m_dHotTerms.size();
+			dUse[p->m_iOrdinal] = (int)m_dHotTerms.size()+1;	// slot + 1
 			DevLeaf_t tLeaf {};
 			tLeaf.m_uFirstBlk = p->m_uFirstBlk;
 			tLeaf.m_nBlocks = p->m_nBlocks;
@@ -1291,10 +1322,10 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				PlannedQuery_t & p = m_dPlans[i];
 				for ( size_t l=0; l<p.m_dLeafTerms.size(); ++l )
 				{
-					auto it = hSlot.find ( p.m_dLeafTerms[l] );
-					if ( it!=hSlot.end() )
+					const int iSlot = p.m_dLeafTerms[l] ? dUse[p.m_dLeafTerms[l]->m_iOrdinal]-1 : -1;
+					if ( iSlot>=0 )
 					{
-						p.m_tDev.m_dLeaves[l].m_iHot = it->second;
+						p.m_tDev.m_dLeaves[l].m_iHot = iSlot;
 						if ( ( p.m_tDev.m_uOrigMask>>l ) & 1u )
 							p.m_tDev.m_bOrigHot = 1;
 						if ( p.m_tDev.m_iDriverLeaf==(int)l )
@@ -1302,6 +1333,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 					}
 				}
 			}
+		for ( const auto & t : dHot )
+			dUse[t.second->m_iOrdinal] = 0;
 	}
 
 	// launch class 5 runs on the presence bitmaps when the store has them (every index class 5 admits has <= 4 fields)
@@ -1375,7 +1408,8 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	// class 5 on orbits_kernel: every keyword outside the hot store is decoded once per run into a plain posting list
 	if ( m_iOrMode==3 && !dOrder[5].empty() )
 	{
-		std::unordered_map<const TermInfo_t*,uint32_t> hOff;
+		std::vector<int32_t> & dUse = pIndex->m_dTermUse;	// index into m_dListTerms + 1
+		std::vector<const TermInfo_t*> dTouched;
 		uint64_t uEntries = 0;
 		for ( int i : dOrder[5] )
 		{
@@ -1385,18 +1419,21 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				const TermInfo_t * pTerm = p.m_dLeafTerms[l];
 				if ( p.m_tDev.m_dLeaves[l].m_iHot>=0 || !pTerm )
 					continue;
-				auto it = hOff.find ( pTerm );
-				if ( it==hOff.end() )
+				int32_t & iList = dUse[pTerm->m_iOrdinal];
+				if ( !iList )
 				{
-					it = hOff.emplace ( pTerm, (uint32_t)std::min<uint64_t> ( uEntries, 0xFFFFFFFFu ) ).first;
 					DevLeaf_t tLeaf = p.m_tDev.m_dLeaves[l];
-					tLeaf.m_uListOff = it->second;
+					tLeaf.m_uListOff = (uint32_t)std::min<uint64_t> ( uEntries, 0xFFFFFFFFu );
 					m_dListTerms.push_back ( tLeaf );
+					iList = (int32_t)m_dListTerms.size();
+					dTouched.push_back ( pTerm );
 					uEntries += ( (uint64_t)pTerm->m_nBlocks*32 + 31 ) & ~31ull;
 				}
-				p.m_tDev.m_dLeaves[l].m_uListOff = it->second;
+				p.m_tDev.m_dLeaves[l].m_uListOff = m_dListTerms[iList-1].m_uListOff;
 			}
 		}
+		for ( const TermInfo_t * pTerm : dTouched )
+			dUse[pTerm->m_iOrdinal] = 0;
 		if ( uEntries>=( 1ull<<30 ) || uRows>=( 1u<<31 ) )
 		{
 			// (the lists would not fit / the candidate queue's flag bit is taken: the class stays on stream_kernel<512,1>)
@@ -1410,6 +1447,37 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				m_dListBlkStart.push_back ( m_dListBlkStart.back()+t.m_nBlocks );
 		}
 	}
+
+	// the store's descriptors go up now ...
+	if ( !m_dHotTerms.empty() )
+	{
+		CUDA_TRY ( m_dHotDesc.AllocAsync ( m_dHotTerms.size(), m_tStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, m_tStream ), m_sError );
+		CUDA_TRY ( m_dHotLvlSlotDev.AllocAsync ( m_dHotLvlSlot.size(), m_tStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dHotLvlSlotDev.m_p, m_dHotLvlSlot.data(), m_dHotLvlSlot.size()*4, cudaMemcpyHostToDevice, m_tStream ), m_sError );
+		CUDA_TRY ( m_dHotBlkStartDev.AllocAsync ( m_dHotBlkStart.size(), m_tStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dHotBlkStartDev.m_p, m_dHotBlkStart.data(), m_dHotBlkStart.size()*4, cudaMemcpyHostToDevice, m_tStream ), m_sError );
+	}
+	if ( !m_dListTerms.empty() )
+	{
+		CUDA_TRY ( m_dListDesc.AllocAsync ( m_dListTerms.size(), m_tStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dListDesc.m_p, m_dListTerms.data(), m_dListTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, m_tStream ), m_sError );
+		CUDA_TRY ( m_dListBlkStartDev.AllocAsync ( m_dListBlkStart.size(), m_tStream ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dListBlkStartDev.m_p, m_dListBlkStart.data(), m_dListBlkStart.size()*4, cudaMemcpyHostToDevice, m_tStream ), m_sError );
+	}
+	// ... and with bEagerHot (the one-call paths: prepare + run under one lock) K0 starts right here on the index's second stream,
+	// behind everything queued on the batch's stream so far (earlier runs own the store until they end); the rest of this
+	// function (work items, the 34 MB of device queries, their upload) then overlaps with the decode instead of preceding it
+	if ( bEagerHot && ( !m_dHotTerms.empty() || !m_dListTerms.empty() ) )
+	{
+		CUDA_TRY ( cudaEventRecord ( m_tEvHotDone, m_tStream ), m_sError );
+		CUDA_TRY ( cudaStreamWaitEvent ( pIndex->m_tHotStream, m_tEvHotDone, 0 ), m_sError );
+		int iRes = BuildHotStore ( pIndex->m_tHotStream );
+		if ( iRes!=MGPU_OK )
+			return iRes;
+		m_bHotPending = true;
+	}
+	fnMark ( "store descriptors" );
 
 	// estimated work of a query in its class (decides how many items it is cut into)
 	auto fnWork = [&] ( const PlannedQuery_t & p, int c ) -> int64_t
@@ -1548,9 +1616,6 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	const int nDevQ = (int)m_dSlots.size();
 	m_nDevQueries = nDevQ;
 	const int nItems = (int)m_dItems.size();
-	// the stream of this batch: captured here and used for its allocations, kernels, copies and frees (mgpu_index_set_stream
-	// between prepare and run / free must not split them over two streams)
-	m_tStream = pIndex->m_tStream;
 	cudaStream_t tAllocStream = m_tStream;
 	m_iPoolCap = m_iKMax + 32768;	// >= K + what one round of any kernel can push (stream: 8 mini-tiles x 8 warps x 512 rows)
 	m_iScratchStride = 2*Pow2Ceil ( iMaxKeysPerQuery );
@@ -1569,22 +1634,6 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	m_nHitpos = std::max ( (size_t)m_dCtas[1]*MAX_LEAVES*TILE_W, (size_t)m_dCtas[4]*EVAL_WARPS*MAX_LEAVES*32 );
 	m_nPre = (size_t)std::max ( { m_dCtas[0], m_dCtas[1], m_dCtas[3], m_dCtas[5], m_dCtas[6] } )*PRE_BLOCKS*32;
 	m_nPreHitpos = (size_t)m_dCtas[1]*PRE_BLOCKS*32;
-	if ( !m_dHotTerms.empty() )
-	{
-		CUDA_TRY ( m_dHotDesc.AllocAsync ( m_dHotTerms.size(), tAllocStream ), m_sError );
-		CUDA_TRY ( cudaMemcpyAsync ( m_dHotDesc.m_p, m_dHotTerms.data(), m_dHotTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, tAllocStream ), m_sError );
-		CUDA_TRY ( m_dHotLvlSlotDev.AllocAsync ( m_dHotLvlSlot.size(), tAllocStream ), m_sError );
-		CUDA_TRY ( cudaMemcpyAsync ( m_dHotLvlSlotDev.m_p, m_dHotLvlSlot.data(), m_dHotLvlSlot.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
-		CUDA_TRY ( m_dHotBlkStartDev.AllocAsync ( m_dHotBlkStart.size(), tAllocStream ), m_sError );
-		CUDA_TRY ( cudaMemcpyAsync ( m_dHotBlkStartDev.m_p, m_dHotBlkStart.data(), m_dHotBlkStart.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
-	}
-	if ( !m_dListTerms.empty() )
-	{
-		CUDA_TRY ( m_dListDesc.AllocAsync ( m_dListTerms.size(), tAllocStream ), m_sError );
-		CUDA_TRY ( cudaMemcpyAsync ( m_dListDesc.m_p, m_dListTerms.data(), m_dListTerms.size()*sizeof(DevLeaf_t), cudaMemcpyHostToDevice, tAllocStream ), m_sError );
-		CUDA_TRY ( m_dListBlkStartDev.AllocAsync ( m_dListBlkStart.size(), tAllocStream ), m_sError );
-		CUDA_TRY ( cudaMemcpyAsync ( m_dListBlkStartDev.m_p, m_dListBlkStart.data(), m_dListBlkStart.size()*4, cudaMemcpyHostToDevice, tAllocStream ), m_sError );
-	}
 	CUDA_TRY ( m_dItemKeys.AllocAsync ( (size_t)nItems*m_iKMax, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dItemOut.AllocAsync ( nItems, tAllocStream ), m_sError );
 	CUDA_TRY ( m_dScratch.AllocAsync ( (size_t)nDevQ*m_iScratchStride, tAllocStream ), m_sError );
@@ -1639,12 +1688,6 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	m_tStats.h2d_bytes = (int64_t)nDevQ*sizeof(DevQuery_t) + (int64_t)nItems*sizeof(DevWorkItem_t);
 	m_tStats.work_items = nItems;
 
-	CUDA_TRY ( cudaEventCreate ( &m_tEv0 ), m_sError );
-	CUDA_TRY ( cudaEventCreate ( &m_tEv1 ), m_sError );
-	CUDA_TRY ( cudaEventCreate ( &m_tEv2 ), m_sError );
-	CUDA_TRY ( cudaEventCreate ( &m_tEvHot ), m_sError );
-	for ( int c=0; c<NUM_CLASSES; ++c )
-		CUDA_TRY ( cudaEventCreate ( &m_dEvClass[c] ), m_sError );
 	for ( int c=0; c<NUM_CLASSES; ++c )
 	{
 		m_tStats.class_queries[c] = (int32_t)dOrder[c].size();
@@ -1654,6 +1697,88 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	}
 	fnMark ( "events + stats" );
 	m_tStats.host_setup_ms = std::chrono::duration<float,std::milli> ( std::chrono::steady_clock::now()-tPlanned ).count();
+	return MGPU_OK;
+}
+
+/// K0 (+ K0b): decodes the batch's hot keywords once into the dense store and the non-hot keywords of launch class 5 into plain
+/// posting lists, on tStream. The store lives in the index's run scratch: contents never survive a run.
+int Batch_c::BuildHotStore ( cudaStream_t s )
+{
+	Index_c * pIndex = m_pIndex;
+	Index_c::RunScratch_t & tScr = pIndex->m_tScratch;
+	m_tHot = DevHotStore_t {};
+	m_tLists = DevPostingLists_t {};
+	m_nHotLaunches = 0;
+	if ( !m_dHotTerms.empty() )
+	{
+		CUDA_TRY ( tScr.m_dHotData.Grow ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
+		CUDA_TRY ( tScr.m_dHotEscape.Grow ( (size_t)m_iHotEscapeCap*3 ), m_sError );
+		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1 ), m_sError );
+		if ( m_nHotBitFields )
+			CUDA_TRY ( tScr.m_dHotBits.Grow ( m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 ) ), m_sError );
+		if ( m_nListEntries )
+		{
+			CUDA_TRY ( tScr.m_dListRows.Grow ( m_nListEntries+64 ), m_sError );
+			CUDA_TRY ( tScr.m_dListVals.Grow ( m_nListEntries+64 ), m_sError );
+		}
+		if ( m_nHotLvl )
+			CUDA_TRY ( tScr.m_dHotLvlBits.Grow ( (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 ) ), m_sError );
+	}
+	CUDA_TRY ( cudaEventRecord ( m_tEvHot, s ), m_sError );
+	DevHotStore_t & tHot = m_tHot;
+	if ( !m_dHotTerms.empty() )
+	{
+		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotData.m_p, 0, m_dHotTerms.size()*(size_t)m_iHotStride*2, s ), m_sError );
+		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
+		HotDecodeParams_t H {};
+		H.m_tIndex = pIndex->m_tDev;
+		H.m_pTerms = m_dHotDesc.m_p;
+		H.m_nHot = (int)m_dHotTerms.size();
+		H.m_iEscapeCap = m_iHotEscapeCap;
+		H.m_pData = tScr.m_dHotData.m_p;
+		H.m_pEscape = tScr.m_dHotEscape.m_p;
+		H.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
+		H.m_iStride = m_iHotStride;
+		H.m_bTfClass = pIndex->m_tHdr.m_dFields.size()<=4 ? 1 : 0;
+		H.m_pBlkStart = m_dHotBlkStartDev.m_p;
+		H.m_nBitFields = m_nHotBitFields;
+		H.m_pBits = m_nHotBitFields ? tScr.m_dHotBits.m_p : nullptr;
+		H.m_pLvlSlot = m_nHotLvl ? m_dHotLvlSlotDev.m_p : nullptr;
+		H.m_pLvlBits = m_nHotLvl ? tScr.m_dHotLvlBits.m_p : nullptr;
+		if ( m_nHotLvl )
+			CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotLvlBits.m_p, 0, (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 )*4, s ), m_sError );
+		if ( m_nHotBitFields )
+			CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotBits.m_p, 0, m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 )*4, s ), m_sError );
+		CUDA_TRY ( LaunchHotDecode ( H, pIndex->m_nSMs*8, s ), m_sError );
+		++m_nHotLaunches;
+		tHot.m_pData = tScr.m_dHotData.m_p;
+		tHot.m_pEscape = tScr.m_dHotEscape.m_p;
+		tHot.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
+		tHot.m_iStride = m_iHotStride;
+		tHot.m_nHot = (int)m_dHotTerms.size();
+		tHot.m_bTfClass = H.m_bTfClass;
+		tHot.m_pBits = H.m_pBits;
+		tHot.m_iBitStride = m_iHotStride/32;
+		tHot.m_nBitFields = m_nHotBitFields;
+		tHot.m_pLvlSlot = H.m_pLvlSlot;
+		tHot.m_pLvlBits = H.m_pLvlBits;
+	}
+	if ( !m_dListTerms.empty() )
+	{
+		// K0b: posting lists of class 5's keywords outside the hot store
+		SparseDecodeParams_t L {};
+		L.m_tIndex = pIndex->m_tDev;
+		L.m_pTerms = m_dListDesc.m_p;
+		L.m_pBlkStart = m_dListBlkStartDev.m_p;
+		L.m_nTerms = (int)m_dListTerms.size();
+		L.m_pRows = tScr.m_dListRows.m_p;
+		L.m_pVals = tScr.m_dListVals.m_p;
+		CUDA_TRY ( LaunchSparseDecode ( L, pIndex->m_nSMs*8, s ), m_sError );
+		++m_nHotLaunches;
+		m_tLists.m_pRows = L.m_pRows;
+		m_tLists.m_pVals = L.m_pVals;
+	}
+	CUDA_TRY ( cudaEventRecord ( m_tEvHotDone, s ), m_sError );
 	return MGPU_OK;
 }
 
@@ -1680,79 +1805,22 @@ int Batch_c::Run()
 	if ( m_dCtas[5] || m_dCtas[6] )
 		CUDA_TRY ( tScr.m_dOrList.Grow ( std::max ( (size_t)m_dCtas[5]*StreamOrListCap ( m_iOrMode ), (size_t)m_dCtas[6]*StreamOrListCap ( 2 ) )*EVAL_WARPS ), m_sError );
 	CUDA_TRY ( tScr.m_dPreHitpos.Grow ( m_nPreHitpos ), m_sError );
-	if ( !m_dHotTerms.empty() )
-	{
-		CUDA_TRY ( tScr.m_dHotData.Grow ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
-		CUDA_TRY ( tScr.m_dHotEscape.Grow ( (size_t)m_iHotEscapeCap*3 ), m_sError );
-		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1 ), m_sError );
-		if ( m_nHotBitFields )
-			CUDA_TRY ( tScr.m_dHotBits.Grow ( m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 ) ), m_sError );
-		if ( m_nListEntries )
-		{
-			CUDA_TRY ( tScr.m_dListRows.Grow ( m_nListEntries+64 ), m_sError );
-			CUDA_TRY ( tScr.m_dListVals.Grow ( m_nListEntries+64 ), m_sError );
-		}
-		if ( m_nHotLvl )
-			CUDA_TRY ( tScr.m_dHotLvlBits.Grow ( (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 ) ), m_sError );
-	}
 
-	// K0: decode the batch's hot keywords once into the dense store
-	DevHotStore_t tHot {};
-	int nLaunches = 1;
-	CUDA_TRY ( cudaEventRecord ( m_tEvHot, s ), m_sError );
-	if ( !m_dHotTerms.empty() )
+	// K0 / K0b: the batch's hot-term store and posting lists. Prepare ( bEagerHot ) has already started them on the index's second
+	// stream (first run only): this stream then just waits for them
+	if ( m_bHotPending )
 	{
-		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotData.m_p, 0, m_dHotTerms.size()*(size_t)m_iHotStride*2, s ), m_sError );
-		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
-		HotDecodeParams_t H {};
-		H.m_tIndex = pIndex->m_tDev;
-		H.m_pTerms = m_dHotDesc.m_p;
-		H.m_nHot = (int)m_dHotTerms.size();
-		H.m_iEscapeCap = m_iHotEscapeCap;
-		H.m_pData = tScr.m_dHotData.m_p;
-		H.m_pEscape = tScr.m_dHotEscape.m_p;
-		H.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
-		H.m_iStride = m_iHotStride;
-		H.m_bTfClass = pIndex->m_tHdr.m_dFields.size()<=4 ? 1 : 0;
-		H.m_pBlkStart = m_dHotBlkStartDev.m_p;
-		H.m_nBitFields = m_nHotBitFields;
-		H.m_pBits = m_nHotBitFields ? tScr.m_dHotBits.m_p : nullptr;
-		H.m_pLvlSlot = m_nHotLvl ? m_dHotLvlSlotDev.m_p : nullptr;
-		H.m_pLvlBits = m_nHotLvl ? tScr.m_dHotLvlBits.m_p : nullptr;
-		if ( m_nHotLvl )
-			CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotLvlBits.m_p, 0, (size_t)m_nHotLvl*2*(size_t)( m_iHotStride/32 )*4, s ), m_sError );
-		if ( m_nHotBitFields )
-			CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotBits.m_p, 0, m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 )*4, s ), m_sError );
-		CUDA_TRY ( LaunchHotDecode ( H, pIndex->m_nSMs*8, s ), m_sError );
-		++nLaunches;
-		tHot.m_pData = tScr.m_dHotData.m_p;
-		tHot.m_pEscape = tScr.m_dHotEscape.m_p;
-		tHot.m_pEscapeCount = tScr.m_dHotEscapeCount.m_p;
-		tHot.m_iStride = m_iHotStride;
-		tHot.m_nHot = (int)m_dHotTerms.size();
-		tHot.m_bTfClass = H.m_bTfClass;
-		tHot.m_pBits = H.m_pBits;
-		tHot.m_iBitStride = m_iHotStride/32;
-		tHot.m_nBitFields = m_nHotBitFields;
-		tHot.m_pLvlSlot = H.m_pLvlSlot;
-		tHot.m_pLvlBits = H.m_pLvlBits;
-	}
-	DevPostingLists_t tLists {};
-	if ( !m_dListTerms.empty() )
+		CUDA_TRY ( cudaStreamWaitEvent ( s, m_tEvHotDone, 0 ), m_sError );
+		m_bHotPending = false;
+	} else
 	{
-		// K0b: posting lists of class 5's keywords outside the hot store
-		SparseDecodeParams_t L {};
-		L.m_tIndex = pIndex->m_tDev;
-		L.m_pTerms = m_dListDesc.m_p;
-		L.m_pBlkStart = m_dListBlkStartDev.m_p;
-		L.m_nTerms = (int)m_dListTerms.size();
-		L.m_pRows = tScr.m_dListRows.m_p;
-		L.m_pVals = tScr.m_dListVals.m_p;
-		CUDA_TRY ( LaunchSparseDecode ( L, pIndex->m_nSMs*8, s ), m_sError );
-		++nLaunches;
-		tLists.m_pRows = L.m_pRows;
-		tLists.m_pVals = L.m_pVals;
+		int iRes = BuildHotStore ( s );
+		if ( iRes!=MGPU_OK )
+			return iRes;
 	}
+	const DevHotStore_t & tHot = m_tHot;
+	const DevPostingLists_t & tLists = m_tLists;
+	int nLaunches = 1 + m_nHotLaunches;
 	CUDA_TRY ( cudaEventRecord ( m_tEv0, s ), m_sError );
 	for ( int c=0; c<NUM_CLASSES; ++c )
 	{
@@ -1824,7 +1892,7 @@ int Batch_c::Sync()
 	if ( m_bRan && m_nDevQueries )
 	{
 		cudaEventElapsedTime ( &m_tStats.eval_kernel_ms, m_tEv0, m_tEv1 );
-		cudaEventElapsedTime ( &m_tStats.hot_decode_ms, m_tEvHot, m_tEv0 );
+		cudaEventElapsedTime ( &m_tStats.hot_decode_ms, m_tEvHot, m_tEvHotDone );
 		m_tStats.hot_terms = (int32_t)m_dHotTerms.size();
 		cudaEvent_t tPrev = m_tEv0;
 		for ( int c=0; c<NUM_CLASSES; ++c )
@@ -1906,7 +1974,9 @@ int Batch_c::Fetch ( mgpu_result * pResults )
 	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
 	m_tStats.d2h_bytes = (int64_t)nQueries*12 + (int64_t)nSlots*24;
 
-	for ( int iQuery=0; iQuery<nQueries; ++iQuery )
+	auto fnUnpack = [&] ( int iFrom, int iTo )
+	{
+	for ( int iQuery=iFrom; iQuery<iTo; ++iQuery )
 	{
 		const PlannedQuery_t & p = m_dPlans[iQuery];
 		mgpu_result & r = pResults[iQuery];
@@ -1941,6 +2011,19 @@ int Batch_c::Fetch ( mgpu_result * pResults )
 				r.sort_attr[i] = v;
 			}
 		}
+	}
+	};
+	// 24 B per result slot into the caller's arrays: a few threads for big batches (3.5 ms single-threaded for 10k x 100)
+	const int nThreads = (int)std::max<int64_t> ( 1, std::min<int64_t> ( { (int64_t)std::thread::hardware_concurrency(), 8, (int64_t)( nSlots/65536 ) } ) );
+	if ( nThreads<=1 )
+		fnUnpack ( 0, nQueries );
+	else
+	{
+		std::vector<std::thread> dThreads;
+		for ( int t=0; t<nThreads; ++t )
+			dThreads.emplace_back ( fnUnpack, (int)( (int64_t)nQueries*t/nThreads ), (int)( (int64_t)nQueries*( t+1 )/nThreads ) );
+		for ( auto & t : dThreads )
+			t.join();
 	}
 	return MGPU_OK;
 }

@@ -26,6 +26,7 @@ struct TermInfo_t
 	int64_t		m_iDoclistOffset = 0;
 	int64_t		m_iDoclistLength = 0;	///< .spd extent incl. the terminating zero
 	int64_t		m_iSkiplistBytes = 0;	///< .spe extent
+	int			m_iOrdinal = 0;			///< position in the dictionary (flat per-keyword side arrays)
 };
 
 template<typename T>
@@ -85,9 +86,11 @@ struct EngineOptions_t
 	int		m_bTiming = 0;				///< "timing": print the host setup phases of every batch to stderr
 	int		m_bHotStore = 1;			///< "hot_store": decode keywords shared by >= 2 queries once per batch into the dense store
 	int		m_iHotDiv = 200;			///< "hot_div": a hot keyword sits in >= 1/hot_div of the rows
+	int		m_iHotMinUses = 2;		///< "hot_min_uses": ... and used by at least this many queries of the batch
 	int		m_iHotGB = 24;				///< "hot_gb": cap of the dense store
 	int		m_iOrRangeTiles = 1024;		///< "or_range_tiles": rows/2048 per work item of the bound + exact pass classes
 	int		m_iDnfPct = 12;				///< "dnf_pct": a group driver of the intersection kernel sits in < dnf_pct % of the rows
+	int		m_bEagerHot = 1;			///< "eager_hot": one-call batches start K0 inside Prepare, on the index's second stream (0: at the head of Run)
 	int		m_bOrBits = 1;				///< "or_bits": pure OR programs run on orbits_kernel (0: stream_kernel<512,1>)
 	int		m_iBitsDnfDiv = 0;			///< "bits_dnf_div": > 0 = ... only when the group's rarest keyword sits in at least 1/bits_dnf_div of the rows
 	int		m_bBitsDnf = 1;				///< "bits_dnf": AND groups of hot keywords (and ORs of them) intersect their bitmaps on orbits_kernel (0: and_kernel / class 6)
@@ -111,6 +114,7 @@ public:
 	uint32_t		m_uRowidBase = 0;
 	cudaStream_t	m_tStream = nullptr;		///< stream in use (own or caller's)
 	cudaStream_t	m_tOwnStream = nullptr;
+	cudaStream_t	m_tHotStream = nullptr;		///< second stream: a one-call batch builds its hot-term store here while the host still prepares the rest
 	int				m_nSMs = 148;
 	std::mutex		m_tLock;		///< serialises batches on this handle
 	std::mutex		m_tCacheLock;
@@ -118,6 +122,7 @@ public:
 	mgpu_batch_stats m_tLastSearchStats {};
 
 	std::unordered_map<std::string,TermInfo_t> m_hTerms;
+	std::vector<int32_t>	m_dTermUse;		///< per keyword (by ordinal): scratch counters of Batch_c::Prepare, all zero between batches (under m_tLock)
 
 	/// Scratch that only lives during a batch run (candidate pools, predecode lists, hit positions, the dense hot-term
 	/// store): owned by the index and re-used by every batch, so a batch costs no big cudaMalloc. Contents never survive a run.
@@ -237,7 +242,11 @@ public:
 	int						m_iOrMode = 1;			///< kernel of launch class 5: 3 = orbits_kernel, 1 = stream_kernel<512,1>
 	int64_t					m_iHotStride = 0;
 	int						m_iHotEscapeCap = 0;
-	cudaEvent_t				m_tEvHot = nullptr;
+	cudaEvent_t				m_tEvHot = nullptr, m_tEvHotDone = nullptr;
+	DevHotStore_t			m_tHot {};				///< what BuildHotStore() made (pointers into the index's run scratch)
+	DevPostingLists_t		m_tLists {};
+	int						m_nHotLaunches = 0;
+	bool					m_bHotPending = false;	///< Prepare ( bEagerHot ) has started K0 on the index's second stream: the first Run() waits for it instead of building
 	cudaEvent_t				m_dEvClass[NUM_CLASSES] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	bool					m_dClassRan[NUM_CLASSES] = { false, false, false, false, false, false, false };
 
@@ -246,7 +255,9 @@ public:
 	bool			m_bRan = false;
 
 	/// pTemplate: plans made once on another shard of the same index (re-bound here instead of planning again); nMaxThreads caps the host threads
-	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate=nullptr, int nMaxThreads=0 );
+	/// bEagerHot: the caller runs the batch right away under the same lock (mgpu_search_batch, the sharded call): K0 starts inside Prepare
+	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate=nullptr, int nMaxThreads=0, bool bEagerHot=false );
+	int		BuildHotStore ( cudaStream_t tStream );
 	int		Run();
 	int		Sync();
 	int		Fetch ( mgpu_result * pResults );

@@ -271,7 +271,7 @@ public:
 			Index_c * pIndex = m_dShards[s].get();
 			dBatches[s].reset ( new Batch_c );
 			Batch_c & b = *dBatches[s];
-			int iRes = b.Prepare ( pIndex, dQueries.data(), nQueries, &dTemplate, nBindThreads );
+			int iRes = b.Prepare ( pIndex, dQueries.data(), nQueries, &dTemplate, nBindThreads, pIndex->m_tOpt.m_bEagerHot!=0 );
 			if ( iRes==MGPU_OK )
 				iRes = b.Run();
 			if ( iRes==MGPU_OK )
