@@ -107,30 +107,44 @@ struct RankHit_t
 	uint32_t	m_uWeight;
 };
 
-/// acceptor + generator state of one phrase/proximity node
+/// acceptor + generator state of one hit-level node (the kinds' private parts share their bytes: per-thread local memory)
 struct NWayState_t
 {
-	// FSMphrase_c: m_dStates; FSMproximity_c: m_dProx
+	// FSMphrase_c: m_dStates; FSMproximity_c: m_dProx; ExtOrder_c (BEFORE): m_dVal[0..15] = the longest prefix found so far,
+	// m_dVal[16..31] = the most recent attempt (raw hits)
 	uint32_t	m_dVal[NWAY_MAX_SPAN+2];	///< phrase: expected hitpos-with-field per state; proximity: last position per query word
-	uint8_t		m_dTag[NWAY_MAX_SPAN+2];	///< phrase: m_iTagQword per state
-	int			m_nStates;
-	uint32_t	m_uExpPos, m_uWords;		///< proximity
-	int			m_iMinQindex;
 	RankHit_t	m_tHead;					///< next folded hit (m_uHitpos==0: exhausted)
 	uint32_t	m_uFirstRawHit;				///< raw hit that completed the first match (doc field mask, src/searchnode.cpp:3827-3833)
 	bool		m_bAny;
-	// FSMmultinear_c, two children (NEAR)
-	uint32_t	m_uLastP, m_uFirstHit, m_uChainWeight;
-	uint32_t	m_uFirstQpos, m_uFirstNpos;
-	// ExtOrder_c (BEFORE): m_dVal[0..15] = the longest prefix found so far, m_dVal[16..31] = the most recent attempt (raw hits)
-	int			m_nLongest, m_nRecent, m_iPosLongest, m_iPosRecent, m_iField;
-	uint32_t	m_dEmit[MAX_PHRASE_WORDS];	///< a complete sequence, handed out hit by hit
-	int			m_nEmit, m_iEmitNext;
+	union
+	{
+		struct
+		{
+			uint8_t		m_dTag[NWAY_MAX_SPAN+2];	///< phrase: m_iTagQword per state
+			int			m_nStates;
+			uint32_t	m_uExpPos, m_uWords;		///< proximity
+			int			m_iMinQindex;
+		};
+		struct
+		{
+			// FSMmultinear_c, two children (NEAR)
+			uint32_t	m_uLastP, m_uFirstHit, m_uChainWeight;
+			uint32_t	m_uFirstQpos, m_uFirstNpos;
+		};
+		struct
+		{
+			// ExtOrder_c (BEFORE)
+			int			m_nLongest, m_nRecent, m_iPosLongest, m_iPosRecent, m_iField;
+			uint32_t	m_dEmit[MAX_PHRASE_WORDS];	///< a complete sequence, handed out hit by hit
+			int			m_nEmit, m_iEmitNext;
+		};
+	};
 };
 
 __device__ __forceinline__ void ResetFSM ( const DevNWay_t & n, NWayState_t & s )
 {
-	s.m_nStates = 0;
+	if ( n.m_eKind<=NWAY_PROXIMITY )
+		s.m_nStates = 0;
 	if ( n.m_eKind==NWAY_NEAR )
 	{
 		// FSMmultinear_c::ResetFSM (m_uFirstQpos / m_uFirstNpos are always set by the chain's first hit before they are read)
@@ -398,7 +412,8 @@ static const uint64_t HITPOS_ABSENT = ~0ull;	///< hit scratch: the keyword does 
 /// BEFORE (ExtOrder_c::GetMatchingHits :4706-4829): by position, the lowest child wins a tie; a complete sequence is handed out
 /// hit by hit. NOTNEAR (ExtNotNear_c::FilterHits :5352-5380): the MUST keyword's hits that no NOT hit follows within N positions.
 /// Quorum (ExtQuorum_c::CollectHits :4543-4565): every hit of the keywords on the document, by (position, qpos).
-__device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
+template<int KIND>
+__device__ __noinline__ void NWayAdvanceT ( const DevQuery_t & q, int j, DocHits_t & H )
 {
 	const DevNWay_t & n = q.m_dNWay[j];
 	NWayState_t & s = H.m_dNWay[j];
@@ -414,7 +429,7 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 	{
 		H.m_dHead[l] = NextHit ( H.m_dCur[l], q.m_dLeaves[l].m_uQueriedFields, q.m_dLeaves[l].m_iTermPos );
 	};
-	if ( n.m_eKind==NWAY_NOTNEAR )
+	if constexpr ( KIND==NWAY_NOTNEAR )
 	{
 		const int lMust = n.m_dLeaf[0], lNot = n.m_dLeaf[1];
 		while ( true )
@@ -439,9 +454,10 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 			}
 		}
 	}
+	if constexpr ( KIND!=NWAY_NOTNEAR )
 	while ( true )
 	{
-		if ( n.m_eKind==NWAY_BEFORE && s.m_iEmitNext<s.m_nEmit )
+		if ( KIND==NWAY_BEFORE && s.m_iEmitNext<s.m_nEmit )
 		{
 			const int i = s.m_iEmitNext++;
 			s.m_tHead.m_uHitpos = s.m_dEmit[i]; s.m_tHead.m_uQpos = (uint32_t)n.m_dAtomPos[i]; s.m_tHead.m_uSpanlen = 1; s.m_tHead.m_uWeight = 1;
@@ -458,9 +474,9 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 				continue;
 			const uint32_t uQpos = q.m_dLeaves[l].m_uAtomPos;
 			bool bLess;
-			if ( n.m_eKind==NWAY_BEFORE )
+			if ( KIND==NWAY_BEFORE )
 				bLess = ( h & ~( 1u<<23 ) )<( uBestHit & ~( 1u<<23 ) );
-			else if ( n.m_eKind==NWAY_QUORUM )
+			else if ( KIND==NWAY_QUORUM )
 				bLess = ( h & ~( 1u<<23 ) )<( uBestHit & ~( 1u<<23 ) ) || ( ( h & ~( 1u<<23 ) )==( uBestHit & ~( 1u<<23 ) ) && uQpos<uBestQpos );
 			else
 				bLess = h<uBestHit || ( h==uBestHit && uQpos>uBestQpos );
@@ -476,7 +492,7 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 		}
 		fnNext ( iBest );
 		bool bEmit;
-		switch ( n.m_eKind )
+		switch ( KIND )
 		{
 		case NWAY_PROXIMITY:	bEmit = ProximityFSM ( n, s, uBestHit, (int)uBestQpos, s.m_tHead ); break;
 		case NWAY_NEAR:			bEmit = NearFSM ( n, s, uBestHit, uBestQpos, (uint32_t)iBestW, s.m_tHead ); break;
@@ -494,6 +510,20 @@ __device__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
 			fnEmitted ( uBestHit );
 			return;
 		}
+	}
+}
+
+/// (one instantiation per kind: the per-hit loops of phrase / proximity carry no tests for the other kinds)
+__device__ __forceinline__ void NWayAdvance ( const DevQuery_t & q, int j, DocHits_t & H )
+{
+	switch ( q.m_dNWay[j].m_eKind )
+	{
+	case NWAY_PHRASE:		NWayAdvanceT<NWAY_PHRASE> ( q, j, H ); break;
+	case NWAY_PROXIMITY:	NWayAdvanceT<NWAY_PROXIMITY> ( q, j, H ); break;
+	case NWAY_NEAR:			NWayAdvanceT<NWAY_NEAR> ( q, j, H ); break;
+	case NWAY_BEFORE:		NWayAdvanceT<NWAY_BEFORE> ( q, j, H ); break;
+	case NWAY_NOTNEAR:		NWayAdvanceT<NWAY_NOTNEAR> ( q, j, H ); break;
+	default:				NWayAdvanceT<NWAY_QUORUM> ( q, j, H ); break;
 	}
 }
 

@@ -1535,7 +1535,7 @@ __device__ __forceinline__ bool ProbeGroup ( const DevIndex_t & tIdx, const DevH
 /// dense store; sparse ones by a binary search of the resident skiplist (block table) per candidate, then only the blocks that
 /// hold a candidate are decoded (each once per warp) and searched. TF*IDF accumulates in that same order.
 template<bool HITS>
-__global__ void __launch_bounds__ ( EVAL_THREADS ) and_kernel ( EvalParams_t P )
+__global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) and_kernel ( EvalParams_t P )
 {
 	__shared__ AndShared_t S;
 	const int tid = threadIdx.x, iWarp = tid>>5, iLane = tid & 31;
