@@ -54,8 +54,7 @@ struct OrBitsShared_t
 	// bitmap pass: the program's hot UNITS (a hot keyword of the OR, or an AND group of hot keywords) sorted by their weight bound,
 	// biggest first; their member keywords flat in that order
 	const uint32_t * m_dBitPtr[MAX_LEAVES];				///< member: the keyword's field-0 bitmap (field f: + f*bit stride)
-	uint32_t		m_dBitFields[MAX_LEAVES];			///< member: queried fields the index has
-	uint8_t			m_dMemLast[MAX_LEAVES];				///< member: the last one of its unit
+	uint32_t		m_dBitFields[MAX_LEAVES];			///< member: queried fields the index has | 256 if it is the last one of its unit; padded with 0 to a multiple of 4 members
 	int32_t			m_nMembers;
 	int32_t			m_dUb[MAX_LEAVES];					///< unit: sum over its keywords of ceil ( max ( idf, 0 )*64000 ) + 1
 	int32_t			m_dSuffix[MAX_LEAVES+1];			///< sum of m_dUb[i..]
@@ -255,12 +254,17 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 				{
 					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
 					S.m_dBitPtr[nMem] = P.m_tHot.m_pBits + (size_t)tLeaf.m_iHot*P.m_tHot.m_nBitFields*iBitStride;
-					S.m_dBitFields[nMem] = tLeaf.m_uQueriedFields & uIndexFields;
-					S.m_dMemLast[nMem] = ( iOp==dUnitOp0[u]+dUnitOps[u]-1 ) ? 1 : 0;
+					S.m_dBitFields[nMem] = ( tLeaf.m_uQueriedFields & uIndexFields & 255u ) | ( ( iOp==dUnitOp0[u]+dUnitOps[u]-1 ) ? 256u : 0u );
 					++nMem;
 				}
 			}
 			S.m_nMembers = nMem;
+			for ( int i=nMem; i<( ( nMem+3 ) & ~3 ); ++i )
+			{
+				// (padding: no field, no load; the last unit has been closed before)
+				S.m_dBitPtr[i] = P.m_tHot.m_pBits;
+				S.m_dBitFields[i] = 0;
+			}
 			int iSum = 0;
 			S.m_dSuffix[nHot] = 0;
 			for ( int i=nHot-1; i>=0; --i )
@@ -691,42 +695,40 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 					int iUnit = 0;
 					for ( int i0=0; i0<nMembers; i0+=4 )
 					{
-						uint32_t dW[4][NF];
+						uint32_t dW[4][NF], dInfo[4];
 						#pragma unroll
 						for ( int j=0; j<4; ++j )
 						{
-							const bool b = i0+j<nMembers;
-							const uint32_t uMask = b ? S.m_dBitFields[i0+j] : 0u;
-							const uint32_t * p = S.m_dBitPtr[b ? i0+j : 0] + uWord;
+							dInfo[j] = S.m_dBitFields[i0+j];
+							const uint32_t * p = S.m_dBitPtr[i0+j] + uWord;
 							#pragma unroll
 							for ( int f=0; f<NF; ++f )
-								dW[j][f] = ( ( uMask>>f ) & 1u ) ? __ldg ( p + f*iBitStride ) : 0u;
+								dW[j][f] = ( ( dInfo[j]>>f ) & 1u ) ? __ldg ( p + f*iBitStride ) : 0u;
 						}
 						#pragma unroll
 						for ( int j=0; j<4; ++j )
-							if ( i0+j<nMembers )
+						{
+							uint32_t uAny = 0;
+							#pragma unroll
+							for ( int f=0; f<NF; ++f )
 							{
-								uint32_t uAny = 0;
+								dFu[f] |= dW[j][f];
+								uAny |= dW[j][f];
+							}
+							uUnitP &= uAny;
+							if ( dInfo[j] & 256u )
+							{
 								#pragma unroll
 								for ( int f=0; f<NF; ++f )
 								{
-									dFu[f] |= dW[j][f];
-									uAny |= dW[j][f];
+									dF[f] |= dFu[f] & uUnitP;
+									dFu[f] = 0;
 								}
-								uUnitP &= uAny;
-								if ( S.m_dMemLast[i0+j] )
-								{
-									#pragma unroll
-									for ( int f=0; f<NF; ++f )
-									{
-										dF[f] |= dFu[f] & uUnitP;
-										dFu[f] = 0;
-									}
-									pPsm[iUnit*32+iLane] = uUnitP;
-									++iUnit;
-									uUnitP = 0xFFFFFFFFu;
-								}
+								pPsm[iUnit*32+iLane] = uUnitP;
+								++iUnit;
+								uUnitP = 0xFFFFFFFFu;
 							}
+						}
 					}
 				}
 				++uDbgMinis;
@@ -754,6 +756,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 					}
 					int iPrevFv = 0;
 					uint32_t uFvRows = 0;
+					bool bFvAny = false;
 					for ( int iCls=0; iCls<nClasses; ++iCls )
 					{
 						const uint32_t uCode = pClass[iCls];	// (same address in every lane)
@@ -766,7 +769,10 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 							for ( int f=0; f<NF; ++f )
 								uFvRows &= ( ( fv>>f ) & 1 ) ? dF[f] : ~dF[f];
 							iPrevFv = fv;
+							bFvAny = __any_sync ( FULL_MASK, uFvRows!=0 );
 						}
+						if ( !bFvAny )
+							continue;	// no row of this mini-tile matches in exactly these fields
 						uint32_t m = uFvRows;
 						m &= a==0 ? dT1[0] : a==1 ? dT1[1] : a==2 ? dT1[2] : 0xFFFFFFFFu;
 						m &= b==0 ? dT2[0] : b==1 ? dT2[1] : b==2 ? dT2[2] : 0xFFFFFFFFu;
