@@ -177,7 +177,10 @@ typedef struct mgpu_index mgpu_index;
  * `rowid_base` = global rowid of local row 0 (contiguous rowid-range shards); only
  * used when packing multi-GPU merge keys. */
 int				mgpu_index_open ( const char * path_prefix, int device, uint32_t rowid_base, mgpu_index ** out );
-void			mgpu_index_close ( mgpu_index * idx );
+/* Lifetime: a batch keeps a pointer to its index, so free every batch of a handle before closing it. Closing a handle with live
+   batches is refused (MGPU_E_BAD_QUERY, the handle stays valid); a successful close first drains the handle's own streams. A caller
+   stream installed with mgpu_index_set_stream must outlive the batches prepared on it. */
+int				mgpu_index_close ( mgpu_index * idx );
 /* run this handle's kernels and copies on the caller's CUDA stream (cudaStream_t) instead of the handle's own one,
  * so that callers can bracket batches with their own events; NULL restores the private stream */
 int				mgpu_index_set_stream ( mgpu_index * idx, void * cuda_stream );

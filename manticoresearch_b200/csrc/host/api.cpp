@@ -43,11 +43,27 @@ int mgpu_index_open ( const char * path_prefix, int device, uint32_t rowid_base,
 	return MGPU_OK;
 }
 
-void mgpu_index_close ( mgpu_index * idx )
+int mgpu_index_close ( mgpu_index * idx )
 {
-	if ( idx )
+	if ( !idx )
+		return MGPU_OK;
+	{
+		// batches hold a plain pointer to their index: closing under them is refused (the handle stays valid), and whatever the
+		// handle's streams still run is drained before the device memory goes away
+		std::lock_guard<std::mutex> tGuard ( idx->m_t.m_tLock );
+		if ( idx->m_t.m_nLiveBatches.load()>0 )
+		{
+			idx->m_t.m_sError = "mgpu_index_close: batches of this index are still alive (free them first)";
+			return MGPU_E_BAD_QUERY;
+		}
 		cudaSetDevice ( idx->m_t.m_iDevice );
+		if ( idx->m_t.m_tOwnStream )
+			cudaStreamSynchronize ( idx->m_t.m_tOwnStream );
+		if ( idx->m_t.m_tHotStream )
+			cudaStreamSynchronize ( idx->m_t.m_tHotStream );
+	}
 	delete idx;
+	return MGPU_OK;
 }
 
 int mgpu_index_set_stream ( mgpu_index * idx, void * cuda_stream )

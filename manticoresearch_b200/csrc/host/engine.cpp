@@ -214,6 +214,12 @@ int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
 				m_sError = "dictionary entry points outside .spd";
 				return MGPU_E_FORMAT;
 			}
+			// a doclist record is four varints, the list ends with a zero byte; a keyword cannot sit in more documents than the index has
+			if ( e.m_iDocs<1 || (int64_t)e.m_iDocs>m_tHdr.m_iDocinfo || (int64_t)e.m_iDocs*4+1>e.m_iDoclistLength )
+			{
+				m_sError = "implausible document count for keyword " + e.m_sKeyword;
+				return MGPU_E_FORMAT;
+			}
 		}
 	}
 
@@ -251,7 +257,13 @@ int Index_c::Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase )
 			ByteReader_t r ( tSpe.m_p+e.m_iSkiplistOffset, tSpe.m_iLen-e.m_iSkiplistOffset );
 			for ( uint32_t b=1; b<t.m_nBlocks; ++b )
 			{
-				uRow += 32 + (uint32_t)r.Unzip();
+				const uint64_t uRowNext = (uint64_t)uRow + 32 + r.Unzip();
+				if ( uRowNext>(uint64_t)m_tHdr.m_iDocinfo )
+				{
+					m_sError = "skiplist rowid beyond the index for keyword " + e.m_sKeyword;
+					return MGPU_E_FORMAT;
+				}
+				uRow = (uint32_t)uRowNext;
 				uOff += 4*32 + r.Unzip();
 				uHit += r.Unzip();
 				dBlkRowid.push_back ( uRow ); dBlkOff.push_back ( uOff ); dBlkHitpos.push_back ( uHit );
@@ -1151,6 +1163,8 @@ Batch_c::~Batch_c()
 	if ( m_bHotPending && m_tEvHotDone )
 		cudaStreamWaitEvent ( m_tStream, m_tEvHotDone, 0 );
 	if ( m_tEvHotDone ) cudaEventDestroy ( m_tEvHotDone );
+	if ( m_pIndex )
+		--m_pIndex->m_nLiveBatches;
 	if ( m_tEv0 ) cudaEventDestroy ( m_tEv0 );
 	if ( m_tEv1 ) cudaEventDestroy ( m_tEv1 );
 	if ( m_tEv2 ) cudaEventDestroy ( m_tEv2 );
@@ -1170,6 +1184,7 @@ static int Pow2Ceil ( int n )
 int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads, bool bEagerHot )
 {
 	m_pIndex = pIndex;
+	++pIndex->m_nLiveBatches;
 	const EngineOptions_t tOpt = pIndex->m_tOpt;	// one consistent copy per batch
 	CUDA_TRY ( cudaSetDevice ( pIndex->m_iDevice ), m_sError );
 	const auto tStart = std::chrono::steady_clock::now();
@@ -1728,7 +1743,7 @@ int Batch_c::BuildHotStore ( cudaStream_t s )
 	DevHotStore_t & tHot = m_tHot;
 	if ( !m_dHotTerms.empty() )
 	{
-		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotData.m_p, 0, m_dHotTerms.size()*(size_t)m_iHotStride*2, s ), m_sError );
+		// (the u16 rows are cleared by hot_decode_kernel itself, block by block; only the bitmaps are memset)
 		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
 		HotDecodeParams_t H {};
 		H.m_tIndex = pIndex->m_tDev;

@@ -8,6 +8,7 @@
 #include "../../../include/mgpu.h"
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -118,6 +119,7 @@ public:
 	int				m_nSMs = 148;
 	std::mutex		m_tLock;		///< serialises batches on this handle
 	std::mutex		m_tCacheLock;
+	std::atomic<int>	m_nLiveBatches { 0 };	///< batches prepared on this handle and not freed yet (mgpu_index_close refuses while > 0)
 	std::vector<struct PlannedQuery_t> m_dPlanCache;	///< the last batch's (cleared) plan array: its memory is reused by the next batch
 	mgpu_batch_stats m_tLastSearchStats {};
 

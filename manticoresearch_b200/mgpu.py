@@ -125,7 +125,7 @@ def load_library(path=None):
     sig = {
         "mgpu_abi_version": (C.c_int, []),
         "mgpu_index_open": (C.c_int, [C.c_char_p, C.c_int, u32, C.POINTER(vp)]),
-        "mgpu_index_close": (None, [vp]),
+        "mgpu_index_close": (C.c_int, [vp]),
         "mgpu_index_set_stream": (C.c_int, [vp, vp]),
         "mgpu_index_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
         "mgpu_last_error": (C.c_char_p, [vp]),
@@ -439,7 +439,9 @@ class Index:
 
     def close(self):
         if self._h:
-            self._lib.mgpu_index_close(self._h)
+            rc = self._lib.mgpu_index_close(self._h)
+            if rc != MGPU_OK:       # batches of this handle are still alive: the handle stays open
+                raise MgpuError(rc, (self._lib.mgpu_last_error(self._h) or b"").decode())
             self._h = None
 
     def __del__(self):

@@ -551,3 +551,41 @@ def test_reference_built_index_on_gpu():
     finally:
         gpu.close()
         cpu.close()
+
+
+def test_close_is_refused_while_batches_live(tmp_path):
+    """a batch keeps a pointer to its index: mgpu_index_close with a live batch is refused and the handle keeps working"""
+    prefix = str(tmp_path / "life")
+    docs = [{"id": 1 + i, "fields": [[("aa", 1)] + ([("bb", 2)] if i % 3 == 0 else [])], "attrs": []} for i in range(3000)]
+    M.build_index(prefix, ["body"], docs)
+    gpu = M.Index(prefix, device=0)
+    q = [M.Query(M.OR(M.kw("aa", 1), M.kw("bb", 2)), ranker=M.RANK_BM25, max_matches=10)]
+    batch = gpu.prepare(q)
+    with pytest.raises(M.MgpuError):
+        gpu.close()
+    batch.run()
+    first = batch.fetch().get(0)
+    batch.free()
+    again = gpu.search(q).get(0)
+    assert first["rowid"] == again["rowid"] and first["weight"] == again["weight"] and len(first["rowid"]) > 0
+    gpu.close()
+
+
+def test_corrupt_dictionary_is_rejected_at_open(tmp_path):
+    """mgpu_index_open validates what the kernels will trust: a keyword that claims more documents than its doclist can hold
+    (four varints per record) comes back as MGPU_E_FORMAT, not as out-of-bounds device reads"""
+    import shutil
+    prefix = str(tmp_path / "ok")
+    docs = [{"id": 1 + i, "fields": [[("w%d" % (i % 50), 1), ("all", 2)]], "attrs": []} for i in range(2000)]
+    M.build_index(prefix, ["body"], docs)
+    bad = str(tmp_path / "bad")
+    for ext in ("sph", "spi", "spd", "spp", "spe", "spa", "spm"):
+        if os.path.exists(prefix + "." + ext):
+            shutil.copy(prefix + "." + ext, bad + "." + ext)
+    # truncate .spd in the middle of the last doclists: offsets past the end / doclists shorter than 4 bytes per document
+    size = os.path.getsize(bad + ".spd")
+    with open(bad + ".spd", "r+b") as f:
+        f.truncate(size // 2)
+    with pytest.raises(M.MgpuError) as e:
+        M.Index(bad, device=0)
+    assert e.value.code == M.MGPU_E_FORMAT
