@@ -1121,6 +1121,7 @@ bool EngineOptions_t::Set ( const char * szName, int64_t iValue )
 		{ "or_range_tiles",	&EngineOptions_t::m_iOrRangeTiles,	1, 1<<20 },
 		{ "dnf_pct",		&EngineOptions_t::m_iDnfPct,		1, 100 },
 		{ "eager_hot",		&EngineOptions_t::m_bEagerHot,		0, 1 },
+		{ "force_hot",		&EngineOptions_t::m_bForceHot,		0, 1 },
 		{ "or_bits",		&EngineOptions_t::m_bOrBits,		0, 1 },
 		{ "bits_dnf",		&EngineOptions_t::m_bBitsDnf,		0, 1 },
 		{ "bits_dnf_div",	&EngineOptions_t::m_iBitsDnfDiv,	0, 1<<20 },
@@ -1289,14 +1290,45 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			for ( const TermInfo_t * p : m_dPlans[i].m_dLeafTerms )
 				if ( p && (int64_t)p->m_iDocs*iHotDiv>=(int64_t)uRows && !dUse[p->m_iOrdinal]++ )
 					dTouched.push_back ( p );
+		// OR-of-AND-groups programs with a group led by a dense keyword cannot walk that driver block by block (and_kernel), and the
+		// tile kernels pay ~10x a bitmap query for them: every keyword of theirs goes into the store, however rare or rarely used
+		// (a sparse keyword costs K0 a few microseconds), so that the whole program runs on the bitmaps (orbits_kernel)
+		const int32_t FORCE_BIT = 1<<30;
+		if ( tOpt.m_bBitsDnf && tOpt.m_bOrBits && tOpt.m_bForceHot && pIndex->m_tHdr.m_dFields.size()<=4 && !pIndex->m_tDev.m_pDead && tOpt.m_bOrClass )
+			for ( int i : dDocOnly )
+			{
+				const PlannedQuery_t & p = m_dPlans[i];
+				const DevQuery_t & q = p.m_tDev;
+				if ( q.m_nGroups<=0 || q.m_bPureOr || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
+					continue;
+				bool bDense = false, bAll = true;
+				for ( int g=0; g<q.m_nGroups; ++g )
+				{
+					const TermInfo_t * pDrv = p.m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
+					bDense |= pDrv && (int64_t)pDrv->m_iDocs*100>=(int64_t)uRows*std::max ( 1, tOpt.m_iDnfPct );
+				}
+				for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
+					bAll &= pTerm!=nullptr;
+				if ( !bDense || !bAll )
+					continue;
+				for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
+				{
+					if ( !dUse[pTerm->m_iOrdinal] )
+						dTouched.push_back ( pTerm );
+					dUse[pTerm->m_iOrdinal] |= FORCE_BIT;
+				}
+			}
 		std::vector<std::pair<int64_t,const TermInfo_t*>> dHot;
 		// ... or a keyword in >= 1/16 of the rows that only one query uses (small batches): one pass over its doclist into the
 		// store and its bitmaps beats walking it posting by posting
 		for ( const TermInfo_t * p : dTouched )
 		{
-			const int nUse = dUse[p->m_iOrdinal];
+			const int nUse = dUse[p->m_iOrdinal] & ( FORCE_BIT-1 );
+			const bool bForced = ( dUse[p->m_iOrdinal] & FORCE_BIT )!=0;
 			dUse[p->m_iOrdinal] = 0;
-			if ( nUse>=tOpt.m_iHotMinUses || (int64_t)p->m_iDocs*16>=(int64_t)uRows )
+			if ( bForced )
+				dHot.push_back ( { INT64_MAX/2, p } );
+			else if ( nUse>=tOpt.m_iHotMinUses || (int64_t)p->m_iDocs*16>=(int64_t)uRows )
 				dHot.push_back ( { (int64_t)nUse*p->m_iDocs, p } );
 		}
 		std::sort ( dHot.begin(), dHot.end(), [] ( const auto & a, const auto & b ) { return a.first>b.first || ( a.first==b.first && a.second->m_uFirstBlk<b.second->m_uFirstBlk ); } );
