@@ -1182,6 +1182,24 @@ static int Pow2Ceil ( int n )
 	return p;
 }
 
+/// fn ( from, to, thread ) over [0, n) on nThreads host threads (contiguous ranges, thread t gets the t-th one); inline for one thread
+template<typename FN>
+static void ParallelFor ( int n, int nThreads, FN && fn )
+{
+	nThreads = std::max ( 1, std::min ( nThreads, n ) );
+	if ( nThreads<=1 )
+	{
+		fn ( 0, n, 0 );
+		return;
+	}
+	std::vector<std::thread> dThreads;
+	for ( int t=1; t<nThreads; ++t )
+		dThreads.emplace_back ( fn, (int)( (int64_t)n*t/nThreads ), (int)( (int64_t)n*( t+1 )/nThreads ), t );
+	fn ( 0, (int)( (int64_t)n/nThreads ), 0 );
+	for ( auto & t : dThreads )
+		t.join();
+}
+
 int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads, bool bEagerHot )
 {
 	m_pIndex = pIndex;
@@ -1242,19 +1260,43 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	};
 	m_tStats.host_plan_ms = std::chrono::duration<float,std::milli> ( tPlanned-tStart ).count();
 
-	// runnable queries; three launch classes (see engine.h)
+	// runnable queries; three launch classes (see engine.h). The plans are 3.4 KB apiece: every pass over a 10k-query batch walks
+	// 34 MB, so the passes of this function run on a few host threads (contiguous query ranges, merged in thread order)
+	int nSetupThreads = (int)std::min<unsigned> ( std::max ( 1u, std::thread::hardware_concurrency() ), 6u );
+	nSetupThreads = std::max ( 1, std::min ( nSetupThreads, nQueries/1024 ) );
+	if ( tOpt.m_iPlanThreads>0 )
+		nSetupThreads = std::min ( nSetupThreads, tOpt.m_iPlanThreads );
+	if ( nMaxThreads>0 )
+		nSetupThreads = std::min ( nSetupThreads, nMaxThreads );
 	std::vector<int> dDocOnly, dOrder[NUM_CLASSES];
-	for ( int i=0; i<nQueries; ++i )
-		if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
+	{
+		struct Part_t { std::vector<int> m_dDocOnly, m_dHits1, m_dHits4; int m_iKMax = 1; int64_t m_iAlg = 0, m_iPostings = 0; };
+		std::vector<Part_t> dParts ( nSetupThreads );
+		ParallelFor ( nQueries, nSetupThreads, [&] ( int iFrom, int iTo, int t )
 		{
-			if ( m_dPlans[i].m_tDev.m_bNeedHits )
-				dOrder [ ( m_dPlans[i].m_tDev.m_nGroups==1 && tOpt.m_bAndKernel ) ? 4 : 1 ].push_back ( i );
-			else
-				dDocOnly.push_back ( i );
-			m_iKMax = std::max ( m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
-			m_tStats.algorithmic_bytes += m_dPlans[i].m_iAlgBytes;
-			m_tStats.postings += m_dPlans[i].m_iCost;
+			Part_t & tPart = dParts[t];
+			for ( int i=iFrom; i<iTo; ++i )
+				if ( m_dPlans[i].m_iStatus==MGPU_OK && m_dPlans[i].m_tDev.m_nOps>0 )
+				{
+					if ( m_dPlans[i].m_tDev.m_bNeedHits )
+						( ( m_dPlans[i].m_tDev.m_nGroups==1 && tOpt.m_bAndKernel ) ? tPart.m_dHits4 : tPart.m_dHits1 ).push_back ( i );
+					else
+						tPart.m_dDocOnly.push_back ( i );
+					tPart.m_iKMax = std::max ( tPart.m_iKMax, m_dPlans[i].m_tDev.m_iMaxMatches );
+					tPart.m_iAlg += m_dPlans[i].m_iAlgBytes;
+					tPart.m_iPostings += m_dPlans[i].m_iCost;
+				}
+		} );
+		for ( const Part_t & tPart : dParts )
+		{
+			dDocOnly.insert ( dDocOnly.end(), tPart.m_dDocOnly.begin(), tPart.m_dDocOnly.end() );
+			dOrder[1].insert ( dOrder[1].end(), tPart.m_dHits1.begin(), tPart.m_dHits1.end() );
+			dOrder[4].insert ( dOrder[4].end(), tPart.m_dHits4.begin(), tPart.m_dHits4.end() );
+			m_iKMax = std::max ( m_iKMax, tPart.m_iKMax );
+			m_tStats.algorithmic_bytes += tPart.m_iAlg;
+			m_tStats.postings += tPart.m_iPostings;
 		}
+	}
 	if ( dDocOnly.empty() && dOrder[1].empty() && dOrder[4].empty() )
 		return MGPU_OK;
 
@@ -1286,38 +1328,44 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		// 3 ms through hash maps, on the critical path in front of K0)
 		std::vector<int32_t> & dUse = pIndex->m_dTermUse;
 		std::vector<const TermInfo_t*> dTouched;
-		for ( int i : dDocOnly )
-			for ( const TermInfo_t * p : m_dPlans[i].m_dLeafTerms )
-				if ( p && (int64_t)p->m_iDocs*iHotDiv>=(int64_t)uRows && !dUse[p->m_iOrdinal]++ )
-					dTouched.push_back ( p );
 		// OR-of-AND-groups programs with a group led by a dense keyword cannot walk that driver block by block (and_kernel), and the
 		// tile kernels pay ~10x a bitmap query for them: every keyword of theirs goes into the store, however rare or rarely used
 		// (a sparse keyword costs K0 a few microseconds), so that the whole program runs on the bitmaps (orbits_kernel)
 		const int32_t FORCE_BIT = 1<<30;
-		if ( tOpt.m_bBitsDnf && tOpt.m_bOrBits && tOpt.m_bForceHot && pIndex->m_tHdr.m_dFields.size()<=4 && !pIndex->m_tDev.m_pDead && tOpt.m_bOrClass )
-			for ( int i : dDocOnly )
+		const bool bForce = tOpt.m_bBitsDnf && tOpt.m_bOrBits && tOpt.m_bForceHot && pIndex->m_tHdr.m_dFields.size()<=4 && !pIndex->m_tDev.m_pDead && tOpt.m_bOrClass;
+		{
+			// (counters are bumped atomically; whoever moves one off zero lists the keyword)
+			std::vector<std::vector<const TermInfo_t*>> dPartTouched ( nSetupThreads );
+			ParallelFor ( (int)dDocOnly.size(), nSetupThreads, [&] ( int iFrom, int iTo, int t )
 			{
-				const PlannedQuery_t & p = m_dPlans[i];
-				const DevQuery_t & q = p.m_tDev;
-				if ( q.m_nGroups<=0 || q.m_bPureOr || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
-					continue;
-				bool bDense = false, bAll = true;
-				for ( int g=0; g<q.m_nGroups; ++g )
+				std::vector<const TermInfo_t*> & dMine = dPartTouched[t];
+				for ( int k=iFrom; k<iTo; ++k )
 				{
-					const TermInfo_t * pDrv = p.m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
-					bDense |= pDrv && (int64_t)pDrv->m_iDocs*100>=(int64_t)uRows*std::max ( 1, tOpt.m_iDnfPct );
+					const PlannedQuery_t & p = m_dPlans[dDocOnly[k]];
+					for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
+						if ( pTerm && (int64_t)pTerm->m_iDocs*iHotDiv>=(int64_t)uRows && !__atomic_fetch_add ( &dUse[pTerm->m_iOrdinal], 1, __ATOMIC_RELAXED ) )
+							dMine.push_back ( pTerm );
+					const DevQuery_t & q = p.m_tDev;
+					if ( !bForce || q.m_nGroups<=0 || q.m_bPureOr || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
+						continue;
+					bool bDense = false, bAll = true;
+					for ( int g=0; g<q.m_nGroups; ++g )
+					{
+						const TermInfo_t * pDrv = p.m_dLeafTerms[q.m_dOps[q.m_dGroupOp0[g]].m_uLeaf];
+						bDense |= pDrv && (int64_t)pDrv->m_iDocs*100>=(int64_t)uRows*std::max ( 1, tOpt.m_iDnfPct );
+					}
+					for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
+						bAll &= pTerm!=nullptr;
+					if ( !bDense || !bAll )
+						continue;
+					for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
+						if ( !__atomic_fetch_or ( &dUse[pTerm->m_iOrdinal], FORCE_BIT, __ATOMIC_RELAXED ) )
+							dMine.push_back ( pTerm );
 				}
-				for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
-					bAll &= pTerm!=nullptr;
-				if ( !bDense || !bAll )
-					continue;
-				for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
-				{
-					if ( !dUse[pTerm->m_iOrdinal] )
-						dTouched.push_back ( pTerm );
-					dUse[pTerm->m_iOrdinal] |= FORCE_BIT;
-				}
-			}
+			} );
+			for ( const auto & dMine : dPartTouched )
+				dTouched.insert ( dTouched.end(), dMine.begin(), dMine.end() );
+		}
 		std::vector<std::pair<int64_t,const TermInfo_t*>> dHot;
 		// ... or a keyword in >= 1/16 of the rows that only one query uses (small batches): one pass over its doclist into the
 		// store and its bitmaps beats walking it posting by posting
@@ -1364,22 +1412,25 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				if ( (int64_t)m_dHotTerms[h].m_nDocs*3>=(int64_t)uRows )
 					m_dHotLvlSlot[h] = m_nHotLvl++;
 		if ( !m_dHotTerms.empty() )
-			for ( int i : dDocOnly )
+			ParallelFor ( (int)dDocOnly.size(), nSetupThreads, [&] ( int iFrom, int iTo, int )
 			{
-				PlannedQuery_t & p = m_dPlans[i];
-				for ( size_t l=0; l<p.m_dLeafTerms.size(); ++l )
+				for ( int k=iFrom; k<iTo; ++k )
 				{
-					const int iSlot = p.m_dLeafTerms[l] ? dUse[p.m_dLeafTerms[l]->m_iOrdinal]-1 : -1;
-					if ( iSlot>=0 )
+					PlannedQuery_t & p = m_dPlans[dDocOnly[k]];
+					for ( size_t l=0; l<p.m_dLeafTerms.size(); ++l )
 					{
-						p.m_tDev.m_dLeaves[l].m_iHot = iSlot;
-						if ( ( p.m_tDev.m_uOrigMask>>l ) & 1u )
-							p.m_tDev.m_bOrigHot = 1;
-						if ( p.m_tDev.m_iDriverLeaf==(int)l )
-							p.m_tDev.m_iDriverLeaf = -1;
+						const int iSlot = p.m_dLeafTerms[l] ? dUse[p.m_dLeafTerms[l]->m_iOrdinal]-1 : -1;
+						if ( iSlot>=0 )
+						{
+							p.m_tDev.m_dLeaves[l].m_iHot = iSlot;
+							if ( ( p.m_tDev.m_uOrigMask>>l ) & 1u )
+								p.m_tDev.m_bOrigHot = 1;
+							if ( p.m_tDev.m_iDriverLeaf==(int)l )
+								p.m_tDev.m_iDriverLeaf = -1;
+						}
 					}
 				}
-			}
+			} );
 		for ( const auto & t : dHot )
 			dUse[t.second->m_iOrdinal] = 0;
 	}
@@ -1393,9 +1444,13 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	const bool bNoOrClass = !tOpt.m_bOrClass, bNoDnfClass = !tOpt.m_bDnfClass;	// (experiments)
 	// a group's driver may sit in at most iDnfMul/iDnfDiv of the rows (option dnf_pct: percent, for experiments)
 	const int64_t iDnfDiv = 100, iDnfMul = std::max ( 1, tOpt.m_iDnfPct );
-	for ( int i : dDocOnly )
+	std::vector<uint8_t> dClassOf ( dDocOnly.size(), 0 );
+	ParallelFor ( (int)dDocOnly.size(), nSetupThreads, [&] ( int iFrom, int iTo, int )
+	{
+	for ( int iDoc=iFrom; iDoc<iTo; ++iDoc )
 	{
 		// intersection kernel: DNF programs (1 group = pure AND) whose every group is led by a sparse keyword
+		const int i = dDocOnly[iDoc];
 		DevQuery_t & q = m_dPlans[i].m_tDev;
 		bool bDnf = q.m_nGroups>0 && !bNoAndKernel;
 		for ( int g=0; g<q.m_nGroups && bDnf; ++g )
@@ -1429,7 +1484,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			}
 		if ( bBitsDnf )
 		{
-			dOrder[5].push_back ( i );
+			dClassOf[iDoc] = 5;
 			continue;
 		}
 		const bool bBoundOk = !bDnf && bBoundBase;
@@ -1449,8 +1504,11 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			}
 		if ( ( !bDnf && !bHotDnf ) || ( bHotDnf && q.m_bPureOr ) )
 			q.m_nGroups = 0;
-		dOrder [ bDnf ? 2 : bOrClass ? 5 : bHotDnf ? 6 : m_dPlans[i].m_nStack>1 ? 3 : 0 ].push_back ( i );
+		dClassOf[iDoc] = (uint8_t)( bDnf ? 2 : bOrClass ? 5 : bHotDnf ? 6 : m_dPlans[i].m_nStack>1 ? 3 : 0 );
 	}
+	} );
+	for ( size_t iDoc=0; iDoc<dDocOnly.size(); ++iDoc )
+		dOrder[dClassOf[iDoc]].push_back ( dDocOnly[iDoc] );
 
 	// class 5 on orbits_kernel: every keyword outside the hot store is decoded once per run into a plain posting list
 	if ( m_iOrMode==3 && !dOrder[5].empty() )
