@@ -777,7 +777,10 @@ struct Planner_c
 	{
 		DevQuery_t & d = m_tOut.m_tDev;
 		memset ( &d, 0, sizeof(d) );
+		m_tOut.m_dLeafTerms.m_n = m_tOut.m_dLeafWord.m_n = 0;
 		m_tOut.m_dWordStats.assign ( std::max ( m_q.n_words, 0 ), mgpu_wordstat { 0, 0 } );
+		if ( m_q.n_words>MAX_LEAVES )
+			return MGPU_E_UNSUPPORTED;	// (more keywords than a device query has leaves)
 		for ( int i=0; i<m_q.n_words && m_q.words; ++i )
 			if ( m_q.words[i].word )
 				if ( const TermInfo_t * p = m_tIndex.FindTerm ( m_q.words[i].word ) )
@@ -1067,9 +1070,10 @@ int PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_
 /// A plan made on one rowid-range shard, re-bound to another shard of the same index: the program, IDFs (global statistics), weights,
 /// filters and sort keys do not depend on the shard; the keywords' dictionary entries and the statistics derived from them do.
 /// Only valid for queries that carry global word_docs (so that no keyword order was decided from shard-local counts).
-void RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan )
+void RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan, const int32_t * pWordIds, const TermInfo_t * const * pTermOfId )
 {
-	for ( size_t i=0; i<tPlan.m_dWordStats.size(); ++i )
+	// (the sharded handle reports the keywords' statistics from its global table: the shards' own are not needed then)
+	for ( size_t i=0; i<tPlan.m_dWordStats.size() && !pWordIds; ++i )
 	{
 		tPlan.m_dWordStats[i] = mgpu_wordstat { 0, 0 };
 		if ( tQuery.words && tQuery.words[i].word )
@@ -1085,7 +1089,8 @@ void RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuer
 	tPlan.m_iAlgBytes = 0;
 	for ( size_t l=0; l<tPlan.m_dLeafTerms.size(); ++l )
 	{
-		const TermInfo_t * pTerm = tIndex.FindTerm ( tQuery.words[tPlan.m_dLeafWord[l]].word );
+		const int iWord = tPlan.m_dLeafWord[l];
+		const TermInfo_t * pTerm = pWordIds ? ( pWordIds[iWord]>=0 ? pTermOfId[pWordIds[iWord]] : nullptr ) : tIndex.FindTerm ( tQuery.words[iWord].word );
 		tPlan.m_dLeafTerms[l] = pTerm;
 		DevLeaf_t & t = tPlan.m_tDev.m_dLeaves[l];
 		t.m_uFirstBlk = pTerm ? pTerm->m_uFirstBlk : 0;
@@ -1200,7 +1205,8 @@ static void ParallelFor ( int n, int nThreads, FN && fn )
 		t.join();
 }
 
-int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads, bool bEagerHot )
+int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads, bool bEagerHot,
+	const int32_t * pWordIds, const size_t * pWordOff, const TermInfo_t * const * pTermOfId )
 {
 	m_pIndex = pIndex;
 	++pIndex->m_nLiveBatches;
@@ -1232,7 +1238,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				{
 					// planned once for all shards (sharded.cpp): take the plan and bind its keywords to this shard's dictionary
 					m_dPlans[i] = (*pTemplate)[i];
-					RebindPlan ( *pIndex, pQueries[i], m_dPlans[i] );
+					RebindPlan ( *pIndex, pQueries[i], m_dPlans[i], pWordIds ? pWordIds+pWordOff[i] : nullptr, pTermOfId );
 				} else
 					PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
 		};
@@ -1770,7 +1776,9 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 				pStage[i].m_nItems = m_dSlots[i].m_nItems;
 			}
 		};
-		const int nThreads = std::max ( 1, std::min ( { (int)std::thread::hardware_concurrency(), 8, nDevQ/256 } ) );
+		int nThreads = std::max ( 1, std::min ( { (int)std::thread::hardware_concurrency(), 8, nDevQ/256 } ) );
+		if ( nMaxThreads>0 )
+			nThreads = std::min ( nThreads, nMaxThreads );	// (a sharded call runs one of these per shard at the same time)
 		if ( nThreads<=1 )
 			fnFill ( 0, nDevQ );
 		else

@@ -168,6 +168,26 @@ public:
 	int		FieldIndex ( const char * szName ) const;
 };
 
+/// fixed-capacity array with the few vector calls the planner uses: a plan holds no heap memory, so a batch's plan array is copied,
+/// cleared and handed to another shard without 3 allocations per query
+template<typename T, int N>
+struct FixedVec_T
+{
+	T		m_d[N];
+	int		m_n = 0;
+	size_t	size() const				{ return (size_t)m_n; }
+	T &		operator[] ( size_t i )		{ return m_d[i]; }
+	const T & operator[] ( size_t i ) const { return m_d[i]; }
+	const T * begin() const				{ return m_d; }
+	const T * end() const				{ return m_d+m_n; }
+	void	assign ( size_t n, const T & v )
+	{
+		m_n = (int)std::min<size_t> ( n, (size_t)N );
+		for ( int i=0; i<m_n; ++i )
+			m_d[i] = v;
+	}
+};
+
 /// one planned query: device descriptor + host bookkeeping
 struct PlannedQuery_t
 {
@@ -177,16 +197,18 @@ struct PlannedQuery_t
 	int				m_nStack = 1;
 	int64_t			m_iCost = 0;			///< sum of df over leaves (postings)
 	int64_t			m_iAlgBytes = 0;		///< SURVEY 8(d) algorithmic bytes (doclists + skiplists)
-	std::vector<mgpu_wordstat> m_dWordStats;
-	std::vector<const TermInfo_t*> m_dLeafTerms;	///< dictionary entry of every leaf (null = keyword not in the index)
-	std::vector<int>			m_dLeafWord;	///< index of every leaf's keyword in mgpu_query::words
+	FixedVec_T<mgpu_wordstat,MAX_LEAVES> m_dWordStats;	///< per query keyword (queries with more than MAX_LEAVES keywords are refused)
+	FixedVec_T<const TermInfo_t*,MAX_LEAVES> m_dLeafTerms;	///< dictionary entry of every leaf (null = keyword not in the index)
+	FixedVec_T<int,MAX_LEAVES>	m_dLeafWord;	///< index of every leaf's keyword in mgpu_query::words
 	int				m_iFirstIntKeyShift = -1;
 	int				m_iFirstIntKeyBits = 0;
 	bool			m_bFirstIntKeyDesc = false;
 };
 
 int		PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut );
-void	RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan );
+/// pWordIds / pTermOfId (sharded handle): the query's keywords as ids of the handle's global keyword table and this shard's dictionary
+/// entry per id; without them the keywords are looked up by name
+void	RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan, const int32_t * pWordIds=nullptr, const TermInfo_t * const * pTermOfId=nullptr );
 
 class Batch_c
 {
@@ -259,7 +281,9 @@ public:
 
 	/// pTemplate: plans made once on another shard of the same index (re-bound here instead of planning again); nMaxThreads caps the host threads
 	/// bEagerHot: the caller runs the batch right away under the same lock (mgpu_search_batch, the sharded call): K0 starts inside Prepare
-	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate=nullptr, int nMaxThreads=0, bool bEagerHot=false );
+	/// pWordIds [ pWordOff[i] + word ] / pTermOfId: see RebindPlan
+	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate=nullptr, int nMaxThreads=0, bool bEagerHot=false,
+				const int32_t * pWordIds=nullptr, const size_t * pWordOff=nullptr, const TermInfo_t * const * pTermOfId=nullptr );
 	int		BuildHotStore ( cudaStream_t tStream );
 	int		Run();
 	int		Sync();

@@ -82,7 +82,9 @@ public:
 	std::string										m_sError;
 	std::vector<std::unique_ptr<Index_c>>			m_dShards;
 	std::vector<uint32_t>							m_dBase;		///< [shards+1] global rowid of every shard's row 0, and the total
-	std::unordered_map<std::string,int64_t>			m_hGlobalDocs;	///< keyword -> documents over all shards
+	struct GlobalWord_t { int64_t m_iDocs = 0, m_iHits = 0; int32_t m_iId = -1; };
+	std::unordered_map<std::string,GlobalWord_t>	m_hGlobalDocs;	///< keyword -> documents / hits over all shards, id in the tables below
+	std::vector<std::vector<const TermInfo_t*>>		m_dTermOfId;	///< [shard][keyword id] -> the shard's dictionary entry (null: not in this shard)
 	int64_t											m_iTotalDocs = 0;
 	std::mutex										m_tLock;		///< one batch at a time per handle
 	mgpu_sharded_stats								m_tStats {};
@@ -93,7 +95,8 @@ public:
 
 	// host arrays reused from call to call (their pages stay mapped)
 	std::vector<mgpu_query>			m_dQueries;
-	std::vector<int64_t>			m_dWordDocs;
+	std::vector<int64_t>			m_dWordDocs, m_dWordHits;
+	std::vector<int32_t>			m_dWordIds;
 	std::vector<PlannedQuery_t>		m_dTemplate;
 
 	// exchange buffers on shard 0's GPU (grow-only)
@@ -142,11 +145,22 @@ public:
 			uBase += p->m_tDev.m_uRows;
 			m_iTotalDocs += (int64_t)p->m_tHdr.m_iTotalDocuments;
 			for ( const auto & kv : p->m_hTerms )
-				m_hGlobalDocs[kv.first] += kv.second.m_iDocs;
+			{
+				GlobalWord_t & t = m_hGlobalDocs[kv.first];
+				if ( t.m_iId<0 )
+					t.m_iId = (int32_t)m_hGlobalDocs.size()-1;
+				t.m_iDocs += kv.second.m_iDocs;
+				t.m_iHits += kv.second.m_iHits;
+			}
 			m_bSameDevice = m_bSameDevice && dDevices[s]==dDevices[0];
 			m_dShards.push_back ( std::move ( p ) );
 		}
 		m_dBase.push_back ( (uint32_t)std::min<uint64_t> ( uBase, 0xFFFFFFFFull ) );
+		// every shard's dictionary entry per global keyword id: the shard threads bind a batch's keywords by id, not by name
+		m_dTermOfId.assign ( nShards, std::vector<const TermInfo_t*> ( m_hGlobalDocs.size(), nullptr ) );
+		for ( int s=0; s<nShards; ++s )
+			for ( const auto & kv : m_dShards[s]->m_hTerms )
+				m_dTermOfId[s][m_hGlobalDocs[kv.first].m_iId] = &kv.second;
 		bool bDistinct = true;
 		for ( int s=0; s<nShards; ++s )
 			for ( int t=0; t<s; ++t )
@@ -195,6 +209,10 @@ public:
 			dWordOff[i+1] = dWordOff[i] + (size_t)std::max ( dQueries[i].n_words, 0 );
 		std::vector<int64_t> & dWordDocs = m_dWordDocs;
 		dWordDocs.resize ( dWordOff[nQueries] );
+		std::vector<int32_t> & dWordIds = m_dWordIds;
+		dWordIds.resize ( dWordOff[nQueries] );
+		std::vector<int64_t> & dWordHits = m_dWordHits;
+		dWordHits.resize ( dWordOff[nQueries] );
 		std::vector<PlannedQuery_t> & dTemplate = m_dTemplate;
 		dTemplate.clear();
 		dTemplate.resize ( nQueries );
@@ -210,23 +228,32 @@ public:
 					mgpu_query & q = dQueries[i];
 					if ( !q.total_docs )
 						q.total_docs = m_iTotalDocs;
-					if ( !q.word_docs && q.words && q.n_words>0 )
+					if ( q.words && q.n_words>0 )
 					{
-						int64_t * pDocs = dWordDocs.data()+dWordOff[i];
+						// one lookup per keyword for the whole handle: statistics of the whole index, and the id the shards bind it by
+						int64_t * pDocs = dWordDocs.data()+dWordOff[i], * pHits = dWordHits.data()+dWordOff[i];
+						int32_t * pIds = dWordIds.data()+dWordOff[i];
 						for ( int w=0; w<q.n_words; ++w )
 						{
-							int64_t iDocs = -1;
+							pDocs[w] = -1;
+							pHits[w] = 0;
+							pIds[w] = -1;
 							if ( q.words[w].word )
 							{
 								auto it = m_hGlobalDocs.find ( q.words[w].word );
-								iDocs = it==m_hGlobalDocs.end() ? 0 : it->second;
+								pDocs[w] = it==m_hGlobalDocs.end() ? 0 : it->second.m_iDocs;
+								pHits[w] = it==m_hGlobalDocs.end() ? 0 : it->second.m_iHits;
+								pIds[w] = it==m_hGlobalDocs.end() ? -1 : it->second.m_iId;
 							}
-							pDocs[w] = iDocs;
 						}
-						q.word_docs = pDocs;
+						if ( !q.word_docs )
+							q.word_docs = pDocs;
 					}
 					q.shard_of_global = 1;
 					PlanQuery ( *m_dShards[0], q, dTemplate[i] );
+					// the keywords' statistics reported with the result: the whole index's (the shards' dictionaries summed at open)
+					for ( size_t w=0; w<dTemplate[i].m_dWordStats.size(); ++w )
+						dTemplate[i].m_dWordStats[w] = mgpu_wordstat { std::max<int64_t> ( dWordDocs[dWordOff[i]+w], 0 ), dWordHits[dWordOff[i]+w] };
 				}
 			};
 			if ( nThreads<=1 )
@@ -271,7 +298,8 @@ public:
 			Index_c * pIndex = m_dShards[s].get();
 			dBatches[s].reset ( new Batch_c );
 			Batch_c & b = *dBatches[s];
-			int iRes = b.Prepare ( pIndex, dQueries.data(), nQueries, &dTemplate, nBindThreads, pIndex->m_tOpt.m_bEagerHot!=0 );
+			int iRes = b.Prepare ( pIndex, dQueries.data(), nQueries, &dTemplate, nBindThreads, pIndex->m_tOpt.m_bEagerHot!=0,
+				m_dWordIds.data(), dWordOff.data(), m_dTermOfId[s].data() );
 			if ( iRes==MGPU_OK )
 				iRes = b.Run();
 			if ( iRes==MGPU_OK )
@@ -411,15 +439,7 @@ public:
 			r.total_found = 0;
 			if ( r.word_stats )
 				for ( size_t w=0; w<p.m_dWordStats.size(); ++w )
-				{
-					mgpu_wordstat t { 0, 0 };
-					for ( int s=0; s<nShards; ++s )
-					{
-						t.docs += dBatches[s]->m_dPlans[i].m_dWordStats[w].docs;
-						t.hits += dBatches[s]->m_dPlans[i].m_dWordStats[w].hits;
-					}
-					r.word_stats[w] = t;
-				}
+					r.word_stats[w] = p.m_dWordStats[w];
 			if ( p.m_iStatus!=MGPU_OK || !p.m_tDev.m_nOps )
 				continue;
 			r.n_matches = std::min ( dCount[i], p.m_tDev.m_iMaxMatches );
@@ -552,7 +572,7 @@ int mgpu_sharded_word_docs ( const mgpu_sharded * sh, const char * word, int64_t
 	if ( it==sh->m_t.m_hGlobalDocs.end() )
 		return 0;
 	if ( docs )
-		*docs = it->second;
+		*docs = it->second.m_iDocs;
 	return 1;
 }
 
