@@ -172,13 +172,13 @@ struct DevNWay_t
 	uint8_t		m_dCount[MAX_PHRASE_WORDS];	///< quorum: how often the query repeats the keyword (ExtQuorum_c::TermTuple_t::m_iCount)
 };
 
-struct DevQuery_t
+/// A device query = core + extension. The core (1.4 KB: keywords, program, weights, scalars) is what every query has; the extension
+/// (1.9 KB: filters, sort keys, hit-level nodes) only exists for queries that use any of it (m_iExt >= 0) and travels in an array of its
+/// own, so a 10k-query batch of plain boolean queries moves 14 MB of descriptors instead of 33 MB (host passes, upload, per-item loads).
+struct DevQueryCore_t
 {
 	DevLeaf_t	m_dLeaves[MAX_LEAVES];
 	DevOp_t		m_dOps[MAX_OPS];
-	DevFilter_t	m_dFilters[MAX_FILTERS];
-	DevSortKey_t m_dSortKeys[5];
-	DevNWay_t	m_dNWay[MAX_NWAY];
 	int32_t		m_dWeights[MAX_FIELDS];	///< bound field weights
 	int32_t		m_nLeaves;
 	int32_t		m_nOps;
@@ -198,16 +198,48 @@ struct DevQuery_t
 	uint32_t	m_uPreMask;				///< leaves whose op scatters unconditionally (SET/OR/ANDNOT/MAYBE): decoded in the tile predecode phase
 	uint32_t	m_uOrigMask;			///< leaves whose op can bring a document into the result (SET / OR operands)
 	int32_t		m_bOrigHot;				///< one of those is a hot (dense) keyword: every mini-tile has to be visited
-	int32_t		m_iPad;
+	int32_t		m_iExt;					///< index of the query's DevQueryExt_t in the batch's extension array; -1 = none (no filters, sort keys, hit-level nodes)
 	int32_t		m_iMaxQpos;				///< ExtRanker_c::m_iMaxQpos (SPH04 exact-hit test)
 	int32_t		m_nQwords;				///< ExtRanker_c::m_iQwords (MATCHANY phrase factor)
 	int32_t		m_bPureOr;				///< the program is SET, OR, OR... over keywords (single level): eligible for the register path of stream_kernel
-	int32_t		m_iPad2;
+	int32_t		m_bWeightKey;			///< one of the sort keys is the weight (host routing)
 	int32_t		m_nGroups;				///< >0: the program is an OR of AND groups (DNF; 1 = pure AND): op ranges below
 	uint8_t		m_dGroupOp0[MAX_GROUPS];
 	uint8_t		m_dGroupOps[MAX_GROUPS];
 	int32_t		m_iDriverLeaf;			///< pure AND program opened by this (sparse) keyword: tiles without its postings are skipped; -1 = none
 };
+
+struct DevQueryExt_t
+{
+	DevFilter_t	m_dFilters[MAX_FILTERS];
+	DevSortKey_t m_dSortKeys[5];
+	DevNWay_t	m_dNWay[MAX_NWAY];
+};
+
+/// the whole query as the planner builds it and as the kernels hold it in shared memory
+struct DevQuery_t : DevQueryCore_t, DevQueryExt_t
+{
+};
+
+#ifdef __CUDACC__
+/// loads query iQuery of the batch into shared memory: the core, and the extension if the query has one (its counts are zero otherwise,
+/// so nothing reads the extension's bytes). All nThreads threads of the CTA call it; the caller synchronises.
+__device__ __forceinline__ void LoadQuery ( DevQuery_t & tDst, const DevQueryCore_t * pQueries, const DevQueryExt_t * pExt, uint32_t iQuery, int tid, int nThreads )
+{
+	const uint32_t * pSrc = reinterpret_cast<const uint32_t *>( pQueries+iQuery );
+	uint32_t * pDst = reinterpret_cast<uint32_t *>( static_cast<DevQueryCore_t *>( &tDst ) );
+	for ( int i=tid; i<(int)( sizeof(DevQueryCore_t)/4 ); i+=nThreads )
+		pDst[i] = pSrc[i];
+	const int iExt = pQueries[iQuery].m_iExt;
+	if ( iExt>=0 )
+	{
+		const uint32_t * pSrcE = reinterpret_cast<const uint32_t *>( pExt+iExt );
+		uint32_t * pDstE = reinterpret_cast<uint32_t *>( static_cast<DevQueryExt_t *>( &tDst ) );
+		for ( int i=tid; i<(int)( sizeof(DevQueryExt_t)/4 ); i+=nThreads )
+			pDstE[i] = pSrcE[i];
+	}
+}
+#endif
 
 /// one predecoded posting of the tile predecode phase
 struct PreEntry_t
@@ -243,7 +275,8 @@ struct DevItemOut_t
 struct EvalParams_t
 {
 	DevIndex_t				m_tIndex;
-	const DevQuery_t *		m_pQueries;
+	const DevQueryCore_t *	m_pQueries;
+	const DevQueryExt_t *	m_pQueryExt;		///< extensions of the queries with m_iExt >= 0
 	const DevWorkItem_t *	m_pItems;
 	int32_t					m_nItems;
 	int32_t					m_iPoolCap;		///< keys per pool buffer (per CTA, two buffers)
@@ -289,7 +322,8 @@ struct HotDecodeParams_t
 struct MergeParams_t
 {
 	DevIndex_t				m_tIndex;
-	const DevQuery_t *		m_pQueries;
+	const DevQueryCore_t *	m_pQueries;
+	const DevQueryExt_t *	m_pQueryExt;		///< extensions of the queries with m_iExt >= 0
 	int32_t					m_nQueries;
 	int32_t					m_iKMax;
 	const Key128_t *		m_pItemKeys;

@@ -809,10 +809,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) eval_kernel ( EvalParams_t P,
 
 		// stage the query descriptor
 		{
-			const uint32_t * pSrc = reinterpret_cast<const uint32_t *>( P.m_pQueries+tItem.m_uQuery );
-			uint32_t * pDst = reinterpret_cast<uint32_t *>( &S.m_tQ );
-			for ( int i=tid; i<(int)( sizeof(DevQuery_t)/4 ); i+=EVAL_THREADS )
-				pDst[i] = pSrc[i];
+			LoadQuery ( S.m_tQ, P.m_pQueries, P.m_pQueryExt, tItem.m_uQuery, tid, EVAL_THREADS );
 		}
 		if ( tid==0 )
 		{
@@ -1591,10 +1588,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) and_kernel ( EvalParams_t 
 			break;
 		const DevWorkItem_t tItem = P.m_pItems[iItem];
 		{
-			const uint32_t * pSrc = reinterpret_cast<const uint32_t *>( P.m_pQueries+tItem.m_uQuery );
-			uint32_t * pDst = reinterpret_cast<uint32_t *>( &S.m_tQ );
-			for ( int i=tid; i<(int)( sizeof(DevQuery_t)/4 ); i+=EVAL_THREADS )
-				pDst[i] = pSrc[i];
+			LoadQuery ( S.m_tQ, P.m_pQueries, P.m_pQueryExt, tItem.m_uQuery, tid, EVAL_THREADS );
 		}
 		if ( tid==0 )
 		{
@@ -1837,7 +1831,7 @@ __global__ void __launch_bounds__ ( 256 ) merge_kernel ( MergeParams_t P )
 
 	for ( int iQuery=blockIdx.x; iQuery<P.m_nQueries; iQuery+=gridDim.x )
 	{
-		const DevQuery_t & q = P.m_pQueries[iQuery];
+		const DevQueryCore_t & q = P.m_pQueries[iQuery];
 		const int iK = q.m_iMaxMatches;
 		Key128_t * pA = P.m_pScratch + (size_t)iQuery*P.m_iScratchStride;	// [0, stride/2) gather, [stride/2, stride) select output
 		const int iHalf = P.m_iScratchStride/2;

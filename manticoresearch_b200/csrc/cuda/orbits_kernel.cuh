@@ -154,10 +154,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 			break;
 		const DevWorkItem_t tItem = P.m_pItems[iItem];
 		{
-			const uint32_t * pSrc = reinterpret_cast<const uint32_t *>( P.m_pQueries+tItem.m_uQuery );
-			uint32_t * pDst = reinterpret_cast<uint32_t *>( &S.m_tQ );
-			for ( int i=tid; i<(int)( sizeof(DevQuery_t)/4 ); i+=EVAL_THREADS )
-				pDst[i] = pSrc[i];
+			LoadQuery ( S.m_tQ, P.m_pQueries, P.m_pQueryExt, tItem.m_uQuery, tid, EVAL_THREADS );
 		}
 		if ( tid==0 )
 		{

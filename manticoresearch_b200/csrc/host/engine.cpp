@@ -379,6 +379,7 @@ struct Planner_c
 	const Index_c &		m_tIndex;
 	const mgpu_query &	m_q;
 	PlannedQuery_t &	m_tOut;
+	DevQuery_t			m_tFull;			///< the query as built here; Finish() hands the core to m_tOut and the extension to the caller
 	std::vector<PLeaf_t> m_dLeaves;
 	std::vector<PNode_t> m_dNodes;
 	int					m_iError = MGPU_OK;
@@ -533,7 +534,7 @@ struct Planner_c
 	/// an AND chain over the keywords sorted by doc count, then the acceptor over their merged hits
 	int CreateMultiNode ( const mgpu_xqnode & tNode )
 	{
-		DevQuery_t & d = m_tOut.m_tDev;
+		DevQuery_t & d = m_tFull;
 		if ( d.m_nNWay>=MAX_NWAY || tNode.n_words>MAX_PHRASE_WORDS )
 			return Fail ( MGPU_E_UNSUPPORTED );
 		if ( tNode.first_word<0 || tNode.first_word+tNode.n_words>m_q.n_words )
@@ -578,7 +579,7 @@ struct Planner_c
 	/// Children that are phrases, OR groups or other operators are not on the GPU path.
 	int CreateKeywordOpNode ( const mgpu_xqnode & tNode, const int32_t * pChildren, int nChildren )
 	{
-		DevQuery_t & d = m_tOut.m_tDev;
+		DevQuery_t & d = m_tFull;
 		if ( tNode.op!=MGPU_OP_NOTNEAR && nChildren<2 )
 			return -1;	// ("order node requires at least two children" / no phrase node from one child: an empty node)
 		if ( tNode.op==MGPU_OP_NOTNEAR && nChildren!=2 )
@@ -621,7 +622,7 @@ struct Planner_c
 	/// reach the threshold. One quorum node per query on the GPU path.
 	int CreateQuorumNode ( const mgpu_xqnode & tNode )
 	{
-		DevQuery_t & d = m_tOut.m_tDev;
+		DevQuery_t & d = m_tFull;
 		if ( d.m_nNWay>=MAX_NWAY )
 			return Fail ( MGPU_E_UNSUPPORTED );
 		for ( int j=0; j<d.m_nNWay; ++j )
@@ -718,7 +719,7 @@ struct Planner_c
 		case PN_MULTIAND:
 		case PN_NWAY:
 			{
-				const int eNWay = t.m_eKind==PN_NWAY ? m_tOut.m_tDev.m_dNWay[t.m_iNWay].m_eKind : -1;
+				const int eNWay = t.m_eKind==PN_NWAY ? m_tFull.m_dNWay[t.m_iNWay].m_eKind : -1;
 				AddOp ( OP_TERM_SET, iSp, 0, 0, 0, t.m_dLeaves[0], 1 );
 				int iAlive = 1;
 				if ( eNWay==NWAY_NOTNEAR )
@@ -757,12 +758,12 @@ struct Planner_c
 
 	void AddOp ( int eCode, int iDst, int iSrc, int iAliveDst, int iAliveSrc, int iLeaf, int iAliveOut, int iArg=0 )
 	{
-		if ( m_tOut.m_tDev.m_nOps>=MAX_OPS || iAliveOut>250 )
+		if ( m_tFull.m_nOps>=MAX_OPS || iAliveOut>250 )
 		{
 			Fail ( MGPU_E_UNSUPPORTED );
 			return;
 		}
-		DevOp_t & o = m_tOut.m_tDev.m_dOps[m_tOut.m_tDev.m_nOps++];
+		DevOp_t & o = m_tFull.m_dOps[m_tFull.m_nOps++];
 		o.m_eCode = (uint8_t)eCode;
 		o.m_uDst = (uint8_t)iDst;
 		o.m_uSrc = (uint8_t)iSrc;
@@ -775,7 +776,7 @@ struct Planner_c
 
 	int Run()
 	{
-		DevQuery_t & d = m_tOut.m_tDev;
+		DevQuery_t & d = m_tFull;
 		memset ( &d, 0, sizeof(d) );
 		m_tOut.m_dLeafTerms.m_n = m_tOut.m_dLeafWord.m_n = 0;
 		m_tOut.m_dWordStats.assign ( std::max ( m_q.n_words, 0 ), mgpu_wordstat { 0, 0 } );
@@ -1060,10 +1061,18 @@ struct Planner_c
 } // namespace
 
 
-int PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut )
+int PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut, DevQueryExt_t & tExt, bool & bHasExt )
 {
 	Planner_c tPlanner ( tIndex, tQuery, tOut );
 	tOut.m_iStatus = tPlanner.Run();
+	DevQuery_t & tFull = tPlanner.m_tFull;
+	for ( int k=0; k<tFull.m_nSortKeys; ++k )
+		tFull.m_bWeightKey |= tFull.m_dSortKeys[k].m_eKind==1;
+	tFull.m_iExt = -1;
+	tOut.m_tDev = static_cast<const DevQueryCore_t &>( tFull );
+	bHasExt = tOut.m_iStatus==MGPU_OK && ( tFull.m_nFilters>0 || tFull.m_nSortKeys>0 || tFull.m_nNWay>0 );
+	if ( bHasExt )
+		tExt = static_cast<const DevQueryExt_t &>( tFull );
 	return tOut.m_iStatus;
 }
 
@@ -1206,7 +1215,7 @@ static void ParallelFor ( int n, int nThreads, FN && fn )
 }
 
 int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate, int nMaxThreads, bool bEagerHot,
-	const int32_t * pWordIds, const size_t * pWordOff, const TermInfo_t * const * pTermOfId )
+	const int32_t * pWordIds, const size_t * pWordOff, const TermInfo_t * const * pTermOfId, const std::vector<DevQueryExt_t> * pTemplateExt )
 {
 	m_pIndex = pIndex;
 	++pIndex->m_nLiveBatches;
@@ -1231,8 +1240,11 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			nThreads = tOpt.m_iPlanThreads;
 		if ( nMaxThreads>0 )
 			nThreads = std::min ( nThreads, nMaxThreads );
-		auto fnPlan = [&] ( int iFrom, int iTo )
+		// (extensions: collected per thread, numbered in query order afterwards)
+		std::vector<std::vector<std::pair<int,DevQueryExt_t>>> dThreadExt ( std::max ( nThreads, 1 ) );
+		auto fnPlan = [&] ( int iFrom, int iTo, int iThread )
 		{
+			DevQueryExt_t tExt;
 			for ( int i=iFrom; i<iTo; ++i )
 				if ( pTemplate )
 				{
@@ -1240,18 +1252,20 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 					m_dPlans[i] = (*pTemplate)[i];
 					RebindPlan ( *pIndex, pQueries[i], m_dPlans[i], pWordIds ? pWordIds+pWordOff[i] : nullptr, pTermOfId );
 				} else
-					PlanQuery ( *pIndex, pQueries[i], m_dPlans[i] );
+				{
+					bool bHasExt = false;
+					PlanQuery ( *pIndex, pQueries[i], m_dPlans[i], tExt, bHasExt );
+					if ( bHasExt )
+						dThreadExt[iThread].push_back ( { i, tExt } );
+				}
 		};
-		if ( nThreads<=1 )
-			fnPlan ( 0, nQueries );
-		else
-		{
-			std::vector<std::thread> dThreads;
-			for ( int t=0; t<nThreads; ++t )
-				dThreads.emplace_back ( fnPlan, (int)( (int64_t)nQueries*t/nThreads ), (int)( (int64_t)nQueries*( t+1 )/nThreads ) );
-			for ( auto & t : dThreads )
-				t.join();
-		}
+		ParallelFor ( nQueries, nThreads, fnPlan );
+		for ( const auto & dMine : dThreadExt )
+			for ( const auto & t : dMine )
+			{
+				m_dPlans[t.first].m_tDev.m_iExt = (int)m_dExt.size();
+				m_dExt.push_back ( t.second );
+			}
 	}
 	const auto tPlanned = std::chrono::steady_clock::now();
 	const bool bTiming = tOpt.m_bTiming!=0;
@@ -1351,7 +1365,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 					for ( const TermInfo_t * pTerm : p.m_dLeafTerms )
 						if ( pTerm && (int64_t)pTerm->m_iDocs*iHotDiv>=(int64_t)uRows && !__atomic_fetch_add ( &dUse[pTerm->m_iOrdinal], 1, __ATOMIC_RELAXED ) )
 							dMine.push_back ( pTerm );
-					const DevQuery_t & q = p.m_tDev;
+					const DevQueryCore_t & q = p.m_tDev;
 					if ( !bForce || q.m_nGroups<=0 || q.m_bPureOr || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
 						continue;
 					bool bDense = false, bAll = true;
@@ -1457,7 +1471,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	{
 		// intersection kernel: DNF programs (1 group = pure AND) whose every group is led by a sparse keyword
 		const int i = dDocOnly[iDoc];
-		DevQuery_t & q = m_dPlans[i].m_tDev;
+		DevQueryCore_t & q = m_dPlans[i].m_tDev;
 		bool bDnf = q.m_nGroups>0 && !bNoAndKernel;
 		for ( int g=0; g<q.m_nGroups && bDnf; ++g )
 		{
@@ -1467,9 +1481,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		}
 		// pure OR programs under BM25, no dead rows, <= 4 fields, ordered by relevance or by attributes alone (a sort key on the
 		// weight would need the bound inside the key): the bound + exact pass kernel; filters run inside its bound pass
-		bool bWeightKey = false;
-		for ( int k=0; k<q.m_nSortKeys; ++k )
-			bWeightKey |= q.m_dSortKeys[k].m_eKind==1;
+		const bool bWeightKey = q.m_bWeightKey!=0;
 		const bool bBoundBase = q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !bNoOrClass;
 		// OR-of-AND-groups programs (a pure AND is one group) whose multi-keyword groups hold hot keywords only intersect their
 		// presence bitmaps on orbits_kernel instead of walking a driver's doclist block by block
@@ -1658,7 +1670,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		for ( const Part_t & t : dParts )
 		{
 			// (the 3 KB device query itself is copied once, in parallel, straight into the pinned upload buffer below)
-			const DevQuery_t & q = m_dPlans[t.m_iQuery].m_tDev;
+			const DevQueryCore_t & q = m_dPlans[t.m_iQuery].m_tDev;
 			DevSlot_t tSlot { t.m_iQuery, (int)m_dItems.size(), t.m_nParts };
 			const int iDevQuery = (int)m_dSlots.size();
 			int64_t nUnits = nTiles, iUnit = TILE_W, iLimit = uRows;
@@ -1761,7 +1773,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 	{
 		// device queries: gathered by a few threads into the index's pinned upload buffer (grow-only, free again once this call's
 		// copy has completed below), then one DMA
-		DevQuery_t * pStage = (DevQuery_t *)pIndex->PinnedUpload ( (size_t)nDevQ*sizeof(DevQuery_t) );
+		DevQueryCore_t * pStage = (DevQueryCore_t *)pIndex->PinnedUpload ( (size_t)nDevQ*sizeof(DevQueryCore_t) );
 		if ( !pStage )
 		{
 			m_sError = "cudaHostAlloc failed";
@@ -1771,7 +1783,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		{
 			for ( int i=iFrom; i<iTo; ++i )
 			{
-				memcpy ( pStage+i, &m_dPlans[m_dSlots[i].m_iQuery].m_tDev, sizeof(DevQuery_t) );
+				memcpy ( pStage+i, &m_dPlans[m_dSlots[i].m_iQuery].m_tDev, sizeof(DevQueryCore_t) );
 				pStage[i].m_iFirstItem = m_dSlots[i].m_iFirstItem;
 				pStage[i].m_nItems = m_dSlots[i].m_nItems;
 			}
@@ -1789,7 +1801,15 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			for ( auto & t : dThreads )
 				t.join();
 		}
-		CUDA_TRY ( cudaMemcpyAsync ( m_dQ.m_p, pStage, (size_t)nDevQ*sizeof(DevQuery_t), cudaMemcpyHostToDevice, s ), m_sError );
+		CUDA_TRY ( cudaMemcpyAsync ( m_dQ.m_p, pStage, (size_t)nDevQ*sizeof(DevQueryCore_t), cudaMemcpyHostToDevice, s ), m_sError );
+		// the few queries with filters / sort keys / hit-level nodes: their extensions (a sharded call: the template's, shared by the shards)
+		const std::vector<DevQueryExt_t> & dExt = pTemplateExt ? *pTemplateExt : m_dExt;
+		if ( !dExt.empty() )
+		{
+			CUDA_TRY ( m_dExtDev.AllocAsync ( dExt.size(), s ), m_sError );
+			CUDA_TRY ( cudaMemcpyAsync ( m_dExtDev.m_p, dExt.data(), dExt.size()*sizeof(DevQueryExt_t), cudaMemcpyHostToDevice, s ), m_sError );
+		}
+		m_tStats.h2d_bytes = (int64_t)dExt.size()*sizeof(DevQueryExt_t);
 	}
 	CUDA_TRY ( cudaMemcpyAsync ( m_dI.m_p, m_dItems.data(), (size_t)nItems*sizeof(DevWorkItem_t), cudaMemcpyHostToDevice, s ), m_sError );
 	CUDA_TRY ( cudaMemcpyAsync ( m_dOutSlot.m_p, m_dDevToQuery.data(), (size_t)nDevQ*4, cudaMemcpyHostToDevice, s ), m_sError );
@@ -1798,7 +1818,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 			CUDA_TRY ( cudaMemcpyAsync ( m_dOrder[i].m_p, m_dItemOrder[i].data(), m_dItemOrder[i].size()*4, cudaMemcpyHostToDevice, s ), m_sError );
 	CUDA_TRY ( cudaStreamSynchronize ( s ), m_sError );
 	fnMark ( "upload + sync" );
-	m_tStats.h2d_bytes = (int64_t)nDevQ*sizeof(DevQuery_t) + (int64_t)nItems*sizeof(DevWorkItem_t);
+	m_tStats.h2d_bytes += (int64_t)nDevQ*sizeof(DevQueryCore_t) + (int64_t)nItems*sizeof(DevWorkItem_t);
 	m_tStats.work_items = nItems;
 
 	for ( int c=0; c<NUM_CLASSES; ++c )
@@ -1944,6 +1964,7 @@ int Batch_c::Run()
 		EvalParams_t P {};
 		P.m_tIndex = pIndex->m_tDev;
 		P.m_pQueries = m_dQ.m_p;
+		P.m_pQueryExt = m_dExtDev.m_p;
 		P.m_pItems = m_dI.m_p + iFirst;
 		P.m_nItems = nClassItems;
 		P.m_iPoolCap = m_iPoolCap;
@@ -1978,6 +1999,7 @@ int Batch_c::Run()
 	MergeParams_t M {};
 	M.m_tIndex = pIndex->m_tDev;
 	M.m_pQueries = m_dQ.m_p;
+	M.m_pQueryExt = m_dExtDev.m_p;
 	M.m_nQueries = m_nDevQueries;
 	M.m_iKMax = m_iKMax;
 	M.m_pItemKeys = m_dItemKeys.m_p;

@@ -193,7 +193,7 @@ struct PlannedQuery_t
 {
 	PlannedQuery_t() {}						///< (user-provided on purpose: a batch's plan array is not zeroed twice; the planner clears m_tDev itself)
 	int				m_iStatus = MGPU_OK;
-	DevQuery_t		m_tDev;
+	DevQueryCore_t	m_tDev;					///< (filters, sort keys and hit-level nodes: m_tDev.m_iExt into the batch's extension array)
 	int				m_nStack = 1;
 	int64_t			m_iCost = 0;			///< sum of df over leaves (postings)
 	int64_t			m_iAlgBytes = 0;		///< SURVEY 8(d) algorithmic bytes (doclists + skiplists)
@@ -205,7 +205,8 @@ struct PlannedQuery_t
 	bool			m_bFirstIntKeyDesc = false;
 };
 
-int		PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut );
+/// tExt: the query's filters / sort keys / hit-level nodes; returns through bHasExt whether it has any (the caller then stores tExt and sets tOut.m_tDev.m_iExt)
+int		PlanQuery ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tOut, DevQueryExt_t & tExt, bool & bHasExt );
 /// pWordIds / pTermOfId (sharded handle): the query's keywords as ids of the handle's global keyword table and this shard's dictionary
 /// entry per id; without them the keywords are looked up by name
 void	RebindPlan ( const Index_c & tIndex, const mgpu_query & tQuery, PlannedQuery_t & tPlan, const int32_t * pWordIds=nullptr, const TermInfo_t * const * pTermOfId=nullptr );
@@ -235,7 +236,9 @@ public:
 	int		m_iPoolCap = 0;
 	int		m_iScratchStride = 0;
 
-	DevBuf_T<DevQuery_t>	m_dQ;
+	DevBuf_T<DevQueryCore_t>	m_dQ;
+	std::vector<DevQueryExt_t>	m_dExt;		///< extensions of this batch's own plans (a sharded call shares the template's)
+	DevBuf_T<DevQueryExt_t>	m_dExtDev;
 	DevBuf_T<DevWorkItem_t>	m_dI;
 	DevBuf_T<int32_t>		m_dCounter;
 	std::vector<int32_t>	m_dItemOrder[2];	///< classes 5, 6: items in rowid-range-major order (index relative to the class's first item)
@@ -283,7 +286,8 @@ public:
 	/// bEagerHot: the caller runs the batch right away under the same lock (mgpu_search_batch, the sharded call): K0 starts inside Prepare
 	/// pWordIds [ pWordOff[i] + word ] / pTermOfId: see RebindPlan
 	int		Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueries, const std::vector<PlannedQuery_t> * pTemplate=nullptr, int nMaxThreads=0, bool bEagerHot=false,
-				const int32_t * pWordIds=nullptr, const size_t * pWordOff=nullptr, const TermInfo_t * const * pTermOfId=nullptr );
+				const int32_t * pWordIds=nullptr, const size_t * pWordOff=nullptr, const TermInfo_t * const * pTermOfId=nullptr,
+				const std::vector<DevQueryExt_t> * pTemplateExt=nullptr );
 	int		BuildHotStore ( cudaStream_t tStream );
 	int		Run();
 	int		Sync();

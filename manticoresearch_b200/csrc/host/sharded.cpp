@@ -98,6 +98,7 @@ public:
 	std::vector<int64_t>			m_dWordDocs, m_dWordHits;
 	std::vector<int32_t>			m_dWordIds;
 	std::vector<PlannedQuery_t>		m_dTemplate;
+	std::vector<DevQueryExt_t>		m_dTemplateExt;
 
 	// exchange buffers on shard 0's GPU (grow-only)
 	DevBuf_T<Key128_t>		m_dGatherKeys, m_dMergeScratch, m_dOutKeys;
@@ -221,8 +222,10 @@ public:
 			nThreads = std::max ( 1, std::min ( nThreads, nQueries/256 ) );
 			if ( m_dShards[0]->m_tOpt.m_iPlanThreads>0 )
 				nThreads = m_dShards[0]->m_tOpt.m_iPlanThreads;
-			auto fnPlan = [&] ( int iFrom, int iTo )
+			std::vector<std::vector<std::pair<int,DevQueryExt_t>>> dThreadExt ( std::max ( nThreads, 1 ) );
+			auto fnPlan = [&] ( int iFrom, int iTo, int iThread )
 			{
+				DevQueryExt_t tExt;
 				for ( int i=iFrom; i<iTo; ++i )
 				{
 					mgpu_query & q = dQueries[i];
@@ -250,22 +253,33 @@ public:
 							q.word_docs = pDocs;
 					}
 					q.shard_of_global = 1;
-					PlanQuery ( *m_dShards[0], q, dTemplate[i] );
+					bool bHasExt = false;
+					PlanQuery ( *m_dShards[0], q, dTemplate[i], tExt, bHasExt );
+					if ( bHasExt )
+						dThreadExt[iThread].push_back ( { i, tExt } );
 					// the keywords' statistics reported with the result: the whole index's (the shards' dictionaries summed at open)
 					for ( size_t w=0; w<dTemplate[i].m_dWordStats.size(); ++w )
 						dTemplate[i].m_dWordStats[w] = mgpu_wordstat { std::max<int64_t> ( dWordDocs[dWordOff[i]+w], 0 ), dWordHits[dWordOff[i]+w] };
 				}
 			};
 			if ( nThreads<=1 )
-				fnPlan ( 0, nQueries );
+				fnPlan ( 0, nQueries, 0 );
 			else
 			{
 				std::vector<std::thread> dThreads;
 				for ( int t=0; t<nThreads; ++t )
-					dThreads.emplace_back ( fnPlan, (int)( (int64_t)nQueries*t/nThreads ), (int)( (int64_t)nQueries*( t+1 )/nThreads ) );
+					dThreads.emplace_back ( fnPlan, (int)( (int64_t)nQueries*t/nThreads ), (int)( (int64_t)nQueries*( t+1 )/nThreads ), t );
 				for ( auto & t : dThreads )
 					t.join();
 			}
+			// the queries' extensions (filters, sort keys, hit-level nodes), numbered in query order; every shard uploads this array
+			m_dTemplateExt.clear();
+			for ( const auto & dMine : dThreadExt )
+				for ( const auto & t : dMine )
+				{
+					dTemplate[t.first].m_tDev.m_iExt = (int)m_dTemplateExt.size();
+					m_dTemplateExt.push_back ( t.second );
+				}
 		}
 		const auto tPlanned = std::chrono::steady_clock::now();
 		m_tStats.host_plan_ms = fnMs ( tStart, tPlanned );
@@ -299,7 +313,7 @@ public:
 			dBatches[s].reset ( new Batch_c );
 			Batch_c & b = *dBatches[s];
 			int iRes = b.Prepare ( pIndex, dQueries.data(), nQueries, &dTemplate, nBindThreads, pIndex->m_tOpt.m_bEagerHot!=0,
-				m_dWordIds.data(), dWordOff.data(), m_dTermOfId[s].data() );
+				m_dWordIds.data(), dWordOff.data(), m_dTermOfId[s].data(), &m_dTemplateExt );
 			if ( iRes==MGPU_OK )
 				iRes = b.Run();
 			if ( iRes==MGPU_OK )
