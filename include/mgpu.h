@@ -186,7 +186,7 @@ int				mgpu_index_close ( mgpu_index * idx );
 int				mgpu_index_set_stream ( mgpu_index * idx, void * cuda_stream );
 /* Engine options of this handle, set once after open (the library never reads tuning from the environment; searchd would map
    its own config keys here, cf. CSphConfigSection in src/sphinxutils.h). Names: "plan_threads", "timing", "hot_store", "hot_div", "hot_min_uses",
-   "hot_gb", "or_range_tiles", "dnf_pct", "stats", and the A/B switches "eager_hot", "force_hot", "or_bits", "bits_dnf", "bits_dnf_div", "or_class", "dnf_class", "and_kernel", "dnf", "chain",
+   "hot_gb", "or_range_tiles", "dnf_pct", "stats", and the A/B switches "eager_hot", "force_hot", "group_neg", "or_bits", "bits_dnf", "bits_dnf_div", "or_class", "dnf_class", "and_kernel", "dnf", "chain",
    "reg_or", "jump" (0/1). Returns MGPU_E_BAD_QUERY for an unknown name or a value out of range. */
 int				mgpu_index_set_option ( mgpu_index * idx, const char * name, int64_t value );
 const char *	mgpu_last_error ( const mgpu_index * idx );   /* idx may be NULL: last open error */

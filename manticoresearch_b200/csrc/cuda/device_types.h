@@ -203,6 +203,8 @@ struct DevQueryCore_t
 	int32_t		m_nQwords;				///< ExtRanker_c::m_iQwords (MATCHANY phrase factor)
 	int32_t		m_bPureOr;				///< the program is SET, OR, OR... over keywords (single level): eligible for the register path of stream_kernel
 	int32_t		m_bWeightKey;			///< one of the sort keys is the weight (host routing)
+	int32_t		m_bGroupNeg;			///< the (single) AND group ends in TERM_ANDNOT ops: `a b -c` (and_kernel rejects candidates that hold them)
+	int32_t		m_iPad;
 	int32_t		m_nGroups;				///< >0: the program is an OR of AND groups (DNF; 1 = pure AND): op ranges below
 	uint8_t		m_dGroupOp0[MAX_GROUPS];
 	uint8_t		m_dGroupOps[MAX_GROUPS];

@@ -1541,6 +1541,13 @@ __device__ __forceinline__ bool ProbeGroup ( const DevIndex_t & tIdx, const DevH
 		uint32_t uHits;
 		uint64_t uHitpos;
 		const uint32_t uF = WarpProbeKeyword<HITS> ( tIdx, tHot, tLeaf, uRowid, bActive, S, iWarp, iLane, uHits, uHitpos );
+		if ( q.m_dOps[iOp].m_eCode==OP_TERM_ANDNOT )
+		{
+			// `a b -c`: ExtAndNot_c keeps the left side's documents that the right side does not hold, with the left side's weight and fields
+			// (src/searchnode.cpp:3618-3706)
+			bActive = bActive && !uF;
+			continue;
+		}
 		if ( bActive )
 		{
 			if ( uF )

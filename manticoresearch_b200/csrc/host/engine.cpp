@@ -903,6 +903,18 @@ struct Planner_c
 				int j = i+1;
 				while ( j<d.m_nOps && d.m_dOps[j].m_eCode==OP_TERM_AND && d.m_dOps[j].m_uDst==iDst )
 					++j;
+				// `a b -c -d`: negated keywords behind the group, if they end the whole program (one group; and_kernel probes and rejects)
+				if ( i==0 && iDst==0 && j<d.m_nOps && d.m_dOps[j].m_eCode==OP_TERM_ANDNOT && m_tIndex.m_tOpt.m_bGroupNeg )
+				{
+					int k = j;
+					while ( k<d.m_nOps && d.m_dOps[k].m_eCode==OP_TERM_ANDNOT && d.m_dOps[k].m_uDst==0 )
+						++k;
+					if ( k==d.m_nOps )
+					{
+						d.m_bGroupNeg = 1;
+						j = k;
+					}
+				}
 				d.m_dGroupOp0[nGroups] = (uint8_t)i;
 				d.m_dGroupOps[nGroups] = (uint8_t)( j-i );
 				++nGroups;
@@ -932,6 +944,12 @@ struct Planner_c
 			bool bAnyMulti = false;
 			for ( int g=0; g<nGroups; ++g )
 				bAnyMulti |= d.m_dGroupOps[g]>1;
+			if ( d.m_bGroupNeg && ( !bOk || nGroups!=1 || d.m_bNeedHits ) )
+			{
+				// (hit-consuming programs: the right side of an ANDNOT never emits hits; they stay on dense tiles)
+				bOk = false;
+				d.m_bGroupNeg = 0;
+			}
 			d.m_nGroups = ( bOk && bAnyMulti && m_tIndex.m_tOpt.m_bDnf ) ? nGroups : ( d.m_iDriverLeaf>=0 ? 1 : 0 );
 			if ( d.m_nGroups==1 && d.m_iDriverLeaf>=0 )
 			{
@@ -1135,6 +1153,7 @@ bool EngineOptions_t::Set ( const char * szName, int64_t iValue )
 		{ "or_range_tiles",	&EngineOptions_t::m_iOrRangeTiles,	1, 1<<20 },
 		{ "dnf_pct",		&EngineOptions_t::m_iDnfPct,		1, 100 },
 		{ "eager_hot",		&EngineOptions_t::m_bEagerHot,		0, 1 },
+		{ "group_neg",		&EngineOptions_t::m_bGroupNeg,		0, 1 },
 		{ "force_hot",		&EngineOptions_t::m_bForceHot,		0, 1 },
 		{ "or_bits",		&EngineOptions_t::m_bOrBits,		0, 1 },
 		{ "bits_dnf",		&EngineOptions_t::m_bBitsDnf,		0, 1 },
@@ -1366,7 +1385,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 						if ( pTerm && (int64_t)pTerm->m_iDocs*iHotDiv>=(int64_t)uRows && !__atomic_fetch_add ( &dUse[pTerm->m_iOrdinal], 1, __ATOMIC_RELAXED ) )
 							dMine.push_back ( pTerm );
 					const DevQueryCore_t & q = p.m_tDev;
-					if ( !bForce || q.m_nGroups<=0 || q.m_bPureOr || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
+					if ( !bForce || q.m_nGroups<=0 || q.m_bPureOr || q.m_bGroupNeg || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
 						continue;
 					bool bDense = false, bAll = true;
 					for ( int g=0; g<q.m_nGroups; ++g )
@@ -1485,7 +1504,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		const bool bBoundBase = q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !bNoOrClass;
 		// OR-of-AND-groups programs (a pure AND is one group) whose multi-keyword groups hold hot keywords only intersect their
 		// presence bitmaps on orbits_kernel instead of walking a driver's doclist block by block
-		bool bBitsDnf = m_iOrMode==3 && tOpt.m_bBitsDnf && bBoundBase && !q.m_bPureOr && q.m_nGroups>0 && !q.m_nFilters && !q.m_nSortKeys;
+		bool bBitsDnf = m_iOrMode==3 && tOpt.m_bBitsDnf && bBoundBase && !q.m_bPureOr && q.m_nGroups>0 && !q.m_bGroupNeg && !q.m_nFilters && !q.m_nSortKeys;
 		for ( int g=0; g<q.m_nGroups && bBitsDnf; ++g )
 			if ( q.m_dGroupOps[g]>1 )
 			{
@@ -1510,7 +1529,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		// ... and the same passes with run-time options (class 6): pure OR programs with filters / attribute sort keys, and
 		// OR-of-AND-groups programs (a dense driver kept them off the intersection kernel) whose multi-keyword groups hold at most
 		// one keyword outside the dense store
-		bool bHotDnf = bBoundOk && !bOrClass && ( q.m_bPureOr || q.m_nGroups>0 ) && !bNoDnfClass;
+		bool bHotDnf = bBoundOk && !bOrClass && ( q.m_bPureOr || q.m_nGroups>0 ) && !q.m_bGroupNeg && !bNoDnfClass;
 		if ( bHotDnf && !q.m_bPureOr )
 			for ( int g=0; g<q.m_nGroups && bHotDnf; ++g )
 			{
