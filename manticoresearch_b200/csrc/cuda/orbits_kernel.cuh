@@ -209,10 +209,12 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 					const int l = q.m_dOps[iOp].m_uLeaf;
 					const DevLeaf_t & tLeaf = q.m_dLeaves[l];
 					const float fIDF = tLeaf.m_fIDF;
+					// a negated keyword at the end of an AND group (`a b -c`): rows that hold it leave the unit, it adds no weight (flag 2)
+					const bool bNegOp = q.m_dOps[iOp].m_eCode==OP_TERM_ANDNOT;
 					// tf < 1: the keyword adds less than idf when it sits on the row, and nothing above 0 when idf <= 0
-					iUbUnit += fIDF>0.0f ? (int)ceilf ( __fmul_rn ( fminf ( fIDF, 1.0f ), 64000.0f ) )+1 : 0;
+					iUbUnit += ( fIDF>0.0f && !bNegOp ) ? (int)ceilf ( __fmul_rn ( fminf ( fIDF, 1.0f ), 64000.0f ) )+1 : 0;
 					S.m_dOpPtr[iOp] = nullptr;
-					S.m_dOpLast[iOp] = ( iOp==iOp0+nUnitOps-1 ) ? 1 : 0;
+					S.m_dOpLast[iOp] = (uint8_t)( ( ( iOp==iOp0+nUnitOps-1 ) ? 1 : 0 ) | ( bNegOp ? 2 : 0 ) );
 					if ( tLeaf.m_iHot<0 )
 					{
 						// (a single keyword outside the hot store: its postings come from the decoded list)
@@ -251,7 +253,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 				{
 					const DevLeaf_t & tLeaf = q.m_dLeaves[q.m_dOps[iOp].m_uLeaf];
 					S.m_dBitPtr[nMem] = P.m_tHot.m_pBits + (size_t)tLeaf.m_iHot*P.m_tHot.m_nBitFields*iBitStride;
-					S.m_dBitFields[nMem] = ( tLeaf.m_uQueriedFields & uIndexFields & 255u ) | ( ( iOp==dUnitOp0[u]+dUnitOps[u]-1 ) ? 256u : 0u );
+					S.m_dBitFields[nMem] = ( tLeaf.m_uQueriedFields & uIndexFields & 255u ) | ( ( iOp==dUnitOp0[u]+dUnitOps[u]-1 ) ? 256u : 0u )
+						| ( q.m_dOps[iOp].m_eCode==OP_TERM_ANDNOT ? 512u : 0u );
 					++nMem;
 				}
 			}
@@ -392,7 +395,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 						const uint32_t uHits = dRaw[i] & 255u;
 						const DevLeaf_t & tLeaf = q.m_dLeaves[S.m_dHotLeaf[h0+i]];
 						const uint32_t uFields = ( dRaw[i]>>8 ) & tLeaf.m_uQueriedFields;
-						if ( !uHits || !uFields )
+						if ( S.m_dHotLast[h0+i] & 2 )
+						{
+							if ( uHits && uFields )
+								bAll = false;	// the row holds a negated keyword of the group
+						} else if ( !uHits || !uFields )
 							bAll = false;
 						else
 						{
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 							uFG |= uFields;
 							bFirst = false;
 						}
-						if ( S.m_dHotLast[h0+i] )
+						if ( S.m_dHotLast[h0+i] & 1 )
 						{
 							if ( bAll && !bFirst )
 							{
@@ -450,7 +457,11 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 						const float fHits = __uint2float_rn ( uHits );
 						fBase = uHits<255u ? S.m_dTf[uHits] : __fdiv_rn ( fHits, __fadd_rn ( fHits, 1.2f ) );
 					}
-					if ( !uHits || !uFields )
+					if ( S.m_dOpLast[iOp] & 2 )
+					{
+						if ( uHits && uFields )
+							bAll = false;
+					} else if ( !uHits || !uFields )
 						bAll = false;
 					else
 					{
@@ -459,7 +470,7 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 						uFG |= uFields;
 						bFirst = false;
 					}
-					if ( S.m_dOpLast[iOp] )
+					if ( S.m_dOpLast[iOp] & 1 )
 					{
 						if ( bAll && !bFirst )
 						{
@@ -708,11 +719,16 @@ __global__ void __launch_bounds__ ( EVAL_THREADS, 3 ) orbits_kernel ( EvalParams
 							uint32_t uAny = 0;
 							#pragma unroll
 							for ( int f=0; f<NF; ++f )
-							{
-								dFu[f] |= dW[j][f];
 								uAny |= dW[j][f];
+							if ( dInfo[j] & 512u )
+								uUnitP &= ~uAny;	// negated member: its rows leave the unit
+							else
+							{
+								#pragma unroll
+								for ( int f=0; f<NF; ++f )
+									dFu[f] |= dW[j][f];
+								uUnitP &= uAny;
 							}
-							uUnitP &= uAny;
 							if ( dInfo[j] & 256u )
 							{
 								#pragma unroll

@@ -1153,7 +1153,7 @@ bool EngineOptions_t::Set ( const char * szName, int64_t iValue )
 		{ "or_range_tiles",	&EngineOptions_t::m_iOrRangeTiles,	1, 1<<20 },
 		{ "dnf_pct",		&EngineOptions_t::m_iDnfPct,		1, 100 },
 		{ "eager_hot",		&EngineOptions_t::m_bEagerHot,		0, 1 },
-		{ "group_neg",		&EngineOptions_t::m_bGroupNeg,		0, 1 },
+		{ "group_neg",		&EngineOptions_t::m_bGroupNeg,		0, 2 },
 		{ "force_hot",		&EngineOptions_t::m_bForceHot,		0, 1 },
 		{ "or_bits",		&EngineOptions_t::m_bOrBits,		0, 1 },
 		{ "bits_dnf",		&EngineOptions_t::m_bBitsDnf,		0, 1 },
@@ -1385,7 +1385,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 						if ( pTerm && (int64_t)pTerm->m_iDocs*iHotDiv>=(int64_t)uRows && !__atomic_fetch_add ( &dUse[pTerm->m_iOrdinal], 1, __ATOMIC_RELAXED ) )
 							dMine.push_back ( pTerm );
 					const DevQueryCore_t & q = p.m_tDev;
-					if ( !bForce || q.m_nGroups<=0 || q.m_bPureOr || q.m_bGroupNeg || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
+					if ( !bForce || q.m_nGroups<=0 || q.m_bPureOr || q.m_eRanker!=1 || q.m_nFilters || q.m_nSortKeys || q.m_nWeights>4 )
 						continue;
 					bool bDense = false, bAll = true;
 					for ( int g=0; g<q.m_nGroups; ++g )
@@ -1504,7 +1504,7 @@ int Batch_c::Prepare ( Index_c * pIndex, const mgpu_query * pQueries, int nQueri
 		const bool bBoundBase = q.m_eRanker==1 && !bWeightKey && q.m_nWeights<=4 && !pIndex->m_tDev.m_pDead && !bNoOrClass;
 		// OR-of-AND-groups programs (a pure AND is one group) whose multi-keyword groups hold hot keywords only intersect their
 		// presence bitmaps on orbits_kernel instead of walking a driver's doclist block by block
-		bool bBitsDnf = m_iOrMode==3 && tOpt.m_bBitsDnf && bBoundBase && !q.m_bPureOr && q.m_nGroups>0 && !q.m_bGroupNeg && !q.m_nFilters && !q.m_nSortKeys;
+		bool bBitsDnf = m_iOrMode==3 && tOpt.m_bBitsDnf && bBoundBase && !q.m_bPureOr && q.m_nGroups>0 && ( !q.m_bGroupNeg || tOpt.m_bGroupNeg>1 ) && !q.m_nFilters && !q.m_nSortKeys;
 		for ( int g=0; g<q.m_nGroups && bBitsDnf; ++g )
 			if ( q.m_dGroupOps[g]>1 )
 			{

@@ -92,7 +92,7 @@ struct EngineOptions_t
 	int		m_iOrRangeTiles = 1024;		///< "or_range_tiles": rows/2048 per work item of the bound + exact pass classes
 	int		m_iDnfPct = 12;				///< "dnf_pct": a group driver of the intersection kernel sits in < dnf_pct % of the rows
 	int		m_bEagerHot = 1;			///< "eager_hot": one-call batches start K0 inside Prepare, on the index's second stream (0: at the head of Run)
-	int		m_bGroupNeg = 1;			///< "group_neg": `a b -c` programs led by a sparse keyword run on and_kernel (0: dense tiles)
+	int		m_bGroupNeg = 2;			///< "group_neg": `a b -c` programs run on and_kernel (1) and, when all their keywords are hot, on the bitmaps (2); 0: dense tiles
 	int		m_bForceHot = 1;			///< "force_hot": every keyword of a program that must run on the bitmaps (a group led by a dense keyword) enters the hot store
 	int		m_bOrBits = 1;				///< "or_bits": pure OR programs run on orbits_kernel (0: stream_kernel<512,1>)
 	int		m_iBitsDnfDiv = 0;			///< "bits_dnf_div": > 0 = ... only when the group's rarest keyword sits in at least 1/bits_dnf_div of the rows

@@ -226,6 +226,54 @@ def test_cfg4_mix_with_andnot(synth):
     _compare_batch(synth, queries)
 
 
+def test_negated_group_members_all_routes(synth):
+    """`a b -c -d` programs: on the bitmaps when every keyword is hot (the negated one clears the group's presence word), on and_kernel when
+    a sparse keyword leads (probe, reject if present), on dense tiles with group_neg=0; field limits on either side; missing keywords"""
+    import random
+    rng = random.Random(4242)
+
+    def w(lo, hi, pos):
+        return M.kw("t%07d" % rng.randint(lo, hi), pos)
+
+    qs = []
+    for i in range(240):
+        shape = i % 6
+        if shape == 0:      # all dense (repeated below, so every keyword is hot)
+            pos = [w(1, 12, 1), w(1, 12, 2)]
+            neg = [w(1, 20, 3)]
+        elif shape == 1:    # two negated keywords
+            pos = [w(1, 15, 1), w(1, 30, 2), w(1, 30, 3)]
+            neg = [w(1, 10, 4), w(5, 40, 5)]
+        elif shape == 2:    # sparse driver, dense negated keyword
+            pos = [w(3000, 40000, 1), w(1, 50, 2)]
+            neg = [w(1, 8, 3)]
+        elif shape == 3:    # sparse negated keyword
+            pos = [w(1, 20, 1), w(1, 20, 2)]
+            neg = [w(2000, 60000, 3)]
+        elif shape == 4:    # field limits
+            pos = [w(1, 10, 1).fields(2), w(1, 25, 2)]
+            neg = [w(1, 10, 3).fields(rng.choice([1, 2, 3]))]
+        else:               # a keyword the index does not hold on the negated side
+            pos = [w(1, 10, 1), w(1, 40, 2)]
+            neg = [M.kw("nosuchword", 3)]
+        left = M.AND(*pos)
+        root = left
+        for n in neg:
+            root = M.ANDNOT(root, n)
+        qs.append(M.Query(root, ranker=M.RANK_BM25, field_weights=rng.choice([[10, 1], [1, 1], None]), max_matches=rng.choice([5, 100, 2000])))
+    batch = synth["gpu"].prepare(qs + qs[:120])
+    st = batch.stats()
+    batch.free()
+    assert st["class_queries"][5] >= 100 and st["class_queries"][2] >= 40, st["class_queries"]
+    assert _compare_batch(synth, qs + qs[:120]) == 0
+    for mode in (1, 0):
+        synth["gpu"].set_option("group_neg", mode)
+        try:
+            assert _compare_batch(synth, qs + qs[:120]) == 0
+        finally:
+            synth["gpu"].set_option("group_neg", 2)
+
+
 def test_random_boolean_trees(synth):
     """fuzz: random AND/OR/ANDNOT/MAYBE trees, field limits, boosts, negative/zero weights, missing words, index weights"""
     queries = workload.random_boolean_queries(400, seed=1234)
