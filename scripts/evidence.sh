@@ -1,3 +1,4 @@
+# The commands behind profiles/r02_summary.md, run as ONE gpurun call (every ncu pass follows its plain run): bash scripts/evidence.sh
 set -x
 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_v35_bench_default.json 2> gpurun_out/r02_v35_bench_default.err
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --parity 0 > gpurun_out/r02_v35_bench_plain.log 2>&1 || exit 1
