@@ -28,6 +28,8 @@ typedef struct mgpu_build_doc_input {
 	const int32_t *	tok_pos;          /* 1-based position inside the field (gaps allowed) */
 	int32_t			skiplist_block;   /* 0 -> 32 */
 	int32_t			hit_format_inline;/* 1 = inline (default), 0 = plain */
+	int32_t			dict_crc;         /* 0 = dict=keywords (default); 1 = dict=crc: entries keyed by sphFNV64 word ids
+	                                     (CSphDiskDictTraits, src/sphinx.cpp:18263-18339) */
 } mgpu_build_doc_input;
 int				mgpu_build_index ( const char * path_prefix, const mgpu_build_doc_input * in, char * err, int errlen );
 

@@ -160,9 +160,15 @@ public:
 	int		Open ( const char * szPrefix, int iDevice, uint32_t uRowidBase );
 	~Index_c();
 
+	/// the key a query keyword has in m_hTerms: the keyword itself (dict=keywords) or its word id's key (dict=crc: the query side
+	/// hashes the keyword like the indexer did, CSphDictCRC::GetWordID -> sphFNV64, src/sphinx.cpp:17318, 17569)
+	std::string DictKey ( const char * szWord ) const
+	{
+		return m_tHdr.m_bWordDict ? std::string ( szWord ) : CrcDictKey ( WordIdFNV64 ( szWord ) );
+	}
 	const TermInfo_t * FindTerm ( const char * szWord ) const
 	{
-		auto it = m_hTerms.find ( szWord );
+		auto it = m_tHdr.m_bWordDict ? m_hTerms.find ( szWord ) : m_hTerms.find ( CrcDictKey ( WordIdFNV64 ( szWord ) ) );
 		return it==m_hTerms.end() ? nullptr : &it->second;
 	}
 	int		AttrIndex ( const char * szName ) const;

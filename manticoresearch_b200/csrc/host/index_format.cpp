@@ -281,15 +281,42 @@ BYTE DoclistHintPack ( int64_t iDocs, int64_t iLen )
 }
 
 
-DictWriter_c::DictWriter_c ( int iSkiplistBlockSize )
+DictWriter_c::DictWriter_c ( int iSkiplistBlockSize, bool bCrc )
 	: m_iSkiplistBlockSize ( iSkiplistBlockSize )
+	, m_bCrc ( bCrc )
 {
-	m_tOut.PutByte ( 1 );	// CSphDictKeywords::DictBegin, src/sphinx.cpp:19382
+	m_tOut.PutByte ( 1 );	// CSphDictKeywords::DictBegin, src/sphinx.cpp:19382; CSphDiskDictTraits::DictBegin :18262-18267
 }
 
 
 void DictWriter_c::AddEntry ( const DictEntry_t & e )
 {
+	if ( m_bCrc )
+	{
+		// CSphDiskDictTraits::DictEntry, src/sphinx.cpp:18288-18330
+		if ( ( m_iWords % SPH_WORDLIST_CHECKPOINT )==0 )
+		{
+			if ( m_iWords )
+			{
+				m_tOut.Zip ( 0 );	// indicate checkpoint
+				m_tOut.Zip ( (uint64_t)( e.m_iDoclistOffset-m_iLastDoclistPos ) );	// store last length
+			}
+			m_uLastWordID = 0;
+			m_iLastDoclistPos = 0;
+			m_dCrcCheckpoints.push_back ( { e.m_uWordID, m_tOut.Pos() } );
+		}
+		m_tOut.Zip ( e.m_uWordID-m_uLastWordID );
+		m_tOut.Zip ( (uint64_t)( e.m_iDoclistOffset-m_iLastDoclistPos ) );
+		m_uLastWordID = e.m_uWordID;
+		m_iLastDoclistPos = e.m_iDoclistOffset;
+		m_tOut.Zip ( (uint64_t)e.m_iDocs );
+		m_tOut.Zip ( (uint64_t)e.m_iHits );
+		if ( e.m_iDocs>m_iSkiplistBlockSize )
+			m_tOut.Zip ( (uint64_t)e.m_iSkiplistOffset );
+		m_iWords++;
+		return;
+	}
+
 	// src/sphinx.cpp:19468-19511
 	if ( ( m_iWords % SPH_WORDLIST_CHECKPOINT )==0 )
 	{
@@ -332,8 +359,25 @@ void DictWriter_c::AddEntry ( const DictEntry_t & e )
 }
 
 
-void DictWriter_c::Finish ( IndexHeader_t & h )
+void DictWriter_c::Finish ( IndexHeader_t & h, int64_t iDoclistEnd )
 {
+	if ( m_bCrc )
+	{
+		// DictEndEntries + DictEnd, src/sphinx.cpp:18269-18286, 18332-18337
+		m_tOut.Zip ( 0 );
+		m_tOut.Zip ( (uint64_t)( iDoclistEnd-m_iLastDoclistPos ) );
+		h.m_iDictCheckpointsOffset = m_tOut.Pos();
+		h.m_iDictCheckpoints = (DWORD)m_dCrcCheckpoints.size();
+		for ( const auto & c : m_dCrcCheckpoints )
+		{
+			m_tOut.PutOffset ( (int64_t)c.first );
+			m_tOut.PutOffset ( c.second );
+		}
+		h.m_iInfixCodepointBytes = 0;
+		h.m_iInfixBlocksOffset = 0;
+		h.m_iInfixBlocksWordsSize = 0;
+		return;
+	}
 	// src/sphinx.cpp:19537-19576
 	m_tOut.Zip ( 0 );
 	m_tOut.Zip ( 0 );
@@ -363,15 +407,56 @@ bool ReadDictionary ( const BYTE * pSpi, size_t iLen, const IndexHeader_t & h, s
 	dOut.clear();
 	if ( !h.m_iDictCheckpoints )
 		return true;
-	if ( !h.m_bWordDict )
-	{
-		sError = "dict=crc indexes are not supported by this loader yet (dict=keywords only)";
-		return false;
-	}
 	if ( h.m_iDictCheckpointsOffset<=0 || (size_t)h.m_iDictCheckpointsOffset>iLen )
 	{
 		sError = "dictionary checkpoints offset out of bounds";
 		return false;
+	}
+	if ( !h.m_bWordDict )
+	{
+		// dict=crc: checkpoints {u64 word id, u64 offset} (CWordlist::Preread -> CheckpointReader_c for crc dictionaries,
+		// src/indexformat.cpp:354-410); chunks of delta-coded entries, closed by a zero id delta + the last doclist's length
+		// (CWordlist::GetWord, :425-473)
+		ByteReader_t rCp ( pSpi+h.m_iDictCheckpointsOffset, iLen-h.m_iDictCheckpointsOffset );
+		const int iBlk = (int)h.m_iSkiplistBlockSize;
+		for ( DWORD i=0; i<h.m_iDictCheckpoints; ++i )
+		{
+			rCp.GetOffset();	// the chunk's first word id (the entries repeat it)
+			const int64_t iOff = rCp.GetOffset();
+			if ( rCp.m_bError || iOff<=0 || iOff>=h.m_iDictCheckpointsOffset )
+			{
+				sError = "dictionary checkpoint out of bounds";
+				return false;
+			}
+			ByteReader_t r ( pSpi+iOff, (size_t)( h.m_iDictCheckpointsOffset-iOff ) );
+			uint64_t uLastID = 0;
+			int64_t iLastOff = 0;
+			while ( true )
+			{
+				const uint64_t uDelta = r.Unzip();
+				if ( !uDelta || r.m_bError )
+					break;
+				DictEntry_t e;
+				uLastID += uDelta;
+				iLastOff += (int64_t)r.Unzip();
+				e.m_uWordID = uLastID;
+				e.m_sKeyword = CrcDictKey ( uLastID );
+				e.m_iDoclistOffset = iLastOff;
+				e.m_iDocs = (int)r.Unzip();
+				e.m_iHits = (int)r.Unzip();
+				if ( e.m_iDocs>iBlk )
+					e.m_iSkiplistOffset = (int64_t)r.Unzip();
+				if ( r.m_bError )
+					break;
+				dOut.push_back ( e );
+			}
+			if ( r.m_bError )
+			{
+				sError = "dictionary chunk truncated";
+				return false;
+			}
+		}
+		return true;
 	}
 
 	// checkpoint table: {u32 len, bytes, u64 offset}* (CWordlist::Preread, src/indexformat.cpp:331-344)

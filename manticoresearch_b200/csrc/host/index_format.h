@@ -2,6 +2,7 @@
 // Reference: header writer src/sphinx.cpp:8781-8891 (IndexWriteHeader), reader :13207-13392 (LoadHeader);
 // settings blocks src/indexsettings.cpp:303-333 (tokenizer), :405-453 (dict), :506-523 (field filter).
 #pragma once
+#include <string.h>
 
 #include "vbyte.h"
 #include <string>
@@ -82,9 +83,30 @@ struct IndexHeader_t
 };
 
 /// CSphDictEntry (src/sphinx.h) as stored in .spi
+/// sphFNV64 over a zero-terminated keyword (src/fnv64.cpp:16-50): the word id of dict=crc indexes (CCRCEngine<false>::DoCrc, src/sphinx.cpp:17318)
+inline uint64_t WordIdFNV64 ( const char * sWord )
+{
+	uint64_t h = 0xcbf29ce484222325ull;
+	for ( const unsigned char * p = (const unsigned char *)sWord; *p; ++p )
+	{
+		h ^= (uint64_t)*p;
+		h *= 0x100000001b3ull;
+	}
+	return h;
+}
+
+/// how a dict=crc entry is named in the loaders' keyword maps: a zero byte (no keyword starts with one) + the 8 bytes of its word id
+inline std::string CrcDictKey ( uint64_t uWordID )
+{
+	std::string s ( 9, '\0' );
+	memcpy ( &s[1], &uWordID, 8 );
+	return s;
+}
+
 struct DictEntry_t
 {
-	std::string	m_sKeyword;
+	std::string	m_sKeyword;				// dict=crc: CrcDictKey ( m_uWordID )
+	uint64_t	m_uWordID = 0;			// dict=crc only
 	int64_t		m_iDoclistOffset = 0;
 	int64_t		m_iDoclistLength = 0;	// bytes incl. the terminating zero varint
 	int			m_iDocs = 0;
@@ -110,9 +132,15 @@ struct DictWriter_c
 	struct Checkpoint_t { std::string m_sWord; int64_t m_iOffset; };
 	std::vector<Checkpoint_t> m_dCheckpoints;
 
-	explicit DictWriter_c ( int iSkiplistBlockSize );
+	/// bCrc: the dict=crc form (CSphDiskDictTraits::DictEntry / DictEndEntries / DictEnd, src/sphinx.cpp:18263-18339): entries sorted by
+	/// word id, delta-coded ids and doclist offsets, checkpoints of {word id, offset}; Finish needs the end of the last doclist then
+	explicit DictWriter_c ( int iSkiplistBlockSize, bool bCrc=false );
 	void	AddEntry ( const DictEntry_t & tEntry );
-	void	Finish ( IndexHeader_t & tHdr );
+	void	Finish ( IndexHeader_t & tHdr, int64_t iDoclistEnd=0 );
+	bool		m_bCrc = false;
+	uint64_t	m_uLastWordID = 0;
+	int64_t		m_iLastDoclistPos = 0;
+	std::vector<std::pair<uint64_t,int64_t>> m_dCrcCheckpoints;
 };
 
 /// reads every dictionary entry of a dict=keywords or dict=crc .spi

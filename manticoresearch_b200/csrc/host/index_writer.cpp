@@ -358,11 +358,27 @@ bool BuildIndexFromDocs ( const char * szPrefix, const mgpu_build_doc_input & tI
 	tHdr.m_iSkiplistBlockSize = iBlk;
 	tHdr.m_eHitFormat = tIn.hit_format_inline ? SPH_HIT_FORMAT_INLINE : SPH_HIT_FORMAT_PLAIN;
 	tHdr.m_iTotalDocuments = (DWORD)tIn.n_docs;
+	const bool bCrc = tIn.dict_crc!=0;
+	tHdr.m_bWordDict = bCrc ? 0 : 1;
 
-	// keyword order = strcmp order (CSphDictKeywords sorts its chunks with strcmp, src/sphinx.cpp:19589-19595)
+	// keyword order = strcmp order (CSphDictKeywords sorts its chunks with strcmp, src/sphinx.cpp:19589-19595);
+	// dict=crc: ascending word id (the hit stream is sorted by word id, CSphHitBuilder::cidxHit sees them in that order)
 	std::vector<int> dKwOrder ( tIn.n_keywords );
 	std::iota ( dKwOrder.begin(), dKwOrder.end(), 0 );
-	std::sort ( dKwOrder.begin(), dKwOrder.end(), [&] ( int a, int b ) { return strcmp ( tIn.keywords[a], tIn.keywords[b] )<0; } );
+	std::vector<uint64_t> dKwID ( tIn.n_keywords, 0 );
+	if ( bCrc )
+	{
+		for ( int i=0; i<tIn.n_keywords; ++i )
+			dKwID[i] = WordIdFNV64 ( tIn.keywords[i] );
+		std::sort ( dKwOrder.begin(), dKwOrder.end(), [&] ( int a, int b ) { return dKwID[a]<dKwID[b]; } );
+		for ( int i=0; i+1<tIn.n_keywords; ++i )
+			if ( dKwID[dKwOrder[i]]==dKwID[dKwOrder[i+1]] || !dKwID[dKwOrder[i]] )
+			{
+				sError = "keywords collide under FNV64 (or hash to zero)";
+				return false;
+			}
+	} else
+		std::sort ( dKwOrder.begin(), dKwOrder.end(), [&] ( int a, int b ) { return strcmp ( tIn.keywords[a], tIn.keywords[b] )<0; } );
 	std::vector<int> dKwRank ( tIn.n_keywords );
 	for ( int i=0; i<tIn.n_keywords; ++i )
 		dKwRank[dKwOrder[i]] = i;
@@ -404,7 +420,7 @@ bool BuildIndexFromDocs ( const char * szPrefix, const mgpu_build_doc_input & tI
 
 	ByteBuf_t tSpd, tSpp, tSpe;
 	tSpd.PutByte ( 1 ); tSpp.PutByte ( 1 ); tSpe.PutByte ( 1 );	// CreateIndexFiles, :8404-8409
-	DictWriter_c tDict ( iBlk );
+	DictWriter_c tDict ( iBlk, bCrc );
 	TermEncoder_c tEnc ( iBlk, tIn.hit_format_inline!=0 );
 
 	std::vector<RowID_t> dRows;
@@ -422,6 +438,7 @@ bool BuildIndexFromDocs ( const char * szPrefix, const mgpu_build_doc_input & tI
 		}
 		DictEntry_t tEntry;
 		tEntry.m_sKeyword = tIn.keywords[dKwOrder[dHits[i].m_iKw]];
+		tEntry.m_uWordID = dKwID[dKwOrder[dHits[i].m_iKw]];
 		tEntry.m_iDoclistOffset = tSpd.Pos();
 		int64_t iSkipLocal = -1;
 		TermOut_t tOut = tEnc.Encode ( dRows.data(), dPos.data(), (int64_t)dRows.size(), tSpd, 0, tSpp, 0, tSpe, &iSkipLocal );
@@ -432,7 +449,7 @@ bool BuildIndexFromDocs ( const char * szPrefix, const mgpu_build_doc_input & tI
 		tDict.AddEntry ( tEntry );
 		i = j;
 	}
-	tDict.Finish ( tHdr );
+	tDict.Finish ( tHdr, tSpd.Pos() );
 
 	if ( !WriteFile ( sPrefix+".spd", tSpd.m_d.data(), tSpd.m_d.size(), sError ) ) return false;
 	if ( !WriteFile ( sPrefix+".spp", tSpp.m_d.data(), tSpp.m_d.size(), sError ) ) return false;

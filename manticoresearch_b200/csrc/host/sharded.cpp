@@ -142,6 +142,11 @@ public:
 				m_sError = p->m_sError;
 				return iRes;
 			}
+			if ( s && p->m_tHdr.m_bWordDict!=m_dShards[0]->m_tHdr.m_bWordDict )
+			{
+				m_sError = "shards mix dict=keywords and dict=crc";
+				return MGPU_E_FORMAT;
+			}
 			m_dBase.push_back ( (uint32_t)uBase );
 			uBase += p->m_tDev.m_uRows;
 			m_iTotalDocs += (int64_t)p->m_tHdr.m_iTotalDocuments;
@@ -243,7 +248,7 @@ public:
 							pIds[w] = -1;
 							if ( q.words[w].word )
 							{
-								auto it = m_hGlobalDocs.find ( q.words[w].word );
+								auto it = m_hGlobalDocs.find ( m_dShards[0]->DictKey ( q.words[w].word ) );
 								pDocs[w] = it==m_hGlobalDocs.end() ? 0 : it->second.m_iDocs;
 								pHits[w] = it==m_hGlobalDocs.end() ? 0 : it->second.m_iHits;
 								pIds[w] = it==m_hGlobalDocs.end() ? -1 : it->second.m_iId;
@@ -582,7 +587,7 @@ int mgpu_sharded_word_docs ( const mgpu_sharded * sh, const char * word, int64_t
 {
 	if ( !sh || !word )
 		return 0;
-	auto it = sh->m_t.m_hGlobalDocs.find ( word );
+	auto it = sh->m_t.m_hGlobalDocs.find ( sh->m_t.m_dShards[0]->DictKey ( word ) );
 	if ( it==sh->m_t.m_hGlobalDocs.end() )
 		return 0;
 	if ( docs )

@@ -91,7 +91,7 @@ class c_build_doc_input(C.Structure):
                 ("docids", C.POINTER(C.c_int64)), ("attrs", C.POINTER(C.c_uint32)),
                 ("n_keywords", C.c_int32), ("keywords", C.POINTER(C.c_char_p)),
                 ("field_tok_offsets", C.POINTER(C.c_int64)), ("tok_keyword", C.POINTER(C.c_int32)), ("tok_pos", C.POINTER(C.c_int32)),
-                ("skiplist_block", C.c_int32), ("hit_format_inline", C.c_int32)]
+                ("skiplist_block", C.c_int32), ("hit_format_inline", C.c_int32), ("dict_crc", C.c_int32)]
 
 
 class SynthParams(C.Structure):
@@ -655,7 +655,7 @@ class Batch:
 # index building (host only)
 # ---------------------------------------------------------------------------------------------
 
-def build_index(path_prefix, field_names, docs, attr_names=(), skiplist_block=32, hit_format_inline=True):
+def build_index(path_prefix, field_names, docs, attr_names=(), skiplist_block=32, hit_format_inline=True, dict_crc=False):
     """docs: list of dicts {"id": int, "fields": [[(keyword, pos), ...] per field], "attrs": [uint32...]}.
 
     Row order = list order (the reference assigns rowids in source order)."""
@@ -687,6 +687,7 @@ def build_index(path_prefix, field_names, docs, attr_names=(), skiplist_block=32
     inp.n_keywords, inp.keywords = len(keywords), a_kw
     inp.field_tok_offsets, inp.tok_keyword, inp.tok_pos = a_off, a_tk, a_tp
     inp.skiplist_block, inp.hit_format_inline = skiplist_block, int(hit_format_inline)
+    inp.dict_crc = int(dict_crc)
     err = C.create_string_buffer(512)
     rc = writer_lib().mgpu_build_index(path_prefix.encode(), C.byref(inp), err, 512)
     if rc != MGPU_OK:

@@ -138,7 +138,32 @@ struct Index_t
 	bool m_bInlineHits = true;
 	int m_iSkipBlock = 32;
 	std::unordered_map<std::string,WordEntry_t> m_hWords;
+	bool m_bWordDict = true;
+	std::unordered_map<uint64_t,WordEntry_t> m_hWordIds;	// dict=crc: by word id
 	std::string m_sError;
+
+	// the query side of a dict=crc index hashes the keyword with sphFNV64 (src/fnv64.cpp:16-50; CSphDictCRC<false>::GetWordID,
+	// src/sphinx.cpp:17318, 17569) and looks the id up (CWordlist::GetWord, src/indexformat.cpp:425-473)
+	static uint64_t FNV64 ( const char * s )
+	{
+		uint64_t h = 14695981039346656037ULL;
+		while ( *s )
+		{
+			h ^= (BYTE)*s++;
+			h *= 1099511628211ULL;
+		}
+		return h;
+	}
+	const WordEntry_t * FindWord ( const char * szWord ) const
+	{
+		if ( m_bWordDict )
+		{
+			auto it = m_hWords.find ( szWord );
+			return it==m_hWords.end() ? nullptr : &it->second;
+		}
+		auto it = m_hWordIds.find ( FNV64 ( szWord ) );
+		return it==m_hWordIds.end() ? nullptr : &it->second;
+	}
 
 	bool Open ( const std::string & sPrefix );
 	const DWORD * Row ( RowID_t r ) const	{ return (const DWORD *)m_tSpa.m_p + (int64_t)r*m_iStride; }	// src/sphinx.cpp:11984
@@ -234,7 +259,37 @@ bool Index_t::Open ( const std::string & sPrefix )
 	bool bWordDict = c.Byte()!=0;
 	c.Byte(); c.String();
 	m_iRows = c.Offset();
-	if ( !bWordDict ) { m_sError = "dict=crc not supported by the oracle"; return false; }
+	m_bWordDict = bWordDict;
+	if ( !bWordDict )
+	{
+		// dict=crc: checkpoints are { u64 first word id, u64 offset } (CSphDiskDictTraits::DictEnd, src/sphinx.cpp:18269-18286); each points
+		// at up to 64 entries of { zipped word id delta, zipped doclist offset delta, docs, hits, [skiplist offset] }, closed by a zero
+		// delta + the last doclist's length (DictEntry / DictEndEntries, :18288-18337; read back by CWordlist::GetWord, src/indexformat.cpp:425-473)
+		const BYTE * pCp = m_tSpi.m_p + iCpOffset;
+		for ( DWORD i=0; i<nCp; ++i, pCp += 16 )
+		{
+			int64_t iOff; memcpy ( &iOff, pCp+8, 8 );
+			const BYTE * p = m_tSpi.m_p + iOff;
+			uint64_t uID = 0;
+			int64_t iDoclist = 0;
+			while ( true )
+			{
+				uint64_t uDelta = Unzip ( p );
+				if ( !uDelta )
+					break;
+				uID += uDelta;
+				iDoclist += (int64_t)Unzip ( p );
+				WordEntry_t e;
+				e.m_iDoclistOffset = iDoclist;
+				e.m_iDocs = (int)Unzip ( p );
+				e.m_iHits = (int)Unzip ( p );
+				if ( e.m_iDocs>m_iSkipBlock )
+					e.m_iSkiplistOffset = (int64_t)Unzip ( p );
+				m_hWordIds.emplace ( uID, e );
+			}
+		}
+		return true;
+	}
 
 	// dictionary: checkpoints then 64-word blocks, src/indexformat.cpp:331-344, 641-691
 	const BYTE * pCp = m_tSpi.m_p + iCpOffset;
@@ -308,10 +363,10 @@ struct Qword_t
 	{
 		m_pIndex = pIndex;
 		m_sWord = sWord;
-		auto it = pIndex->m_hWords.find ( sWord );
-		if ( it==pIndex->m_hWords.end() )
+		const WordEntry_t * pEntry = pIndex->FindWord ( sWord.c_str() );
+		if ( !pEntry )
 			return false;
-		const WordEntry_t & e = it->second;
+		const WordEntry_t & e = *pEntry;
 		m_iDocs = e.m_iDocs;
 		m_iHits = e.m_iHits;
 		m_iDoclistOffset = e.m_iDoclistOffset;
@@ -2383,9 +2438,9 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 	if ( tRes.word_stats )
 		for ( int i=0; i<q.n_words; ++i )
 		{
-			auto it = tIndex.m_hWords.find ( q.words[i].word );
-			tRes.word_stats[i].docs = it==tIndex.m_hWords.end() ? 0 : it->second.m_iDocs;
-			tRes.word_stats[i].hits = it==tIndex.m_hWords.end() ? 0 : it->second.m_iHits;
+			const WordEntry_t * pEntry = tIndex.FindWord ( q.words[i].word );
+			tRes.word_stats[i].docs = pEntry ? pEntry->m_iDocs : 0;
+			tRes.word_stats[i].hits = pEntry ? pEntry->m_iHits : 0;
 		}
 	if ( !pRoot )
 		return MGPU_OK;
@@ -2686,11 +2741,11 @@ int oracle_decode_hitlist ( oracle_index * p, const char * szWord, uint64_t uHit
 
 int oracle_word_stats ( oracle_index * p, const char * szWord, int64_t * pDocs, int64_t * pHits )
 {
-	auto it = p->m_t.m_hWords.find ( szWord );
-	if ( it==p->m_t.m_hWords.end() )
+	const WordEntry_t * pEntry = p->m_t.FindWord ( szWord );
+	if ( !pEntry )
 		return 0;
-	*pDocs = it->second.m_iDocs;
-	*pHits = it->second.m_iHits;
+	*pDocs = pEntry->m_iDocs;
+	*pHits = pEntry->m_iHits;
 	return 1;
 }
 

@@ -37,3 +37,16 @@ def golden_indexes(tmp_path_factory, golden_cases):
         helpers.build_golden_index(case, prefix)
         out[case["name"]] = prefix
     return out
+
+
+@pytest.fixture(scope="session")
+def golden_indexes_crc(tmp_path_factory, golden_cases):
+    """the same golden corpora written with dict=crc (FNV64 word ids instead of keywords in .spi)"""
+    import helpers
+    base = tmp_path_factory.mktemp("golden_idx_crc")
+    out = {}
+    for case in golden_cases:
+        prefix = str(base / case["name"])
+        helpers.build_golden_index(case, prefix, dict_crc=True)
+        out[case["name"]] = prefix
+    return out

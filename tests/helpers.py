@@ -185,12 +185,12 @@ def load_golden():
         return json.load(f)["cases"]
 
 
-def build_golden_index(case, prefix):
+def build_golden_index(case, prefix, dict_crc=False):
     docs = []
     for d in case["docs"]:
         docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ()), case.get("phrase_boundary", ""), case.get("phrase_boundary_step", 0))
                                                 for t in d["fields"]], "attrs": d.get("attrs", [])})
-    M.build_index(prefix, case["fields"], docs, attr_names=case.get("attrs", ()))
+    M.build_index(prefix, case["fields"], docs, attr_names=case.get("attrs", ()), dict_crc=dict_crc)
 
 
 def golden_query(case, q):

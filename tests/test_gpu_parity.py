@@ -391,6 +391,30 @@ def test_hot_store_escape_and_plain_format(tmp_path):
             cpu.close()
 
 
+def test_golden_vectors_on_gpu_dict_crc(golden_cases, golden_indexes_crc, tmp_path):
+    """dict=crc indexes (word ids = sphFNV64 of the keyword, src/sphinx.cpp:18263-18339): mgpu_index_open reads the id-keyed
+    dictionary, query keywords are hashed at bind time; same golden results. Plus the sharded handle over two crc shards"""
+    test_golden_vectors_on_gpu(golden_cases, golden_indexes_crc)
+    docs_a = [{"id": 1 + i, "fields": [[("alpha", 1)], [("beta", 1), ("gamma%d" % (i % 3), 2)]], "attrs": []} for i in range(100)]
+    docs_b = [{"id": 101 + i, "fields": [[("beta", 1)], [("alpha", 1), ("gamma%d" % (i % 5), 2)]], "attrs": []} for i in range(70)]
+    pa, pb, pf = str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "full")
+    M.build_index(pa, ["title", "body"], docs_a, dict_crc=True)
+    M.build_index(pb, ["title", "body"], docs_b, dict_crc=True)
+    M.build_index(pf, ["title", "body"], docs_a + docs_b, dict_crc=True)
+    sh, cpu = M.ShardedIndex([pa, pb], [0, 0]), helpers.OracleIndex(pf)
+    try:
+        qs = [M.Query(M.AND(M.kw("alpha", 1), M.kw("gamma1", 2)), ranker=M.RANK_BM25, field_weights=[3, 1], max_matches=50),
+              M.Query(M.OR(M.kw("gamma4", 1), M.kw("gamma2", 2), M.kw("missing", 3)), ranker=M.RANK_PROXIMITY_BM25, max_matches=50),
+              M.Query(M.PHRASE([("beta", 1), ("gamma0", 2)]), ranker=M.RANK_PROXIMITY_BM25, max_matches=50)]
+        g, c = sh.search(qs), cpu.search(qs)
+        for i, q in enumerate(qs):
+            helpers.assert_same_results(g.get(i), c.get(i), ctx="crc shards, query %d" % i)
+            assert g.word_stats(i, len(q.keywords())) == c.word_stats(i, len(q.keywords()))
+    finally:
+        sh.close()
+        cpu.close()
+
+
 def test_golden_vectors_on_gpu(golden_cases, golden_indexes):
     """the reference's own golden results (17 model.bin files + gtest WeightBoundary): every query runs on the CUDA path, quorum /
     NEAR / BEFORE / NOTNEAR over plain keywords included; the trees flagged gpu_unsupported (make_golden.py: n-way NEAR, operator

@@ -61,3 +61,83 @@ def test_reference_built_index_opens():
         assert r["total_found"] == 1 and r["rowid"] == [0]
     finally:
         idx.close()
+
+
+def _fnv1a64(b):
+    h = 0xcbf29ce484222325
+    for c in b:
+        h = ((h ^ c) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _unzip(raw, pos):
+    """MSB-first 7-bit groups (src/fileio.cpp:31-45)"""
+    v = 0
+    while True:
+        b = raw[pos]
+        pos += 1
+        v = (v << 7) | (b & 0x7F)
+        if not b & 0x80:
+            return v, pos
+
+
+def test_dict_crc_golden(golden_cases, golden_indexes, golden_indexes_crc):
+    """dict=crc (CSphDiskDictTraits, src/sphinx.cpp:18263-18339; CWordlist::GetWord, src/indexformat.cpp:425-473): every golden corpus
+    rewritten with FNV64 word ids gives the reference's golden results through the oracle's crc reader, the .spi holds ascending
+    FNV-1a ids (published known answers: "a", "foobar"), and the doclist files are the keywords build's, reordered"""
+    import struct
+    assert _fnv1a64(b"a") == 0xaf63dc4c8601ec8c and _fnv1a64(b"foobar") == 0x85944171f73967e8
+    ran = 0
+    for case in golden_cases:
+        prefix = golden_indexes_crc[case["name"]]
+        raw = open(prefix + ".spi", "rb").read()
+        hdr = open(prefix + ".sph", "rb").read()
+        assert raw[0] == 1
+        idx, kw = helpers.OracleIndex(prefix), helpers.OracleIndex(golden_indexes[case["name"]])
+        try:
+            words = set()
+            for d in case["docs"]:
+                for t in d["fields"]:
+                    for w, _ in helpers.tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ()), case.get("phrase_boundary", ""), case.get("phrase_boundary_step", 0)):
+                        words.add(w)
+            ids = sorted(_fnv1a64(w.encode()) for w in words)
+            # walk the chunks from the first one: 64 entries, zero delta + last doclist length, next chunk
+            got, pos, n_in_chunk, last = [], 1, 0, 0
+            while len(got) < len(ids):
+                delta, pos = _unzip(raw, pos)
+                if delta == 0:
+                    assert n_in_chunk == 64
+                    _, pos = _unzip(raw, pos)
+                    n_in_chunk, last = 0, 0
+                    continue
+                last += delta
+                got.append(last)
+                _, pos = _unzip(raw, pos)
+                docs, pos = _unzip(raw, pos)
+                _, pos = _unzip(raw, pos)
+                if docs > 32:
+                    _, pos = _unzip(raw, pos)
+                n_in_chunk += 1
+            assert got == ids, case["name"]
+            for w in sorted(words)[:50]:
+                assert idx.word_stats(w) == kw.word_stats(w)
+                a, b = idx.decode_doclist(w), kw.decode_doclist(w)
+                for x, y in zip(a[:3], b[:3]):
+                    assert (x == y).all()
+            assert idx.word_stats("nosuchkeywordanywhere") is None
+            for q in case["queries"]:
+                query = helpers.golden_query(case, q)
+                r = idx.search([query]).get(0)
+                assert r["status"] == 0, q["text"]
+                got_m = list(zip(r["docid"], r["weight"]))
+                if q.get("ids_only"):
+                    got_m = [(d, 0) for d, _ in got_m]
+                if q.get("limit"):
+                    got_m = got_m[:q["limit"]]
+                assert got_m == [tuple(m) for m in q["expect"]["matches"]], (case["name"], q["text"])
+                assert r["total_found"] == q["expect"]["total_found"], q["text"]
+                ran += 1
+        finally:
+            idx.close()
+            kw.close()
+    assert ran == sum(len(c["queries"]) for c in golden_cases)
