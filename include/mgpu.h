@@ -39,7 +39,7 @@ enum {
 	MGPU_OP_AND = 0,        /* SPH_QUERY_AND */
 	MGPU_OP_OR = 1,         /* SPH_QUERY_OR */
 	MGPU_OP_MAYBE = 2,      /* SPH_QUERY_MAYBE */
-	MGPU_OP_NOT = 3,        /* SPH_QUERY_NOT (must have been fixed up to ANDNOT by the parser) */
+	MGPU_OP_NOT = 3,        /* SPH_QUERY_NOT: only as the one-child wrapper FixupNots leaves on the right side of an ANDNOT */
 	MGPU_OP_ANDNOT = 4,     /* SPH_QUERY_ANDNOT */
 	MGPU_OP_BEFORE = 5,     /* SPH_QUERY_BEFORE: a << b << c; on the GPU path when every child is a plain keyword */
 	MGPU_OP_PHRASE = 6,     /* SPH_QUERY_PHRASE */
@@ -301,6 +301,42 @@ void			mgpu_unpack_key ( const uint64_t key[2], uint32_t * global_rowid, int32_t
  * arrays; used by the parity tests of the VByte block decoder against the oracle's
  * DiskIndexQword_c::ReadNext restatement (src/sphinx.cpp:511-549). host arrays sized docs. */
 int				mgpu_decode_doclist ( mgpu_index * idx, const char * word, uint32_t * rowid, uint32_t * hits, uint32_t * fields, uint64_t * hitlist_pos, int64_t capacity, int64_t * n_out );
+
+/* ------------------------------------------------------------------------------------- */
+/* Query front-end: extended query syntax -> the flattened tree above.
+ * Replaces sphParseExtendedQuery / XQParser_t::Parse (src/sphinxquery.cpp:1741-1830, 1990-2014; grammar src/sphinxquery.y) with its
+ * tree fix-ups (XQParseHelper_c::FixupTree, :343-387) and the legacy match modes' rewrite (PrepareQueryEmulation,
+ * src/searchd.cpp:2141-2190).  Host only, no GPU needed.  The tokenizer is the reference's default charset_table (ASCII
+ * alphanumerics + '_', Cyrillic, case folded) plus CJK unigrams when ngram_cjk is set; min_word_len and stop words consume query
+ * positions as in the reference (overshort_step / stopword_step).  Not parsed: zones, SENTENCE / PARAGRAPH, exact-form '=',
+ * wildcards, blended characters (MGPU_E_UNSUPPORTED where the syntax is recognised). */
+enum {
+	MGPU_MATCH_ALL = 0,       /* SPH_MATCH_ALL: every word; ranker SPH_RANK_PROXIMITY */
+	MGPU_MATCH_ANY = 1,       /* SPH_MATCH_ANY: "words"/1; ranker SPH_RANK_MATCHANY */
+	MGPU_MATCH_PHRASE = 2,    /* SPH_MATCH_PHRASE: "words"; ranker SPH_RANK_PROXIMITY */
+	MGPU_MATCH_BOOLEAN = 3,   /* SPH_MATCH_BOOLEAN: extended syntax, ranker SPH_RANK_NONE */
+	MGPU_MATCH_EXTENDED = 4   /* SPH_MATCH_EXTENDED / EXTENDED2 */
+};
+typedef struct mgpu_parser_settings {
+	int32_t			n_fields;
+	const char * const * field_names;   /* index schema, for @field limits (CSphSchema::GetFieldIndex) */
+	int32_t			min_word_len;       /* CSphTokenizerSettings::m_iMinWordLen (0 -> 1) */
+	int32_t			n_stopwords;
+	const char * const * stopwords;     /* dictionary forms */
+	int32_t			overshort_step;     /* CSphIndexSettings::m_iOvershortStep (reference default 1) */
+	int32_t			stopword_step;      /* m_iStopwordStep (reference default 1) */
+	int32_t			match_mode;         /* MGPU_MATCH_* */
+	int32_t			ngram_cjk;          /* ngram_len=1 over the CJK ranges */
+} mgpu_parser_settings;
+typedef struct mgpu_parsed mgpu_parsed;
+/* *out is set whenever settings and out are valid, also on a parse error (then it carries the message); free it with mgpu_parsed_free */
+int				mgpu_parse_query ( const mgpu_parser_settings * settings, const char * text, mgpu_parsed ** out );
+/* points q's tree members (nodes, children, words, root, and the ranker for the legacy match modes) at the parsed tree;
+ * the pointers live until mgpu_parsed_free */
+int				mgpu_parsed_fill ( const mgpu_parsed * p, mgpu_query * q );
+const char *	mgpu_parsed_error ( const mgpu_parsed * p );      /* XQQuery_t::m_sParseError */
+const char *	mgpu_parsed_warning ( const mgpu_parsed * p );    /* XQQuery_t::m_sParseWarning */
+void			mgpu_parsed_free ( mgpu_parsed * p );
 
 int				mgpu_abi_version ( void );
 

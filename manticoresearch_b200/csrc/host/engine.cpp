@@ -504,6 +504,10 @@ struct Planner_c
 		if ( bAndTerms )
 			return Create ( pChildren[0] );
 
+		// the one-child NOT wrapper FixupNots leaves under an ANDNOT: the generic fold of a single child is the child (:1785-1806)
+		if ( tNode.op==MGPU_OP_NOT && nChildren==1 )
+			return Create ( pChildren[0] );
+
 		int iKind;
 		switch ( tNode.op )
 		{

@@ -94,6 +94,12 @@ class c_build_doc_input(C.Structure):
                 ("skiplist_block", C.c_int32), ("hit_format_inline", C.c_int32), ("dict_crc", C.c_int32)]
 
 
+class c_parser_settings(C.Structure):
+    _fields_ = [("n_fields", C.c_int32), ("field_names", C.POINTER(C.c_char_p)), ("min_word_len", C.c_int32),
+                ("n_stopwords", C.c_int32), ("stopwords", C.POINTER(C.c_char_p)), ("overshort_step", C.c_int32),
+                ("stopword_step", C.c_int32), ("match_mode", C.c_int32), ("ngram_cjk", C.c_int32)]
+
+
 class SynthParams(C.Structure):
     """mgpu_synth_params; defaults = the corpus of SURVEY.md 8(d)."""
     _fields_ = [("seed", C.c_uint64), ("first_doc", C.c_int64), ("n_docs", C.c_int64), ("vocab", C.c_int32),
@@ -155,6 +161,11 @@ def load_library(path=None):
         "mgpu_merge_shard_keys": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
         "mgpu_decode_doclist": (C.c_int, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), i64, C.POINTER(i64)]),
+        "mgpu_parse_query": (C.c_int, [C.POINTER(c_parser_settings), C.c_char_p, C.POINTER(vp)]),
+        "mgpu_parsed_fill": (C.c_int, [vp, C.POINTER(c_query)]),
+        "mgpu_parsed_error": (C.c_char_p, [vp]),
+        "mgpu_parsed_warning": (C.c_char_p, [vp]),
+        "mgpu_parsed_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib_, name)
@@ -209,6 +220,7 @@ EXPORTED_SYMBOLS = [
     "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist",
     "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
     "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
+    "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
 ]
 
 # ---------------------------------------------------------------------------------------------
@@ -301,6 +313,48 @@ class SortKey:
 class Filter:
     def __init__(self, attr, min_value=None, max_value=None, values=None, exclude=False):
         self.attr, self.min_value, self.max_value, self.values, self.exclude = attr, min_value, max_value, values, exclude
+
+
+MATCH_ALL, MATCH_ANY, MATCH_PHRASE, MATCH_BOOLEAN, MATCH_EXTENDED = range(5)
+
+
+def parse_query(text, field_names, min_word_len=1, stopwords=(), match_mode=MATCH_EXTENDED, ngram_cjk=True, overshort_step=1, stopword_step=1):
+    """mgpu_parse_query -> (root Node, ranker forced by a legacy match mode or None, warning). Raises MgpuError on a parse error.
+    Host only: works without a GPU."""
+    l = lib()
+    st = c_parser_settings()
+    names = (C.c_char_p * max(1, len(field_names)))(*[f.encode() for f in field_names])
+    stops = (C.c_char_p * max(1, len(stopwords)))(*[w.encode("utf-8") for w in stopwords])
+    st.n_fields, st.field_names, st.min_word_len = len(field_names), names, min_word_len
+    st.n_stopwords, st.stopwords = len(stopwords), stops
+    st.overshort_step, st.stopword_step, st.match_mode, st.ngram_cjk = overshort_step, stopword_step, match_mode, int(ngram_cjk)
+    h = C.c_void_p()
+    rc = l.mgpu_parse_query(C.byref(st), text.encode("utf-8"), C.byref(h))
+    if not h:
+        raise MgpuError(rc, "mgpu_parse_query: bad arguments")
+    try:
+        if rc != MGPU_OK:
+            raise MgpuError(rc, l.mgpu_parsed_error(h).decode("utf-8", "replace"))
+        q = c_query()
+        q.ranker = -1
+        rc = l.mgpu_parsed_fill(h, C.byref(q))
+        if rc != MGPU_OK:
+            raise MgpuError(rc, "mgpu_parsed_fill")
+
+        def build(i):
+            cn = q.nodes[i]
+            n = Node(cn.op, oparg=cn.oparg, field_mask=cn.field_mask, field_max_pos=cn.field_max_pos)
+            for k in range(cn.first_word, cn.first_word + cn.n_words):
+                w = q.words[k]
+                n.words.append(Keyword(w.word.decode("utf-8"), w.atom_pos, boost=w.boost, field_start=bool(w.field_start), field_end=bool(w.field_end), excluded=bool(w.excluded)))
+            for k in range(cn.first_child, cn.first_child + cn.n_children):
+                n.children.append(build(q.children[k]))
+            return n
+
+        root = build(q.root)
+        return root, (q.ranker if q.ranker >= 0 else None), l.mgpu_parsed_warning(h).decode("utf-8", "replace")
+    finally:
+        l.mgpu_parsed_free(h)
 
 
 class Query:

@@ -7,7 +7,7 @@ each test.xml's <db_insert>/<custom_insert>; the expected results come straight 
 (PHP serialize(), see php_unserialize.py).  Query TREES are written by hand below, in the shape the
 reference's parser produces (XQParser_t::AddOp n-ary nodes, one keyword per leaf, phrase/proximity
 nodes with word lists, atom positions 1,2,3.. in query order, src/sphinxquery.cpp:1267, 1634-1678),
-because the parser itself needs bison and is out of scope.
+because the reference's parser needs bison; tests/test_query_parser.py checks mgpu_parse_query (the restated parser) against them.
 
 Tree notation: ["kw", word, atompos, fieldmask?], ["and"|"or"|"andnot"|"maybe", child...],
 ["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...], ["before", child...], ["notnear", N, must, not].
@@ -77,7 +77,9 @@ q019 = [
     (9, "我", ["kw", "我", 1]),
     (10, "basic | china", ["or", ["kw", "basic", 1], ["kw", "china", 2]]),
     (11, '"test program" | basic', ["or", ["phrase", [["test", 1], ["program", 2]]], ["kw", "basic", 3]]),
-    (12, '"test that"~3 | basic', ["or", ["prox", 3, [["test", 1], ["that", 2]]], ["kw", "basic", 3]]),
+    # after "..."~N the parser's position is FixupAtomPos() = last word + 1 and the next keyword advances it again (src/sphinxquery.y:103,
+    # src/sphinxquery.cpp:1267): `basic` sits at 4, found when mgpu_parse_query was checked against these trees
+    (12, '"test that"~3 | basic', ["or", ["prox", 3, [["test", 1], ["that", 2]]], ["kw", "basic", 4]]),
     (14, "@title sample @body -basic", ["andnot", ["kw", "sample", 1, TITLE], ["kw", "basic", 2, BODY]]),
     (15, "-basic|perl sample", ["andnot", ["kw", "sample", 3], ["or", ["kw", "basic", 1], ["kw", "perl", 2]]]),
     (17, "77", ["kw", "77", 1]),
@@ -366,7 +368,7 @@ q349 = {0: NN(1, K("a", 1), K("c", 2)), 1: NN(2, K("a", 1), K("c", 2)), 2: NN(3,
         24: NN(1, K("d", 1), K("a", 2)), 25: NN(3, K("d", 1), K("a", 2)), 26: NN(1, K("c", 1), K("x", 2)), 27: NN(2, K("c", 1), K("x", 2)),
         28: NN(3, K("c", 1), K("x", 2)), 29: NN(2, K("x", 1), K("c", 2)),
         30: NN(2, NN(3, PH("ab", 1), ["or", K("d", 3), K("e", 4)]), K("c", 5)),
-        31: NN(1, ["prox", 4, [["a", 1], ["b", 2]]], K("c", 3)),
+        31: NN(1, ["prox", 4, [["a", 1], ["b", 2]]], K("c", 4)),
         32: NN(1, ["or", PH("ab", 1), PW("a x b", 3)], K("c", 6))}
 case = {"name": "test_349", "fields": ["title"], "attrs": ["gid"], "min_word_len": 1,
         "docs": [{"id": d[0], "fields": [d[1].replace("-", " ")], "attrs": [11]} for d in docs_349], "queries": []}

@@ -391,6 +391,36 @@ def test_hot_store_escape_and_plain_format(tmp_path):
             cpu.close()
 
 
+def test_parsed_golden_queries_on_gpu(golden_cases, golden_indexes):
+    """query text -> mgpu_parse_query -> mgpu_search_batch: the tree exactly as the restated parser shapes it (one-child AND / NOT
+    wrappers of FixupNots, OR form of "..."/1, excluded flags of TagExcluded, n-ary NEAR of TransformNear) gives the reference's
+    golden results on the CUDA path, or is refused where the hand-written tree is"""
+    import test_query_parser as TQ
+    ran = 0
+    for case in golden_cases:
+        gpu = M.Index(golden_indexes[case["name"]], device=0)
+        try:
+            for qi, q in enumerate(case["queries"]):
+                query = helpers.golden_query(case, q)
+                query.root = TQ.parse_case_query(case, qi)[0]
+                r = gpu.search([query]).get(0)
+                if q.get("gpu_unsupported"):
+                    assert r["status"] == M.MGPU_E_UNSUPPORTED, (case["name"], q["text"], r["status"])
+                    continue
+                assert r["status"] == 0, (case["name"], q["text"], r["status"])
+                got = list(zip(r["docid"], r["weight"]))
+                if q.get("ids_only"):
+                    got = [(d, 0) for d, _ in got]
+                if q.get("limit"):
+                    got = got[:q["limit"]]
+                assert got == [tuple(m) for m in q["expect"]["matches"]], (case["name"], q["text"])
+                assert r["total_found"] == q["expect"]["total_found"]
+                ran += 1
+        finally:
+            gpu.close()
+    assert ran >= 130
+
+
 def test_golden_vectors_on_gpu_dict_crc(golden_cases, golden_indexes_crc, tmp_path):
     """dict=crc indexes (word ids = sphFNV64 of the keyword, src/sphinx.cpp:18263-18339): mgpu_index_open reads the id-keyed
     dictionary, query keywords are hashed at bind time; same golden results. Plus the sharded handle over two crc shards"""

@@ -109,7 +109,7 @@ def test_ctypes_mirrors_match_the_header(tmp_path):
     import subprocess
     pairs = [("mgpu_xqkeyword", M.c_xqkeyword), ("mgpu_xqnode", M.c_xqnode), ("mgpu_sortkey", M.c_sortkey), ("mgpu_filter", M.c_filter),
              ("mgpu_query", M.c_query), ("mgpu_wordstat", M.c_wordstat), ("mgpu_result", M.c_result), ("mgpu_batch_stats", M.c_batch_stats), ("mgpu_sharded_stats", M.c_sharded_stats),
-             ("mgpu_build_doc_input", M.c_build_doc_input), ("mgpu_synth_params", M.SynthParams)]
+             ("mgpu_build_doc_input", M.c_build_doc_input), ("mgpu_synth_params", M.SynthParams), ("mgpu_parser_settings", M.c_parser_settings)]
     src = tmp_path / "sizes.c"
     body = "".join('printf("%%s %%zu %%zu\\n", "%s", sizeof(%s), offsetof(%s, %s));\n' % (c, c, c, py._fields_[-1][0]) for c, py in pairs)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mgpu.h"\n#include "mgpu_writer.h"\nint main(void){\n' + body + "return 0;}\n")

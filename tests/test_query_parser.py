@@ -1,0 +1,192 @@
+"""Query front-end: mgpu_parse_query restates XQParser_t (src/sphinxquery.cpp:1011-1830, grammar
+src/sphinxquery.y) + XQParseHelper_c::FixupTree (:343-387) + PrepareQueryEmulation (src/searchd.cpp:2141-2190).
+
+Pinned two ways on the reference's own test queries (the `text` of every golden vector is the string test.xml sends to searchd):
+the parsed tree equals the hand-transcribed tree of tests/golden/make_golden.py, and the parsed tree run through the oracle gives
+the reference's model.bin results. Host only: no GPU involved."""
+import re
+
+import pytest
+
+import helpers
+import manticoresearch_b200.mgpu as M
+
+# the legacy match modes of the golden cases (test.xml <query mode="...">); everything else is extended2
+LEGACY = {("test_017", 0): M.MATCH_PHRASE, ("test_017", 1): M.MATCH_PHRASE, ("test_017", 2): M.MATCH_PHRASE, ("test_017", 3): M.MATCH_PHRASE,
+          ("test_015", 0): M.MATCH_PHRASE, ("test_015", 1): M.MATCH_PHRASE, ("test_015", 2): M.MATCH_PHRASE, ("test_015", 3): M.MATCH_PHRASE,
+          ("test_016", 0): M.MATCH_ANY, ("test_016", 1): M.MATCH_ANY}
+
+OPS = {M.OP_AND: "and", M.OP_OR: "or", M.OP_ANDNOT: "andnot", M.OP_MAYBE: "maybe", M.OP_BEFORE: "before"}
+
+
+def match_text(text):
+    """the MATCH() argument of a SphinxQL golden query, or the text itself"""
+    m = re.search(r"match\s*\(\s*'(.*?)'\s*\)", text)
+    return m.group(1) if m else text
+
+
+def compact(n):
+    """Node -> the compact form of make_golden.py; one-child AND / NOT wrappers (FixupNots leaves them, ExtNode_i::Create folds them) dropped"""
+    if n.words:
+        if len(n.words) == 1 and n.op == M.OP_AND:
+            k = n.words[0]
+            out = ["kw", k.word, k.atom_pos]
+            mods = {}
+            if k.field_start:
+                mods["start"] = 1
+            if k.field_end:
+                mods["end"] = 1
+            if n.field_max_pos:
+                mods["max_pos"] = n.field_max_pos
+            if n.field_mask != 0xFFFFFFFF or mods:
+                out.append(n.field_mask)
+            if mods:
+                out.append(mods)
+            return out
+        ws = [[k.word, k.atom_pos] for k in n.words]
+        if n.op == M.OP_PHRASE:
+            return ["phrase", ws] + ([n.field_mask] if n.field_mask != 0xFFFFFFFF else [])
+        if n.op == M.OP_PROXIMITY:
+            return ["prox", n.oparg, ws]
+        if n.op == M.OP_QUORUM:
+            return ["quorum", n.oparg, ws]
+        raise AssertionError(n.op)
+    kids = [compact(c) for c in n.children]
+    if n.op in (M.OP_AND, M.OP_NOT) and len(kids) == 1:
+        return kids[0]
+    if n.op == M.OP_NEAR:
+        return ["near", n.oparg] + kids
+    if n.op == M.OP_NOTNEAR:
+        return ["notnear", n.oparg] + kids
+    return [OPS[n.op]] + kids
+
+
+def parse_case_query(case, qi):
+    q = case["queries"][qi]
+    return M.parse_query(match_text(q["text"]), case["fields"], min_word_len=case.get("min_word_len", 1), stopwords=case.get("stopwords", ()),
+                         match_mode=LEGACY.get((case["name"], qi), M.MATCH_EXTENDED))
+
+
+def _cases():
+    return [(c["name"], i) for c in helpers.load_golden() for i in range(len(c["queries"]))]
+
+
+@pytest.mark.parametrize("case_name,qi", _cases())
+def test_parsed_tree_equals_hand_tree_and_reproduces_golden(golden_cases, golden_indexes, case_name, qi):
+    case = next(c for c in golden_cases if c["name"] == case_name)
+    q = case["queries"][qi]
+    root, ranker, _ = parse_case_query(case, qi)
+    def transformed(t):     # TransformQuorum (src/sphinx.cpp:14643-14669): "a b"/1 reaches the index as an OR; the planner takes either form
+        if t[0] == "quorum" and t[1] == 1:
+            return ["or"] + [["kw", w, p] for w, p in t[2]]
+        return [transformed(c) if isinstance(c, list) and c and isinstance(c[0], str) and c[0] in
+                ("kw", "and", "or", "andnot", "maybe", "phrase", "prox", "quorum", "near", "before", "notnear") else c for c in t]
+
+    hand = transformed(q["tree"])
+    assert compact(root) == hand, (q["text"], compact(root), hand)
+    if ranker is not None:
+        assert ranker == helpers.RANKERS[q["ranker"]], q["text"]
+    # the parsed tree, exactly as the parser shaped it, through the oracle == the reference's result
+    query = helpers.golden_query(case, q)
+    query.root = root
+    idx = helpers.OracleIndex(golden_indexes[case_name])
+    try:
+        r = idx.search([query]).get(0)
+        assert r["status"] == 0, q["text"]
+        got = list(zip(r["docid"], r["weight"]))
+        if q.get("ids_only"):
+            got = [(d, 0) for d, _ in got]
+        if q.get("limit"):
+            got = got[:q["limit"]]
+        assert got == [tuple(m) for m in q["expect"]["matches"]], q["text"]
+        assert r["total_found"] == q["expect"]["total_found"], q["text"]
+    finally:
+        idx.close()
+
+
+FIELDS = ["title", "body"]
+
+
+def P(text, **kw):
+    return compact(M.parse_query(text, FIELDS, **kw)[0])
+
+
+def test_operators_and_fixups():
+    assert P("a b c") == ["and", ["kw", "a", 1], ["kw", "b", 2], ["kw", "c", 3]]
+    assert P("a | b | c") == ["or", ["kw", "a", 1], ["kw", "b", 2], ["kw", "c", 3]]
+    assert P("a MAYBE b") == ["maybe", ["kw", "a", 1], ["kw", "b", 2]]
+    assert P("a maybe b") == ["and", ["kw", "a", 1], ["kw", "maybe", 2], ["kw", "b", 3]]      # operators are case sensitive
+    assert P("a -b") == ["andnot", ["kw", "a", 1], ["kw", "b", 2]]
+    assert P("a !b !c") == ["andnot", ["kw", "a", 1], ["or", ["kw", "b", 2], ["kw", "c", 3]]]
+    assert P("(a b) | c") == ["or", ["and", ["kw", "a", 1], ["kw", "b", 2]], ["kw", "c", 3]]
+    assert P("a (b | c) d") == ["and", ["kw", "a", 1], ["or", ["kw", "b", 2], ["kw", "c", 3]], ["kw", "d", 4]]
+    assert P("Hello WORLD_1") == ["and", ["kw", "hello", 1], ["kw", "world_1", 2]]
+    assert P("well-known fact") == ["and", ["kw", "well", 1], ["kw", "known", 2], ["kw", "fact", 3]]   # a dash inside a word separates
+    assert P('"a b c"~5 d') == ["and", ["prox", 5, [["a", 1], ["b", 2], ["c", 3]]], ["kw", "d", 5]]     # FixupAtomPos: last word + 1, then the keyword's own step
+    assert [k.excluded for k in M.parse_query("a -(b c)", FIELDS)[0].all_keywords()] == [False, True, True]
+    assert P('"a b c"/2 d') == ["and", ["quorum", 2, [["a", 1], ["b", 2], ["c", 3]]], ["kw", "d", 5]]   # the threshold token takes one
+    assert P('"single"') == ["kw", "single", 1]                                                          # FixupDegenerates
+    assert P('"one"/3') == ["kw", "one", 1]
+    assert P("a << b << c") == ["before", ["kw", "a", 1], ["kw", "b", 2], ["kw", "c", 3]]
+    assert P("a NEAR/3 b NEAR/3 c") == ["near", 3, ["kw", "a", 1], ["kw", "b", 2], ["kw", "c", 3]]
+    assert P("a NEAR/3 b NEAR/4 c") == ["near", 4, ["near", 3, ["kw", "a", 1], ["kw", "b", 2]], ["kw", "c", 3]]
+    assert P("a NOTNEAR/2 b") == ["notnear", 2, ["kw", "a", 1], ["kw", "b", 2]]
+    assert P("a NEAR b") == ["and", ["kw", "a", 1], ["kw", "near", 2], ["kw", "b", 3]]                  # NEAR without /N is a keyword
+    assert P("") == ["and"] and P("  .. ,, ") == ["and"]                                                 # nothing to search for: one empty node
+
+
+def test_field_limits_and_modifiers():
+    assert P("@title a b @body c") == ["and", ["kw", "a", 1, 1], ["kw", "b", 2, 1], ["kw", "c", 3, 2]]
+    assert P("@(title,body) a") == ["kw", "a", 1, 3]
+    assert P("@!body a") == ["kw", "a", 1, 0xFFFFFFFD]
+    assert P("@* a") == ["kw", "a", 1]
+    assert P("@title[5] a") == ["kw", "a", 1, 1, {"max_pos": 5}]
+    assert P("(@title a) b") == ["and", ["kw", "a", 1, 1], ["kw", "b", 2]]         # a limit inside parentheses ends with them
+    assert P("@title (a b) c") == ["and", ["kw", "a", 1, 1], ["kw", "b", 2, 1], ["kw", "c", 3, 1]]       # AddOp appends to the AND on its left
+    assert P('@body "a b"') == ["phrase", [["a", 1], ["b", 2]], 2]
+    assert P("^a b$") == ["and", ["kw", "a", 1, 0xFFFFFFFF, {"start": 1}], ["kw", "b", 2, 0xFFFFFFFF, {"end": 1}]]
+    root = M.parse_query("a^1.5 b", FIELDS)[0]
+    assert [k.boost for k in root.all_keywords()] == [1.5, 1.0]
+    with pytest.raises(M.MgpuError) as e:
+        P("@nosuchfield a")
+    assert e.value.code == M.MGPU_E_BAD_QUERY and "nosuchfield" in str(e.value)
+
+
+def test_positions_stopwords_overshort_escapes():
+    assert P("walking in my shoes", min_word_len=3) == ["and", ["kw", "walking", 1], ["kw", "shoes", 4]]
+    assert P("the lord of the rings", stopwords=("the", "of")) == ["and", ["kw", "lord", 2], ["kw", "rings", 5]]
+    assert P("the lord of the rings", stopwords=("the", "of"), stopword_step=0) == ["and", ["kw", "lord", 1], ["kw", "rings", 2]]
+    assert P('"the lord of the rings"', stopwords=("the", "of")) == ["phrase", [["lord", 2], ["rings", 5]]]
+    assert P(r"aaa\!bbb \-ccc") == ["and", ["kw", "aaa", 1], ["kw", "bbb", 2], ["kw", "ccc", 3]]        # escaped specials separate
+    assert P("walking -in shoes", min_word_len=3) == ["and", ["kw", "walking", 1], ["kw", "shoes", 3]]   # 'la !word': the NOT goes with its overshort operand
+    assert P("привет МИР") == ["and", ["kw", "привет", 1], ["kw", "мир", 2]]
+    assert P("我吐") == ["and", ["kw", "我", 1], ["kw", "吐", 2]]
+
+
+def test_legacy_match_modes():
+    root, ranker, _ = M.parse_query('hello "world" -x', FIELDS, match_mode=M.MATCH_ALL)
+    assert compact(root) == ["and", ["kw", "hello", 1], ["kw", "world", 2], ["kw", "x", 3]] and ranker == M.RANK_PROXIMITY
+    root, ranker, _ = M.parse_query("hello world", FIELDS, match_mode=M.MATCH_ANY)
+    assert compact(root) == ["or", ["kw", "hello", 1], ["kw", "world", 2]] and ranker == M.RANK_MATCHANY
+    root, ranker, _ = M.parse_query("hello | world", FIELDS, match_mode=M.MATCH_PHRASE)
+    assert compact(root) == ["phrase", [["hello", 1], ["world", 2]]] and ranker == M.RANK_PROXIMITY
+    root, ranker, _ = M.parse_query("hello | world", FIELDS, match_mode=M.MATCH_BOOLEAN)
+    assert compact(root) == ["or", ["kw", "hello", 1], ["kw", "world", 2]] and ranker == M.RANK_NONE
+
+
+@pytest.mark.parametrize("text,needle", [
+    ("-a", "single NOT"), ("-a -b", "NOT operators only"), ("a | (-b)", "NOT is not allowed within OR"), ("a << -b", "before operand"),
+    ('"a b"/0', "quorum threshold too low"), ('"a b"~0', "proximity threshold too low"), ("a (b", "syntax error"), ("a | | b", "syntax error"),
+    ('"a b', "syntax error"), ('"a b"/1.5', "quorum threshold out of bounds"),
+])
+def test_parse_errors(text, needle):
+    with pytest.raises(M.MgpuError) as e:
+        M.parse_query(text, FIELDS)
+    assert e.value.code == M.MGPU_E_BAD_QUERY and needle in str(e.value), str(e.value)
+
+
+@pytest.mark.parametrize("text", ["a SENTENCE b", "a PARAGRAPH b", "ZONE:h1 a", "ZONESPAN:(h1,h2) a"])
+def test_unsupported_syntax_is_refused_not_guessed(text):
+    with pytest.raises(M.MgpuError) as e:
+        M.parse_query(text, FIELDS)
+    assert e.value.code == M.MGPU_E_UNSUPPORTED
