@@ -65,7 +65,9 @@ enum {
 enum {
 	MGPU_KEYPART_ROWID = 0,
 	MGPU_KEYPART_WEIGHT = 1,
-	MGPU_KEYPART_INT = 2      /* fixed-width integer row attribute (<=32 bits on the GPU path) */
+	MGPU_KEYPART_INT = 2,     /* fixed-width integer row attribute (32 or 64 bits, dword aligned) */
+	MGPU_KEYPART_FLOAT = 3    /* SPH_KEYPART_FLOAT (src/sphinxsort.cpp:4690-4696): a 32-bit row attribute compared as an IEEE float;
+	                             -0 ties with +0 as in the reference; NaNs (no order in the reference) sort by their bit pattern */
 };
 
 /* ---- filters: the integer subset of ISphFilter::Eval (src/sphinxfilter.h:51) ---- */
@@ -102,7 +104,7 @@ typedef struct mgpu_xqnode {
 /* one key of CSphMatchComparatorState (src/sortsetup.h:19-57) */
 typedef struct mgpu_sortkey {
 	int32_t			kind;          /* MGPU_KEYPART_* */
-	int32_t			attr;          /* attribute index in the index schema (MGPU_KEYPART_INT) */
+	int32_t			attr;          /* attribute index in the index schema (MGPU_KEYPART_INT / MGPU_KEYPART_FLOAT) */
 	int32_t			desc;          /* bit of m_uAttrDesc */
 } mgpu_sortkey;
 
@@ -301,6 +303,14 @@ void			mgpu_unpack_key ( const uint64_t key[2], uint32_t * global_rowid, int32_t
  * arrays; used by the parity tests of the VByte block decoder against the oracle's
  * DiskIndexQword_c::ReadNext restatement (src/sphinx.cpp:511-549). host arrays sized docs. */
 int				mgpu_decode_doclist ( mgpu_index * idx, const char * word, uint32_t * rowid, uint32_t * hits, uint32_t * fields, uint64_t * hitlist_pos, int64_t capacity, int64_t * n_out );
+
+/* ------------------------------------------------------------------------------------- */
+/* Index consistency check: the checks of DiskIndexChecker_c (`indextool --check`, src/indexcheck.cpp:443-983,
+ * 1292-1317) over the files the query path loads: schema, attribute row count, dead-row map size, duplicate document ids, dictionary
+ * order / counts / checkpoints, every doclist decoded end to end (rowid order and bounds, hit counts, hitlist order, field masks,
+ * hitlist offsets) and every skiplist recomputed.  Host only, no GPU.  Returns MGPU_OK when the check ran (also when it found
+ * failures): *n_failures counts them and `report` holds the first 64 messages, one per line, in the reference's wording. */
+int				mgpu_index_check ( const char * path_prefix, int64_t * n_failures, char * report, int report_len );
 
 /* ------------------------------------------------------------------------------------- */
 /* Query front-end: extended query syntax -> the flattened tree above.

@@ -486,7 +486,14 @@ __device__ __forceinline__ Key128_t MakeKey ( const DevIndex_t & tIdx, const Dev
 			int iBits = 32;
 			if ( t.m_eKind==1 )			v = uW;
 			else if ( t.m_eKind==0 )	v = uRowid + tIdx.m_uRowidBase;
-			else
+			else if ( t.m_eKind==3 )
+			{
+				// SPH_KEYPART_FLOAT: IEEE bits -> an unsigned key of the same order (-0 joins +0)
+				uint32_t u = (uint32_t)LoadAttr ( tIdx, uRowid, t.m_iDwordOff, 32 );
+				if ( u==0x80000000u )
+					u = 0;
+				v = ( u & 0x80000000u ) ? (uint32_t)~u : ( u | 0x80000000u );
+			} else
 			{
 				int64_t a = LoadAttr ( tIdx, uRowid, t.m_iDwordOff, t.m_iBitCount );
 				if ( t.m_iBitCount==64 ) { v = (uint64_t)a ^ 0x8000000000000000ull; iBits = 64; }

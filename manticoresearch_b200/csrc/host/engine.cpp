@@ -1058,6 +1058,15 @@ struct Planner_c
 				t.m_iDwordOff = (int)( a.m_iBitOffset/32 );
 				t.m_iBitCount = (int)a.m_iBitCount;
 				iBits = t.m_iBitCount;
+			} else if ( k.kind==MGPU_KEYPART_FLOAT )
+			{
+				if ( k.attr<0 || k.attr>=(int)m_tIndex.m_tHdr.m_dAttrs.size() )
+					return MGPU_E_BAD_QUERY;
+				const SchemaAttr_t & a = m_tIndex.m_tHdr.m_dAttrs[k.attr];
+				if ( a.m_iBitCount!=32 || ( a.m_iBitOffset & 31 ) )
+					return MGPU_E_UNSUPPORTED;
+				t.m_iDwordOff = (int)( a.m_iBitOffset/32 );
+				t.m_iBitCount = 32;
 			} else if ( k.kind!=MGPU_KEYPART_WEIGHT && k.kind!=MGPU_KEYPART_ROWID )
 				return MGPU_E_UNSUPPORTED;
 			iCur -= iBits;

@@ -16,7 +16,7 @@ MGPU_E_IO, MGPU_E_FORMAT, MGPU_E_UNSUPPORTED, MGPU_E_BAD_QUERY, MGPU_E_NO_DEVICE
 
 OP_AND, OP_OR, OP_MAYBE, OP_NOT, OP_ANDNOT, OP_BEFORE, OP_PHRASE, OP_PROXIMITY, OP_QUORUM, OP_NEAR, OP_NOTNEAR = range(11)
 RANK_PROXIMITY_BM25, RANK_BM25, RANK_NONE, RANK_WORDCOUNT, RANK_PROXIMITY, RANK_MATCHANY, RANK_FIELDMASK, RANK_SPH04 = range(8)
-KEYPART_ROWID, KEYPART_WEIGHT, KEYPART_INT = range(3)
+KEYPART_ROWID, KEYPART_WEIGHT, KEYPART_INT, KEYPART_FLOAT = range(4)
 FILTER_RANGE, FILTER_VALUES = range(2)
 
 
@@ -161,6 +161,7 @@ def load_library(path=None):
         "mgpu_merge_shard_keys": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
         "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
         "mgpu_decode_doclist": (C.c_int, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), i64, C.POINTER(i64)]),
+        "mgpu_index_check": (C.c_int, [C.c_char_p, C.POINTER(i64), C.c_char_p, C.c_int]),
         "mgpu_parse_query": (C.c_int, [C.POINTER(c_parser_settings), C.c_char_p, C.POINTER(vp)]),
         "mgpu_parsed_fill": (C.c_int, [vp, C.POINTER(c_query)]),
         "mgpu_parsed_error": (C.c_char_p, [vp]),
@@ -220,7 +221,7 @@ EXPORTED_SYMBOLS = [
     "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist",
     "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
     "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
-    "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
+    "mgpu_index_check", "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
 ]
 
 # ---------------------------------------------------------------------------------------------
@@ -316,6 +317,16 @@ class Filter:
 
 
 MATCH_ALL, MATCH_ANY, MATCH_PHRASE, MATCH_BOOLEAN, MATCH_EXTENDED = range(5)
+
+
+def check_index(path_prefix):
+    """mgpu_index_check -> (number of failures, report text). Host only."""
+    n = C.c_int64(0)
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib().mgpu_index_check(path_prefix.encode(), C.byref(n), buf, len(buf))
+    if rc != MGPU_OK:
+        raise MgpuError(rc, "mgpu_index_check: " + buf.value.decode("utf-8", "replace").strip())
+    return n.value, buf.value.decode("utf-8", "replace")
 
 
 def parse_query(text, field_names, min_word_len=1, stopwords=(), match_mode=MATCH_EXTENDED, ngram_cjk=True, overshort_step=1, stopword_step=1):

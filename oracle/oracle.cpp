@@ -2494,7 +2494,7 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 		{
 			tComp.m_dKind[i] = q.sort_keys[i].kind;
 			tComp.m_dDesc[i] = q.sort_keys[i].desc;
-			if ( q.sort_keys[i].kind==MGPU_KEYPART_INT && ( q.sort_keys[i].attr<0 || q.sort_keys[i].attr>=(int)tIndex.m_dAttrs.size() ) )
+			if ( ( q.sort_keys[i].kind==MGPU_KEYPART_INT || q.sort_keys[i].kind==MGPU_KEYPART_FLOAT ) && ( q.sort_keys[i].attr<0 || q.sort_keys[i].attr>=(int)tIndex.m_dAttrs.size() ) )
 				return MGPU_E_BAD_QUERY;
 		}
 	}
@@ -2629,7 +2629,19 @@ static int SearchOne ( const Index_t & tIndex, const mgpu_query & q, mgpu_result
 		tMatch.m_tRowID = tDoc.m_tRowID;
 		tMatch.m_iWeight = iWeight*iIndexWeight;
 		for ( int i=0; i<tComp.m_nKeys; ++i )
-			tMatch.m_dKeys[i] = tComp.m_dKind[i]==MGPU_KEYPART_INT ? tIndex.GetAttr ( tDoc.m_tRowID, q.sort_keys[i].attr ) : 0;
+		{
+			tMatch.m_dKeys[i] = ( tComp.m_dKind[i]==MGPU_KEYPART_INT || tComp.m_dKind[i]==MGPU_KEYPART_FLOAT ) ? tIndex.GetAttr ( tDoc.m_tRowID, q.sort_keys[i].attr ) : 0;
+			if ( tComp.m_dKind[i]==MGPU_KEYPART_FLOAT )
+			{
+				// SPH_KEYPART_FLOAT, src/sphinxsort.cpp:4690-4696: compared as floats. Kept as an integer of the same order so that the
+				// comparator stays a strict weak order when a row holds a NaN (the reference's aa>bb is false both ways there)
+				DWORD u = (DWORD)tMatch.m_dKeys[i];
+				float f; memcpy ( &f, &u, 4 );
+				if ( f==0.0f )
+					u = 0;
+				tMatch.m_dKeys[i] = ( u & 0x80000000u ) ? (int64_t)(DWORD)~u : (int64_t)( u | 0x80000000u );
+			}
+		}
 		tQueue.Push ( tMatch );
 	}
 

@@ -391,6 +391,21 @@ def test_hot_store_escape_and_plain_format(tmp_path):
             cpu.close()
 
 
+def test_float_sort_key_on_gpu(tmp_path):
+    """MGPU_KEYPART_FLOAT: the packed key holds the float's order-preserving integer image; same order as the oracle's float comparator"""
+    import test_oracle_operators as TO
+    prefix, _ = TO._float_corpus(tmp_path)
+    gpu, cpu = M.Index(prefix, device=0), helpers.OracleIndex(prefix)
+    try:
+        qs = TO.float_sort_queries()
+        g, c = gpu.search(qs), cpu.search(qs)
+        for i in range(len(qs)):
+            helpers.assert_same_results(g.get(i), c.get(i), ctx="float sort key, query %d" % i)
+    finally:
+        gpu.close()
+        cpu.close()
+
+
 def test_parsed_golden_queries_on_gpu(golden_cases, golden_indexes):
     """query text -> mgpu_parse_query -> mgpu_search_batch: the tree exactly as the restated parser shapes it (one-child AND / NOT
     wrappers of FixupNots, OR form of "..."/1, excluded flags of TagExcluded, n-ary NEAR of TransformNear) gives the reference's

@@ -149,3 +149,58 @@ def test_shard_builder_is_a_rowid_range_of_the_corpus(tmp_path):
     finally:
         fi.close()
         si.close()
+
+
+def test_index_check_passes_what_the_writer_and_the_reference_wrote(tmp_path, golden_indexes, golden_indexes_crc):
+    """mgpu_index_check (DiskIndexChecker_c, src/indexcheck.cpp): no failures on the product writer's indexes (synthetic with skiplists,
+    golden corpora in both dictionary forms, plain hit format) nor on the index the reference's own writer produced"""
+    prefix = str(tmp_path / "chk")
+    M.build_synthetic(prefix, M.SynthParams(4000, vocab=3000, threads=2))
+    assert M.check_index(prefix) == (0, "")
+    for name in ("test_019", "test_116", "test_055"):
+        assert M.check_index(golden_indexes[name]) == (0, ""), name
+        assert M.check_index(golden_indexes_crc[name]) == (0, ""), name
+    docs = [{"id": 5 + i, "fields": [[("a", 1), ("b", 2)], [("a", 1)] * 0 + [("c", p + 1) for p in range(1 + i % 4)]], "attrs": [i]} for i in range(200)]
+    plain = str(tmp_path / "plain")
+    M.build_index(plain, ["title", "body"], docs, attr_names=["n"], hit_format_inline=False)
+    assert M.check_index(plain) == (0, "")
+    ref = os.path.join(ROOT, "tests", "golden", "ref_index", "index.0")
+    assert M.check_index(ref) == (0, "")
+
+
+def test_index_check_finds_corruption(tmp_path):
+    """each kind of damage is reported in the reference's words, and never crashes the checker"""
+    import shutil
+    prefix = str(tmp_path / "ok")
+    M.build_synthetic(prefix, M.SynthParams(3000, vocab=2000, threads=1))
+
+    def damaged(ext, fn):
+        dst = str(tmp_path / ("bad_" + ext))
+        for e in ("sph", "spi", "spd", "spp", "spe", "spa", "spm"):
+            shutil.copy(prefix + "." + e, dst + "." + e)
+        raw = bytearray(open(dst + "." + ext, "rb").read())
+        fn(raw)
+        open(dst + "." + ext, "wb").write(bytes(raw))
+        return M.check_index(dst)
+
+    def flip(pos, val=None):
+        def f(raw):
+            raw[pos] = (raw[pos] ^ 0x15) if val is None else val
+        return f
+
+    n, rep = damaged("spe", flip(40))
+    assert n > 0 and "skiplist" in rep
+    n, rep = damaged("spd", flip(1000))
+    assert n > 0
+    n, rep = damaged("spp", lambda raw: raw.__setitem__(slice(5000, 5004), b"\0\0\0\0"))     # hitlists end early
+    assert n > 0 and ("hit" in rep)
+    n, rep = damaged("spm", lambda raw: raw.extend(b"\0\0\0\0"))
+    assert n == 1 and "dead row map" in rep
+    n, rep = damaged("spa", lambda raw: raw.__setitem__(slice(16, 24), raw[0:8]))      # row 1 gets row 0's document id
+    assert n >= 1 and "duplicate of docid" in rep
+    n, rep = damaged("spd", lambda raw: raw.__delitem__(slice(len(raw) // 2, len(raw))))
+    assert n > 0
+    n, rep = damaged("spi", lambda raw: raw.__setitem__(slice(2, 6), b"zzzz"))       # the first keyword now sorts behind the second
+    assert n > 0 and "word order decreased" in rep
+    with pytest.raises(M.MgpuError):
+        M.check_index(str(tmp_path / "nosuchindex"))

@@ -110,3 +110,45 @@ def test_nway_near_and_before_are_contained_and_monotone(corpus):
         assert before <= allof
         # a << b << c implies a << b
         assert before <= set(_rows(idx, M.Node(M.OP_BEFORE, children=kws()[:2])))
+
+
+def _float_corpus(tmp_path, n=300):
+    import random
+    import struct
+    rng = random.Random(11)
+    special = [0.0, -0.0, 1.5, -1.5, 3.0e38, -3.0e38, 1e-40, -1e-40, float("inf"), float("-inf")]
+    vals = [special[i] if i < len(special) else rng.choice([rng.uniform(-100, 100), rng.randint(-3, 3) * 0.5]) for i in range(n)]
+    bits = [struct.unpack("<I", struct.pack("<f", v))[0] for v in vals]
+    docs = [{"id": 1 + i, "fields": [[("w", 1)] + ([("x", 2)] if i % 3 else [])], "attrs": [bits[i], i % 7]} for i in range(n)]
+    prefix = str(tmp_path / "flt")
+    M.build_index(prefix, ["body"], docs, attr_names=["price", "grp"])
+    return prefix, [struct.unpack("<f", struct.pack("<I", b))[0] for b in bits]
+
+
+def float_sort_queries():
+    price, grp = 1, 2       # attribute 0 is the document id
+    root = M.OR(M.kw("w", 1), M.kw("x", 2))
+    return [M.Query(root, ranker=M.RANK_BM25, max_matches=1000, sort_keys=[M.SortKey(M.KEYPART_FLOAT, price, True)]),
+            M.Query(root, ranker=M.RANK_BM25, max_matches=1000, sort_keys=[M.SortKey(M.KEYPART_FLOAT, price, False)]),
+            M.Query(root, ranker=M.RANK_BM25, max_matches=40, sort_keys=[M.SortKey(M.KEYPART_INT, grp, False), M.SortKey(M.KEYPART_FLOAT, price, True)]),
+            M.Query(root, ranker=M.RANK_BM25, max_matches=25, sort_keys=[M.SortKey(M.KEYPART_FLOAT, price, False), M.SortKey(M.KEYPART_WEIGHT, 0, True)])]
+
+
+def test_float_sort_key(tmp_path):
+    """SPH_KEYPART_FLOAT (src/sphinxsort.cpp:4690-4696): a 32-bit attribute ordered as an IEEE float, -0 == +0, ties by the next key and
+    finally by rowid ascending; checked against Python's own float ordering"""
+    prefix, vals = _float_corpus(tmp_path)
+    idx = helpers.OracleIndex(prefix)
+    try:
+        qs = float_sort_queries()
+        rs = idx.search(qs)
+        n = len(vals)
+        desc = sorted(range(n), key=lambda i: (-vals[i], i))
+        asc = sorted(range(n), key=lambda i: (vals[i], i))
+        assert list(rs.get(0)["rowid"]) == desc and list(rs.get(1)["rowid"]) == asc
+        by_grp = sorted(range(n), key=lambda i: (i % 7, -vals[i], i))[:40]
+        assert list(rs.get(2)["rowid"]) == by_grp
+        w = dict(zip(rs.get(0)["rowid"], rs.get(0)["weight"]))
+        assert list(rs.get(3)["rowid"]) == sorted(range(n), key=lambda i: (vals[i], -w[i], i))[:25]
+    finally:
+        idx.close()
