@@ -348,6 +348,25 @@ const char *	mgpu_parsed_error ( const mgpu_parsed * p );      /* XQQuery_t::m_s
 const char *	mgpu_parsed_warning ( const mgpu_parsed * p );    /* XQQuery_t::m_sParseWarning */
 void			mgpu_parsed_free ( mgpu_parsed * p );
 
+/* ------------------------------------------------------------------------------------- */
+/* Wire responder: the binary SphinxAPI `search` command for ONE local index, request packet in, reply packet out.
+ * Replaces the server side of SEARCHD_COMMAND_SEARCH: HandleCommandSearch + ParseSearchQuery (src/searchd.cpp:6932-7000, 2201-2560),
+ * the sort-mode / weight / filter setup between them and the index (src/sortsetup.cpp, src/sphinx.cpp:13903-13947) and SendResult
+ * (src/searchd.cpp:3340-3510), for client protocol versions 1.29..1.33 (0x11D..0x121).  The queries of one packet run as one
+ * mgpu_search_batch call.  Anything the hot path has no counterpart for (group-by, expression rankers / sorts, geo anchors, select
+ * lists other than "*", string and float filters, cutoff, outer order) is answered with SEARCHD_ERROR for that query, as searchd
+ * answers a query it cannot run.  No sockets: the embedding daemon owns the connection (src/netreceive_api.cpp).
+ * idx may be NULL: packets are parsed, described and answered with per-query errors (host-only use, tests).
+ * tokenizer may be NULL: min_word_len / overshort_step / stopword_step come from the index header, no stop words. */
+typedef struct mgpu_api mgpu_api;
+int				mgpu_api_create ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out );
+/* *reply points into memory owned by the responder, valid until the next call on it or mgpu_api_free. Returns MGPU_OK whenever a
+ * reply packet was produced (protocol and query errors travel inside the reply, as on the wire). */
+int				mgpu_api_handle ( mgpu_api * api, const void * request, size_t request_len, const void ** reply, size_t * reply_len );
+/* the queries of the last packet as SphinxQL-like text, one per line (what query_log_format=sphinxql logs for API queries) */
+const char *	mgpu_api_describe_last ( const mgpu_api * api );
+void			mgpu_api_free ( mgpu_api * api );
+
 int				mgpu_abi_version ( void );
 
 #ifdef __cplusplus

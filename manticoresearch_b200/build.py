@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgpu.so")
 
 CUDA_SOURCES = ["cuda/kernels.cu"]
-HOST_SOURCES = ["host/index_format.cpp", "host/engine.cpp", "host/sharded.cpp", "host/api.cpp", "host/query_parser.cpp", "host/index_check.cpp"]
+HOST_SOURCES = ["host/index_format.cpp", "host/engine.cpp", "host/sharded.cpp", "host/api.cpp", "host/query_parser.cpp", "host/index_check.cpp", "host/api_wire.cpp"]
 # the index writer + synthetic corpus: a host-only library of its own (no CUDA), so that the CPU arm of bench.py and the
 # golden-corpus builders never map libmgpu.so
 WRITER_LIB = os.path.join(HERE, "libmgpu_writer.so")

@@ -1,0 +1,252 @@
+"""Wire responder: mgpu_api_handle answers the binary SphinxAPI `search` command.
+
+The request packets are the bytes the reference's own client (api/sphinxapi.py) puts on the wire (tests/golden/api_requests.json,
+made by tests/golden/make_api_fixtures.py). CPU tests: packets parse, are described, protocol errors are answered as searchd answers
+them. GPU test: the replies carry exactly what the same queries give through mgpu_search_batch, plus the rows' attributes. When
+/root/reference is present, the replies captured on the GPU (tests/golden/api_replies.json) are read back by the reference's client."""
+import json
+import os
+import struct
+
+import pytest
+
+import helpers
+import manticoresearch_b200.mgpu as M
+
+GOLD = os.path.join(helpers.ROOT, "tests", "golden")
+REQUESTS = {k: bytes.fromhex(v) for k, v in json.load(open(os.path.join(GOLD, "api_requests.json")))["requests"].items()}
+
+SEARCHD_OK, SEARCHD_ERROR, SEARCHD_WARNING = 0, 1, 3
+WORDS = ["hello", "world", "there", "extra", "filler"]
+
+
+def corpus_docs():
+    """60 documents, fields title / body, attributes group_id / stamp; deterministic"""
+    docs = []
+    for i in range(60):
+        title = [(WORDS[(i + k) % 5], k + 1) for k in range(1 + i % 3)]
+        body = [(WORDS[(i * 7 + k * 3) % 5], k + 1) for k in range(2 + i % 5)]
+        docs.append({"id": 2 + i, "fields": [title, body], "attrs": [i % 4, 100 + (i * 13) % 90]})
+    return docs
+
+
+def build_corpus(prefix):
+    M.build_index(prefix, ["title", "body"], corpus_docs(), attr_names=["group_id", "stamp"])
+
+
+class Reader:
+    def __init__(self, raw):
+        self.raw, self.p = raw, 0
+
+    def u32(self):
+        v = struct.unpack_from(">L", self.raw, self.p)[0]
+        self.p += 4
+        return v
+
+    def u64(self):
+        v = struct.unpack_from(">Q", self.raw, self.p)[0]
+        self.p += 8
+        return v
+
+    def string(self):
+        n = self.u32()
+        s = self.raw[self.p:self.p + n].decode("utf-8")
+        self.p += n
+        return s
+
+
+def parse_reply(raw, n_queries):
+    """the reply packet as the protocol defines it (SendResult, src/searchd.cpp:3398-3510) -> (status, [result dict])"""
+    status, ver, length = struct.unpack_from(">2HL", raw, 0)
+    assert length == len(raw) - 8
+    r = Reader(raw[8:])
+    if status != SEARCHD_OK:
+        return status, r.string()
+    assert ver == 0x121
+    out = []
+    for _ in range(n_queries):
+        res = {"status": r.u32(), "error": "", "warning": ""}
+        out.append(res)
+        if res["status"] != SEARCHD_OK:
+            msg = r.string()
+            if res["status"] == SEARCHD_WARNING:
+                res["warning"] = msg
+            else:
+                res["error"] = msg
+                continue
+        res["fields"] = [r.string() for _ in range(r.u32())]
+        res["attrs"] = [(r.string(), r.u32()) for _ in range(r.u32())]
+        count, id64 = r.u32(), r.u32()
+        assert id64 == 1
+        res["matches"] = []
+        for _ in range(count):
+            m = {"id": r.u64(), "weight": r.u32(), "attrs": {}}
+            for name, typ in res["attrs"]:
+                m["attrs"][name] = r.u64() if typ == 6 else r.u32()
+            res["matches"].append(m)
+        res["total"], res["total_found"], res["time_msec"] = r.u32(), r.u32(), r.u32()
+        res["words"] = {}
+        for _ in range(r.u32()):
+            w = r.string()
+            res["words"][w] = (r.u32(), r.u32())
+    assert r.p == len(r.raw)
+    return status, out
+
+
+N_QUERIES = {"default": 1, "any_attr_desc": 1, "extended_sort_filter_weights": 1, "phrase_range_idrange": 1, "multi": 4, "positional_weights": 1}
+
+
+def test_requests_of_the_reference_client_parse(tmp_path):
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    api = M.ApiResponder(None, prefix)
+    try:
+        expect = {
+            "default": ["MATCH('hello world')", "FROM idx", "ORDER BY relevance", "LIMIT 0,20", "mode=extended2", "ranker=0", "max_matches=1000"],
+            "any_attr_desc": ["MATCH('hello there')", "ORDER BY attr_desc(group_id)", "LIMIT 1,3", "mode=any", "max_matches=50", "/* a comment */"],
+            "extended_sort_filter_weights": ["group_id IN (1,3)", "ORDER BY extended(@weight desc, group_id asc)", "ranker=1", "field_weights=(title=5)"],
+            "phrase_range_idrange": ["stamp NOT BETWEEN 100 AND 160", "id BETWEEN 3 AND 40", "mode=phrase", "LIMIT 0,100"],
+            "multi": ["MATCH('\"hello world\"~3 | extra')", "GROUP BY group_id", "MATCH('hello | (world')", "ORDER BY attr_asc(stamp)", "ranker=3"],
+            "positional_weights": ["weights=(3,1)", "MATCH('world there')"],
+        }
+        for name, req in REQUESTS.items():
+            raw = api.handle(req)
+            desc = api.describe_last()
+            assert desc.count(";\n") == N_QUERIES[name]
+            for frag in expect[name]:
+                assert frag in desc, (name, frag, desc)
+            status, results = parse_reply(raw, N_QUERIES[name])
+            assert status == SEARCHD_OK
+            errors = [r["error"] for r in results]
+            assert all(r["status"] == SEARCHD_ERROR for r in results)
+            if name == "multi":
+                assert "group-by is not supported" in errors[1] and "query error: syntax error" in errors[2]
+                assert "no index is attached" in errors[0] and "no index is attached" in errors[3]
+            else:
+                assert "no index is attached" in errors[0]
+    finally:
+        api.close()
+
+
+def test_protocol_errors(tmp_path):
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    api = M.ApiResponder(None, prefix)
+    try:
+        good = REQUESTS["default"]
+
+        def err(packet):
+            status, msg = parse_reply(api.handle(packet), 0)
+            assert status == SEARCHD_ERROR
+            return msg
+
+        assert "truncated" in err(good[:-3])
+        assert "truncated" in err(good[:40])
+        assert "truncated" in err(b"")
+        assert "unknown command" in err(struct.pack(">2HL", 7, 0x120, len(good) - 8) + good[8:])
+        assert "client version is higher" in err(struct.pack(">2HL", 0, 0x125, len(good) - 8) + good[8:])
+        assert "major command version mismatch" in err(struct.pack(">2HL", 0, 0x220, len(good) - 8) + good[8:])
+        assert "bad multi-query count" in err(good[:12] + struct.pack(">L", 0) + good[16:])
+        assert "bad multi-query count" in err(good[:12] + struct.pack(">L", 1000) + good[16:])
+        assert "truncated" in err(good[:12] + struct.pack(">L", 2) + good[16:])      # says two queries, carries one
+        # every prefix of every packet is answered, never crashes
+        for req in REQUESTS.values():
+            for cut in range(0, len(req), 7):
+                status, _ = parse_reply(api.handle(struct.pack(">2HL", 0, 0x120, max(cut - 8, 0)) + req[8:cut]), 0)
+                assert status == SEARCHD_ERROR
+    finally:
+        api.close()
+
+
+def expected_queries(gid, stamp):
+    """the mgpu queries the packets stand for, built by hand (not through the responder)"""
+    A = lambda *ws: M.AND(*[M.kw(w, i + 1) for i, w in enumerate(ws)])
+    return {
+        "default": [(M.Query(A("hello", "world"), max_matches=1000), 0, 20)],
+        "any_attr_desc": [(M.Query(M.OR(M.kw("hello", 1), M.kw("there", 2)), ranker=M.RANK_MATCHANY, max_matches=50,
+                                   sort_keys=[M.SortKey(M.KEYPART_INT, gid, True), M.SortKey(M.KEYPART_WEIGHT, 0, True)]), 1, 3)],
+        "extended_sort_filter_weights": [(M.Query(M.OR(M.kw("hello", 1), M.kw("world", 2), M.kw("there", 3)), ranker=M.RANK_BM25, max_matches=1000,
+                                                  field_weights=[5, 1], filters=[M.Filter(gid, values=[1, 3])],
+                                                  sort_keys=[M.SortKey(M.KEYPART_WEIGHT, 0, True), M.SortKey(M.KEYPART_INT, gid, False)]), 0, 20)],
+        "phrase_range_idrange": [(M.Query(M.PHRASE([("hello", 1), ("world", 2)]), ranker=M.RANK_PROXIMITY, max_matches=100,
+                                          filters=[M.Filter(stamp, 100, 160, exclude=True), M.Filter(0, 3, 40)]), 0, 100)],
+        "multi": [(M.Query(M.OR(M.PROXIMITY([("hello", 1), ("world", 2)], 3), M.kw("extra", 4)), ranker=M.RANK_WORDCOUNT, max_matches=1000), 0, 20), None, None,
+                  (M.Query(M.ANDNOT(M.kw("hello", 1).fields(1), M.kw("there", 2).fields(1)), ranker=M.RANK_WORDCOUNT, max_matches=1000,
+                           sort_keys=[M.SortKey(M.KEYPART_INT, stamp, False), M.SortKey(M.KEYPART_WEIGHT, 0, True)]), 0, 20)],
+        "positional_weights": [(M.Query(A("world", "there"), max_matches=1000, field_weights=[3, 1]), 0, 1000)],
+    }
+
+
+@pytest.mark.gpu
+def test_replies_equal_direct_search(tmp_path):
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    docs = {d["id"]: d for d in corpus_docs()}
+    gpu = M.Index(prefix, device=0)
+    api = M.ApiResponder(gpu, prefix)
+    replies = {}
+    try:
+        gid, stamp = gpu.attr_index("group_id"), gpu.attr_index("stamp")
+        exp = expected_queries(gid, stamp)
+        nonempty = 0
+        for name, req in REQUESTS.items():
+            raw = api.handle(req)
+            replies[name] = raw.hex()
+            status, results = parse_reply(raw, N_QUERIES[name])
+            assert status == SEARCHD_OK
+            for qi, res in enumerate(results):
+                if exp[name][qi] is None:
+                    assert res["status"] == SEARCHD_ERROR and res["error"]
+                    continue
+                query, offset, limit = exp[name][qi]
+                d = gpu.search([query]).get(0)
+                assert d["status"] == 0
+                assert res["status"] == SEARCHD_OK, (name, qi, res["error"])
+                assert res["fields"] == ["title", "body"] and res["attrs"] == [("group_id", 1), ("stamp", 1)]
+                want = list(zip(d["docid"], d["weight"]))[offset:offset + limit]
+                assert [(m["id"], m["weight"]) for m in res["matches"]] == want, (name, qi)
+                for m in res["matches"]:
+                    assert m["attrs"] == {"group_id": docs[m["id"]]["attrs"][0], "stamp": docs[m["id"]]["attrs"][1]}
+                assert res["total"] == len(d["docid"]) and res["total_found"] == d["total_found"]
+                kws = query.keywords()
+                stats = gpu.search([query]).word_stats(0, len(kws))
+                assert res["words"] == {k.word: tuple(s) for k, s in zip(kws, stats)}
+                nonempty += len(want) > 0
+        assert nonempty >= 6
+        out_dir = os.path.join(helpers.ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "api_replies.json"), "w") as f:
+                json.dump({"source": "mgpu_api_handle on the B200, tests/test_api_wire.py::test_replies_equal_direct_search", "replies": replies}, f, indent=1)
+    finally:
+        api.close()
+        gpu.close()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/api/sphinxapi.py") or not os.path.exists(os.path.join(GOLD, "api_replies.json")),
+                    reason="needs the reference's client (this container) and the replies captured on the GPU")
+def test_reference_client_reads_the_replies():
+    """the reference's client sends its request into a fake socket and parses the reply packet the responder produced on the GPU"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_api_fixtures", os.path.join(GOLD, "make_api_fixtures.py"))
+    F = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(F)
+    S = F.load_client()
+    replies = {k: bytes.fromhex(v) for k, v in json.load(open(os.path.join(GOLD, "api_replies.json")))["replies"].items()}
+    docs = {d["id"]: d for d in corpus_docs()}
+    for name, raw in replies.items():
+        sent, results, error = F.run_client(S, name, raw)
+        assert sent == REQUESTS[name]                   # the fixture is what this client sends
+        assert results is not None, error
+        _, mine = parse_reply(raw, N_QUERIES[name])
+        assert len(results) == len(mine)
+        for theirs, ours in zip(results, mine):
+            assert theirs["status"] == ours["status"]
+            if ours["status"] == SEARCHD_ERROR:
+                assert theirs["error"] == ours["error"]
+                continue
+            assert theirs["fields"] == ours["fields"] and [tuple(a) for a in theirs["attrs"]] == ours["attrs"]
+            assert [(m["id"], m["weight"], m["attrs"]) for m in theirs["matches"]] == [(m["id"], m["weight"], m["attrs"]) for m in ours["matches"]]
+            assert (theirs["total"], theirs["total_found"]) == (ours["total"], ours["total_found"])
+            assert {w["word"]: (w["docs"], w["hits"]) for w in theirs["words"]} == ours["words"]
+            for m in theirs["matches"]:
+                assert m["attrs"]["group_id"] == docs[m["id"]]["attrs"][0]
