@@ -26,7 +26,7 @@ extern "C" {
 enum {
 	MGPU_OK = 0,
 	MGPU_E_IO = -1,           /* index files missing / unreadable */
-	MGPU_E_FORMAT = -2,       /* not an index-format v57..v62 plain index with a keywords dictionary, or hitless/unsupported settings */
+	MGPU_E_FORMAT = -2,       /* not an index-format v57..v62 plain index (dict=keywords or dict=crc), or hitless / unsupported settings */
 	MGPU_E_UNSUPPORTED = -3,  /* query uses an operator/ranker/sort the CUDA path does not implement */
 	MGPU_E_BAD_QUERY = -4,    /* malformed tree (reference: sphCreateRanker returns nullptr, sphinxsearch.cpp:4377) */
 	MGPU_E_NO_DEVICE = -5,    /* no CUDA device; the product never falls back to the CPU */
