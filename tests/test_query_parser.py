@@ -190,3 +190,48 @@ def test_unsupported_syntax_is_refused_not_guessed(text):
     with pytest.raises(M.MgpuError) as e:
         M.parse_query(text, FIELDS)
     assert e.value.code == M.MGPU_E_UNSUPPORTED
+
+
+def test_fuzz_never_crashes_and_trees_are_well_formed(tmp_path):
+    """random token soup: the parser answers (a tree or a message) and every tree it returns is one the engine's planner takes:
+    the oracle runs it (or refuses an operator shape), never reports a malformed tree"""
+    import random
+    rng = random.Random(20260219)
+    vocab = ["a", "b", "c", "dd", "e5", "the", "x", "NEAR/2", "NOTNEAR/3", "MAYBE", "<<", "|", "-", "!", "(", ")", '"', '"', "~2", "/2", "/0.5", "@title", "@body",
+             "@(title,body)", "@!title", "@title[3]", "^", "$", "\\", "=", "*", "привет", "我", "  ", "^1.5", "@*", "-a", "b$", "^c"]
+    docs = [{"id": 1 + i, "fields": [[(w, k + 1) for k, w in enumerate(rng.choices(["a", "b", "c", "dd", "e5", "x"], k=3))],
+                                      [(w, k + 1) for k, w in enumerate(rng.choices(["a", "b", "c", "dd", "e5", "x"], k=6))]], "attrs": []} for i in range(50)]
+    prefix = str(tmp_path / "fz")
+    M.build_index(prefix, FIELDS, docs)
+    idx = helpers.OracleIndex(prefix)
+    parsed = failed = 0
+    try:
+        for _ in range(1500):
+            text = " ".join(rng.choices(vocab, k=rng.randint(1, 9))) if rng.random() < 0.8 else "".join(rng.choices(vocab, k=rng.randint(1, 9)))
+            try:
+                root, _, _ = M.parse_query(text, FIELDS, stopwords=("the",), min_word_len=rng.choice([1, 2]))
+            except M.MgpuError as e:
+                assert e.code in (M.MGPU_E_BAD_QUERY, M.MGPU_E_UNSUPPORTED) and str(e), text
+                failed += 1
+                continue
+            parsed += 1
+
+            def check(n):
+                assert not (n.words and n.children), text
+                if n.words and n.op in (M.OP_PHRASE, M.OP_PROXIMITY, M.OP_QUORUM):
+                    pos = [k.atom_pos for k in n.words]
+                    assert pos == sorted(pos) and len(set(pos)) == len(pos) and len(pos) >= 2, (text, pos)
+                for k in n.words:
+                    assert k.word and k.atom_pos >= 1, text
+                if n.op == M.OP_ANDNOT:
+                    assert len(n.children) == 2, text
+                if n.op == M.OP_NOT:
+                    assert len(n.children) == 1, text
+                for c in n.children:
+                    check(c)
+            check(root)
+            r = idx.search([M.Query(root, max_matches=10)]).get(0)
+            assert r["status"] in (0, M.MGPU_E_UNSUPPORTED), (text, r["status"])
+        assert parsed > 200 and failed > 200
+    finally:
+        idx.close()
