@@ -6,7 +6,7 @@
 // src/sphinx.cpp:4655-4711) for the default charset_table + CJK unigrams, and the legacy match modes' rewrite into extended syntax
 // (PrepareQueryEmulation, src/searchd.cpp:2141-2190).
 // Not restated: blended characters, multiform destinations, query token-filter plugins, zones, SENTENCE / PARAGRAPH, exact-form
-// '=' (index_exact_words), wildcards, the phrase star, @@relaxed.  Those return MGPU_E_UNSUPPORTED or parse as the plain text would.
+// '=' (index_exact_words), wildcards, @@relaxed.  Those return MGPU_E_UNSUPPORTED or parse as the plain text would.
 #include "../../../include/mgpu.h"
 
 #include <math.h>
@@ -323,6 +323,7 @@ private:
 	std::vector<LimitSpec_t*>		m_dStateSpec;
 	std::vector<std::unique_ptr<LimitSpec_t>> m_dSpecPool;
 	std::vector<std::string>		m_dIntTokens;
+	std::vector<int>				m_dPhraseStar;	// positions of the `*` placeholders inside the phrase being lexed
 
 	int		m_iAtomPos = 0;
 	int		m_iPendingNulls = 0, m_iPendingType = 0;
@@ -622,6 +623,7 @@ private:
 					break;
 			}
 
+			const char * pLastTokenEnd = m_tTok.GetTokenEnd();
 			const char * sToken = m_tTok.GetToken();
 			if ( !sToken )
 			{
@@ -659,6 +661,24 @@ private:
 			if ( !bPhrase && ( ( nLeft>5 && !strncmp ( p, "ZONE:", 5 ) && ( IsAlphaRef ( p[5] ) || p[5]=='(' ) )
 				|| ( nLeft>9 && !strncmp ( p, "ZONESPAN:", 9 ) && ( IsAlphaRef ( p[9] ) || p[9]=='(' ) ) ) )
 				return Fail ( MGPU_E_UNSUPPORTED, "ZONE / ZONESPAN limits are not supported" );
+
+			// a separate star inside a phrase ("that * box") shifts the in-query positions behind it: count the [ * ] between the tokens (:1318-1348)
+			if ( bPhrase && pLastTokenEnd && m_tTok.GetTokenStart() )
+			{
+				int iSpace = 0, iStar = 0;
+				for ( const char * sCur = pLastTokenEnd; sCur<m_tTok.GetTokenStart(); ++sCur )
+				{
+					const int iCur = (int)( sCur-pLastTokenEnd );
+					if ( *sCur=='*' )
+						iStar = iCur;
+					else if ( *sCur==' ' )
+					{
+						if ( iSpace+2==iCur && iStar+1==iCur )
+							m_dPhraseStar.push_back ( m_iAtomPos );
+						iSpace = iCur;
+					}
+				}
+			}
 
 			if ( m_tTok.WasTokenSpecial() )
 			{
@@ -712,7 +732,11 @@ private:
 				{
 					const bool bWasQuoted = m_bQuoted;
 					if ( sToken[0]=='"' )
+					{
 						m_bQuoted = !m_bQuoted;
+						if ( m_bQuoted )
+							m_dPhraseStar.clear();
+					}
 					m_iPendingType = sToken[0];
 					m_tPendingToken = Token_t();
 					m_tTok.m_bPhrase = m_bQuoted;
@@ -948,6 +972,36 @@ private:
 		return pRes;
 	}
 
+	/// XQParser_t::PhraseShiftQpos, :1701-1738
+	void PhraseShiftQpos ( PNode_t * pNode )
+	{
+		if ( m_dPhraseStar.empty() )
+			return;
+		size_t iLast = 0;
+		const int iQposShiftStart = m_dPhraseStar[0];
+		int iQposShift = 0;
+		int iLastStarPos = m_dPhraseStar[0];
+		for ( size_t iWord=0; iWord<pNode->m_dWords.size(); ++iWord )
+		{
+			PWord_t & tWord = pNode->m_dWords[iWord];
+			while ( iLast<m_dPhraseStar.size() && m_dPhraseStar[iLast]<=tWord.m_iAtomPos )
+			{
+				iLastStarPos = m_dPhraseStar[iLast];
+				++iLast;
+				++iQposShift;
+			}
+			if ( tWord.m_sWord=="*" || ( tWord.m_bNull && tWord.m_iAtomPos==iLastStarPos ) )
+			{
+				pNode->m_dWords.erase ( pNode->m_dWords.begin()+iWord );
+				--iWord;
+				--iQposShift;
+				continue;
+			}
+			if ( iQposShiftStart<=tWord.m_iAtomPos )
+				tWord.m_iAtomPos += iQposShift;
+		}
+	}
+
 	PNode_t * KeywordOfNumber ( const Token_t & t )
 	{
 		return AddKeyword ( t.m_iStrIndex>=0 ? m_dIntTokens[t.m_iStrIndex].c_str() : nullptr );
@@ -1042,7 +1096,10 @@ private:
 				return pPhrase;
 			}
 			if ( pPhrase )
+			{
 				pPhrase->m_iOp = MGPU_OP_PHRASE;	// SetPhrase
+				PhraseShiftQpos ( pPhrase );
+			}
 			return pPhrase;
 		}
 		bOk = false;
