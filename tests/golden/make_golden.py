@@ -44,7 +44,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,052,054,055,059,094,114,115,116,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,041,052,054,055,059,094,114,115,116,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -483,6 +483,36 @@ out["cases"].append({
 # BEFORE / NOTNEAR over plain keywords in the hit stage. Left to the oracle: NEAR with three and more children (the reference's
 # FSMmultinear_c keeps m_uFirstQpos across documents, so the hits of a document depend on the documents before it) and
 # NEAR / BEFORE / NOTNEAR whose children are phrases, OR groups or other operators.
+# ---------------------------------------------------------------------------------------------
+# test_041 "phrase shift": a separate star inside a phrase stands for any one keyword ("that * box"): XQParser_t::GetToken counts the
+# [ * ] between the phrase's tokens and PhraseShiftQpos moves the in-query positions behind them (src/sphinxquery.cpp:1318-1348, 1701-1738);
+# the first star right behind the quote does not match the [ * ] pattern, so `"* * * box always"` shifts by two. Indexes `phrase_shift`
+# (plain) and `phrase_shift_min_wlen` (min_word_len=2: the document's `a` is overshort and still takes a position). SphinxQL rows carry
+# no weights (ids_only). Plain phrases over keywords: the CUDA path runs them.
+# ---------------------------------------------------------------------------------------------
+m41 = model("test_041")
+docs_041 = [(1, "that orange box might be and not yellow"), (2, "however that is a green box always apears here as usual"), (3, "that orange box might be not yellow")]
+
+
+def PS(*wp):
+    return ["phrase", [[w, p] for w, p in wp]]
+
+
+q041 = {"phrase_shift": {107: PS(("that", 1), ("box", 2)), 108: PS(("that", 1), ("box", 3)), 109: PS(("that", 1), ("box", 5)),
+                         110: PS(("that", 1), ("box", 3), ("might", 4), ("not", 7), ("yellow", 8)), 120: PS(("box", 3), ("always", 4))},
+        "phrase_shift_min_wlen": {115: PS(("that", 1), ("box", 2)), 116: PS(("that", 1), ("box", 3)), 117: PS(("that", 1), ("box", 5)),
+                                  118: PS(("that", 1), ("box", 3), ("might", 4), ("not", 7), ("yellow", 8)), 122: PS(("box", 3), ("always", 4))}}
+for index, trees in q041.items():
+    case = {"name": "test_041_" + index, "fields": ["title"], "attrs": ["idd"], "min_word_len": 2 if index.endswith("min_wlen") else 1,
+            "docs": [{"id": d[0], "fields": [d[1]], "attrs": [11]} for d in docs_041], "queries": []}
+    for qi, tree in trees.items():
+        r = m41[qi]
+        assert (" FROM %s WHERE" % index) in r["sphinxql"], r["sphinxql"]
+        case["queries"].append({"text": r["sphinxql"].strip(), "tree": tree, "ranker": "proximity_bm25", "sort": "id_asc", "ids_only": True,
+                                "expect": {"matches": [[int(row["id"]), 0] for row in (r.get("rows") or {}).values()], "total_found": int(r["total_rows"]), "words": {}}})
+    out["cases"].append(case)
+
+
 # ---------------------------------------------------------------------------------------------
 def gpu_refuses(t):
     kind = t[0]

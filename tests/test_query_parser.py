@@ -21,7 +21,7 @@ OPS = {M.OP_AND: "and", M.OP_OR: "or", M.OP_ANDNOT: "andnot", M.OP_MAYBE: "maybe
 
 def match_text(text):
     """the MATCH() argument of a SphinxQL golden query, or the text itself"""
-    m = re.search(r"match\s*\(\s*'(.*?)'\s*\)", text)
+    m = re.search(r"match\s*\(\s*'(.*?)'\s*\)", text, re.I)
     return m.group(1) if m else text
 
 
