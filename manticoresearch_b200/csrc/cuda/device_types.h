@@ -68,8 +68,8 @@ struct DevHotStore_t
 	const uint16_t *	m_pData;		///< [nHot][m_iStride]: low byte 0 = keyword absent, 1..254 = hit count, 255 = see escape list;
 										///< high byte = field mask (indexes with <= 8 fields); with m_bTfClass its high nibble holds
 										///< ceil ( 15*hits/(hits+1.2) ), the row's tf class for the weight bound of stream_kernel
-	const uint32_t *	m_pEscape;		///< [m_nEscape][3]: hot slot, rowid, hit count (documents with >= 255 hits)
-	const int32_t *		m_pEscapeCount;
+	const uint32_t *	m_pEscape;		///< [m_nEscape][4]: hot slot, rowid, hit count, next entry of the bucket (documents with >= 255 hits)
+	const int32_t *		m_pEscapeCount;	///< [1+65536]: entries, then the bucket heads (-1 = empty)
 	int64_t				m_iStride;		///< rows rounded up to TILE_W
 	int32_t				m_nHot;
 	int32_t				m_bTfClass;		///< indexes with <= 4 fields: bits 12..15 of a row hold its tf class (consumers mask fields by the queried fields)

@@ -585,13 +585,26 @@ __device__ __forceinline__ bool AnyAliveInRange ( const uint32_t * pBits, uint32
 	return __any_sync ( FULL_MASK, bAny );
 }
 
-/// documents with >= 255 hits of a hot keyword are rare: their hit counts live in a short list
+/// documents with >= 255 hits of a hot keyword: their hit counts live in a list of { hot slot, rowid, hits, next } entries chained
+/// per bucket of a 65536-way hash of ( slot, rowid ); the bucket heads follow the entry counter in m_pEscapeCount. A lookup walks one
+/// chain (n / 65536 entries on average), not the list
+static const int HOT_ESCAPE_BUCKETS = 65536;
+__device__ __forceinline__ uint32_t HotEscapeBucket ( uint32_t uHot, uint32_t uRowid )
+{
+	return ( ( uRowid*2654435761u ) ^ ( uHot*40503u ) )>>16;
+}
+
 __device__ uint32_t HotEscapeHits ( const DevHotStore_t & tHot, int iHot, uint32_t uRowid )
 {
-	const int n = __ldg ( tHot.m_pEscapeCount );
-	for ( int i=0; i<n; ++i )
-		if ( __ldg ( tHot.m_pEscape+3*i )==(uint32_t)iHot && __ldg ( tHot.m_pEscape+3*i+1 )==uRowid )
-			return __ldg ( tHot.m_pEscape+3*i+2 );
+	const int nCap = __ldg ( tHot.m_pEscapeCount );
+	int i = __ldg ( tHot.m_pEscapeCount+1+HotEscapeBucket ( (uint32_t)iHot, uRowid ) );
+	for ( int nSteps=0; i>=0 && nSteps<=nCap; ++nSteps )
+	{
+		const uint4 t = __ldg ( reinterpret_cast<const uint4 *>( tHot.m_pEscape )+i );
+		if ( t.x==(uint32_t)iHot && t.y==uRowid )
+			return t.z;
+		i = (int)t.w;
+	}
 	return 255u;
 }
 
@@ -676,7 +689,8 @@ __global__ void __launch_bounds__ ( EVAL_THREADS ) hot_decode_kernel ( HotDecode
 					const int i = atomicAdd ( P.m_pEscapeCount, 1 );
 					if ( i<P.m_iEscapeCap )
 					{
-						P.m_pEscape[3*i] = (uint32_t)h; P.m_pEscape[3*i+1] = d.m_uRowid; P.m_pEscape[3*i+2] = d.m_uHits;
+						const int iNext = atomicExch ( P.m_pEscapeCount+1+HotEscapeBucket ( (uint32_t)h, d.m_uRowid ), i );
+						reinterpret_cast<uint4 *>( P.m_pEscape )[i] = make_uint4 ( (uint32_t)h, d.m_uRowid, d.m_uHits, (uint32_t)iNext );
 					}
 				}
 			}

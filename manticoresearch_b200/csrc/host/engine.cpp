@@ -1877,8 +1877,8 @@ int Batch_c::BuildHotStore ( cudaStream_t s )
 	if ( !m_dHotTerms.empty() )
 	{
 		CUDA_TRY ( tScr.m_dHotData.Grow ( m_dHotTerms.size()*(size_t)m_iHotStride ), m_sError );
-		CUDA_TRY ( tScr.m_dHotEscape.Grow ( (size_t)m_iHotEscapeCap*3 ), m_sError );
-		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1 ), m_sError );
+		CUDA_TRY ( tScr.m_dHotEscape.Grow ( (size_t)m_iHotEscapeCap*4+4 ), m_sError );	// { hot slot, rowid, hits, next in bucket }
+		CUDA_TRY ( tScr.m_dHotEscapeCount.Grow ( 1+65536 ), m_sError );					// entry counter + the bucket heads (HOT_ESCAPE_BUCKETS)
 		if ( m_nHotBitFields )
 			CUDA_TRY ( tScr.m_dHotBits.Grow ( m_dHotTerms.size()*(size_t)m_nHotBitFields*(size_t)( m_iHotStride/32 ) ), m_sError );
 		if ( m_nListEntries )
@@ -1895,6 +1895,7 @@ int Batch_c::BuildHotStore ( cudaStream_t s )
 	{
 		// (the u16 rows are cleared by hot_decode_kernel itself, block by block; only the bitmaps are memset)
 		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotEscapeCount.m_p, 0, sizeof(int32_t), s ), m_sError );
+		CUDA_TRY ( cudaMemsetAsync ( tScr.m_dHotEscapeCount.m_p+1, 0xFF, 65536*sizeof(int32_t), s ), m_sError );	// empty chains
 		HotDecodeParams_t H {};
 		H.m_tIndex = pIndex->m_tDev;
 		H.m_pTerms = m_dHotDesc.m_p;

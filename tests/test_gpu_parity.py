@@ -361,7 +361,8 @@ def test_hot_store_escape_and_plain_format(tmp_path):
     rng = random.Random(7)
     docs = []
     for i in range(4500):
-        body = [("common", p + 1) for p in range(rng.choice([1, 1, 2, 3, 300 if i % 911 == 0 else 4]))]
+        # >= 255 hits of a hot keyword: every 911th document, and a dense stretch of them (the escape entries are chained per hash bucket)
+        body = [("common", p + 1) for p in range(rng.choice([1, 1, 2, 3, 300 if i % 911 == 0 else 4]) if not 2000 <= i < 2600 else 255 + i % 50)]
         n0 = len(body)
         if i % 3 == 0:
             body += [("third", n0 + 1), ("third", n0 + 2)]
