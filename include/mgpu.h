@@ -352,7 +352,8 @@ void			mgpu_parsed_free ( mgpu_parsed * p );
 /* Wire responder: the binary SphinxAPI `search` command for ONE local index, request packet in, reply packet out.
  * Replaces the server side of SEARCHD_COMMAND_SEARCH: HandleCommandSearch + ParseSearchQuery (src/searchd.cpp:6932-7000, 2201-2560),
  * the sort-mode / weight / filter setup between them and the index (src/sortsetup.cpp, src/sphinx.cpp:13903-13947) and SendResult
- * (src/searchd.cpp:3340-3510), for client protocol versions 1.29..1.33 (0x11D..0x121).  The queries of one packet run as one
+ * (src/searchd.cpp:3340-3510), for client protocol versions 1.29..1.33 (0x11D..0x121); also SEARCHD_COMMAND_KEYWORDS (HandleCommandKeywords:
+ * the text tokenized as the index tokenizes it, with the dictionary's docs / hits on request).  The queries of one packet run as one
  * mgpu_search_batch call.  Anything the hot path has no counterpart for (group-by, expression rankers / sorts, geo anchors, select
  * lists other than "*", string and float filters, cutoff, outer order) is answered with SEARCHD_ERROR for that query, as searchd
  * answers a query it cannot run.  No sockets: the embedding daemon owns the connection (src/netreceive_api.cpp).

@@ -1,4 +1,4 @@
-// Wire responder for the binary SphinxAPI `search` command, on top of the C ABI.
+// Wire responder for the binary SphinxAPI `search` and `keywords` commands, on top of the C ABI.
 //
 // Restates the server side of SEARCHD_COMMAND_SEARCH for one local index: the packet header (APIHeader / APIAnswer, src/searchdaemon.cpp),
 // ParseSearchQuery + ParseSearchFilter (src/searchd.cpp:2201-2560), the legacy sort modes and the extended sort clause
@@ -23,10 +23,13 @@
 
 namespace mgpu
 {
+void TokenizePlain ( const mgpu_parser_settings & s, const char * sText, std::vector<std::pair<std::string,int>> & dOut );	// query_parser.cpp
+
 namespace
 {
 
-enum { SEARCHD_COMMAND_SEARCH = 0 };
+enum { SEARCHD_COMMAND_SEARCH = 0, SEARCHD_COMMAND_KEYWORDS = 3 };
+enum { VER_COMMAND_KEYWORDS = 0x101 };	// src/searchdaemon.h:189
 enum { SEARCHD_OK = 0, SEARCHD_ERROR = 1, SEARCHD_RETRY = 2, SEARCHD_WARNING = 3 };
 enum { VER_COMMAND_SEARCH = 0x121 };	// src/searchdaemon.h:186
 enum { SPH_SORT_RELEVANCE = 0, SPH_SORT_ATTR_DESC = 1, SPH_SORT_ATTR_ASC = 2, SPH_SORT_TIME_SEGMENTS = 3, SPH_SORT_EXTENDED = 4, SPH_SORT_EXPR = 5 };
@@ -763,6 +766,60 @@ int mgpu_api_handle ( mgpu_api * api, const void * request, size_t request_len, 
 	if ( r.m_bError || uLen!=(size_t)( r.m_pEnd-r.m_p ) )
 	{
 		SendErrorReply ( tOut, "invalid or truncated request" );
+		return fnDone();
+	}
+	if ( uCommand==SEARCHD_COMMAND_KEYWORDS )
+	{
+		// HandleCommandKeywords (src/searchd.cpp): the text tokenized as the index would tokenize it, optionally with the dictionary's counts
+		char sBuf[160];
+		if ( ( uVer>>8 )!=( VER_COMMAND_KEYWORDS>>8 ) || uVer>VER_COMMAND_KEYWORDS )
+		{
+			if ( ( uVer>>8 )!=( VER_COMMAND_KEYWORDS>>8 ) )
+				snprintf ( sBuf, sizeof(sBuf), "major command version mismatch (expected v.%d.x, got v.%d.%d)", VER_COMMAND_KEYWORDS>>8, uVer>>8, uVer & 255 );
+			else
+				snprintf ( sBuf, sizeof(sBuf), "client version is higher than daemon version (client is v.%d.%d, daemon is v.%d.%d)", uVer>>8, uVer & 255, VER_COMMAND_KEYWORDS>>8, VER_COMMAND_KEYWORDS & 255 );
+			SendErrorReply ( tOut, sBuf );
+			return fnDone();
+		}
+		const std::string sQuery = r.GetString();
+		const std::string sIndex = r.GetString();
+		const bool bStats = r.GetInt()!=0;
+		if ( uVer>=0x101 )
+		{
+			r.GetInt(); r.GetInt(); r.GetInt(); r.GetInt();		// fold lemmas / blended / wildcards, expansion limit: nothing to fold here
+		}
+		if ( r.m_bError || r.m_p!=r.m_pEnd )
+		{
+			SendErrorReply ( tOut, "invalid or truncated request" );
+			return fnDone();
+		}
+		if ( bStats && !A.m_pIndex )
+		{
+			SendErrorReply ( tOut, "no index is attached to this responder" );
+			return fnDone();
+		}
+		A.m_sDescribe = "CALL KEYWORDS('" + sQuery + "', '" + sIndex + "', " + ( bStats ? "1" : "0" ) + ");\n";
+		std::vector<std::pair<std::string,int>> dWords;
+		TokenizePlain ( A.m_tTok, sQuery.c_str(), dWords );
+		tOut.SendWord ( SEARCHD_OK );
+		tOut.SendWord ( VER_COMMAND_KEYWORDS );
+		tOut.SendDword ( 0 );
+		tOut.SendInt ( (int)dWords.size() );
+		for ( const auto & w : dWords )
+		{
+			tOut.SendString ( w.first );	// tokenized
+			tOut.SendString ( w.first );	// normalized: no morphology on this path
+			if ( uVer>=0x101 )
+				tOut.SendInt ( w.second );
+			if ( bStats )
+			{
+				int64_t iDocs = 0, iHits = 0;
+				mgpu_index_word_stats ( A.m_pIndex, w.first.c_str(), &iDocs, &iHits );
+				tOut.SendAsDword ( iDocs );
+				tOut.SendAsDword ( iHits );
+			}
+		}
+		tOut.PatchDword ( 4, (uint32_t)( tOut.m_d.size()-8 ) );
 		return fnDone();
 	}
 	if ( uCommand!=SEARCHD_COMMAND_SEARCH )

@@ -88,6 +88,7 @@ public:
 	bool			m_bPhrase = false;
 	int				m_iMinWordLen = 1;
 	bool			m_bCjk = true;
+	bool			m_bIndexMode = false;	///< the index tokenizer: no specials, no escapes
 
 	void SetBuffer ( const char * p, int iLen )
 	{
@@ -119,7 +120,7 @@ public:
 			int iCode = -1;
 			if ( m_pCur<m_pEnd )
 			{
-				if ( *m_pCur=='\\' )
+				if ( *m_pCur=='\\' && !m_bIndexMode )
 				{
 					// an escaped character never acts as a special (CodepointArbitrationQ, bWasEscaped)
 					++m_pCur;
@@ -132,7 +133,7 @@ public:
 			}
 
 			int iFolded = iCode<0 ? 0 : Fold ( iCode );
-			const bool bSpecialChar = iCode>=0 && iCode<128 && strchr ( "()|-!@~\"/^$<", iCode )!=nullptr;
+			const bool bSpecialChar = !m_bIndexMode && iCode>=0 && iCode<128 && strchr ( "()|-!@~\"/^$<", iCode )!=nullptr;
 			bool bSpecial = bSpecialChar;
 			if ( bSpecial )
 			{
@@ -1364,6 +1365,33 @@ private:
 		return pRoot ? pRoot : NewNode ( *m_dStateSpec.back() );
 	}
 };
+
+/// index-mode tokenization of a text for the KEYWORDS command (CSphIndex_VLN::DoGetKeywords, src/sphinx.cpp: Clone ( SPH_CLONE_INDEX ),
+/// none of the query specials): { keyword, in-query position }, stop words dropped after taking their position
+void TokenizePlain ( const mgpu_parser_settings & s, const char * sText, std::vector<std::pair<std::string,int>> & dOut )
+{
+	QueryTokenizer_c tTok;
+	tTok.m_iMinWordLen = s.min_word_len>0 ? s.min_word_len : 1;
+	tTok.m_bCjk = s.ngram_cjk!=0;
+	tTok.m_bIndexMode = true;
+	std::string sBuf ( sText ? sText : "" );
+	tTok.SetBuffer ( sBuf.c_str(), (int)sBuf.size() );
+	std::unordered_set<std::string> hStop;
+	for ( int i=0; i<s.n_stopwords; ++i )
+		hStop.insert ( s.stopwords[i] );
+	int iPos = 0;
+	while ( const char * sToken = tTok.GetToken() )
+	{
+		iPos += 1 + tTok.GetOvershortCount()*( s.overshort_step ? 1 : 0 );
+		if ( hStop.count ( sToken ) )
+		{
+			if ( !s.stopword_step )
+				--iPos;
+			continue;
+		}
+		dOut.push_back ( { sToken, iPos } );
+	}
+}
 
 } // namespace mgpu
 

@@ -99,11 +99,26 @@ def run_client(S, name, reply):
     return bytes(sock.sent), res, c.GetLastError()
 
 
+KEYWORDS = {"keywords_plain": ("Hello, WORLD there-extra  nosuchword", "idx", 0), "keywords_stats": ("hello world hello zzz", "idx", 1)}
+
+
+def run_keywords(S, name, reply):
+    """-> (request bytes of BuildKeywords, what the client parsed out of `reply`, its last error)"""
+    c = S.SphinxClient()
+    sock = FakeSocket(reply)
+    c._Connect = lambda: sock
+    res = c.BuildKeywords(*KEYWORDS[name])
+    return bytes(sock.sent), res, c.GetLastError()
+
+
 def main():
     S = load_client()
     out = {"source": "requests built by ravelry/manticoresearch api/sphinxapi.py (VER_COMMAND_SEARCH 0x120)", "requests": {}}
     for name in scenarios(S):
         req, _, _ = run_client(S, name, ERROR_REPLY)
+        out["requests"][name] = req.hex()
+    for name in KEYWORDS:
+        req, _, _ = run_keywords(S, name, ERROR_REPLY)
         out["requests"][name] = req.hex()
     with open(os.path.join(HERE, "api_requests.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -93,6 +93,27 @@ def parse_reply(raw, n_queries):
     return status, out
 
 
+SEARCH_NAMES = ["default", "any_attr_desc", "extended_sort_filter_weights", "phrase_range_idrange", "multi", "positional_weights"]
+
+
+def parse_keywords_reply(raw, stats, ver=0x100):
+    status, rver, length = struct.unpack_from(">2HL", raw, 0)
+    assert length == len(raw) - 8
+    r = Reader(raw[8:])
+    if status != SEARCHD_OK:
+        return status, r.string()
+    out = []
+    for _ in range(r.u32()):
+        e = {"tokenized": r.string(), "normalized": r.string()}
+        if ver >= 0x101:
+            e["qpos"] = r.u32()
+        if stats:
+            e["docs"], e["hits"] = r.u32(), r.u32()
+        out.append(e)
+    assert r.p == len(r.raw)
+    return status, out
+
+
 N_QUERIES = {"default": 1, "any_attr_desc": 1, "extended_sort_filter_weights": 1, "phrase_range_idrange": 1, "multi": 4, "positional_weights": 1}
 
 
@@ -109,7 +130,8 @@ def test_requests_of_the_reference_client_parse(tmp_path):
             "multi": ["MATCH('\"hello world\"~3 | extra')", "GROUP BY group_id", "MATCH('hello | (world')", "ORDER BY attr_asc(stamp)", "ranker=3"],
             "positional_weights": ["weights=(3,1)", "MATCH('world there')"],
         }
-        for name, req in REQUESTS.items():
+        for name in SEARCH_NAMES:
+            req = REQUESTS[name]
             raw = api.handle(req)
             desc = api.describe_last()
             assert desc.count(";\n") == N_QUERIES[name]
@@ -124,6 +146,35 @@ def test_requests_of_the_reference_client_parse(tmp_path):
                 assert "no index is attached" in errors[0] and "no index is attached" in errors[3]
             else:
                 assert "no index is attached" in errors[0]
+    finally:
+        api.close()
+
+
+def test_keywords_command(tmp_path):
+    """SEARCHD_COMMAND_KEYWORDS (HandleCommandKeywords): the index tokenizer's view of a text; without an index only the no-stats form"""
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    api = M.ApiResponder(None, prefix)
+    try:
+        status, words = parse_keywords_reply(api.handle(REQUESTS["keywords_plain"]), False)
+        assert status == SEARCHD_OK
+        assert [w["tokenized"] for w in words] == ["hello", "world", "there", "extra", "nosuchword"] and all(w["normalized"] == w["tokenized"] for w in words)
+        assert "CALL KEYWORDS('Hello, WORLD there-extra  nosuchword', 'idx', 0)" in api.describe_last()
+        status, msg = parse_keywords_reply(api.handle(REQUESTS["keywords_stats"]), True)
+        assert status == SEARCHD_ERROR and "no index" in msg
+        # protocol 1.1 adds four flags to the request and the in-query position to every keyword
+        body = REQUESTS["keywords_plain"][8:] + struct.pack(">4L", 0, 0, 0, 0)
+        status, words = parse_keywords_reply(api.handle(struct.pack(">2HL", 3, 0x101, len(body)) + body), False, ver=0x101)
+        assert [w["qpos"] for w in words] == [1, 2, 3, 4, 5]
+        status, msg = parse_keywords_reply(api.handle(struct.pack(">2HL", 3, 0x102, len(body)) + body), False)
+        assert status == SEARCHD_ERROR and "client version is higher" in msg
+    finally:
+        api.close()
+    api = M.ApiResponder(None, prefix, min_word_len=3, stopwords=("there",))
+    try:
+        body = REQUESTS["keywords_plain"][8:] + struct.pack(">4L", 0, 0, 0, 0)
+        _, words = parse_keywords_reply(api.handle(struct.pack(">2HL", 3, 0x101, len(body)) + body), False, ver=0x101)
+        assert [(w["tokenized"], w["qpos"]) for w in words] == [("hello", 1), ("world", 2), ("extra", 4), ("nosuchword", 5)]
     finally:
         api.close()
 
@@ -150,9 +201,15 @@ def test_protocol_errors(tmp_path):
         assert "bad multi-query count" in err(good[:12] + struct.pack(">L", 1000) + good[16:])
         assert "truncated" in err(good[:12] + struct.pack(">L", 2) + good[16:])      # says two queries, carries one
         # every prefix of every packet is answered, never crashes
-        for req in REQUESTS.values():
+        for name in SEARCH_NAMES:
+            req = REQUESTS[name]
             for cut in range(0, len(req), 7):
                 status, _ = parse_reply(api.handle(struct.pack(">2HL", 0, 0x120, max(cut - 8, 0)) + req[8:cut]), 0)
+                assert status == SEARCHD_ERROR
+        for name in ("keywords_plain", "keywords_stats"):
+            req = REQUESTS[name]
+            for cut in range(8, len(req)):
+                status, _ = parse_keywords_reply(api.handle(struct.pack(">2HL", 3, 0x100, cut - 8) + req[8:cut]), False)
                 assert status == SEARCHD_ERROR
     finally:
         api.close()
@@ -189,7 +246,15 @@ def test_replies_equal_direct_search(tmp_path):
         gid, stamp = gpu.attr_index("group_id"), gpu.attr_index("stamp")
         exp = expected_queries(gid, stamp)
         nonempty = 0
-        for name, req in REQUESTS.items():
+        raw = api.handle(REQUESTS["keywords_stats"])
+        replies["keywords_stats"] = raw.hex()
+        status, words = parse_keywords_reply(raw, True)
+        assert status == SEARCHD_OK and [w["tokenized"] for w in words] == ["hello", "world", "hello", "zzz"]
+        for w in words:
+            assert (w["docs"], w["hits"]) == (gpu.word_stats(w["tokenized"]) or (0, 0))
+        assert words[0]["docs"] > 0 and words[3]["docs"] == 0
+        for name in SEARCH_NAMES:
+            req = REQUESTS[name]
             raw = api.handle(req)
             replies[name] = raw.hex()
             status, results = parse_reply(raw, N_QUERIES[name])
@@ -233,7 +298,13 @@ def test_reference_client_reads_the_replies():
     S = F.load_client()
     replies = {k: bytes.fromhex(v) for k, v in json.load(open(os.path.join(GOLD, "api_replies.json")))["replies"].items()}
     docs = {d["id"]: d for d in corpus_docs()}
+    sent, words, error = F.run_keywords(S, "keywords_stats", replies["keywords_stats"])
+    assert sent == REQUESTS["keywords_stats"] and words is not None, error
+    _, mine = parse_keywords_reply(replies["keywords_stats"], True)
+    assert words == mine and [w["tokenized"] for w in words] == ["hello", "world", "hello", "zzz"]
     for name, raw in replies.items():
+        if name.startswith("keywords"):
+            continue
         sent, results, error = F.run_client(S, name, raw)
         assert sent == REQUESTS[name]                   # the fixture is what this client sends
         assert results is not None, error
