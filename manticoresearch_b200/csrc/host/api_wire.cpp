@@ -688,11 +688,24 @@ static void SendErrorReply ( NetWriter_t & tOut, const std::string & sError )
 extern "C"
 {
 
+static int ApiCreateImpl ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out );
+
 int mgpu_api_create ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out )
 {
 	if ( !path_prefix || !out )
 		return MGPU_E_BAD_QUERY;
 	*out = nullptr;
+	try
+	{
+		return ApiCreateImpl ( idx, path_prefix, tokenizer, out );
+	} catch ( ... )
+	{
+		return MGPU_E_NOMEM;
+	}
+}
+
+static int ApiCreateImpl ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out )
+{
 	std::unique_ptr<mgpu_api> p ( new mgpu_api );
 	p->m_pIndex = idx;
 	Mapped_t tSph;
@@ -743,7 +756,21 @@ const char * mgpu_api_describe_last ( const mgpu_api * api )
 	return api ? api->m_sDescribe.c_str() : "";
 }
 
+static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_len, const void ** reply, size_t * reply_len );
+
 int mgpu_api_handle ( mgpu_api * api, const void * request, size_t request_len, const void ** reply, size_t * reply_len )
+{
+	// no exception crosses the ABI (a packet can ask for allocations up to its own size; bad_alloc is the one thing left to catch)
+	try
+	{
+		return ApiHandleImpl ( api, request, request_len, reply, reply_len );
+	} catch ( ... )
+	{
+		return MGPU_E_NOMEM;
+	}
+}
+
+static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_len, const void ** reply, size_t * reply_len )
 {
 	if ( !api || !reply || !reply_len || ( request_len && !request ) )
 		return MGPU_E_BAD_QUERY;

@@ -297,7 +297,20 @@ static void CheckDictionary ( const IndexHeader_t & h, const std::vector<DictEnt
 } // namespace
 } // namespace mgpu
 
+static int IndexCheckImpl ( const char * path_prefix, int64_t * n_failures, char * report, int report_len );
+
 extern "C" int mgpu_index_check ( const char * path_prefix, int64_t * n_failures, char * report, int report_len )
+{
+	try
+	{
+		return IndexCheckImpl ( path_prefix, n_failures, report, report_len );
+	} catch ( ... )
+	{
+		return MGPU_E_NOMEM;	// no exception crosses the ABI
+	}
+}
+
+static int IndexCheckImpl ( const char * path_prefix, int64_t * n_failures, char * report, int report_len )
 {
 	using namespace mgpu;
 	if ( n_failures )
@@ -341,6 +354,11 @@ extern "C" int mgpu_index_check ( const char * path_prefix, int64_t * n_failures
 	if ( h.m_eHitless!=SPH_HITLESS_NONE )
 	{
 		R.Fail ( "hitless indexes are not supported" );
+		return fnFinish ( MGPU_E_FORMAT );
+	}
+	if ( h.m_iDocinfo<0 || h.m_iDocinfo>=(int64_t)0xFFFFFFFFll || h.m_dAttrs.size()>4096 )
+	{
+		R.Fail ( "implausible row count %lld or attribute count %d in the header", (long long)h.m_iDocinfo, (int)h.m_dAttrs.size() );
 		return fnFinish ( MGPU_E_FORMAT );
 	}
 	if ( (int)h.m_iSkiplistBlockSize<=0 )

@@ -18,6 +18,7 @@
 #include <vector>
 #include <memory>
 #include <unordered_set>
+#include <algorithm>
 
 namespace mgpu
 {
@@ -58,6 +59,7 @@ struct PNode_t
 	LimitSpec_t				m_tSpec;
 	std::vector<PWord_t>	m_dWords;
 	std::vector<PNode_t*>	m_dChildren;
+	int						m_iDepth = 1;			// height of the subtree: the fix-ups and the planner recurse over it
 };
 
 struct Token_t
@@ -335,6 +337,8 @@ private:
 
 	bool	m_bHaveTok = false;
 	Token_t	m_tCur;
+	static const int MAX_TREE_DEPTH = 512;
+	int		m_iParenDepth = 0;
 
 	int Fail ( int iCode, const std::string & s )
 	{
@@ -853,7 +857,10 @@ private:
 			PNode_t * pNode = NewNode ( *m_dStateSpec.back() );
 			pNode->m_iOp = MGPU_OP_NOT;
 			if ( pLeft )
+			{
 				pNode->m_dChildren.push_back ( pLeft );
+				pNode->m_iDepth = pLeft->m_iDepth+1;
+			}
 			return pNode;
 		}
 		if ( !pLeft || !pRight )
@@ -861,6 +868,7 @@ private:
 		if ( !pLeft->m_dChildren.empty() && pLeft->m_iOp==iOp && pLeft->m_iOpArg==iOpArg )
 		{
 			pLeft->m_dChildren.push_back ( pRight );
+			pLeft->m_iDepth = std::max ( pLeft->m_iDepth, pRight->m_iDepth+1 );
 			return pLeft;
 		}
 		PNode_t * pNode = NewNode ( HasMissedField ( pRight->m_tSpec ) ? pLeft->m_tSpec : pRight->m_tSpec );
@@ -868,6 +876,9 @@ private:
 		pNode->m_iOpArg = iOpArg;
 		pNode->m_dChildren.push_back ( pLeft );
 		pNode->m_dChildren.push_back ( pRight );
+		pNode->m_iDepth = std::max ( pLeft->m_iDepth, pRight->m_iDepth )+1;
+		if ( pNode->m_iDepth>MAX_TREE_DEPTH )
+			Fail ( MGPU_E_BAD_QUERY, "query too complex, not enough stack (tree deeper than " + std::to_string ( MAX_TREE_DEPTH ) + " levels)" );
 		return pNode;
 	}
 
@@ -1019,7 +1030,15 @@ private:
 		if ( t=='(' )
 		{
 			Take();
+			if ( ++m_iParenDepth>MAX_TREE_DEPTH )
+			{
+				// the reference measures its stack (sphGetStackUsed) and answers "query too complex"; here the nesting is counted
+				bOk = false;
+				Fail ( MGPU_E_BAD_QUERY, "query too complex, not enough stack (parentheses nested deeper than " + std::to_string ( MAX_TREE_DEPTH ) + " levels)" );
+				return nullptr;
+			}
 			PNode_t * pRes = ParseExpr();
+			--m_iParenDepth;
 			if ( Peek()!=')' )
 			{
 				bOk = false;
@@ -1466,7 +1485,23 @@ static int Flatten ( const PNode_t * p, mgpu_parsed & tOut )
 extern "C"
 {
 
+static int ParseQueryImpl ( const mgpu_parser_settings * settings, const char * text, mgpu_parsed ** out );
+
 int mgpu_parse_query ( const mgpu_parser_settings * settings, const char * text, mgpu_parsed ** out )
+{
+	// no exception crosses the ABI
+	try
+	{
+		return ParseQueryImpl ( settings, text, out );
+	} catch ( ... )
+	{
+		if ( out )
+			*out = nullptr;
+		return MGPU_E_NOMEM;
+	}
+}
+
+static int ParseQueryImpl ( const mgpu_parser_settings * settings, const char * text, mgpu_parsed ** out )
 {
 	if ( !settings || !out || settings->n_fields<0 || ( settings->n_fields && !settings->field_names ) || ( settings->n_stopwords>0 && !settings->stopwords ) )
 		return MGPU_E_BAD_QUERY;

@@ -235,3 +235,20 @@ def test_fuzz_never_crashes_and_trees_are_well_formed(tmp_path):
         assert parsed > 200 and failed > 200
     finally:
         idx.close()
+
+
+def test_pathological_nesting_is_refused_not_crashed():
+    """a daemon must survive any query text: deep parentheses / deep operator chains answer "query too complex" (the reference
+    measures its stack for the same purpose), long flat queries parse"""
+    with pytest.raises(M.MgpuError) as e:
+        M.parse_query("(" * 100000 + "a" + ")" * 100000, FIELDS)
+    assert "too complex" in str(e.value)
+    with pytest.raises(M.MgpuError) as e:
+        M.parse_query(" ".join("w%d NEAR/%d" % (i, i + 1) for i in range(3000)) + " z", FIELDS)
+    assert "too complex" in str(e.value)
+    root, _, _ = M.parse_query(" ".join("w%d" % i for i in range(20000)), FIELDS)
+    assert len(root.children) == 20000
+    root, _, _ = M.parse_query(" | ".join("w%d" % i for i in range(20000)), FIELDS)
+    assert len(root.children) == 20000
+    root, _, _ = M.parse_query("(" * 300 + "a b" + ")" * 300, FIELDS)
+    assert compact(root) == ["and", ["kw", "a", 1], ["kw", "b", 2]]
