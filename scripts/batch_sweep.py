@@ -23,6 +23,7 @@ from manticoresearch_b200 import workload  # noqa: E402
 def main():
     docs = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
     prefix, _, _, _ = bench.ensure_index(M, docs, 0, 1)
+    os.sync()       # the index files were just written: let their write-back finish before latencies are taken (it stalls host threads for 100s of ms)
     idx = M.Index(prefix, device=0)
     allq = workload.cfg2_queries(n=10_000, max_matches=100)
     out = {"workload": bench.WORKLOADS["cfg2"]["desc"], "docs": docs, "call": "mgpu_search_batch (host buffers, plan + H2D + kernels + D2H per call)", "sizes": []}
