@@ -197,6 +197,7 @@ const char *	mgpu_last_error ( const mgpu_index * idx );   /* idx may be NULL: l
 int64_t			mgpu_index_total_docs ( const mgpu_index * idx );
 int32_t			mgpu_index_num_fields ( const mgpu_index * idx );
 int32_t			mgpu_index_field_index ( const mgpu_index * idx, const char * name );   /* CSphSchema::GetFieldIndex */
+const char *	mgpu_index_field_name ( const mgpu_index * idx, int32_t field );        /* CSphSchema::GetFieldName; NULL if out of range */
 int32_t			mgpu_index_attr_index ( const mgpu_index * idx, const char * name );    /* CSphSchema::GetAttrIndex */
 /* dictionary lookup: DiskIndexQwordSetup_c::Setup (src/sphinx.cpp:12950-13078). returns 1 if found */
 int				mgpu_index_word_stats ( const mgpu_index * idx, const char * word, int64_t * docs, int64_t * hits );

@@ -64,7 +64,11 @@ struct GpuXQNode_t
 /// the CSphQuery fields the hot path reads (src/sphinx.h:2586-2691)
 struct GpuQuery_t
 {
-	std::unique_ptr<GpuXQNode_t>	m_pRoot;			///< XQQuery_t::m_pRoot
+	std::unique_ptr<GpuXQNode_t>	m_pRoot;			///< XQQuery_t::m_pRoot; null = parse m_sQuery
+	std::string		m_sQuery;							///< CSphQuery::m_sQuery: the query text, parsed by mgpu_parse_query (sphParseExtendedQuery + transforms)
+	int				m_eMode = MGPU_MATCH_EXTENDED;		///< CSphQuery::m_eMode (legacy modes rewrite the text and pick the ranker, PrepareQueryEmulation)
+	int				m_iMinWordLen = 1;					///< the index's tokenizer settings the parser needs
+	std::vector<std::string> m_dStopwords;
 	int				m_eRanker = MGPU_RANK_PROXIMITY_BM25;	///< m_eRanker
 	std::vector<int> m_dFieldWeights;					///< bound weights (CSphQueryContext::m_dWeights)
 	std::vector<mgpu_sortkey> m_dSortKeys;				///< CSphMatchComparatorState
@@ -93,6 +97,8 @@ struct GpuQueryResultMeta_t
 	int64_t		m_iTotalMatches = 0;		///< total_found
 	std::string	m_sError;
 	std::string	m_sWarning;
+	std::string	m_sParseError;		///< XQQuery_t::m_sParseError (text queries)
+	std::string	m_sParseWarning;	///< XQQuery_t::m_sParseWarning
 };
 
 /// ISphMatchSorter (src/sphinxsort.h:39-133), the subset MatchExtended and the result merge use
@@ -204,10 +210,36 @@ public:
 		{
 			Flatten ( pQueries[i], dFlat[i], dQ[i] );
 			Flat_t & f = dFlat[i];
+			if ( !pQueries[i].m_pRoot )
+			{
+				// the reference's own shape: MultiQuery gets the text and parses it against this index's schema (src/sphinx.cpp:15403-15430)
+				std::vector<const char *> dFields, dStops;
+				for ( int iField=0; iField<mgpu_index_num_fields ( m_pIndex ); ++iField )
+					dFields.push_back ( mgpu_index_field_name ( m_pIndex, iField ) );
+				for ( const std::string & s : pQueries[i].m_dStopwords )
+					dStops.push_back ( s.c_str() );
+				mgpu_parser_settings tTok {};
+				tTok.n_fields = (int)dFields.size();	tTok.field_names = dFields.data();
+				tTok.n_stopwords = (int)dStops.size();	tTok.stopwords = dStops.empty() ? nullptr : dStops.data();
+				tTok.min_word_len = pQueries[i].m_iMinWordLen;
+				tTok.overshort_step = 1; tTok.stopword_step = 1; tTok.ngram_cjk = 1;
+				tTok.match_mode = pQueries[i].m_eMode;
+				const int iParse = mgpu_parse_query ( &tTok, pQueries[i].m_sQuery.c_str(), &f.m_pParsed );
+				if ( iParse!=MGPU_OK )
+				{
+					pMeta[i].m_sParseError = f.m_pParsed ? mgpu_parsed_error ( f.m_pParsed ) : "parser failed";
+					dQ[i].n_nodes = 0;	// runs as an empty query; reported below
+					dQ[i].root = -1;
+				} else
+				{
+					pMeta[i].m_sParseWarning = mgpu_parsed_warning ( f.m_pParsed );
+					mgpu_parsed_fill ( f.m_pParsed, &dQ[i] );
+				}
+			}
 			const int iK = std::max ( 1, ppSorters[i]->GetMaxMatches() );
 			dQ[i].max_matches = iK;
 			f.m_dRowid.resize ( iK ); f.m_dWeight.resize ( iK ); f.m_dDocid.resize ( iK ); f.m_dSortAttr.resize ( iK );
-			f.m_dStats.resize ( std::max<size_t> ( 1, f.m_dWords.size() ) );
+			f.m_dStats.resize ( (size_t)std::max ( 1, dQ[i].n_words ) );
 			dR[i].rowid = f.m_dRowid.data(); dR[i].weight = f.m_dWeight.data(); dR[i].docid = f.m_dDocid.data();
 			dR[i].sort_attr = f.m_dSortAttr.data(); dR[i].word_stats = f.m_dStats.data();
 		}
@@ -216,6 +248,12 @@ public:
 		for ( int i=0; i<iQueries; ++i )
 		{
 			GpuQueryResultMeta_t & tMeta = pMeta[i];
+			if ( !tMeta.m_sParseError.empty() )
+			{
+				tMeta.m_sError = tMeta.m_sParseError;	// XQQuery_t::m_sParseError -> tMeta.m_sError, src/sphinx.cpp:15412
+				bOk = false;
+				continue;
+			}
 			if ( iRes!=MGPU_OK || dR[i].status!=MGPU_OK )
 			{
 				// reference: MultiQuery returns false and sets tMeta.m_sError (src/sphinx.cpp:15690); per query m_iMultiplier=-1
@@ -235,8 +273,8 @@ public:
 			ppSorters[i]->SetTotalCount ( dR[i].total_found );
 			tMeta.m_iTotalMatches = dR[i].total_found;
 			tMeta.m_dWordStats.clear();
-			for ( size_t w=0; w<dFlat[i].m_dWords.size(); ++w )	// AddStat, src/sphinxsearch.cpp:4365-4371
-				tMeta.m_dWordStats.push_back ( { dFlat[i].m_dWordStrings[w], dFlat[i].m_dStats[w].docs, dFlat[i].m_dStats[w].hits } );
+			for ( int w=0; w<dQ[i].n_words; ++w )	// AddStat, src/sphinxsearch.cpp:4365-4371
+				tMeta.m_dWordStats.push_back ( { dQ[i].words[w].word, dFlat[i].m_dStats[w].docs, dFlat[i].m_dStats[w].hits } );
 		}
 		return bOk;
 	}
@@ -252,6 +290,10 @@ private:
 		std::vector<int32_t>		m_dWeight;
 		std::vector<int64_t>		m_dDocid, m_dSortAttr;
 		std::vector<mgpu_wordstat>	m_dStats;
+		mgpu_parsed *				m_pParsed = nullptr;
+		Flat_t() = default;
+		Flat_t ( const Flat_t & ) = delete;
+		~Flat_t() { mgpu_parsed_free ( m_pParsed ); }
 	};
 
 	static int FlattenNode ( const GpuXQNode_t * pNode, Flat_t & f )

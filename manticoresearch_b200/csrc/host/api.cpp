@@ -98,6 +98,10 @@ const char * mgpu_last_error ( const mgpu_index * idx )
 int64_t mgpu_index_total_docs ( const mgpu_index * idx )	{ return idx ? (int64_t)idx->m_t.m_tHdr.m_iTotalDocuments : 0; }
 int32_t mgpu_index_num_fields ( const mgpu_index * idx )	{ return idx ? (int32_t)idx->m_t.m_tHdr.m_dFields.size() : 0; }
 int32_t mgpu_index_field_index ( const mgpu_index * idx, const char * name )	{ return ( idx && name ) ? idx->m_t.FieldIndex ( name ) : -1; }
+const char * mgpu_index_field_name ( const mgpu_index * idx, int32_t field )
+{
+	return ( idx && field>=0 && field<(int32_t)idx->m_t.m_tHdr.m_dFields.size() ) ? idx->m_t.m_tHdr.m_dFields[field].m_sName.c_str() : nullptr;
+}
 int32_t mgpu_index_attr_index ( const mgpu_index * idx, const char * name )	{ return ( idx && name ) ? idx->m_t.AttrIndex ( name ) : -1; }
 
 int mgpu_index_word_stats ( const mgpu_index * idx, const char * word, int64_t * docs, int64_t * hits )

@@ -165,6 +165,7 @@ def load_library(path=None):
         "mgpu_api_handle": (C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "mgpu_api_describe_last": (C.c_char_p, [vp]),
         "mgpu_api_free": (None, [vp]),
+        "mgpu_index_field_name": (C.c_char_p, [vp, i32]),
         "mgpu_index_check": (C.c_int, [C.c_char_p, C.POINTER(i64), C.c_char_p, C.c_int]),
         "mgpu_parse_query": (C.c_int, [C.POINTER(c_parser_settings), C.c_char_p, C.POINTER(vp)]),
         "mgpu_parsed_fill": (C.c_int, [vp, C.POINTER(c_query)]),
@@ -226,7 +227,7 @@ EXPORTED_SYMBOLS = [
     "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
     "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
     "mgpu_api_create", "mgpu_api_handle", "mgpu_api_describe_last", "mgpu_api_free",
-    "mgpu_index_check", "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
+    "mgpu_index_field_name", "mgpu_index_check", "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
 ]
 
 # ---------------------------------------------------------------------------------------------

@@ -116,6 +116,37 @@ int main ( int argc, char ** argv )
 		CHECK ( tMeta.m_dWordStats.size()==1 && tMeta.m_dWordStats[0].m_iDocs==1 && tMeta.m_dWordStats[0].m_iHits==2 );
 	}
 
+	{
+		// the same test the way the reference writes it: the query TEXT goes in (tQuery.m_sQuery = "@title cat", sphParseExtendedQuery inside)
+		GpuQuery_t tQuery;
+		tQuery.m_sQuery = "@title cat";
+		GpuMatchQueue_c tSorter ( 1000 );
+		GpuQueryResultMeta_t tMeta;
+		CHECK ( tIndex.MultiQuery ( tMeta, tQuery, &tSorter ) );
+		CHECK ( tSorter.GetLength()==1 && tSorter.GetTotalCount()==1 );
+		GpuMatch_t tMatch;
+		tSorter.Flatten ( &tMatch );
+		CHECK ( tMatch.m_tRowID==0 && tMatch.m_iWeight==1500 && tMatch.m_iDocID==1 );
+		CHECK ( tMeta.m_dWordStats.size()==1 && tMeta.m_dWordStats[0].m_sWord=="cat" && tMeta.m_dWordStats[0].m_iHits==2 );
+
+		// a text the parser refuses: MultiQuery returns false with the parser's message, nothing is pushed
+		GpuQuery_t tBad;
+		tBad.m_sQuery = "cat | (";
+		GpuMatchQueue_c tSorter2 ( 10 );
+		GpuQueryResultMeta_t tMeta2;
+		CHECK ( !tIndex.MultiQuery ( tMeta2, tBad, &tSorter2 ) );
+		CHECK ( tSorter2.GetLength()==0 && tMeta2.m_sError.find ( "syntax error" )!=std::string::npos );
+
+		// legacy match mode through the text path: mode=any is "we cat"/1 under SPH_RANK_MATCHANY (PrepareQueryEmulation)
+		GpuQuery_t tAny;
+		tAny.m_sQuery = "dog cat";
+		tAny.m_eMode = MGPU_MATCH_ANY;
+		GpuMatchQueue_c tSorter3 ( 10 );
+		GpuQueryResultMeta_t tMeta3;
+		CHECK ( tIndex.MultiQuery ( tMeta3, tAny, &tSorter3 ) );
+		CHECK ( tSorter3.GetLength()==1 );
+	}
+
 	// test/test_322 "field weights": match('program flow'), field_weights=(body=2,spam=-10) -> 3:-4574, 2:-6579, 1:-14585
 	Corpus_t tW;
 	tW.m_dFields = { "title", "body", "spam" };
