@@ -268,6 +268,7 @@ int				mgpu_sharded_search_batch ( mgpu_sharded * sh, const mgpu_query * queries
 int				mgpu_sharded_set_option ( mgpu_sharded * sh, const char * name, int64_t value );   /* mgpu_index_set_option on every shard */
 int64_t			mgpu_sharded_total_docs ( const mgpu_sharded * sh );
 int				mgpu_sharded_word_docs ( const mgpu_sharded * sh, const char * word, int64_t * docs );   /* global df; returns 1 if found */
+int				mgpu_sharded_word_stats ( const mgpu_sharded * sh, const char * word, int64_t * docs, int64_t * hits );   /* summed over the shards */
 const char *	mgpu_sharded_last_error ( const mgpu_sharded * sh );   /* sh may be NULL: last open error */
 typedef struct mgpu_sharded_stats {
 	int32_t			n_shards;
@@ -362,6 +363,9 @@ void			mgpu_parsed_free ( mgpu_parsed * p );
  * tokenizer may be NULL: min_word_len / overshort_step / stopword_step come from the index header, no stop words. */
 typedef struct mgpu_api mgpu_api;
 int				mgpu_api_create ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out );
+/* the same responder over a sharded handle (one GPU per rowid-range shard): the packet's queries run as one mgpu_sharded_search_batch,
+ * attribute values come from the shard that holds the row, keyword statistics are the whole index's. path_prefixes in shard order. */
+int				mgpu_api_create_sharded ( mgpu_sharded * sh, const char * const * path_prefixes, int n_shards, const mgpu_parser_settings * tokenizer, mgpu_api ** out );
 /* *reply points into memory owned by the responder, valid until the next call on it or mgpu_api_free. Returns MGPU_OK whenever a
  * reply packet was produced (protocol and query errors travel inside the reply, as on the wire). */
 int				mgpu_api_handle ( mgpu_api * api, const void * request, size_t request_len, const void ** reply, size_t * reply_len );

@@ -318,9 +318,21 @@ using namespace mgpu;
 struct mgpu_api
 {
 	mgpu_index *				m_pIndex = nullptr;
+	mgpu_sharded *				m_pSharded = nullptr;	///< set instead of m_pIndex: rowid-range shards, results carry global rowids
 	IndexHeader_t				m_tHdr;
-	Mapped_t					m_tSpa;
+	std::vector<std::unique_ptr<Mapped_t>> m_dSpa;		///< the shards' attribute rows, in shard order
+	std::vector<uint64_t>		m_dBase;				///< global rowid of every shard's row 0, plus the total at the end
 	int							m_iStride = 0;
+
+	bool HasIndex () const		{ return m_pIndex || m_pSharded; }
+	/// the attribute row of a (global) rowid
+	const DWORD * Row ( uint32_t uRowid ) const
+	{
+		size_t s = 0;
+		while ( s+1<m_dSpa.size() && uRowid>=m_dBase[s+1] )
+			++s;
+		return (const DWORD *)m_dSpa[s]->m_p + (size_t)( uRowid-m_dBase[s] )*m_iStride;
+	}
 	mgpu_parser_settings		m_tTok {};
 	std::vector<std::string>	m_dFieldNames, m_dStopwords;
 	std::vector<const char *>	m_dFieldPtrs, m_dStopPtrs;
@@ -636,12 +648,11 @@ static void SendResult ( const mgpu_api & A, const ApiQuery_t & q, const Prepare
 	const int iCount = std::max ( 0, std::min ( q.m_iLimit, r.n_matches-iFrom ) );
 	tOut.SendInt ( iCount );
 	tOut.SendInt ( 1 );		// 64-bit ids
-	const DWORD * pRows = (const DWORD *)A.m_tSpa.m_p;
 	for ( int i=iFrom; i<iFrom+iCount; ++i )
 	{
 		tOut.SendUint64 ( (uint64_t)r.docid[i] );
 		tOut.SendInt ( r.weight[i] );
-		const DWORD * pRow = pRows + (size_t)r.rowid[i]*A.m_iStride;
+		const DWORD * pRow = A.Row ( r.rowid[i] );
 		for ( size_t a=1; a<A.m_tHdr.m_dAttrs.size(); ++a )
 		{
 			const SchemaAttr_t & t = A.m_tHdr.m_dAttrs[a];
@@ -688,7 +699,7 @@ static void SendErrorReply ( NetWriter_t & tOut, const std::string & sError )
 extern "C"
 {
 
-static int ApiCreateImpl ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out );
+static int ApiCreateImpl ( mgpu_index * idx, mgpu_sharded * sh, const char * const * path_prefixes, int n_prefixes, const mgpu_parser_settings * tokenizer, mgpu_api ** out );
 
 int mgpu_api_create ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out )
 {
@@ -697,27 +708,54 @@ int mgpu_api_create ( mgpu_index * idx, const char * path_prefix, const mgpu_par
 	*out = nullptr;
 	try
 	{
-		return ApiCreateImpl ( idx, path_prefix, tokenizer, out );
+		return ApiCreateImpl ( idx, nullptr, &path_prefix, 1, tokenizer, out );
 	} catch ( ... )
 	{
 		return MGPU_E_NOMEM;
 	}
 }
 
-static int ApiCreateImpl ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out )
+static int ApiCreateImpl ( mgpu_index * idx, mgpu_sharded * sh, const char * const * path_prefixes, int n_prefixes, const mgpu_parser_settings * tokenizer, mgpu_api ** out )
 {
 	std::unique_ptr<mgpu_api> p ( new mgpu_api );
 	p->m_pIndex = idx;
-	Mapped_t tSph;
+	p->m_pSharded = sh;
 	std::string sError;
-	const std::string sPrefix ( path_prefix );
-	if ( !tSph.Map ( sPrefix+".sph" ) || !p->m_tSpa.Map ( sPrefix+".spa" ) )
-		return MGPU_E_IO;
-	if ( !ReadHeader ( tSph.m_p, tSph.m_iLen, p->m_tHdr, sError ) || p->m_tHdr.m_dAttrs.empty() )
-		return MGPU_E_FORMAT;
-	p->m_iStride = p->m_tHdr.RowStride();
-	if ( (int64_t)p->m_tSpa.m_iLen<p->m_tHdr.m_iDocinfo*p->m_iStride*4 )
-		return MGPU_E_FORMAT;
+	uint64_t uBase = 0;
+	for ( int s=0; s<n_prefixes; ++s )
+	{
+		if ( !path_prefixes[s] )
+			return MGPU_E_BAD_QUERY;
+		const std::string sPrefix ( path_prefixes[s] );
+		Mapped_t tSph;
+		std::unique_ptr<Mapped_t> pSpa ( new Mapped_t );
+		if ( !tSph.Map ( sPrefix+".sph" ) || !pSpa->Map ( sPrefix+".spa" ) )
+			return MGPU_E_IO;
+		IndexHeader_t tHdr;
+		if ( !ReadHeader ( tSph.m_p, tSph.m_iLen, tHdr, sError ) || tHdr.m_dAttrs.empty() || tHdr.m_iDocinfo<0 )
+			return MGPU_E_FORMAT;
+		const int iStride = tHdr.RowStride();
+		if ( (int64_t)pSpa->m_iLen/4/std::max ( iStride, 1 )<tHdr.m_iDocinfo )
+			return MGPU_E_FORMAT;
+		if ( s==0 )
+		{
+			p->m_tHdr = tHdr;
+			p->m_iStride = iStride;
+		} else
+		{
+			// shards of one index share its schema
+			bool bSame = tHdr.m_dAttrs.size()==p->m_tHdr.m_dAttrs.size() && tHdr.m_dFields.size()==p->m_tHdr.m_dFields.size() && iStride==p->m_iStride;
+			for ( size_t a=0; bSame && a<tHdr.m_dAttrs.size(); ++a )
+				bSame = tHdr.m_dAttrs[a].m_sName==p->m_tHdr.m_dAttrs[a].m_sName && tHdr.m_dAttrs[a].m_iBitOffset==p->m_tHdr.m_dAttrs[a].m_iBitOffset
+					&& tHdr.m_dAttrs[a].m_iBitCount==p->m_tHdr.m_dAttrs[a].m_iBitCount;
+			if ( !bSame )
+				return MGPU_E_FORMAT;
+		}
+		p->m_dSpa.push_back ( std::move ( pSpa ) );
+		p->m_dBase.push_back ( uBase );
+		uBase += (uint64_t)tHdr.m_iDocinfo;
+	}
+	p->m_dBase.push_back ( uBase );
 
 	// the tokenizer settings are copied; the field names are always the index's own
 	if ( tokenizer )
@@ -744,6 +782,20 @@ static int ApiCreateImpl ( mgpu_index * idx, const char * path_prefix, const mgp
 	p->m_tTok.stopwords = p->m_dStopPtrs.empty() ? nullptr : p->m_dStopPtrs.data();
 	*out = p.release();
 	return MGPU_OK;
+}
+
+int mgpu_api_create_sharded ( mgpu_sharded * sh, const char * const * path_prefixes, int n_shards, const mgpu_parser_settings * tokenizer, mgpu_api ** out )
+{
+	if ( !path_prefixes || n_shards<1 || !out )
+		return MGPU_E_BAD_QUERY;
+	*out = nullptr;
+	try
+	{
+		return ApiCreateImpl ( nullptr, sh, path_prefixes, n_shards, tokenizer, out );
+	} catch ( ... )
+	{
+		return MGPU_E_NOMEM;
+	}
 }
 
 void mgpu_api_free ( mgpu_api * api )
@@ -820,7 +872,7 @@ static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_
 			SendErrorReply ( tOut, "invalid or truncated request" );
 			return fnDone();
 		}
-		if ( bStats && !A.m_pIndex )
+		if ( bStats && !A.HasIndex() )
 		{
 			SendErrorReply ( tOut, "no index is attached to this responder" );
 			return fnDone();
@@ -841,7 +893,10 @@ static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_
 			if ( bStats )
 			{
 				int64_t iDocs = 0, iHits = 0;
-				mgpu_index_word_stats ( A.m_pIndex, w.first.c_str(), &iDocs, &iHits );
+				if ( A.m_pSharded )
+					mgpu_sharded_word_stats ( A.m_pSharded, w.first.c_str(), &iDocs, &iHits );
+				else
+					mgpu_index_word_stats ( A.m_pIndex, w.first.c_str(), &iDocs, &iHits );
 				tOut.SendAsDword ( iDocs );
 				tOut.SendAsDword ( iHits );
 			}
@@ -917,7 +972,7 @@ static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_
 		dPrepared.emplace_back ( new Prepared_t );
 		Prepared_t & P = *dPrepared.back();
 		Prepare ( A, q, P );
-		if ( P.m_sError.empty() && !A.m_pIndex )
+		if ( P.m_sError.empty() && !A.HasIndex() )
 			P.m_sError = "no index is attached to this responder";
 		if ( P.m_sError.empty() )
 		{
@@ -928,7 +983,9 @@ static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_
 	}
 	if ( !dBatch.empty() )
 	{
-		const int iRes = mgpu_search_batch ( A.m_pIndex, dBatch.data(), (int)dBatch.size(), dResults.data() );
+		const int iRes = A.m_pSharded ? mgpu_sharded_search_batch ( A.m_pSharded, dBatch.data(), (int)dBatch.size(), dResults.data() )
+			: mgpu_search_batch ( A.m_pIndex, dBatch.data(), (int)dBatch.size(), dResults.data() );
+		const char * sLast = A.m_pSharded ? mgpu_sharded_last_error ( A.m_pSharded ) : mgpu_last_error ( A.m_pIndex );
 		for ( auto & pP : dPrepared )
 			if ( pP->m_iBatchSlot>=0 )
 			{
@@ -937,7 +994,7 @@ static int ApiHandleImpl ( mgpu_api * api, const void * request, size_t request_
 				if ( iStatus==MGPU_E_UNSUPPORTED )
 					pP->m_sError = "query uses an operator or option the GPU path does not implement";
 				else if ( iStatus!=MGPU_OK )
-					pP->m_sError = std::string ( "search failed: " ) + ( mgpu_last_error ( A.m_pIndex ) ? mgpu_last_error ( A.m_pIndex ) : "" ) + " (code " + std::to_string ( iStatus ) + ")";
+					pP->m_sError = std::string ( "search failed: " ) + ( sLast ? sLast : "" ) + " (code " + std::to_string ( iStatus ) + ")";
 			}
 	}
 	const int iMsec = (int)std::chrono::duration_cast<std::chrono::milliseconds> ( std::chrono::steady_clock::now()-tStart ).count();

@@ -595,6 +595,20 @@ int mgpu_sharded_word_docs ( const mgpu_sharded * sh, const char * word, int64_t
 	return 1;
 }
 
+int mgpu_sharded_word_stats ( const mgpu_sharded * sh, const char * word, int64_t * docs, int64_t * hits )
+{
+	if ( !sh || !word )
+		return 0;
+	auto it = sh->m_t.m_hGlobalDocs.find ( sh->m_t.m_dShards[0]->DictKey ( word ) );
+	if ( it==sh->m_t.m_hGlobalDocs.end() )
+		return 0;
+	if ( docs )
+		*docs = it->second.m_iDocs;
+	if ( hits )
+		*hits = it->second.m_iHits;
+	return 1;
+}
+
 const char * mgpu_sharded_last_error ( const mgpu_sharded * sh )
 {
 	return sh ? sh->m_t.m_sError.c_str() : g_sLastShardedOpenError.c_str();

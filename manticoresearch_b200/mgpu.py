@@ -162,6 +162,8 @@ def load_library(path=None):
         "mgpu_unpack_key": (None, [C.POINTER(C.c_uint64), C.POINTER(u32), C.POINTER(i32), C.POINTER(C.c_uint64)]),
         "mgpu_decode_doclist": (C.c_int, [vp, C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64), i64, C.POINTER(i64)]),
         "mgpu_api_create": (C.c_int, [vp, C.c_char_p, C.POINTER(c_parser_settings), C.POINTER(vp)]),
+        "mgpu_api_create_sharded": (C.c_int, [vp, C.POINTER(C.c_char_p), C.c_int, C.POINTER(c_parser_settings), C.POINTER(vp)]),
+        "mgpu_sharded_word_stats": (C.c_int, [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
         "mgpu_api_handle": (C.c_int, [vp, C.c_char_p, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "mgpu_api_describe_last": (C.c_char_p, [vp]),
         "mgpu_api_free": (None, [vp]),
@@ -226,7 +228,7 @@ EXPORTED_SYMBOLS = [
     "mgpu_merge_shard_keys", "mgpu_unpack_key", "mgpu_decode_doclist",
     "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
     "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
-    "mgpu_api_create", "mgpu_api_handle", "mgpu_api_describe_last", "mgpu_api_free",
+    "mgpu_api_create", "mgpu_api_create_sharded", "mgpu_sharded_word_stats", "mgpu_api_handle", "mgpu_api_describe_last", "mgpu_api_free",
     "mgpu_index_field_name", "mgpu_index_check", "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
 ]
 
@@ -326,7 +328,8 @@ MATCH_ALL, MATCH_ANY, MATCH_PHRASE, MATCH_BOOLEAN, MATCH_EXTENDED = range(5)
 
 
 class ApiResponder:
-    """mgpu_api_*: SphinxAPI `search` packets in, reply packets out. index may be None (host-only: parse / describe / error replies)."""
+    """mgpu_api_*: SphinxAPI `search` / `keywords` packets in, reply packets out. index: an Index (path_prefix = its prefix), a ShardedIndex
+    (path_prefix = the shards' prefixes in order) or None (host-only: parse / describe / error replies)."""
     def __init__(self, index, path_prefix, min_word_len=None, stopwords=()):
         self._lib = lib()
         self._h = C.c_void_p()
@@ -336,7 +339,13 @@ class ApiResponder:
             self._stops = (C.c_char_p * max(1, len(stopwords)))(*[w.encode("utf-8") for w in stopwords])
             st.min_word_len, st.n_stopwords, st.stopwords = min_word_len or 1, len(stopwords), self._stops
             st.overshort_step, st.stopword_step, st.ngram_cjk = 1, 1, 1
-        rc = self._lib.mgpu_api_create(index._h if index is not None else None, path_prefix.encode(), C.byref(st) if st is not None else None, C.byref(self._h))
+        pst = C.byref(st) if st is not None else None
+        if isinstance(index, ShardedIndex):
+            prefixes = list(path_prefix)
+            arr = (C.c_char_p * len(prefixes))(*[p.encode() for p in prefixes])
+            rc = self._lib.mgpu_api_create_sharded(index._h, arr, len(prefixes), pst, C.byref(self._h))
+        else:
+            rc = self._lib.mgpu_api_create(index._h if index is not None else None, path_prefix.encode(), pst, C.byref(self._h))
         if rc != MGPU_OK:
             raise MgpuError(rc, "mgpu_api_create")
 

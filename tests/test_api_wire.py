@@ -321,3 +321,35 @@ def test_reference_client_reads_the_replies():
             assert {w["word"]: (w["docs"], w["hits"]) for w in theirs["words"]} == ours["words"]
             for m in theirs["matches"]:
                 assert m["attrs"]["group_id"] == docs[m["id"]]["attrs"][0]
+
+
+@pytest.mark.gpu
+def test_sharded_responder_answers_like_the_single_index_one(tmp_path):
+    """mgpu_api_create_sharded: the same packets over two rowid-range shards (one mgpu_sharded_search_batch per packet): same matches,
+    weights, attribute values (read from the shard that holds the row), totals and whole-index keyword statistics"""
+    full = str(tmp_path / "full")
+    build_corpus(full)
+    docs = corpus_docs()
+    prefixes = [str(tmp_path / "s0"), str(tmp_path / "s1")]
+    M.build_index(prefixes[0], ["title", "body"], docs[:37], attr_names=["group_id", "stamp"])
+    M.build_index(prefixes[1], ["title", "body"], docs[37:], attr_names=["group_id", "stamp"])
+    gpu, sh = M.Index(full, device=0), M.ShardedIndex(prefixes, [0, 0])
+    one, two = M.ApiResponder(gpu, full), M.ApiResponder(sh, prefixes)
+    try:
+        for name in SEARCH_NAMES:
+            _, a = parse_reply(one.handle(REQUESTS[name]), N_QUERIES[name])
+            _, b = parse_reply(two.handle(REQUESTS[name]), N_QUERIES[name])
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                x.pop("time_msec", None)
+                y.pop("time_msec", None)
+                assert x == y, name
+            assert any(r["status"] == SEARCHD_OK and r["matches"] for r in b)
+        _, wa = parse_keywords_reply(one.handle(REQUESTS["keywords_stats"]), True)
+        _, wb = parse_keywords_reply(two.handle(REQUESTS["keywords_stats"]), True)
+        assert wa == wb and wb[0]["docs"] > 0
+    finally:
+        one.close()
+        two.close()
+        sh.close()
+        gpu.close()
