@@ -353,3 +353,39 @@ def test_sharded_responder_answers_like_the_single_index_one(tmp_path):
         two.close()
         sh.close()
         gpu.close()
+
+
+def test_mutated_packets_never_crash(tmp_path):
+    """byte-level fuzz of the daemon-facing entry point: every mutation of a valid packet is answered with a well-formed reply"""
+    import random
+    rng = random.Random(4242)
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    api = M.ApiResponder(None, prefix)
+    try:
+        names = list(REQUESTS)
+        ok = err = 0
+        for _ in range(4000):
+            name = rng.choice(names)
+            raw = bytearray(REQUESTS[name])
+            for _ in range(rng.randint(1, 4)):
+                how = rng.random()
+                pos = rng.randrange(8, len(raw))
+                if how < 0.5:
+                    raw[pos] = rng.randrange(256)
+                elif how < 0.7:
+                    raw[pos:pos + 4] = struct.pack(">L", rng.choice([0, 1, 0xFFFFFFFF, 0x7FFFFFFF, 0x80000000, len(raw), 1 << 20]))
+                elif how < 0.85:
+                    del raw[pos:pos + rng.randint(1, 16)]
+                else:
+                    raw[pos:pos] = bytes(rng.randrange(256) for _ in range(rng.randint(1, 16)))
+            if rng.random() < 0.8:
+                raw[4:8] = struct.pack(">L", len(raw) - 8)      # keep the framing right so that the body parser is what gets exercised
+            reply = api.handle(bytes(raw))
+            status, ver, length = struct.unpack_from(">2HL", reply, 0)
+            assert length == len(reply) - 8 and status in (SEARCHD_OK, SEARCHD_ERROR)
+            ok += status == SEARCHD_OK
+            err += status == SEARCHD_ERROR
+        assert ok > 200 and err > 200
+    finally:
+        api.close()
