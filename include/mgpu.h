@@ -360,6 +360,8 @@ void			mgpu_parsed_free ( mgpu_parsed * p );
  * lists other than "*", string and float filters, cutoff, outer order) is answered with SEARCHD_ERROR for that query, as searchd
  * answers a query it cannot run.  No sockets: the embedding daemon owns the connection (src/netreceive_api.cpp).
  * idx may be NULL: packets are parsed, described and answered with per-query errors (host-only use, tests).
+ * A responder serves one packet at a time (its reply buffer is reused): one responder per connection thread; the index handle under
+ * them is shared and thread-safe.
  * tokenizer may be NULL: min_word_len / overshort_step / stopword_step come from the index header, no stop words. */
 typedef struct mgpu_api mgpu_api;
 int				mgpu_api_create ( mgpu_index * idx, const char * path_prefix, const mgpu_parser_settings * tokenizer, mgpu_api ** out );

@@ -761,8 +761,9 @@ static int ApiCreateImpl ( mgpu_index * idx, mgpu_sharded * sh, const char * con
 	if ( tokenizer )
 	{
 		p->m_tTok = *tokenizer;
-		for ( int i=0; i<tokenizer->n_stopwords; ++i )
-			p->m_dStopwords.push_back ( tokenizer->stopwords[i] );
+		for ( int i=0; i<tokenizer->n_stopwords && tokenizer->stopwords; ++i )
+			if ( tokenizer->stopwords[i] )
+				p->m_dStopwords.push_back ( tokenizer->stopwords[i] );
 	} else
 	{
 		p->m_tTok.min_word_len = (int)p->m_tHdr.m_iMinWordLen;

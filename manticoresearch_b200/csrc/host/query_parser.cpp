@@ -276,9 +276,10 @@ public:
 		m_tTok.m_iMinWordLen = s.min_word_len>0 ? s.min_word_len : 1;
 		m_tTok.m_bCjk = s.ngram_cjk!=0;
 		for ( int i=0; i<s.n_fields; ++i )
-			m_dFields.push_back ( s.field_names[i] );
+			m_dFields.push_back ( s.field_names[i] ? s.field_names[i] : "" );
 		for ( int i=0; i<s.n_stopwords; ++i )
-			m_hStopwords.insert ( s.stopwords[i] );
+			if ( s.stopwords[i] )
+				m_hStopwords.insert ( s.stopwords[i] );
 		m_iOvershortStep = s.overshort_step<0 ? 0 : ( s.overshort_step>1 ? 1 : s.overshort_step );
 		m_bEmptyStopword = ( s.stopword_step==0 );
 	}
@@ -1397,7 +1398,8 @@ void TokenizePlain ( const mgpu_parser_settings & s, const char * sText, std::ve
 	tTok.SetBuffer ( sBuf.c_str(), (int)sBuf.size() );
 	std::unordered_set<std::string> hStop;
 	for ( int i=0; i<s.n_stopwords; ++i )
-		hStop.insert ( s.stopwords[i] );
+		if ( s.stopwords[i] )
+			hStop.insert ( s.stopwords[i] );
 	int iPos = 0;
 	while ( const char * sToken = tTok.GetToken() )
 	{
