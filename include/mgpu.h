@@ -348,6 +348,9 @@ int				mgpu_parse_query ( const mgpu_parser_settings * settings, const char * te
 int				mgpu_parsed_fill ( const mgpu_parsed * p, mgpu_query * q );
 const char *	mgpu_parsed_error ( const mgpu_parsed * p );      /* XQQuery_t::m_sParseError */
 const char *	mgpu_parsed_warning ( const mgpu_parsed * p );    /* XQQuery_t::m_sParseWarning */
+/* the tree as SHOW PLAN prints it (`transformed_tree`: sphExplainQuery + sph::RenderBsonPlan, src/sphinxsearch.cpp:300-335, 430-530;
+ * a percent quorum shows its percentage, as there) */
+const char *	mgpu_parsed_explain ( const mgpu_parsed * p );
 void			mgpu_parsed_free ( mgpu_parsed * p );
 
 /* ------------------------------------------------------------------------------------- */

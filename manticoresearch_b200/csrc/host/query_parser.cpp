@@ -11,6 +11,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <strings.h>
 #include <ctype.h>
@@ -1428,6 +1429,7 @@ struct mgpu_parsed
 	std::vector<std::string>	m_dStrings;
 	int							m_iRoot = 0;
 	std::string					m_sError, m_sWarning;
+	std::string					m_sExplain;		///< SHOW PLAN's transformed_tree
 	int							m_iRanker = -1;
 };
 
@@ -1440,6 +1442,69 @@ static int CountWords ( const PNode_t * p )
 	for ( const PNode_t * c : p->m_dChildren )
 		n += CountWords ( c );
 	return n;
+}
+
+/// the tree as SHOW PLAN prints it: BuildProfileBson + RenderPlainBsonPlan (src/sphinxsearch.cpp:300-335, 430-495) with the plain
+/// indent and line break ("  ", "\n"); a keyword is KEYWORD(word, querypos=N[, excluded][, field_start][, field_end][, boost=%f])
+static void Explain ( const PNode_t * p, const std::vector<std::string> & dFields, int iIndent, std::string & sOut )
+{
+	static const char * dNames[] = { "AND", "OR", "MAYBE", "NOT", "ANDNOT", "BEFORE", "PHRASE", "PROXIMITY", "QUORUM", "NEAR", "NOTNEAR" };
+	if ( iIndent )
+		sOut += "\n";
+	for ( int i=0; i<iIndent; ++i )
+		sOut += "  ";
+	sOut += ( p->m_iOp>=0 && p->m_iOp<=MGPU_OP_NOTNEAR ) ? dNames[p->m_iOp] : "OPERATOR";
+	sOut += "(";
+	bool bComma = false;
+	auto fnItem = [&] ( const std::string & s ) { if ( bComma ) sOut += ", "; sOut += s; bComma = true; };
+	if ( p->m_iOp==MGPU_OP_PROXIMITY || p->m_iOp==MGPU_OP_NEAR )
+		fnItem ( "distance=" + std::to_string ( p->m_iOpArg ) );
+	else if ( p->m_iOp==MGPU_OP_QUORUM )
+		fnItem ( "count=" + std::to_string ( p->m_iOpArg ) );
+	if ( !p->m_dChildren.empty() && !p->m_dWords.empty() )
+		fnItem ( "virtually-plain" );
+	if ( !p->m_dWords.empty() )
+	{
+		// AddAccessSpecsBson: only keyword nodes carry their limits into the plan
+		if ( p->m_tSpec.m_bFieldSpec && p->m_tSpec.m_uFieldMask!=0xFFFFFFFFu )
+		{
+			std::string s = "fields=(";
+			bool bFirst = true;
+			for ( size_t i=0; i<dFields.size() && i<32; ++i )
+				if ( p->m_tSpec.m_uFieldMask & ( 1u<<i ) )
+				{
+					s += ( bFirst ? "" : ", " ) + dFields[i];
+					bFirst = false;
+				}
+			fnItem ( s + ")" );
+		}
+		if ( p->m_tSpec.m_iFieldMaxPos )
+			fnItem ( "max_field_pos=" + std::to_string ( p->m_tSpec.m_iFieldMaxPos ) );
+	}
+	if ( p->m_dChildren.empty() )
+		for ( const PWord_t & w : p->m_dWords )
+		{
+			std::string s = "KEYWORD(" + w.m_sWord + ", querypos=" + std::to_string ( w.m_iAtomPos );
+			if ( w.m_bExcluded )	s += ", excluded";
+			if ( w.m_bFieldStart )	s += ", field_start";
+			if ( w.m_bFieldEnd )	s += ", field_end";
+			if ( w.m_fBoost!=1.0f )
+			{
+				char sBuf[64];
+				snprintf ( sBuf, sizeof(sBuf), ", boost=%f", (double)w.m_fBoost );
+				s += sBuf;
+			}
+			fnItem ( s + ")" );
+		}
+	else
+		for ( const PNode_t * c : p->m_dChildren )
+		{
+			if ( bComma )
+				sOut += ", ";
+			bComma = true;
+			Explain ( c, dFields, iIndent+1, sOut );
+		}
+	sOut += ")";
 }
 
 static int Flatten ( const PNode_t * p, mgpu_parsed & tOut )
@@ -1547,6 +1612,12 @@ static int ParseQueryImpl ( const mgpu_parser_settings * settings, const char * 
 		tParser.TransformQuorum ( pRoot );
 		tParser.TransformNear ( pRoot );
 		tParser.TagExcluded ( pRoot, false );
+		{
+			std::vector<std::string> dFields;
+			for ( int i=0; i<settings->n_fields; ++i )
+				dFields.push_back ( settings->field_names[i] ? settings->field_names[i] : "" );
+			mgpu::Explain ( pRoot, dFields, 0, pRes->m_sExplain );
+		}
 		pRes->m_dStrings.reserve ( mgpu::CountWords ( pRoot ) );
 		pRes->m_iRoot = mgpu::Flatten ( pRoot, *pRes );
 		for ( auto & k : pRes->m_dWords )
@@ -1574,6 +1645,7 @@ int mgpu_parsed_fill ( const mgpu_parsed * p, mgpu_query * q )
 
 const char * mgpu_parsed_error ( const mgpu_parsed * p )		{ return p ? p->m_sError.c_str() : ""; }
 const char * mgpu_parsed_warning ( const mgpu_parsed * p )	{ return p ? p->m_sWarning.c_str() : ""; }
+const char * mgpu_parsed_explain ( const mgpu_parsed * p )	{ return p ? p->m_sExplain.c_str() : ""; }
 void mgpu_parsed_free ( mgpu_parsed * p )					{ delete p; }
 
 } // extern "C"

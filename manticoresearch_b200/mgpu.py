@@ -173,6 +173,7 @@ def load_library(path=None):
         "mgpu_parsed_fill": (C.c_int, [vp, C.POINTER(c_query)]),
         "mgpu_parsed_error": (C.c_char_p, [vp]),
         "mgpu_parsed_warning": (C.c_char_p, [vp]),
+        "mgpu_parsed_explain": (C.c_char_p, [vp]),
         "mgpu_parsed_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -229,7 +230,7 @@ EXPORTED_SYMBOLS = [
     "mgpu_sharded_open", "mgpu_sharded_close", "mgpu_sharded_search_batch", "mgpu_sharded_set_option", "mgpu_sharded_total_docs",
     "mgpu_sharded_word_docs", "mgpu_sharded_last_error", "mgpu_sharded_get_stats",
     "mgpu_api_create", "mgpu_api_create_sharded", "mgpu_sharded_word_stats", "mgpu_api_handle", "mgpu_api_describe_last", "mgpu_api_free",
-    "mgpu_index_field_name", "mgpu_index_check", "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_free",
+    "mgpu_index_field_name", "mgpu_index_check", "mgpu_parse_query", "mgpu_parsed_fill", "mgpu_parsed_error", "mgpu_parsed_warning", "mgpu_parsed_explain", "mgpu_parsed_free",
 ]
 
 # ---------------------------------------------------------------------------------------------
@@ -375,7 +376,12 @@ def check_index(path_prefix):
     return n.value, buf.value.decode("utf-8", "replace")
 
 
-def parse_query(text, field_names, min_word_len=1, stopwords=(), match_mode=MATCH_EXTENDED, ngram_cjk=True, overshort_step=1, stopword_step=1):
+def explain_query(text, field_names, **kwargs):
+    """mgpu_parsed_explain: the parsed tree in SHOW PLAN's text form"""
+    return parse_query(text, field_names, _explain=True, **kwargs)
+
+
+def parse_query(text, field_names, min_word_len=1, stopwords=(), match_mode=MATCH_EXTENDED, ngram_cjk=True, overshort_step=1, stopword_step=1, _explain=False):
     """mgpu_parse_query -> (root Node, ranker forced by a legacy match mode or None, warning). Raises MgpuError on a parse error.
     Host only: works without a GPU."""
     l = lib()
@@ -392,6 +398,8 @@ def parse_query(text, field_names, min_word_len=1, stopwords=(), match_mode=MATC
     try:
         if rc != MGPU_OK:
             raise MgpuError(rc, l.mgpu_parsed_error(h).decode("utf-8", "replace"))
+        if _explain:
+            return l.mgpu_parsed_explain(h).decode("utf-8", "replace")
         q = c_query()
         q.ranker = -1
         rc = l.mgpu_parsed_fill(h, C.byref(q))

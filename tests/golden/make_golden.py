@@ -535,3 +535,35 @@ for case in out["cases"]:
 with open(os.path.join(HERE, "golden_vectors.json"), "w", encoding="utf-8") as f:
     json.dump(out, f, ensure_ascii=False, indent=1)
 print("wrote", sum(len(c["queries"]) for c in out["cases"]), "golden queries in", len(out["cases"]), "cases")
+
+# ---------------------------------------------------------------------------------------------
+# SHOW PLAN: the reference's OWN parser output (`transformed_tree`, sphExplainQuery) for every query of its test suite whose index has
+# no morphology / wordforms / blended characters in play -> tests/golden/show_plan.json; tests/test_query_parser.py requires
+# mgpu_parsed_explain to print the same text. test_207's lemmatised keywords are kept for their MODIFIERS (field_end / boost): the
+# keyword itself is masked there.
+# ---------------------------------------------------------------------------------------------
+plans = []
+
+
+def harvest(test, keep, **settings):
+    m = php_unserialize(open(os.path.join(REF, test, "model.bin"), "rb").read())[0]
+    prev = None
+    for k, q in m.items():
+        if isinstance(q, dict) and str(q.get("sphinxql", "")).lower().strip().startswith("show plan") and k in keep:
+            tree = [row["Value"] for row in (q.get("rows") or {}).values() if row.get("Variable") == "transformed_tree"][0]
+            mm = re.search(r"match\s*\(\s*'(.*)'\s*\)", prev["sphinxql"], re.I | re.S)
+            text = mm.group(1).replace("\\\\", "\\")        # the SphinxQL string literal's own escaping
+            plans.append(dict({"test": test, "query": text, "plan": tree}, **settings))
+        prev = q
+
+
+harvest("test_022", {24, 27, 30, 33, 36, 39}, fields=["title", "content"])      # multi1 / multi2: their multiforms do not fire on these
+harvest("test_022", {68}, fields=["title", "content"])                          # '"foo bar baz"/24 mois': the threshold takes a position
+harvest("test_113", {8}, fields=["title"])
+harvest("test_115", {43, 46}, fields=["title"])
+harvest("test_192", {57}, fields=["title", "content"])
+harvest("test_222", {217}, fields=["title"])                                    # escaped modifiers are not modifiers
+harvest("test_207", {211, 213, 215, 217, 219}, fields=["title"], mask_words=True)
+with open(os.path.join(HERE, "show_plan.json"), "w", encoding="utf-8") as f:
+    json.dump({"source": "SHOW PLAN rows of ravelry/manticoresearch test/test_022,113,115,192,207,222 model.bin", "plans": plans}, f, ensure_ascii=False, indent=1)
+print("wrote %d SHOW PLAN vectors" % len(plans))

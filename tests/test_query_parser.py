@@ -252,3 +252,29 @@ def test_pathological_nesting_is_refused_not_crashed():
     assert len(root.children) == 20000
     root, _, _ = M.parse_query("(" * 300 + "a b" + ")" * 300, FIELDS)
     assert compact(root) == ["and", ["kw", "a", 1], ["kw", "b", 2]]
+
+
+def _show_plans():
+    import json
+    import os
+    return json.load(open(os.path.join(helpers.ROOT, "tests", "golden", "show_plan.json"), encoding="utf-8"))["plans"]
+
+
+@pytest.mark.parametrize("i", range(17))
+def test_explain_equals_the_references_show_plan(i):
+    """mgpu_parsed_explain vs the `transformed_tree` rows the reference's searchd printed for its own test queries (SHOW PLAN,
+    sphExplainQuery): the reference parser's output itself, not a hand transcription"""
+    p = _show_plans()[i]
+    got = " ".join(M.explain_query(p["query"], p["fields"]).split())
+    want = " ".join(p["plan"].split())
+    if p.get("mask_words"):     # a lemmatiser rewrote the keyword there; its modifiers are what this vector pins
+        mask = lambda s: re.sub(r"KEYWORD\([^,]+,", "KEYWORD(*,", s).replace(", morphed", "")
+        got, want = mask(got), mask(want)
+    assert got == want, p["query"]
+
+
+def test_explain_format():
+    assert M.explain_query("@title hello -world", FIELDS) == ("ANDNOT(\n  AND(\n    AND(fields=(title), KEYWORD(hello, querypos=1))), \n  NOT(\n"
+                                                               "    AND(fields=(title), KEYWORD(world, querypos=2, excluded))))")
+    assert " ".join(M.explain_query('"a b"~3 | ^c$ | @body[5] d', FIELDS).split()) == \
+        "OR( PROXIMITY(distance=3, KEYWORD(a, querypos=1), KEYWORD(b, querypos=2)), AND(KEYWORD(c, querypos=4, field_start, field_end)), AND(fields=(body), max_field_pos=5, KEYWORD(d, querypos=5)))"
