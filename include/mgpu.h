@@ -320,7 +320,7 @@ int				mgpu_index_check ( const char * path_prefix, int64_t * n_failures, char *
  * tree fix-ups (XQParseHelper_c::FixupTree, :343-387) and the legacy match modes' rewrite (PrepareQueryEmulation,
  * src/searchd.cpp:2141-2190).  Host only, no GPU needed.  The tokenizer is the reference's default charset_table (ASCII
  * alphanumerics + '_', Cyrillic, case folded) plus CJK unigrams when ngram_cjk is set; min_word_len and stop words consume query
- * positions as in the reference (overshort_step / stopword_step).  Not parsed: zones, SENTENCE / PARAGRAPH, exact-form '=',
+ * positions as in the reference (overshort_step / stopword_step).  @@relaxed and the phrase star are understood.  Not parsed: zones, SENTENCE / PARAGRAPH, exact-form '=',
  * wildcards, blended characters (MGPU_E_UNSUPPORTED where the syntax is recognised). */
 enum {
 	MGPU_MATCH_ALL = 0,       /* SPH_MATCH_ALL: every word; ranker SPH_RANK_PROXIMITY */

@@ -6,7 +6,7 @@
 // src/sphinx.cpp:4655-4711) for the default charset_table + CJK unigrams, and the legacy match modes' rewrite into extended syntax
 // (PrepareQueryEmulation, src/searchd.cpp:2141-2190).
 // Not restated: blended characters, multiform destinations, query token-filter plugins, zones, SENTENCE / PARAGRAPH, exact-form
-// '=' (index_exact_words), wildcards, @@relaxed.  Those return MGPU_E_UNSUPPORTED or parse as the plain text would.
+// '=' (index_exact_words), wildcards.  Those return MGPU_E_UNSUPPORTED or parse as the plain text would.
 #include "../../../include/mgpu.h"
 
 #include <math.h>
@@ -294,6 +294,13 @@ public:
 	PNode_t * Parse ( const char * sQuery )
 	{
 		m_sQuery = sQuery ? sQuery : "";
+		// the relaxed syntax option (:1752-1760): unknown fields are warnings, not errors
+		m_bStopOnInvalid = true;
+		if ( m_sQuery.compare ( 0, 9, "@@relaxed" )==0 && !IsAlphaRef ( m_sQuery.size()>9 ? m_sQuery[9] : 0 ) )
+		{
+			m_sQuery.erase ( 0, 9 );
+			m_bStopOnInvalid = false;
+		}
 		m_dStateSpec.clear();
 		m_dSpecPool.clear();
 		m_dSpecPool.emplace_back ( new LimitSpec_t );
@@ -341,6 +348,7 @@ private:
 	Token_t	m_tCur;
 	static const int MAX_TREE_DEPTH = 512;
 	int		m_iParenDepth = 0;
+	bool	m_bStopOnInvalid = true;
 
 	int Fail ( int iCode, const std::string & s )
 	{
@@ -426,8 +434,13 @@ private:
 				uMask |= 1u<<i;
 				return true;
 			}
-		Fail ( MGPU_E_BAD_QUERY, "no field '" + sName + "' found in schema" );
-		return false;
+		if ( m_bStopOnInvalid )
+		{
+			Fail ( MGPU_E_BAD_QUERY, "no field '" + sName + "' found in schema" );
+			return false;
+		}
+		m_sWarning = "no field '" + sName + "' found in schema";	// @@relaxed: the limit matches no field, its keywords are dropped below
+		return true;
 	}
 
 	/// XQParseHelper_c::ParseFields, :77-214
@@ -1367,8 +1380,29 @@ public:
 
 private:
 	/// XQParseHelper_c::FixupTree, :343-387; an empty tree comes back as one node without words or children
+	/// XQParseHelper_c::DeleteNodesWOFields, :217-255: children whose field limit matched no field of the schema (@@relaxed) go away
+	void DeleteNodesWOFields ( PNode_t * pNode )
+	{
+		if ( !pNode )
+			return;
+		for ( size_t i=0; i<pNode->m_dChildren.size(); )
+		{
+			if ( pNode->m_dChildren[i]->m_tSpec.m_uFieldMask==0 )
+			{
+				pNode->m_dChildren[i] = pNode->m_dChildren.back();	// RemoveFast
+				pNode->m_dChildren.pop_back();
+			} else
+			{
+				DeleteNodesWOFields ( pNode->m_dChildren[i] );
+				++i;
+			}
+		}
+	}
+
 	PNode_t * FixupTree ( PNode_t * pRoot )
 	{
+		if ( !m_bStopOnInvalid )
+			DeleteNodesWOFields ( pRoot );
 		pRoot = SweepNulls ( pRoot );
 		FixupDegenerates ( pRoot );
 		FixupNulls ( pRoot );

@@ -278,3 +278,18 @@ def test_explain_format():
                                                                "    AND(fields=(title), KEYWORD(world, querypos=2, excluded))))")
     assert " ".join(M.explain_query('"a b"~3 | ^c$ | @body[5] d', FIELDS).split()) == \
         "OR( PROXIMITY(distance=3, KEYWORD(a, querypos=1), KEYWORD(b, querypos=2)), AND(KEYWORD(c, querypos=4, field_start, field_end)), AND(fields=(body), max_field_pos=5, KEYWORD(d, querypos=5)))"
+
+
+def test_relaxed_mode():
+    """@@relaxed (src/sphinxquery.cpp:1752-1760, AddField :49-74, DeleteNodesWOFields :217-255): unknown fields warn instead of failing and
+    the keywords under them leave the tree"""
+    root, _, warning = M.parse_query("@@relaxed @nosuch hello @title world", FIELDS)
+    assert compact(root) == ["kw", "world", 2, 1] and "no field 'nosuch' found in schema" in warning
+    root, _, warning = M.parse_query("@@relaxed ((@title hello) | (@missed world)) @body other terms", FIELDS)
+    assert compact(root) == ["and", ["kw", "hello", 1, 1], ["kw", "other", 3, 2], ["kw", "terms", 4, 2]]
+    root, _, warning = M.parse_query("@@relaxed @(title,nosuch) hello", FIELDS)
+    assert compact(root) == ["kw", "hello", 1, 1]
+    with pytest.raises(M.MgpuError):
+        M.parse_query("@nosuch hello", FIELDS)
+    with pytest.raises(M.MgpuError):
+        M.parse_query("@@relaxedx @nosuch hello", FIELDS)      # not the option: a field limit on an unknown field `relaxedx`... and a syntax error before it
