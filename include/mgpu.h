@@ -46,7 +46,9 @@ enum {
 	MGPU_OP_PROXIMITY = 7,  /* SPH_QUERY_PROXIMITY, oparg = N of "..."~N */
 	MGPU_OP_QUORUM = 8,     /* SPH_QUERY_QUORUM, oparg = threshold (absolute); one real quorum node per query on the GPU path */
 	MGPU_OP_NEAR = 9,       /* SPH_QUERY_NEAR, oparg = distance; n-ary in the reference, two plain keywords on the GPU path */
-	MGPU_OP_NOTNEAR = 10    /* SPH_QUERY_NOTNEAR, oparg = distance; two children: must, not (plain keywords on the GPU path) */
+	MGPU_OP_NOTNEAR = 10,   /* SPH_QUERY_NOTNEAR, oparg = distance; two children: must, not (plain keywords on the GPU path) */
+	MGPU_OP_SENTENCE = 11,  /* SPH_QUERY_SENTENCE: mgpu_parse_query produces it; the evaluators answer MGPU_E_UNSUPPORTED (needs index_sp boundary hits) */
+	MGPU_OP_PARAGRAPH = 12  /* SPH_QUERY_PARAGRAPH: likewise */
 };
 
 /* ---- ESphRankMode (src/sphinx.h:2388-2404) ---- */
@@ -320,7 +322,7 @@ int				mgpu_index_check ( const char * path_prefix, int64_t * n_failures, char *
  * tree fix-ups (XQParseHelper_c::FixupTree, :343-387) and the legacy match modes' rewrite (PrepareQueryEmulation,
  * src/searchd.cpp:2141-2190).  Host only, no GPU needed.  The tokenizer is the reference's default charset_table (ASCII
  * alphanumerics + '_', Cyrillic, case folded) plus CJK unigrams when ngram_cjk is set; min_word_len and stop words consume query
- * positions as in the reference (overshort_step / stopword_step).  @@relaxed and the phrase star are understood.  Not parsed: zones, SENTENCE / PARAGRAPH, exact-form '=',
+ * positions as in the reference (overshort_step / stopword_step).  @@relaxed, the phrase star and SENTENCE / PARAGRAPH are understood.  Not parsed: zones, exact-form '=',
  * wildcards, blended characters (MGPU_E_UNSUPPORTED where the syntax is recognised). */
 enum {
 	MGPU_MATCH_ALL = 0,       /* SPH_MATCH_ALL: every word; ranker SPH_RANK_PROXIMITY */

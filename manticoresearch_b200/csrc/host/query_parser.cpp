@@ -5,7 +5,7 @@
 // which this image does not have), the query-mode tokenizer rules the lexer leans on (CSphTokenizerBase::CodepointArbitrationQ,
 // src/sphinx.cpp:4655-4711) for the default charset_table + CJK unigrams, and the legacy match modes' rewrite into extended syntax
 // (PrepareQueryEmulation, src/searchd.cpp:2141-2190).
-// Not restated: blended characters, multiform destinations, query token-filter plugins, zones, SENTENCE / PARAGRAPH, exact-form
+// SENTENCE / PARAGRAPH are parsed (the evaluators refuse them).  Not restated: blended characters, multiform destinations, query token-filter plugins, zones, exact-form
 // '=' (index_exact_words), wildcards.  Those return MGPU_E_UNSUPPORTED or parse as the plain text would.
 #include "../../../include/mgpu.h"
 
@@ -27,7 +27,7 @@ namespace mgpu
 enum Tok_e
 {
 	TOK_EOF = 0,
-	TOK_KEYWORD = 256, TOK_NEAR, TOK_NOTNEAR, TOK_INT, TOK_FLOAT, TOK_FIELDLIMIT, TOK_BEFORE, TOK_MAYBE,
+	TOK_KEYWORD = 256, TOK_NEAR, TOK_NOTNEAR, TOK_INT, TOK_FLOAT, TOK_FIELDLIMIT, TOK_BEFORE, TOK_MAYBE, TOK_SENTENCE, TOK_PARAGRAPH,
 	TOK_ERROR = -1
 };
 
@@ -668,9 +668,20 @@ private:
 				break;
 			}
 			const size_t nLeft = (size_t)( sBufferEnd-p );
-			if ( !bPhrase && ( ( !strcasecmp ( sToken, "sentence" ) && nLeft>=8 && !strncmp ( p, "SENTENCE", 8 ) )
-				|| ( !strcasecmp ( sToken, "paragraph" ) && nLeft>=9 && !strncmp ( p, "PARAGRAPH", 9 ) ) ) )
-				return Fail ( MGPU_E_UNSUPPORTED, "SENTENCE / PARAGRAPH need the indexing side's boundary markers; not supported" );
+			if ( !bPhrase && !strcasecmp ( sToken, "sentence" ) && nLeft>=8 && !strncmp ( p, "SENTENCE", 8 ) )
+			{
+				m_iPendingType = TOK_SENTENCE;
+				m_tPendingToken = Token_t();
+				m_iAtomPos -= 1;
+				break;
+			}
+			if ( !bPhrase && !strcasecmp ( sToken, "paragraph" ) && nLeft>=9 && !strncmp ( p, "PARAGRAPH", 9 ) )
+			{
+				m_iPendingType = TOK_PARAGRAPH;
+				m_tPendingToken = Token_t();
+				m_iAtomPos -= 1;
+				break;
+			}
 			if ( !bPhrase && !strcasecmp ( sToken, "maybe" ) && nLeft>=5 && !strncmp ( p, "MAYBE", 5 ) )
 			{
 				m_iPendingType = TOK_MAYBE;
@@ -1029,6 +1040,69 @@ private:
 		}
 	}
 
+	/// sentence: sp_item TOK_SENTENCE sp_item | sentence TOK_SENTENCE sp_item (and the same for paragraph); sp_item: keyword | '"' phrase '"'
+	PNode_t * UnitChain ( PNode_t * pLeft, bool & bOk )
+	{
+		const int iFirst = Peek();
+		if ( iFirst!=TOK_SENTENCE && iFirst!=TOK_PARAGRAPH )
+			return pLeft;
+		while ( m_iErrorCode==MGPU_OK && Peek()==iFirst )
+		{
+			Take();
+			PNode_t * pRight = nullptr;
+			const int t = Peek();
+			if ( t==TOK_KEYWORD )
+				pRight = Take().m_pNode;
+			else if ( t==TOK_INT || t==TOK_FLOAT )
+				pRight = KeywordOfNumber ( Take() );
+			else if ( t=='"' )
+			{
+				Take();
+				while ( m_iErrorCode==MGPU_OK )
+				{
+					const int k = Peek();
+					PNode_t * pTok = nullptr;
+					if ( k==TOK_KEYWORD )
+						pTok = Take().m_pNode;
+					else if ( k==TOK_INT || k==TOK_FLOAT )
+						pTok = KeywordOfNumber ( Take() );
+					else
+						break;
+					if ( pTok )
+					{
+						if ( !pRight )
+							pRight = pTok;
+						else
+							pRight->m_dWords.push_back ( pTok->m_dWords[0] );
+					}
+				}
+				if ( Peek()!='"' )
+				{
+					bOk = false;
+					SyntaxError();
+					return nullptr;
+				}
+				Take();
+				if ( pRight )
+					pRight->m_iOp = MGPU_OP_PHRASE;
+			} else
+			{
+				bOk = false;
+				SyntaxError();
+				return nullptr;
+			}
+			pLeft = AddOp ( iFirst==TOK_SENTENCE ? MGPU_OP_SENTENCE : MGPU_OP_PARAGRAPH, pLeft, pRight );
+		}
+		const int iNext = Peek();
+		if ( iNext==TOK_SENTENCE || iNext==TOK_PARAGRAPH )
+		{
+			bOk = false;	// the grammar does not mix the two in one chain
+			SyntaxError();
+			return nullptr;
+		}
+		return pLeft;
+	}
+
 	PNode_t * KeywordOfNumber ( const Token_t & t )
 	{
 		return AddKeyword ( t.m_iStrIndex>=0 ? m_dIntTokens[t.m_iStrIndex].c_str() : nullptr );
@@ -1039,9 +1113,9 @@ private:
 		bOk = true;
 		int t = Peek();
 		if ( t==TOK_KEYWORD )
-			return Take().m_pNode;
+			return UnitChain ( Take().m_pNode, bOk );
 		if ( t==TOK_INT || t==TOK_FLOAT )
-			return KeywordOfNumber ( Take() );
+			return UnitChain ( KeywordOfNumber ( Take() ), bOk );
 		if ( t=='(' )
 		{
 			Take();
@@ -1129,6 +1203,13 @@ private:
 					}
 				}
 				return pPhrase;
+			}
+			const int iUnit = Peek();
+			if ( iUnit==TOK_SENTENCE || iUnit==TOK_PARAGRAPH )
+			{
+				if ( pPhrase )
+					pPhrase->m_iOp = MGPU_OP_PHRASE;	// sp_item: '"' phrase '"' (no star shift there)
+				return UnitChain ( pPhrase, bOk );
 			}
 			if ( pPhrase )
 			{
@@ -1482,12 +1563,12 @@ static int CountWords ( const PNode_t * p )
 /// indent and line break ("  ", "\n"); a keyword is KEYWORD(word, querypos=N[, excluded][, field_start][, field_end][, boost=%f])
 static void Explain ( const PNode_t * p, const std::vector<std::string> & dFields, int iIndent, std::string & sOut )
 {
-	static const char * dNames[] = { "AND", "OR", "MAYBE", "NOT", "ANDNOT", "BEFORE", "PHRASE", "PROXIMITY", "QUORUM", "NEAR", "NOTNEAR" };
+	static const char * dNames[] = { "AND", "OR", "MAYBE", "NOT", "ANDNOT", "BEFORE", "PHRASE", "PROXIMITY", "QUORUM", "NEAR", "NOTNEAR", "SENTENCE", "PARAGRAPH" };
 	if ( iIndent )
 		sOut += "\n";
 	for ( int i=0; i<iIndent; ++i )
 		sOut += "  ";
-	sOut += ( p->m_iOp>=0 && p->m_iOp<=MGPU_OP_NOTNEAR ) ? dNames[p->m_iOp] : "OPERATOR";
+	sOut += ( p->m_iOp>=0 && p->m_iOp<=MGPU_OP_PARAGRAPH ) ? dNames[p->m_iOp] : "OPERATOR";
 	sOut += "(";
 	bool bComma = false;
 	auto fnItem = [&] ( const std::string & s ) { if ( bComma ) sOut += ", "; sOut += s; bComma = true; };

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MGPU_OK = 0
 MGPU_E_IO, MGPU_E_FORMAT, MGPU_E_UNSUPPORTED, MGPU_E_BAD_QUERY, MGPU_E_NO_DEVICE, MGPU_E_CUDA, MGPU_E_NOMEM = -1, -2, -3, -4, -5, -6, -7
 
-OP_AND, OP_OR, OP_MAYBE, OP_NOT, OP_ANDNOT, OP_BEFORE, OP_PHRASE, OP_PROXIMITY, OP_QUORUM, OP_NEAR, OP_NOTNEAR = range(11)
+OP_AND, OP_OR, OP_MAYBE, OP_NOT, OP_ANDNOT, OP_BEFORE, OP_PHRASE, OP_PROXIMITY, OP_QUORUM, OP_NEAR, OP_NOTNEAR, OP_SENTENCE, OP_PARAGRAPH = range(13)
 RANK_PROXIMITY_BM25, RANK_BM25, RANK_NONE, RANK_WORDCOUNT, RANK_PROXIMITY, RANK_MATCHANY, RANK_FIELDMASK, RANK_SPH04 = range(8)
 KEYPART_ROWID, KEYPART_WEIGHT, KEYPART_INT, KEYPART_FLOAT = range(4)
 FILTER_RANGE, FILTER_VALUES = range(2)

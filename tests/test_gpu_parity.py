@@ -437,6 +437,17 @@ def test_parsed_golden_queries_on_gpu(golden_cases, golden_indexes):
     assert ran >= 130
 
 
+def test_sentence_paragraph_are_refused_on_gpu(synth):
+    """the front-end parses SENTENCE / PARAGRAPH; the CUDA path (no index_sp boundary hits) must refuse them per query, never guess"""
+    gpu = synth["gpu"]
+    qs = [M.Query(M.parse_query("t0000001 SENTENCE t0000002", ["title", "body"])[0], max_matches=10),
+          M.Query(M.parse_query("t0000001 t0000002", ["title", "body"])[0], max_matches=10),
+          M.Query(M.parse_query('t0000001 PARAGRAPH "t0000002 t0000003"', ["title", "body"])[0], max_matches=10)]
+    r = gpu.search(qs)
+    assert r.get(0)["status"] == M.MGPU_E_UNSUPPORTED and r.get(2)["status"] == M.MGPU_E_UNSUPPORTED
+    assert r.get(1)["status"] == 0 and r.get(1)["total_found"] > 0
+
+
 def test_golden_vectors_on_gpu_dict_crc(golden_cases, golden_indexes_crc, tmp_path):
     """dict=crc indexes (word ids = sphFNV64 of the keyword, src/sphinx.cpp:18263-18339): mgpu_index_open reads the id-keyed
     dictionary, query keywords are hashed at bind time; same golden results. Plus the sharded handle over two crc shards"""

@@ -185,7 +185,30 @@ def test_parse_errors(text, needle):
     assert e.value.code == M.MGPU_E_BAD_QUERY and needle in str(e.value), str(e.value)
 
 
-@pytest.mark.parametrize("text", ["a SENTENCE b", "a PARAGRAPH b", "ZONE:h1 a", "ZONESPAN:(h1,h2) a"])
+def test_sentence_and_paragraph_parse_and_are_refused_by_the_evaluators(tmp_path):
+    """sentence / paragraph rules of the grammar (src/sphinxquery.y:125-138): left-associative chains over keywords and quoted phrases;
+    the front-end hands them on, the evaluators (no index_sp boundary hits on this path) answer MGPU_E_UNSUPPORTED"""
+    E = lambda t: " ".join(M.explain_query(t, FIELDS).split())
+    assert E("a SENTENCE b") == "SENTENCE( AND(KEYWORD(a, querypos=1)), AND(KEYWORD(b, querypos=2)))"
+    assert E('a SENTENCE "b c" SENTENCE d') == ("SENTENCE( AND(KEYWORD(a, querypos=1)), PHRASE(KEYWORD(b, querypos=2), KEYWORD(c, querypos=3)), "
+                                                 "AND(KEYWORD(d, querypos=4)))")
+    assert E("x | a PARAGRAPH b") == "OR( AND(KEYWORD(x, querypos=1)), PARAGRAPH( AND(KEYWORD(a, querypos=2)), AND(KEYWORD(b, querypos=3))))"
+    assert E("a sentence b") == "AND( AND(KEYWORD(a, querypos=1)), AND(KEYWORD(sentence, querypos=2)), AND(KEYWORD(b, querypos=3)))"
+    for bad in ("a SENTENCE", "a SENTENCE (b c)", "a SENTENCE b PARAGRAPH c", "SENTENCE a"):
+        with pytest.raises(M.MgpuError) as e:
+            M.parse_query(bad, FIELDS)
+        assert "syntax error" in str(e.value), bad
+    prefix = str(tmp_path / "sp")
+    M.build_index(prefix, FIELDS, [{"id": 1, "fields": [[("a", 1)], [("b", 1)]], "attrs": []}])
+    idx = helpers.OracleIndex(prefix)
+    try:
+        r = idx.search([M.Query(M.parse_query("a SENTENCE b", FIELDS)[0], max_matches=10)]).get(0)
+        assert r["status"] == M.MGPU_E_UNSUPPORTED
+    finally:
+        idx.close()
+
+
+@pytest.mark.parametrize("text", ["ZONE:h1 a", "ZONESPAN:(h1,h2) a"])
 def test_unsupported_syntax_is_refused_not_guessed(text):
     with pytest.raises(M.MgpuError) as e:
         M.parse_query(text, FIELDS)
