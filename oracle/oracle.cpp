@@ -1813,6 +1813,114 @@ struct NotNearNode_c : TwoferNode_c
 	void CollectHits ( std::vector<ExtHit_t> & dHits ) override	{ dHits.insert ( dHits.end(), m_dCurHits.begin(), m_dCurHits.end() ); }
 };
 
+/// ExtUnit_c, src/searchnode.cpp:4958-5330: SENTENCE / PARAGRAPH = an AND whose hits must not be separated by a hit of the boundary
+/// keyword ("\3sentence" / "\3paragraph", written by the indexing side under index_sp); only the hits of matching units go up
+struct UnitNode_c : TwoferNode_c
+{
+	std::unique_ptr<TermNode_c> m_pDot;
+	ExtDoc_t m_tDot { INVALID_ROWID, 0, 0.0f };
+	bool m_bHasDot = false, m_bEofDot = false;
+	std::vector<ExtHit_t> m_dCurHits, m_dDotHits;
+
+	bool PullDot()	{ if ( m_bHasDot ) return true; if ( m_bEofDot ) return false; m_bHasDot = m_pDot->Next ( m_tDot ); m_bEofDot = !m_bHasDot; return m_bHasDot; }
+
+	/// FilterHits, :5082-5163 (positions compared raw, as there)
+	bool FilterHits ()
+	{
+		const std::vector<ExtHit_t> & h1 = m_dTmpL, & h2 = m_dTmpR, & hd = m_dDotHits;
+		size_t i1 = 0, i2 = 0, id = 0;
+		DWORD uSentenceEnd = hd.empty() ? UINT_MAX : 0;		// no dots in the document: it degenerates into AND
+		bool bRegistered = false;
+		while ( true )
+		{
+			if ( uSentenceEnd )
+			{
+				const bool bValid1 = i1<h1.size() && h1[i1].m_uHitpos<uSentenceEnd;
+				const bool bValid2 = i2<h2.size() && h2[i2].m_uHitpos<uSentenceEnd;
+				if ( !bValid1 && !bValid2 )
+				{
+					uSentenceEnd = 0;
+					if ( i1<h1.size() && i2<h2.size() )
+						continue;	// perhaps more sentences in this document
+					break;
+				}
+				bRegistered = true;
+				if ( bValid1 && ( !bValid2 || IsHitLess ( h1[i1], h2[i2] ) ) )
+					m_dCurHits.push_back ( h1[i1++] );
+				else
+					m_dCurHits.push_back ( h2[i2++] );
+			} else
+			{
+				const DWORD uMin = std::min ( h1[i1].m_uHitpos, h2[i2].m_uHitpos );
+				const DWORD uMax = std::max ( h1[i1].m_uHitpos, h2[i2].m_uHitpos );
+				while ( id<hd.size() && hd[id].m_uHitpos<=uMin )
+					++id;
+				if ( id>=hd.size() )
+				{
+					uSentenceEnd = UINT_MAX;	// no more dots past the pair: everything up to the end of the document matches
+					continue;
+				}
+				if ( hd[id].m_uHitpos<uMax )
+				{
+					// "A dot B": both sides move past this dot
+					const DWORD uDot = hd[id].m_uHitpos;
+					while ( i1<h1.size() && h1[i1].m_uHitpos<=uDot ) ++i1;
+					if ( i1>=h1.size() ) break;
+					while ( i2<h2.size() && h2[i2].m_uHitpos<=uDot ) ++i2;
+					if ( i2>=h2.size() ) break;
+					continue;
+				}
+				while ( id<hd.size() && hd[id].m_uHitpos<=uMax )
+					++id;
+				uSentenceEnd = id>=hd.size() ? UINT_MAX : hd[id].m_uHitpos;
+			}
+		}
+		return bRegistered;
+	}
+
+	bool Next ( ExtDoc_t & tDoc ) override
+	{
+		while ( true )
+		{
+			if ( !m_bHasL )
+			{
+				if ( m_bHasR ) m_pLeft->HintRowID ( m_tR.m_tRowID );
+				if ( !PullL() ) return false;
+			}
+			if ( !m_bHasR )
+			{
+				m_pRight->HintRowID ( m_tL.m_tRowID );
+				if ( !PullR() ) return false;
+			}
+			if ( m_tL.m_tRowID!=m_tR.m_tRowID )
+			{
+				if ( m_tL.m_tRowID<m_tR.m_tRowID ) m_bHasL = false; else m_bHasR = false;
+				continue;
+			}
+			const RowID_t tRowID = m_tL.m_tRowID;
+			m_pDot->HintRowID ( tRowID );
+			while ( PullDot() && m_tDot.m_tRowID<tRowID )
+				m_bHasDot = false;
+			m_dTmpL.clear(); m_dTmpR.clear(); m_dDotHits.clear(); m_dCurHits.clear();
+			m_pLeft->CollectHits ( m_dTmpL );
+			m_pRight->CollectHits ( m_dTmpR );
+			if ( m_bHasDot && m_tDot.m_tRowID==tRowID )
+			{
+				m_pDot->CollectHits ( m_dDotHits );
+				m_bHasDot = false;
+			}
+			tDoc.m_tRowID = tRowID;
+			tDoc.m_uDocFields = m_tL.m_uDocFields | m_tR.m_uDocFields;
+			tDoc.m_fTFIDF = m_tL.m_fTFIDF + m_tR.m_fTFIDF;
+			m_bHasL = m_bHasR = false;
+			if ( !m_dTmpL.empty() && !m_dTmpR.empty() && FilterHits() )
+				return true;
+		}
+	}
+	void HintRowID ( RowID_t t ) override	{ m_pLeft->HintRowID ( t ); m_pRight->HintRowID ( t ); }
+	void CollectHits ( std::vector<ExtHit_t> & dHits ) override	{ dHits.insert ( dHits.end(), m_dCurHits.begin(), m_dCurHits.end() ); }
+};
+
 struct Setup_t
 {
 	const Index_t * m_pIndex;
@@ -2022,6 +2130,38 @@ static Node_c * CreateNode ( int iNode, Setup_t & tSetup )
 	}
 	if ( bAndTerms )
 		return CreateNode ( pChildren[0], tSetup );	// degenerate 1-child AND: generic create returns the child
+
+	if ( tNode.op==MGPU_OP_SENTENCE || tNode.op==MGPU_OP_PARAGRAPH )
+	{
+		// generic create, src/searchnode.cpp:1785-1806: pCur = new ExtUnit_c ( pCur, pNext, field mask, boundary keyword )
+		Node_c * pCur = nullptr;
+		for ( int i=0; i<nChildren; ++i )
+		{
+			Node_c * pNext = CreateNode ( pChildren[i], tSetup );
+			if ( tSetup.m_iError!=MGPU_OK )
+			{
+				delete pNext; delete pCur;
+				return nullptr;
+			}
+			if ( !pNext ) continue;
+			if ( !pCur ) { pCur = pNext; continue; }
+			auto * pUnit = new UnitNode_c;
+			pUnit->m_iAtomPos = pCur->m_iAtomPos;
+			pUnit->m_pLeft.reset ( pCur );
+			pUnit->m_pRight.reset ( pNext );
+			TermNode_c * pDot = new TermNode_c;
+			const char * sUnit = tNode.op==MGPU_OP_SENTENCE ? "\3sentence" : "\3paragraph";
+			pDot->m_tQword.Setup ( tSetup.m_pIndex, sUnit );
+			pDot->m_tQword.m_sWord = sUnit;
+			pDot->m_tQword.m_pIndex = tSetup.m_pIndex;
+			pDot->m_uQueriedFields = tNode.field_mask;
+			pDot->m_bNotWeighted = true;
+			pDot->m_bUseBM25 = tSetup.m_bUseBM25;
+			pUnit->m_pDot.reset ( pDot );
+			pCur = pUnit;
+		}
+		return pCur;
+	}
 
 	if ( tNode.op==MGPU_OP_NOTNEAR )
 	{

@@ -10,7 +10,8 @@ nodes with word lists, atom positions 1,2,3.. in query order, src/sphinxquery.cp
 because the reference's parser needs bison; tests/test_query_parser.py checks mgpu_parse_query (the restated parser) against them.
 
 Tree notation: ["kw", word, atompos, fieldmask?], ["and"|"or"|"andnot"|"maybe", child...],
-["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...], ["before", child...], ["notnear", N, must, not].
+["phrase", [[word,pos]...], fieldmask?], ["prox", N, [[word,pos]...]], ["quorum", N, [[word,pos]...]], ["near", N, child...], ["before", child...], ["notnear", N, must, not],
+["sentence"|"paragraph", child...].
 """
 import json
 import os
@@ -44,7 +45,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,041,052,054,055,059,094,114,115,116,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,041,052,054,055,059,094,114,115,116,133,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -484,6 +485,52 @@ out["cases"].append({
 # FSMmultinear_c keeps m_uFirstQpos across documents, so the hits of a document depend on the documents before it) and
 # NEAR / BEFORE / NOTNEAR whose children are phrases, OR groups or other operators.
 # ---------------------------------------------------------------------------------------------
+# test_133 "SENTENCE, PARAGRAPH, and ZONE operators", index `test` (html_strip=1, index_sp=1): the eight SENTENCE / PARAGRAPH queries.
+# ExtUnit_c (src/searchnode.cpp:4958-5330) over the boundary hits the indexing side writes (BuildZoneHits, src/sphinx.cpp:22232-22270:
+# a boundary takes a position of its own; a paragraph mark is also a sentence mark). The index holds 17 documents (301 / 302 are
+# commented out in test.xml); the zone documents only matter through N. Oracle only: the CUDA path refuses these operators.
+# ---------------------------------------------------------------------------------------------
+xml133 = open(os.path.join(REF, "test_133", "test.xml"), encoding="utf-8").read()
+xml133 = re.sub(r"<!--.*?-->", "", xml133, flags=re.S)
+docs_133 = []
+for m in re.finditer(r"<db_insert>\s*(?:<!\[CDATA\[)?\s*insert into test_table values \( (\d+), (\d+), (.*?)\);?\s*(?:\]\]>)?\s*</db_insert>", xml133, re.S):
+    doc_id, gid, expr = int(m.group(1)), int(m.group(2)), m.group(3).strip()
+    cdata = "<![CDATA[" in m.group(0)
+    if doc_id == 5:
+        text = "A ram zam zam. " * 171 + "Zam ram!"
+    elif doc_id == 400:
+        body = re.search(r"CONCAT\('Clock',CHAR\(4\),'(.*)'\)", expr, re.S).group(1)
+        text = "Clock\x04" + body.replace("\\'", "'")
+    else:
+        text = re.match(r"'(.*)'$", expr, re.S).group(1).replace("\\'", "'")
+        if not cdata:
+            text = text.replace("&lt;", "<").replace("&gt;", ">").replace("&amp;", "&")
+    docs_133.append((doc_id, gid, text))
+docs_133.sort()
+assert [d[0] for d in docs_133] == [1, 2, 3, 4, 5, 6, 100, 101, 200, 201, 202, 211, 300, 310, 311, 400, 500], [d[0] for d in docs_133]
+m133 = model("test_133")
+
+
+def UNIT(kind, *kids):
+    return [kind] + list(kids)
+
+
+q133 = {0: UNIT("sentence", K("one", 1), K("two", 2)),
+        1: ["and", UNIT("sentence", K("one", 1), K("two", 2)), K("three", 3)],
+        2: UNIT("sentence", K("one", 1), K("two", 2), K("three", 3)),
+        3: UNIT("sentence", PH(["one", "two"], 1), K("three", 3)),
+        4: UNIT("sentence", K("zam", 1), K("ram", 2)),
+        5: UNIT("paragraph", K("fox", 1), K("dog", 2)),
+        6: UNIT("sentence", K("sentence", 1), K("paragraph", 2)),
+        7: UNIT("paragraph", K("sentence", 1), K("paragraph", 2))}
+case = {"name": "test_133", "fields": ["title"], "attrs": ["gid"], "min_word_len": 1, "html_strip": 1, "index_sp": 1,
+        "docs": [{"id": d[0], "fields": [d[2]], "attrs": [d[1]]} for d in docs_133], "queries": []}
+for qi, tree in q133.items():
+    case["queries"].append({"text": m133[qi]["query"], "tree": tree, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m133[qi])})
+out["cases"].append(case)
+
+
+# ---------------------------------------------------------------------------------------------
 # test_041 "phrase shift": a separate star inside a phrase stands for any one keyword ("that * box"): XQParser_t::GetToken counts the
 # [ * ] between the phrase's tokens and PhraseShiftQpos moves the in-query positions behind them (src/sphinxquery.cpp:1318-1348, 1701-1738);
 # the first star right behind the quote does not match the [ * ] pattern, so `"* * * box always"` shifts by two. Indexes `phrase_shift`
@@ -518,6 +565,8 @@ def gpu_refuses(t):
     kind = t[0]
     if kind in ("kw", "phrase", "prox", "quorum"):
         return False
+    if kind in ("sentence", "paragraph"):
+        return True
     kids = t[2:] if kind in ("near", "notnear") else t[1:]
     if kind in ("near", "before", "notnear"):
         if any(k[0] != "kw" for k in kids) or (kind == "near" and len(kids) != 2):

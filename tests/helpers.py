@@ -117,9 +117,50 @@ def _is_word_char(ch):
     return ch.isascii() and (ch.isalnum() or ch == "_") or 0x410 <= o <= 0x44F
 
 
-def tokenize(text, min_word_len=1, stopwords=(), phrase_boundary="", phrase_boundary_step=0):
+MAGIC_SENTENCE, MAGIC_PARAGRAPH = "\x03sentence", "\x03paragraph"     # MAGIC_WORD_SENTENCE / MAGIC_WORD_PARAGRAPH, src/sphinx.cpp:163-164
+_PARA_TAGS = ("p", "div", "h1", "h2", "h3", "h4", "h5", "h6", "li", "ul", "ol", "tr", "td", "th", "table", "br", "hr", "blockquote", "pre", "form", "address", "dl", "dd", "dt")
+
+
+def html_strip(text):
+    """the part of the reference's HTML stripper the golden corpora need: block-level tags become a paragraph mark (\\x03 =
+    MAGIC_CODE_PARAGRAPH, src/sphinxint.h:50), every other tag a separator"""
+    import re
+
+    def sub(m):
+        name = re.match(r"</?\s*([A-Za-z0-9_]+)", m.group(0))
+        return "\x03" if name and name.group(1).lower() in _PARA_TAGS else " "
+    return re.sub(r"<[^<>]*>?", sub, text)
+
+
+def _sentence_boundary(text, i, cur):
+    """CSphTokenizerBase::CodepointArbitrationI (src/sphinx.cpp:4577-4652) for the character at i, with `cur` accumulated so far"""
+    ch = text[i]
+    if ch in "?!":
+        return True
+    if ch != ".":
+        return False
+    nxt = text[i + 1] if i + 1 < len(text) else "\0"
+    nxt2 = text[i + 2] if i + 2 < len(text) else "\0"
+    nxt3 = text[i + 3] if i + 3 < len(text) else "\0"
+    is_alpha = lambda c: c.isascii() and (c.isalnum() or c in "-_")
+    inword = is_alpha(nxt) or ord(nxt) >= 0x80 or nxt == ","
+    inphrase = nxt in " \t\r\n" and ("a" <= nxt2 <= "z" or (nxt2 == "(" and "a" <= nxt3 <= "z"))
+    cap = lambda c: "A" <= c <= "Z"
+    middle = False
+    if len(cur) == 1:
+        middle = cap(text[i - 1])
+    elif len(cur) == 2 and cap(text[i - 2]):
+        middle = not cap(text[i - 1]) or text[i - 2:i] in ("MR", "MS", "DR")
+    elif len(cur) == 3:
+        middle = cur[0] in "md" and cur[1] == "r" and cur[2] == "s"
+    return not (inword or inphrase or middle)
+
+
+def tokenize(text, min_word_len=1, stopwords=(), phrase_boundary="", phrase_boundary_step=0, index_sp=False):
     """-> [(keyword, pos)], pos 1-based; overshort tokens and stop words consume a position (overshort_step=1, stopword_step=1);
-    a phrase_boundary character followed by a separator (or the end) advances the position by phrase_boundary_step"""
+    a phrase_boundary character followed by a separator (or the end) advances the position by phrase_boundary_step;
+    index_sp: sentence / paragraph boundaries become hits of the magic keywords at a position of their own
+    (CSphSource_Document::BuildZoneHits, src/sphinx.cpp:22232-22270)"""
     out, pos, cur = [], 0, ""
 
     def flush():
@@ -137,6 +178,15 @@ def tokenize(text, min_word_len=1, stopwords=(), phrase_boundary="", phrase_boun
             out.append((ch, pos))
         elif _is_word_char(ch):
             cur += ch.lower()
+        elif index_sp and ch == "\x03":
+            flush()
+            pos += 1
+            out.append((MAGIC_SENTENCE, pos))
+            out.append((MAGIC_PARAGRAPH, pos))
+        elif index_sp and ch in ".?!" and _sentence_boundary(text, i, cur):
+            flush()
+            pos += 1
+            out.append((MAGIC_SENTENCE, pos))
         else:
             flush()
             if ch in phrase_boundary and (i + 1 == len(text) or not (_is_word_char(text[i + 1]) or _is_cjk(text[i + 1]))):
@@ -171,6 +221,8 @@ def tree_to_node(t):
         return M.Node(M.OP_NEAR, children=[tree_to_node(c) for c in t[2:]], oparg=t[1])
     if kind == "before":
         return M.Node(M.OP_BEFORE, children=[tree_to_node(c) for c in t[1:]])
+    if kind in ("sentence", "paragraph"):
+        return M.Node(M.OP_SENTENCE if kind == "sentence" else M.OP_PARAGRAPH, children=[tree_to_node(c) for c in t[1:]])
     if kind == "notnear":
         return M.Node(M.OP_NOTNEAR, children=[tree_to_node(t[2]), tree_to_node(t[3])], oparg=t[1])
     raise ValueError(kind)
@@ -185,11 +237,16 @@ def load_golden():
         return json.load(f)["cases"]
 
 
+def case_tokens(case, text):
+    """a golden case's document text -> [(keyword, pos)] with the case's indexing settings"""
+    return tokenize(html_strip(text) if case.get("html_strip") else text, case.get("min_word_len", 1), case.get("stopwords", ()),
+                    case.get("phrase_boundary", ""), case.get("phrase_boundary_step", 0), index_sp=bool(case.get("index_sp")))
+
+
 def build_golden_index(case, prefix, dict_crc=False):
     docs = []
     for d in case["docs"]:
-        docs.append({"id": d["id"], "fields": [tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ()), case.get("phrase_boundary", ""), case.get("phrase_boundary_step", 0))
-                                                for t in d["fields"]], "attrs": d.get("attrs", [])})
+        docs.append({"id": d["id"], "fields": [case_tokens(case, t) for t in d["fields"]], "attrs": d.get("attrs", [])})
     M.build_index(prefix, case["fields"], docs, attr_names=case.get("attrs", ()), dict_crc=dict_crc)
 
 

@@ -98,7 +98,7 @@ def test_dict_crc_golden(golden_cases, golden_indexes, golden_indexes_crc):
             words = set()
             for d in case["docs"]:
                 for t in d["fields"]:
-                    for w, _ in helpers.tokenize(t, case.get("min_word_len", 1), case.get("stopwords", ()), case.get("phrase_boundary", ""), case.get("phrase_boundary_step", 0)):
+                    for w, _ in helpers.case_tokens(case, t):
                         words.add(w)
             ids = sorted(_fnv1a64(w.encode()) for w in words)
             # walk the chunks from the first one: 64 entries, zero delta + last doclist length, next chunk
