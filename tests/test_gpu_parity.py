@@ -442,10 +442,15 @@ def test_sentence_paragraph_are_refused_on_gpu(synth):
     gpu = synth["gpu"]
     qs = [M.Query(M.parse_query("t0000001 SENTENCE t0000002", ["title", "body"])[0], max_matches=10),
           M.Query(M.parse_query("t0000001 t0000002", ["title", "body"])[0], max_matches=10),
-          M.Query(M.parse_query('t0000001 PARAGRAPH "t0000002 t0000003"', ["title", "body"])[0], max_matches=10)]
+          M.Query(M.parse_query('t0000001 PARAGRAPH "t0000002 t0000003"', ["title", "body"])[0], max_matches=10),
+          M.Query(M.parse_query("", ["title", "body"])[0], max_matches=10),                         # nothing to search for: the parser's empty node
+          M.Query(M.parse_query("@@relaxed @nosuch t0000001 t0000002", ["title", "body"])[0], max_matches=10)]
     r = gpu.search(qs)
     assert r.get(0)["status"] == M.MGPU_E_UNSUPPORTED and r.get(2)["status"] == M.MGPU_E_UNSUPPORTED
     assert r.get(1)["status"] == 0 and r.get(1)["total_found"] > 0
+    assert r.get(3)["status"] == 0 and r.get(3)["total_found"] == 0
+    c = synth["cpu"].search(qs)
+    helpers.assert_same_results(r.get(4), c.get(4), ctx="relaxed query")
 
 
 def test_golden_vectors_on_gpu_dict_crc(golden_cases, golden_indexes_crc, tmp_path):
