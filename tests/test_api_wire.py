@@ -389,3 +389,133 @@ def test_mutated_packets_never_crash(tmp_path):
         assert ok > 200 and err > 200
     finally:
         api.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own C client (api/libsphinxclient, protocol 1.30) over a loopback socket: oracle/_ref/refclient is compiled from the
+# reference's sources by oracle/Makefile (this container) and travels to the GPU box as a binary
+# ---------------------------------------------------------------------------------------------
+REFCLIENT = os.path.join(helpers.ROOT, "oracle", "_ref", "refclient")
+
+
+def run_refclient(api, scenario, n_connections=1):
+    """serves n_connections on 127.0.0.1 the way searchd does (handshake, one command packet per connection -> mgpu_api_handle) while
+    the reference client runs `scenario`; -> (its stdout lines, the request packets it sent)"""
+    import socket
+    import subprocess
+    import threading
+    srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(4)
+    srv.settimeout(20)
+    port = srv.getsockname()[1]
+    packets = []
+
+    def recv_all(conn, n):
+        buf = b""
+        while len(buf) < n:
+            chunk = conn.recv(n - len(buf))
+            if not chunk:
+                break
+            buf += chunk
+        return buf
+
+    def serve():
+        for _ in range(n_connections):
+            conn, _ = srv.accept()
+            conn.settimeout(20)
+            try:
+                conn.sendall(struct.pack(">L", 1))          # searchd's protocol version first
+                recv_all(conn, 4)                           # the client's
+                head = recv_all(conn, 8)
+                if len(head) < 8:
+                    continue
+                body = recv_all(conn, struct.unpack(">L", head[4:8])[0])
+                packets.append(head + body)
+                conn.sendall(api.handle(head + body))
+            finally:
+                conn.close()
+
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    out = subprocess.run([REFCLIENT, str(port), scenario], capture_output=True, text=True, timeout=60)
+    t.join(20)
+    srv.close()
+    assert out.returncode == 0, out.stderr
+    return out.stdout.splitlines(), packets
+
+
+@pytest.mark.skipif(not os.path.exists(REFCLIENT), reason="oracle/_ref/refclient is built where /root/reference is present")
+def test_reference_c_client_talks_to_the_responder(tmp_path):
+    """protocol 1.30 requests of the reference's C client parse (its packets differ from the Python client's 1.32 ones: no token-filter
+    fields), and the responder's error replies are what that client reports"""
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    api = M.ApiResponder(None, prefix)
+    try:
+        lines, packets = run_refclient(api, "extended_sort_filter_weights")
+        assert struct.unpack_from(">2H", packets[0], 0) == (0, 0x11E)
+        desc = api.describe_last()
+        for frag in ("MATCH('hello | world | there')", "group_id IN (1,3)", "ORDER BY extended(@weight desc, group_id asc)", "ranker=1", "field_weights=(title=5)"):
+            assert frag in desc, (frag, desc)
+        assert any("no index is attached" in l for l in lines)      # (sphinx_query() hands a failed single query back as the client's error)
+        lines, packets = run_refclient(api, "multi")
+        assert api.describe_last().count(";\n") == 4
+        assert [l for l in lines if l.startswith("query ")] == ["query 0", "query 1", "query 2", "query 3"]
+        assert any("group-by is not supported" in l for l in lines) and any("syntax error" in l for l in lines)
+        lines, packets = run_refclient(api, "keywords_stats")
+        assert struct.unpack_from(">2H", packets[0], 0) == (3, 0x100) and any("no index is attached" in l for l in lines)
+    finally:
+        api.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REFCLIENT), reason="oracle/_ref/refclient is built where /root/reference is present and travels with the snapshot")
+def test_reference_c_client_end_to_end_on_gpu(tmp_path):
+    """the UNMODIFIED reference client, compiled from its own sources, queries the B200 through the responder over a socket: what it
+    prints equals a direct mgpu_search_batch of the same queries"""
+    prefix = str(tmp_path / "api")
+    build_corpus(prefix)
+    docs = {d["id"]: d for d in corpus_docs()}
+    gpu = M.Index(prefix, device=0)
+    api = M.ApiResponder(gpu, prefix)
+    try:
+        gid, stamp = gpu.attr_index("group_id"), gpu.attr_index("stamp")
+        exp = expected_queries(gid, stamp)
+        checked = 0
+        for name in ("default", "any_attr_desc", "extended_sort_filter_weights", "phrase_range_idrange", "multi"):
+            lines, _ = run_refclient(api, name)
+            blocks, cur = [], None
+            for l in lines:
+                if l.startswith("status "):
+                    cur = {"status": int(l.split()[1]), "matches": [], "words": {}}
+                    blocks.append(cur)
+                elif l.startswith("match "):
+                    f = l.split()
+                    cur["matches"].append((int(f[1]), int(f[2]), int(f[3]), int(f[4])))
+                elif l.startswith("total "):
+                    f = l.split()
+                    cur["total"], cur["total_found"] = int(f[1]), int(f[3])
+                elif l.startswith("word "):
+                    f = l.split()
+                    cur["words"][f[1]] = (int(f[2]), int(f[3]))
+            assert len(blocks) == N_QUERIES[name], lines
+            for qi, b in enumerate(blocks):
+                if exp[name][qi] is None:
+                    assert b["status"] == SEARCHD_ERROR
+                    continue
+                query, offset, limit = exp[name][qi]
+                d = gpu.search([query]).get(0)
+                assert b["status"] == SEARCHD_OK, (name, qi, lines)
+                want = [(i, w, docs[i]["attrs"][0], docs[i]["attrs"][1]) for i, w in list(zip(d["docid"], d["weight"]))[offset:offset + limit]]
+                assert b["matches"] == want, (name, qi)
+                assert (b["total"], b["total_found"]) == (len(d["docid"]), d["total_found"])
+                checked += len(want) > 0
+        assert checked >= 5
+        lines, _ = run_refclient(api, "keywords_stats")
+        kws = [l.split() for l in lines if l.startswith("keyword ")]
+        assert [k[1] for k in kws] == ["hello", "world", "hello", "zzz"]
+        assert (int(kws[0][3]), int(kws[0][4])) == gpu.word_stats("hello") and (int(kws[3][3]), int(kws[3][4])) == (0, 0)
+    finally:
+        api.close()
+        gpu.close()
