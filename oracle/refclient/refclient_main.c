@@ -99,6 +99,29 @@ int main ( int argc, char ** argv )
 			printf ( "query %d\n", i );
 			print_result ( r+i );
 		}
+	} else if ( !strcmp ( scenario, "smoke" ) )
+	{
+		/* the calls of the client's own smoke test (api/libsphinxclient/test.c:58-75, 322-345, 396-416, 450-465) */
+		const char * names[2] = { "title", "content" };
+		const int weights[2] = { 100, 1 };
+		const sphinx_int64_t group = 1;
+		const char * queries[3] = { "is", "is test", "test number" };
+		int i, n = 0;
+		sphinx_keyword_info * k;
+		sphinx_set_match_mode ( c, SPH_MATCH_EXTENDED2 );
+		sphinx_set_sort_mode ( c, SPH_SORT_RELEVANCE, NULL );
+		k = sphinx_build_keywords ( c, "hello test one", "test1", SPH_TRUE, &n );
+		for ( i=0; k && i<n; i++ )
+			printf ( "keyword %s %s %d %d\n", k[i].tokenized, k[i].normalized, k[i].num_docs, k[i].num_hits );
+		for ( i=0; i<3; i++ )
+		{
+			sphinx_set_field_weights ( c, 2, names, weights );
+			print_result ( sphinx_query ( c, queries[i], "test1", NULL ) );
+		}
+		sphinx_add_filter ( c, "group_id", 1, &group, SPH_FALSE );
+		sphinx_set_field_weights ( c, 2, names, weights );
+		print_result ( sphinx_query ( c, "is", "test1", NULL ) );
+		sphinx_reset_filters ( c );
 	} else if ( !strcmp ( scenario, "keywords_stats" ) )
 	{
 		int i, n = 0;

@@ -45,7 +45,7 @@ def ql_expect(r):
 ALL = 0xFFFFFFFF
 TITLE, BODY = 1, 2
 
-out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,041,052,054,055,059,094,114,115,116,133,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335", "cases": []}
+out = {"source": "ravelry/manticoresearch test/test_015,016,017,019,030,037,041,052,054,055,059,094,114,115,116,133,138,322,349 model.bin + src/gtests/gtests_rtstuff.cpp:244-335 + api/libsphinxclient/smoke_ref.txt", "cases": []}
 
 # ---------------------------------------------------------------------------------------------
 # test_019 "extended queries", index `test` (min_word_len=2, ngram_len=1 for CJK)
@@ -527,6 +527,39 @@ case = {"name": "test_133", "fields": ["title"], "attrs": ["gid"], "min_word_len
         "docs": [{"id": d[0], "fields": [d[2]], "attrs": [d[1]]} for d in docs_133], "queries": []}
 for qi, tree in q133.items():
     case["queries"].append({"text": m133[qi]["query"], "tree": tree, "ranker": "proximity_bm25", "gpu_unsupported": True, "expect": api_expect(m133[qi])})
+out["cases"].append(case)
+
+
+# ---------------------------------------------------------------------------------------------
+# api/libsphinxclient: the C client's own smoke test. smoke_ref.txt is what its test program printed against a real searchd over the
+# index of smoke_data.csv (fields title / content, attributes idd / group_id; the multi-value attributes are left out): extended2,
+# SPH_RANK_PROXIMITY_BM25, field_weights=(title=100, content=1) (test.c:58-75). The three plain queries and the group_id filter.
+# tests/test_api_wire.py replays the same calls through the reference's client and the wire responder on the GPU.
+# ---------------------------------------------------------------------------------------------
+LSC = os.path.join(os.path.dirname(REF), "api", "libsphinxclient")
+smoke_docs = []
+for line in open(os.path.join(LSC, "smoke_data.csv"), encoding="utf-8"):
+    f = line.rstrip("\n").split("+")
+    if len(f) >= 5:
+        smoke_docs.append({"id": int(f[0]), "fields": [f[1], f[2]], "attrs": [int(f[3]), int(f[4])]})
+ref_txt = open(os.path.join(LSC, "smoke_ref.txt"), encoding="utf-8").read()
+blocks = re.findall(r"Query '([^']*)' retrieved (\d+) of (\d+) matches\.\nQuery stats:\n((?:\t.*\n)*)\nMatches:\n((?:\d+\. .*\n)*)", ref_txt)
+
+
+def smoke_expect(b):
+    words = {m.group(1): [int(m.group(3)), int(m.group(2))] for m in re.finditer(r"'([^']*)' found (\d+) times in (\d+) documents", b[3])}
+    matches = [[int(m.group(1)), int(m.group(2))] for m in re.finditer(r"doc_id=(\d+), weight=(\d+)", b[4])]
+    return {"matches": matches, "total_found": int(b[2]), "words": words}
+
+
+assert [b[0] for b in blocks[:3]] == ["is", "is test", "test number"]
+case = {"name": "libsphinxclient_smoke", "fields": ["title", "content"], "attrs": ["idd", "group_id"], "min_word_len": 1, "docs": smoke_docs, "queries": []}
+for b, tree in zip(blocks[:3], [K("is", 1), ["and", K("is", 1), K("test", 2)], ["and", K("test", 1), K("number", 2)]]):
+    case["queries"].append({"text": b[0], "tree": tree, "ranker": "proximity_bm25", "field_weights": [100, 1], "expect": smoke_expect(b)})
+after_filter = ref_txt[ref_txt.index("* test_filter"):]               # test_filter (test.c:396-416): group_id = 1 first
+flt = re.findall(r"Query '([^']*)' retrieved (\d+) of (\d+) matches\.\nQuery stats:\n((?:\t.*\n)*)\nMatches:\n((?:\d+\. .*\n)*)", after_filter)[0]
+case["queries"].append({"text": "is", "tree": K("is", 1), "ranker": "proximity_bm25", "field_weights": [100, 1], "filters": [["group_id", 1, 1]],
+                        "expect": smoke_expect(flt)})
 out["cases"].append(case)
 
 

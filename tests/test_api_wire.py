@@ -519,3 +519,64 @@ def test_reference_c_client_end_to_end_on_gpu(tmp_path):
     finally:
         api.close()
         gpu.close()
+
+
+def _smoke_case():
+    return next(c for c in helpers.load_golden() if c["name"] == "libsphinxclient_smoke")
+
+
+def _parse_refclient(lines):
+    blocks, cur, kws = [], None, []
+    for l in lines:
+        f = l.split()
+        if l.startswith("status "):
+            cur = {"status": int(f[1]), "matches": [], "words": {}}
+            blocks.append(cur)
+        elif l.startswith("match "):
+            cur["matches"].append([int(f[1]), int(f[2])])
+        elif l.startswith("total "):
+            cur["total"], cur["total_found"] = int(f[1]), int(f[3])
+        elif l.startswith("word "):
+            cur["words"][f[1]] = [int(f[2]), int(f[3])]
+        elif l.startswith("keyword "):
+            kws.append((f[1], f[2], int(f[3]), int(f[4])))
+    return blocks, kws
+
+
+@pytest.mark.skipif(not os.path.exists(REFCLIENT), reason="oracle/_ref/refclient is built where /root/reference is present")
+def test_c_client_smoke_requests_parse(tmp_path):
+    prefix = str(tmp_path / "smoke")
+    helpers.build_golden_index(_smoke_case(), prefix)
+    api = M.ApiResponder(None, prefix)
+    try:
+        lines, packets = run_refclient(api, "smoke", n_connections=5)
+        assert len(packets) == 5 and struct.unpack_from(">2H", packets[0], 0) == (3, 0x100)
+        assert "group_id IN (1)" in api.describe_last() and "field_weights=(title=100,content=1)" in api.describe_last()
+    finally:
+        api.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REFCLIENT), reason="oracle/_ref/refclient is built where /root/reference is present and travels with the snapshot")
+def test_c_client_smoke_test_against_its_reference_output(tmp_path):
+    """api/libsphinxclient/smoke_ref.txt: what the C client's own test program printed against a real searchd. The same client, the same
+    calls, the same data, against the responder on the GPU: keyword statistics of build_keywords, matches with weights, totals and
+    per-query keyword statistics of the three queries and of the filtered one"""
+    case = _smoke_case()
+    prefix = str(tmp_path / "smoke")
+    helpers.build_golden_index(case, prefix)
+    gpu = M.Index(prefix, device=0)
+    api = M.ApiResponder(gpu, prefix)
+    try:
+        lines, _ = run_refclient(api, "smoke", n_connections=5)
+        blocks, kws = _parse_refclient(lines)
+        assert kws == [("hello", "hello", 0, 0), ("test", "test", 3, 5), ("one", "one", 1, 2)]      # smoke_ref.txt, test_keywords
+        assert len(blocks) == 4
+        for b, q in zip(blocks, case["queries"]):
+            assert b["status"] == SEARCHD_OK
+            assert b["matches"] == q["expect"]["matches"], q["text"]
+            assert b["total"] == len(q["expect"]["matches"]) and b["total_found"] == q["expect"]["total_found"]
+            assert b["words"] == q["expect"]["words"], q["text"]
+    finally:
+        api.close()
+        gpu.close()
